@@ -1,0 +1,283 @@
+"""ctypes wrapper around oracle/liborc.so -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module.  PARITY UNPINNED (see hec_oracle.h).
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "liborc.so")
+
+u64p = C.POINTER(C.c_uint64)
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "hec_oracle.c")
+    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return _LIB
+
+
+def _p(a):
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(u64p)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB)
+        L.orc_ctx_new.restype = C.c_void_p
+        L.orc_ctx_new.argtypes = [C.c_int, u64p, C.c_int, u64p, C.c_int]
+        L.orc_ctx_free.argtypes = [C.c_void_p]
+        L.orc_get_const.restype = C.c_uint64
+        L.orc_get_const.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.orc_get_table.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, u64p]
+        L.orc_beta_full.argtypes = [C.c_void_p]
+        for f in ("orc_s_mred",):
+            getattr(L, f).restype = C.c_uint64
+            getattr(L, f).argtypes = [C.c_uint64] * 4
+        L.orc_s_mform.restype = C.c_uint64
+        L.orc_s_mform.argtypes = [C.c_uint64] * 4
+        L.orc_s_bred_add.restype = C.c_uint64
+        L.orc_s_bred_add.argtypes = [C.c_uint64] * 3
+        L.orc_ntt.argtypes = [C.c_void_p, C.c_int, C.c_int, u64p, u64p]
+        L.orc_intt.argtypes = [C.c_void_p, C.c_int, C.c_int, u64p, u64p]
+        L.orc_permute_index.argtypes = [C.c_int, C.c_uint64, C.POINTER(C.c_uint32)]
+        L.orc_galois_for_rotation.restype = C.c_uint64
+        L.orc_galois_for_rotation.argtypes = [C.c_int, C.c_int]
+        L.orc_mul_pt.argtypes = [C.c_void_p, C.c_int] + [u64p] * 5
+        L.orc_const_limbs.restype = C.c_double
+        L.orc_const_limbs.argtypes = [C.c_void_p, C.c_int, C.c_double, u64p]
+        L.orc_mul_const.argtypes = [C.c_void_p, C.c_int, u64p, u64p, u64p]
+        L.orc_div_round_last_ntt.argtypes = [C.c_void_p, C.c_int, u64p, u64p]
+        L.orc_rescale_count.restype = C.c_int
+        L.orc_rescale_count.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double)]
+        L.orc_add.argtypes = [C.c_void_p, C.c_int, u64p, u64p, u64p]
+        L.orc_sub.argtypes = [C.c_void_p, C.c_int, u64p, u64p, u64p]
+        L.orc_keyswitch.argtypes = [C.c_void_p, C.c_int, u64p, u64p, u64p, u64p]
+        L.orc_moddown.argtypes = [C.c_void_p, C.c_int, u64p, u64p, u64p]
+        L.orc_rotate_gal.argtypes = [C.c_void_p, C.c_int, u64p, u64p, C.c_uint64, u64p, u64p, u64p]
+        L.orc_conv_then_pack.restype = C.c_int
+        L.orc_conv_then_pack.argtypes = [C.c_void_p, u64p, u64p, C.c_double, u64p, C.c_double, C.c_int, C.c_int,
+                                         C.c_double, u64p, C.POINTER(u64p), u64p, u64p, u64p,
+                                         C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double),
+                                         C.POINTER(C.c_double)]
+        L.orc_gen_secret.argtypes = [C.c_void_p, C.c_uint64, C.c_int, u64p, u64p]
+        L.orc_gen_rotkey.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, u64p, u64p, u64p]
+        L.orc_encrypt.argtypes = [C.c_void_p, C.c_uint64, C.c_int, u64p, u64p, u64p, u64p]
+        L.orc_decrypt.argtypes = [C.c_void_p, C.c_int, u64p, u64p, u64p, u64p]
+        _lib = L
+    return _lib
+
+
+class Ct:
+    """Oracle ciphertext: c0,c1 [(level+1)][N] uint64, NTT domain, canonical."""
+
+    def __init__(self, c0, c1, scale):
+        self.c0, self.c1, self.scale = np.ascontiguousarray(c0), np.ascontiguousarray(c1), float(scale)
+
+    @property
+    def level(self):
+        return self.c0.shape[0] - 1
+
+
+class Oracle:
+    def __init__(self, logN, Q, P):
+        self.L = lib()
+        self.logN, self.N, self.Q, self.P = logN, 1 << logN, list(Q), list(P)
+        q = np.array(self.Q, dtype=np.uint64)
+        p = np.array(self.P if self.P else [0], dtype=np.uint64)
+        self.h = self.L.orc_ctx_new(logN, _p(q), len(self.Q), _p(p), len(self.P))
+        self.beta_full = self.L.orc_beta_full(self.h) if self.P else 0
+
+    def __del__(self):
+        try:
+            self.L.orc_ctx_free(self.h)
+        except Exception:
+            pass
+
+    # ---- tables ----
+    def const(self, ring, limb, which):
+        return int(self.L.orc_get_const(self.h, ring, limb, which))
+
+    def table(self, ring, limb, which):
+        out = np.empty(self.N, dtype=np.uint64)
+        self.L.orc_get_table(self.h, ring, limb, which, _p(out))
+        return out
+
+    # ---- ring ----
+    def ntt(self, a, limb, ring=0):
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        out = np.empty_like(a)
+        self.L.orc_ntt(self.h, ring, limb, _p(a), _p(out))
+        return out
+
+    def intt(self, a, limb, ring=0):
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        out = np.empty_like(a)
+        self.L.orc_intt(self.h, ring, limb, _p(a), _p(out))
+        return out
+
+    def permute_index(self, galEl):
+        idx = np.empty(self.N, dtype=np.uint32)
+        self.L.orc_permute_index(self.logN, galEl, idx.ctypes.data_as(C.POINTER(C.c_uint32)))
+        return idx
+
+    def galois_for_rotation(self, k):
+        return int(self.L.orc_galois_for_rotation(self.logN, k))
+
+    # ---- evaluator ----
+    def mul_pt(self, ct, pt, pt_scale=1.0):
+        lv = min(ct.level, pt.shape[0] - 1)
+        c0, c1, p = (np.ascontiguousarray(x[:lv + 1]) for x in (ct.c0, ct.c1, pt))
+        o0, o1 = np.empty_like(c0), np.empty_like(c1)
+        self.L.orc_mul_pt(self.h, lv, _p(c0), _p(c1), _p(p), _p(o0), _p(o1))
+        return Ct(o0, o1, ct.scale * pt_scale)
+
+    def const_limbs(self, level, constant):
+        k = np.zeros(level + 1, dtype=np.uint64)
+        up = self.L.orc_const_limbs(self.h, level, constant, _p(k))
+        return k, up
+
+    def mul_const(self, ct, constant):
+        k, up = self.const_limbs(ct.level, constant)
+        o0, o1 = np.empty_like(ct.c0), np.empty_like(ct.c1)
+        self.L.orc_mul_const(self.h, ct.level, _p(ct.c0), _p(k), _p(o0))
+        self.L.orc_mul_const(self.h, ct.level, _p(ct.c1), _p(k), _p(o1))
+        return Ct(o0, o1, ct.scale * up)
+
+    def div_round_last(self, a):
+        a = np.ascontiguousarray(a)
+        lv = a.shape[0] - 1
+        out = np.empty((lv, self.N), dtype=np.uint64)
+        self.L.orc_div_round_last_ntt(self.h, lv, _p(a), _p(out))
+        return out
+
+    def rescale(self, ct, min_scale):
+        """Rescale (L:ckks/evaluator.go:1291-1325); only 0 or 1 division supported here."""
+        if ct.level == 0:
+            raise ValueError("cannot Rescale: input Ciphertext already at level 0")
+        s = C.c_double()
+        nb = self.L.orc_rescale_count(self.h, ct.level, ct.scale, min_scale, C.byref(s))
+        c0, c1 = ct.c0, ct.c1
+        for _ in range(nb):
+            c0, c1 = self.div_round_last(c0), self.div_round_last(c1)
+        return Ct(c0, c1, s.value)
+
+    def set_scale(self, ct, scale):
+        """SetScale (L:ckks/evaluator.go:1194-1209)."""
+        t = self.mul_const(ct, scale / ct.scale)
+        t = self.rescale(t, scale)
+        t.scale = scale
+        return t
+
+    def add(self, a, b):
+        lv = min(a.level, b.level)
+        x0, x1, y0, y1 = (np.ascontiguousarray(v[:lv + 1]) for v in (a.c0, a.c1, b.c0, b.c1))
+        o0, o1 = np.empty_like(x0), np.empty_like(x1)
+        self.L.orc_add(self.h, lv, _p(x0), _p(y0), _p(o0))
+        self.L.orc_add(self.h, lv, _p(x1), _p(y1), _p(o1))
+        return Ct(o0, o1, a.scale)
+
+    def sub(self, a, b):
+        lv = min(a.level, b.level)
+        x0, x1, y0, y1 = (np.ascontiguousarray(v[:lv + 1]) for v in (a.c0, a.c1, b.c0, b.c1))
+        o0, o1 = np.empty_like(x0), np.empty_like(x1)
+        self.L.orc_sub(self.h, lv, _p(x0), _p(y0), _p(o0))
+        self.L.orc_sub(self.h, lv, _p(x1), _p(y1), _p(o1))
+        return Ct(o0, o1, a.scale)
+
+    def add_pt(self, ct, pt):
+        lv = min(ct.level, pt.shape[0] - 1)
+        x0, p = np.ascontiguousarray(ct.c0[:lv + 1]), np.ascontiguousarray(pt[:lv + 1])
+        o0 = np.empty_like(x0)
+        self.L.orc_add(self.h, lv, _p(x0), _p(p), _p(o0))
+        return Ct(o0, ct.c1[:lv + 1].copy(), ct.scale)
+
+    def keyswitch(self, c1, swk):
+        c1 = np.ascontiguousarray(c1)
+        lv = c1.shape[0] - 1
+        d0, d1 = np.empty_like(c1), np.empty_like(c1)
+        self.L.orc_keyswitch(self.h, lv, _p(c1), _p(swk), _p(d0), _p(d1))
+        return d0, d1
+
+    def moddown(self, accQ, accP):
+        accQ, accP = np.ascontiguousarray(accQ), np.ascontiguousarray(accP)
+        lv = accQ.shape[0] - 1
+        out = np.empty_like(accQ)
+        self.L.orc_moddown(self.h, lv, _p(accQ), _p(accP), _p(out))
+        return out
+
+    def rotate_gal(self, ct, galEl, swk):
+        o0, o1 = np.empty_like(ct.c0), np.empty_like(ct.c1)
+        self.L.orc_rotate_gal(self.h, ct.level, _p(ct.c0), _p(ct.c1), galEl, _p(swk), _p(o0), _p(o1))
+        return Ct(o0, o1, ct.scale)
+
+    def rotate(self, ct, k, swk):
+        return self.rotate_gal(ct, self.galois_for_rotation(k), swk)
+
+    # ---- compositions ----
+    def conv_then_pack(self, ct_in, pt_ker, pt_scale, norm, out_scale, pt_idx, swks, pt_bias=None,
+                       nthreads=1):
+        """evalConv_BN hot interval (eval.go:250-260).  swks: dict galEl-index j -> key array
+        for galEl 2^(j+1)+1.  Returns (Ct, t_mult, t_pack)."""
+        B = pt_ker.shape[0]
+        arr = (u64p * self.logN)()
+        keep = []
+        for j in range(self.logN):
+            if swks.get(j) is not None:
+                k = np.ascontiguousarray(swks[j])
+                keep.append(k)
+                arr[j] = _p(k)
+        o0, o1 = np.empty(self.N, dtype=np.uint64), np.empty(self.N, dtype=np.uint64)
+        s, tm, tp = C.c_double(), C.c_double(), C.c_double()
+        pt_ker = np.ascontiguousarray(pt_ker)
+        pt_idx = np.ascontiguousarray(pt_idx)
+        rc = self.L.orc_conv_then_pack(self.h, _p(ct_in.c0), _p(ct_in.c1), ct_in.scale, _p(pt_ker), pt_scale,
+                                       B, norm, out_scale, _p(pt_idx), arr,
+                                       _p(pt_bias) if pt_bias is not None else None, _p(o0), _p(o1),
+                                       C.byref(s), nthreads, C.byref(tm), C.byref(tp))
+        if rc != 0:
+            raise RuntimeError("LV or scale after conv then pack, inconsistent")
+        return Ct(o0[None, :], o1[None, :], s.value), tm.value, tp.value
+
+    def monomial_pts(self):
+        """pl_idx[i] = NTT(X^(2^i)) at level 0, scale 1 (conv.go:241-254)."""
+        out = np.empty((self.logN, self.N), dtype=np.uint64)
+        for i in range(self.logN):
+            m = np.zeros(self.N, dtype=np.uint64)
+            m[1 << i] = 1
+            out[i] = self.ntt(m, 0)
+        return out
+
+    # ---- semantic helpers ----
+    def gen_secret(self, seed, h=192):
+        sQ = np.empty((len(self.Q), self.N), dtype=np.uint64)
+        sP = np.empty((max(len(self.P), 1), self.N), dtype=np.uint64)
+        self.L.orc_gen_secret(self.h, seed, h, _p(sQ), _p(sP))
+        return sQ, sP
+
+    def gen_rotkey(self, seed, galEl, sQ, sP):
+        swk = np.empty((self.beta_full, 2, len(self.Q) + len(self.P), self.N), dtype=np.uint64)
+        self.L.orc_gen_rotkey(self.h, seed, galEl, _p(sQ), _p(sP), _p(swk))
+        return swk
+
+    def encrypt(self, seed, m, sQ):
+        m = np.ascontiguousarray(m)
+        lv = m.shape[0] - 1
+        c0, c1 = np.empty_like(m), np.empty_like(m)
+        self.L.orc_encrypt(self.h, seed, lv, _p(m), _p(sQ), _p(c0), _p(c1))
+        return c0, c1
+
+    def decrypt(self, ct, sQ):
+        m = np.empty_like(ct.c0)
+        self.L.orc_decrypt(self.h, ct.level, _p(ct.c0), _p(ct.c1), _p(sQ), _p(m))
+        return m

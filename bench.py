@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py -- homomorphic convolutions / second of the evalConv_BN hot interval
+(eval.go:250-260 = conv_then_pack + bias add) on B200.
+
+A "step" is one pass of the fused path over one batch of --cts independent level-1 input
+ciphertexts (synthetic uniform residues) with the workload of BASELINE.json
+configs[1]: conv k=3, B=16 output channels, N=2^16, level 1 -> 0, one special prime.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--cts M] [--batch B]
+    python bench.py --impl reference ...      # the CPU path (oracle port) on the host cores
+
+N>1 runs under torchrun, one rank per GPU; ranks process independent ciphertexts (weak
+scaling, no data-path collective); the only collectives are the barrier and the max of the
+device times.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+from optimal_conv_b200 import params as PR  # noqa: E402
+from optimal_conv_b200 import synth  # noqa: E402
+
+N = 1 << PR.LOGN
+LIMB = N * 8
+METRIC = "homomorphic convolutions/sec (N=2^16 CKKS, k=3, batch=16)"
+
+
+def conv_alg_limbs(B):
+    """algorithmic limbs of one conv: 10B - 1 + 4 log2 B"""
+    return 10 * B - 1 + 4 * (B.bit_length() - 1)
+
+
+def kernel_alg_limbs(name, M, B):
+    """Distinct limbs one run of fused kernel `name` must read + write (DESIGN.md "Kernels"),
+    summed over its launches in one run (Stage A: 1 launch; Stage B: one per pack level)."""
+    na, jobs = B, M * B * 2
+    if name == "A1":
+        return 2 * M + na + jobs            # ct limb q1 of both polys, pt limb q1 per channel, out
+    if name == "A2":
+        return 2 * jobs
+    if name == "A3":
+        return jobs + 2 * M + na + jobs     # w2, ct limb q0, pt limb q0, out
+    tot, n = 0, na
+    while n > 1:
+        nbt = M * (n // 2)                  # butterflies in this level's launch
+        tot += {"B1": 3 * nbt + 1,          # a1, b1, monomial -> w1
+                "B2": 2 * nbt,
+                "B3": 3 * nbt + 2,          # w2 (shared by both key polys), 2 key P limbs -> 2 outputs
+                "B4": 4 * nbt,
+                "B5": 8 * nbt + 3 + (1 if n == 2 else 0)}[name]  # w4 x2, a0,a1,b0,b1, mono, 2 key Q limbs (+bias) -> 2 out
+        n //= 2
+    return tot
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.rows.append(f)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.rows[0][1]),
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def run_reference(args):
+    """The reference's CPU implementation of the path: the oracle port (the reference is Go +
+    an un-vendored module and cannot be built here).  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle.orc import Ct, Oracle
+    B = args.batch
+    Q, P = PR.Q_SET6[:2], PR.P_PACK
+    w = synth.conv_workload(Q, P, PR.LOGN, B, seed=2024, n_ct=1)
+    o = Oracle(PR.LOGN, Q, P)
+    idx = o.monomial_pts()
+    ct = Ct(w["ct"][0][0], w["ct"][0][1], PR.SCALE)
+    ncpu = os.cpu_count() or 1
+
+    def one(nt):
+        t = time.perf_counter()
+        o.conv_then_pack(ct, w["pt_ker"], PR.SCALE, 1, PR.SCALE, idx, w["keys"], w["bias"], nthreads=nt)
+        return time.perf_counter() - t
+
+    # the reference is single-threaded; also try all host threads over channels / tree nodes
+    t1 = min(one(1) for _ in range(2))
+    tall = min(one(ncpu) for _ in range(2)) if ncpu > 1 else t1
+    nt = 1 if t1 <= tall else ncpu
+    for _ in range(args.warmup):
+        one(nt)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one(nt)
+    dt = time.perf_counter() - t0
+    val = args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "conv/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "conv3_B%d_N65536_lvl1to0_P1" % B, "cts_per_step": 1},
+        "cpu_baseline": {"value": val, "unit": "conv/s", "cores": nt, "kind": "port",
+                         "sample": "1 conv (B=%d) per step, %d steps; 1-thread %.3f s/conv, %d-thread %.3f s/conv"
+                                   % (B, args.steps, t1, ncpu, tall)},
+        "e2e": {"value": val, "unit": "conv/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--cts", type=int, default=16, help="independent input ciphertexts per step per GPU")
+    ap.add_argument("--batch", type=int, default=16, help="B: output channels packed per ciphertext")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=12, help="convs timed for cpu_baseline (0 = skip)")
+    ap.add_argument("--ring", type=int, default=8, help="distinct input batches rotated through (> L2)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from optimal_conv_b200 import hec
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B, M = args.batch, args.cts
+    Q, P = PR.Q_SET6[:2], PR.P_PACK
+
+    # ---- operands (seeded; every rank its own ciphertexts, shared weights/keys) ----
+    w = synth.conv_workload(Q, P, PR.LOGN, B, seed=2024, n_ct=1)
+    ctx = hec.Context(PR.LOGN, Q, P, device=local)
+    mono = np.zeros((PR.LOGN, N), dtype=np.uint64)
+    for i in range(PR.LOGN):  # pl_idx[i] = NTT(X^(2^i)) via the GPU NTT (conv.go:248-253)
+        m = np.zeros(N, dtype=np.uint64)
+        m[1 << i] = 1
+        mono[i] = ctx.ntt(m, 0)
+    ker = [ctx.upload_pt(w["pt_ker"][i], PR.SCALE) for i in range(B)]
+    idx = [ctx.upload_pt(mono[i:i + 1], 1.0) for i in range(PR.LOGN)]
+    bias = ctx.upload_pt(w["bias"][None, :], PR.SCALE)
+    for j, k in w["keys"].items():
+        ctx.upload_swk((1 << (j + 1)) + 1, k, 0)
+    # ring of distinct input batches, larger than L2 in total: ring * M * 2 MiB
+    ring = max(1, args.ring)
+    host_in0 = torch.empty((ring, M, 2, N), dtype=torch.int64).pin_memory()
+    host_in1 = torch.empty((ring, M, 2, N), dtype=torch.int64).pin_memory()
+    v0, v1 = host_in0.numpy().view(np.uint64), host_in1.numpy().view(np.uint64)
+    for r in range(ring):
+        for m in range(M):
+            s = 7 + 1000 * rank + 100 * r + m
+            v0[r, m] = synth.uniform_limbs(2 * s, Q, N)
+            v1[r, m] = synth.uniform_limbs(2 * s + 1, Q, N)
+    dev_in = [[ctx.upload_ct(v0[r, m], v1[r, m], PR.SCALE) for m in range(M)] for r in range(ring)]
+    host_out0 = torch.empty((M, N), dtype=torch.int64).pin_memory()
+    host_out1 = torch.empty((M, N), dtype=torch.int64).pin_memory()
+    plan = ctx.plan(ker, 1, PR.SCALE, PR.SCALE, idx, bias, M)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """sum of per-step device times (CUDA events on the library's stream); L2 flushed between steps"""
+        tot = 0.0
+        for s in range(steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            ctx.timer_start()
+            fn(s)
+            tot += ctx.timer_stop_ms()
+        return tot
+
+    def step_dev(s):
+        plan.run(dev_in[s % ring])
+
+    def step_e2e(s):
+        r = s % ring
+        plan.run_host(host_in0[r], host_in1[r], host_out0, host_out1)
+
+    # ---- kernel-resident throughput ----
+    timed(step_dev, args.warmup)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    l0 = ctx.launch_count()
+    ms_dev = timed(step_dev, args.steps)
+    launches = ctx.launch_count() - l0
+    barrier()
+    # ---- end to end through the C ABI with host buffers ----
+    timed(step_e2e, args.warmup)
+    barrier()
+    ms_e2e = timed(step_e2e, args.steps)
+    barrier()
+    sampler.stop_flag = True
+    # ---- per-kernel times (kernels launched one by one) for the roofline of the dominant kernel ----
+    prof = {}
+    for rep in range(3):
+        flush.zero_()
+        torch.cuda.synchronize()
+        for name, ms in plan.profile(dev_in[rep % ring]):
+            prof.setdefault(name, []).append(ms)
+    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = t.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    convs = world * M * args.steps
+    value = convs / (ms_dev / 1e3)
+    e2e = convs / (ms_e2e / 1e3)
+    levels = B.bit_length() - 1
+    # launches of each kernel per run and jobs per launch
+    per_kernel = {}
+    for name, times in prof.items():
+        reps = 3
+        n_launch = len(times) // reps
+        per_kernel[name] = {"ms_per_run": sum(times) / reps, "launches_per_run": n_launch}
+    dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_run"])
+    alg_bytes_run = kernel_alg_limbs(dom, M, B) * LIMB
+    dom_ms = per_kernel[dom]["ms_per_run"]
+    achieved = alg_bytes_run / (dom_ms / 1e3) / 1e9
+    n_l = per_kernel[dom]["launches_per_run"]
+    share = dom_ms / sum(v["ms_per_run"] for v in per_kernel.values())
+    conv_bytes = conv_alg_limbs(B) * LIMB
+    conv_gbs = conv_bytes * (M * args.steps) / (ms_dev / 1e3) / 1e9  # per GPU
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "conv/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "conv3_B%d_N65536_lvl1to0_P1" % B, "cts_per_step_per_gpu": M,
+                   "convs_per_step": world * M, "l2": "L2 flushed (256 MiB write) between steps + ring of %d input "
+                   "batches (%d MiB)" % (ring, ring * M * 4 * LIMB >> 20), "timing": "sum of per-step CUDA-event times, max over ranks"},
+        "e2e": {"value": e2e, "unit": "conv/s", "h2d_bytes_per_step": M * 4 * LIMB, "d2h_bytes_per_step": M * 2 * LIMB,
+                "ms_per_step": ms_e2e / args.steps,
+                "note": "hec_plan_run_host: pinned host ciphertexts in, level-0 ciphertexts out; kernel plaintexts/keys resident"},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+        "roofline": {"bound": "hbm", "kernel": "k_conv" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "alg_bytes_per_run": alg_bytes_run, "launches_per_run": n_l,
+                     "avg_launch_ms": dom_ms / max(1, n_l), "share_of_step": share},
+        "roofline_conv": {"alg_bytes_per_conv": conv_bytes, "achieved": conv_gbs, "peak": peak, "unit": "GB/s",
+                          "frac": conv_gbs / peak, "note": "whole conv, per GPU: (10B-1+4log2B) limbs x convs / time"},
+        "kernels_ms_per_run": {k: round(v["ms_per_run"], 4) for k, v in sorted(per_kernel.items())},
+    }
+    # ---- CPU baseline beside it: the oracle port, 1 thread (the reference is single-threaded) ----
+    if world == 1 and args.cpu_sample > 0:
+        from oracle.orc import Ct, Oracle
+        o = Oracle(PR.LOGN, Q, P)
+        oidx = o.monomial_pts()
+        ct = Ct(w["ct"][0][0], w["ct"][0][1], PR.SCALE)
+        o.conv_then_pack(ct, w["pt_ker"], PR.SCALE, 1, PR.SCALE, oidx, w["keys"], w["bias"])
+        t0 = time.perf_counter()
+        for _ in range(args.cpu_sample):
+            o.conv_then_pack(ct, w["pt_ker"], PR.SCALE, 1, PR.SCALE, oidx, w["keys"], w["bias"])
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": args.cpu_sample / dt, "unit": "conv/s", "cores": 1, "kind": "port",
+                                "sample": "%d convs of the same workload (B=%d), oracle port, 1 thread of %d host cores"
+                                          % (args.cpu_sample, B, os.cpu_count() or 1)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

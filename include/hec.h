@@ -1,0 +1,146 @@
+/*
+ * hec.h -- C ABI of libhec.so: a B200-native (sm_100a) CKKS evaluator for the
+ * homomorphic-convolution hot path of dwkim606/optimal_conv.
+ *
+ * This is the drop-in boundary.  The reference's Go code programs
+ * against the interface `ckks.Evaluator` held in `context.evaluator` /
+ * `context.pack_evaluator` (main.go:39-40); every entry point below names the
+ * reference call it replaces.  A cgo shim binds exactly these.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; polynomials are passed as arrays of per-limb
+ *    `const uint64_t*` (N contiguous words each, canonical residues in [0,q_i)),
+ *    exactly `ring.Poly.Coeffs[limb]` of the Lattigo fork.  NTT domain unless stated.
+ *  - the caller owns host buffers and may free/move them when a call returns
+ *    (uploads copy; no host pointer is retained -- the cgo pointer rule).
+ *  - ciphertexts / plaintexts / keys live on the device behind opaque handles.
+ *  - every function returns 0 or a negative HEC_E_* code; hec_last_error(ctx) gives
+ *    text.  The Go shim panics on non-zero, which reproduces the reference's
+ *    panic-on-inconsistency behaviour (conv.go:541-543, eval.go:252-257).
+ *  - a context is NOT re-entrant (like a Lattigo evaluator with shared pools); one
+ *    CUDA stream per context; calls are asynchronous on it; download / sync block.
+ *  - there is no CPU fallback: every op is a CUDA kernel; if no device is present
+ *    hec_ctx_create fails with HEC_E_CUDA.
+ */
+#ifndef HEC_H
+#define HEC_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HEC_OK 0
+#define HEC_E_INVAL (-1)       /* bad argument */
+#define HEC_E_CUDA (-2)        /* CUDA runtime error / no device */
+#define HEC_E_LEVEL (-3)       /* level or degree mismatch; Rescale at level 0 */
+#define HEC_E_NOKEY (-4)       /* rotation key missing (L:ckks/evaluator.go:1575-1597 panic) */
+#define HEC_E_SCALE (-5)       /* "LV or scale after conv then pack, inconsistent" (conv.go:541) */
+#define HEC_E_UNSUPPORTED (-6) /* shape outside what this build implements */
+#define HEC_E_NOMEM (-7)
+
+typedef struct hec_ctx hec_ctx;
+typedef struct hec_ct hec_ct;     /* ckks.Ciphertext (degree 1) on device */
+typedef struct hec_pt hec_pt;     /* ckks.Plaintext (NTT form) on device */
+typedef struct hec_plan hec_plan; /* a prepared evalConv_BN (kernels resident, CUDA graph) */
+
+const char *hec_version(void);
+
+/* ---- context: replaces ckks.NewEvaluator(params, evk) (main.go:430,435,441; conv.go:258).
+ * Q/P are params.Q() / params.P(); logN must be 16 in this build. */
+int hec_ctx_create(hec_ctx **ctx, int logN, const uint64_t *Q, int nQ, const uint64_t *P, int nP, int device);
+void hec_ctx_destroy(hec_ctx *ctx);
+const char *hec_last_error(const hec_ctx *ctx);
+int hec_sync(hec_ctx *ctx);
+/* device-side elapsed time helpers for benchmarks (CUDA events on the context stream) */
+int hec_timer_start(hec_ctx *ctx);
+int hec_timer_stop_ms(hec_ctx *ctx, float *ms); /* synchronises */
+/* number of kernels this context has launched so far (for bench.py's gpu_launches) */
+uint64_t hec_launch_count(const hec_ctx *ctx);
+
+/* ---- plaintexts: what Encoder.EncodeCoeffs+ToNTT / EncodeNTT produce (conv.go:513-514,
+ * eval.go:242-243).  limbs[0..level]. */
+int hec_pt_upload(hec_ctx *ctx, int level, const uint64_t *const *limbs, double scale, hec_pt **out);
+void hec_pt_free(hec_ctx *ctx, hec_pt *pt);
+
+/* ---- ciphertexts: rlwe.Ciphertext{Value [2]*ring.Poly} + Scale. */
+int hec_ct_upload(hec_ctx *ctx, int level, const uint64_t *const *c0, const uint64_t *const *c1,
+                  double scale, hec_ct **out);
+int hec_ct_download(hec_ctx *ctx, const hec_ct *ct, uint64_t *const *c0, uint64_t *const *c1);
+int hec_ct_copy_new(hec_ctx *ctx, const hec_ct *ct, hec_ct **out); /* ct.CopyNew() (conv.go:273) */
+int hec_ct_level(const hec_ct *ct);                                /* ct.Level() */
+double hec_ct_scale(const hec_ct *ct);                             /* ct.Scale */
+void hec_ct_set_scale(hec_ct *ct, double scale);                   /* ct.SetScalingFactor (conv.go:274) */
+void hec_ct_free(hec_ctx *ctx, hec_ct *ct);
+
+/* ---- rotation keys: rlwe.SwitchingKey{Value [][2]*ring.Poly} for Galois element galEl,
+ * as Lattigo stores them (NTT + Montgomery form over Q||P).
+ * limbs[(d*2 + k)*(nQ+nP) + t] = Value[d][k].Coeffs[t].  Only digits / Q-limbs needed up to
+ * max_level are read and kept (the level-0 slice of a pack key is 2 MiB of 812 MiB). */
+int hec_swk_upload(hec_ctx *ctx, uint64_t galEl, int max_level, const uint64_t *const *limbs);
+int hec_swk_drop(hec_ctx *ctx, uint64_t galEl);
+
+/* ---- evaluator ops (the subset of ckks.Evaluator the conv path calls) ------------------ */
+/* MulNew(ct, pt)  (conv.go:168,288,527) */
+int hec_mul_pt_new(hec_ctx *ctx, const hec_ct *ct, const hec_pt *pt, hec_ct **out);
+/* MultByConst(ct, c, ct) */
+int hec_mult_by_const(hec_ctx *ctx, hec_ct *ct, double c);
+/* Rescale(ct, minScale, ct)  -- error HEC_E_LEVEL at level 0 like the reference */
+int hec_rescale(hec_ctx *ctx, hec_ct *ct, double min_scale);
+/* SetScale(ct, scale)  (conv.go:528) */
+int hec_set_scale(hec_ctx *ctx, hec_ct *ct, double scale);
+/* Add(a,b,out) / AddNew / SubNew (conv.go:289-292).  out may alias a or b. */
+int hec_add(hec_ctx *ctx, const hec_ct *a, const hec_ct *b, hec_ct *out);
+int hec_add_new(hec_ctx *ctx, const hec_ct *a, const hec_ct *b, hec_ct **out);
+int hec_sub_new(hec_ctx *ctx, const hec_ct *a, const hec_ct *b, hec_ct **out);
+/* Add(ct, pt, ct)  (eval.go:258) */
+int hec_add_pt(hec_ctx *ctx, hec_ct *ct, const hec_pt *pt);
+/* RotateGal(ct, galEl, out)  (conv.go:291); out may alias ct */
+int hec_rotate_gal(hec_ctx *ctx, const hec_ct *ct, uint64_t galEl, hec_ct *out);
+/* RotateNew(ct, k)  (eval.go:123) */
+int hec_rotate_new(hec_ctx *ctx, const hec_ct *ct, int k, hec_ct **out);
+/* RotateHoisted(ct, rotations) (conv.go:133): outs[i] <- rotation by rots[i] */
+int hec_rotate_hoisted(hec_ctx *ctx, const hec_ct *ct, const int *rots, int n, hec_ct **outs);
+/* GaloisElementForColumnRotationBy(k) */
+uint64_t hec_galois_for_rotation(const hec_ctx *ctx, int k);
+
+/* ---- ring-level entry points (parity tests of the kernels themselves) ------------------ */
+/* ring: 0 = Q chain, 1 = P chain.  Host in / host out, one limb. ring.NTT / ring.InvNTT */
+int hec_ntt(hec_ctx *ctx, int ring, int limb, const uint64_t *in, uint64_t *out, int inverse);
+/* KeySwitcher.SwitchKeysInPlace on a host poly c1[0..level] with the key of galEl */
+int hec_keyswitch(hec_ctx *ctx, int level, const uint64_t *const *c1, uint64_t galEl,
+                  uint64_t *const *d0, uint64_t *const *d1);
+/* FastBasisExtender.ModDownSplitNTTPQ: accQ[0..level], accP[0..nP) -> out[0..level] */
+int hec_moddown(hec_ctx *ctx, int level, const uint64_t *const *accQ, const uint64_t *const *accP,
+                uint64_t *const *out);
+
+/* ---- the conv path --------------------------------------------------------------------- */
+#define HEC_CONV_FUSED 0   /* fused kernels (the measured path) */
+#define HEC_CONV_OPLEVEL 1 /* replay conv.go:522-546 / 266-300 op by op through the evaluator ops */
+/* conv_then_pack (conv.go:522-546) [+ Add(pl_bn_b) of evalConv_BN, eval.go:258, when pt_bias != NULL].
+ * pt_ker[max_ob] at level ECD_LV, pt_idx[logN] (gen_idxNlogs, conv.go:241-261), keys for galEl
+ * 2^j+1 must have been uploaded.  Returns HEC_E_SCALE on the reference's consistency panic. */
+int hec_conv_then_pack(hec_ctx *ctx, const hec_ct *ct_in, const hec_pt *const *pt_ker, int max_ob, int norm,
+                       double out_scale, const hec_pt *const *pt_idx, const hec_pt *pt_bias, int flags,
+                       hec_ct **out);
+
+/* A prepared evalConv_BN for `batch` independent input ciphertexts per run: kernel
+ * plaintexts, monomials, bias and keys stay resident; the kernel sequence is captured in a
+ * CUDA graph.  in_level must be 1 (ECD_LV) in this build. */
+int hec_plan_create(hec_ctx *ctx, const hec_pt *const *pt_ker, int max_ob, int norm, double in_scale,
+                    double out_scale, const hec_pt *const *pt_idx, const hec_pt *pt_bias, int batch,
+                    hec_plan **plan);
+/* device-resident run: outs[i] are allocated on first use if *outs[i] == NULL */
+int hec_plan_run(hec_plan *plan, const hec_ct *const *ins, hec_ct **outs);
+/* host-buffer run (the end-to-end call): for each ciphertext i, in_c0/in_c1 point to
+ * 2 limb pointers (level 1), out_c0/out_c1 to 1 limb pointer (level 0).  Copies run inside. */
+int hec_plan_run_host(hec_plan *plan, const uint64_t *const *in_c0, const uint64_t *const *in_c1,
+                      uint64_t *const *out_c0, uint64_t *const *out_c1);
+/* per-launch device times (ms) of one run with the kernels launched one by one, in launch
+ * order A1,A2,A3,(B1..B5) per pack level -- measurement aid for the roofline report */
+int hec_plan_profile(hec_plan *plan, const hec_ct *const *ins, float *ms, int cap, int *n);
+void hec_plan_destroy(hec_plan *plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,782 @@
+// hec.cu -- libhec.so: context, generic evaluator ops, C ABI (see include/hec.h).
+// The fused conv path lives in hec_conv.cu.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include "hec_host.cuh"
+
+using namespace hec;
+
+// =========================================================================================
+// ring constants
+// =========================================================================================
+namespace hec {
+
+// smallest primitive root >= 3 (search starts at 2 and increments before testing;
+// L:ring/utils.go:69-90)
+static u64 primitive_root(u64 q) {
+    std::vector<u64> fac;
+    u64 m = q - 1;
+    for (u64 p = 2; p * p <= m; p += (p == 2 ? 1 : 2))
+        if (m % p == 0) { fac.push_back(p); while (m % p == 0) m /= p; }
+    if (m > 1) fac.push_back(m);
+    for (u64 g = 3;; g++) {
+        bool ok = true;
+        for (u64 f : fac) if (powmod(g, (q - 1) / f, q) == 1) { ok = false; break; }
+        if (ok) return g;
+    }
+}
+
+void build_mod(HostMod &m, u64 q) {
+    const u64 N = HEC_N;
+    m.q = q;
+    u64 inv = 1;
+    for (int i = 0; i < 7; i++) inv *= 2 - q * inv; // Newton: q*inv = 1 mod 2^64
+    m.qinv = inv;
+    m.rmod = mform(1, q);
+    m.ninv = mform(invmod(N, q), q);
+    m.gen = primitive_root(q);
+    u64 psi = powmod(m.gen, (q - 1) / (2 * N), q);
+    u64 psi_i = invmod(psi, q);
+    m.psi.resize(N);
+    m.psi_inv.resize(N);
+    u64 a = 1, b = 1; // psi^j, psi^-j
+    for (u32 j = 0; j < N; j++) {
+        u32 r = bitrev16(j);
+        m.psi[r] = mform(a, q);
+        m.psi_inv[r] = mform(b, q);
+        a = mulmod(a, psi, q);
+        b = mulmod(b, psi_i, q);
+    }
+}
+
+static void build_modup(const hec_ctx *c, ModupTab &T, const std::vector<int> &src) {
+    int n = (int)src.size(), nt = c->nQ + c->nP;
+    T.n = n;
+    T.smod = src;
+    T.qib.resize(n);
+    T.qisp.assign(nt, std::vector<u64>(n));
+    T.qpjinv.assign(nt, std::vector<u64>(n + 1));
+    for (int i = 0; i < n; i++) {
+        u64 qi = c->q(src[i]), star = 1;
+        for (int k = 0; k < n; k++) if (k != i) star = mulmod(star, c->q(src[k]) % qi, qi);
+        T.qib[i] = mform(invmod(star, qi), qi);
+        for (int t = 0; t < nt; t++) {
+            u64 pt = c->q(t), s = 1;
+            for (int k = 0; k < n; k++) if (k != i) s = mulmod(s, c->q(src[k]) % pt, pt);
+            T.qisp[t][i] = mform(s, pt);
+        }
+    }
+    for (int t = 0; t < nt; t++) {
+        u64 pt = c->q(t), Qm = 1;
+        for (int k = 0; k < n; k++) Qm = mulmod(Qm, c->q(src[k]) % pt, pt);
+        u64 v = pt - Qm;
+        T.qpjinv[t][0] = 0;
+        for (int i = 1; i <= n; i++) { u64 s = T.qpjinv[t][i - 1] + v; T.qpjinv[t][i] = s >= pt ? s - pt : s; }
+    }
+}
+
+} // namespace hec
+
+u64 *hec_ctx::scratch(size_t limbs) {
+    u64 *p = arena + arena_top * HEC_N;
+    arena_top += limbs;
+    return p;
+}
+
+static int reserve(hec_ctx *c, size_t limbs) {
+    c->scratch_reset();
+    if (limbs <= c->arena_limbs) return HEC_OK;
+    HEC_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->arena) cudaFree(c->arena);
+    c->arena = nullptr;
+    c->arena_limbs = 0;
+    HEC_CUDA(c, cudaMalloc(&c->arena, limbs * HEC_N * sizeof(u64)));
+    c->arena_limbs = limbs;
+    return HEC_OK;
+}
+
+// =========================================================================================
+// launch helpers
+// =========================================================================================
+static int check_launch(hec_ctx *c, const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return c->fail(HEC_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    return HEC_OK;
+}
+
+// forward / inverse NTT of a list of limbs (in -> out; in == out allowed)
+int hec_launch_ntt(hec_ctx *c, std::vector<LimbJob> &jobs, bool inverse) {
+    for (size_t off = 0; off < jobs.size(); off += HEC_MAXJOBS) {
+        int n = (int)std::min<size_t>(HEC_MAXJOBS, jobs.size() - off);
+        NttJobs A, B;
+        for (int i = 0; i < n; i++) {
+            A.j[i] = jobs[off + i];
+            B.j[i] = jobs[off + i];
+            B.j[i].in = jobs[off + i].out; // second pass runs in place on out
+        }
+        dim3 grid(HEC_TILES_PER_LIMB, n);
+        if (!inverse) {
+            k_col_fwd<<<grid, HEC_THREADS, 0, c->stream>>>(A, c->dmods);
+            k_row_fwd<<<grid, HEC_THREADS, 0, c->stream>>>(B, c->dmods);
+        } else {
+            k_row_inv<<<grid, HEC_THREADS, 0, c->stream>>>(A, c->dmods);
+            k_col_inv<<<grid, HEC_THREADS, 0, c->stream>>>(B, c->dmods);
+        }
+        c->launches += 2;
+    }
+    return check_launch(c, "ntt");
+}
+
+template <int OP>
+static int launch_ew(hec_ctx *c, std::vector<EwJob> &jobs) {
+    for (size_t off = 0; off < jobs.size(); off += HEC_EWJOBS) {
+        int n = (int)std::min<size_t>(HEC_EWJOBS, jobs.size() - off);
+        EwJobs J;
+        for (int i = 0; i < n; i++) J.j[i] = jobs[off + i];
+        k_ew<OP><<<dim3(32, n), 256, 0, c->stream>>>(J, c->dmods);
+        c->launches += 1;
+    }
+    return check_launch(c, "ew");
+}
+static EwJob ewjob(const u64 *a, const u64 *b, u64 *out, int mod, u64 s0 = 0, u32 g = 0) {
+    EwJob j;
+    j.a = a; j.b = b; j.out = out; j.mod = mod; j.g = g; j.s0 = s0; j.s1 = 0;
+    return j;
+}
+
+static int launch_modup(hec_ctx *c, std::vector<ModupJob> &jobs) {
+    for (size_t off = 0; off < jobs.size(); off += HEC_MUJOBS) {
+        int n = (int)std::min<size_t>(HEC_MUJOBS, jobs.size() - off);
+        ModupJobs J;
+        for (int i = 0; i < n; i++) J.j[i] = jobs[off + i];
+        k_modup<<<dim3(32, n), 256, 0, c->stream>>>(J, c->dmods);
+        c->launches += 1;
+    }
+    return check_launch(c, "modup");
+}
+static ModupJob modup_job(const hec_ctx *c, const ModupTab &T, const u64 *src, size_t src_stride, int target, u64 *dst) {
+    ModupJob j;
+    memset(&j, 0, sizeof j);
+    j.n = T.n;
+    for (int s = 0; s < T.n; s++) {
+        j.src[s] = src + s * src_stride;
+        j.smod[s] = T.smod[s];
+        j.qib[s] = T.qib[s];
+        j.qisp[s] = T.qisp[target][s];
+    }
+    for (int v = 0; v <= T.n; v++) j.qpjinv[v] = T.qpjinv[target][v];
+    j.dst = dst;
+    j.tmod = target;
+    (void)c;
+    return j;
+}
+
+// =========================================================================================
+// context
+// =========================================================================================
+extern "C" const char *hec_version(void) { return "libhec 0.1 (sm_100a)"; }
+
+extern "C" int hec_ctx_create(hec_ctx **out, int logN, const uint64_t *Q, int nQ, const uint64_t *P, int nP, int device) {
+    if (!out || !Q || nQ < 1 || nP < 0 || (nP > 0 && !P)) return HEC_E_INVAL;
+    *out = nullptr;
+    if (logN != HEC_LOGN) return HEC_E_UNSUPPORTED;
+    if (nP > HEC_MAXA) return HEC_E_UNSUPPORTED;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device || device < 0) return HEC_E_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return HEC_E_CUDA;
+    hec_ctx *c = new hec_ctx();
+    c->device = device; c->nQ = nQ; c->nP = nP;
+    int nm = nQ + nP;
+    c->hm.resize(nm);
+    for (int i = 0; i < nm; i++) {
+        u64 q = i < nQ ? Q[i] : P[i - nQ];
+        if ((q & 1) == 0 || q >= (1ull << 61) || (q - 1) % (2ull * HEC_N) != 0) { delete c; return HEC_E_INVAL; }
+        build_mod(c->hm[i], q);
+    }
+    auto bail = [&](int code) { hec_ctx_destroy(c); return code; };
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(HEC_E_CUDA);
+    cudaEventCreate(&c->ev0);
+    cudaEventCreate(&c->ev1);
+    size_t tw = (size_t)nm * 2 * HEC_N;
+    if (cudaMalloc(&c->dtables, tw * sizeof(u64)) != cudaSuccess) return bail(HEC_E_NOMEM);
+    if (cudaMalloc(&c->dmods, nm * sizeof(ModC)) != cudaSuccess) return bail(HEC_E_NOMEM);
+    std::vector<ModC> mc(nm);
+    for (int i = 0; i < nm; i++) {
+        u64 *psi = c->dtables + (size_t)i * 2 * HEC_N, *psi_inv = psi + HEC_N;
+        cudaMemcpy(psi, c->hm[i].psi.data(), HEC_N * sizeof(u64), cudaMemcpyHostToDevice);
+        cudaMemcpy(psi_inv, c->hm[i].psi_inv.data(), HEC_N * sizeof(u64), cudaMemcpyHostToDevice);
+        mc[i].q = c->hm[i].q; mc[i].qinv = c->hm[i].qinv; mc[i].q2 = 2 * c->hm[i].q;
+        mc[i].ninv = c->hm[i].ninv; mc[i].rmod = c->hm[i].rmod;
+        mc[i].psi = psi; mc[i].psi_inv = psi_inv;
+    }
+    if (cudaMemcpy(c->dmods, mc.data(), nm * sizeof(ModC), cudaMemcpyHostToDevice) != cudaSuccess) return bail(HEC_E_CUDA);
+    // RescaleParams (L:ring/ring.go:63-117)
+    c->resc.resize(nQ);
+    for (int L = 1; L < nQ; L++) {
+        c->resc[L].resize(L);
+        for (int i = 0; i < L; i++) {
+            u64 qi = Q[i];
+            c->resc[L][i] = mform(qi - invmod(Q[L] % qi, qi), qi);
+        }
+    }
+    if (nP > 0) {
+        c->alpha = nP;
+        c->beta_full = (nQ + nP - 1) / nP;
+        c->negpinv.resize(nQ);
+        for (int i = 0; i < nQ; i++) {
+            u64 qi = Q[i], Pm = 1;
+            for (int j = 0; j < nP; j++) Pm = mulmod(Pm, P[j] % qi, qi);
+            c->negpinv[i] = qi - mform(invmod(Pm, qi), qi); // [A] test_run 0x4e5049: params := qi - modDownParams[i]
+        }
+        std::vector<int> src;
+        for (int j = 0; j < nP; j++) src.push_back(c->modP(j));
+        build_modup(c, c->pq, src);
+        // Decomposer tables (L:ring/ring_basis_extension.go:482-538)
+        c->xalpha.assign(c->beta_full, nP);
+        if (nQ % nP) c->xalpha[c->beta_full - 1] = nQ % nP;
+        c->dec.resize(c->beta_full);
+        for (int d = 0; d < c->beta_full; d++) {
+            c->dec[d].resize(nP + 1);
+            for (int nd = 2; nd <= c->xalpha[d]; nd++) {
+                src.clear();
+                for (int k = 0; k < nd; k++) src.push_back(d * nP + k);
+                build_modup(c, c->dec[d][nd], src);
+            }
+        }
+    }
+    *out = c;
+    return HEC_OK;
+}
+
+extern "C" void hec_ctx_destroy(hec_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (auto &kv : c->keys) cudaFree(kv.second.buf);
+    if (c->arena) cudaFree(c->arena);
+    if (c->dtables) cudaFree(c->dtables);
+    if (c->dmods) cudaFree(c->dmods);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+extern "C" const char *hec_last_error(const hec_ctx *c) { return c ? c->err.c_str() : "null context"; }
+extern "C" int hec_sync(hec_ctx *c) {
+    if (!c) return HEC_E_INVAL;
+    cudaSetDevice(c->device);
+    HEC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return HEC_OK;
+}
+extern "C" int hec_timer_start(hec_ctx *c) {
+    cudaSetDevice(c->device);
+    HEC_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    return HEC_OK;
+}
+extern "C" int hec_timer_stop_ms(hec_ctx *c, float *ms) {
+    cudaSetDevice(c->device);
+    HEC_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    HEC_CUDA(c, cudaEventSynchronize(c->ev1));
+    HEC_CUDA(c, cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return HEC_OK;
+}
+extern "C" uint64_t hec_launch_count(const hec_ctx *c) { return c ? c->launches : 0; }
+
+// =========================================================================================
+// handles
+// =========================================================================================
+int hec_ct_alloc(hec_ctx *c, int level, double scale, hec_ct **out) {
+    hec_ct *ct = new hec_ct();
+    ct->alloc = level + 1; ct->level = level; ct->scale = scale;
+    if (cudaMalloc(&ct->buf, (size_t)2 * ct->alloc * HEC_N * sizeof(u64)) != cudaSuccess) {
+        delete ct;
+        return c->fail(HEC_E_NOMEM, "cudaMalloc ciphertext");
+    }
+    *out = ct;
+    return HEC_OK;
+}
+
+extern "C" int hec_pt_upload(hec_ctx *c, int level, const uint64_t *const *limbs, double scale, hec_pt **out) {
+    if (!c || !limbs || !out || level < 0 || level >= c->nQ) return c ? c->fail(HEC_E_INVAL, "pt_upload args") : HEC_E_INVAL;
+    cudaSetDevice(c->device);
+    hec_pt *pt = new hec_pt();
+    pt->level = level; pt->scale = scale;
+    if (cudaMalloc(&pt->buf, (size_t)(level + 1) * HEC_N * sizeof(u64)) != cudaSuccess) { delete pt; return c->fail(HEC_E_NOMEM, "cudaMalloc plaintext"); }
+    std::vector<EwJob> jobs;
+    for (int i = 0; i <= level; i++) {
+        u64 *d = pt->buf + (size_t)i * HEC_N;
+        HEC_CUDA(c, cudaMemcpyAsync(d, limbs[i], HEC_N * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+        u64 q = c->q(i);
+        jobs.push_back(ewjob(d, nullptr, d, i, mform(c->hm[i].rmod, q))); // MFormLvl: * R^2 * R^-1
+    }
+    int rc = launch_ew<EW_TOMONT>(c, jobs);
+    if (rc) return rc;
+    HEC_CUDA(c, cudaStreamSynchronize(c->stream));
+    *out = pt;
+    return HEC_OK;
+}
+extern "C" void hec_pt_free(hec_ctx *c, hec_pt *pt) {
+    if (!pt) return;
+    if (c) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
+    cudaFree(pt->buf);
+    delete pt;
+}
+
+extern "C" int hec_ct_upload(hec_ctx *c, int level, const uint64_t *const *c0, const uint64_t *const *c1, double scale, hec_ct **out) {
+    if (!c || !c0 || !c1 || !out || level < 0 || level >= c->nQ) return c ? c->fail(HEC_E_INVAL, "ct_upload args") : HEC_E_INVAL;
+    cudaSetDevice(c->device);
+    hec_ct *ct = nullptr;
+    int rc = hec_ct_alloc(c, level, scale, &ct);
+    if (rc) return rc;
+    for (int i = 0; i <= level; i++) {
+        HEC_CUDA(c, cudaMemcpyAsync(ct->limb(0, i), c0[i], HEC_N * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+        HEC_CUDA(c, cudaMemcpyAsync(ct->limb(1, i), c1[i], HEC_N * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+    }
+    HEC_CUDA(c, cudaStreamSynchronize(c->stream));
+    *out = ct;
+    return HEC_OK;
+}
+extern "C" int hec_ct_download(hec_ctx *c, const hec_ct *ct, uint64_t *const *c0, uint64_t *const *c1) {
+    if (!c || !ct || !c0 || !c1) return c ? c->fail(HEC_E_INVAL, "ct_download args") : HEC_E_INVAL;
+    cudaSetDevice(c->device);
+    for (int i = 0; i <= ct->level; i++) {
+        HEC_CUDA(c, cudaMemcpyAsync(c0[i], ct->limb(0, i), HEC_N * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+        HEC_CUDA(c, cudaMemcpyAsync(c1[i], ct->limb(1, i), HEC_N * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    }
+    HEC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return HEC_OK;
+}
+extern "C" int hec_ct_copy_new(hec_ctx *c, const hec_ct *ct, hec_ct **out) {
+    if (!c || !ct || !out) return HEC_E_INVAL;
+    cudaSetDevice(c->device);
+    hec_ct *n = nullptr;
+    int rc = hec_ct_alloc(c, ct->level, ct->scale, &n);
+    if (rc) return rc;
+    for (int p = 0; p < 2; p++)
+        HEC_CUDA(c, cudaMemcpyAsync(n->limb(p, 0), ct->limb(p, 0), (size_t)(ct->level + 1) * HEC_N * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
+    *out = n;
+    return HEC_OK;
+}
+extern "C" int hec_ct_level(const hec_ct *ct) { return ct ? ct->level : -1; }
+extern "C" double hec_ct_scale(const hec_ct *ct) { return ct ? ct->scale : 0.0; }
+extern "C" void hec_ct_set_scale(hec_ct *ct, double s) { if (ct) ct->scale = s; }
+extern "C" void hec_ct_free(hec_ctx *c, hec_ct *ct) {
+    if (!ct) return;
+    if (c) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
+    if (ct->owned) cudaFree(ct->buf);
+    delete ct;
+}
+
+extern "C" int hec_swk_upload(hec_ctx *c, uint64_t galEl, int max_level, const uint64_t *const *limbs) {
+    if (!c || !limbs || c->nP == 0 || max_level < 0 || max_level >= c->nQ) return c ? c->fail(HEC_E_INVAL, "swk_upload args") : HEC_E_INVAL;
+    cudaSetDevice(c->device);
+    hec_swk_drop(c, galEl);
+    SwKey k;
+    k.Lk = max_level + 1;
+    k.ndig = (k.Lk + c->alpha - 1) / c->alpha;
+    int kl = k.Lk + c->nP, full = c->nQ + c->nP;
+    if (cudaMalloc(&k.buf, (size_t)k.ndig * 2 * kl * HEC_N * sizeof(u64)) != cudaSuccess) return c->fail(HEC_E_NOMEM, "cudaMalloc key");
+    for (int d = 0; d < k.ndig; d++)
+        for (int p = 0; p < 2; p++)
+            for (int t = 0; t < kl; t++) {
+                int srct = t < k.Lk ? t : c->nQ + (t - k.Lk);
+                const u64 *src = (const u64 *)limbs[(size_t)(d * 2 + p) * full + srct];
+                u64 *dst = k.buf + ((size_t)(d * 2 + p) * kl + t) * HEC_N;
+                HEC_CUDA(c, cudaMemcpyAsync(dst, src, HEC_N * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+            }
+    HEC_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->keys[galEl] = k;
+    return HEC_OK;
+}
+extern "C" int hec_swk_drop(hec_ctx *c, uint64_t galEl) {
+    if (!c) return HEC_E_INVAL;
+    auto it = c->keys.find(galEl);
+    if (it == c->keys.end()) return HEC_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(it->second.buf);
+    c->keys.erase(it);
+    return HEC_OK;
+}
+
+// =========================================================================================
+// generic evaluator ops
+// =========================================================================================
+extern "C" int hec_mul_pt_new(hec_ctx *c, const hec_ct *ct, const hec_pt *pt, hec_ct **out) {
+    if (!c || !ct || !pt || !out) return HEC_E_INVAL;
+    cudaSetDevice(c->device);
+    int level = std::min(ct->level, pt->level);
+    hec_ct *o = nullptr;
+    int rc = hec_ct_alloc(c, level, ct->scale * pt->scale, &o);
+    if (rc) return rc;
+    std::vector<EwJob> jobs;
+    for (int p = 0; p < 2; p++)
+        for (int i = 0; i <= level; i++) jobs.push_back(ewjob(ct->limb(p, i), pt->buf + (size_t)i * HEC_N, o->limb(p, i), i));
+    rc = launch_ew<EW_MULMONT>(c, jobs);
+    if (rc) { hec_ct_free(c, o); return rc; }
+    *out = o;
+    return HEC_OK;
+}
+
+// scaleUpExact (L:ckks/utils.go:31-57): floor(|c*n| + 0.5) mod q with sign; prec-53
+// big.Float arithmetic == IEEE double
+static u64 scale_up_exact(double value, double n, u64 q) {
+    bool neg = value < 0;
+    volatile double x = neg ? -n * value : n * value;
+    volatile double y = x + 0.5;
+    double fl = floor(y);
+    u64 res;
+    if (fl < 18446744073709551616.0) res = (u64)fl % q;
+    else {
+        int e;
+        double m = frexp(fl, &e);
+        u64 mant = (u64)ldexp(m, 53);
+        res = mant % q;
+        for (int i = 0; i < e - 53; i++) res = (u64)(((u128)res * 2) % q);
+    }
+    return neg ? (res ? q - res : 0) : res;
+}
+// getConstAndScale, float64 case (L:ckks/evaluator.go:508-561)
+double hec_const_limbs(const hec_ctx *c, int level, double constant, std::vector<u64> &k) {
+    double up = 1.0;
+    if (constant != 0) {
+        double vi = (double)(int64_t)constant;
+        if (constant - vi != 0) up = (double)c->q(level);
+    }
+    k.resize(level + 1);
+    for (int i = 0; i <= level; i++) k[i] = constant != 0 ? scale_up_exact(constant, up, c->q(i)) : 0;
+    return up;
+}
+
+extern "C" int hec_mult_by_const(hec_ctx *c, hec_ct *ct, double constant) {
+    if (!c || !ct) return HEC_E_INVAL;
+    cudaSetDevice(c->device);
+    std::vector<u64> k;
+    double up = hec_const_limbs(c, ct->level, constant, k);
+    std::vector<EwJob> jobs;
+    for (int p = 0; p < 2; p++)
+        for (int i = 0; i <= ct->level; i++) jobs.push_back(ewjob(ct->limb(p, i), nullptr, ct->limb(p, i), i, mform(k[i], c->q(i))));
+    int rc = launch_ew<EW_MULSCALAR>(c, jobs);
+    if (rc) return rc;
+    ct->scale *= up;
+    return HEC_OK;
+}
+
+// one DivRoundByLastModulusNTT on both polys (L:ring/ring_scaling.go:442-513)
+static int div_round_last(hec_ctx *c, hec_ct *ct) {
+    int L = ct->level;
+    int rc = reserve(c, 2 + 2 * (size_t)L);
+    if (rc) return rc;
+    u64 qL = c->q(L), half = (qL - 1) >> 1;
+    u64 *t = c->scratch(2), *u = c->scratch(2 * (size_t)L);
+    std::vector<LimbJob> nj;
+    for (int p = 0; p < 2; p++) nj.push_back({ct->limb(p, L), t + (size_t)p * HEC_N, L, 0});
+    if ((rc = hec_launch_ntt(c, nj, true))) return rc;
+    std::vector<EwJob> ej;
+    for (int p = 0; p < 2; p++) ej.push_back(ewjob(t + (size_t)p * HEC_N, nullptr, t + (size_t)p * HEC_N, L, half));
+    if ((rc = launch_ew<EW_CENTER>(c, ej))) return rc;
+    ej.clear();
+    nj.clear();
+    for (int p = 0; p < 2; p++)
+        for (int i = 0; i < L; i++) {
+            u64 qi = c->q(i);
+            u64 *ui = u + ((size_t)p * L + i) * HEC_N;
+            ej.push_back(ewjob(t + (size_t)p * HEC_N, nullptr, ui, i, qi - half % qi));
+            nj.push_back({ui, ui, i, 0});
+        }
+    if ((rc = launch_ew<EW_REDUCE_ADD>(c, ej))) return rc;
+    if ((rc = hec_launch_ntt(c, nj, false))) return rc;
+    ej.clear();
+    for (int p = 0; p < 2; p++)
+        for (int i = 0; i < L; i++)
+            ej.push_back(ewjob(u + ((size_t)p * L + i) * HEC_N, ct->limb(p, i), ct->limb(p, i), i, c->resc[L][i]));
+    if ((rc = launch_ew<EW_SUBMUL>(c, ej))) return rc;
+    ct->level = L - 1;
+    return HEC_OK;
+}
+
+extern "C" int hec_rescale(hec_ctx *c, hec_ct *ct, double min_scale) {
+    if (!c || !ct) return HEC_E_INVAL;
+    cudaSetDevice(c->device);
+    // L:ckks/evaluator.go:1291-1325
+    if (ct->level == 0) return c->fail(HEC_E_LEVEL, "cannot Rescale: input Ciphertext already at level 0");
+    while (ct->level > 0 && ct->scale / (double)c->q(ct->level) >= min_scale / 2) {
+        double s = ct->scale / (double)c->q(ct->level);
+        int rc = div_round_last(c, ct);
+        if (rc) return rc;
+        ct->scale = s;
+    }
+    return HEC_OK;
+}
+
+extern "C" int hec_set_scale(hec_ctx *c, hec_ct *ct, double scale) {
+    // L:ckks/evaluator.go:1194-1209
+    int rc = hec_mult_by_const(c, ct, scale / ct->scale);
+    if (rc) return rc;
+    if ((rc = hec_rescale(c, ct, scale))) return rc;
+    ct->scale = scale;
+    return HEC_OK;
+}
+
+template <int OP>
+static int addsub(hec_ctx *c, const hec_ct *a, const hec_ct *b, hec_ct *out) {
+    int level = std::min(std::min(a->level, b->level), out->alloc - 1);
+    std::vector<EwJob> jobs;
+    for (int p = 0; p < 2; p++)
+        for (int i = 0; i <= level; i++) jobs.push_back(ewjob(a->limb(p, i), b->limb(p, i), out->limb(p, i), i));
+    int rc = launch_ew<OP>(c, jobs);
+    if (rc) return rc;
+    out->level = level;
+    out->scale = a->scale;
+    return HEC_OK;
+}
+extern "C" int hec_add(hec_ctx *c, const hec_ct *a, const hec_ct *b, hec_ct *out) {
+    if (!c || !a || !b || !out) return HEC_E_INVAL;
+    cudaSetDevice(c->device);
+    return addsub<EW_ADD>(c, a, b, out);
+}
+extern "C" int hec_add_new(hec_ctx *c, const hec_ct *a, const hec_ct *b, hec_ct **out) {
+    if (!c || !a || !b || !out) return HEC_E_INVAL;
+    cudaSetDevice(c->device);
+    hec_ct *o = nullptr;
+    int rc = hec_ct_alloc(c, std::min(a->level, b->level), a->scale, &o);
+    if (rc) return rc;
+    if ((rc = addsub<EW_ADD>(c, a, b, o))) { hec_ct_free(c, o); return rc; }
+    *out = o;
+    return HEC_OK;
+}
+extern "C" int hec_sub_new(hec_ctx *c, const hec_ct *a, const hec_ct *b, hec_ct **out) {
+    if (!c || !a || !b || !out) return HEC_E_INVAL;
+    cudaSetDevice(c->device);
+    hec_ct *o = nullptr;
+    int rc = hec_ct_alloc(c, std::min(a->level, b->level), a->scale, &o);
+    if (rc) return rc;
+    if ((rc = addsub<EW_SUB>(c, a, b, o))) { hec_ct_free(c, o); return rc; }
+    *out = o;
+    return HEC_OK;
+}
+extern "C" int hec_add_pt(hec_ctx *c, hec_ct *ct, const hec_pt *pt) {
+    if (!c || !ct || !pt) return HEC_E_INVAL;
+    cudaSetDevice(c->device);
+    int level = std::min(ct->level, pt->level);
+    std::vector<EwJob> jobs;
+    for (int i = 0; i <= level; i++) jobs.push_back(ewjob(ct->limb(0, i), pt->buf + (size_t)i * HEC_N, ct->limb(0, i), i));
+    int rc = launch_ew<EW_ADD_MONT>(c, jobs);
+    if (rc) return rc;
+    ct->level = level;
+    return HEC_OK;
+}
+
+// ---- key switching -----------------------------------------------------------------------
+// ModDownSplitNTTPQ (L:ring/ring_basis_extension.go:247-291), in place on accQ.
+// Needs nP + L scratch limbs (caller reserved).
+static int moddown(hec_ctx *c, int level, u64 *accQ, u64 *accP) {
+    int L = level + 1, nP = c->nP, rc;
+    std::vector<LimbJob> nj;
+    for (int j = 0; j < nP; j++) nj.push_back({accP + (size_t)j * HEC_N, accP + (size_t)j * HEC_N, c->modP(j), 0});
+    if ((rc = hec_launch_ntt(c, nj, true))) return rc; // InvNTT on P (canonical residues of the lazy original)
+    u64 *x = c->scratch(L);
+    std::vector<ModupJob> mj;
+    nj.clear();
+    for (int i = 0; i < L; i++) {
+        mj.push_back(modup_job(c, c->pq, accP, HEC_N, c->modQ(i), x + (size_t)i * HEC_N));
+        nj.push_back({x + (size_t)i * HEC_N, x + (size_t)i * HEC_N, i, 0});
+    }
+    if ((rc = launch_modup(c, mj))) return rc;
+    if ((rc = hec_launch_ntt(c, nj, false))) return rc;
+    std::vector<EwJob> ej;
+    for (int i = 0; i < L; i++)
+        ej.push_back(ewjob(x + (size_t)i * HEC_N, accQ + (size_t)i * HEC_N, accQ + (size_t)i * HEC_N, i, c->negpinv[i]));
+    return launch_ew<EW_SUBMUL>(c, ej);
+}
+
+struct Decomp { u64 *D; int L, beta; };
+static size_t decomp_limbs(const hec_ctx *c, int level) {
+    int L = level + 1, beta = (L + c->alpha - 1) / c->alpha;
+    return (size_t)L + (size_t)beta * (L + c->nP);
+}
+// DecomposeNTT (L:rlwe/keyswitch.go:94-141; DecomposeAndSplit L:ring/ring_basis_extension.go:543-664)
+static int decompose(hec_ctx *c, int level, const u64 *c1, Decomp &out) {
+    int L = level + 1, nP = c->nP, alpha = c->alpha, rc;
+    int beta = (L + alpha - 1) / alpha, W = L + nP;
+    u64 *cinv = c->scratch(L);
+    u64 *D = c->scratch((size_t)beta * W);
+    std::vector<LimbJob> nj;
+    for (int i = 0; i < L; i++) nj.push_back({c1 + (size_t)i * HEC_N, cinv + (size_t)i * HEC_N, i, 0});
+    if ((rc = hec_launch_ntt(c, nj, true))) return rc;
+    std::vector<EwJob> lift, copy;
+    std::vector<ModupJob> mj;
+    nj.clear();
+    for (int d = 0; d < beta; d++) {
+        int st = d * alpha, nd = std::min(c->xalpha[d], L - st);
+        for (int t = 0; t < W; t++) {
+            u64 *dst = D + ((size_t)d * W + t) * HEC_N;
+            int mod = t < L ? c->modQ(t) : c->modP(t - L);
+            if (t < L && t >= st && t < st + nd) { // in-digit limb: reuse the NTT form of c1
+                copy.push_back(ewjob(c1 + (size_t)t * HEC_N, nullptr, dst, mod));
+                continue;
+            }
+            if (nd == 1) lift.push_back(ewjob(cinv + (size_t)st * HEC_N, nullptr, dst, mod, 0)); // copy path
+            else mj.push_back(modup_job(c, c->dec[d][nd], cinv + (size_t)st * HEC_N, HEC_N, mod, dst));
+            nj.push_back({dst, dst, mod, 0});
+        }
+    }
+    if (!copy.empty() && (rc = launch_ew<EW_COPY>(c, copy))) return rc;
+    if (!lift.empty() && (rc = launch_ew<EW_REDUCE_ADD>(c, lift))) return rc;
+    if (!mj.empty() && (rc = launch_modup(c, mj))) return rc;
+    if ((rc = hec_launch_ntt(c, nj, false))) return rc;
+    out.D = D; out.L = L; out.beta = beta;
+    return HEC_OK;
+}
+// KeyswitchHoisted (L:rlwe/keyswitch.go:234-304): inner product with the key + mod-down.
+// d0,d1: [L][N] outputs.  Needs 2*nP + (nP... ) scratch: 2*nP accumulators + L for moddown.
+static int keyswitch_from_decomp(hec_ctx *c, int level, const Decomp &dc, const SwKey &key, u64 *d0, u64 *d1) {
+    int L = level + 1, nP = c->nP, W = L + nP, kl = key.Lk + nP, rc;
+    if (key.Lk < L || key.ndig < dc.beta) return c->fail(HEC_E_NOKEY, "switching key slice does not cover this level");
+    u64 *accP = c->scratch(2 * (size_t)nP);
+    u64 *accQ[2] = {d0, d1};
+    for (int d = 0; d < dc.beta; d++) {
+        std::vector<EwJob> jobs;
+        for (int p = 0; p < 2; p++)
+            for (int t = 0; t < W; t++) {
+                const u64 *dh = dc.D + ((size_t)d * W + t) * HEC_N;
+                int kt = t < L ? t : key.Lk + (t - L);
+                const u64 *kp = key.buf + ((size_t)(d * 2 + p) * kl + kt) * HEC_N;
+                u64 *acc = t < L ? accQ[p] + (size_t)t * HEC_N : accP + ((size_t)p * nP + (t - L)) * HEC_N;
+                jobs.push_back(ewjob(dh, kp, acc, t < L ? c->modQ(t) : c->modP(t - L)));
+            }
+        rc = d == 0 ? launch_ew<EW_MULMONT>(c, jobs) : launch_ew<EW_MAC>(c, jobs);
+        if (rc) return rc;
+    }
+    for (int p = 0; p < 2; p++) {
+        size_t mark = c->arena_top;
+        if ((rc = moddown(c, level, accQ[p], accP + (size_t)p * nP * HEC_N))) return rc;
+        c->arena_top = mark;
+    }
+    return HEC_OK;
+}
+static size_t ks_limbs(const hec_ctx *c, int level) { return decomp_limbs(c, level) + 2 * c->nP + (level + 1); }
+
+// permuteNTT tail (L:ckks/evaluator.go:1575-1597): d0 += c0, then PermuteNTTWithIndexLvl x2
+static int finish_rotation(hec_ctx *c, int level, const hec_ct *ct, u64 galEl, u64 *d0, u64 *d1, hec_ct *out) {
+    int L = level + 1, rc;
+    std::vector<EwJob> jobs;
+    for (int i = 0; i < L; i++) jobs.push_back(ewjob(d0 + (size_t)i * HEC_N, ct->limb(0, i), d0 + (size_t)i * HEC_N, i));
+    if ((rc = launch_ew<EW_ADD>(c, jobs))) return rc;
+    jobs.clear();
+    for (int i = 0; i < L; i++) {
+        jobs.push_back(ewjob(d0 + (size_t)i * HEC_N, nullptr, out->limb(0, i), i, 0, (u32)galEl));
+        jobs.push_back(ewjob(d1 + (size_t)i * HEC_N, nullptr, out->limb(1, i), i, 0, (u32)galEl));
+    }
+    if ((rc = launch_ew<EW_PERMUTE>(c, jobs))) return rc;
+    out->level = level;
+    out->scale = ct->scale;
+    return HEC_OK;
+}
+
+extern "C" int hec_rotate_gal(hec_ctx *c, const hec_ct *ct, uint64_t galEl, hec_ct *out) {
+    if (!c || !ct || !out) return HEC_E_INVAL;
+    cudaSetDevice(c->device);
+    auto it = c->keys.find(galEl);
+    if (it == c->keys.end()) return c->fail(HEC_E_NOKEY, "rotation key for galEl " + std::to_string(galEl) + " missing");
+    int level = std::min(ct->level, out->alloc - 1), L = level + 1, rc;
+    if ((rc = reserve(c, ks_limbs(c, level) + 2 * (size_t)L))) return rc;
+    u64 *d0 = c->scratch(L), *d1 = c->scratch(L);
+    Decomp dc;
+    if ((rc = decompose(c, level, ct->limb(1, 0), dc))) return rc;
+    if ((rc = keyswitch_from_decomp(c, level, dc, it->second, d0, d1))) return rc;
+    return finish_rotation(c, level, ct, galEl, d0, d1, out);
+}
+
+extern "C" uint64_t hec_galois_for_rotation(const hec_ctx *c, int k) {
+    (void)c;
+    // GaloisElementForColumnRotationBy (L:rlwe/params.go:308-312): 5^(k & (2N-1)) mod 2N
+    u64 mask = 2ull * HEC_N - 1, e = (u64)(int64_t)k & mask, g = 1, b = 5;
+    for (; e; e >>= 1) { if (e & 1) g = (g * b) & mask; b = (b * b) & mask; }
+    return g;
+}
+extern "C" int hec_rotate_new(hec_ctx *c, const hec_ct *ct, int k, hec_ct **out) {
+    if (!c || !ct || !out) return HEC_E_INVAL;
+    cudaSetDevice(c->device);
+    hec_ct *o = nullptr;
+    int rc = hec_ct_alloc(c, ct->level, ct->scale, &o);
+    if (rc) return rc;
+    if ((rc = hec_rotate_gal(c, ct, hec_galois_for_rotation(c, k), o))) { hec_ct_free(c, o); return rc; }
+    *out = o;
+    return HEC_OK;
+}
+// RotateHoisted (L:ckks/linear_transform.go:10-27): one DecomposeNTT shared by all rotations
+extern "C" int hec_rotate_hoisted(hec_ctx *c, const hec_ct *ct, const int *rots, int n, hec_ct **outs) {
+    if (!c || !ct || !rots || !outs || n < 0) return HEC_E_INVAL;
+    cudaSetDevice(c->device);
+    int level = ct->level, L = level + 1, rc;
+    for (int r = 0; r < n; r++)
+        if (rots[r] != 0 && !c->keys.count(hec_galois_for_rotation(c, rots[r])))
+            return c->fail(HEC_E_NOKEY, "rotation key for rotation " + std::to_string(rots[r]) + " missing");
+    if ((rc = reserve(c, ks_limbs(c, level) + 2 * (size_t)L))) return rc;
+    u64 *d0 = c->scratch(L), *d1 = c->scratch(L);
+    Decomp dc;
+    if ((rc = decompose(c, level, ct->limb(1, 0), dc))) return rc;
+    size_t mark = c->arena_top;
+    for (int r = 0; r < n; r++) {
+        outs[r] = nullptr;
+        if (rots[r] == 0) { if ((rc = hec_ct_copy_new(c, ct, &outs[r]))) return rc; continue; }
+        u64 g = hec_galois_for_rotation(c, rots[r]);
+        if ((rc = hec_ct_alloc(c, level, ct->scale, &outs[r]))) return rc;
+        c->arena_top = mark;
+        if ((rc = keyswitch_from_decomp(c, level, dc, c->keys[g], d0, d1))) return rc;
+        if ((rc = finish_rotation(c, level, ct, g, d0, d1, outs[r]))) return rc;
+    }
+    return HEC_OK;
+}
+
+// =========================================================================================
+// ring-level test entry points (host in / host out)
+// =========================================================================================
+extern "C" int hec_ntt(hec_ctx *c, int ring, int limb, const uint64_t *in, uint64_t *out, int inverse) {
+    if (!c || !in || !out || ring < 0 || ring > 1 || limb < 0 || limb >= (ring ? c->nP : c->nQ)) return c ? c->fail(HEC_E_INVAL, "ntt args") : HEC_E_INVAL;
+    cudaSetDevice(c->device);
+    int rc = reserve(c, 1);
+    if (rc) return rc;
+    u64 *d = c->scratch(1);
+    HEC_CUDA(c, cudaMemcpyAsync(d, in, HEC_N * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+    std::vector<LimbJob> nj = {{d, d, ring ? c->modP(limb) : c->modQ(limb), 0}};
+    if ((rc = hec_launch_ntt(c, nj, inverse != 0))) return rc;
+    HEC_CUDA(c, cudaMemcpyAsync(out, d, HEC_N * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    HEC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return HEC_OK;
+}
+extern "C" int hec_keyswitch(hec_ctx *c, int level, const uint64_t *const *c1, uint64_t galEl, uint64_t *const *d0, uint64_t *const *d1) {
+    if (!c || !c1 || !d0 || !d1 || level < 0 || level >= c->nQ) return c ? c->fail(HEC_E_INVAL, "keyswitch args") : HEC_E_INVAL;
+    cudaSetDevice(c->device);
+    auto it = c->keys.find(galEl);
+    if (it == c->keys.end()) return c->fail(HEC_E_NOKEY, "rotation key missing");
+    int L = level + 1, rc;
+    if ((rc = reserve(c, ks_limbs(c, level) + 3 * (size_t)L))) return rc;
+    u64 *x = c->scratch(L), *a0 = c->scratch(L), *a1 = c->scratch(L);
+    for (int i = 0; i < L; i++) HEC_CUDA(c, cudaMemcpyAsync(x + (size_t)i * HEC_N, c1[i], HEC_N * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+    Decomp dc;
+    if ((rc = decompose(c, level, x, dc))) return rc;
+    if ((rc = keyswitch_from_decomp(c, level, dc, it->second, a0, a1))) return rc;
+    for (int i = 0; i < L; i++) {
+        HEC_CUDA(c, cudaMemcpyAsync(d0[i], a0 + (size_t)i * HEC_N, HEC_N * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+        HEC_CUDA(c, cudaMemcpyAsync(d1[i], a1 + (size_t)i * HEC_N, HEC_N * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    }
+    HEC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return HEC_OK;
+}
+extern "C" int hec_moddown(hec_ctx *c, int level, const uint64_t *const *accQ, const uint64_t *const *accP, uint64_t *const *out) {
+    if (!c || !accQ || !accP || !out || c->nP == 0 || level < 0 || level >= c->nQ) return c ? c->fail(HEC_E_INVAL, "moddown args") : HEC_E_INVAL;
+    cudaSetDevice(c->device);
+    int L = level + 1, rc;
+    if ((rc = reserve(c, 2 * (size_t)L + c->nP))) return rc;
+    u64 *aq = c->scratch(L), *ap = c->scratch(c->nP);
+    for (int i = 0; i < L; i++) HEC_CUDA(c, cudaMemcpyAsync(aq + (size_t)i * HEC_N, accQ[i], HEC_N * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+    for (int j = 0; j < c->nP; j++) HEC_CUDA(c, cudaMemcpyAsync(ap + (size_t)j * HEC_N, accP[j], HEC_N * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+    if ((rc = moddown(c, level, aq, ap))) return rc;
+    for (int i = 0; i < L; i++) HEC_CUDA(c, cudaMemcpyAsync(out[i], aq + (size_t)i * HEC_N, HEC_N * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    HEC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return HEC_OK;
+}

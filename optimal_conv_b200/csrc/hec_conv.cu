@@ -1,0 +1,360 @@
+// hec_conv.cu -- the conv_then_pack path (conv.go:522-546 incl. pack_ctxts conv.go:266-300,
+// + the bias Add of evalConv_BN eval.go:258):
+//   * op-level replay through the evaluator ops (reads like the Go code), and
+//   * the fused plan: 3 kernels for Stage A + 5 per pack-tree level, captured in a CUDA graph.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include "hec_host.cuh"
+
+using namespace hec;
+
+int hec_ct_alloc(hec_ctx *c, int level, double scale, hec_ct **out);
+double hec_const_limbs(const hec_ctx *c, int level, double constant, std::vector<u64> &k);
+
+// =========================================================================================
+// op-level replay (host side mirrors the reference line by line)
+// =========================================================================================
+// pack_ctxts (conv.go:266-300)
+static int pack_ctxts(hec_ctx *ev, std::vector<hec_ct *> &ctxts_in, int max_cnum, int real_cnum,
+                      const hec_pt *const *idx, hec_ct **result) {
+    int step = max_cnum / 2;
+    int norm = max_cnum / real_cnum;
+    int rc;
+    std::vector<hec_ct *> ctxts(max_cnum, nullptr);
+    for (int i = 0; i < max_cnum; i++)
+        if (i % norm == 0) {
+            if ((rc = hec_ct_copy_new(ev, ctxts_in[i], &ctxts[i]))) return rc;
+            hec_ct_set_scale(ctxts[i], hec_ct_scale(ctxts[i]) * (double)real_cnum);
+        }
+    int logStep = 0;
+    for (int i = step; i > 1; i /= 2) logStep++;
+    int j = HEC_LOGN - logStep;
+    while (step >= norm && step >= 1) {
+        for (int i = 0; i < step; i += norm) {
+            hec_ct *tmp1 = nullptr, *tmp2 = nullptr;
+            if ((rc = hec_mul_pt_new(ev, ctxts[i + step], idx[logStep], &tmp1))) return rc;
+            if ((rc = hec_sub_new(ev, ctxts[i], tmp1, &tmp2))) return rc;
+            if ((rc = hec_add(ev, ctxts[i], tmp1, tmp1))) return rc;
+            if ((rc = hec_rotate_gal(ev, tmp2, (1ull << j) + 1, tmp2))) return rc;
+            if ((rc = hec_add(ev, tmp1, tmp2, ctxts[i]))) return rc;
+            hec_ct_free(ev, tmp1);
+            hec_ct_free(ev, tmp2);
+        }
+        step /= 2;
+        logStep--;
+        j++;
+    }
+    *result = ctxts[0];
+    for (int i = 1; i < max_cnum; i++) if (ctxts[i]) hec_ct_free(ev, ctxts[i]);
+    return HEC_OK;
+}
+
+// conv_then_pack (conv.go:522-546)
+static int conv_then_pack_oplevel(hec_ctx *ev, const hec_ct *ctxt_in, const hec_pt *const *pl_ker, int max_ob, int norm,
+                                  double out_scale, const hec_pt *const *plain_idx, hec_ct **out) {
+    std::vector<hec_ct *> ctxt_out(max_ob, nullptr);
+    int rc;
+    for (int i = 0; i < max_ob; i++)
+        if (i % norm == 0) {
+            if ((rc = hec_mul_pt_new(ev, ctxt_in, pl_ker[i], &ctxt_out[i]))) return rc;
+            if ((rc = hec_set_scale(ev, ctxt_out[i], out_scale / (double)(max_ob / norm)))) return rc;
+        }
+    hec_ct *res = nullptr;
+    if ((rc = pack_ctxts(ev, ctxt_out, max_ob, max_ob / norm, plain_idx, &res))) return rc;
+    for (auto p : ctxt_out) if (p) hec_ct_free(ev, p);
+    if (out_scale != hec_ct_scale(res) || 0 != hec_ct_level(res)) {
+        hec_ct_free(ev, res);
+        return ev->fail(HEC_E_SCALE, "LV or scale after conv then pack, inconsistent");
+    }
+    *out = res;
+    return HEC_OK;
+}
+
+// =========================================================================================
+// fused plan
+// =========================================================================================
+struct hec_plan {
+    hec_ctx *c = nullptr;
+    int B = 0, norm = 1, na = 0, M = 0, levels = 0;
+    double in_scale = 0, out_scale = 0;
+    const u64 **d_ctin = nullptr, **d_ptk = nullptr;
+    u64 *pool = nullptr; // all scratch / level buffers
+    u64 *stage_in = nullptr, *xfinal = nullptr;
+    ConvA pa;
+    std::vector<ConvB> pb;
+    const u64 *bias = nullptr; int bias_mod = 0;
+    cudaGraphExec_t exec = nullptr;
+    int launches_per_run = 0;
+};
+
+static int plan_launch_all(hec_plan *p, const std::function<void()> &after = [] {}) {
+    hec_ctx *c = p->c;
+    cudaStream_t s = c->stream;
+    dim3 gA(HEC_TILES_PER_LIMB, p->M * p->na * 2);
+    k_convA1<<<gA, HEC_THREADS, 0, s>>>(p->pa, c->dmods);
+    after();
+    k_convA2<<<gA, HEC_THREADS, 0, s>>>(p->pa, c->dmods);
+    after();
+    k_convA3<<<gA, HEC_THREADS, 0, s>>>(p->pa, c->dmods);
+    after();
+    for (auto &b : p->pb) {
+        int nb = b.n / 2;
+        dim3 g1(HEC_TILES_PER_LIMB, p->M * nb), g2(HEC_TILES_PER_LIMB, p->M * nb * 2);
+        k_convB1<<<g1, HEC_THREADS, 0, s>>>(b, c->dmods);
+        after();
+        k_convB2<<<g1, HEC_THREADS, 0, s>>>(b, c->dmods);
+        after();
+        k_convB3<<<g2, HEC_THREADS, 0, s>>>(b, c->dmods);
+        after();
+        k_convB4<<<g2, HEC_THREADS, 0, s>>>(b, c->dmods);
+        after();
+        k_convB5<<<g2, HEC_THREADS, 0, s>>>(b, c->dmods);
+        after();
+    }
+    if (p->levels == 0 && p->bias) { // single channel: bias not folded into a B5 epilogue
+        EwJobs J;
+        for (int m = 0; m < p->M; m++) {
+            u64 *x = p->xfinal + (size_t)m * 2 * HEC_N;
+            J.j[0].a = x; J.j[0].b = p->bias; J.j[0].out = x; J.j[0].mod = p->pa.mq0; J.j[0].g = 0; J.j[0].s0 = 0; J.j[0].s1 = 0;
+            k_ew<EW_ADD_MONT><<<dim3(32, 1), 256, 0, s>>>(J, c->dmods);
+            after();
+        }
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return c->fail(HEC_E_CUDA, std::string("conv launch: ") + cudaGetErrorString(e));
+    return HEC_OK;
+}
+
+extern "C" void hec_plan_destroy(hec_plan *p) {
+    if (!p) return;
+    cudaSetDevice(p->c->device);
+    cudaStreamSynchronize(p->c->stream);
+    if (p->exec) cudaGraphExecDestroy(p->exec);
+    if (p->pool) cudaFree(p->pool);
+    if (p->d_ctin) cudaFree((void *)p->d_ctin);
+    if (p->d_ptk) cudaFree((void *)p->d_ptk);
+    delete p;
+}
+
+extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_ob, int norm, double in_scale,
+                               double out_scale, const hec_pt *const *pt_idx, const hec_pt *pt_bias, int batch,
+                               hec_plan **out) {
+    if (!c || !pt_ker || !pt_idx || !out || batch < 1 || max_ob < 1 || norm < 1) return c ? c->fail(HEC_E_INVAL, "plan args") : HEC_E_INVAL;
+    cudaSetDevice(c->device);
+    if ((max_ob & (max_ob - 1)) || (norm & (norm - 1)) || norm > max_ob || max_ob > 256)
+        return c->fail(HEC_E_UNSUPPORTED, "max_ob and norm must be powers of two, max_ob <= 256");
+    if (c->nQ < 2 || c->nP != 1) return c->fail(HEC_E_UNSUPPORTED, "fused conv needs >= 2 Q limbs and exactly one special prime (main.go:446-454)");
+    const int B = max_ob, na = B / norm, M = batch;
+    for (int i = 0; i < B; i += norm)
+        if (!pt_ker[i] || pt_ker[i]->level < 1) return c->fail(HEC_E_LEVEL, "kernel plaintexts must be at level >= 1 (ECD_LV)");
+    // ---- SetScale bookkeeping (L:ckks/evaluator.go:1194-1209, 1291-1325) ----
+    const double pt_scale = pt_ker[0]->scale;
+    const double target = out_scale / (double)(B / norm);
+    double s = in_scale * pt_scale;
+    std::vector<u64> k;
+    double up = hec_const_limbs(c, 1, target / s, k);
+    s *= up;
+    int nb = 0;
+    while (1 - nb > 0 && s / (double)c->q(1 - nb) >= target / 2) { s /= (double)c->q(1 - nb); nb++; }
+    double res_scale = target * (double)(B / norm); // pack_ctxts conv.go:274
+    if (nb != 1 || res_scale != out_scale) return c->fail(HEC_E_SCALE, "LV or scale after conv then pack, inconsistent");
+
+    hec_plan *p = new hec_plan();
+    p->c = c; p->B = B; p->norm = norm; p->na = na; p->M = M; p->in_scale = in_scale; p->out_scale = out_scale;
+    int levels = 0;
+    for (int t = na; t > 1; t >>= 1) levels++;
+    p->levels = levels;
+    auto bail = [&](int code, const char *msg) { hec_plan_destroy(p); return c->fail(code, msg); };
+    // ---- device memory: pointer tables + one pool ----
+    if (cudaMalloc((void **)&p->d_ctin, M * sizeof(u64 *)) != cudaSuccess) return bail(HEC_E_NOMEM, "cudaMalloc");
+    if (cudaMalloc((void **)&p->d_ptk, B * sizeof(u64 *)) != cudaSuccess) return bail(HEC_E_NOMEM, "cudaMalloc");
+    std::vector<const u64 *> hk(B, nullptr);
+    for (int i = 0; i < B; i += norm) hk[i] = pt_ker[i]->buf;
+    if (cudaMemcpy((void *)p->d_ptk, hk.data(), B * sizeof(u64 *), cudaMemcpyHostToDevice) != cudaSuccess) return bail(HEC_E_CUDA, "memcpy ptk");
+    size_t jobsA = (size_t)M * na * 2;          // limbs per Stage-A buffer
+    size_t nb0 = (size_t)M * std::max(1, na / 2);
+    size_t limbs = 4 * (size_t)M                 // staged inputs [M][2][2]
+                 + 2 * jobsA                     // w1, w2
+                 + 2 * jobsA                     // X_0 .. X_last (geometric, < 2x)
+                 + nb0 * (1 + 1 + 2 + 2);        // wb1..wb4
+    if (cudaMalloc(&p->pool, limbs * HEC_N * sizeof(u64)) != cudaSuccess) return bail(HEC_E_NOMEM, "cudaMalloc plan pool");
+    u64 *cur = p->pool;
+    auto take = [&](size_t n) { u64 *r = cur; cur += n * HEC_N; return r; };
+    p->stage_in = take(4 * (size_t)M);
+    u64 *w1 = take(jobsA), *w2 = take(jobsA);
+    std::vector<u64 *> X(levels + 1);
+    for (int l = 0; l <= levels; l++) X[l] = take((size_t)M * (na >> l) * 2);
+    u64 *wb1 = take(nb0), *wb2 = take(nb0), *wb3 = take(2 * nb0), *wb4 = take(2 * nb0);
+    p->xfinal = X[levels];
+    // ---- Stage A constants ----
+    const int mq0 = c->modQ(0), mq1 = c->modQ(1), mp0 = c->modP(0);
+    const u64 q0 = c->q(mq0), q1 = c->q(mq1), p0 = c->q(mp0);
+    ConvA &A = p->pa;
+    A.ctin = p->d_ctin; A.ptk = p->d_ptk; A.w1 = w1; A.w2 = w2; A.xout = X[0];
+    A.na = na; A.norm = norm; A.mq0 = mq0; A.mq1 = mq1;
+    A.k0m = mform(k[0], q0); A.k1m = mform(k[1], q1);
+    A.half1 = (q1 - 1) >> 1;
+    A.hneg0 = q0 - A.half1 % q0;
+    A.resc0 = c->resc[1][0];
+    // ---- tree levels ----
+    int step = B / 2, logStep = 0;
+    for (int i = step; i > 1; i /= 2) logStep++;
+    int j = HEC_LOGN - logStep;
+    if (pt_bias) { p->bias = pt_bias->buf; p->bias_mod = mq0; }
+    for (int l = 0; l < levels; l++, step /= 2, logStep--, j++) {
+        u64 g = (1ull << j) + 1;
+        auto it = c->keys.find(g);
+        if (it == c->keys.end()) return bail(HEC_E_NOKEY, "rotation key for a pack level is missing");
+        if (j < 9) return bail(HEC_E_UNSUPPORTED, "automorphism not local to a 256-word block");
+        if (!pt_idx[logStep]) return bail(HEC_E_INVAL, "pt_idx entry missing");
+        ConvB b;
+        memset(&b, 0, sizeof b);
+        b.xin = X[l]; b.xout = X[l + 1];
+        b.mono = pt_idx[logStep]->buf;
+        b.key = it->second.buf;
+        b.keyL = it->second.Lk + c->nP;
+        b.keyPoff = it->second.Lk;
+        b.bias = (l == levels - 1 && pt_bias) ? pt_bias->buf : nullptr;
+        b.w1 = wb1; b.w2 = wb2; b.w3 = wb3; b.w4 = wb4;
+        b.n = na >> l; b.mq0 = mq0; b.mp0 = mp0;
+        b.galEl = (u32)g;
+        b.negpinv = c->negpinv[0];
+        b.qpj1 = c->pq.qpjinv[mq0][1];
+        b.p0f = (double)p0;
+        p->pb.push_back(b);
+    }
+    p->launches_per_run = 3 + 5 * levels + ((levels == 0 && pt_bias) ? M : 0);
+    // ---- capture the kernel sequence in a CUDA graph ----
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return bail(HEC_E_CUDA, "begin capture");
+    int rc = plan_launch_all(p);
+    cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+    if (rc || e != cudaSuccess || !graph) return bail(HEC_E_CUDA, "graph capture failed");
+    e = cudaGraphInstantiate(&p->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return bail(HEC_E_CUDA, "graph instantiate failed");
+    *out = p;
+    return HEC_OK;
+}
+
+static int plan_run_graph(hec_plan *p, const std::vector<const u64 *> &ptrs) {
+    hec_ctx *c = p->c;
+    // small pageable copy: staged by the driver at call time, so `ptrs` may die on return
+    HEC_CUDA(c, cudaMemcpyAsync((void *)p->d_ctin, ptrs.data(), p->M * sizeof(u64 *), cudaMemcpyHostToDevice, c->stream));
+    HEC_CUDA(c, cudaGraphLaunch(p->exec, c->stream));
+    c->launches += p->launches_per_run;
+    return HEC_OK;
+}
+
+extern "C" int hec_plan_run(hec_plan *p, const hec_ct *const *ins, hec_ct **outs) {
+    if (!p || !ins || !outs) return HEC_E_INVAL;
+    hec_ctx *c = p->c;
+    cudaSetDevice(c->device);
+    std::vector<const u64 *> ptrs(p->M);
+    for (int m = 0; m < p->M; m++) {
+        if (!ins[m] || ins[m]->level != 1 || ins[m]->alloc != 2) return c->fail(HEC_E_LEVEL, "plan inputs must be level-1 ciphertexts");
+        if (ins[m]->scale != p->in_scale) return c->fail(HEC_E_SCALE, "input scale differs from the plan's");
+        ptrs[m] = ins[m]->buf;
+    }
+    int rc = plan_run_graph(p, ptrs);
+    if (rc) return rc;
+    for (int m = 0; m < p->M; m++) {
+        if (!outs[m] && (rc = hec_ct_alloc(c, 0, p->out_scale, &outs[m]))) return rc;
+        if (outs[m]->alloc != 1) return c->fail(HEC_E_LEVEL, "plan outputs must be level-0 ciphertexts");
+        outs[m]->level = 0;
+        outs[m]->scale = p->out_scale;
+        HEC_CUDA(c, cudaMemcpyAsync(outs[m]->buf, p->xfinal + (size_t)m * 2 * HEC_N, 2 * HEC_N * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    return HEC_OK;
+}
+
+extern "C" int hec_plan_run_host(hec_plan *p, const uint64_t *const *in_c0, const uint64_t *const *in_c1,
+                                 uint64_t *const *out_c0, uint64_t *const *out_c1) {
+    if (!p || !in_c0 || !in_c1 || !out_c0 || !out_c1) return HEC_E_INVAL;
+    hec_ctx *c = p->c;
+    cudaSetDevice(c->device);
+    const size_t LB = HEC_N * sizeof(u64);
+    std::vector<const u64 *> ptrs(p->M);
+    for (int m = 0; m < p->M; m++) {
+        u64 *d = p->stage_in + (size_t)m * 4 * HEC_N; // [2 polys][2 limbs][N]
+        for (int i = 0; i < 2; i++) {
+            HEC_CUDA(c, cudaMemcpyAsync(d + (size_t)(0 * 2 + i) * HEC_N, in_c0[m * 2 + i], LB, cudaMemcpyHostToDevice, c->stream));
+            HEC_CUDA(c, cudaMemcpyAsync(d + (size_t)(1 * 2 + i) * HEC_N, in_c1[m * 2 + i], LB, cudaMemcpyHostToDevice, c->stream));
+        }
+        ptrs[m] = d;
+    }
+    int rc = plan_run_graph(p, ptrs);
+    if (rc) return rc;
+    for (int m = 0; m < p->M; m++) {
+        const u64 *x = p->xfinal + (size_t)m * 2 * HEC_N;
+        HEC_CUDA(c, cudaMemcpyAsync(out_c0[m], x, LB, cudaMemcpyDeviceToHost, c->stream));
+        HEC_CUDA(c, cudaMemcpyAsync(out_c1[m], x + HEC_N, LB, cudaMemcpyDeviceToHost, c->stream));
+    }
+    HEC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return HEC_OK;
+}
+
+// per-launch device times of one run, kernels launched one by one (not through the graph):
+// order A1,A2,A3,(B1..B5) x levels.  For bench.py's roofline of the dominant kernel.
+extern "C" int hec_plan_profile(hec_plan *p, const hec_ct *const *ins, float *ms, int cap, int *n) {
+    if (!p || !ins || !ms || !n) return HEC_E_INVAL;
+    hec_ctx *c = p->c;
+    cudaSetDevice(c->device);
+    int nk = p->launches_per_run;
+    if (cap < nk) return c->fail(HEC_E_INVAL, "profile buffer too small");
+    std::vector<const u64 *> ptrs(p->M);
+    for (int m = 0; m < p->M; m++) {
+        if (!ins[m] || ins[m]->level != 1 || ins[m]->alloc != 2) return c->fail(HEC_E_LEVEL, "plan inputs must be level-1 ciphertexts");
+        ptrs[m] = ins[m]->buf;
+    }
+    HEC_CUDA(c, cudaMemcpyAsync((void *)p->d_ctin, ptrs.data(), p->M * sizeof(u64 *), cudaMemcpyHostToDevice, c->stream));
+    std::vector<cudaEvent_t> ev(nk + 1);
+    for (auto &e : ev) cudaEventCreate(&e);
+    int k = 0;
+    cudaEventRecord(ev[0], c->stream);
+    int rc = plan_launch_all(p, [&] { if (k < nk) cudaEventRecord(ev[++k], c->stream); });
+    cudaStreamSynchronize(c->stream);
+    c->launches += nk;
+    for (int i = 0; i < k; i++) cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+    for (auto &e : ev) cudaEventDestroy(e);
+    *n = k;
+    return rc;
+}
+
+// =========================================================================================
+// hec_conv_then_pack
+// =========================================================================================
+extern "C" int hec_conv_then_pack(hec_ctx *c, const hec_ct *ct_in, const hec_pt *const *pt_ker, int max_ob, int norm,
+                                  double out_scale, const hec_pt *const *pt_idx, const hec_pt *pt_bias, int flags,
+                                  hec_ct **out) {
+    if (!c || !ct_in || !pt_ker || !pt_idx || !out) return HEC_E_INVAL;
+    cudaSetDevice(c->device);
+    int rc;
+    if (flags == HEC_CONV_OPLEVEL) {
+        hec_ct *res = nullptr;
+        if ((rc = conv_then_pack_oplevel(c, ct_in, pt_ker, max_ob, norm, out_scale, pt_idx, &res))) return rc;
+        if (pt_bias && (rc = hec_add_pt(c, res, pt_bias))) { hec_ct_free(c, res); return rc; } // eval.go:258
+        *out = res;
+        return HEC_OK;
+    }
+    if (ct_in->level != 1) return c->fail(HEC_E_UNSUPPORTED, "fused conv_then_pack expects a level-1 input (ECD_LV = 1)");
+    hec_plan *plan = nullptr;
+    if ((rc = hec_plan_create(c, pt_ker, max_ob, norm, ct_in->scale, out_scale, pt_idx, pt_bias, 1, &plan))) return rc;
+    hec_ct *res = nullptr;
+    const hec_ct *ins[1] = {ct_in};
+    hec_ct *tmp = nullptr;
+    if (ct_in->alloc != 2) { // compact a ciphertext whose buffer still has dropped limbs
+        if ((rc = hec_ct_alloc(c, 1, ct_in->scale, &tmp))) { hec_plan_destroy(plan); return rc; }
+        for (int p = 0; p < 2; p++)
+            cudaMemcpyAsync(tmp->limb(p, 0), ct_in->limb(p, 0), 2 * HEC_N * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream);
+        ins[0] = tmp;
+    }
+    rc = hec_plan_run(plan, ins, &res);
+    hec_plan_destroy(plan);
+    if (tmp) hec_ct_free(c, tmp);
+    if (rc) { if (res) hec_ct_free(c, res); return rc; }
+    *out = res;
+    return HEC_OK;
+}

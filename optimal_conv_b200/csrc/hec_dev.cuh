@@ -1,0 +1,215 @@
+// hec_dev.cuh -- device-side modular arithmetic and the two NTT tile shapes (sm_100a).
+//
+// A limb of N = 2^16 words is viewed as a 256 x 256 matrix (index j = r*256 + c).
+//  * "column" kernels own 256 rows x 16 columns and run the 8 stages whose butterfly
+//    distance is a multiple of 256 (forward stages m = 1..128, inverse stages t >= 256);
+//  * "row" kernels own 16 contiguous 256-word blocks and run the 8 stages inside a block
+//    (forward m = 256..32768, inverse t = 1..128).
+// A thread keeps 16 coefficients in registers and does 4 stages between exchanges, so a
+// 16-stage transform is 2 kernels x (4 + exchange + 4).  The forward transform always ends
+// on a row kernel and the inverse always starts on one, which is what lets the fused
+// kernels chain  inverse -> pointwise -> forward  without leaving the tile.
+//
+// Arithmetic follows the Lattigo conventions the reference relies on:
+// Montgomery form with R = 2^64, twiddle tables NttPsi[brev(j)] = psi^j * R, natural-order
+// input and bit-reversed output.  Lazy ranges are ours (Harvey): forward values live in
+// [0,4q), inverse values in [0,2q); every value that leaves a kernel for the caller is
+// canonical, so results are bit-identical to the reference's canonical residues.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+#define HEC_LOGN 16
+#define HEC_N 65536
+#define HEC_TILE 4096           // words per CTA tile (both shapes)
+#define HEC_TILES_PER_LIMB 16
+#define HEC_THREADS 256
+#define HEC_ROW_PITCH 272       // 256 + one pad word per 16 (bank-conflict-free 16p+k reads)
+
+struct ModC {
+    u64 q, qinv;      // q * qinv = 1 mod 2^64
+    u64 q2;           // 2q
+    u64 ninv;         // N^-1 * R mod q
+    u64 rmod;         // R mod q  (mred(x, rmod) = x mod q, canonical)
+    const u64 *psi;   // NttPsi  (Montgomery, bit-reversed)
+    const u64 *psi_inv;
+};
+
+// ---- scalar primitives -----------------------------------------------------------------
+// x*y*R^-1 mod q, result in (0, 2q).  Needs x*y < q*2^64 (always true for y < q).
+__device__ __forceinline__ u64 mred_lazy(u64 x, u64 y, u64 q, u64 qinv) {
+    u64 lo = x * y;
+    u64 hi = __umul64hi(x, y);
+    u64 h = __umul64hi(lo * qinv, q);
+    return hi - h + q;
+}
+// canonical [0,q)
+__device__ __forceinline__ u64 mred(u64 x, u64 y, u64 q, u64 qinv) {
+    u64 r = mred_lazy(x, y, q, qinv);
+    return r >= q ? r - q : r;
+}
+__device__ __forceinline__ u64 cred(u64 a, u64 q) { return a >= q ? a - q : a; }
+__device__ __forceinline__ u64 addmod(u64 a, u64 b, u64 q) { return cred(a + b, q); }
+__device__ __forceinline__ u64 submod(u64 a, u64 b, u64 q) { return cred(a + q - b, q); }
+// [0,4q) -> [0,q)
+__device__ __forceinline__ u64 canon4(u64 a, u64 q, u64 q2) { return cred(cred(a, q2), q); }
+
+// Cooley-Tukey butterfly, X,Y in [0,4q) -> [0,4q)
+__device__ __forceinline__ void ct_bfly(u64 &X, u64 &Y, u64 w, u64 q, u64 qinv, u64 q2) {
+    u64 x = cred(X, q2);
+    u64 t = mred_lazy(Y, w, q, qinv);
+    X = x + t;
+    Y = x - t + q2;
+}
+// Gentleman-Sande butterfly, X,Y in [0,2q) -> [0,2q)
+__device__ __forceinline__ void gs_bfly(u64 &X, u64 &Y, u64 w, u64 q, u64 qinv, u64 q2) {
+    u64 u = X, v = Y;
+    X = cred(u + v, q2);
+    Y = mred_lazy(u - v + q2, w, q, qinv);
+}
+
+// Four forward stages on 16 register-resident coefficients.  The coefficient at slot k
+// pairs with slot k+d for d = 8,4,2,1; stage d uses twiddles psi[ng*base + gi], ng = 8/d,
+// gi = k / (2d).  `base` encodes where the 16 coefficients sit in the limb:
+//   column kernel, rows p+16k : base = 1            column kernel, rows 16g+k : base = 16+g
+//   row kernel, words p+16k   : base = 256+b        row kernel, words 16p+k   : base = 4096+16b+p
+__device__ __forceinline__ void fwd4(u64 (&x)[16], const u64 *__restrict__ psi, u32 base, u64 q, u64 qinv, u64 q2) {
+#pragma unroll
+    for (int lg = 0; lg < 4; lg++) {
+        const int d = 8 >> lg, ng = 1 << lg;
+#pragma unroll
+        for (int gi = 0; gi < ng; gi++) {
+            u64 w = __ldg(psi + ng * base + gi);
+#pragma unroll
+            for (int k = 0; k < d; k++) ct_bfly(x[gi * 2 * d + k], x[gi * 2 * d + k + d], w, q, qinv, q2);
+        }
+    }
+}
+// Four inverse stages (d = 1,2,4,8), same indexing with the psi_inv table.
+__device__ __forceinline__ void inv4(u64 (&x)[16], const u64 *__restrict__ psi_inv, u32 base, u64 q, u64 qinv, u64 q2) {
+#pragma unroll
+    for (int lg = 3; lg >= 0; lg--) {
+        const int d = 8 >> lg, ng = 1 << lg;
+#pragma unroll
+        for (int gi = 0; gi < ng; gi++) {
+            u64 w = __ldg(psi_inv + ng * base + gi);
+#pragma unroll
+            for (int k = 0; k < d; k++) gs_bfly(x[gi * 2 * d + k], x[gi * 2 * d + k + d], w, q, qinv, q2);
+        }
+    }
+}
+
+// ---- row-kernel tile geometry ------------------------------------------------------------
+// 256 threads; thread (p = tid&15, bb = tid>>4) works on block b = 16*tile + bb.
+// layout A' : slot k <-> word p + 16k   (global accesses coalesced: 16 lanes x 8 B)
+// layout B' : slot k <-> word 16p + k
+// The exchange only moves data inside a half-warp's own block, so __syncwarp() suffices.
+struct RowGeom {
+    u32 p, bb, b;
+    u32 gbase;   // word offset of layout-A' slot 0 in the limb: b*256 + p
+    u32 sbase;   // smem offset of this block
+    __device__ __forceinline__ RowGeom(u32 tile) {
+        u32 tid = threadIdx.x;
+        p = tid & 15; bb = tid >> 4; b = tile * 16 + bb;
+        gbase = b * 256 + p;
+        sbase = bb * HEC_ROW_PITCH;
+    }
+    __device__ __forceinline__ u32 baseA() const { return 256 + b; }
+    __device__ __forceinline__ u32 baseB() const { return 4096 + 16 * b + p; }
+};
+__device__ __forceinline__ void row_loadA(u64 (&x)[16], const u64 *__restrict__ g, const RowGeom &G) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) x[k] = g[G.gbase + 16 * k];
+}
+__device__ __forceinline__ void row_storeA(const u64 (&x)[16], u64 *__restrict__ g, const RowGeom &G) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) g[G.gbase + 16 * k] = x[k];
+}
+__device__ __forceinline__ void row_AtoB(u64 (&x)[16], u64 *sm, const RowGeom &G) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) sm[G.sbase + G.p + 17 * k] = x[k];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 16; k++) x[k] = sm[G.sbase + 17 * G.p + k];
+    __syncwarp();
+}
+__device__ __forceinline__ void row_BtoA(u64 (&x)[16], u64 *sm, const RowGeom &G) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) sm[G.sbase + 17 * G.p + k] = x[k];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 16; k++) x[k] = sm[G.sbase + G.p + 17 * k];
+    __syncwarp();
+}
+// layout-B' global access: 16 contiguous words per thread, as 8 x 128-bit
+__device__ __forceinline__ void row_loadB(u64 (&x)[16], const u64 *__restrict__ g, const RowGeom &G) {
+    const ulonglong2 *v = reinterpret_cast<const ulonglong2 *>(g + G.b * 256 + 16 * G.p);
+#pragma unroll
+    for (int k = 0; k < 8; k++) { ulonglong2 t = __ldg(v + k); x[2 * k] = t.x; x[2 * k + 1] = t.y; }
+}
+__device__ __forceinline__ void row_fwd8(u64 (&x)[16], u64 *sm, const RowGeom &G, const ModC &M) {
+    fwd4(x, M.psi, G.baseA(), M.q, M.qinv, M.q2);
+    row_AtoB(x, sm, G);
+    fwd4(x, M.psi, G.baseB(), M.q, M.qinv, M.q2);
+}
+// in: layout B'; out: layout A'
+__device__ __forceinline__ void row_inv8(u64 (&x)[16], u64 *sm, const RowGeom &G, const ModC &M) {
+    inv4(x, M.psi_inv, G.baseB(), M.q, M.qinv, M.q2);
+    row_BtoA(x, sm, G);
+    inv4(x, M.psi_inv, G.baseA(), M.q, M.qinv, M.q2);
+}
+
+// ---- column-kernel tile geometry ---------------------------------------------------------
+// 256 threads; thread (cc = tid&15, pg = tid>>4) works on column c = 16*tile + cc.
+// layout A : slot k <-> row pg + 16k ;  layout B : slot k <-> row 16pg + k.
+// Both layouts are coalesced in global memory (16 lanes x 8 B along a row).
+struct ColGeom {
+    u32 cc, pg, c;
+    __device__ __forceinline__ ColGeom(u32 tile) {
+        u32 tid = threadIdx.x;
+        cc = tid & 15; pg = tid >> 4; c = tile * 16 + cc;
+    }
+    __device__ __forceinline__ u32 gA(int k) const { return (pg + 16 * k) * 256 + c; }
+    __device__ __forceinline__ u32 gB(int k) const { return (16 * pg + k) * 256 + c; }
+    __device__ __forceinline__ u32 sA(int k) const { return (pg + 16 * k) * 16 + cc; }
+    __device__ __forceinline__ u32 sB(int k) const { return (16 * pg + k) * 16 + cc; }
+};
+__device__ __forceinline__ void col_AtoB(u64 (&x)[16], u64 *sm, const ColGeom &G) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) sm[G.sA(k)] = x[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; k++) x[k] = sm[G.sB(k)];
+    __syncthreads();
+}
+__device__ __forceinline__ void col_BtoA(u64 (&x)[16], u64 *sm, const ColGeom &G) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) sm[G.sB(k)] = x[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; k++) x[k] = sm[G.sA(k)];
+    __syncthreads();
+}
+// in: layout A, out: layout B
+__device__ __forceinline__ void col_fwd8(u64 (&x)[16], u64 *sm, const ColGeom &G, const ModC &M) {
+    fwd4(x, M.psi, 1, M.q, M.qinv, M.q2);
+    col_AtoB(x, sm, G);
+    fwd4(x, M.psi, 16 + G.pg, M.q, M.qinv, M.q2);
+}
+// in: layout B, out: layout A
+__device__ __forceinline__ void col_inv8(u64 (&x)[16], u64 *sm, const ColGeom &G, const ModC &M) {
+    inv4(x, M.psi_inv, 16 + G.pg, M.q, M.qinv, M.q2);
+    col_BtoA(x, sm, G);
+    inv4(x, M.psi_inv, 1, M.q, M.qinv, M.q2);
+}
+
+// PermuteNTTIndex computed on the fly (L:ring/ring_automorphism.go:31-44):
+// index_g[i] = brev(((g * (2*brev(i)+1)) mod 2N - 1) / 2)
+__device__ __forceinline__ u32 brev16(u32 x) { return __brev(x) >> 16; }
+__device__ __forceinline__ u32 perm_index(u32 i, u32 g) {
+    u32 t = (g * (2u * brev16(i) + 1u)) & (2u * HEC_N - 1u);
+    return brev16((t - 1u) >> 1);
+}

@@ -1,0 +1,99 @@
+// hec_host.cuh -- host-side ring constants, context and handle types of libhec.
+// Tables follow the reference's Lattigo fork: primitive-root choice and psi tables
+// L:ring/ring.go:118-200, L:ring/utils.go:69-90; rescale / mod-down / mod-up constants
+// L:ring/ring.go:63-117, L:ring/ring_basis_extension.go:43-145,482-538.
+#pragma once
+#include <cuda_runtime.h>
+#include <map>
+#include <string>
+#include <vector>
+#include "hec_kernels.cuh"
+#include "../../include/hec.h"
+
+typedef unsigned __int128 u128;
+
+namespace hec {
+
+inline u64 mulmod(u64 a, u64 b, u64 q) { return (u64)(((u128)a * b) % q); }
+inline u64 powmod(u64 b, u64 e, u64 q) {
+    u64 r = 1 % q;
+    b %= q;
+    for (; e; e >>= 1) { if (e & 1) r = mulmod(r, b, q); b = mulmod(b, b, q); }
+    return r;
+}
+inline u64 invmod(u64 a, u64 q) { return powmod(a % q, q - 2, q); } // q prime
+inline u64 mform(u64 a, u64 q) { return (u64)((((u128)(a % q)) << 64) % q); }
+inline u32 bitrev16(u32 x) {
+    u32 r = 0;
+    for (int i = 0; i < 16; i++) r |= ((x >> i) & 1u) << (15 - i);
+    return r;
+}
+
+struct HostMod {
+    u64 q = 0, qinv = 0, ninv = 0, rmod = 0, gen = 0;
+    std::vector<u64> psi, psi_inv; // Montgomery form, bit-reversed
+};
+void build_mod(HostMod &m, u64 q);
+
+// tables of one exact basis extension  S = {s_0..s_{n-1}}  ->  any target modulus
+struct ModupTab {
+    int n = 0;
+    std::vector<int> smod;               // source modulus indices
+    std::vector<u64> qib;                // [n]
+    std::vector<std::vector<u64>> qisp;  // [target][n]
+    std::vector<std::vector<u64>> qpjinv; // [target][n+1]
+};
+
+struct SwKey {
+    u64 *buf = nullptr; // [ndig][2][Lk + nP][N], Montgomery
+    int ndig = 0, Lk = 0;
+};
+
+} // namespace hec
+
+struct hec_ct {
+    u64 *buf = nullptr; // [2][alloc][N]
+    int alloc = 0, level = 0;
+    double scale = 0;
+    bool owned = true;
+    u64 *limb(int c, int i) const { return buf + ((size_t)c * alloc + i) * HEC_N; }
+};
+struct hec_pt {
+    u64 *buf = nullptr; // [level+1][N], Montgomery form (pt * R mod q)
+    int level = 0;
+    double scale = 0;
+};
+
+struct hec_ctx {
+    int device = 0, nQ = 0, nP = 0, alpha = 0, beta_full = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<hec::HostMod> hm; // Q then P
+    ModC *dmods = nullptr;
+    u64 *dtables = nullptr;
+    std::vector<std::vector<u64>> resc; // resc[L][i] = MForm(q_i - q_L^-1 mod q_i)
+    std::vector<u64> negpinv;           // q_i - MForm(P^-1 mod q_i)
+    hec::ModupTab pq;                   // P -> Q
+    std::vector<int> xalpha;
+    std::vector<std::vector<hec::ModupTab>> dec; // dec[d][nd]
+    std::map<u64, hec::SwKey> keys;
+    // scratch arena for the generic ops (stream-ordered reuse)
+    u64 *arena = nullptr;
+    size_t arena_limbs = 0, arena_top = 0;
+    uint64_t launches = 0;
+    std::string err;
+
+    int modQ(int i) const { return i; }
+    int modP(int j) const { return nQ + j; }
+    u64 q(int mod) const { return hm[mod].q; }
+    u64 *scratch(size_t limbs);
+    void scratch_reset() { arena_top = 0; }
+    int fail(int code, const std::string &msg) { err = msg; return code; }
+};
+
+#define HEC_CUDA(ctx, call)                                                                        \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return (ctx)->fail(HEC_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));    \
+    } while (0)

@@ -1,0 +1,375 @@
+// hec_kernels.cuh -- all CUDA kernels of libhec (sm_100a).
+//
+// Two families:
+//  (1) generic per-limb kernels (NTT passes, element-wise ops, basis extension) from which
+//      the op-level evaluator (any level / alpha / beta) is composed;
+//  (2) fused kernels for the reference's conv_then_pack path (conv.go:522-546, 266-300) at
+//      level 1 -> 0 with one special prime: 3 kernels for Stage A, 5 per pack-tree level.
+// Reference routines each kernel covers are cited at the kernel.
+#pragma once
+#include "hec_dev.cuh"
+
+// =========================================================================================
+// (1) generic kernels
+// =========================================================================================
+#define HEC_MAXJOBS 64
+struct LimbJob { const u64 *in; u64 *out; int mod; int pad; };
+struct NttJobs { LimbJob j[HEC_MAXJOBS]; };
+
+// forward NTT = k_col_fwd then k_row_fwd;  inverse = k_row_inv then k_col_inv
+// (ring.NTT / ring.InvNTT, L:ring/ring_ntt.go:74-626).  grid = (16, njobs).
+__global__ void __launch_bounds__(HEC_THREADS) k_col_fwd(NttJobs J, const ModC *__restrict__ mods) {
+    __shared__ u64 sm[HEC_TILE];
+    const LimbJob job = J.j[blockIdx.y];
+    const ModC M = mods[job.mod];
+    ColGeom G(blockIdx.x);
+    u64 x[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) x[k] = job.in[G.gA(k)];
+    col_fwd8(x, sm, G, M);
+#pragma unroll
+    for (int k = 0; k < 16; k++) job.out[G.gB(k)] = x[k];
+}
+__global__ void __launch_bounds__(HEC_THREADS) k_row_fwd(NttJobs J, const ModC *__restrict__ mods) {
+    __shared__ u64 sm[16 * HEC_ROW_PITCH];
+    const LimbJob job = J.j[blockIdx.y];
+    const ModC M = mods[job.mod];
+    RowGeom G(blockIdx.x);
+    u64 x[16];
+    row_loadA(x, job.in, G);
+    row_fwd8(x, sm, G, M);
+    row_BtoA(x, sm, G);
+#pragma unroll
+    for (int k = 0; k < 16; k++) x[k] = canon4(x[k], M.q, M.q2);
+    row_storeA(x, job.out, G);
+}
+__global__ void __launch_bounds__(HEC_THREADS) k_row_inv(NttJobs J, const ModC *__restrict__ mods) {
+    __shared__ u64 sm[16 * HEC_ROW_PITCH];
+    const LimbJob job = J.j[blockIdx.y];
+    const ModC M = mods[job.mod];
+    RowGeom G(blockIdx.x);
+    u64 x[16];
+    row_loadA(x, job.in, G);
+    row_AtoB(x, sm, G);
+    row_inv8(x, sm, G, M);
+    row_storeA(x, job.out, G);
+}
+__global__ void __launch_bounds__(HEC_THREADS) k_col_inv(NttJobs J, const ModC *__restrict__ mods) {
+    __shared__ u64 sm[HEC_TILE];
+    const LimbJob job = J.j[blockIdx.y];
+    const ModC M = mods[job.mod];
+    ColGeom G(blockIdx.x);
+    u64 x[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) x[k] = job.in[G.gB(k)];
+    col_inv8(x, sm, G, M);
+#pragma unroll
+    for (int k = 0; k < 16; k++) job.out[G.gA(k)] = mred(x[k], M.ninv, M.q, M.qinv);
+}
+
+// ---- element-wise ------------------------------------------------------------------------
+#define HEC_EWJOBS 48
+struct EwJob { const u64 *a; const u64 *b; u64 *out; int mod; u32 g; u64 s0; u64 s1; };
+struct EwJobs { EwJob j[HEC_EWJOBS]; };
+enum {
+    EW_MULMONT = 0, // out = a * b * R^-1        (MulCoeffsMontgomery; b in Montgomery form)
+    EW_MULSCALAR,   // out = a * s0 * R^-1        (MultByConst; s0 = MForm(k))
+    EW_ADD,         // out = a + b                (AddLvl)
+    EW_SUB,         // out = a - b                (SubLvl)
+    EW_ADD_MONT,    // out = a + b*R^-1           (Add(ct, pt) with pt stored in Montgomery form)
+    EW_TOMONT,      // out = a * s0 * R^-1, s0 = R^2 mod q   (MFormLvl)
+    EW_REDUCE_ADD,  // out = (a mod q) + s0       (a < 2^64 from another modulus; rescale/digit lift)
+    EW_CENTER,      // out = cred(a + s0)         (rescale: + (q_L-1)/2 mod q_L)
+    EW_SUBMUL,      // out = (a + 2q - b) * s0 * R^-1, a < 4q lazy, b canonical  (rescale / mod-down combine)
+    EW_MAC,         // out = out + a * b * R^-1   (key inner product, canonical accumulator)
+    EW_PERMUTE,     // out[i] = a[index_g[i]]     (PermuteNTTWithIndexLvl)
+    EW_COPY
+};
+template <int OP>
+__global__ void __launch_bounds__(256) k_ew(EwJobs J, const ModC *__restrict__ mods) {
+    const EwJob job = J.j[blockIdx.y];
+    const u64 q = mods[job.mod].q, qinv = mods[job.mod].qinv, rmod = mods[job.mod].rmod;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < HEC_N; i += gridDim.x * blockDim.x) {
+        u64 r;
+        if (OP == EW_MULMONT) r = mred(job.a[i], job.b[i], q, qinv);
+        else if (OP == EW_MULSCALAR || OP == EW_TOMONT) r = mred(job.a[i], job.s0, q, qinv);
+        else if (OP == EW_ADD) r = addmod(job.a[i], job.b[i], q);
+        else if (OP == EW_SUB) r = submod(job.a[i], job.b[i], q);
+        else if (OP == EW_ADD_MONT) r = addmod(job.a[i], mred(job.b[i], 1ull, q, qinv), q);
+        else if (OP == EW_REDUCE_ADD) r = addmod(mred(job.a[i], rmod, q, qinv), job.s0, q);
+        else if (OP == EW_CENTER) r = cred(job.a[i] + job.s0, q);
+        else if (OP == EW_SUBMUL) r = mred(job.a[i] + 2 * q - job.b[i], job.s0, q, qinv);
+        else if (OP == EW_MAC) r = addmod(job.out[i], mred(job.a[i], job.b[i], q, qinv), q);
+        else if (OP == EW_PERMUTE) r = job.a[perm_index(i, job.g)];
+        else r = job.a[i];
+        job.out[i] = r;
+    }
+}
+
+// ---- exact basis extension (modUpExact / reconstructRNS / multSum,
+// L:ring/ring_basis_extension.go:438-457,670-779).  One job per target limb. -------------
+#define HEC_MAXA 5
+#define HEC_MUJOBS 12
+struct ModupJob {
+    const u64 *src[HEC_MAXA]; // coefficient-domain source limbs (any representative, < 2^64)
+    int smod[HEC_MAXA];
+    u64 qib[HEC_MAXA];        // MForm((Q_d/q_i)^-1 mod q_i)
+    u64 qisp[HEC_MAXA];       // MForm(Q_d/q_i mod p_t) for this target
+    u64 qpjinv[HEC_MAXA + 1]; // -v*Q_d mod p_t
+    u64 *dst;
+    int tmod, n;
+};
+struct ModupJobs { ModupJob j[HEC_MUJOBS]; };
+__global__ void __launch_bounds__(256) k_modup(ModupJobs J, const ModC *__restrict__ mods) {
+    const ModupJob &job = J.j[blockIdx.y];
+    const u64 pt = mods[job.tmod].q, ptinv = mods[job.tmod].qinv;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < HEC_N; i += gridDim.x * blockDim.x) {
+        double vi = 0.0;
+        u64 acc = 0;
+        for (int s = 0; s < job.n; s++) {
+            const u64 qs = mods[job.smod[s]].q;
+            u64 y = mred(job.src[s][i], job.qib[s], qs, mods[job.smod[s]].qinv);
+            // v = (uint64) sum_i float64(y_i)/float64(q_i): IEEE double, sequential, no FMA
+            vi = __dadd_rn(vi, __ddiv_rn(__ull2double_rn(y), __ull2double_rn(qs)));
+            acc = addmod(acc, mred(y, job.qisp[s], pt, ptinv), pt);
+        }
+        u64 v = (u64)__double2ull_rz(vi);
+        job.dst[i] = addmod(acc, job.qpjinv[v], pt);
+    }
+}
+
+// =========================================================================================
+// (2) fused conv_then_pack kernels
+// =========================================================================================
+// ---- Stage A: for every active output channel i and poly c (conv.go:525-531):
+//   MulNew(ct_in, pl_ker[i])   L:ckks/evaluator.go:1360-1444 (pt branch)
+//   SetScale -> MultByConst    L:ckks/evaluator.go:782-863 (constants from the host)
+//            -> Rescale -> divRoundByLastModulusNTT   L:ring/ring_scaling.go:442-513
+struct ConvA {
+    const u64 *const *ctin; // [M] -> [2 polys][2 limbs][N]
+    const u64 *const *ptk;  // [B] -> [2 limbs][N], Montgomery form
+    u64 *w1, *w2;           // [M*na*2][N] scratch
+    u64 *xout;              // [M*na][2][N] level-0 ciphertexts
+    int na, norm, mq0, mq1;
+    u64 k0m, k1m;           // MForm(c_i) of the MultByConst constant
+    u64 half1;              // (q1-1)>>1
+    u64 hneg0;              // q0 - (half1 mod q0)
+    u64 resc0;              // MForm(q0 - q1^-1 mod q0)  (RescaleParams)
+};
+struct AJob {
+    int c, a, m;
+    __device__ __forceinline__ AJob(int job, int na) { c = job & 1; a = (job >> 1) % na; m = (job >> 1) / na; }
+};
+// A1: limb q1:  (ct*pt*k1) -> inverse stages t = 1..128
+__global__ void __launch_bounds__(HEC_THREADS) k_convA1(ConvA P, const ModC *__restrict__ mods) {
+    __shared__ u64 sm[16 * HEC_ROW_PITCH];
+    const AJob J(blockIdx.y, P.na);
+    const ModC M = mods[P.mq1];
+    RowGeom G(blockIdx.x);
+    const u64 *ct = P.ctin[J.m] + (size_t)(J.c * 2 + 1) * HEC_N;
+    const u64 *pt = P.ptk[J.a * P.norm] + HEC_N;
+    u64 x[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        u32 i = G.gbase + 16 * k;
+        x[k] = mred(mred(ct[i], __ldg(pt + i), M.q, M.qinv), P.k1m, M.q, M.qinv);
+    }
+    row_AtoB(x, sm, G);
+    row_inv8(x, sm, G, M);
+    row_storeA(x, P.w1 + (size_t)blockIdx.y * HEC_N, G);
+}
+// A2: finish InvNTT_q1, centre, lift into q0, forward stages m = 1..128 under q0
+__global__ void __launch_bounds__(HEC_THREADS) k_convA2(ConvA P, const ModC *__restrict__ mods) {
+    __shared__ u64 sm[HEC_TILE];
+    const ModC M1 = mods[P.mq1];
+    const ModC M0 = mods[P.mq0];
+    ColGeom G(blockIdx.x);
+    const u64 *in = P.w1 + (size_t)blockIdx.y * HEC_N;
+    u64 *out = P.w2 + (size_t)blockIdx.y * HEC_N;
+    u64 x[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) x[k] = in[G.gB(k)];
+    col_inv8(x, sm, G, M1);
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        u64 t = mred(x[k], M1.ninv, M1.q, M1.qinv);        // InvNTT final pass, canonical
+        t = cred(t + P.half1, M1.q);                        // + (q1-1)/2 mod q1
+        x[k] = mred(t, M0.rmod, M0.q, M0.qinv) + P.hneg0;   // (t mod q0) - half  in [0,2q0)
+    }
+    col_fwd8(x, sm, G, M0);
+#pragma unroll
+    for (int k = 0; k < 16; k++) out[G.gB(k)] = x[k];
+}
+// A3: finish NTT_q0, combine with limb q0 of ct*pt*k0:  out = (p0 - u) * q1^-1
+__global__ void __launch_bounds__(HEC_THREADS) k_convA3(ConvA P, const ModC *__restrict__ mods) {
+    __shared__ u64 sm[16 * HEC_ROW_PITCH];
+    const AJob J(blockIdx.y, P.na);
+    const ModC M = mods[P.mq0];
+    RowGeom G(blockIdx.x);
+    const u64 *ct = P.ctin[J.m] + (size_t)(J.c * 2) * HEC_N;
+    const u64 *pt = P.ptk[J.a * P.norm];
+    u64 x[16];
+    row_loadA(x, P.w2 + (size_t)blockIdx.y * HEC_N, G);
+    row_fwd8(x, sm, G, M);
+    row_BtoA(x, sm, G);
+    u64 *out = P.xout + (size_t)blockIdx.y * HEC_N; // ((m*na + a)*2 + c) == job
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        u32 i = G.gbase + 16 * k;
+        u64 v = mred(mred(ct[i], __ldg(pt + i), M.q, M.qinv), P.k0m, M.q, M.qinv);
+        out[i] = mred(x[k] + M.q2 - v, P.resc0, M.q, M.qinv);
+    }
+}
+
+// ---- Stage B: one level of pack_ctxts (conv.go:286-297).  For butterfly (a = ct[i], b = ct[i+step]):
+//   tmp1 = b * X^step ; tmp2 = a - tmp1 ; tmp1 = a + tmp1 ; tmp2 = RotateGal(tmp2, 2^j+1) ; out = tmp1 + tmp2
+// RotateGal -> permuteNTT (L:ckks/evaluator.go:1575-1597) -> SwitchKeysInPlace
+// (L:rlwe/keyswitch.go:72-225; level 0, alpha = 1, beta = 1: single-limb digit = copy path)
+// -> ModDownSplitNTTPQ (L:ring/ring_basis_extension.go:247-291) -> + c0 -> PermuteNTTWithIndexLvl.
+struct ConvB {
+    const u64 *xin;  // [M*n][2][N]
+    u64 *xout;       // [M*n/2][2][N]
+    const u64 *mono; // NTT(X^step) at q0, Montgomery form
+    const u64 *key;  // digit 0 of the switching key: [2][keyL][N], Montgomery
+    const u64 *bias; // Montgomery-form bias plaintext (only the last level), or null
+    u64 *w1, *w2, *w3, *w4;
+    int n, keyL, keyPoff, mq0, mp0;
+    u32 galEl;
+    u64 negpinv;     // q0 - MForm(P^-1 mod q0)   [A] test_run 0x4e5049
+    u64 qpj1;        // q0 - (p0 mod q0) = qpjInv[1]
+    double p0f;      // float64(p0)
+};
+struct BJob {
+    int c, u, m;
+    const u64 *a, *b;
+    __device__ __forceinline__ BJob(int job, bool has_c, const ConvB &P) {
+        int nb = P.n >> 1;
+        c = has_c ? (job & 1) : 0;
+        int bu = has_c ? (job >> 1) : job;
+        m = bu / nb; u = bu % nb;
+        a = P.xin + (size_t)(m * P.n + u) * 2 * HEC_N;
+        b = P.xin + (size_t)(m * P.n + u + nb) * 2 * HEC_N;
+    }
+};
+// B1: z = tmp2.c1 = a1 - b1*mono ; inverse stages t = 1..128 under q0      grid.y = M*nb
+__global__ void __launch_bounds__(HEC_THREADS) k_convB1(ConvB P, const ModC *__restrict__ mods) {
+    __shared__ u64 sm[16 * HEC_ROW_PITCH];
+    const BJob J(blockIdx.y, false, P);
+    const ModC M = mods[P.mq0];
+    RowGeom G(blockIdx.x);
+    u64 x[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        u32 i = G.gbase + 16 * k;
+        x[k] = submod(J.a[HEC_N + i], mred(J.b[HEC_N + i], __ldg(P.mono + i), M.q, M.qinv), M.q);
+    }
+    row_AtoB(x, sm, G);
+    row_inv8(x, sm, G, M);
+    row_storeA(x, P.w1 + (size_t)blockIdx.y * HEC_N, G);
+}
+// B2: finish InvNTT_q0 (canonical digit), copy-path lift into p0, forward stages m = 1..128 under p0
+__global__ void __launch_bounds__(HEC_THREADS) k_convB2(ConvB P, const ModC *__restrict__ mods) {
+    __shared__ u64 sm[HEC_TILE];
+    const ModC MQ = mods[P.mq0];
+    const ModC MP = mods[P.mp0];
+    ColGeom G(blockIdx.x);
+    const u64 *in = P.w1 + (size_t)blockIdx.y * HEC_N;
+    u64 *out = P.w2 + (size_t)blockIdx.y * HEC_N;
+    u64 x[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) x[k] = in[G.gB(k)];
+    col_inv8(x, sm, G, MQ);
+    const bool fits = MQ.q <= MP.q2; // digit residue < q0 must be < 4*p0 for the lazy forward
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        u64 c = mred(x[k], MQ.ninv, MQ.q, MQ.qinv);
+        x[k] = fits ? c : mred(c, MP.rmod, MP.q, MP.qinv);
+    }
+    col_fwd8(x, sm, G, MP);
+#pragma unroll
+    for (int k = 0; k < 16; k++) out[G.gB(k)] = x[k];
+}
+// B3: finish NTT_p0 of the digit, multiply by key[c] (P limb), inverse stages t = 1..128 under p0
+//     grid.y = M*nb*2
+__global__ void __launch_bounds__(HEC_THREADS) k_convB3(ConvB P, const ModC *__restrict__ mods) {
+    __shared__ u64 sm[16 * HEC_ROW_PITCH];
+    const BJob J(blockIdx.y, true, P);
+    const ModC M = mods[P.mp0];
+    RowGeom G(blockIdx.x);
+    u64 x[16], kk[16];
+    row_loadA(x, P.w2 + (size_t)(blockIdx.y >> 1) * HEC_N, G);
+    row_fwd8(x, sm, G, M);
+    row_loadB(kk, P.key + (size_t)(J.c * P.keyL + P.keyPoff) * HEC_N, G);
+#pragma unroll
+    for (int k = 0; k < 16; k++) x[k] = mred_lazy(x[k], kk[k], M.q, M.qinv);
+    row_inv8(x, sm, G, M);
+    row_storeA(x, P.w3 + (size_t)blockIdx.y * HEC_N, G);
+}
+// B4: finish InvNTTLazy_p0, exact basis extension P -> q0 (float64 overflow count v),
+//     forward stages m = 1..128 under q0                                   grid.y = M*nb*2
+__global__ void __launch_bounds__(HEC_THREADS) k_convB4(ConvB P, const ModC *__restrict__ mods) {
+    __shared__ u64 sm[HEC_TILE];
+    const ModC MP = mods[P.mp0];
+    const ModC MQ = mods[P.mq0];
+    ColGeom G(blockIdx.x);
+    const u64 *in = P.w3 + (size_t)blockIdx.y * HEC_N;
+    u64 *out = P.w4 + (size_t)blockIdx.y * HEC_N;
+    u64 x[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) x[k] = in[G.gB(k)];
+    col_inv8(x, sm, G, MP);
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        // y = MRed(e, qibMont) with qibMont = MForm(1): the canonical residue mod p0
+        u64 y = mred(x[k], MP.ninv, MP.q, MP.qinv);
+        double f = __ddiv_rn(__ull2double_rn(y), P.p0f);
+        u64 v = (u64)__double2ull_rz(__dadd_rn(0.0, f));
+        x[k] = mred(y, MQ.rmod, MQ.q, MQ.qinv) + (v ? P.qpj1 : 0ull); // in [0,2q0)
+    }
+    col_fwd8(x, sm, G, MQ);
+#pragma unroll
+    for (int k = 0; k < 16; k++) out[G.gB(k)] = x[k];
+}
+// B5: finish NTT_q0, mod-down combine with acc_Q = z*key[c] (Q limb), + tmp2.c0 (c = 0),
+//     apply sigma_g inside the 256-word block, add tmp1 (+ bias)           grid.y = M*nb*2
+__global__ void __launch_bounds__(HEC_THREADS) k_convB5(ConvB P, const ModC *__restrict__ mods) {
+    __shared__ u64 sm[16 * HEC_ROW_PITCH];
+    const BJob J(blockIdx.y, true, P);
+    const ModC M = mods[P.mq0];
+    RowGeom G(blockIdx.x);
+    u64 x[16], t1[16];
+    row_loadA(x, P.w4 + (size_t)blockIdx.y * HEC_N, G);
+    row_fwd8(x, sm, G, M);
+    row_BtoA(x, sm, G);
+    const u64 *kq = P.key + (size_t)(J.c * P.keyL) * HEC_N;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        u32 i = G.gbase + 16 * k;
+        u64 mono = __ldg(P.mono + i);
+        u64 a1 = J.a[HEC_N + i];
+        u64 m1 = mred(J.b[HEC_N + i], mono, M.q, M.qinv);
+        u64 z = submod(a1, m1, M.q);                                 // tmp2.c1
+        u64 accq = mred(z, __ldg(kq + i), M.q, M.qinv);              // MulCoeffsMontgomeryConstant + Reduce
+        u64 d = mred(x[k] + M.q2 - accq, P.negpinv, M.q, M.qinv);    // ModDownSplitNTTPQ combine
+        if (J.c == 0) {
+            u64 a0 = J.a[i];
+            u64 m0 = mred(J.b[i], mono, M.q, M.qinv);
+            d = addmod(d, submod(a0, m0, M.q), M.q);                 // + tmp2.c0  (AddLvl)
+            t1[k] = addmod(a0, m0, M.q);                             // tmp1.c0
+        } else {
+            t1[k] = addmod(a1, m1, M.q);                             // tmp1.c1
+        }
+        u32 e = G.p + 16 * k;
+        sm[G.sbase + e + (e >> 4)] = d;
+    }
+    __syncwarp();
+    u64 *out = P.xout + (size_t)blockIdx.y * HEC_N;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        u32 i = G.gbase + 16 * k;
+        u32 s = perm_index(i, P.galEl) & 255u;                       // sigma_g stays inside the block
+        u64 r = addmod(t1[k], sm[G.sbase + s + (s >> 4)], M.q);
+        if (P.bias != nullptr && J.c == 0) r = addmod(r, mred(__ldg(P.bias + i), 1ull, M.q, M.qinv), M.q);
+        out[i] = r;
+    }
+}

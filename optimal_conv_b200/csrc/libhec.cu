@@ -1,0 +1,3 @@
+// libhec.cu -- single translation unit of libhec.so (kernels are defined in headers).
+#include "hec.cu"
+#include "hec_conv.cu"

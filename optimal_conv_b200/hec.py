@@ -1,0 +1,355 @@
+"""ctypes binding of libhec.so -- the same C ABI (include/hec.h) a cgo shim binds.
+
+Thin by design: every method is one C-ABI call.  There is no CPU fallback: if the CUDA
+library is missing or no device is present, construction raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhec.so")
+
+u64p = C.POINTER(C.c_uint64)
+u64pp = C.POINTER(u64p)
+vp = C.c_void_p
+
+HEC_OK, HEC_E_INVAL, HEC_E_CUDA, HEC_E_LEVEL, HEC_E_NOKEY, HEC_E_SCALE, HEC_E_UNSUPPORTED, HEC_E_NOMEM = (
+    0, -1, -2, -3, -4, -5, -6, -7)
+CONV_FUSED, CONV_OPLEVEL = 0, 1
+
+# every symbol include/hec.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "hec_version", "hec_ctx_create", "hec_ctx_destroy", "hec_last_error", "hec_sync", "hec_timer_start",
+    "hec_timer_stop_ms", "hec_launch_count", "hec_pt_upload", "hec_pt_free", "hec_ct_upload", "hec_ct_download",
+    "hec_ct_copy_new", "hec_ct_level", "hec_ct_scale", "hec_ct_set_scale", "hec_ct_free", "hec_swk_upload",
+    "hec_swk_drop", "hec_mul_pt_new", "hec_mult_by_const", "hec_rescale", "hec_set_scale", "hec_add", "hec_add_new",
+    "hec_sub_new", "hec_add_pt", "hec_rotate_gal", "hec_rotate_new", "hec_rotate_hoisted", "hec_galois_for_rotation",
+    "hec_ntt", "hec_keyswitch", "hec_moddown", "hec_conv_then_pack", "hec_plan_create", "hec_plan_run",
+    "hec_plan_run_host", "hec_plan_profile", "hec_plan_destroy",
+]
+
+
+class HecError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libhec error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load libhec.so; fails loudly if it has not been built (python __graft_entry__.py build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'`" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    L.hec_version.restype = C.c_char_p
+    L.hec_ctx_create.argtypes = [C.POINTER(vp), C.c_int, u64p, C.c_int, u64p, C.c_int, C.c_int]
+    L.hec_ctx_destroy.argtypes = [vp]
+    L.hec_ctx_destroy.restype = None
+    L.hec_last_error.argtypes = [vp]
+    L.hec_last_error.restype = C.c_char_p
+    L.hec_sync.argtypes = [vp]
+    L.hec_timer_start.argtypes = [vp]
+    L.hec_timer_stop_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.hec_launch_count.argtypes = [vp]
+    L.hec_launch_count.restype = C.c_uint64
+    L.hec_pt_upload.argtypes = [vp, C.c_int, u64pp, C.c_double, C.POINTER(vp)]
+    L.hec_pt_free.argtypes = [vp, vp]
+    L.hec_pt_free.restype = None
+    L.hec_ct_upload.argtypes = [vp, C.c_int, u64pp, u64pp, C.c_double, C.POINTER(vp)]
+    L.hec_ct_download.argtypes = [vp, vp, u64pp, u64pp]
+    L.hec_ct_copy_new.argtypes = [vp, vp, C.POINTER(vp)]
+    L.hec_ct_level.argtypes = [vp]
+    L.hec_ct_scale.argtypes = [vp]
+    L.hec_ct_scale.restype = C.c_double
+    L.hec_ct_set_scale.argtypes = [vp, C.c_double]
+    L.hec_ct_set_scale.restype = None
+    L.hec_ct_free.argtypes = [vp, vp]
+    L.hec_ct_free.restype = None
+    L.hec_swk_upload.argtypes = [vp, C.c_uint64, C.c_int, u64pp]
+    L.hec_swk_drop.argtypes = [vp, C.c_uint64]
+    L.hec_mul_pt_new.argtypes = [vp, vp, vp, C.POINTER(vp)]
+    L.hec_mult_by_const.argtypes = [vp, vp, C.c_double]
+    L.hec_rescale.argtypes = [vp, vp, C.c_double]
+    L.hec_set_scale.argtypes = [vp, vp, C.c_double]
+    L.hec_add.argtypes = [vp, vp, vp, vp]
+    L.hec_add_new.argtypes = [vp, vp, vp, C.POINTER(vp)]
+    L.hec_sub_new.argtypes = [vp, vp, vp, C.POINTER(vp)]
+    L.hec_add_pt.argtypes = [vp, vp, vp]
+    L.hec_rotate_gal.argtypes = [vp, vp, C.c_uint64, vp]
+    L.hec_rotate_new.argtypes = [vp, vp, C.c_int, C.POINTER(vp)]
+    L.hec_rotate_hoisted.argtypes = [vp, vp, C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+    L.hec_galois_for_rotation.argtypes = [vp, C.c_int]
+    L.hec_galois_for_rotation.restype = C.c_uint64
+    L.hec_ntt.argtypes = [vp, C.c_int, C.c_int, u64p, u64p, C.c_int]
+    L.hec_keyswitch.argtypes = [vp, C.c_int, u64pp, C.c_uint64, u64pp, u64pp]
+    L.hec_moddown.argtypes = [vp, C.c_int, u64pp, u64pp, u64pp]
+    L.hec_conv_then_pack.argtypes = [vp, vp, C.POINTER(vp), C.c_int, C.c_int, C.c_double, C.POINTER(vp), vp, C.c_int,
+                                     C.POINTER(vp)]
+    L.hec_plan_create.argtypes = [vp, C.POINTER(vp), C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(vp), vp,
+                                  C.c_int, C.POINTER(vp)]
+    L.hec_plan_run.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    L.hec_plan_run_host.argtypes = [vp, u64pp, u64pp, u64pp, u64pp]
+    L.hec_plan_profile.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]
+    L.hec_plan_destroy.argtypes = [vp]
+    L.hec_plan_destroy.restype = None
+    _lib = L
+    return L
+
+
+def _rows(a):
+    """per-limb pointer array for a contiguous [L][N] uint64 array"""
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"] and a.ndim == 2
+    arr = (u64p * a.shape[0])()
+    for i in range(a.shape[0]):
+        arr[i] = a[i].ctypes.data_as(u64p)
+    return arr
+
+
+def _ptrs(addresses):
+    arr = (u64p * len(addresses))()
+    for i, x in enumerate(addresses):
+        arr[i] = C.cast(C.c_void_p(int(x)), u64p)
+    return arr
+
+
+class Plaintext:
+    def __init__(self, ctx, h):
+        self.ctx, self.h = ctx, h
+
+    def free(self):
+        if self.h:
+            self.ctx.L.hec_pt_free(self.ctx.h, self.h)
+            self.h = None
+
+
+class Ciphertext:
+    """ckks.Ciphertext on the device."""
+
+    def __init__(self, ctx, h):
+        self.ctx, self.h = ctx, h
+
+    @property
+    def level(self):
+        return self.ctx.L.hec_ct_level(self.h)
+
+    @property
+    def scale(self):
+        return self.ctx.L.hec_ct_scale(self.h)
+
+    def set_scale(self, s):
+        self.ctx.L.hec_ct_set_scale(self.h, s)
+
+    def download(self):
+        n = self.level + 1
+        c0 = np.empty((n, self.ctx.N), dtype=np.uint64)
+        c1 = np.empty((n, self.ctx.N), dtype=np.uint64)
+        self.ctx._chk(self.ctx.L.hec_ct_download(self.ctx.h, self.h, _rows(c0), _rows(c1)))
+        return c0, c1
+
+    def free(self):
+        if self.h:
+            self.ctx.L.hec_ct_free(self.ctx.h, self.h)
+            self.h = None
+
+
+class Context:
+    """One evaluator (ckks.NewEvaluator, main.go:430-441) bound to one GPU."""
+
+    def __init__(self, logN, Q, P, device=0):
+        self.L = lib()
+        self.logN, self.N, self.Q, self.P = logN, 1 << logN, list(Q), list(P)
+        q = np.array(self.Q, dtype=np.uint64)
+        p = np.array(self.P if self.P else [0], dtype=np.uint64)
+        h = vp()
+        rc = self.L.hec_ctx_create(C.byref(h), logN, q.ctypes.data_as(u64p), len(self.Q), p.ctypes.data_as(u64p),
+                                   len(self.P), device)
+        if rc != 0:
+            raise HecError(rc, "hec_ctx_create failed (no CUDA device or unsupported parameters)")
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.L.hec_ctx_destroy(self.h)
+            self.h = None
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise HecError(rc, self.L.hec_last_error(self.h).decode())
+
+    def sync(self):
+        self._chk(self.L.hec_sync(self.h))
+
+    def timer_start(self):
+        self._chk(self.L.hec_timer_start(self.h))
+
+    def timer_stop_ms(self):
+        ms = C.c_float()
+        self._chk(self.L.hec_timer_stop_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        return int(self.L.hec_launch_count(self.h))
+
+    # ---- uploads ----
+    def upload_pt(self, limbs, scale):
+        limbs = np.ascontiguousarray(limbs, dtype=np.uint64)
+        h = vp()
+        self._chk(self.L.hec_pt_upload(self.h, limbs.shape[0] - 1, _rows(limbs), scale, C.byref(h)))
+        return Plaintext(self, h)
+
+    def upload_ct(self, c0, c1, scale):
+        c0, c1 = np.ascontiguousarray(c0, dtype=np.uint64), np.ascontiguousarray(c1, dtype=np.uint64)
+        h = vp()
+        self._chk(self.L.hec_ct_upload(self.h, c0.shape[0] - 1, _rows(c0), _rows(c1), scale, C.byref(h)))
+        return Ciphertext(self, h)
+
+    def upload_swk(self, galEl, swk, max_level):
+        """swk: [digits][2][nQ+nP][N] as Lattigo stores it."""
+        swk = np.ascontiguousarray(swk, dtype=np.uint64)
+        flat = swk.reshape(-1, self.N)
+        self._chk(self.L.hec_swk_upload(self.h, galEl, max_level, _rows(flat)))
+
+    # ---- evaluator ops (ckks.Evaluator subset) ----
+    def MulNew(self, ct, pt):
+        h = vp()
+        self._chk(self.L.hec_mul_pt_new(self.h, ct.h, pt.h, C.byref(h)))
+        return Ciphertext(self, h)
+
+    def MultByConst(self, ct, c):
+        self._chk(self.L.hec_mult_by_const(self.h, ct.h, c))
+
+    def Rescale(self, ct, min_scale):
+        self._chk(self.L.hec_rescale(self.h, ct.h, min_scale))
+
+    def SetScale(self, ct, scale):
+        self._chk(self.L.hec_set_scale(self.h, ct.h, scale))
+
+    def Add(self, a, b, out):
+        self._chk(self.L.hec_add(self.h, a.h, b.h, out.h))
+
+    def AddNew(self, a, b):
+        h = vp()
+        self._chk(self.L.hec_add_new(self.h, a.h, b.h, C.byref(h)))
+        return Ciphertext(self, h)
+
+    def SubNew(self, a, b):
+        h = vp()
+        self._chk(self.L.hec_sub_new(self.h, a.h, b.h, C.byref(h)))
+        return Ciphertext(self, h)
+
+    def AddPt(self, ct, pt):
+        self._chk(self.L.hec_add_pt(self.h, ct.h, pt.h))
+
+    def CopyNew(self, ct):
+        h = vp()
+        self._chk(self.L.hec_ct_copy_new(self.h, ct.h, C.byref(h)))
+        return Ciphertext(self, h)
+
+    def RotateGal(self, ct, galEl, out):
+        self._chk(self.L.hec_rotate_gal(self.h, ct.h, galEl, out.h))
+
+    def RotateNew(self, ct, k):
+        h = vp()
+        self._chk(self.L.hec_rotate_new(self.h, ct.h, k, C.byref(h)))
+        return Ciphertext(self, h)
+
+    def RotateHoisted(self, ct, rotations):
+        n = len(rotations)
+        rots = (C.c_int * n)(*rotations)
+        outs = (vp * n)()
+        self._chk(self.L.hec_rotate_hoisted(self.h, ct.h, rots, n, outs))
+        return {r: Ciphertext(self, vp(outs[i])) for i, r in enumerate(rotations)}
+
+    def galois_for_rotation(self, k):
+        return int(self.L.hec_galois_for_rotation(self.h, k))
+
+    # ---- ring level ----
+    def ntt(self, a, limb, ring=0, inverse=False):
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        out = np.empty_like(a)
+        self._chk(self.L.hec_ntt(self.h, ring, limb, a.ctypes.data_as(u64p), out.ctypes.data_as(u64p), int(inverse)))
+        return out
+
+    def keyswitch(self, c1, galEl):
+        c1 = np.ascontiguousarray(c1, dtype=np.uint64)
+        d0, d1 = np.empty_like(c1), np.empty_like(c1)
+        self._chk(self.L.hec_keyswitch(self.h, c1.shape[0] - 1, _rows(c1), galEl, _rows(d0), _rows(d1)))
+        return d0, d1
+
+    def moddown(self, accQ, accP):
+        accQ, accP = np.ascontiguousarray(accQ, dtype=np.uint64), np.ascontiguousarray(accP, dtype=np.uint64)
+        out = np.empty_like(accQ)
+        self._chk(self.L.hec_moddown(self.h, accQ.shape[0] - 1, _rows(accQ), _rows(accP), _rows(out)))
+        return out
+
+    # ---- conv path ----
+    def conv_then_pack(self, ct_in, pt_ker, norm, out_scale, pt_idx, pt_bias=None, flags=CONV_FUSED):
+        """conv_then_pack (conv.go:522-546) [+ bias Add, eval.go:258]."""
+        B = len(pt_ker)
+        ker = (vp * B)(*[(p.h if p is not None else None) for p in pt_ker])
+        idx = (vp * len(pt_idx))(*[(p.h if p is not None else None) for p in pt_idx])
+        h = vp()
+        self._chk(self.L.hec_conv_then_pack(self.h, ct_in.h, ker, B, norm, out_scale, idx,
+                                            pt_bias.h if pt_bias is not None else None, flags, C.byref(h)))
+        return Ciphertext(self, h)
+
+    def plan(self, pt_ker, norm, in_scale, out_scale, pt_idx, pt_bias, batch):
+        return Plan(self, pt_ker, norm, in_scale, out_scale, pt_idx, pt_bias, batch)
+
+
+class Plan:
+    """A prepared evalConv_BN over `batch` independent ciphertexts (CUDA graph)."""
+
+    def __init__(self, ctx, pt_ker, norm, in_scale, out_scale, pt_idx, pt_bias, batch):
+        self.ctx, self.batch = ctx, batch
+        B = len(pt_ker)
+        ker = (vp * B)(*[(p.h if p is not None else None) for p in pt_ker])
+        idx = (vp * len(pt_idx))(*[(p.h if p is not None else None) for p in pt_idx])
+        h = vp()
+        ctx._chk(ctx.L.hec_plan_create(ctx.h, ker, B, norm, in_scale, out_scale, idx,
+                                       pt_bias.h if pt_bias is not None else None, batch, C.byref(h)))
+        self.h = h
+        self._keep = (pt_ker, pt_idx, pt_bias)
+        self._outs = (vp * batch)()
+
+    def run(self, cts):
+        """device-resident run; returns `batch` level-0 ciphertext handles (reused across runs)."""
+        ins = (vp * self.batch)(*[c.h for c in cts])
+        self.ctx._chk(self.ctx.L.hec_plan_run(self.h, ins, self._outs))
+        return [Ciphertext(self.ctx, vp(self._outs[i])) for i in range(self.batch)]
+
+    def run_host(self, in_c0, in_c1, out_c0, out_c1):
+        """host-buffer run.  in_c0/in_c1: [batch][2][N] uint64 arrays (pinned for async copies);
+        out_c0/out_c1: [batch][N].  Accepts numpy arrays or objects with data_ptr() (torch)."""
+        N = self.ctx.N
+
+        def base(a):
+            return a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data
+
+        b0, b1, o0, o1 = base(in_c0), base(in_c1), base(out_c0), base(out_c1)
+        pin0 = _ptrs([b0 + (m * 2 + i) * N * 8 for m in range(self.batch) for i in range(2)])
+        pin1 = _ptrs([b1 + (m * 2 + i) * N * 8 for m in range(self.batch) for i in range(2)])
+        po0 = _ptrs([o0 + m * N * 8 for m in range(self.batch)])
+        po1 = _ptrs([o1 + m * N * 8 for m in range(self.batch)])
+        self.ctx._chk(self.ctx.L.hec_plan_run_host(self.h, pin0, pin1, po0, po1))
+
+    def profile(self, cts):
+        """[(kernel name, ms)] of one run with kernels launched one by one."""
+        ins = (vp * self.batch)(*[c.h for c in cts])
+        ms = (C.c_float * 256)()
+        n = C.c_int()
+        self.ctx._chk(self.ctx.L.hec_plan_profile(self.h, ins, ms, 256, C.byref(n)))
+        names = ["A1", "A2", "A3"] + ["B%d" % (i % 5 + 1) for i in range(max(0, n.value - 3))]
+        return [(names[i], ms[i]) for i in range(n.value)]
+
+    def destroy(self):
+        if self.h:
+            self.ctx.L.hec_plan_destroy(self.h)
+            self.h = None

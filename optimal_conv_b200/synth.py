@@ -33,3 +33,31 @@ def uniform_mod(seed: int, n: int, q: int) -> np.ndarray:
 def uniform_limbs(seed: int, moduli, n: int) -> np.ndarray:
     """[len(moduli)][n] uniform canonical residues, one stream per limb."""
     return np.stack([uniform_mod(seed * 1000003 + 7919 * i, n, q) for i, q in enumerate(moduli)])
+
+
+def conv_workload(Q, P, logN, B, seed, n_ct=1):
+    """Seeded synthetic operands of one evalConv_BN hot interval:
+    n_ct level-1 input ciphertexts, B kernel plaintexts (level 1), a level-0 bias plaintext,
+    and rotation keys (uniform words read as NTT+Montgomery form) for the pack levels of B.
+    Returns a dict of numpy arrays; no GPU, no oracle."""
+    N = 1 << logN
+    q2 = list(Q[:2])
+    mods = list(Q) + list(P)
+    beta_full = (len(Q) + len(P) - 1) // len(P)
+    w = {"B": B, "N": N}
+    w["ct"] = [(uniform_limbs(seed * 31 + 2 * m, q2, N), uniform_limbs(seed * 31 + 2 * m + 1, q2, N))
+               for m in range(n_ct)]
+    w["pt_ker"] = np.stack([uniform_limbs(seed * 977 + 100 + i, q2, N) for i in range(B)])
+    w["bias"] = uniform_mod(seed * 131 + 7, N, Q[0])
+    keys = {}
+    step, log_step = B // 2, 0
+    while (1 << log_step) < max(step, 1):
+        log_step += 1
+    j = logN - log_step
+    while step >= 1:
+        keys[j - 1] = np.stack([np.stack([uniform_limbs(seed * 7919 + 1000 * j + 10 * d + k, mods, N)
+                                          for k in range(2)]) for d in range(beta_full)])
+        step //= 2
+        j += 1
+    w["keys"] = keys  # index i <-> galEl 2^(i+1)+1 (conv.go:255)
+    return w

@@ -1,0 +1,51 @@
+"""CPU: libhec.so loads, exports every symbol include/hec.h declares, and refuses to
+pretend there is a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "hec.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(hec_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    from optimal_conv_b200 import hec
+    assert declared_symbols() == sorted(hec.SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as g
+    g.build()
+    from optimal_conv_b200 import hec
+    L = ctypes.CDLL(hec.LIB_PATH)
+    for s in declared_symbols():
+        assert hasattr(L, s), s
+    L.hec_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in L.hec_version()
+    hec.lib()
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    from optimal_conv_b200 import hec, params as PR
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(hec.HecError) as e:
+        hec.Context(PR.LOGN, PR.Q_SET6[:2], PR.P_PACK)
+    assert e.value.code == hec.HEC_E_CUDA
+
+
+def test_product_path_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "optimal_conv_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.lower().replace("no oracle", ""), f

@@ -35,7 +35,9 @@ void build_mod(HostMod &m, u64 q) {
     for (int i = 0; i < 7; i++) inv *= 2 - q * inv; // Newton: q*inv = 1 mod 2^64
     m.qinv = inv;
     m.rmod = mform(1, q);
-    m.ninv = mform(invmod(N, q), q);
+    auto shoup = [q](u64 w) { return (u64)(((u128)w << 64) / q); };
+    m.ninv_w = invmod(N, q);
+    m.ninv_s = shoup(m.ninv_w);
     m.gen = primitive_root(q);
     u64 psi = powmod(m.gen, (q - 1) / (2 * N), q);
     u64 psi_i = invmod(psi, q);
@@ -44,8 +46,8 @@ void build_mod(HostMod &m, u64 q) {
     u64 a = 1, b = 1; // psi^j, psi^-j
     for (u32 j = 0; j < N; j++) {
         u32 r = bitrev16(j);
-        m.psi[r] = mform(a, q);
-        m.psi_inv[r] = mform(b, q);
+        m.psi[r] = make_ulonglong2(a, shoup(a));
+        m.psi_inv[r] = make_ulonglong2(b, shoup(b));
         a = mulmod(a, psi, q);
         b = mulmod(b, psi_i, q);
     }
@@ -200,16 +202,17 @@ extern "C" int hec_ctx_create(hec_ctx **out, int logN, const uint64_t *Q, int nQ
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
     size_t tw = (size_t)nm * 2 * HEC_N;
-    if (cudaMalloc(&c->dtables, tw * sizeof(u64)) != cudaSuccess) return bail(HEC_E_NOMEM);
+    if (cudaMalloc(&c->dtables, tw * sizeof(ulonglong2)) != cudaSuccess) return bail(HEC_E_NOMEM);
     if (cudaMalloc(&c->dmods, nm * sizeof(ModC)) != cudaSuccess) return bail(HEC_E_NOMEM);
     std::vector<ModC> mc(nm);
     for (int i = 0; i < nm; i++) {
-        u64 *psi = c->dtables + (size_t)i * 2 * HEC_N, *psi_inv = psi + HEC_N;
-        cudaMemcpy(psi, c->hm[i].psi.data(), HEC_N * sizeof(u64), cudaMemcpyHostToDevice);
-        cudaMemcpy(psi_inv, c->hm[i].psi_inv.data(), HEC_N * sizeof(u64), cudaMemcpyHostToDevice);
+        ulonglong2 *psi = c->dtables + (size_t)i * 2 * HEC_N, *psi_inv = psi + HEC_N;
+        cudaMemcpy(psi, c->hm[i].psi.data(), HEC_N * sizeof(ulonglong2), cudaMemcpyHostToDevice);
+        cudaMemcpy(psi_inv, c->hm[i].psi_inv.data(), HEC_N * sizeof(ulonglong2), cudaMemcpyHostToDevice);
         mc[i].q = c->hm[i].q; mc[i].qinv = c->hm[i].qinv; mc[i].q2 = 2 * c->hm[i].q;
-        mc[i].ninv = c->hm[i].ninv; mc[i].rmod = c->hm[i].rmod;
+        mc[i].rmod = c->hm[i].rmod; mc[i].ninv_w = c->hm[i].ninv_w; mc[i].ninv_s = c->hm[i].ninv_s;
         mc[i].psi = psi; mc[i].psi_inv = psi_inv;
+        mc[i].tight = c->hm[i].q >= (1ull << 58) ? 1 : 0; mc[i].pad = 0;
     }
     if (cudaMemcpy(c->dmods, mc.data(), nm * sizeof(ModC), cudaMemcpyHostToDevice) != cudaSuccess) return bail(HEC_E_CUDA);
     // RescaleParams (L:ring/ring.go:63-117)

@@ -106,7 +106,7 @@ static int plan_launch_all(hec_plan *p, const std::function<void()> &after = [] 
         after();
         k_convB2<<<g1, HEC_THREADS, 0, s>>>(b, c->dmods);
         after();
-        k_convB3<<<g2, HEC_THREADS, 0, s>>>(b, c->dmods);
+        k_convB3<<<g1, HEC_THREADS, HEC_B3_SMEM, s>>>(b, c->dmods);
         after();
         k_convB4<<<g2, HEC_THREADS, 0, s>>>(b, c->dmods);
         after();
@@ -226,6 +226,8 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
         p->pb.push_back(b);
     }
     p->launches_per_run = 3 + 5 * levels + ((levels == 0 && pt_bias) ? M : 0);
+    if (cudaFuncSetAttribute(k_convB3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEC_B3_SMEM) != cudaSuccess)
+        return bail(HEC_E_CUDA, "cudaFuncSetAttribute(k_convB3)");
     // ---- capture the kernel sequence in a CUDA graph ----
     cudaGraph_t graph = nullptr;
     if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return bail(HEC_E_CUDA, "begin capture");

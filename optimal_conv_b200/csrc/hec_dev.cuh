@@ -10,11 +10,16 @@
 // on a row kernel and the inverse always starts on one, which is what lets the fused
 // kernels chain  inverse -> pointwise -> forward  without leaving the tile.
 //
-// Arithmetic follows the Lattigo conventions the reference relies on:
-// Montgomery form with R = 2^64, twiddle tables NttPsi[brev(j)] = psi^j * R, natural-order
-// input and bit-reversed output.  Lazy ranges are ours (Harvey): forward values live in
-// [0,4q), inverse values in [0,2q); every value that leaves a kernel for the caller is
-// canonical, so results are bit-identical to the reference's canonical residues.
+// Conventions follow the Lattigo fork the reference relies on: psi is the
+// (q-1)/2N-th power of the smallest primitive root >= 3, tables are indexed NttPsi[brev(j)] =
+// psi^j, natural-order input and bit-reversed output; point-wise products use Montgomery form
+// with R = 2^64 exactly like MulCoeffsMontgomery.  How a residue class is represented
+// *inside* a transform is ours: twiddles are stored as Shoup pairs (w, floor(w*2^64/q)) --
+// the kernels are bound by the integer-multiply pipe (profiles/r01a), and a Shoup product is
+// 6 wide + 4 narrow multiplies against 10 + 3 for a Montgomery product -- and ranges are lazy
+// (forward: no correction at all for q < 2^58, a 4q correction every other stage otherwise;
+// inverse: [0,2q)).  Every value that leaves for the caller is canonical, so results are
+// bit-identical to the reference's canonical residues.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -32,10 +37,12 @@ typedef unsigned int u32;
 struct ModC {
     u64 q, qinv;      // q * qinv = 1 mod 2^64
     u64 q2;           // 2q
-    u64 ninv;         // N^-1 * R mod q
     u64 rmod;         // R mod q  (mred(x, rmod) = x mod q, canonical)
-    const u64 *psi;   // NttPsi  (Montgomery, bit-reversed)
-    const u64 *psi_inv;
+    u64 ninv_w, ninv_s; // N^-1 mod q and its Shoup companion
+    const ulonglong2 *psi;     // (psi^j, floor(psi^j * 2^64 / q)) at index brev(j)
+    const ulonglong2 *psi_inv; // same for psi^-j
+    int tight;        // q >= 2^58: forward transform needs range corrections
+    int pad;
 };
 
 // ---- scalar primitives -----------------------------------------------------------------
@@ -54,21 +61,26 @@ __device__ __forceinline__ u64 mred(u64 x, u64 y, u64 q, u64 qinv) {
 __device__ __forceinline__ u64 cred(u64 a, u64 q) { return a >= q ? a - q : a; }
 __device__ __forceinline__ u64 addmod(u64 a, u64 b, u64 q) { return cred(a + b, q); }
 __device__ __forceinline__ u64 submod(u64 a, u64 b, u64 q) { return cred(a + q - b, q); }
-// [0,4q) -> [0,q)
-__device__ __forceinline__ u64 canon4(u64 a, u64 q, u64 q2) { return cred(cred(a, q2), q); }
 
-// Cooley-Tukey butterfly, X,Y in [0,4q) -> [0,4q)
-__device__ __forceinline__ void ct_bfly(u64 &X, u64 &Y, u64 w, u64 q, u64 qinv, u64 q2) {
-    u64 x = cred(X, q2);
-    u64 t = mred_lazy(Y, w, q, qinv);
+// Shoup product: y * w mod q in [0,2q) for ANY y < 2^64, given ws = floor(w * 2^64 / q).
+__device__ __forceinline__ u64 shoup(u64 y, ulonglong2 w, u64 q) {
+    u64 qe = __umul64hi(y, w.y);
+    return y * w.x - qe * q;
+}
+// Cooley-Tukey butterfly.  FIX: X >= 4q is pulled back by 4q first (bounds in fwd4).
+template <bool FIX>
+__device__ __forceinline__ void ct_bfly(u64 &X, u64 &Y, ulonglong2 w, u64 q, u64 q2) {
+    u64 x = X;
+    if (FIX) x = cred(x, 2 * q2);
+    u64 t = shoup(Y, w, q);
     X = x + t;
     Y = x - t + q2;
 }
 // Gentleman-Sande butterfly, X,Y in [0,2q) -> [0,2q)
-__device__ __forceinline__ void gs_bfly(u64 &X, u64 &Y, u64 w, u64 q, u64 qinv, u64 q2) {
+__device__ __forceinline__ void gs_bfly(u64 &X, u64 &Y, ulonglong2 w, u64 q, u64 q2) {
     u64 u = X, v = Y;
     X = cred(u + v, q2);
-    Y = mred_lazy(u - v + q2, w, q, qinv);
+    Y = shoup(u - v + q2, w, q);
 }
 
 // Four forward stages on 16 register-resident coefficients.  The coefficient at slot k
@@ -76,31 +88,45 @@ __device__ __forceinline__ void gs_bfly(u64 &X, u64 &Y, u64 w, u64 q, u64 qinv, 
 // gi = k / (2d).  `base` encodes where the 16 coefficients sit in the limb:
 //   column kernel, rows p+16k : base = 1            column kernel, rows 16g+k : base = 16+g
 //   row kernel, words p+16k   : base = 256+b        row kernel, words 16p+k   : base = 4096+16b+p
-__device__ __forceinline__ void fwd4(u64 (&x)[16], const u64 *__restrict__ psi, u32 base, u64 q, u64 qinv, u64 q2) {
+// Ranges.  Each stage adds at most 2q to a value.  TIGHT = false (q < 2^58): no correction;
+// a 16-stage transform of inputs < 4q stays < 36q < 2^64.  TIGHT = true (q < 2^61): the first
+// and third stage pull X back below 4q, so values entering are < 8q and values leaving are
+// < 8q < 2^64 (the Y operand never needs it: shoup() accepts any 64-bit value).
+template <bool TIGHT>
+__device__ __forceinline__ void fwd4(u64 (&x)[16], const ulonglong2 *__restrict__ psi, u32 base, u64 q, u64 q2) {
 #pragma unroll
     for (int lg = 0; lg < 4; lg++) {
         const int d = 8 >> lg, ng = 1 << lg;
 #pragma unroll
         for (int gi = 0; gi < ng; gi++) {
-            u64 w = __ldg(psi + ng * base + gi);
+            ulonglong2 w = __ldg(psi + ng * base + gi);
 #pragma unroll
-            for (int k = 0; k < d; k++) ct_bfly(x[gi * 2 * d + k], x[gi * 2 * d + k + d], w, q, qinv, q2);
+            for (int k = 0; k < d; k++) {
+                if (TIGHT && (lg == 0 || lg == 2)) ct_bfly<true>(x[gi * 2 * d + k], x[gi * 2 * d + k + d], w, q, q2);
+                else ct_bfly<false>(x[gi * 2 * d + k], x[gi * 2 * d + k + d], w, q, q2);
+            }
         }
     }
 }
 // Four inverse stages (d = 1,2,4,8), same indexing with the psi_inv table.
-__device__ __forceinline__ void inv4(u64 (&x)[16], const u64 *__restrict__ psi_inv, u32 base, u64 q, u64 qinv, u64 q2) {
+__device__ __forceinline__ void inv4(u64 (&x)[16], const ulonglong2 *__restrict__ psi_inv, u32 base, u64 q, u64 q2) {
 #pragma unroll
     for (int lg = 3; lg >= 0; lg--) {
         const int d = 8 >> lg, ng = 1 << lg;
 #pragma unroll
         for (int gi = 0; gi < ng; gi++) {
-            u64 w = __ldg(psi_inv + ng * base + gi);
+            ulonglong2 w = __ldg(psi_inv + ng * base + gi);
 #pragma unroll
-            for (int k = 0; k < d; k++) gs_bfly(x[gi * 2 * d + k], x[gi * 2 * d + k + d], w, q, qinv, q2);
+            for (int k = 0; k < d; k++) gs_bfly(x[gi * 2 * d + k], x[gi * 2 * d + k + d], w, q, q2);
         }
     }
 }
+// final pass of InvNTT: x * N^-1, canonical
+__device__ __forceinline__ u64 inv_final(u64 x, const ModC &M) {
+    return cred(shoup(x, make_ulonglong2(M.ninv_w, M.ninv_s), M.q), M.q);
+}
+// any 64-bit representative -> canonical residue
+__device__ __forceinline__ u64 canon(u64 x, const ModC &M) { return mred(x, M.rmod, M.q, M.qinv); }
 
 // ---- row-kernel tile geometry ------------------------------------------------------------
 // 256 threads; thread (p = tid&15, bb = tid>>4) works on block b = 16*tile + bb.
@@ -150,16 +176,23 @@ __device__ __forceinline__ void row_loadB(u64 (&x)[16], const u64 *__restrict__ 
 #pragma unroll
     for (int k = 0; k < 8; k++) { ulonglong2 t = __ldg(v + k); x[2 * k] = t.x; x[2 * k + 1] = t.y; }
 }
+// in: layout A' (values < 4q, or < 8q if tight); out: layout B' (lazy, see fwd4)
 __device__ __forceinline__ void row_fwd8(u64 (&x)[16], u64 *sm, const RowGeom &G, const ModC &M) {
-    fwd4(x, M.psi, G.baseA(), M.q, M.qinv, M.q2);
-    row_AtoB(x, sm, G);
-    fwd4(x, M.psi, G.baseB(), M.q, M.qinv, M.q2);
+    if (M.tight) {
+        fwd4<true>(x, M.psi, G.baseA(), M.q, M.q2);
+        row_AtoB(x, sm, G);
+        fwd4<true>(x, M.psi, G.baseB(), M.q, M.q2);
+    } else {
+        fwd4<false>(x, M.psi, G.baseA(), M.q, M.q2);
+        row_AtoB(x, sm, G);
+        fwd4<false>(x, M.psi, G.baseB(), M.q, M.q2);
+    }
 }
-// in: layout B'; out: layout A'
+// in: layout B' (values < 2q); out: layout A' (< 2q)
 __device__ __forceinline__ void row_inv8(u64 (&x)[16], u64 *sm, const RowGeom &G, const ModC &M) {
-    inv4(x, M.psi_inv, G.baseB(), M.q, M.qinv, M.q2);
+    inv4(x, M.psi_inv, G.baseB(), M.q, M.q2);
     row_BtoA(x, sm, G);
-    inv4(x, M.psi_inv, G.baseA(), M.q, M.qinv, M.q2);
+    inv4(x, M.psi_inv, G.baseA(), M.q, M.q2);
 }
 
 // ---- column-kernel tile geometry ---------------------------------------------------------
@@ -195,15 +228,21 @@ __device__ __forceinline__ void col_BtoA(u64 (&x)[16], u64 *sm, const ColGeom &G
 }
 // in: layout A, out: layout B
 __device__ __forceinline__ void col_fwd8(u64 (&x)[16], u64 *sm, const ColGeom &G, const ModC &M) {
-    fwd4(x, M.psi, 1, M.q, M.qinv, M.q2);
-    col_AtoB(x, sm, G);
-    fwd4(x, M.psi, 16 + G.pg, M.q, M.qinv, M.q2);
+    if (M.tight) {
+        fwd4<true>(x, M.psi, 1, M.q, M.q2);
+        col_AtoB(x, sm, G);
+        fwd4<true>(x, M.psi, 16 + G.pg, M.q, M.q2);
+    } else {
+        fwd4<false>(x, M.psi, 1, M.q, M.q2);
+        col_AtoB(x, sm, G);
+        fwd4<false>(x, M.psi, 16 + G.pg, M.q, M.q2);
+    }
 }
 // in: layout B, out: layout A
 __device__ __forceinline__ void col_inv8(u64 (&x)[16], u64 *sm, const ColGeom &G, const ModC &M) {
-    inv4(x, M.psi_inv, 16 + G.pg, M.q, M.qinv, M.q2);
+    inv4(x, M.psi_inv, 16 + G.pg, M.q, M.q2);
     col_BtoA(x, sm, G);
-    inv4(x, M.psi_inv, 1, M.q, M.qinv, M.q2);
+    inv4(x, M.psi_inv, 1, M.q, M.q2);
 }
 
 // PermuteNTTIndex computed on the fly (L:ring/ring_automorphism.go:31-44):

@@ -30,8 +30,9 @@ inline u32 bitrev16(u32 x) {
 }
 
 struct HostMod {
-    u64 q = 0, qinv = 0, ninv = 0, rmod = 0, gen = 0;
-    std::vector<u64> psi, psi_inv; // Montgomery form, bit-reversed
+    u64 q = 0, qinv = 0, rmod = 0, gen = 0;
+    u64 ninv_w = 0, ninv_s = 0;          // N^-1 mod q and floor(N^-1 * 2^64 / q)
+    std::vector<ulonglong2> psi, psi_inv; // (w, floor(w * 2^64 / q)) at index brev(j), w = psi^(+-j)
 };
 void build_mod(HostMod &m, u64 q);
 
@@ -70,7 +71,7 @@ struct hec_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<hec::HostMod> hm; // Q then P
     ModC *dmods = nullptr;
-    u64 *dtables = nullptr;
+    ulonglong2 *dtables = nullptr;
     std::vector<std::vector<u64>> resc; // resc[L][i] = MForm(q_i - q_L^-1 mod q_i)
     std::vector<u64> negpinv;           // q_i - MForm(P^-1 mod q_i)
     hec::ModupTab pq;                   // P -> Q

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(HEC_THREADS) k_row_fwd(NttJobs J, const ModC *
     row_fwd8(x, sm, G, M);
     row_BtoA(x, sm, G);
 #pragma unroll
-    for (int k = 0; k < 16; k++) x[k] = canon4(x[k], M.q, M.q2);
+    for (int k = 0; k < 16; k++) x[k] = canon(x[k], M);
     row_storeA(x, job.out, G);
 }
 __global__ void __launch_bounds__(HEC_THREADS) k_row_inv(NttJobs J, const ModC *__restrict__ mods) {
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(HEC_THREADS) k_col_inv(NttJobs J, const ModC *
     for (int k = 0; k < 16; k++) x[k] = job.in[G.gB(k)];
     col_inv8(x, sm, G, M);
 #pragma unroll
-    for (int k = 0; k < 16; k++) job.out[G.gA(k)] = mred(x[k], M.ninv, M.q, M.qinv);
+    for (int k = 0; k < 16; k++) job.out[G.gA(k)] = inv_final(x[k], M);
 }
 
 // ---- element-wise ------------------------------------------------------------------------
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(HEC_THREADS) k_convA2(ConvA P, const ModC *__r
     col_inv8(x, sm, G, M1);
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        u64 t = mred(x[k], M1.ninv, M1.q, M1.qinv);        // InvNTT final pass, canonical
+        u64 t = inv_final(x[k], M1);                        // InvNTT final pass, canonical
         t = cred(t + P.half1, M1.q);                        // + (q1-1)/2 mod q1
         x[k] = mred(t, M0.rmod, M0.q, M0.qinv) + P.hneg0;   // (t mod q0) - half  in [0,2q0)
     }
@@ -279,31 +279,46 @@ __global__ void __launch_bounds__(HEC_THREADS) k_convB2(ConvB P, const ModC *__r
 #pragma unroll
     for (int k = 0; k < 16; k++) x[k] = in[G.gB(k)];
     col_inv8(x, sm, G, MQ);
-    const bool fits = MQ.q <= MP.q2; // digit residue < q0 must be < 4*p0 for the lazy forward
+    const bool fits = MQ.q <= MP.q2; // the digit residue (< q0) is fed to the lazy forward as is
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        u64 c = mred(x[k], MQ.ninv, MQ.q, MQ.qinv);
-        x[k] = fits ? c : mred(c, MP.rmod, MP.q, MP.qinv);
+        u64 c = inv_final(x[k], MQ);
+        x[k] = fits ? c : canon(c, MP);
     }
     col_fwd8(x, sm, G, MP);
 #pragma unroll
     for (int k = 0; k < 16; k++) out[G.gB(k)] = x[k];
 }
-// B3: finish NTT_p0 of the digit, multiply by key[c] (P limb), inverse stages t = 1..128 under p0
-//     grid.y = M*nb*2
+// B3: finish NTT_p0 of the digit (once), then for both key polys: multiply by key[c] (P limb) and
+//     run inverse stages t = 1..128 under p0                               grid.y = M*nb
+#define HEC_B3_SMEM ((16 * HEC_ROW_PITCH + HEC_TILE) * sizeof(u64)) // dynamic: above the 48 KB static limit
 __global__ void __launch_bounds__(HEC_THREADS) k_convB3(ConvB P, const ModC *__restrict__ mods) {
-    __shared__ u64 sm[16 * HEC_ROW_PITCH];
-    const BJob J(blockIdx.y, true, P);
+    extern __shared__ __align__(16) u64 dsm[];
+    u64 *sm = dsm;
+    u64 *stash = dsm + 16 * HEC_ROW_PITCH; // NTT_p0(digit), kept for the second key poly
     const ModC M = mods[P.mp0];
     RowGeom G(blockIdx.x);
-    u64 x[16], kk[16];
-    row_loadA(x, P.w2 + (size_t)(blockIdx.y >> 1) * HEC_N, G);
-    row_fwd8(x, sm, G, M);
-    row_loadB(kk, P.key + (size_t)(J.c * P.keyL + P.keyPoff) * HEC_N, G);
+    {
+        u64 x[16];
+        row_loadA(x, P.w2 + (size_t)blockIdx.y * HEC_N, G);
+        row_fwd8(x, sm, G, M);
 #pragma unroll
-    for (int k = 0; k < 16; k++) x[k] = mred_lazy(x[k], kk[k], M.q, M.qinv);
-    row_inv8(x, sm, G, M);
-    row_storeA(x, P.w3 + (size_t)blockIdx.y * HEC_N, G);
+        for (int k = 0; k < 16; k++) stash[k * HEC_THREADS + threadIdx.x] = x[k]; // own slots only
+    }
+#pragma unroll 1
+    for (int c = 0; c < 2; c++) {
+        const ulonglong2 *kv = reinterpret_cast<const ulonglong2 *>(
+            P.key + (size_t)(c * P.keyL + P.keyPoff) * HEC_N + G.b * 256 + 16 * G.p);
+        u64 y[16];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            ulonglong2 t = __ldg(kv + k);
+            y[2 * k] = mred_lazy(stash[(2 * k) * HEC_THREADS + threadIdx.x], t.x, M.q, M.qinv);
+            y[2 * k + 1] = mred_lazy(stash[(2 * k + 1) * HEC_THREADS + threadIdx.x], t.y, M.q, M.qinv);
+        }
+        row_inv8(y, sm, G, M);
+        row_storeA(y, P.w3 + (size_t)(blockIdx.y * 2 + c) * HEC_N, G);
+    }
 }
 // B4: finish InvNTTLazy_p0, exact basis extension P -> q0 (float64 overflow count v),
 //     forward stages m = 1..128 under q0                                   grid.y = M*nb*2
@@ -321,7 +336,7 @@ __global__ void __launch_bounds__(HEC_THREADS) k_convB4(ConvB P, const ModC *__r
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         // y = MRed(e, qibMont) with qibMont = MForm(1): the canonical residue mod p0
-        u64 y = mred(x[k], MP.ninv, MP.q, MP.qinv);
+        u64 y = inv_final(x[k], MP);
         double f = __ddiv_rn(__ull2double_rn(y), P.p0f);
         u64 v = (u64)__double2ull_rz(__dadd_rn(0.0, f));
         x[k] = mred(y, MQ.rmod, MQ.q, MQ.qinv) + (v ? P.qpj1 : 0ull); // in [0,2q0)

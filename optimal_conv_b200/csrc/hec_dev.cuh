@@ -33,6 +33,9 @@ typedef unsigned int u32;
 #define HEC_TILES_PER_LIMB 16
 #define HEC_THREADS 256
 #define HEC_ROW_PITCH 272       // 256 + one pad word per 16 (bank-conflict-free 16p+k reads)
+#ifndef HEC_MINB
+#define HEC_MINB 3               // resident CTAs per SM the fused kernels are compiled for (<= 85 registers)
+#endif
 
 struct ModC {
     u64 q, qinv;      // q * qinv = 1 mod 2^64

@@ -161,7 +161,7 @@ struct AJob {
     __device__ __forceinline__ AJob(int job, int na) { c = job & 1; a = (job >> 1) % na; m = (job >> 1) / na; }
 };
 // A1: limb q1:  (ct*pt*k1) -> inverse stages t = 1..128
-__global__ void __launch_bounds__(HEC_THREADS) k_convA1(ConvA P, const ModC *__restrict__ mods) {
+__global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convA1(ConvA P, const ModC *__restrict__ mods) {
     __shared__ u64 sm[16 * HEC_ROW_PITCH];
     const AJob J(blockIdx.y, P.na);
     const ModC M = mods[P.mq1];
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(HEC_THREADS) k_convA1(ConvA P, const ModC *__r
     row_storeA(x, P.w1 + (size_t)blockIdx.y * HEC_N, G);
 }
 // A2: finish InvNTT_q1, centre, lift into q0, forward stages m = 1..128 under q0
-__global__ void __launch_bounds__(HEC_THREADS) k_convA2(ConvA P, const ModC *__restrict__ mods) {
+__global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convA2(ConvA P, const ModC *__restrict__ mods) {
     __shared__ u64 sm[HEC_TILE];
     const ModC M1 = mods[P.mq1];
     const ModC M0 = mods[P.mq0];
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(HEC_THREADS) k_convA2(ConvA P, const ModC *__r
     for (int k = 0; k < 16; k++) out[G.gB(k)] = x[k];
 }
 // A3: finish NTT_q0, combine with limb q0 of ct*pt*k0:  out = (p0 - u) * q1^-1
-__global__ void __launch_bounds__(HEC_THREADS) k_convA3(ConvA P, const ModC *__restrict__ mods) {
+__global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convA3(ConvA P, const ModC *__restrict__ mods) {
     __shared__ u64 sm[16 * HEC_ROW_PITCH];
     const AJob J(blockIdx.y, P.na);
     const ModC M = mods[P.mq0];
@@ -252,7 +252,7 @@ struct BJob {
     }
 };
 // B1: z = tmp2.c1 = a1 - b1*mono ; inverse stages t = 1..128 under q0      grid.y = M*nb
-__global__ void __launch_bounds__(HEC_THREADS) k_convB1(ConvB P, const ModC *__restrict__ mods) {
+__global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convB1(ConvB P, const ModC *__restrict__ mods) {
     __shared__ u64 sm[16 * HEC_ROW_PITCH];
     const BJob J(blockIdx.y, false, P);
     const ModC M = mods[P.mq0];
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(HEC_THREADS) k_convB1(ConvB P, const ModC *__r
     row_storeA(x, P.w1 + (size_t)blockIdx.y * HEC_N, G);
 }
 // B2: finish InvNTT_q0 (canonical digit), copy-path lift into p0, forward stages m = 1..128 under p0
-__global__ void __launch_bounds__(HEC_THREADS) k_convB2(ConvB P, const ModC *__restrict__ mods) {
+__global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convB2(ConvB P, const ModC *__restrict__ mods) {
     __shared__ u64 sm[HEC_TILE];
     const ModC MQ = mods[P.mq0];
     const ModC MP = mods[P.mp0];
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(HEC_THREADS) k_convB2(ConvB P, const ModC *__r
 // B3: finish NTT_p0 of the digit (once), then for both key polys: multiply by key[c] (P limb) and
 //     run inverse stages t = 1..128 under p0                               grid.y = M*nb
 #define HEC_B3_SMEM ((16 * HEC_ROW_PITCH + HEC_TILE) * sizeof(u64)) // dynamic: above the 48 KB static limit
-__global__ void __launch_bounds__(HEC_THREADS) k_convB3(ConvB P, const ModC *__restrict__ mods) {
+__global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convB3(ConvB P, const ModC *__restrict__ mods) {
     extern __shared__ __align__(16) u64 dsm[];
     u64 *sm = dsm;
     u64 *stash = dsm + 16 * HEC_ROW_PITCH; // NTT_p0(digit), kept for the second key poly
@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(HEC_THREADS) k_convB3(ConvB P, const ModC *__r
 }
 // B4: finish InvNTTLazy_p0, exact basis extension P -> q0 (float64 overflow count v),
 //     forward stages m = 1..128 under q0                                   grid.y = M*nb*2
-__global__ void __launch_bounds__(HEC_THREADS) k_convB4(ConvB P, const ModC *__restrict__ mods) {
+__global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convB4(ConvB P, const ModC *__restrict__ mods) {
     __shared__ u64 sm[HEC_TILE];
     const ModC MP = mods[P.mp0];
     const ModC MQ = mods[P.mq0];
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(HEC_THREADS) k_convB4(ConvB P, const ModC *__r
 }
 // B5: finish NTT_q0, mod-down combine with acc_Q = z*key[c] (Q limb), + tmp2.c0 (c = 0),
 //     apply sigma_g inside the 256-word block, add tmp1 (+ bias)           grid.y = M*nb*2
-__global__ void __launch_bounds__(HEC_THREADS) k_convB5(ConvB P, const ModC *__restrict__ mods) {
+__global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convB5(ConvB P, const ModC *__restrict__ mods) {
     __shared__ u64 sm[16 * HEC_ROW_PITCH];
     const BJob J(blockIdx.y, true, P);
     const ModC M = mods[P.mq0];

@@ -28,7 +28,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 from optimal_conv_b200 import params as PR  # noqa: E402
-from optimal_conv_b200 import synth  # noqa: E402
+from optimal_conv_b200 import shard, synth  # noqa: E402
 
 N = 1 << PR.LOGN
 LIMB = N * 8
@@ -160,9 +160,7 @@ def main():
     import torch.distributed as dist
     from optimal_conv_b200 import hec
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, local, world = shard.world()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
@@ -245,20 +243,15 @@ def main():
         torch.cuda.synchronize()
         for name, ms in plan.profile(dev_in[rep % ring]):
             prof.setdefault(name, []).append(ms)
-    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_dev, ms_e2e = t.tolist()
+    # whole-job throughput: every rank's convs over the slowest rank's device time (no data-path collective)
+    value, ms_dev = shard.throughput(M, args.steps, ms_dev, device="cuda")
+    e2e, ms_e2e = shard.throughput(M, args.steps, ms_e2e, device="cuda")
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
     peak, peak_src = peaks()
-    convs = world * M * args.steps
-    value = convs / (ms_dev / 1e3)
-    e2e = convs / (ms_e2e / 1e3)
-    levels = B.bit_length() - 1
     # launches of each kernel per run and jobs per launch
     per_kernel = {}
     for name, times in prof.items():

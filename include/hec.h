@@ -123,6 +123,14 @@ int hec_conv_then_pack(hec_ctx *ctx, const hec_ct *ct_in, const hec_pt *const *p
                        double out_scale, const hec_pt *const *pt_idx, const hec_pt *pt_bias, int flags,
                        hec_ct **out);
 
+/* Baseline (rotation-per-tap) convolution: the timed interval of evalConv_BN_BL_test
+ * (eval.go:108-131) = preConv_BL (conv.go:120-143: RotateHoisted by i*in_wid+j, |i|,|j| <= ker_wid/2)
+ * + rot_iters x [postConv_BL (conv.go:146-178: sum over taps of MulNew) + RotateNew(i*rot_step) + Add]
+ * + Add(pl_bn_b).  pt_taps[i*ker_wid^2 + tap] are the plaintexts postConv_BL encodes on the host
+ * (conv.go:165-166), passed pre-encoded.  Keys for all rotations must be uploaded. */
+int hec_conv_bl(hec_ctx *ctx, const hec_ct *ct_in, int in_wid, int ker_wid, int rot_iters, int rot_step,
+                const hec_pt *const *pt_taps, const hec_pt *pt_bias, hec_ct **out);
+
 /* A prepared evalConv_BN for `batch` independent input ciphertexts per run: kernel
  * plaintexts, monomials, bias and keys stay resident; the kernel sequence is captured in a
  * CUDA graph.  in_level must be 1 (ECD_LV) in this build. */
@@ -135,6 +143,16 @@ int hec_plan_run(hec_plan *plan, const hec_ct *const *ins, hec_ct **outs);
  * 2 limb pointers (level 1), out_c0/out_c1 to 1 limb pointer (level 0).  Copies run inside. */
 int hec_plan_run_host(hec_plan *plan, const uint64_t *const *in_c0, const uint64_t *const *in_c1,
                       uint64_t *const *out_c0, uint64_t *const *out_c1);
+/* Pipelined host-buffer runs: submit enqueues H2D copies, the kernel graph and D2H copies on three
+ * streams and returns; wait blocks until that batch's outputs are in the caller's buffers.  Two
+ * batches may be in flight, so the copies of one batch overlap the kernels of its neighbours.
+ * Host buffers should be pinned and must stay valid until the matching wait returns. */
+int hec_plan_submit_host(hec_plan *plan, const uint64_t *const *in_c0, const uint64_t *const *in_c1,
+                         uint64_t *const *out_c0, uint64_t *const *out_c1, int *ticket);
+int hec_plan_wait(hec_plan *plan, int ticket);
+/* device-side elapsed time of a pipelined sequence (first H2D enqueued .. last D2H finished) */
+int hec_plan_span_begin(hec_plan *plan);
+int hec_plan_span_end_ms(hec_plan *plan, float *ms);
 /* per-launch device times (ms) of one run with the kernels launched one by one, in launch
  * order A1,A2,A3,(B1..B5) per pack level -- measurement aid for the roofline report */
 int hec_plan_profile(hec_plan *plan, const hec_ct *const *ins, float *ms, int cap, int *n);

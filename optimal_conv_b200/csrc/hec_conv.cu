@@ -73,6 +73,65 @@ static int conv_then_pack_oplevel(hec_ctx *ev, const hec_ct *ctxt_in, const hec_
 }
 
 // =========================================================================================
+// baseline (rotation-per-tap) convolution, op-level: evalConv_BN_BL_test's timed interval
+// (eval.go:108-131) = preConv_BL (conv.go:120-143) + rot_iters x [postConv_BL (conv.go:146-178)
+// + RotateNew + Add (eval.go:118-125)] + bias Add (eval.go:130).  The kernel plaintexts that
+// postConv_BL encodes on the host inside its loop (conv.go:165-166) arrive pre-encoded.
+// =========================================================================================
+extern "C" int hec_conv_bl(hec_ctx *ev, const hec_ct *ct_input, int in_wid, int ker_wid, int rot_iters, int rot_step,
+                           const hec_pt *const *pt_taps, const hec_pt *pl_bn_b, hec_ct **out) {
+    if (!ev || !ct_input || !pt_taps || !out || ker_wid < 1 || !(ker_wid & 1) || rot_iters < 1) return ev ? ev->fail(HEC_E_INVAL, "conv_bl args") : HEC_E_INVAL;
+    cudaSetDevice(ev->device);
+    const int ker_size = ker_wid * ker_wid;
+    int rc;
+    // preConv_BL: one hoisted decomposition, k^2 rotations i*in_wid + j
+    std::vector<int> rotations;
+    for (int i = -(ker_wid / 2); i <= ker_wid / 2; i++)
+        for (int j = -(ker_wid / 2); j <= ker_wid / 2; j++) rotations.push_back(i * in_wid + j);
+    std::vector<hec_ct *> ct_in_rots(ker_size, nullptr);
+    if ((rc = hec_rotate_hoisted(ev, ct_input, rotations.data(), ker_size, ct_in_rots.data()))) return rc;
+    auto cleanup = [&](hec_ct *keep) {
+        for (auto p : ct_in_rots) if (p && p != keep) hec_ct_free(ev, p);
+    };
+    hec_ct *ct_res = nullptr;
+    for (int i = 0; i < rot_iters; i++) {
+        // postConv_BL: sum over taps of MulNew(ct_in_rots[tap], pl_tap)
+        hec_ct *ct_tmp = nullptr;
+        for (int t = 0; t < ker_size; t++) {
+            const hec_pt *pl = pt_taps[(size_t)i * ker_size + t];
+            if (!pl) { cleanup(nullptr); return ev->fail(HEC_E_INVAL, "conv_bl: missing tap plaintext"); }
+            if (t == 0) { if ((rc = hec_mul_pt_new(ev, ct_in_rots[t], pl, &ct_tmp))) { cleanup(nullptr); return rc; } }
+            else {
+                hec_ct *m = nullptr;
+                if ((rc = hec_mul_pt_new(ev, ct_in_rots[t], pl, &m))) { cleanup(nullptr); return rc; }
+                rc = hec_add(ev, ct_tmp, m, ct_tmp);
+                hec_ct_free(ev, m);
+                if (rc) { cleanup(nullptr); return rc; }
+            }
+        }
+        if (i == 0) ct_res = ct_tmp;
+        else {
+            hec_ct *r = nullptr;
+            if ((rc = hec_rotate_new(ev, ct_tmp, i * rot_step, &r))) { cleanup(nullptr); return rc; }
+            rc = hec_add(ev, ct_res, r, ct_res);
+            hec_ct_free(ev, r);
+            hec_ct_free(ev, ct_tmp);
+            if (rc) { cleanup(nullptr); return rc; }
+        }
+    }
+    cleanup(nullptr);
+    if (pl_bn_b) {
+        if (hec_ct_scale(ct_res) != pl_bn_b->scale) { // eval.go:127-129
+            hec_ct_free(ev, ct_res);
+            return ev->fail(HEC_E_SCALE, "Different scale between pl_bn_b and ctxt");
+        }
+        if ((rc = hec_add_pt(ev, ct_res, pl_bn_b))) { hec_ct_free(ev, ct_res); return rc; }
+    }
+    *out = ct_res;
+    return HEC_OK;
+}
+
+// =========================================================================================
 // fused plan
 // =========================================================================================
 struct hec_plan {
@@ -87,6 +146,12 @@ struct hec_plan {
     const u64 *bias = nullptr; int bias_mod = 0;
     cudaGraphExec_t exec = nullptr;
     int launches_per_run = 0;
+    // pipelined host runs: copies on their own streams, two batches in flight
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    u64 *stage_in2[2] = {nullptr, nullptr}, *stage_out2[2] = {nullptr, nullptr};
+    int next_ticket = 0;
 };
 
 static int plan_launch_all(hec_plan *p, const std::function<void()> &after = [] {}) {
@@ -132,6 +197,17 @@ extern "C" void hec_plan_destroy(hec_plan *p) {
     cudaSetDevice(p->c->device);
     cudaStreamSynchronize(p->c->stream);
     if (p->exec) cudaGraphExecDestroy(p->exec);
+    for (int i = 0; i < 2; i++) {
+        if (p->ev_in[i]) cudaEventDestroy(p->ev_in[i]);
+        if (p->ev_comp[i]) cudaEventDestroy(p->ev_comp[i]);
+        if (p->ev_out[i]) cudaEventDestroy(p->ev_out[i]);
+        if (p->stage_in2[i]) cudaFree(p->stage_in2[i]);
+        if (p->stage_out2[i]) cudaFree(p->stage_out2[i]);
+    }
+    if (p->ev_t0) cudaEventDestroy(p->ev_t0);
+    if (p->ev_t1) cudaEventDestroy(p->ev_t1);
+    if (p->s_in) cudaStreamDestroy(p->s_in);
+    if (p->s_out) cudaStreamDestroy(p->s_out);
     if (p->pool) cudaFree(p->pool);
     if (p->d_ctin) cudaFree((void *)p->d_ctin);
     if (p->d_ptk) cudaFree((void *)p->d_ptk);
@@ -323,6 +399,89 @@ extern "C" int hec_plan_profile(hec_plan *p, const hec_ct *const *ins, float *ms
     for (auto &e : ev) cudaEventDestroy(e);
     *n = k;
     return rc;
+}
+
+// ---- pipelined host runs -------------------------------------------------------------------
+// submit: H2D (stream s_in) -> graph (context stream) -> D2H (stream s_out), double buffered, so
+// the copies of one batch overlap the kernels of its neighbours.  wait: block until that
+// batch's outputs are in the caller's buffers.  At most two batches in flight.
+static int plan_pipeline_init(hec_plan *p) {
+    hec_ctx *c = p->c;
+    if (p->s_in) return HEC_OK;
+    HEC_CUDA(c, cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking));
+    HEC_CUDA(c, cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        HEC_CUDA(c, cudaEventCreateWithFlags(&p->ev_in[i], cudaEventDisableTiming));
+        HEC_CUDA(c, cudaEventCreateWithFlags(&p->ev_comp[i], cudaEventDisableTiming));
+        HEC_CUDA(c, cudaEventCreateWithFlags(&p->ev_out[i], cudaEventDisableTiming));
+        HEC_CUDA(c, cudaMalloc(&p->stage_in2[i], (size_t)p->M * 4 * HEC_N * sizeof(u64)));
+        HEC_CUDA(c, cudaMalloc(&p->stage_out2[i], (size_t)p->M * 2 * HEC_N * sizeof(u64)));
+    }
+    HEC_CUDA(c, cudaEventCreate(&p->ev_t0));
+    HEC_CUDA(c, cudaEventCreate(&p->ev_t1));
+    return HEC_OK;
+}
+extern "C" int hec_plan_submit_host(hec_plan *p, const uint64_t *const *in_c0, const uint64_t *const *in_c1,
+                                    uint64_t *const *out_c0, uint64_t *const *out_c1, int *ticket) {
+    if (!p || !in_c0 || !in_c1 || !out_c0 || !out_c1 || !ticket) return HEC_E_INVAL;
+    hec_ctx *c = p->c;
+    cudaSetDevice(c->device);
+    int rc = plan_pipeline_init(p);
+    if (rc) return rc;
+    const int t = p->next_ticket++, slot = t & 1;
+    const size_t LB = HEC_N * sizeof(u64);
+    if (t >= 2) HEC_CUDA(c, cudaEventSynchronize(p->ev_out[slot])); // batch t-2 fully delivered
+    HEC_CUDA(c, cudaStreamWaitEvent(p->s_in, p->ev_comp[slot], 0)); // kernels of t-2 done with this input slot
+    std::vector<const u64 *> ptrs(p->M);
+    for (int m = 0; m < p->M; m++) {
+        u64 *d = p->stage_in2[slot] + (size_t)m * 4 * HEC_N;
+        for (int i = 0; i < 2; i++) {
+            HEC_CUDA(c, cudaMemcpyAsync(d + (size_t)i * HEC_N, in_c0[m * 2 + i], LB, cudaMemcpyHostToDevice, p->s_in));
+            HEC_CUDA(c, cudaMemcpyAsync(d + (size_t)(2 + i) * HEC_N, in_c1[m * 2 + i], LB, cudaMemcpyHostToDevice, p->s_in));
+        }
+        ptrs[m] = d;
+    }
+    HEC_CUDA(c, cudaEventRecord(p->ev_in[slot], p->s_in));
+    HEC_CUDA(c, cudaStreamWaitEvent(c->stream, p->ev_in[slot], 0));
+    if ((rc = plan_run_graph(p, ptrs))) return rc;
+    HEC_CUDA(c, cudaMemcpyAsync(p->stage_out2[slot], p->xfinal, (size_t)p->M * 2 * LB, cudaMemcpyDeviceToDevice, c->stream));
+    HEC_CUDA(c, cudaEventRecord(p->ev_comp[slot], c->stream));
+    HEC_CUDA(c, cudaStreamWaitEvent(p->s_out, p->ev_comp[slot], 0));
+    for (int m = 0; m < p->M; m++) {
+        const u64 *x = p->stage_out2[slot] + (size_t)m * 2 * HEC_N;
+        HEC_CUDA(c, cudaMemcpyAsync(out_c0[m], x, LB, cudaMemcpyDeviceToHost, p->s_out));
+        HEC_CUDA(c, cudaMemcpyAsync(out_c1[m], x + HEC_N, LB, cudaMemcpyDeviceToHost, p->s_out));
+    }
+    HEC_CUDA(c, cudaEventRecord(p->ev_out[slot], p->s_out));
+    *ticket = t;
+    return HEC_OK;
+}
+extern "C" int hec_plan_wait(hec_plan *p, int ticket) {
+    if (!p || ticket < 0 || ticket >= p->next_ticket) return HEC_E_INVAL;
+    hec_ctx *c = p->c;
+    cudaSetDevice(c->device);
+    if (ticket < p->next_ticket - 2) return HEC_OK; // already forced complete by a later submit
+    HEC_CUDA(c, cudaEventSynchronize(p->ev_out[ticket & 1]));
+    return HEC_OK;
+}
+// device-side span of a pipelined sequence: begin records on the H2D stream, end on the D2H stream
+extern "C" int hec_plan_span_begin(hec_plan *p) {
+    if (!p) return HEC_E_INVAL;
+    hec_ctx *c = p->c;
+    cudaSetDevice(c->device);
+    int rc = plan_pipeline_init(p);
+    if (rc) return rc;
+    HEC_CUDA(c, cudaEventRecord(p->ev_t0, p->s_in));
+    return HEC_OK;
+}
+extern "C" int hec_plan_span_end_ms(hec_plan *p, float *ms) {
+    if (!p || !ms || !p->s_out) return HEC_E_INVAL;
+    hec_ctx *c = p->c;
+    cudaSetDevice(c->device);
+    HEC_CUDA(c, cudaEventRecord(p->ev_t1, p->s_out));
+    HEC_CUDA(c, cudaEventSynchronize(p->ev_t1));
+    HEC_CUDA(c, cudaEventElapsedTime(ms, p->ev_t0, p->ev_t1));
+    return HEC_OK;
 }
 
 // =========================================================================================

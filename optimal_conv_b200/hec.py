@@ -26,8 +26,9 @@ SYMBOLS = [
     "hec_ct_copy_new", "hec_ct_level", "hec_ct_scale", "hec_ct_set_scale", "hec_ct_free", "hec_swk_upload",
     "hec_swk_drop", "hec_mul_pt_new", "hec_mult_by_const", "hec_rescale", "hec_set_scale", "hec_add", "hec_add_new",
     "hec_sub_new", "hec_add_pt", "hec_rotate_gal", "hec_rotate_new", "hec_rotate_hoisted", "hec_galois_for_rotation",
-    "hec_ntt", "hec_keyswitch", "hec_moddown", "hec_conv_then_pack", "hec_plan_create", "hec_plan_run",
-    "hec_plan_run_host", "hec_plan_profile", "hec_plan_destroy",
+    "hec_ntt", "hec_keyswitch", "hec_moddown", "hec_conv_then_pack", "hec_conv_bl", "hec_plan_create", "hec_plan_run",
+    "hec_plan_run_host", "hec_plan_submit_host", "hec_plan_wait", "hec_plan_span_begin", "hec_plan_span_end_ms",
+    "hec_plan_profile", "hec_plan_destroy",
 ]
 
 
@@ -92,10 +93,15 @@ def lib():
     L.hec_moddown.argtypes = [vp, C.c_int, u64pp, u64pp, u64pp]
     L.hec_conv_then_pack.argtypes = [vp, vp, C.POINTER(vp), C.c_int, C.c_int, C.c_double, C.POINTER(vp), vp, C.c_int,
                                      C.POINTER(vp)]
+    L.hec_conv_bl.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp), vp, C.POINTER(vp)]
     L.hec_plan_create.argtypes = [vp, C.POINTER(vp), C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(vp), vp,
                                   C.c_int, C.POINTER(vp)]
     L.hec_plan_run.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     L.hec_plan_run_host.argtypes = [vp, u64pp, u64pp, u64pp, u64pp]
+    L.hec_plan_submit_host.argtypes = [vp, u64pp, u64pp, u64pp, u64pp, C.POINTER(C.c_int)]
+    L.hec_plan_wait.argtypes = [vp, C.c_int]
+    L.hec_plan_span_begin.argtypes = [vp]
+    L.hec_plan_span_end_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.hec_plan_profile.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]
     L.hec_plan_destroy.argtypes = [vp]
     L.hec_plan_destroy.restype = None
@@ -300,6 +306,15 @@ class Context:
                                             pt_bias.h if pt_bias is not None else None, flags, C.byref(h)))
         return Ciphertext(self, h)
 
+    def conv_bl(self, ct_in, in_wid, ker_wid, rot_step, pt_taps, pt_bias=None):
+        """evalConv_BN_BL_test's timed interval (eval.go:108-131); pt_taps[i][tap]."""
+        flat = [p for row in pt_taps for p in row]
+        arr = (vp * len(flat))(*[p.h for p in flat])
+        h = vp()
+        self._chk(self.L.hec_conv_bl(self.h, ct_in.h, in_wid, ker_wid, len(pt_taps), rot_step, arr,
+                                     pt_bias.h if pt_bias is not None else None, C.byref(h)))
+        return Ciphertext(self, h)
+
     def plan(self, pt_ker, norm, in_scale, out_scale, pt_idx, pt_bias, batch):
         return Plan(self, pt_ker, norm, in_scale, out_scale, pt_idx, pt_bias, batch)
 
@@ -325,9 +340,7 @@ class Plan:
         self.ctx._chk(self.ctx.L.hec_plan_run(self.h, ins, self._outs))
         return [Ciphertext(self.ctx, vp(self._outs[i])) for i in range(self.batch)]
 
-    def run_host(self, in_c0, in_c1, out_c0, out_c1):
-        """host-buffer run.  in_c0/in_c1: [batch][2][N] uint64 arrays (pinned for async copies);
-        out_c0/out_c1: [batch][N].  Accepts numpy arrays or objects with data_ptr() (torch)."""
+    def _host_ptrs(self, in_c0, in_c1, out_c0, out_c1):
         N = self.ctx.N
 
         def base(a):
@@ -338,7 +351,29 @@ class Plan:
         pin1 = _ptrs([b1 + (m * 2 + i) * N * 8 for m in range(self.batch) for i in range(2)])
         po0 = _ptrs([o0 + m * N * 8 for m in range(self.batch)])
         po1 = _ptrs([o1 + m * N * 8 for m in range(self.batch)])
-        self.ctx._chk(self.ctx.L.hec_plan_run_host(self.h, pin0, pin1, po0, po1))
+        return pin0, pin1, po0, po1
+
+    def run_host(self, in_c0, in_c1, out_c0, out_c1):
+        """host-buffer run.  in_c0/in_c1: [batch][2][N] uint64 arrays (pinned for async copies);
+        out_c0/out_c1: [batch][N].  Accepts numpy arrays or objects with data_ptr() (torch)."""
+        self.ctx._chk(self.ctx.L.hec_plan_run_host(self.h, *self._host_ptrs(in_c0, in_c1, out_c0, out_c1)))
+
+    def submit_host(self, in_c0, in_c1, out_c0, out_c1):
+        """pipelined host-buffer run: returns a ticket; buffers must stay valid until wait(ticket)."""
+        t = C.c_int()
+        self.ctx._chk(self.ctx.L.hec_plan_submit_host(self.h, *self._host_ptrs(in_c0, in_c1, out_c0, out_c1), C.byref(t)))
+        return t.value
+
+    def wait(self, ticket):
+        self.ctx._chk(self.ctx.L.hec_plan_wait(self.h, ticket))
+
+    def span_begin(self):
+        self.ctx._chk(self.ctx.L.hec_plan_span_begin(self.h))
+
+    def span_end_ms(self):
+        ms = C.c_float()
+        self.ctx._chk(self.ctx.L.hec_plan_span_end_ms(self.h, C.byref(ms)))
+        return ms.value
 
     def profile(self, cts):
         """[(kernel name, ms)] of one run with kernels launched one by one."""

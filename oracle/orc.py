@@ -249,6 +249,28 @@ class Oracle:
             raise RuntimeError("LV or scale after conv then pack, inconsistent")
         return Ct(o0[None, :], o1[None, :], s.value), tm.value, tp.value
 
+    def conv_bl(self, ct_in, in_wid, ker_wid, rot_step, pt_taps, pt_scale, keys, pt_bias=None):
+        """evalConv_BN_BL_test's timed interval (eval.go:108-131): preConv_BL (conv.go:120-143,
+        RotateHoisted == the same rotations one by one, bit for bit) + postConv_BL (conv.go:146-178)
+        + RotateNew/Add (eval.go:118-125) + bias (eval.go:130).  pt_taps: [rot_iters][k^2][L][N];
+        keys: rotation k -> switching key."""
+        h = ker_wid // 2
+        rots = [i * in_wid + j for i in range(-h, h + 1) for j in range(-h, h + 1)]
+        ct_rots = [ct_in if r == 0 else self.rotate(ct_in, r, keys[r]) for r in rots]
+        res = None
+        for i, taps in enumerate(pt_taps):
+            tmp = None
+            for t, pt in enumerate(taps):
+                m = self.mul_pt(ct_rots[t], pt, pt_scale)
+                tmp = m if tmp is None else self.add(tmp, m)
+            if i == 0:
+                res = tmp
+            else:
+                res = self.add(res, self.rotate(tmp, i * rot_step, keys[i * rot_step]))
+        if pt_bias is not None:
+            res = self.add_pt(res, pt_bias)
+        return res
+
     def monomial_pts(self):
         """pl_idx[i] = NTT(X^(2^i)) at level 0, scale 1 (conv.go:241-254)."""
         out = np.empty((self.logN, self.N), dtype=np.uint64)

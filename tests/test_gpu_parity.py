@@ -306,6 +306,22 @@ def test_plan_batch_device_and_host_runs(orc, idx_np):
         plan.run_host(in0, in1, o0, o1)
         for m in range(3):
             assert np.array_equal(o0[m], refs[m].c0[0]) and np.array_equal(o1[m], refs[m].c1[0]), m
+        # pipelined submissions (two batches in flight, copies overlap kernels): same bits
+        perm = [[0, 1, 2], [2, 0, 1], [1, 2, 0], [0, 2, 1]]
+        ins0 = [np.stack([w["ct"][m][0] for m in pm]) for pm in perm]
+        ins1 = [np.stack([w["ct"][m][1] for m in pm]) for pm in perm]
+        outs0 = [np.zeros((3, N), dtype=np.uint64) for _ in perm]
+        outs1 = [np.zeros((3, N), dtype=np.uint64) for _ in perm]
+        plan.span_begin()
+        tickets = [plan.submit_host(ins0[i], ins1[i], outs0[i], outs1[i]) for i in range(2)]
+        plan.wait(tickets[0])
+        tickets += [plan.submit_host(ins0[i], ins1[i], outs0[i], outs1[i]) for i in range(2, 4)]
+        for t in tickets:
+            plan.wait(t)
+        assert plan.span_end_ms() > 0
+        for i, pm in enumerate(perm):
+            for j, m in enumerate(pm):
+                assert np.array_equal(outs0[i][j], refs[m].c0[0]) and np.array_equal(outs1[i][j], refs[m].c1[0]), (i, j)
         # permuted inputs give permuted outputs (independent units)
         outs = plan.run([G.cts[2], G.cts[0], G.cts[1]])
         g0, _ = outs[0].download()
@@ -367,5 +383,42 @@ def test_semantic_encrypt_conv_decrypt_full_size(orc):
         got = hp.post_process(dec, raw_w, w_)
         want = hp.plain_conv_same(raw, ker, bn_a, bn_b, raw_w, k, B)
         assert np.abs(got - want).max() < 5e-3, np.abs(got - want).max()
+    finally:
+        c.close()
+
+
+def test_baseline_conv_bl_matches_oracle():
+    """Rotation-per-tap baseline (test_BL.go:98-111 -> eval.go:78-134) at its real shape: parameter set 7,
+    level 1 (56+61 bit), two special primes, B=4 channels -> 2 ciphertext slots-halves of w=128:
+    RotateHoisted(k^2 rotations) + per output rotation: k^2 x (MulNew + Add) + RotateNew + Add + bias."""
+    Q, P = PR.Q_SET7[:2], PR.P_PACK_BL
+    c, o = hec.Context(PR.LOGN, Q, P), Oracle(PR.LOGN, Q, P)
+    try:
+        w_, k = 128, 3
+        max_batch = N // (2 * w_ * w_)  # = 2
+        rot_step = w_ * w_
+        h = k // 2
+        rots = [i * w_ + j for i in range(-h, h + 1) for j in range(-h, h + 1)] + [t * rot_step for t in range(1, max_batch)]
+        keys = {}
+        for r in rots:
+            if r == 0:
+                continue
+            keys[r] = np.stack([np.stack([synth.uniform_limbs(5000 + 13 * (r % 9973) + kk, Q + P, N) for kk in range(2)])])
+            c.upload_swk(o.galois_for_rotation(r), keys[r], 1)
+        a0, a1 = synth.uniform_limbs(61, Q, N), synth.uniform_limbs(62, Q, N)
+        taps_np = [[synth.uniform_limbs(700 + 10 * i + t, Q, N) for t in range(k * k)] for i in range(max_batch)]
+        bias_np = synth.uniform_limbs(99, Q, N)
+        A = c.upload_ct(a0, a1, PR.SCALE)
+        taps = [[c.upload_pt(p, PR.SCALE) for p in row] for row in taps_np]
+        bias = c.upload_pt(bias_np, PR.SCALE * PR.SCALE)
+        res = c.conv_bl(A, w_, k, rot_step, taps, bias)
+        ref = o.conv_bl(Ct(a0, a1, PR.SCALE), w_, k, rot_step, taps_np, PR.SCALE, keys, bias_np)
+        g0, g1 = res.download()
+        assert res.level == 1 and res.scale == ref.scale == PR.SCALE * PR.SCALE
+        assert np.array_equal(g0, ref.c0) and np.array_equal(g1, ref.c1)
+        wrong = c.upload_pt(bias_np, PR.SCALE)  # eval.go:127-129 "Different scale between pl_bn_b and ctxt"
+        with pytest.raises(hec.HecError) as e:
+            c.conv_bl(A, w_, k, rot_step, taps, wrong)
+        assert e.value.code == hec.HEC_E_SCALE
     finally:
         c.close()

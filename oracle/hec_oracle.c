@@ -151,16 +151,34 @@ static void ntt_lazy(const ring_mod *r, int N, const u64 *in, u64 *out) {
         for (int mm = m; mm; mm >>= 1) len++;
         t >>= 1;
         int reduce = (len & 1) || t == 1; /* [A] test_run 0x4eabee: the t==1 stage always reduces */
-        for (int i = 0; i < m; i++) {
-            int j1 = (i * t) << 1;
-            F = r->psi[m + i];
-            for (int j = j1; j < j1 + t; j++) {
-                u64 U = out[j];
-                if (reduce && U >= fourq) U -= fourq;
-                u64 V = mred_lazy(out[j + t], F, q, qinv);
-                out[j] = U + V;
-                out[j + t] = U + twoq - V;
+        const u64 *psi = r->psi + m;
+        if (t >= 8) { /* the reference unrolls these loops x8 (ring_ntt.go) */
+            for (int i = 0; i < m; i++) {
+                u64 *x = out + ((size_t)i * t << 1), *y = x + t;
+                F = psi[i];
+                if (reduce) {
+                    for (int j = 0; j < t; j++) {
+                        u64 U = x[j];
+                        if (U >= fourq) U -= fourq;
+                        u64 V = mred_lazy(y[j], F, q, qinv);
+                        x[j] = U + V; y[j] = U + twoq - V;
+                    }
+                } else {
+                    for (int j = 0; j < t; j++) {
+                        u64 U = x[j];
+                        u64 V = mred_lazy(y[j], F, q, qinv);
+                        x[j] = U + V; y[j] = U + twoq - V;
+                    }
+                }
             }
+        } else {
+            /* t = 4, 2, 1: walk the array in strides of 2t with the inner loop fully unrolled */
+#define BF(a, b, w) do { u64 U = out[a]; if (reduce && U >= fourq) U -= fourq; \
+                         u64 V = mred_lazy(out[b], w, q, qinv); out[a] = U + V; out[b] = U + twoq - V; } while (0)
+            if (t == 4) for (int i = 0; i < m; i++) { int b = i << 3; u64 w = psi[i]; BF(b, b + 4, w); BF(b + 1, b + 5, w); BF(b + 2, b + 6, w); BF(b + 3, b + 7, w); }
+            else if (t == 2) for (int i = 0; i < m; i++) { int b = i << 2; u64 w = psi[i]; BF(b, b + 2, w); BF(b + 1, b + 3, w); }
+            else for (int i = 0; i < m; i++) { int b = i << 1; BF(b, b + 1, psi[i]); }
+#undef BF
         }
     }
 }
@@ -188,17 +206,25 @@ static void intt_core(const ring_mod *r, int N, const u64 *in, u64 *out, int laz
     t <<= 1;
     for (int m = N >> 1; m > 1; m >>= 1) {
         h = m >> 1;
-        for (int i = 0; i < h; i++) {
-            int j1 = (i * t) << 1;
-            u64 F = r->psi_inv[h + i];
-            for (int j = j1; j < j1 + t; j++) {
-                u64 U = out[j], V = out[j + t];
-                u64 X = U + V;
-                if (X >= twoq) X -= twoq;
-                out[j] = X;
-                out[j + t] = mred_lazy(U + fourq - V, F, q, qinv);
+        const u64 *psi = r->psi_inv + h;
+#define IBF(a, b, w) do { u64 U = out[a], V = out[b]; u64 X = U + V; if (X >= twoq) X -= twoq; \
+                          out[a] = X; out[b] = mred_lazy(U + fourq - V, w, q, qinv); } while (0)
+        if (t == 2) for (int i = 0; i < h; i++) { int b = i << 2; u64 w = psi[i]; IBF(b, b + 2, w); IBF(b + 1, b + 3, w); }
+        else if (t == 4) for (int i = 0; i < h; i++) { int b = i << 3; u64 w = psi[i]; IBF(b, b + 4, w); IBF(b + 1, b + 5, w); IBF(b + 2, b + 6, w); IBF(b + 3, b + 7, w); }
+        else {
+            for (int i = 0; i < h; i++) {
+                u64 *x = out + ((size_t)i * t << 1), *y = x + t;
+                u64 F = psi[i];
+                for (int j = 0; j < t; j++) {
+                    u64 U = x[j], V = y[j];
+                    u64 X = U + V;
+                    if (X >= twoq) X -= twoq;
+                    x[j] = X;
+                    y[j] = mred_lazy(U + fourq - V, F, q, qinv);
+                }
             }
         }
+#undef IBF
         t <<= 1;
     }
     if (lazy)

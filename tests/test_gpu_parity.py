@@ -422,3 +422,24 @@ def test_baseline_conv_bl_matches_oracle():
         assert e.value.code == hec.HEC_E_SCALE
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("B", [64, 256])
+def test_conv_full_size_channel_counts(orc, idx_np, B):
+    """BASELINE.json configs 3 and 4 (batch 64 / 256 rows of the (B, w) table, main.go:578-579): the whole
+    pack tree (6 resp. 8 levels, galEl 2^11+1 .. 2^17-1+2) against the oracle, bit for bit.  Kernel width
+    only changes plaintext *contents* (SURVEY.md finding 5), so uniform plaintexts cover k = 3, 5, 7."""
+    c = hec.Context(PR.LOGN, Q2, P1)
+    try:
+        w = common.workload({"B": B, "seed": 400 + B})
+        G = common.GpuConv(c, w, idx_np)
+        res = c.conv_then_pack(G.cts[0], G.ker, 1, PR.SCALE, G.idx, G.bias)
+        g0, g1 = res.download()
+        ref = common.oracle_conv(orc, w, 1, PR.SCALE, idx_np, nthreads=os.cpu_count() or 1)
+        assert np.array_equal(g0, ref.c0) and np.array_equal(g1, ref.c1)
+        if B == 64:  # the op-level replay agrees with the fused path
+            res2 = c.conv_then_pack(G.cts[0], G.ker, 1, PR.SCALE, G.idx, G.bias, hec.CONV_OPLEVEL)
+            h0, h1 = res2.download()
+            assert np.array_equal(h0, g0) and np.array_equal(h1, g1)
+    finally:
+        c.close()

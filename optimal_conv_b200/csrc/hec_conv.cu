@@ -139,6 +139,7 @@ struct hec_plan {
     int B = 0, norm = 1, na = 0, M = 0, levels = 0;
     double in_scale = 0, out_scale = 0;
     const u64 **d_ctin = nullptr, **d_ptk = nullptr;
+    u64 *ptk_scaled = nullptr; // [na][2][N]: kernel plaintexts with the MultByConst constant folded in
     u64 *pool = nullptr; // all scratch / level buffers
     u64 *stage_in = nullptr, *xfinal = nullptr;
     ConvA pa;
@@ -209,6 +210,7 @@ extern "C" void hec_plan_destroy(hec_plan *p) {
     if (p->s_in) cudaStreamDestroy(p->s_in);
     if (p->s_out) cudaStreamDestroy(p->s_out);
     if (p->pool) cudaFree(p->pool);
+    if (p->ptk_scaled) cudaFree(p->ptk_scaled);
     if (p->d_ctin) cudaFree((void *)p->d_ctin);
     if (p->d_ptk) cudaFree((void *)p->d_ptk);
     delete p;
@@ -246,8 +248,20 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
     // ---- device memory: pointer tables + one pool ----
     if (cudaMalloc((void **)&p->d_ctin, M * sizeof(u64 *)) != cudaSuccess) return bail(HEC_E_NOMEM, "cudaMalloc");
     if (cudaMalloc((void **)&p->d_ptk, B * sizeof(u64 *)) != cudaSuccess) return bail(HEC_E_NOMEM, "cudaMalloc");
+    // plan-owned copies of the kernel plaintexts with the MultByConst constants folded in:
+    // (ct*pt)*k == ct*(pt*k); one multiply per coefficient at plan creation instead of one per conv
+    if (cudaMalloc(&p->ptk_scaled, (size_t)na * 2 * HEC_N * sizeof(u64)) != cudaSuccess) return bail(HEC_E_NOMEM, "cudaMalloc");
     std::vector<const u64 *> hk(B, nullptr);
-    for (int i = 0; i < B; i += norm) hk[i] = pt_ker[i]->buf;
+    {
+        std::vector<EwJob> ej;
+        for (int a = 0; a < na; a++) {
+            u64 *dst = p->ptk_scaled + (size_t)a * 2 * HEC_N;
+            hk[a * norm] = dst;
+            for (int l = 0; l < 2; l++)
+                ej.push_back(ewjob(pt_ker[a * norm]->buf + (size_t)l * HEC_N, nullptr, dst + (size_t)l * HEC_N, c->modQ(l), mform(k[l], c->q(c->modQ(l)))));
+        }
+        if (launch_ew<EW_MULSCALAR>(c, ej)) return bail(HEC_E_CUDA, "scaling kernel plaintexts");
+    }
     if (cudaMemcpy((void *)p->d_ptk, hk.data(), B * sizeof(u64 *), cudaMemcpyHostToDevice) != cudaSuccess) return bail(HEC_E_CUDA, "memcpy ptk");
     size_t jobsA = (size_t)M * na * 2;          // limbs per Stage-A buffer
     size_t nb0 = (size_t)M * std::max(1, na / 2);
@@ -270,7 +284,6 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
     ConvA &A = p->pa;
     A.ctin = p->d_ctin; A.ptk = p->d_ptk; A.w1 = w1; A.w2 = w2; A.xout = X[0];
     A.na = na; A.norm = norm; A.mq0 = mq0; A.mq1 = mq1;
-    A.k0m = mform(k[0], q0); A.k1m = mform(k[1], q1);
     A.half1 = (q1 - 1) >> 1;
     A.hneg0 = q0 - A.half1 % q0;
     A.resc0 = c->resc[1][0];

@@ -147,11 +147,11 @@ __global__ void __launch_bounds__(256) k_modup(ModupJobs J, const ModC *__restri
 //            -> Rescale -> divRoundByLastModulusNTT   L:ring/ring_scaling.go:442-513
 struct ConvA {
     const u64 *const *ctin; // [M] -> [2 polys][2 limbs][N]
-    const u64 *const *ptk;  // [B] -> [2 limbs][N], Montgomery form
+    const u64 *const *ptk;  // [B] -> [2 limbs][N]: pl_ker[i] * c_limb in Montgomery form (the MultByConst
+                            //        constant is folded into the plan's copy of the kernel plaintexts)
     u64 *w1, *w2;           // [M*na*2][N] scratch
     u64 *xout;              // [M*na][2][N] level-0 ciphertexts
     int na, norm, mq0, mq1;
-    u64 k0m, k1m;           // MForm(c_i) of the MultByConst constant
     u64 half1;              // (q1-1)>>1
     u64 hneg0;              // q0 - (half1 mod q0)
     u64 resc0;              // MForm(q0 - q1^-1 mod q0)  (RescaleParams)
@@ -160,7 +160,7 @@ struct AJob {
     int c, a, m;
     __device__ __forceinline__ AJob(int job, int na) { c = job & 1; a = (job >> 1) % na; m = (job >> 1) / na; }
 };
-// A1: limb q1:  (ct*pt*k1) -> inverse stages t = 1..128
+// A1: limb q1:  ct*(pt*k1) -> inverse stages t = 1..128
 __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convA1(ConvA P, const ModC *__restrict__ mods) {
     __shared__ u64 sm[16 * HEC_ROW_PITCH];
     const AJob J(blockIdx.y, P.na);
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convA1(ConvA P, const
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         u32 i = G.gbase + 16 * k;
-        x[k] = mred(mred(ct[i], __ldg(pt + i), M.q, M.qinv), P.k1m, M.q, M.qinv);
+        x[k] = mred(ct[i], __ldg(pt + i), M.q, M.qinv);
     }
     row_AtoB(x, sm, G);
     row_inv8(x, sm, G, M);
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convA2(ConvA P, const
 #pragma unroll
     for (int k = 0; k < 16; k++) out[G.gB(k)] = x[k];
 }
-// A3: finish NTT_q0, combine with limb q0 of ct*pt*k0:  out = (p0 - u) * q1^-1
+// A3: finish NTT_q0, combine with limb q0 of ct*(pt*k0):  out = (p0 - u) * q1^-1
 __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convA3(ConvA P, const ModC *__restrict__ mods) {
     __shared__ u64 sm[16 * HEC_ROW_PITCH];
     const AJob J(blockIdx.y, P.na);
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convA3(ConvA P, const
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         u32 i = G.gbase + 16 * k;
-        u64 v = mred(mred(ct[i], __ldg(pt + i), M.q, M.qinv), P.k0m, M.q, M.qinv);
+        u64 v = mred(ct[i], __ldg(pt + i), M.q, M.qinv);
         out[i] = mred(x[k] + M.q2 - v, P.resc0, M.q, M.qinv);
     }
 }

@@ -1,6 +1,7 @@
 // Micro-benchmark: throughput of candidate modular-multiply formulations (sm_100a), in
 // modmuls per clock per SM.  Evidence for the butterfly design; not part of the product.
 #include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 typedef unsigned long long u64;
 typedef unsigned int u32;
@@ -55,6 +56,21 @@ __device__ __forceinline__ u64 shoup32(u64 y, u64 w, u32 ws32, u64 nq) {
     return y * w + qe * nq;
 }
 
+__device__ __forceinline__ u64 shoup_nq(u64 y, u64 w, u64 ws, u64 nq) {
+    return y * w + __umul64hi(y, ws) * nq;
+}
+// full butterflies (CT without correction, GS) on register pairs, as in fwd4/inv4
+__device__ __forceinline__ void ct_free(u64 &X, u64 &Y, u64 w, u64 ws, u64 q, u64 q2) {
+    u64 t = shoup_c(Y, w, ws, q);
+    u64 x = X;
+    X = x + t; Y = x - t + q2;
+}
+__device__ __forceinline__ void gs(u64 &X, u64 &Y, u64 w, u64 ws, u64 q, u64 q2) {
+    u64 u = X, v = Y;
+    u64 s = u + v;
+    X = s >= q2 ? s - q2 : s;
+    Y = shoup_c(u - v + q2, w, ws, q);
+}
 template <int OP>
 __global__ void k(u64 *out, u64 q, u64 qinv, u64 w, u64 ws) {
     u64 y[UNR];
@@ -69,6 +85,9 @@ __global__ void k(u64 *out, u64 q, u64 qinv, u64 w, u64 ws) {
             if (OP == 2) y[i] = shoup_ptx(y[i], w, ws, nq);
             if (OP == 3) y[i] = shoup_approx(y[i], w, ws, nq);
             if (OP == 4) y[i] = shoup32(y[i], w, (u32)(ws >> 32), nq);
+            if (OP == 5) y[i] = shoup_nq(y[i], w, ws, nq);
+            if (OP == 6 && (i & 1) == 0) ct_free(y[i], y[i + 1], w + it, ws, q, 2 * q);
+            if (OP == 7 && (i & 1) == 0) gs(y[i], y[i + 1], w + it, ws, q, 2 * q);
         }
     }
     u64 s = 0;
@@ -76,6 +95,7 @@ __global__ void k(u64 *out, u64 q, u64 qinv, u64 w, u64 ws) {
     for (int i = 0; i < UNR; i++) s += y[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
+static int g_blocks = 4, g_threads = 512;
 template <int OP>
 void run(const char *name) {
     u64 *d;
@@ -86,24 +106,29 @@ void run(const char *name) {
     u64 ws = (u64)((((unsigned __int128)w) << 64) / q);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    k<OP><<<148 * 4, 512>>>(d, q, qinv, w, ws);
+    k<OP><<<148 * g_blocks, g_threads>>>(d, q, qinv, w, ws);
     cudaEventRecord(e0);
-    k<OP><<<148 * 4, 512>>>(d, q, qinv, w, ws);
+    k<OP><<<148 * g_blocks, g_threads>>>(d, q, qinv, w, ws);
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
     float ms;
     cudaEventElapsedTime(&ms, e0, e1);
-    double ops = 148.0 * 4 * 512 * ITERS * UNR;
+    double ops = 148.0 * g_blocks * g_threads * ITERS * UNR;
     double cycles = ms * 1e-3 * 1.965e9;
     printf("%-34s %8.3f ms  %6.2f modmul/clk/SM   %5.1f clk per warp-modmul per SMSP\n", name, ms, ops / cycles / 148,
            cycles * 148 * 4 / (ops / 32));
     cudaFree(d);
 }
-int main() {
+int main(int argc, char **argv) {
+    if (argc > 2) { g_blocks = atoi(argv[1]); g_threads = atoi(argv[2]); }
+    printf("warps per SM: %d\n", g_blocks * g_threads / 32);
     run<0>("montgomery lazy (C)");
     run<1>("shoup (C, __umul64hi)");
     run<2>("shoup (PTX mad/madc, +nq)");
     run<3>("shoup approx hi (3 wide)");
     run<4>("shoup32 (32-bit companion)");
+    run<5>("shoup (C, + qe*(-q))");
+    run<6>("CT butterfly free (x2 = per bfly)");
+    run<7>("GS butterfly (x2 = per bfly)");
     return 0;
 }

@@ -40,9 +40,9 @@ def conv_alg_limbs(B):
     return 10 * B - 1 + 4 * (B.bit_length() - 1)
 
 
-def kernel_alg_limbs(name, M, B):
-    """Distinct limbs one run of fused kernel `name` must read + write (DESIGN.md "Kernels"),
-    summed over its launches in one run (Stage A: 1 launch; Stage B: one per pack level)."""
+def kernel_alg_limbs(name, M, B, first_launch_only=False):
+    """Distinct limbs fused kernel `name` must read + write (DESIGN.md "Kernels"), summed over its
+    launches in one run (Stage A: 1 launch; Stage B: one per pack level) or for its first launch."""
     na, jobs = B, M * B * 2
     if name == "A1":
         return 2 * M + na + jobs            # ct limb q1 of both polys, pt limb q1 per channel, out
@@ -58,8 +58,30 @@ def kernel_alg_limbs(name, M, B):
                 "B3": 3 * nbt + 2,          # w2 (shared by both key polys), 2 key P limbs -> 2 outputs
                 "B4": 4 * nbt,
                 "B5": 8 * nbt + 3 + (1 if n == 2 else 0)}[name]  # w4 x2, a0,a1,b0,b1, mono, 2 key Q limbs (+bias) -> 2 out
+        if first_launch_only:
+            return tot
         n //= 2
     return tot
+
+
+def ncu_traffic(kernel):
+    """dram bytes (read + write) of the first launch of `kernel` from the committed ncu --set full capture
+    (profiles/r01c_ncu_summary.csv: same command, --cts 16), or None."""
+    import csv
+    p = os.path.join(ROOT, "profiles", "r01c_ncu_summary.csv")
+    try:
+        rows = list(csv.reader(open(p)))
+        h = rows[0]
+        for r in rows[2:]:
+            if r[0].startswith(kernel + "("):
+                return (float(r[h.index("dram__bytes_read.sum")]) + float(r[h.index("dram__bytes_write.sum")])) * 1e6
+    except Exception:
+        pass
+    return None
+
+
+# measured integer ceiling of the path (profiles/r01_ubench_int_pipe.txt): Shoup modmul/clk/SM
+INT_MODMUL_PER_CLK_SM = 3.91
 
 
 def peaks():
@@ -273,11 +295,18 @@ def main():
         n_launch = len(times) // reps
         per_kernel[name] = {"ms_per_run": sum(times) / reps, "launches_per_run": n_launch}
     dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_run"])
-    alg_bytes_run = kernel_alg_limbs(dom, M, B) * LIMB
     dom_ms = per_kernel[dom]["ms_per_run"]
-    achieved = alg_bytes_run / (dom_ms / 1e3) / 1e9
     n_l = per_kernel[dom]["launches_per_run"]
     share = dom_ms / sum(v["ms_per_run"] for v in per_kernel.values())
+    # roofline of the dominant kernel, per launch, on its first (largest) launch of a run
+    first_ms = sum(prof[dom][i * n_l] for i in range(3)) / 3
+    alg_bytes_launch = kernel_alg_limbs(dom, M, B, first_launch_only=True) * LIMB
+    achieved = alg_bytes_launch / (first_ms / 1e3) / 1e9
+    # integer ceiling: modular multiplies of one conv / measured modmul throughput
+    units = 4 * B * 2 + 12 * (B - 1)                     # half-transforms (8 stages) per conv
+    modmuls = units * (N // 2) * 8 + (5 * B * 2 + 10 * (B - 1)) * N
+    sm_mhz = (sampler.summary().get("sm_mhz") or 1965.0)
+    int_peak = INT_MODMUL_PER_CLK_SM * 148 * sm_mhz * 1e6
     conv_bytes = conv_alg_limbs(B) * LIMB
     conv_gbs = conv_bytes * (M * args.steps) / (ms_dev / 1e3) / 1e9  # per GPU
 
@@ -296,9 +325,14 @@ def main():
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "roofline": {"bound": "hbm", "kernel": "k_conv" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                     "alg_bytes_per_run": alg_bytes_run, "launches_per_run": n_l,
-                     "avg_launch_ms": dom_ms / max(1, n_l), "share_of_step": share},
+                     "frac": achieved / peak, "traffic": ncu_traffic("k_conv" + dom) if M == 16 and B == 16 else None,
+                     "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes_launch, "launch_ms": first_ms,
+                     "launch": "first (largest) of %d launches per run" % n_l, "share_of_step": share,
+                     "traffic_source": "profiles/r01c_ncu_summary.csv (ncu --set full, same command)"},
+        "roofline_int": {"bound": "integer multiply pipe (fmaheavy)", "modmuls_per_conv": modmuls,
+                         "achieved": modmuls * (M * args.steps) / (ms_dev / 1e3), "peak": int_peak,
+                         "unit": "modmul/s", "frac": modmuls * (M * args.steps) / (ms_dev / 1e3) / int_peak,
+                         "peak_source": "tools/ubench_modmul.cu: 3.91 Shoup modmul/clk/SM (profiles/r01_ubench_int_pipe.txt)"},
         "roofline_conv": {"alg_bytes_per_conv": conv_bytes, "achieved": conv_gbs, "peak": peak, "unit": "GB/s",
                           "frac": conv_gbs / peak, "note": "whole conv, per GPU: (10B-1+4log2B) limbs x convs / time"},
         "kernels_ms_per_run": {k: round(v["ms_per_run"], 4) for k, v in sorted(per_kernel.items())},

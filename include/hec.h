@@ -131,6 +131,14 @@ int hec_conv_then_pack(hec_ctx *ctx, const hec_ct *ct_in, const hec_pt *const *p
 int hec_conv_bl(hec_ctx *ctx, const hec_ct *ct_in, int in_wid, int ker_wid, int rot_iters, int rot_step,
                 const hec_pt *const *pt_taps, const hec_pt *pt_bias, hec_ct **out);
 
+/* ---- between-layer helpers, any level / alpha; masks are host-encoded plaintexts.
+ * ext_ctxt (conv.go:347-371), each half of bsgs_ctxt (conv.go:303-344) and of ext_double_ctxt
+ * (conv.go:374-414): out = sum_i RotateNew(MulNew(input, pts[i]), rots[i]); Rescale(out, min_scale) if
+ * do_rescale.  keep_ctxt (conv.go:417-431): MulNew(input, mask); Rescale. */
+int hec_ext_ctxt(hec_ctx *ctx, const hec_ct *input, int n, const int *rots, const hec_pt *const *pts,
+                 int do_rescale, double min_scale, hec_ct **out);
+int hec_keep_ctxt(hec_ctx *ctx, const hec_ct *input, const hec_pt *mask, double min_scale, hec_ct **out);
+
 /* A prepared evalConv_BN for `batch` independent input ciphertexts per run: kernel
  * plaintexts, monomials, bias and keys stay resident; the kernel sequence is captured in a
  * CUDA graph.  in_level must be 1 (ECD_LV) in this build. */

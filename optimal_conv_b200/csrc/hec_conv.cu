@@ -132,6 +132,47 @@ extern "C" int hec_conv_bl(hec_ctx *ev, const hec_ct *ct_input, int in_wid, int 
 }
 
 // =========================================================================================
+// "next" row: the mask / rotate / rescale helpers between layers, op-level,
+// at any level and alpha.  Masks arrive as host-encoded plaintexts (EncodeNTT, conv.go:312,357).
+// =========================================================================================
+// ext_ctxt (conv.go:347-371) / one half of bsgs_ctxt (conv.go:303-344) / ext_double_ctxt
+// (conv.go:374-414): result = sum_i RotateNew(MulNew(input, pt_i), rot_i) [; Rescale(result, min_scale)]
+extern "C" int hec_ext_ctxt(hec_ctx *ev, const hec_ct *input, int n, const int *rots, const hec_pt *const *pts,
+                            int do_rescale, double min_scale, hec_ct **out) {
+    if (!ev || !input || !rots || !pts || !out || n < 1) return ev ? ev->fail(HEC_E_INVAL, "ext_ctxt args") : HEC_E_INVAL;
+    cudaSetDevice(ev->device);
+    hec_ct *result = nullptr;
+    int rc;
+    for (int i = 0; i < n; i++) {
+        hec_ct *m = nullptr, *r = nullptr;
+        if ((rc = hec_mul_pt_new(ev, input, pts[i], &m))) { if (result) hec_ct_free(ev, result); return rc; }
+        rc = hec_rotate_new(ev, m, rots[i], &r);
+        hec_ct_free(ev, m);
+        if (rc) { if (result) hec_ct_free(ev, result); return rc; }
+        if (!result) result = r;
+        else {
+            rc = hec_add(ev, result, r, result);
+            hec_ct_free(ev, r);
+            if (rc) { hec_ct_free(ev, result); return rc; }
+        }
+    }
+    if (do_rescale && (rc = hec_rescale(ev, result, min_scale))) { hec_ct_free(ev, result); return rc; }
+    *out = result;
+    return HEC_OK;
+}
+// keep_ctxt (conv.go:417-431): MulNew(input, mask) then Rescale(result, params.Scale())
+extern "C" int hec_keep_ctxt(hec_ctx *ev, const hec_ct *input, const hec_pt *mask, double min_scale, hec_ct **out) {
+    if (!ev || !input || !mask || !out) return ev ? ev->fail(HEC_E_INVAL, "keep_ctxt args") : HEC_E_INVAL;
+    cudaSetDevice(ev->device);
+    hec_ct *result = nullptr;
+    int rc;
+    if ((rc = hec_mul_pt_new(ev, input, mask, &result))) return rc;
+    if ((rc = hec_rescale(ev, result, min_scale))) { hec_ct_free(ev, result); return rc; }
+    *out = result;
+    return HEC_OK;
+}
+
+// =========================================================================================
 // fused plan
 // =========================================================================================
 struct hec_plan {

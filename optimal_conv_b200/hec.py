@@ -26,7 +26,7 @@ SYMBOLS = [
     "hec_ct_copy_new", "hec_ct_level", "hec_ct_scale", "hec_ct_set_scale", "hec_ct_free", "hec_swk_upload",
     "hec_swk_drop", "hec_mul_pt_new", "hec_mult_by_const", "hec_rescale", "hec_set_scale", "hec_add", "hec_add_new",
     "hec_sub_new", "hec_add_pt", "hec_rotate_gal", "hec_rotate_new", "hec_rotate_hoisted", "hec_galois_for_rotation",
-    "hec_ntt", "hec_keyswitch", "hec_moddown", "hec_conv_then_pack", "hec_conv_bl", "hec_plan_create", "hec_plan_run",
+    "hec_ntt", "hec_keyswitch", "hec_moddown", "hec_conv_then_pack", "hec_conv_bl", "hec_ext_ctxt", "hec_keep_ctxt", "hec_plan_create", "hec_plan_run",
     "hec_plan_run_host", "hec_plan_submit_host", "hec_plan_wait", "hec_plan_span_begin", "hec_plan_span_end_ms",
     "hec_plan_profile", "hec_plan_destroy",
 ]
@@ -94,6 +94,8 @@ def lib():
     L.hec_conv_then_pack.argtypes = [vp, vp, C.POINTER(vp), C.c_int, C.c_int, C.c_double, C.POINTER(vp), vp, C.c_int,
                                      C.POINTER(vp)]
     L.hec_conv_bl.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp), vp, C.POINTER(vp)]
+    L.hec_ext_ctxt.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int), C.POINTER(vp), C.c_int, C.c_double, C.POINTER(vp)]
+    L.hec_keep_ctxt.argtypes = [vp, vp, vp, C.c_double, C.POINTER(vp)]
     L.hec_plan_create.argtypes = [vp, C.POINTER(vp), C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(vp), vp,
                                   C.c_int, C.POINTER(vp)]
     L.hec_plan_run.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
@@ -313,6 +315,23 @@ class Context:
         h = vp()
         self._chk(self.L.hec_conv_bl(self.h, ct_in.h, in_wid, ker_wid, len(pt_taps), rot_step, arr,
                                      pt_bias.h if pt_bias is not None else None, C.byref(h)))
+        return Ciphertext(self, h)
+
+    def ext_ctxt(self, ct, r_idx, min_scale=None):
+        """ext_ctxt (conv.go:347-371); r_idx: {rot: Plaintext}; min_scale=None skips the Rescale
+        (the two halves of bsgs_ctxt / the first half of ext_double_ctxt)."""
+        rots = list(r_idx)
+        ra = (C.c_int * len(rots))(*rots)
+        pa = (vp * len(rots))(*[r_idx[r].h for r in rots])
+        h = vp()
+        self._chk(self.L.hec_ext_ctxt(self.h, ct.h, len(rots), ra, pa, int(min_scale is not None),
+                                      float(min_scale or 0.0), C.byref(h)))
+        return Ciphertext(self, h)
+
+    def keep_ctxt(self, ct, mask, min_scale):
+        """keep_ctxt (conv.go:417-431)."""
+        h = vp()
+        self._chk(self.L.hec_keep_ctxt(self.h, ct.h, mask.h, min_scale, C.byref(h)))
         return Ciphertext(self, h)
 
     def plan(self, pt_ker, norm, in_scale, out_scale, pt_idx, pt_bias, batch):

@@ -271,6 +271,18 @@ class Oracle:
             res = self.add_pt(res, pt_bias)
         return res
 
+    def ext_ctxt(self, ct, r_idx, pt_scale, keys, min_scale=None):
+        """ext_ctxt (conv.go:347-371): sum_rot RotateNew(MulNew(input, pt_rot), rot) [+ Rescale]."""
+        res = None
+        for rot, pt in r_idx.items():
+            t = self.rotate(self.mul_pt(ct, pt, pt_scale), rot, keys[rot])
+            res = t if res is None else self.add(res, t)
+        return self.rescale(res, min_scale) if min_scale is not None else res
+
+    def keep_ctxt(self, ct, mask, pt_scale, min_scale):
+        """keep_ctxt (conv.go:417-431)."""
+        return self.rescale(self.mul_pt(ct, mask, pt_scale), min_scale)
+
     def monomial_pts(self):
         """pl_idx[i] = NTT(X^(2^i)) at level 0, scale 1 (conv.go:241-254)."""
         out = np.empty((self.logN, self.N), dtype=np.uint64)

@@ -443,3 +443,63 @@ def test_conv_full_size_channel_counts(orc, idx_np, B):
             assert np.array_equal(h0, g0) and np.array_equal(h1, g1)
     finally:
         c.close()
+
+
+def test_between_layer_helpers_alpha5():
+    """ext_ctxt / ext_double_ctxt / keep_ctxt (conv.go:347-431) at level 5 of parameter
+    set 6 with the main evaluator's five special primes (alpha = 5: a full 5-limb digit through the
+    float-assisted basis extension + a truncated 1-limb digit), then Rescale by a 30-bit ReLU prime."""
+    Q, P = PR.Q_SET6[:6], PR.P_ALL
+    c, o = hec.Context(PR.LOGN, Q, P), Oracle(PR.LOGN, Q, P)
+    try:
+        rots = [3, -64, 4096]
+        keys = {}
+        for r in rots:
+            keys[r] = np.stack([np.stack([synth.uniform_limbs(8000 + 17 * (r % 7919) + 3 * d + kk, Q + P, N)
+                                          for kk in range(2)]) for d in range(2)])
+            c.upload_swk(o.galois_for_rotation(r), keys[r], 5)
+        a0, a1 = synth.uniform_limbs(71, Q, N), synth.uniform_limbs(72, Q, N)
+        pscale = float(Q[5])  # NewPlaintext(params, input.Level(), float64(params.Q()[input.Level()]))
+        masks_np = {r: synth.uniform_limbs(900 + i, Q, N) for i, r in enumerate(rots)}
+        A = c.upload_ct(a0, a1, PR.SCALE)
+        masks = {r: c.upload_pt(m, pscale) for r, m in masks_np.items()}
+        oct = Ct(a0, a1, PR.SCALE)
+        # ext_ctxt
+        res = c.ext_ctxt(A, masks, PR.SCALE)
+        ref = o.ext_ctxt(oct, masks_np, pscale, keys, PR.SCALE)
+        g0, g1 = res.download()
+        assert res.level == ref.level == 4 and res.scale == ref.scale
+        assert np.array_equal(g0, ref.c0) and np.array_equal(g1, ref.c1)
+        # ext_double_ctxt: first pass without Rescale, second pass with (conv.go:374-414)
+        mid = c.ext_ctxt(A, masks)
+        res2 = c.ext_ctxt(mid, masks, PR.SCALE)
+        omid = o.ext_ctxt(oct, masks_np, pscale, keys)
+        ref2 = o.ext_ctxt(omid, masks_np, pscale, keys, PR.SCALE)
+        g0, g1 = res2.download()
+        assert res2.level == ref2.level and res2.scale == ref2.scale
+        assert np.array_equal(g0, ref2.c0) and np.array_equal(g1, ref2.c1)
+        # keep_ctxt
+        res3 = c.keep_ctxt(A, masks[3], PR.SCALE)
+        ref3 = o.keep_ctxt(oct, masks_np[3], pscale, PR.SCALE)
+        g0, g1 = res3.download()
+        assert res3.level == ref3.level == 4 and np.array_equal(g0, ref3.c0) and np.array_equal(g1, ref3.c1)
+    finally:
+        c.close()
+
+
+def test_full_level_keyswitch_alpha5_beta6():
+    """The 'full RNS level' stress shape of SURVEY.md 8d: level 27 (28 Q limbs), alpha = 5, beta = 6
+    (five 5-limb digits + one 3-limb digit), 198 MiB switching key -- what `resnet` rotations see."""
+    Q, P = PR.Q_SET6, PR.P_ALL
+    c, o = hec.Context(PR.LOGN, Q, P), Oracle(PR.LOGN, Q, P)
+    try:
+        g = o.galois_for_rotation(7)
+        key = np.stack([np.stack([synth.uniform_limbs(6000 + 3 * d + kk, Q + P, N) for kk in range(2)]) for d in range(6)])
+        c.upload_swk(g, key, 27)
+        for level in (27, 12):
+            c1 = synth.uniform_limbs(81 + level, Q[:level + 1], N)
+            d0, d1 = c.keyswitch(c1, g)
+            e0, e1 = o.keyswitch(c1, key)
+            assert np.array_equal(d0, e0) and np.array_equal(d1, e1), level
+    finally:
+        c.close()

@@ -19,7 +19,6 @@ import os
 import statistics
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -91,24 +90,35 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-class ClockSampler(threading.Thread):
-    def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+class ClockSampler:
+    """nvidia-smi -lms sampling of SM clocks and throttle reasons during the timed region
+    (B200_PROFILING.md clocks line)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def run(self):
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 6:
-                    self.rows.append(f)
-            except Exception:
-                pass
-            time.sleep(0.2)
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 6:
+                self.rows.append(f)
 
     def summary(self):
         if not self.rows:
@@ -166,9 +176,9 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--cts", type=int, default=16, help="independent input ciphertexts per step per GPU")
+    ap.add_argument("--cts", type=int, default=32, help="independent input ciphertexts per step per GPU")
     ap.add_argument("--batch", type=int, default=16, help="B: output channels packed per ciphertext")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=12, help="convs timed for cpu_baseline (0 = skip)")
@@ -259,7 +269,6 @@ def main():
     # ---- kernel-resident throughput ----
     timed(step_dev, args.warmup)
     sampler = ClockSampler(local)
-    sampler.start()
     barrier()
     l0 = ctx.launch_count()
     ms_dev = timed(step_dev, args.steps)
@@ -271,7 +280,16 @@ def main():
     ms_e2e = e2e_pipelined(args.steps)
     barrier()
     ms_e2e_sync = timed(step_e2e_sync, max(3, args.steps // 4)) / max(3, args.steps // 4)
-    sampler.stop_flag = True
+    sampler.stop()
+    # ---- latency of a single conv (batch of one ciphertext), device resident ----
+    plan1 = ctx.plan(ker, 1, PR.SCALE, PR.SCALE, idx, bias, 1)
+    lat = []
+    for i in range(13):
+        torch.cuda.synchronize()
+        ctx.timer_start()
+        plan1.run(dev_in[i % ring][:1])
+        lat.append(ctx.timer_stop_ms())
+    latency_ms = statistics.median(lat[3:])
     # ---- per-kernel times (kernels launched one by one) for the roofline of the dominant kernel ----
     prof = {}
     for rep in range(3):
@@ -325,7 +343,7 @@ def main():
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "roofline": {"bound": "hbm", "kernel": "k_conv" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": ncu_traffic("k_conv" + dom) if M == 16 and B == 16 else None,
+                     "frac": achieved / peak, "traffic": ncu_traffic("k_conv" + dom) if M == 16 and B == 16 else None,  # the ncu capture ran --cts 16
                      "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes_launch, "launch_ms": first_ms,
                      "launch": "first (largest) of %d launches per run" % n_l, "share_of_step": share,
                      "traffic_source": "profiles/r01c_ncu_summary.csv (ncu --set full, same command)"},
@@ -336,6 +354,7 @@ def main():
         "roofline_conv": {"alg_bytes_per_conv": conv_bytes, "achieved": conv_gbs, "peak": peak, "unit": "GB/s",
                           "frac": conv_gbs / peak, "note": "whole conv, per GPU: (10B-1+4log2B) limbs x convs / time"},
         "kernels_ms_per_run": {k: round(v["ms_per_run"], 4) for k, v in sorted(per_kernel.items())},
+        "latency_ms_single_conv": latency_ms,
     }
     # ---- CPU baseline beside it: the oracle port, 1 thread (the reference is single-threaded) ----
     if world == 1 and args.cpu_sample > 0:

@@ -190,11 +190,12 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convA2(ConvA P, const
 #pragma unroll
     for (int k = 0; k < 16; k++) x[k] = in[G.gB(k)];
     col_inv8(x, sm, G, M1);
+    const bool fits = M1.q <= M0.q; // t < q1 <= q0 is already a canonical residue of q0
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         u64 t = inv_final(x[k], M1);                        // InvNTT final pass, canonical
         t = cred(t + P.half1, M1.q);                        // + (q1-1)/2 mod q1
-        x[k] = mred(t, M0.rmod, M0.q, M0.qinv) + P.hneg0;   // (t mod q0) - half  in [0,2q0)
+        x[k] = (fits ? t : canon(t, M0)) + P.hneg0;         // (t mod q0) - half  in [0,2q0)
     }
     col_fwd8(x, sm, G, M0);
 #pragma unroll

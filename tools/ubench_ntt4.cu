@@ -1,0 +1,67 @@
+// Micro-benchmark: cycles per butterfly of the real fwd4 / inv4 register kernels (hec_dev.cuh) with
+// twiddles from global memory (L1/L2 hits), without any global data traffic.  Evidence for where the
+// fused kernels lose time relative to the bare butterfly (tools/ubench_modmul.cu).
+#include <cstdio>
+#include <cstdlib>
+#include "../optimal_conv_b200/csrc/hec_dev.cuh"
+#define ITERS 256
+
+template <int OP>
+__global__ void __launch_bounds__(256, 3) k(u64 *out, const ModC *mods, int it_n) {
+    const ModC M = mods[0];
+    u64 x[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) x[i] = (threadIdx.x * 977 + i * 31 + blockIdx.x) * 0x9E3779B97F4A7C15ull % M.q;
+    for (int it = 0; it < it_n; it++) {
+        u32 base = 16 + ((threadIdx.x >> 4) + it) % 240;
+        if (OP == 0) fwd4<false>(x, M.psi, base, M.q, M.q2);
+        if (OP == 1) fwd4<true>(x, M.psi, base, M.q, M.q2);
+        if (OP == 2) inv4(x, M.psi_inv, base, M.q, M.q2);
+        if (OP == 3) { fwd4<false>(x, M.psi, 1, M.q, M.q2); }            // uniform twiddles (column layout A)
+        if (OP == 0 || OP == 3) {                                          // keep the free-mode values bounded
+#pragma unroll
+            for (int i = 0; i < 16; i++) x[i] &= 0x00ffffffffffffffull;
+        }
+    }
+    u64 s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += x[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+template <int OP>
+void run(const char *name, const ModC *dm) {
+    u64 *d;
+    cudaMalloc(&d, 148 * 3 * 256 * 8);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    k<OP><<<148 * 3, 256>>>(d, dm, ITERS);
+    cudaEventRecord(e0);
+    k<OP><<<148 * 3, 256>>>(d, dm, ITERS);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    double bfly = 148.0 * 3 * 256 * ITERS * 32; // 32 butterflies per fwd4/inv4 per thread
+    double cycles = ms * 1e-3 * 1.965e9;
+    printf("%-40s %7.3f ms  %6.1f clk per warp-butterfly per SMSP\n", name, ms, cycles * 148 * 4 / (bfly / 32));
+    cudaFree(d);
+}
+int main() {
+    // a fake table is fine for timing: (w, ws) pairs
+    u64 q = 0x80000000080001ull;
+    ulonglong2 *tab;
+    cudaMalloc(&tab, 65536 * sizeof(ulonglong2));
+    ulonglong2 *h = (ulonglong2 *)malloc(65536 * sizeof(ulonglong2));
+    for (int i = 0; i < 65536; i++) { u64 w = (0x1234567ull * (i + 1)) % q; h[i] = make_ulonglong2(w, (u64)((((unsigned __int128)w) << 64) / q)); }
+    cudaMemcpy(tab, h, 65536 * sizeof(ulonglong2), cudaMemcpyHostToDevice);
+    ModC m;
+    m.q = q; m.q2 = 2 * q; m.qinv = 1; m.rmod = 1; m.ninv_w = 1; m.ninv_s = 1; m.psi = tab; m.psi_inv = tab; m.tight = 0; m.pad = 0;
+    ModC *dm;
+    cudaMalloc(&dm, sizeof(ModC));
+    cudaMemcpy(dm, &m, sizeof(ModC), cudaMemcpyHostToDevice);
+    run<0>("fwd4<free>, per-thread-group twiddles", dm);
+    run<1>("fwd4<tight>", dm);
+    run<2>("inv4", dm);
+    run<3>("fwd4<free>, uniform twiddles", dm);
+    return 0;
+}

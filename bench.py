@@ -173,6 +173,67 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_side_workload(args):
+    """Measured numbers for the other rows of SURVEY.md section 8 (op-level, generic kernels):
+    --workload conv_bl    : one evalConv_BN_BL_test interval (eval.go:108-131), set 7, level 1, alpha = 2,
+                            B=4 (w=128, k=3): 9 hoisted rotations + 2 x (9 MulNew/Add + RotateNew) + bias
+    --workload keyswitch  : KeySwitcher.SwitchKeysInPlace at level 27, alpha = 5, beta = 6 (SURVEY.md 8d stress)"""
+    import torch
+    from optimal_conv_b200 import hec
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    if args.workload == "keyswitch":
+        Q, P, level = PR.Q_SET6, PR.P_ALL, 27
+        ctx = hec.Context(PR.LOGN, Q, P)
+        g = ctx.galois_for_rotation(7)
+        key = np.stack([np.stack([synth.uniform_limbs(6000 + 3 * d + kk, Q + P, N) for kk in range(2)]) for d in range(6)])
+        ctx.upload_swk(g, key, level)
+        a0, a1 = synth.uniform_limbs(1, Q, N), synth.uniform_limbs(2, Q, N)
+        A = ctx.upload_ct(a0, a1, PR.SCALE)
+        out = ctx.CopyNew(A)
+
+        def step():
+            ctx.RotateGal(A, g, out)
+        unit, name = "rotations/s", "RotateGal (key-switch + automorphism) at level 27, alpha=5, beta=6"
+        # L (c1) + 2*beta*(L+alpha) (key) + 2L (out) + L (c0) limbs, SURVEY.md 8d
+        alg = (28 + 2 * 6 * 33 + 2 * 28 + 28) * LIMB
+    else:
+        Q, P = PR.Q_SET7[:2], PR.P_PACK_BL
+        ctx = hec.Context(PR.LOGN, Q, P)
+        w_, k = 128, 3
+        max_batch, rot_step, h = N // (2 * w_ * w_), w_ * w_, k // 2
+        rots = [i * w_ + j for i in range(-h, h + 1) for j in range(-h, h + 1)] + [t * rot_step for t in range(1, max_batch)]
+        for r in rots:
+            if r:
+                ctx.upload_swk(ctx.galois_for_rotation(r), np.stack([np.stack(
+                    [synth.uniform_limbs(5000 + 13 * (r % 9973) + kk, Q + P, N) for kk in range(2)])]), 1)
+        A = ctx.upload_ct(synth.uniform_limbs(61, Q, N), synth.uniform_limbs(62, Q, N), PR.SCALE)
+        taps = [[ctx.upload_pt(synth.uniform_limbs(700 + 10 * i + t, Q, N), PR.SCALE) for t in range(k * k)] for i in range(max_batch)]
+        bias = ctx.upload_pt(synth.uniform_limbs(99, Q, N), PR.SCALE * PR.SCALE)
+
+        def step():
+            ctx.conv_bl(A, w_, k, rot_step, taps, bias).free()
+        unit, name = "baseline conv calls/s", "evalConv_BN_BL_test interval, B=4 (2 slots-halves), w=128, k=3, level 1, alpha=2"
+        alg = None
+    for _ in range(max(3, args.warmup)):
+        step()
+    ctx.sync()
+    l0 = ctx.launch_count()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        step()
+    ms = ctx.timer_stop_ms()
+    line = {"metric": name, "value": args.steps / (ms / 1e3), "unit": unit, "n_gpus": 1, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "dtype": "u64",
+            "data": "synthetic", "config": {"workload": args.workload, "path": "op-level generic kernels"},
+            "gpu_launches": ctx.launch_count() - l0}
+    if alg:
+        peak, src = peaks()
+        line["roofline"] = {"bound": "hbm", "achieved": alg / (ms / args.steps / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                            "frac": alg / (ms / args.steps / 1e3) / 1e9 / peak, "traffic": None, "peak_source": src}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -181,12 +242,16 @@ def main():
     ap.add_argument("--cts", type=int, default=32, help="independent input ciphertexts per step per GPU")
     ap.add_argument("--batch", type=int, default=16, help="B: output channels packed per ciphertext")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="conv", choices=["conv", "conv_bl", "keyswitch"],
+                    help="conv = the headline fused path; the others are op-level side measurements")
     ap.add_argument("--cpu-sample", type=int, default=12, help="convs timed for cpu_baseline (0 = skip)")
     ap.add_argument("--ring", type=int, default=8, help="distinct input batches rotated through (> L2)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload != "conv":
+        return run_side_workload(args)
 
     import torch
     import torch.distributed as dist

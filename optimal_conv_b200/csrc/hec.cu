@@ -199,6 +199,13 @@ extern "C" int hec_ctx_create(hec_ctx **out, int logN, const uint64_t *Q, int nQ
     }
     auto bail = [&](int code) { hec_ctx_destroy(c); return code; };
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(HEC_E_CUDA);
+    {   // keep freed ciphertext buffers cached in the pool instead of returning them to the driver
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
     size_t tw = (size_t)nm * 2 * HEC_N;
@@ -293,9 +300,11 @@ extern "C" uint64_t hec_launch_count(const hec_ctx *c) { return c ? c->launches 
 int hec_ct_alloc(hec_ctx *c, int level, double scale, hec_ct **out) {
     hec_ct *ct = new hec_ct();
     ct->alloc = level + 1; ct->level = level; ct->scale = scale;
-    if (cudaMalloc(&ct->buf, (size_t)2 * ct->alloc * HEC_N * sizeof(u64)) != cudaSuccess) {
+    // stream-ordered allocation: temporaries of the op-level path come from the device's memory pool and
+    // are recycled without synchronising the stream
+    if (cudaMallocAsync(&ct->buf, (size_t)2 * ct->alloc * HEC_N * sizeof(u64), c->stream) != cudaSuccess) {
         delete ct;
-        return c->fail(HEC_E_NOMEM, "cudaMalloc ciphertext");
+        return c->fail(HEC_E_NOMEM, "cudaMallocAsync ciphertext");
     }
     *out = ct;
     return HEC_OK;
@@ -367,8 +376,12 @@ extern "C" double hec_ct_scale(const hec_ct *ct) { return ct ? ct->scale : 0.0; 
 extern "C" void hec_ct_set_scale(hec_ct *ct, double s) { if (ct) ct->scale = s; }
 extern "C" void hec_ct_free(hec_ctx *c, hec_ct *ct) {
     if (!ct) return;
-    if (c) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
-    if (ct->owned) cudaFree(ct->buf);
+    if (c) {
+        cudaSetDevice(c->device);
+        if (ct->owned) cudaFreeAsync(ct->buf, c->stream); // ordered after every kernel that used it
+    } else if (ct->owned) {
+        cudaFree(ct->buf);
+    }
     delete ct;
 }
 

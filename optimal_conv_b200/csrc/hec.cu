@@ -41,16 +41,35 @@ void build_mod(HostMod &m, u64 q) {
     m.gen = primitive_root(q);
     u64 psi = powmod(m.gen, (q - 1) / (2 * N), q);
     u64 psi_i = invmod(psi, q);
-    m.psi.resize(N);
-    m.psi_inv.resize(N);
-    u64 a = 1, b = 1; // psi^j, psi^-j
+    // NttPsi[brev(j)] = psi^j and NttPsiInv[brev(j)] = psi^-j (L:ring/ring.go:118-200), plain residues
+    std::vector<u64> tab(N), tabi(N);
+    u64 a = 1, b = 1;
     for (u32 j = 0; j < N; j++) {
         u32 r = bitrev16(j);
-        m.psi[r] = make_ulonglong2(a, shoup(a));
-        m.psi_inv[r] = make_ulonglong2(b, shoup(b));
+        tab[r] = a;
+        tabi[r] = b;
         a = mulmod(a, psi, q);
         b = mulmod(b, psi_i, q);
     }
+    // device order: the 15 twiddles {ng*base + gi} of every `base`, in consumption order (hec_dev.cuh fwd4)
+    m.psi.assign(N, make_ulonglong2(0, 0));
+    m.psi_inv.assign(N, make_ulonglong2(0, 0));
+    auto put = [&](size_t dst, u32 base, int j) {
+        int lg = 0;
+        while ((2 << lg) - 1 <= j) lg++;      // slot j = (2^lg - 1) + gi
+        u32 ng = 1u << lg, gi = (u32)j - (ng - 1);
+        u32 idx = ng * base + gi;
+        m.psi[dst] = make_ulonglong2(tab[idx], shoup(tab[idx]));
+        m.psi_inv[dst] = make_ulonglong2(tabi[idx], shoup(tabi[idx]));
+    };
+    for (int j = 0; j < 15; j++) put(HEC_TW_COLA + j, 1, j);
+    for (u32 g = 0; g < 16; g++)
+        for (int j = 0; j < 15; j++) put(HEC_TW_COLB + 15 * g + j, 16 + g, j);
+    for (u32 blk = 0; blk < 256; blk++)
+        for (int j = 0; j < 15; j++) put(HEC_TW_ROWA + 15 * blk + j, 256 + blk, j);
+    for (u32 blk = 0; blk < 256; blk++)
+        for (int j = 0; j < 15; j++)
+            for (u32 p = 0; p < 16; p++) put(HEC_TW_ROWB + 240 * blk + 16 * j + p, 4096 + 16 * blk + p, j);
 }
 
 static void build_modup(const hec_ctx *c, ModupTab &T, const std::vector<int> &src) {

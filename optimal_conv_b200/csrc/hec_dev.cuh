@@ -42,8 +42,8 @@ struct ModC {
     u64 q2;           // 2q
     u64 rmod;         // R mod q  (mred(x, rmod) = x mod q, canonical)
     u64 ninv_w, ninv_s; // N^-1 mod q and its Shoup companion
-    const ulonglong2 *psi;     // (psi^j, floor(psi^j * 2^64 / q)) at index brev(j)
-    const ulonglong2 *psi_inv; // same for psi^-j
+    const ulonglong2 *psi;     // Shoup pairs (w, floor(w * 2^64 / q)) of NttPsi, in consumption order (see fwd4)
+    const ulonglong2 *psi_inv; // same for NttPsiInv
     int tight;        // q >= 2^58: forward transform needs range corrections
     int pad;
 };
@@ -87,22 +87,35 @@ __device__ __forceinline__ void gs_bfly(u64 &X, u64 &Y, ulonglong2 w, u64 q, u64
 }
 
 // Four forward stages on 16 register-resident coefficients.  The coefficient at slot k
-// pairs with slot k+d for d = 8,4,2,1; stage d uses twiddles psi[ng*base + gi], ng = 8/d,
-// gi = k / (2d).  `base` encodes where the 16 coefficients sit in the limb:
+// pairs with slot k+d for d = 8,4,2,1; stage d uses twiddles NttPsi[ng*base + gi], ng = 8/d,
+// gi = k / (2d), where `base` encodes where the 16 coefficients sit in the limb:
 //   column kernel, rows p+16k : base = 1            column kernel, rows 16g+k : base = 16+g
 //   row kernel, words p+16k   : base = 256+b        row kernel, words 16p+k   : base = 4096+16b+p
+// The device tables hold exactly these 15 twiddles per base, in the order they are consumed
+// (slot j = ng-1+gi), so a thread reads t[j*stride]: contiguous per thread for the first three
+// layouts, and interleaved over the 16 lanes of a block for the last one (coalesced 256-byte
+// reads instead of 16 different cache lines -- profiles/r01_ubench_int_pipe.txt).  Table layout
+// (one array of N pairs per modulus and direction, a permutation of NttPsi[1..N-1]):
+//   [0,16)       column layout A              t = T + 0,                 stride 1
+//   [16,256)     column layout B, [g][15]     t = T + 16 + 15 g,         stride 1
+//   [256,4096)   row layout A', [b][15]       t = T + 256 + 15 b,        stride 1
+//   [4096,65536) row layout B', [b][15][16]   t = T + 4096 + 240 b + p,  stride 16
 // Ranges.  Each stage adds at most 2q to a value.  TIGHT = false (q < 2^58): no correction;
 // a 16-stage transform of inputs < 4q stays < 36q < 2^64.  TIGHT = true (q < 2^61): the first
 // and third stage pull X back below 4q, so values entering are < 8q and values leaving are
 // < 8q < 2^64 (the Y operand never needs it: shoup() accepts any 64-bit value).
-template <bool TIGHT>
-__device__ __forceinline__ void fwd4(u64 (&x)[16], const ulonglong2 *__restrict__ psi, u32 base, u64 q, u64 q2) {
+#define HEC_TW_COLA 0
+#define HEC_TW_COLB 16
+#define HEC_TW_ROWA 256
+#define HEC_TW_ROWB 4096
+template <bool TIGHT, int STRIDE>
+__device__ __forceinline__ void fwd4(u64 (&x)[16], const ulonglong2 *__restrict__ t, u64 q, u64 q2) {
 #pragma unroll
     for (int lg = 0; lg < 4; lg++) {
         const int d = 8 >> lg, ng = 1 << lg;
 #pragma unroll
         for (int gi = 0; gi < ng; gi++) {
-            ulonglong2 w = __ldg(psi + ng * base + gi);
+            ulonglong2 w = __ldg(t + (ng - 1 + gi) * STRIDE);
 #pragma unroll
             for (int k = 0; k < d; k++) {
                 if (TIGHT && (lg == 0 || lg == 2)) ct_bfly<true>(x[gi * 2 * d + k], x[gi * 2 * d + k + d], w, q, q2);
@@ -111,14 +124,15 @@ __device__ __forceinline__ void fwd4(u64 (&x)[16], const ulonglong2 *__restrict_
         }
     }
 }
-// Four inverse stages (d = 1,2,4,8), same indexing with the psi_inv table.
-__device__ __forceinline__ void inv4(u64 (&x)[16], const ulonglong2 *__restrict__ psi_inv, u32 base, u64 q, u64 q2) {
+// Four inverse stages (d = 1,2,4,8), same slots from the psi^-1 table.
+template <int STRIDE>
+__device__ __forceinline__ void inv4(u64 (&x)[16], const ulonglong2 *__restrict__ t, u64 q, u64 q2) {
 #pragma unroll
     for (int lg = 3; lg >= 0; lg--) {
         const int d = 8 >> lg, ng = 1 << lg;
 #pragma unroll
         for (int gi = 0; gi < ng; gi++) {
-            ulonglong2 w = __ldg(psi_inv + ng * base + gi);
+            ulonglong2 w = __ldg(t + (ng - 1 + gi) * STRIDE);
 #pragma unroll
             for (int k = 0; k < d; k++) gs_bfly(x[gi * 2 * d + k], x[gi * 2 * d + k + d], w, q, q2);
         }
@@ -146,8 +160,8 @@ struct RowGeom {
         gbase = b * 256 + p;
         sbase = bb * HEC_ROW_PITCH;
     }
-    __device__ __forceinline__ u32 baseA() const { return 256 + b; }
-    __device__ __forceinline__ u32 baseB() const { return 4096 + 16 * b + p; }
+    __device__ __forceinline__ u32 twA() const { return HEC_TW_ROWA + 15 * b; }
+    __device__ __forceinline__ u32 twB() const { return HEC_TW_ROWB + 240 * b + p; }
 };
 __device__ __forceinline__ void row_loadA(u64 (&x)[16], const u64 *__restrict__ g, const RowGeom &G) {
 #pragma unroll
@@ -182,20 +196,20 @@ __device__ __forceinline__ void row_loadB(u64 (&x)[16], const u64 *__restrict__ 
 // in: layout A' (values < 4q, or < 8q if tight); out: layout B' (lazy, see fwd4)
 __device__ __forceinline__ void row_fwd8(u64 (&x)[16], u64 *sm, const RowGeom &G, const ModC &M) {
     if (M.tight) {
-        fwd4<true>(x, M.psi, G.baseA(), M.q, M.q2);
+        fwd4<true, 1>(x, M.psi + G.twA(), M.q, M.q2);
         row_AtoB(x, sm, G);
-        fwd4<true>(x, M.psi, G.baseB(), M.q, M.q2);
+        fwd4<true, 16>(x, M.psi + G.twB(), M.q, M.q2);
     } else {
-        fwd4<false>(x, M.psi, G.baseA(), M.q, M.q2);
+        fwd4<false, 1>(x, M.psi + G.twA(), M.q, M.q2);
         row_AtoB(x, sm, G);
-        fwd4<false>(x, M.psi, G.baseB(), M.q, M.q2);
+        fwd4<false, 16>(x, M.psi + G.twB(), M.q, M.q2);
     }
 }
 // in: layout B' (values < 2q); out: layout A' (< 2q)
 __device__ __forceinline__ void row_inv8(u64 (&x)[16], u64 *sm, const RowGeom &G, const ModC &M) {
-    inv4(x, M.psi_inv, G.baseB(), M.q, M.q2);
+    inv4<16>(x, M.psi_inv + G.twB(), M.q, M.q2);
     row_BtoA(x, sm, G);
-    inv4(x, M.psi_inv, G.baseA(), M.q, M.q2);
+    inv4<1>(x, M.psi_inv + G.twA(), M.q, M.q2);
 }
 
 // ---- column-kernel tile geometry ---------------------------------------------------------
@@ -232,20 +246,20 @@ __device__ __forceinline__ void col_BtoA(u64 (&x)[16], u64 *sm, const ColGeom &G
 // in: layout A, out: layout B
 __device__ __forceinline__ void col_fwd8(u64 (&x)[16], u64 *sm, const ColGeom &G, const ModC &M) {
     if (M.tight) {
-        fwd4<true>(x, M.psi, 1, M.q, M.q2);
+        fwd4<true, 1>(x, M.psi + HEC_TW_COLA, M.q, M.q2);
         col_AtoB(x, sm, G);
-        fwd4<true>(x, M.psi, 16 + G.pg, M.q, M.q2);
+        fwd4<true, 1>(x, M.psi + HEC_TW_COLB + 15 * G.pg, M.q, M.q2);
     } else {
-        fwd4<false>(x, M.psi, 1, M.q, M.q2);
+        fwd4<false, 1>(x, M.psi + HEC_TW_COLA, M.q, M.q2);
         col_AtoB(x, sm, G);
-        fwd4<false>(x, M.psi, 16 + G.pg, M.q, M.q2);
+        fwd4<false, 1>(x, M.psi + HEC_TW_COLB + 15 * G.pg, M.q, M.q2);
     }
 }
 // in: layout B, out: layout A
 __device__ __forceinline__ void col_inv8(u64 (&x)[16], u64 *sm, const ColGeom &G, const ModC &M) {
-    inv4(x, M.psi_inv, 16 + G.pg, M.q, M.q2);
+    inv4<1>(x, M.psi_inv + HEC_TW_COLB + 15 * G.pg, M.q, M.q2);
     col_BtoA(x, sm, G);
-    inv4(x, M.psi_inv, 1, M.q, M.q2);
+    inv4<1>(x, M.psi_inv + HEC_TW_COLA, M.q, M.q2);
 }
 
 // PermuteNTTIndex computed on the fly (L:ring/ring_automorphism.go:31-44):

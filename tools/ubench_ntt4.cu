@@ -14,11 +14,28 @@ __global__ void __launch_bounds__(256, 3) k(u64 *out, const ModC *mods, int it_n
     for (int i = 0; i < 16; i++) x[i] = (threadIdx.x * 977 + i * 31 + blockIdx.x) * 0x9E3779B97F4A7C15ull % M.q;
     for (int it = 0; it < it_n; it++) {
         u32 base = 16 + ((threadIdx.x >> 4) + it) % 240;
-        if (OP == 0) fwd4<false>(x, M.psi, base, M.q, M.q2);
-        if (OP == 1) fwd4<true>(x, M.psi, base, M.q, M.q2);
-        if (OP == 2) inv4(x, M.psi_inv, base, M.q, M.q2);
-        if (OP == 3) { fwd4<false>(x, M.psi, 1, M.q, M.q2); }            // uniform twiddles (column layout A)
-        if (OP == 0 || OP == 3) {                                          // keep the free-mode values bounded
+        if (OP == 0) fwd4<false, 1>(x, M.psi + 15 * base, M.q, M.q2);
+        if (OP == 1) fwd4<true, 1>(x, M.psi + 15 * base, M.q, M.q2);
+        if (OP == 2) inv4<1>(x, M.psi_inv + 15 * base, M.q, M.q2);
+        if (OP == 3) { fwd4<false, 1>(x, M.psi, M.q, M.q2); }               // uniform twiddles (column layout A)
+        if (OP == 4) {   // row layout B' with the natural NttPsi order: lane p reads psi[ng*(4096+16b+p)+gi]
+            u32 b = (blockIdx.x * 16 + (threadIdx.x >> 4) + it) & 255, base = 4096 + 16 * b + (threadIdx.x & 15);
+#pragma unroll
+            for (int lg = 0; lg < 4; lg++) {
+                const int d = 8 >> lg, ng = 1 << lg;
+#pragma unroll
+                for (int gi = 0; gi < ng; gi++) {
+                    ulonglong2 w = __ldg(M.psi + ((ng * base + gi) & 65535));
+#pragma unroll
+                    for (int k = 0; k < d; k++) ct_bfly<false>(x[gi * 2 * d + k], x[gi * 2 * d + k + d], w, M.q, M.q2);
+                }
+            }
+        }
+        if (OP == 5) {   // the same stages with the thread-order table the kernels use (stride 16)
+            u32 b = (blockIdx.x * 16 + (threadIdx.x >> 4) + it) & 255;
+            fwd4<false, 16>(x, M.psi + HEC_TW_ROWB + 240 * b + (threadIdx.x & 15), M.q, M.q2);
+        }
+        if (OP == 0 || OP >= 3) {                                          // keep the free-mode values bounded
 #pragma unroll
             for (int i = 0; i < 16; i++) x[i] &= 0x00ffffffffffffffull;
         }
@@ -59,9 +76,11 @@ int main() {
     ModC *dm;
     cudaMalloc(&dm, sizeof(ModC));
     cudaMemcpy(dm, &m, sizeof(ModC), cudaMemcpyHostToDevice);
-    run<0>("fwd4<free>, per-thread-group twiddles", dm);
+    run<0>("fwd4<free>, per-half-warp twiddles", dm);
     run<1>("fwd4<tight>", dm);
     run<2>("inv4", dm);
     run<3>("fwd4<free>, uniform twiddles", dm);
+    run<4>("fwd4<free>, row B', NttPsi order (16 lines/load)", dm);
+    run<5>("fwd4<free>, row B', thread-order table", dm);
     return 0;
 }

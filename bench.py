@@ -65,9 +65,9 @@ def kernel_alg_limbs(name, M, B, first_launch_only=False):
 
 def ncu_traffic(kernel):
     """dram bytes (read + write) of the first launch of `kernel` from the committed ncu --set full capture
-    (profiles/r01c_ncu_summary.csv: same command, --cts 16), or None."""
+    (profiles/r01d_ncu_summary.csv: same command, default --cts 32), or None."""
     import csv
-    p = os.path.join(ROOT, "profiles", "r01c_ncu_summary.csv")
+    p = os.path.join(ROOT, "profiles", "r01d_ncu_summary.csv")
     try:
         rows = list(csv.reader(open(p)))
         h = rows[0]
@@ -408,10 +408,10 @@ def main():
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "roofline": {"bound": "hbm", "kernel": "k_conv" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": ncu_traffic("k_conv" + dom) if M == 16 and B == 16 else None,  # the ncu capture ran --cts 16
+                     "frac": achieved / peak, "traffic": ncu_traffic("k_conv" + dom) if M == 32 and B == 16 else None,  # the ncu capture ran the default --cts 32
                      "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes_launch, "launch_ms": first_ms,
                      "launch": "first (largest) of %d launches per run" % n_l, "share_of_step": share,
-                     "traffic_source": "profiles/r01c_ncu_summary.csv (ncu --set full, same command)"},
+                     "traffic_source": "profiles/r01d_ncu_summary.csv (ncu --set full, same command)"},
         "roofline_int": {"bound": "integer multiply pipe (fmaheavy)", "modmuls_per_conv": modmuls,
                          "achieved": modmuls * (M * args.steps) / (ms_dev / 1e3), "peak": int_peak,
                          "unit": "modmul/s", "frac": modmuls * (M * args.steps) / (ms_dev / 1e3) / int_peak,

@@ -56,6 +56,40 @@ __device__ __forceinline__ u64 shoup32(u64 y, u64 w, u32 ws32, u64 nq) {
     return y * w + qe * nq;
 }
 
+// explicit 32-bit partial products: only mad.wide / mad.lo (full-rate IMAD), accumulating in place
+__device__ __forceinline__ u64 shoup_ptx2(u64 y, u64 w, u64 ws, u64 nq) {
+    u64 r;
+    asm("{\n\t"
+        ".reg .u32 y0,y1,w0,w1,s0,s1,n0,n1,t0,t1,u0,u1,v0,v1,e0,e1,r0,r1;\n\t"
+        ".reg .u64 t,u,v,e,c,acc;\n\t"
+        "mov.b64 {y0,y1}, %1;\n\t"
+        "mov.b64 {w0,w1}, %2;\n\t"
+        "mov.b64 {s0,s1}, %3;\n\t"
+        "mov.b64 {n0,n1}, %4;\n\t"
+        "mul.wide.u32 t, y0, s0;\n\t"
+        "mov.b64 {t0,t1}, t;\n\t"
+        "mov.b64 c, {t1, 0};\n\t"
+        "mad.wide.u32 u, y0, s1, c;\n\t"        // y0*s1 + hi32(y0*s0)
+        "mov.b64 {u0,u1}, u;\n\t"
+        "mov.b64 c, {u0, 0};\n\t"
+        "mad.wide.u32 v, y1, s0, c;\n\t"        // y1*s0 + lo32(u)
+        "mov.b64 {v0,v1}, v;\n\t"
+        "mov.b64 c, {u1, 0};\n\t"
+        "mad.wide.u32 e, y1, s1, c;\n\t"        // y1*s1 + hi32(u)
+        "mov.b64 c, {v1, 0};\n\t"
+        "add.u64 e, e, c;\n\t"                  // + hi32(v)   -> qe = hi64(y*ws)
+        "mov.b64 {e0,e1}, e;\n\t"
+        "mul.wide.u32 acc, y0, w0;\n\t"
+        "mad.wide.u32 acc, e0, n0, acc;\n\t"
+        "mov.b64 {r0,r1}, acc;\n\t"
+        "mad.lo.u32 r1, y0, w1, r1;\n\t"
+        "mad.lo.u32 r1, y1, w0, r1;\n\t"
+        "mad.lo.u32 r1, e0, n1, r1;\n\t"
+        "mad.lo.u32 r1, e1, n0, r1;\n\t"
+        "mov.b64 %0, {r0,r1};\n\t"
+        "}" : "=l"(r) : "l"(y), "l"(w), "l"(ws), "l"(nq));
+    return r;
+}
 __device__ __forceinline__ u64 shoup_nq(u64 y, u64 w, u64 ws, u64 nq) {
     return y * w + __umul64hi(y, ws) * nq;
 }
@@ -86,6 +120,7 @@ __global__ void k(u64 *out, u64 q, u64 qinv, u64 w, u64 ws) {
             if (OP == 3) y[i] = shoup_approx(y[i], w, ws, nq);
             if (OP == 4) y[i] = shoup32(y[i], w, (u32)(ws >> 32), nq);
             if (OP == 5) y[i] = shoup_nq(y[i], w, ws, nq);
+            if (OP == 8) y[i] = shoup_ptx2(y[i], w, ws, nq);
             if (OP == 6 && (i & 1) == 0) ct_free(y[i], y[i + 1], w + it, ws, q, 2 * q);
             if (OP == 7 && (i & 1) == 0) gs(y[i], y[i + 1], w + it, ws, q, 2 * q);
         }
@@ -128,6 +163,7 @@ int main(int argc, char **argv) {
     run<3>("shoup approx hi (3 wide)");
     run<4>("shoup32 (32-bit companion)");
     run<5>("shoup (C, + qe*(-q))");
+    run<8>("shoup (PTX mad.wide/mad.lo only)");
     run<6>("CT butterfly free (x2 = per bfly)");
     run<7>("GS butterfly (x2 = per bfly)");
     return 0;

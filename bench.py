@@ -176,7 +176,8 @@ def run_reference(args):
 def run_side_workload(args):
     """Measured numbers for the other rows of SURVEY.md section 8 (op-level, generic kernels):
     --workload conv_bl    : one evalConv_BN_BL_test interval (eval.go:108-131), set 7, level 1, alpha = 2,
-                            B=4 (w=128, k=3): 9 hoisted rotations + 2 x (9 MulNew/Add + RotateNew) + bias
+                            for --batch B (4,16,64,256) and --ker k (3,5,7): k^2-1 hoisted rotations +
+                            B/2 x (k^2 MulNew/Add + RotateNew) + bias  (BASELINE.json config 3: the k sweep)
     --workload keyswitch  : KeySwitcher.SwitchKeysInPlace at level 27, alpha = 5, beta = 6 (SURVEY.md 8d stress)"""
     import torch
     from optimal_conv_b200 import hec
@@ -198,23 +199,40 @@ def run_side_workload(args):
         # L (c1) + 2*beta*(L+alpha) (key) + 2L (out) + L (c0) limbs, SURVEY.md 8d
         alg = (28 + 2 * 6 * 33 + 2 * 28 + 28) * LIMB
     else:
+        # one evalConv_BN_BL_test interval for the (B, w) row of main.go:578-579 and kernel width --ker
         Q, P = PR.Q_SET7[:2], PR.P_PACK_BL
         ctx = hec.Context(PR.LOGN, Q, P)
-        w_, k = 128, 3
+        B, k = args.batch, args.ker
+        w_ = PR.WIDTHS[PR.BATCHES.index(B)]
         max_batch, rot_step, h = N // (2 * w_ * w_), w_ * w_, k // 2
         rots = [i * w_ + j for i in range(-h, h + 1) for j in range(-h, h + 1)] + [t * rot_step for t in range(1, max_batch)]
+        keys = {}
         for r in rots:
-            if r:
-                ctx.upload_swk(ctx.galois_for_rotation(r), np.stack([np.stack(
-                    [synth.uniform_limbs(5000 + 13 * (r % 9973) + kk, Q + P, N) for kk in range(2)])]), 1)
-        A = ctx.upload_ct(synth.uniform_limbs(61, Q, N), synth.uniform_limbs(62, Q, N), PR.SCALE)
-        taps = [[ctx.upload_pt(synth.uniform_limbs(700 + 10 * i + t, Q, N), PR.SCALE) for t in range(k * k)] for i in range(max_batch)]
-        bias = ctx.upload_pt(synth.uniform_limbs(99, Q, N), PR.SCALE * PR.SCALE)
+            if r and r not in keys:
+                keys[r] = np.stack([np.stack([synth.uniform_limbs(5000 + 13 * (r % 9973) + kk, Q + P, N) for kk in range(2)])])
+                ctx.upload_swk(ctx.galois_for_rotation(r), keys[r], 1)
+        a0, a1 = synth.uniform_limbs(61, Q, N), synth.uniform_limbs(62, Q, N)
+        A = ctx.upload_ct(a0, a1, PR.SCALE)
+        # a small pool of distinct plaintexts reused cyclically keeps host generation short
+        pool_np = [synth.uniform_limbs(700 + t, Q, N) for t in range(16)]
+        pool = [ctx.upload_pt(p_, PR.SCALE) for p_ in pool_np]
+        taps = [[pool[(i * k * k + t) % 16] for t in range(k * k)] for i in range(max_batch)]
+        bias_np = synth.uniform_limbs(99, Q, N)
+        bias = ctx.upload_pt(bias_np, PR.SCALE * PR.SCALE)
 
         def step():
             ctx.conv_bl(A, w_, k, rot_step, taps, bias).free()
-        unit, name = "baseline conv calls/s", "evalConv_BN_BL_test interval, B=4 (2 slots-halves), w=128, k=3, level 1, alpha=2"
+        unit = "baseline conv calls/s"
+        name = "evalConv_BN_BL_test interval (eval.go:108-131), B=%d (w=%d), k=%d, level 1, alpha=2: %d hoisted + %d full rotations, %d MulNew" % (
+            B, w_, k, k * k - 1, max_batch - 1, max_batch * k * k)
         alg = None
+        if args.cpu_sample > 0:
+            from oracle.orc import Ct, Oracle
+            o = Oracle(PR.LOGN, Q, P)
+            taps_np = [[pool_np[(i * k * k + t) % 16] for t in range(k * k)] for i in range(max_batch)]
+            t0 = time.perf_counter()
+            o.conv_bl(Ct(a0, a1, PR.SCALE), w_, k, rot_step, taps_np, PR.SCALE, keys, bias_np)
+            cpu_s = time.perf_counter() - t0
     for _ in range(max(3, args.warmup)):
         step()
     ctx.sync()
@@ -227,6 +245,9 @@ def run_side_workload(args):
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "dtype": "u64",
             "data": "synthetic", "config": {"workload": args.workload, "path": "op-level generic kernels"},
             "gpu_launches": ctx.launch_count() - l0}
+    if args.workload == "conv_bl" and args.cpu_sample > 0:
+        line["cpu_baseline"] = {"value": 1.0 / cpu_s, "unit": unit, "cores": 1, "kind": "port",
+                                "sample": "1 call of the same workload, oracle port, 1 thread"}
     if alg:
         peak, src = peaks()
         line["roofline"] = {"bound": "hbm", "achieved": alg / (ms / args.steps / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
@@ -241,6 +262,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--cts", type=int, default=32, help="independent input ciphertexts per step per GPU")
     ap.add_argument("--batch", type=int, default=16, help="B: output channels packed per ciphertext")
+    ap.add_argument("--ker", type=int, default=3, help="kernel width k (only changes the work of --workload conv_bl)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="conv", choices=["conv", "conv_bl", "keyswitch"],
                     help="conv = the headline fused path; the others are op-level side measurements")

@@ -605,25 +605,32 @@ extern "C" int hec_add_pt(hec_ctx *c, hec_ct *ct, const hec_pt *pt) {
 }
 
 // ---- key switching -----------------------------------------------------------------------
-// ModDownSplitNTTPQ (L:ring/ring_basis_extension.go:247-291), in place on accQ.
-// Needs nP + L scratch limbs (caller reserved).
-static int moddown(hec_ctx *c, int level, u64 *accQ, u64 *accP) {
+// Every step below is written for a BATCH of independent key-switches at the same level (one
+// launch sequence for all of them): the k^2 hoisted rotations of preConv_BL, the B/2-1 channel
+// rotations of evalConv_BN_BL_test, or a single RotateGal (batch of one).
+
+// ModDownSplitNTTPQ (L:ring/ring_basis_extension.go:247-291), in place on accQ[i] ([L][N]);
+// accP[i] is [nP][N].  Scratch: L limbs per item.
+static int moddown_many(hec_ctx *c, int level, const std::vector<u64 *> &accQ, const std::vector<u64 *> &accP) {
     int L = level + 1, nP = c->nP, rc;
+    size_t n = accQ.size();
     std::vector<LimbJob> nj;
-    for (int j = 0; j < nP; j++) nj.push_back({accP + (size_t)j * HEC_N, accP + (size_t)j * HEC_N, c->modP(j), 0});
+    for (size_t i = 0; i < n; i++)
+        for (int j = 0; j < nP; j++) nj.push_back({accP[i] + (size_t)j * HEC_N, accP[i] + (size_t)j * HEC_N, c->modP(j), 0});
     if ((rc = hec_launch_ntt(c, nj, true))) return rc; // InvNTT on P (canonical residues of the lazy original)
-    u64 *x = c->scratch(L);
+    u64 *x = c->scratch(n * L);
     std::vector<ModupJob> mj;
+    std::vector<EwJob> ej;
     nj.clear();
-    for (int i = 0; i < L; i++) {
-        mj.push_back(modup_job(c, c->pq, accP, HEC_N, c->modQ(i), x + (size_t)i * HEC_N));
-        nj.push_back({x + (size_t)i * HEC_N, x + (size_t)i * HEC_N, i, 0});
-    }
+    for (size_t i = 0; i < n; i++)
+        for (int l = 0; l < L; l++) {
+            u64 *xi = x + (i * L + l) * HEC_N;
+            mj.push_back(modup_job(c, c->pq, accP[i], HEC_N, c->modQ(l), xi));
+            nj.push_back({xi, xi, l, 0});
+            ej.push_back(ewjob(xi, accQ[i] + (size_t)l * HEC_N, accQ[i] + (size_t)l * HEC_N, l, c->negpinv[l]));
+        }
     if ((rc = launch_modup(c, mj))) return rc;
     if ((rc = hec_launch_ntt(c, nj, false))) return rc;
-    std::vector<EwJob> ej;
-    for (int i = 0; i < L; i++)
-        ej.push_back(ewjob(x + (size_t)i * HEC_N, accQ + (size_t)i * HEC_N, accQ + (size_t)i * HEC_N, i, c->negpinv[i]));
     return launch_ew<EW_SUBMUL>(c, ej);
 }
 
@@ -633,96 +640,125 @@ static size_t decomp_limbs(const hec_ctx *c, int level) {
     return (size_t)L + (size_t)beta * (L + c->nP);
 }
 // DecomposeNTT (L:rlwe/keyswitch.go:94-141; DecomposeAndSplit L:ring/ring_basis_extension.go:543-664)
-static int decompose(hec_ctx *c, int level, const u64 *c1, Decomp &out) {
+// of every c1[i] ([L][N], NTT domain).
+static int decompose_many(hec_ctx *c, int level, const std::vector<const u64 *> &c1, std::vector<Decomp> &out) {
     int L = level + 1, nP = c->nP, alpha = c->alpha, rc;
     int beta = (L + alpha - 1) / alpha, W = L + nP;
-    u64 *cinv = c->scratch(L);
-    u64 *D = c->scratch((size_t)beta * W);
-    std::vector<LimbJob> nj;
-    for (int i = 0; i < L; i++) nj.push_back({c1 + (size_t)i * HEC_N, cinv + (size_t)i * HEC_N, i, 0});
-    if ((rc = hec_launch_ntt(c, nj, true))) return rc;
+    size_t n = c1.size();
+    out.resize(n);
+    std::vector<LimbJob> inv, fwd;
     std::vector<EwJob> lift, copy;
     std::vector<ModupJob> mj;
-    nj.clear();
-    for (int d = 0; d < beta; d++) {
-        int st = d * alpha, nd = std::min(c->xalpha[d], L - st);
-        for (int t = 0; t < W; t++) {
-            u64 *dst = D + ((size_t)d * W + t) * HEC_N;
-            int mod = t < L ? c->modQ(t) : c->modP(t - L);
-            if (t < L && t >= st && t < st + nd) { // in-digit limb: reuse the NTT form of c1
-                copy.push_back(ewjob(c1 + (size_t)t * HEC_N, nullptr, dst, mod));
-                continue;
+    for (size_t i = 0; i < n; i++) {
+        u64 *cinv = c->scratch(L);
+        u64 *D = c->scratch((size_t)beta * W);
+        out[i].D = D; out[i].L = L; out[i].beta = beta;
+        for (int l = 0; l < L; l++) inv.push_back({c1[i] + (size_t)l * HEC_N, cinv + (size_t)l * HEC_N, l, 0});
+        for (int d = 0; d < beta; d++) {
+            int st = d * alpha, nd = std::min(c->xalpha[d], L - st);
+            for (int t = 0; t < W; t++) {
+                u64 *dst = D + ((size_t)d * W + t) * HEC_N;
+                int mod = t < L ? c->modQ(t) : c->modP(t - L);
+                if (t < L && t >= st && t < st + nd) { // in-digit limb: reuse the NTT form of c1
+                    copy.push_back(ewjob(c1[i] + (size_t)t * HEC_N, nullptr, dst, mod));
+                    continue;
+                }
+                if (nd == 1) lift.push_back(ewjob(cinv + (size_t)st * HEC_N, nullptr, dst, mod, 0)); // copy path
+                else mj.push_back(modup_job(c, c->dec[d][nd], cinv + (size_t)st * HEC_N, HEC_N, mod, dst));
+                fwd.push_back({dst, dst, mod, 0});
             }
-            if (nd == 1) lift.push_back(ewjob(cinv + (size_t)st * HEC_N, nullptr, dst, mod, 0)); // copy path
-            else mj.push_back(modup_job(c, c->dec[d][nd], cinv + (size_t)st * HEC_N, HEC_N, mod, dst));
-            nj.push_back({dst, dst, mod, 0});
         }
     }
+    if ((rc = hec_launch_ntt(c, inv, true))) return rc;
     if (!copy.empty() && (rc = launch_ew<EW_COPY>(c, copy))) return rc;
     if (!lift.empty() && (rc = launch_ew<EW_REDUCE_ADD>(c, lift))) return rc;
     if (!mj.empty() && (rc = launch_modup(c, mj))) return rc;
-    if ((rc = hec_launch_ntt(c, nj, false))) return rc;
-    out.D = D; out.L = L; out.beta = beta;
-    return HEC_OK;
+    return hec_launch_ntt(c, fwd, false);
 }
-// KeyswitchHoisted (L:rlwe/keyswitch.go:234-304): inner product with the key + mod-down.
-// d0,d1: [L][N] outputs.  Needs 2*nP + (nP... ) scratch: 2*nP accumulators + L for moddown.
-static int keyswitch_from_decomp(hec_ctx *c, int level, const Decomp &dc, const SwKey &key, u64 *d0, u64 *d1) {
-    int L = level + 1, nP = c->nP, W = L + nP, kl = key.Lk + nP, rc;
-    if (key.Lk < L || key.ndig < dc.beta) return c->fail(HEC_E_NOKEY, "switching key slice does not cover this level");
-    u64 *accP = c->scratch(2 * (size_t)nP);
-    u64 *accQ[2] = {d0, d1};
-    for (int d = 0; d < dc.beta; d++) {
+// KeyswitchHoisted (L:rlwe/keyswitch.go:234-304) for item i: inner product of decomposition dc[i] (or the
+// shared dc[0]) with key[i], then mod-down.  d0[i], d1[i]: [L][N] outputs.  Scratch: (2 nP + 2 L) limbs per item.
+static int keyswitch_many(hec_ctx *c, int level, const std::vector<Decomp> &dc, const std::vector<const SwKey *> &key,
+                          const std::vector<u64 *> &d0, const std::vector<u64 *> &d1) {
+    int L = level + 1, nP = c->nP, W = L + nP, rc;
+    size_t n = key.size();
+    int beta = dc[0].beta;
+    for (size_t i = 0; i < n; i++)
+        if (key[i]->Lk < L || key[i]->ndig < beta) return c->fail(HEC_E_NOKEY, "switching key slice does not cover this level");
+    std::vector<u64 *> accQ, accP;
+    for (size_t i = 0; i < n; i++) {
+        u64 *ap = c->scratch(2 * (size_t)nP);
+        accQ.push_back(d0[i]); accP.push_back(ap);
+        accQ.push_back(d1[i]); accP.push_back(ap + (size_t)nP * HEC_N);
+    }
+    for (int d = 0; d < beta; d++) {
         std::vector<EwJob> jobs;
-        for (int p = 0; p < 2; p++)
-            for (int t = 0; t < W; t++) {
-                const u64 *dh = dc.D + ((size_t)d * W + t) * HEC_N;
-                int kt = t < L ? t : key.Lk + (t - L);
-                const u64 *kp = key.buf + ((size_t)(d * 2 + p) * kl + kt) * HEC_N;
-                u64 *acc = t < L ? accQ[p] + (size_t)t * HEC_N : accP + ((size_t)p * nP + (t - L)) * HEC_N;
-                jobs.push_back(ewjob(dh, kp, acc, t < L ? c->modQ(t) : c->modP(t - L)));
-            }
+        for (size_t i = 0; i < n; i++) {
+            const Decomp &D = dc.size() == 1 ? dc[0] : dc[i];
+            int kl = key[i]->Lk + nP;
+            for (int p = 0; p < 2; p++)
+                for (int t = 0; t < W; t++) {
+                    const u64 *dh = D.D + ((size_t)d * W + t) * HEC_N;
+                    int kt = t < L ? t : key[i]->Lk + (t - L);
+                    const u64 *kp = key[i]->buf + ((size_t)(d * 2 + p) * kl + kt) * HEC_N;
+                    u64 *acc = t < L ? accQ[2 * i + p] + (size_t)t * HEC_N : accP[2 * i + p] + (size_t)(t - L) * HEC_N;
+                    jobs.push_back(ewjob(dh, kp, acc, t < L ? c->modQ(t) : c->modP(t - L)));
+                }
+        }
         rc = d == 0 ? launch_ew<EW_MULMONT>(c, jobs) : launch_ew<EW_MAC>(c, jobs);
         if (rc) return rc;
     }
-    for (int p = 0; p < 2; p++) {
-        size_t mark = c->arena_top;
-        if ((rc = moddown(c, level, accQ[p], accP + (size_t)p * nP * HEC_N))) return rc;
-        c->arena_top = mark;
-    }
+    return moddown_many(c, level, accQ, accP);
+}
+static size_t ks_limbs(const hec_ctx *c, int level) { return 2 * c->nP + 2 * (size_t)(level + 1); } // per item, after decompose
+
+// permuteNTT tail (L:ckks/evaluator.go:1575-1597) for every item: d0 += c0, then PermuteNTTWithIndexLvl x2
+static int finish_rotations(hec_ctx *c, int level, const std::vector<const hec_ct *> &ct, const std::vector<u64> &galEl,
+                            const std::vector<u64 *> &d0, const std::vector<u64 *> &d1, const std::vector<hec_ct *> &out) {
+    int L = level + 1, rc;
+    std::vector<EwJob> add, perm;
+    for (size_t i = 0; i < ct.size(); i++)
+        for (int l = 0; l < L; l++) {
+            add.push_back(ewjob(d0[i] + (size_t)l * HEC_N, ct[i]->limb(0, l), d0[i] + (size_t)l * HEC_N, l));
+            perm.push_back(ewjob(d0[i] + (size_t)l * HEC_N, nullptr, out[i]->limb(0, l), l, 0, (u32)galEl[i]));
+            perm.push_back(ewjob(d1[i] + (size_t)l * HEC_N, nullptr, out[i]->limb(1, l), l, 0, (u32)galEl[i]));
+        }
+    if ((rc = launch_ew<EW_ADD>(c, add))) return rc;
+    if ((rc = launch_ew<EW_PERMUTE>(c, perm))) return rc;
+    for (size_t i = 0; i < ct.size(); i++) { out[i]->level = level; out[i]->scale = ct[i]->scale; }
     return HEC_OK;
 }
-static size_t ks_limbs(const hec_ctx *c, int level) { return decomp_limbs(c, level) + 2 * c->nP + (level + 1); }
 
-// permuteNTT tail (L:ckks/evaluator.go:1575-1597): d0 += c0, then PermuteNTTWithIndexLvl x2
-static int finish_rotation(hec_ctx *c, int level, const hec_ct *ct, u64 galEl, u64 *d0, u64 *d1, hec_ct *out) {
-    int L = level + 1, rc;
-    std::vector<EwJob> jobs;
-    for (int i = 0; i < L; i++) jobs.push_back(ewjob(d0 + (size_t)i * HEC_N, ct->limb(0, i), d0 + (size_t)i * HEC_N, i));
-    if ((rc = launch_ew<EW_ADD>(c, jobs))) return rc;
-    jobs.clear();
-    for (int i = 0; i < L; i++) {
-        jobs.push_back(ewjob(d0 + (size_t)i * HEC_N, nullptr, out->limb(0, i), i, 0, (u32)galEl));
-        jobs.push_back(ewjob(d1 + (size_t)i * HEC_N, nullptr, out->limb(1, i), i, 0, (u32)galEl));
+// n independent rotations out[i] = sigma_{galEl[i]}(ct[i]) at a common level; `hoisted`: all ct[i] are the
+// same ciphertext and share one decomposition (RotateHoisted, L:ckks/linear_transform.go:10-27).
+int hec_rotate_many(hec_ctx *c, const std::vector<const hec_ct *> &ct, const std::vector<u64> &galEl,
+                    const std::vector<hec_ct *> &out, bool hoisted) {
+    size_t n = ct.size();
+    if (n == 0) return HEC_OK;
+    std::vector<const SwKey *> keys(n);
+    int level = ct[0]->level;
+    for (size_t i = 0; i < n; i++) {
+        auto it = c->keys.find(galEl[i]);
+        if (it == c->keys.end()) return c->fail(HEC_E_NOKEY, "rotation key for galEl " + std::to_string(galEl[i]) + " missing");
+        keys[i] = &it->second;
+        level = std::min(level, std::min(ct[i]->level, out[i]->alloc - 1));
     }
-    if ((rc = launch_ew<EW_PERMUTE>(c, jobs))) return rc;
-    out->level = level;
-    out->scale = ct->scale;
-    return HEC_OK;
+    int L = level + 1, rc;
+    size_t ndec = hoisted ? 1 : n;
+    if ((rc = reserve(c, ndec * decomp_limbs(c, level) + n * (ks_limbs(c, level) + 2 * (size_t)L)))) return rc;
+    std::vector<u64 *> d0(n), d1(n);
+    for (size_t i = 0; i < n; i++) { d0[i] = c->scratch(L); d1[i] = c->scratch(L); }
+    std::vector<const u64 *> c1;
+    for (size_t i = 0; i < ndec; i++) c1.push_back(ct[i]->limb(1, 0));
+    std::vector<Decomp> dc;
+    if ((rc = decompose_many(c, level, c1, dc))) return rc;
+    if ((rc = keyswitch_many(c, level, dc, keys, d0, d1))) return rc;
+    return finish_rotations(c, level, ct, galEl, d0, d1, out);
 }
 
 extern "C" int hec_rotate_gal(hec_ctx *c, const hec_ct *ct, uint64_t galEl, hec_ct *out) {
     if (!c || !ct || !out) return HEC_E_INVAL;
     cudaSetDevice(c->device);
-    auto it = c->keys.find(galEl);
-    if (it == c->keys.end()) return c->fail(HEC_E_NOKEY, "rotation key for galEl " + std::to_string(galEl) + " missing");
-    int level = std::min(ct->level, out->alloc - 1), L = level + 1, rc;
-    if ((rc = reserve(c, ks_limbs(c, level) + 2 * (size_t)L))) return rc;
-    u64 *d0 = c->scratch(L), *d1 = c->scratch(L);
-    Decomp dc;
-    if ((rc = decompose(c, level, ct->limb(1, 0), dc))) return rc;
-    if ((rc = keyswitch_from_decomp(c, level, dc, it->second, d0, d1))) return rc;
-    return finish_rotation(c, level, ct, galEl, d0, d1, out);
+    return hec_rotate_many(c, {ct}, {galEl}, {out}, false);
 }
 
 extern "C" uint64_t hec_galois_for_rotation(const hec_ctx *c, int k) {
@@ -742,29 +778,26 @@ extern "C" int hec_rotate_new(hec_ctx *c, const hec_ct *ct, int k, hec_ct **out)
     *out = o;
     return HEC_OK;
 }
-// RotateHoisted (L:ckks/linear_transform.go:10-27): one DecomposeNTT shared by all rotations
+// RotateHoisted (L:ckks/linear_transform.go:10-27): one DecomposeNTT shared by all rotations; the inner
+// products, mod-downs and permutations of all rotations are batched into one launch sequence
 extern "C" int hec_rotate_hoisted(hec_ctx *c, const hec_ct *ct, const int *rots, int n, hec_ct **outs) {
     if (!c || !ct || !rots || !outs || n < 0) return HEC_E_INVAL;
     cudaSetDevice(c->device);
-    int level = ct->level, L = level + 1, rc;
-    for (int r = 0; r < n; r++)
-        if (rots[r] != 0 && !c->keys.count(hec_galois_for_rotation(c, rots[r])))
-            return c->fail(HEC_E_NOKEY, "rotation key for rotation " + std::to_string(rots[r]) + " missing");
-    if ((rc = reserve(c, ks_limbs(c, level) + 2 * (size_t)L))) return rc;
-    u64 *d0 = c->scratch(L), *d1 = c->scratch(L);
-    Decomp dc;
-    if ((rc = decompose(c, level, ct->limb(1, 0), dc))) return rc;
-    size_t mark = c->arena_top;
+    int rc;
     for (int r = 0; r < n; r++) {
         outs[r] = nullptr;
-        if (rots[r] == 0) { if ((rc = hec_ct_copy_new(c, ct, &outs[r]))) return rc; continue; }
-        u64 g = hec_galois_for_rotation(c, rots[r]);
-        if ((rc = hec_ct_alloc(c, level, ct->scale, &outs[r]))) return rc;
-        c->arena_top = mark;
-        if ((rc = keyswitch_from_decomp(c, level, dc, c->keys[g], d0, d1))) return rc;
-        if ((rc = finish_rotation(c, level, ct, g, d0, d1, outs[r]))) return rc;
+        if (rots[r] != 0 && !c->keys.count(hec_galois_for_rotation(c, rots[r])))
+            return c->fail(HEC_E_NOKEY, "rotation key for rotation " + std::to_string(rots[r]) + " missing");
     }
-    return HEC_OK;
+    std::vector<const hec_ct *> in;
+    std::vector<u64> gal;
+    std::vector<hec_ct *> out;
+    for (int r = 0; r < n; r++) {
+        if (rots[r] == 0) { if ((rc = hec_ct_copy_new(c, ct, &outs[r]))) return rc; continue; } // cOut[0] = ctIn.CopyNew()
+        if ((rc = hec_ct_alloc(c, ct->level, ct->scale, &outs[r]))) return rc;
+        in.push_back(ct); gal.push_back(hec_galois_for_rotation(c, rots[r])); out.push_back(outs[r]);
+    }
+    return hec_rotate_many(c, in, gal, out, true);
 }
 
 // =========================================================================================
@@ -789,12 +822,12 @@ extern "C" int hec_keyswitch(hec_ctx *c, int level, const uint64_t *const *c1, u
     auto it = c->keys.find(galEl);
     if (it == c->keys.end()) return c->fail(HEC_E_NOKEY, "rotation key missing");
     int L = level + 1, rc;
-    if ((rc = reserve(c, ks_limbs(c, level) + 3 * (size_t)L))) return rc;
+    if ((rc = reserve(c, decomp_limbs(c, level) + ks_limbs(c, level) + 3 * (size_t)L))) return rc;
     u64 *x = c->scratch(L), *a0 = c->scratch(L), *a1 = c->scratch(L);
     for (int i = 0; i < L; i++) HEC_CUDA(c, cudaMemcpyAsync(x + (size_t)i * HEC_N, c1[i], HEC_N * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
-    Decomp dc;
-    if ((rc = decompose(c, level, x, dc))) return rc;
-    if ((rc = keyswitch_from_decomp(c, level, dc, it->second, a0, a1))) return rc;
+    std::vector<Decomp> dc;
+    if ((rc = decompose_many(c, level, {x}, dc))) return rc;
+    if ((rc = keyswitch_many(c, level, dc, {&it->second}, {a0}, {a1}))) return rc;
     for (int i = 0; i < L; i++) {
         HEC_CUDA(c, cudaMemcpyAsync(d0[i], a0 + (size_t)i * HEC_N, HEC_N * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
         HEC_CUDA(c, cudaMemcpyAsync(d1[i], a1 + (size_t)i * HEC_N, HEC_N * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
@@ -806,11 +839,11 @@ extern "C" int hec_moddown(hec_ctx *c, int level, const uint64_t *const *accQ, c
     if (!c || !accQ || !accP || !out || c->nP == 0 || level < 0 || level >= c->nQ) return c ? c->fail(HEC_E_INVAL, "moddown args") : HEC_E_INVAL;
     cudaSetDevice(c->device);
     int L = level + 1, rc;
-    if ((rc = reserve(c, 2 * (size_t)L + c->nP))) return rc;
+    if ((rc = reserve(c, 3 * (size_t)L + c->nP))) return rc;
     u64 *aq = c->scratch(L), *ap = c->scratch(c->nP);
     for (int i = 0; i < L; i++) HEC_CUDA(c, cudaMemcpyAsync(aq + (size_t)i * HEC_N, accQ[i], HEC_N * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
     for (int j = 0; j < c->nP; j++) HEC_CUDA(c, cudaMemcpyAsync(ap + (size_t)j * HEC_N, accP[j], HEC_N * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
-    if ((rc = moddown(c, level, aq, ap))) return rc;
+    if ((rc = moddown_many(c, level, {aq}, {ap}))) return rc;
     for (int i = 0; i < L; i++) HEC_CUDA(c, cudaMemcpyAsync(out[i], aq + (size_t)i * HEC_N, HEC_N * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
     HEC_CUDA(c, cudaStreamSynchronize(c->stream));
     return HEC_OK;

@@ -78,48 +78,104 @@ static int conv_then_pack_oplevel(hec_ctx *ev, const hec_ct *ctxt_in, const hec_
 // + RotateNew + Add (eval.go:118-125)] + bias Add (eval.go:130).  The kernel plaintexts that
 // postConv_BL encodes on the host inside its loop (conv.go:165-166) arrive pre-encoded.
 // =========================================================================================
+int hec_rotate_many(hec_ctx *c, const std::vector<const hec_ct *> &ct, const std::vector<u64> &galEl,
+                    const std::vector<hec_ct *> &out, bool hoisted);
+
+// launch k_dot for a list of (a pointers, b pointers or none, out, modulus) sums; the pointer lists are
+// staged into one stream-ordered device buffer
+struct DotSpec { std::vector<const u64 *> a, b; u64 *out; int mod; };
+static int launch_dot(hec_ctx *c, const std::vector<DotSpec> &specs) {
+    size_t np = 0;
+    for (auto &sp : specs) np += sp.a.size() + sp.b.size();
+    size_t bytes = np * sizeof(u64 *) + specs.size() * sizeof(DotJob);
+    char *dbuf = nullptr;
+    HEC_CUDA(c, cudaMallocAsync(&dbuf, bytes, c->stream));
+    std::vector<char> h(bytes);
+    const u64 **hp = reinterpret_cast<const u64 **>(h.data());
+    const u64 **dp = reinterpret_cast<const u64 **>(dbuf);
+    DotJob *hj = reinterpret_cast<DotJob *>(h.data() + np * sizeof(u64 *));
+    size_t off = 0;
+    for (size_t i = 0; i < specs.size(); i++) {
+        const DotSpec &sp = specs[i];
+        hj[i].a = dp + off;
+        for (auto x : sp.a) hp[off++] = x;
+        hj[i].b = sp.b.empty() ? nullptr : dp + off;
+        for (auto x : sp.b) hp[off++] = x;
+        hj[i].out = sp.out; hj[i].mod = sp.mod; hj[i].T = (int)sp.a.size();
+    }
+    // pageable source: staged by the driver before the call returns, so `h` may die
+    HEC_CUDA(c, cudaMemcpyAsync(dbuf, h.data(), bytes, cudaMemcpyHostToDevice, c->stream));
+    k_dot<<<dim3(32, (unsigned)specs.size()), 256, 0, c->stream>>>(reinterpret_cast<const DotJob *>(dbuf + np * sizeof(u64 *)), c->dmods);
+    c->launches += 1;
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(dbuf, c->stream);
+    if (e != cudaSuccess) return c->fail(HEC_E_CUDA, std::string("k_dot: ") + cudaGetErrorString(e));
+    return HEC_OK;
+}
+
 extern "C" int hec_conv_bl(hec_ctx *ev, const hec_ct *ct_input, int in_wid, int ker_wid, int rot_iters, int rot_step,
                            const hec_pt *const *pt_taps, const hec_pt *pl_bn_b, hec_ct **out) {
     if (!ev || !ct_input || !pt_taps || !out || ker_wid < 1 || !(ker_wid & 1) || rot_iters < 1) return ev ? ev->fail(HEC_E_INVAL, "conv_bl args") : HEC_E_INVAL;
     cudaSetDevice(ev->device);
     const int ker_size = ker_wid * ker_wid;
     int rc;
-    // preConv_BL: one hoisted decomposition, k^2 rotations i*in_wid + j
+    for (int i = 0; i < rot_iters * ker_size; i++)
+        if (!pt_taps[i]) return ev->fail(HEC_E_INVAL, "conv_bl: missing tap plaintext");
+    // preConv_BL (conv.go:120-143): one hoisted decomposition, k^2 rotations i*in_wid + j
     std::vector<int> rotations;
     for (int i = -(ker_wid / 2); i <= ker_wid / 2; i++)
         for (int j = -(ker_wid / 2); j <= ker_wid / 2; j++) rotations.push_back(i * in_wid + j);
-    std::vector<hec_ct *> ct_in_rots(ker_size, nullptr);
-    if ((rc = hec_rotate_hoisted(ev, ct_input, rotations.data(), ker_size, ct_in_rots.data()))) return rc;
-    auto cleanup = [&](hec_ct *keep) {
-        for (auto p : ct_in_rots) if (p && p != keep) hec_ct_free(ev, p);
+    std::vector<hec_ct *> ct_in_rots(ker_size, nullptr), ct_tmp(rot_iters, nullptr), ct_rot(rot_iters, nullptr);
+    auto cleanup = [&]() {
+        for (auto p : ct_in_rots) if (p) hec_ct_free(ev, p);
+        for (auto p : ct_tmp) if (p) hec_ct_free(ev, p);
+        for (auto p : ct_rot) if (p) hec_ct_free(ev, p);
     };
-    hec_ct *ct_res = nullptr;
+    if ((rc = hec_rotate_hoisted(ev, ct_input, rotations.data(), ker_size, ct_in_rots.data()))) { cleanup(); return rc; }
+    // postConv_BL (conv.go:146-178) for every output rotation i: ct_tmp[i] = sum_tap MulNew(ct_in_rots[tap], pl[i][tap])
+    // (the MulNew/Add chain is a sum of Montgomery products; one launch covers all i, limbs and both polys)
+    int level = ct_input->level;
+    for (int i = 0; i < rot_iters * ker_size; i++) level = std::min(level, pt_taps[i]->level);
+    const double scale = ct_input->scale * pt_taps[0]->scale;
+    std::vector<DotSpec> specs;
     for (int i = 0; i < rot_iters; i++) {
-        // postConv_BL: sum over taps of MulNew(ct_in_rots[tap], pl_tap)
-        hec_ct *ct_tmp = nullptr;
-        for (int t = 0; t < ker_size; t++) {
-            const hec_pt *pl = pt_taps[(size_t)i * ker_size + t];
-            if (!pl) { cleanup(nullptr); return ev->fail(HEC_E_INVAL, "conv_bl: missing tap plaintext"); }
-            if (t == 0) { if ((rc = hec_mul_pt_new(ev, ct_in_rots[t], pl, &ct_tmp))) { cleanup(nullptr); return rc; } }
-            else {
-                hec_ct *m = nullptr;
-                if ((rc = hec_mul_pt_new(ev, ct_in_rots[t], pl, &m))) { cleanup(nullptr); return rc; }
-                rc = hec_add(ev, ct_tmp, m, ct_tmp);
-                hec_ct_free(ev, m);
-                if (rc) { cleanup(nullptr); return rc; }
+        if ((rc = hec_ct_alloc(ev, level, scale, &ct_tmp[i]))) { cleanup(); return rc; }
+        for (int p = 0; p < 2; p++)
+            for (int l = 0; l <= level; l++) {
+                DotSpec sp;
+                for (int t = 0; t < ker_size; t++) {
+                    sp.a.push_back(ct_in_rots[t]->limb(p, l));
+                    sp.b.push_back(pt_taps[(size_t)i * ker_size + t]->buf + (size_t)l * HEC_N);
+                }
+                sp.out = ct_tmp[i]->limb(p, l); sp.mod = ev->modQ(l);
+                specs.push_back(sp);
             }
-        }
-        if (i == 0) ct_res = ct_tmp;
-        else {
-            hec_ct *r = nullptr;
-            if ((rc = hec_rotate_new(ev, ct_tmp, i * rot_step, &r))) { cleanup(nullptr); return rc; }
-            rc = hec_add(ev, ct_res, r, ct_res);
-            hec_ct_free(ev, r);
-            hec_ct_free(ev, ct_tmp);
-            if (rc) { cleanup(nullptr); return rc; }
-        }
     }
-    cleanup(nullptr);
+    if ((rc = launch_dot(ev, specs))) { cleanup(); return rc; }
+    // eval.go:118-125: ct_res = ct_tmp[0] + sum_{i>0} RotateNew(ct_tmp[i], i*rot_step); the rotations are
+    // independent of each other and run as one batch
+    std::vector<const hec_ct *> rin;
+    std::vector<u64> gal;
+    std::vector<hec_ct *> rout;
+    for (int i = 1; i < rot_iters; i++) {
+        if ((rc = hec_ct_alloc(ev, level, scale, &ct_rot[i]))) { cleanup(); return rc; }
+        rin.push_back(ct_tmp[i]); gal.push_back(hec_galois_for_rotation(ev, i * rot_step)); rout.push_back(ct_rot[i]);
+    }
+    if ((rc = hec_rotate_many(ev, rin, gal, rout, false))) { cleanup(); return rc; }
+    hec_ct *ct_res = nullptr;
+    if ((rc = hec_ct_alloc(ev, level, scale, &ct_res))) { cleanup(); return rc; }
+    specs.clear();
+    for (int p = 0; p < 2; p++)
+        for (int l = 0; l <= level; l++) {
+            DotSpec sp;
+            sp.a.push_back(ct_tmp[0]->limb(p, l));
+            for (int i = 1; i < rot_iters; i++) sp.a.push_back(ct_rot[i]->limb(p, l));
+            sp.out = ct_res->limb(p, l); sp.mod = ev->modQ(l);
+            specs.push_back(sp);
+        }
+    rc = launch_dot(ev, specs);
+    cleanup();
+    if (rc) { hec_ct_free(ev, ct_res); return rc; }
     if (pl_bn_b) {
         if (hec_ct_scale(ct_res) != pl_bn_b->scale) { // eval.go:127-129
             hec_ct_free(ev, ct_res);
@@ -141,21 +197,38 @@ extern "C" int hec_ext_ctxt(hec_ctx *ev, const hec_ct *input, int n, const int *
                             int do_rescale, double min_scale, hec_ct **out) {
     if (!ev || !input || !rots || !pts || !out || n < 1) return ev ? ev->fail(HEC_E_INVAL, "ext_ctxt args") : HEC_E_INVAL;
     cudaSetDevice(ev->device);
-    hec_ct *result = nullptr;
     int rc;
+    std::vector<hec_ct *> prod(n, nullptr), rot(n, nullptr);
+    auto cleanup = [&]() {
+        for (auto p : prod) if (p) hec_ct_free(ev, p);
+        for (auto p : rot) if (p) hec_ct_free(ev, p);
+    };
+    // the n products and the n rotations are independent of each other: one batch each, then one sum
+    std::vector<const hec_ct *> rin;
+    std::vector<u64> gal;
     for (int i = 0; i < n; i++) {
-        hec_ct *m = nullptr, *r = nullptr;
-        if ((rc = hec_mul_pt_new(ev, input, pts[i], &m))) { if (result) hec_ct_free(ev, result); return rc; }
-        rc = hec_rotate_new(ev, m, rots[i], &r);
-        hec_ct_free(ev, m);
-        if (rc) { if (result) hec_ct_free(ev, result); return rc; }
-        if (!result) result = r;
-        else {
-            rc = hec_add(ev, result, r, result);
-            hec_ct_free(ev, r);
-            if (rc) { hec_ct_free(ev, result); return rc; }
-        }
+        if (!pts[i]) { cleanup(); return ev->fail(HEC_E_INVAL, "ext_ctxt: missing mask plaintext"); }
+        if ((rc = hec_mul_pt_new(ev, input, pts[i], &prod[i]))) { cleanup(); return rc; }
+        if ((rc = hec_ct_alloc(ev, prod[i]->level, prod[i]->scale, &rot[i]))) { cleanup(); return rc; }
+        rin.push_back(prod[i]);
+        gal.push_back(hec_galois_for_rotation(ev, rots[i]));
     }
+    if ((rc = hec_rotate_many(ev, rin, gal, rot, false))) { cleanup(); return rc; }
+    hec_ct *result = nullptr;
+    int level = rot[0]->level;
+    for (int i = 1; i < n; i++) level = std::min(level, rot[i]->level);
+    if ((rc = hec_ct_alloc(ev, level, rot[0]->scale, &result))) { cleanup(); return rc; }
+    std::vector<DotSpec> specs;
+    for (int p = 0; p < 2; p++)
+        for (int l = 0; l <= level; l++) {
+            DotSpec sp;
+            for (int i = 0; i < n; i++) sp.a.push_back(rot[i]->limb(p, l));
+            sp.out = result->limb(p, l); sp.mod = ev->modQ(l);
+            specs.push_back(sp);
+        }
+    rc = launch_dot(ev, specs);
+    cleanup();
+    if (rc) { hec_ct_free(ev, result); return rc; }
     if (do_rescale && (rc = hec_rescale(ev, result, min_scale))) { hec_ct_free(ev, result); return rc; }
     *out = result;
     return HEC_OK;

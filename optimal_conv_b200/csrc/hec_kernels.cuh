@@ -106,6 +106,23 @@ __global__ void __launch_bounds__(256) k_ew(EwJobs J, const ModC *__restrict__ m
     }
 }
 
+// ---- sum over taps: out = sum_t a_t * b_t * R^-1 (b != null: a chain of MulNew + Add, conv.go:168-171)
+// or out = sum_t a_t (b == null: a chain of Add, eval.go:123).  Pointer lists live in device memory.
+struct DotJob { const u64 *const *a; const u64 *const *b; u64 *out; int mod; int T; };
+__global__ void __launch_bounds__(256) k_dot(const DotJob *__restrict__ jobs, const ModC *__restrict__ mods) {
+    const DotJob job = jobs[blockIdx.y];
+    const u64 q = mods[job.mod].q, qinv = mods[job.mod].qinv;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < HEC_N; i += gridDim.x * blockDim.x) {
+        u64 acc = 0;
+        for (int t = 0; t < job.T; t++) {
+            u64 v = job.a[t][i];
+            if (job.b != nullptr) v = mred(v, __ldg(job.b[t] + i), q, qinv);
+            acc = addmod(acc, v, q);
+        }
+        job.out[i] = acc;
+    }
+}
+
 // ---- exact basis extension (modUpExact / reconstructRNS / multSum,
 // L:ring/ring_basis_extension.go:438-457,670-779).  One job per target limb. -------------
 #define HEC_MAXA 5

@@ -47,7 +47,16 @@ def lib():
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
-        raise ImportError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'`" % LIB_PATH)
+        # build in-tree with nvcc when the toolchain is present; there is nothing else to fall back to
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("_hec_build", os.path.join(os.path.dirname(_HERE), "__graft_entry__.py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            mod.build_libhec()
+        except Exception as e:  # noqa: BLE001
+            raise ImportError("%s is not built and could not be built (%s): run "
+                              "`python -c 'import __graft_entry__ as g; g.build()'`" % (LIB_PATH, e))
     L = C.CDLL(LIB_PATH)
     L.hec_version.restype = C.c_char_p
     L.hec_ctx_create.argtypes = [C.POINTER(vp), C.c_int, u64p, C.c_int, u64p, C.c_int, C.c_int]

@@ -24,6 +24,7 @@
  */
 #ifndef HEC_H
 #define HEC_H
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -56,6 +57,10 @@ int hec_timer_start(hec_ctx *ctx);
 int hec_timer_stop_ms(hec_ctx *ctx, float *ms); /* synchronises */
 /* number of kernels this context has launched so far (for bench.py's gpu_launches) */
 uint64_t hec_launch_count(const hec_ctx *ctx);
+/* page-lock / unlock caller memory (e.g. the backing arrays of ring.Poly.Coeffs; Go's heap does not move
+ * objects) so that copies to and from it are asynchronous DMA at full PCIe rate */
+int hec_host_register(hec_ctx *ctx, void *ptr, size_t bytes);
+int hec_host_unregister(hec_ctx *ctx, void *ptr);
 
 /* ---- plaintexts: what Encoder.EncodeCoeffs+ToNTT / EncodeNTT produce (conv.go:513-514,
  * eval.go:242-243).  limbs[0..level]. */

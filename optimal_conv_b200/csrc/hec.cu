@@ -312,6 +312,20 @@ extern "C" int hec_timer_stop_ms(hec_ctx *c, float *ms) {
     return HEC_OK;
 }
 extern "C" uint64_t hec_launch_count(const hec_ctx *c) { return c ? c->launches : 0; }
+// page-lock caller memory (e.g. the backing arrays of ring.Poly.Coeffs: Go's heap does not move objects)
+// so that uploads / downloads / hec_plan_submit_host copy asynchronously at full PCIe rate
+extern "C" int hec_host_register(hec_ctx *c, void *ptr, size_t bytes) {
+    if (!c || !ptr || !bytes) return HEC_E_INVAL;
+    cudaSetDevice(c->device);
+    HEC_CUDA(c, cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return HEC_OK;
+}
+extern "C" int hec_host_unregister(hec_ctx *c, void *ptr) {
+    if (!c || !ptr) return HEC_E_INVAL;
+    cudaSetDevice(c->device);
+    HEC_CUDA(c, cudaHostUnregister(ptr));
+    return HEC_OK;
+}
 
 // =========================================================================================
 // handles

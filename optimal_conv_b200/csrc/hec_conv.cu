@@ -338,6 +338,8 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
     if ((max_ob & (max_ob - 1)) || (norm & (norm - 1)) || norm > max_ob || max_ob > 256)
         return c->fail(HEC_E_UNSUPPORTED, "max_ob and norm must be powers of two, max_ob <= 256");
     if (c->nQ < 2 || c->nP != 1) return c->fail(HEC_E_UNSUPPORTED, "fused conv needs >= 2 Q limbs and exactly one special prime (main.go:446-454)");
+    // the epilogues of A3 / B5 add 2q to an uncorrected forward transform (< 36q): needs q0 < 2^58
+    if (c->q(c->modQ(0)) >= (1ull << 58)) return c->fail(HEC_E_UNSUPPORTED, "fused conv needs a first modulus below 2^58 (use HEC_CONV_OPLEVEL)");
     const int B = max_ob, na = B / norm, M = batch;
     for (int i = 0; i < B; i += norm)
         if (!pt_ker[i] || pt_ker[i]->level < 1) return c->fail(HEC_E_LEVEL, "kernel plaintexts must be at level >= 1 (ECD_LV)");

@@ -22,7 +22,7 @@ CONV_FUSED, CONV_OPLEVEL = 0, 1
 # every symbol include/hec.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "hec_version", "hec_ctx_create", "hec_ctx_destroy", "hec_last_error", "hec_sync", "hec_timer_start",
-    "hec_timer_stop_ms", "hec_launch_count", "hec_pt_upload", "hec_pt_free", "hec_ct_upload", "hec_ct_download",
+    "hec_timer_stop_ms", "hec_launch_count", "hec_host_register", "hec_host_unregister", "hec_pt_upload", "hec_pt_free", "hec_ct_upload", "hec_ct_download",
     "hec_ct_copy_new", "hec_ct_level", "hec_ct_scale", "hec_ct_set_scale", "hec_ct_free", "hec_swk_upload",
     "hec_swk_drop", "hec_mul_pt_new", "hec_mult_by_const", "hec_rescale", "hec_set_scale", "hec_add", "hec_add_new",
     "hec_sub_new", "hec_add_pt", "hec_rotate_gal", "hec_rotate_new", "hec_rotate_hoisted", "hec_galois_for_rotation",
@@ -69,6 +69,8 @@ def lib():
     L.hec_timer_stop_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.hec_launch_count.argtypes = [vp]
     L.hec_launch_count.restype = C.c_uint64
+    L.hec_host_register.argtypes = [vp, vp, C.c_size_t]
+    L.hec_host_unregister.argtypes = [vp, vp]
     L.hec_pt_upload.argtypes = [vp, C.c_int, u64pp, C.c_double, C.POINTER(vp)]
     L.hec_pt_free.argtypes = [vp, vp]
     L.hec_pt_free.restype = None
@@ -210,6 +212,13 @@ class Context:
         ms = C.c_float()
         self._chk(self.L.hec_timer_stop_ms(self.h, C.byref(ms)))
         return ms.value
+
+    def host_register(self, arr):
+        """page-lock a numpy array in place (hec_host_register)"""
+        self._chk(self.L.hec_host_register(self.h, arr.ctypes.data, arr.nbytes))
+
+    def host_unregister(self, arr):
+        self._chk(self.L.hec_host_unregister(self.h, arr.ctypes.data))
 
     def launch_count(self):
         return int(self.L.hec_launch_count(self.h))

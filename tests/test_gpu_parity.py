@@ -303,7 +303,9 @@ def test_plan_batch_device_and_host_runs(orc, idx_np):
         in0 = np.stack([w["ct"][m][0] for m in range(3)])
         in1 = np.stack([w["ct"][m][1] for m in range(3)])
         o0, o1 = np.zeros((3, N), dtype=np.uint64), np.zeros((3, N), dtype=np.uint64)
+        c.host_register(in0)  # page-locked caller memory: asynchronous copies
         plan.run_host(in0, in1, o0, o1)
+        c.host_unregister(in0)
         for m in range(3):
             assert np.array_equal(o0[m], refs[m].c0[0]) and np.array_equal(o1[m], refs[m].c1[0]), m
         # pipelined submissions (two batches in flight, copies overlap kernels): same bits

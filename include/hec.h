@@ -146,7 +146,9 @@ int hec_keep_ctxt(hec_ctx *ctx, const hec_ct *input, const hec_pt *mask, double 
 
 /* A prepared evalConv_BN for `batch` independent input ciphertexts per run: kernel
  * plaintexts, monomials, bias and keys stay resident; the kernel sequence is captured in a
- * CUDA graph.  in_level must be 1 (ECD_LV) in this build. */
+ * CUDA graph.  in_level must be 1 (ECD_LV) in this build.  The plan keeps its own scaled copy of the
+ * kernel plaintexts but references pt_idx, pt_bias and the uploaded keys: they (and the context) must
+ * outlive the plan. */
 int hec_plan_create(hec_ctx *ctx, const hec_pt *const *pt_ker, int max_ob, int norm, double in_scale,
                     double out_scale, const hec_pt *const *pt_idx, const hec_pt *pt_bias, int batch,
                     hec_plan **plan);

@@ -505,3 +505,24 @@ def test_full_level_keyswitch_alpha5_beta6():
             assert np.array_equal(d0, e0) and np.array_equal(d1, e1), level
     finally:
         c.close()
+
+
+def test_plan_batch_with_norm_and_no_bias(orc, idx_np):
+    """batch of 2 ciphertexts, B = 8 with norm = 2 (4 real channels, 2 pack levels), bias omitted"""
+    c = hec.Context(PR.LOGN, Q2, P1)
+    try:
+        w = common.workload({"B": 8, "seed": 88}, n_ct=2)
+        G = common.GpuConv(c, w, idx_np, norm=2)
+        plan = c.plan(G.ker, 2, PR.SCALE, PR.SCALE, G.idx, None, 2)
+        outs = plan.run(G.cts)
+        for m in range(2):
+            ref = common.oracle_conv(orc, w, 2, PR.SCALE, idx_np, m=m, bias=False)
+            g0, g1 = outs[m].download()
+            assert np.array_equal(g0, ref.c0) and np.array_equal(g1, ref.c1), m
+        with pytest.raises(hec.HecError) as e:  # inputs must carry the plan's scale
+            bad = c.upload_ct(w["ct"][0][0], w["ct"][0][1], PR.SCALE * 2)
+            plan.run([bad, G.cts[1]])
+        assert e.value.code == hec.HEC_E_SCALE
+        plan.destroy()
+    finally:
+        c.close()

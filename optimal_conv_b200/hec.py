@@ -149,10 +149,10 @@ class Plaintext:
 
 
 class Ciphertext:
-    """ckks.Ciphertext on the device."""
+    """ckks.Ciphertext on the device.  `owned=False` marks handles that belong to a Plan."""
 
-    def __init__(self, ctx, h):
-        self.ctx, self.h = ctx, h
+    def __init__(self, ctx, h, owned=True):
+        self.ctx, self.h, self.owned = ctx, h, owned
 
     @property
     def level(self):
@@ -173,9 +173,9 @@ class Ciphertext:
         return c0, c1
 
     def free(self):
-        if self.h:
+        if self.h and self.owned:
             self.ctx.L.hec_ct_free(self.ctx.h, self.h)
-            self.h = None
+        self.h = None
 
 
 class Context:
@@ -375,7 +375,7 @@ class Plan:
         """device-resident run; returns `batch` level-0 ciphertext handles (reused across runs)."""
         ins = (vp * self.batch)(*[c.h for c in cts])
         self.ctx._chk(self.ctx.L.hec_plan_run(self.h, ins, self._outs))
-        return [Ciphertext(self.ctx, vp(self._outs[i])) for i in range(self.batch)]
+        return [Ciphertext(self.ctx, vp(self._outs[i]), owned=False) for i in range(self.batch)]
 
     def _host_ptrs(self, in_c0, in_c1, out_c0, out_c1):
         N = self.ctx.N
@@ -423,5 +423,9 @@ class Plan:
 
     def destroy(self):
         if self.h:
+            for i in range(self.batch):
+                if self._outs[i]:
+                    self.ctx.L.hec_ct_free(self.ctx.h, self._outs[i])
+                    self._outs[i] = None
             self.ctx.L.hec_plan_destroy(self.h)
             self.h = None

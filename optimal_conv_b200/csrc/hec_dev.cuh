@@ -61,7 +61,12 @@ __device__ __forceinline__ u64 mred(u64 x, u64 y, u64 q, u64 qinv) {
     u64 r = mred_lazy(x, y, q, qinv);
     return r >= q ? r - q : r;
 }
-__device__ __forceinline__ u64 cred(u64 a, u64 q) { return a >= q ? a - q : a; }
+// conditional subtraction a >= q ? a - q : a as a predicated 64-bit subtract (2 ISETP + 2 predicated
+// IADD3 instead of compare + subtract + 2 SEL)
+__device__ __forceinline__ u64 cred(u64 a, u64 q) {
+    asm("{\n\t.reg .pred p;\n\tsetp.ge.u64 p, %0, %1;\n\t@p sub.u64 %0, %0, %1;\n\t}" : "+l"(a) : "l"(q));
+    return a;
+}
 __device__ __forceinline__ u64 addmod(u64 a, u64 b, u64 q) { return cred(a + b, q); }
 __device__ __forceinline__ u64 submod(u64 a, u64 b, u64 q) { return cred(a + q - b, q); }
 

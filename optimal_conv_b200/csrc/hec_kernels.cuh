@@ -363,12 +363,9 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convB4(ConvB P, const
 #pragma unroll
     for (int k = 0; k < 16; k++) out[G.gB(k)] = x[k];
 }
-#ifndef HEC_MINB_B5
-#define HEC_MINB_B5 HEC_MINB
-#endif
 // B5: finish NTT_q0, mod-down combine with acc_Q = z*key[c] (Q limb), + tmp2.c0 (c = 0),
 //     apply sigma_g inside the 256-word block, add tmp1 (+ bias)           grid.y = M*nb*2
-__global__ void __launch_bounds__(HEC_THREADS, HEC_MINB_B5) k_convB5(ConvB P, const ModC *__restrict__ mods) {
+__global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convB5(ConvB P, const ModC *__restrict__ mods) {
     __shared__ u64 sm[16 * HEC_ROW_PITCH];
     const BJob J(blockIdx.y, true, P);
     const ModC M = mods[P.mq0];

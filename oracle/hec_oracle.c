@@ -601,6 +601,16 @@ static void decompose_digit(const orc_ctx *c, int level, int d, const u64 *c1ntt
  * (< 2^64 only if rhi small).  ntt_lazy's first stage computes U + V with U the raw
  * input, so inputs must stay below 2^64 - 2q; both sources satisfy it (rhi < n*q_src). */
 
+/* test hook: DecomposeAndSplit + NTT of digit d, given c1 in the NTT domain ([level+1][N]);
+ * dQ [(level+1)][N], dP [nP][N] (NTT domain, any representative) */
+void orc_decompose_digit(const orc_ctx *c, int level, int d, const uint64_t *c1ntt, uint64_t *dQ, uint64_t *dP) {
+    int N = c->N, L = level + 1;
+    u64 *cinv = (u64 *)malloc((size_t)L * N * 8);
+    for (int i = 0; i < L; i++) intt_core(&c->Q[i], N, c1ntt + (size_t)i * N, cinv + (size_t)i * N, 0);
+    decompose_digit(c, level, d, c1ntt, cinv, dQ, dP);
+    free(cinv);
+}
+
 void orc_keyswitch(const orc_ctx *c, int level, const uint64_t *c1, const uint64_t *swk,
                    uint64_t *d0, uint64_t *d1) {
     int N = c->N, nQ = c->nQ, nP = c->nP, L = level + 1;

@@ -63,6 +63,7 @@ def lib():
         L.orc_add.argtypes = [C.c_void_p, C.c_int, u64p, u64p, u64p]
         L.orc_sub.argtypes = [C.c_void_p, C.c_int, u64p, u64p, u64p]
         L.orc_keyswitch.argtypes = [C.c_void_p, C.c_int, u64p, u64p, u64p, u64p]
+        L.orc_decompose_digit.argtypes = [C.c_void_p, C.c_int, C.c_int, u64p, u64p, u64p]
         L.orc_moddown.argtypes = [C.c_void_p, C.c_int, u64p, u64p, u64p]
         L.orc_rotate_gal.argtypes = [C.c_void_p, C.c_int, u64p, u64p, C.c_uint64, u64p, u64p, u64p]
         L.orc_conv_then_pack.restype = C.c_int
@@ -208,6 +209,15 @@ class Oracle:
         d0, d1 = np.empty_like(c1), np.empty_like(c1)
         self.L.orc_keyswitch(self.h, lv, _p(c1), _p(swk), _p(d0), _p(d1))
         return d0, d1
+
+    def decompose_digit(self, c1, d):
+        """digit d of DecomposeSingleNTT for c1 [(level+1)][N] (NTT domain) -> (dQ, dP), NTT domain"""
+        c1 = np.ascontiguousarray(c1)
+        lv = c1.shape[0] - 1
+        dQ = np.empty_like(c1)
+        dP = np.empty((len(self.P), self.N), dtype=np.uint64)
+        self.L.orc_decompose_digit(self.h, lv, d, _p(c1), _p(dQ), _p(dP))
+        return dQ, dP
 
     def moddown(self, accQ, accP):
         accQ, accP = np.ascontiguousarray(accQ), np.ascontiguousarray(accP)

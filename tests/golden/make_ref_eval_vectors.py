@@ -1,0 +1,176 @@
+"""Golden vectors from the reference's OWN compiled evaluator code, up to main.conv_then_pack itself.
+
+Run from the repo root in the build container (needs /root/reference/test_run, objdump, nm):
+    python tests/golden/make_ref_eval_vectors.py            # small-N cases, ~2 min
+    python tests/golden/make_ref_eval_vectors.py --only n8_B4      # regenerate one small case
+    python tests/golden/make_ref_eval_vectors.py --full B4_norm1   # N = 2^16 golden config, ~1 h
+The prebuilt binary is never executed.  tests/golden/refmachine.py interprets the compiled routines of
+the Lattigo fork (ring / rlwe / ckks packages) and of package main from their disassembly; objects
+(rings, basis extender, key switcher, evaluator) are built by the reference's own constructors
+(ring.NewRing, ring.NewFastBasisExtender, rlwe.NewKeySwitcher, ckks.NewEvaluator) run the same way.
+Inputs are the repo's seeded synthetic operands (optimal_conv_b200/synth.py), so only SHA-256 digests of
+the outputs are stored: tests/golden/ref_eval_vectors.json, consumed by tests/test_ref_eval_vectors.py.
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, HERE)
+
+import common  # noqa: E402
+from refmachine import CKKS, RING, RLWE, GoPanic, Machine, f2b  # noqa: E402
+from optimal_conv_b200 import params as PR, synth  # noqa: E402
+
+OUT = os.path.join(HERE, "ref_eval_vectors.json")
+OPERAND_CT = "go.itab.*" + CKKS + "Ciphertext," + CKKS + "Operand"
+OPERAND_PT = "go.itab.*" + CKKS + "Plaintext," + CKKS + "Operand"
+
+
+def ints(a):
+    return [int(v) for v in a]
+
+
+def monomials(m, rQ, logN, q0):
+    """pl_idx[i] = NTT(X^(2^i)) at level 0 (conv.go:241-254), transformed by the reference's NTT"""
+    N = 1 << logN
+    out = []
+    for i in range(logN):
+        mono = [0] * N
+        mono[1 << i] = 1
+        pin, pout = m.new_poly([mono]), m.new_poly([[0] * N])
+        m.call(RING + "(*Ring).NTTLvl", [rQ, 0, pin, pout])
+        out.append(m.read_poly(pout)[0])
+    return out
+
+
+# ---------------------------------------------------------------- ring / rlwe level
+def ring_cases():
+    out = {}
+    logN, N = 8, 256
+    for name, Q, P in (("set6_a1", PR.Q_SET6[:3], PR.P_ALL[:1]), ("set7_a2", PR.Q_SET7[:4], PR.P_ALL[:2]),
+                       ("set6_a5", PR.Q_SET6[:6], PR.P_ALL[:5])):
+        m = Machine()
+        rQ, rP = m.new_ring(N, Q), m.new_ring(N, P)
+        rec = {"logN": logN, "Q": ["%x" % q for q in Q], "P": ["%x" % p for p in P], "div_round": {}, "moddown": {},
+               "keyswitch": {}, "decompose": {}}
+        # tables as the reference's genNTTParams builds them
+        rec["tables"] = {"psi": [common.sha(m.read_slice_u64(m.rq(r + 192) + 24 * i)) for r, mods in ((rQ, Q), (rP, P)) for i in range(len(mods))],
+                         "psi_inv": [common.sha(m.read_slice_u64(m.rq(r + 216) + 24 * i)) for r, mods in ((rQ, Q), (rP, P)) for i in range(len(mods))],
+                         "n_inv": [m.rq(m.rq(r + 240) + 8 * i) for r, mods in ((rQ, Q), (rP, P)) for i in range(len(mods))],
+                         "mred": [m.rq(m.rq(r + 96) + 8 * i) for r, mods in ((rQ, Q), (rP, P)) for i in range(len(mods))]}
+        for level in range(1, len(Q)):
+            a = [ints(synth.uniform_mod(10 + i, N, Q[i])) for i in range(level + 1)]
+            pin, pout = m.new_poly(a), m.new_poly([[0] * N for _ in range(level + 1)])
+            m.call(RING + "(*Ring).divRoundByLastModulusNTT", [rQ, level, pin, pout])
+            rec["div_round"][str(level)] = common.sha(np.array(m.read_poly(pout, level), dtype=np.uint64))
+        be = m.call(RING + "NewFastBasisExtender", [rQ, rP, 0])[2]
+        for level in range(0, len(Q)):
+            aQ = [ints(synth.uniform_mod(20 + i, N, Q[i])) for i in range(level + 1)]
+            aP = [ints(synth.uniform_mod(30 + i, N, P[i])) for i in range(len(P))]
+            pQ, pP, p2 = m.new_poly(aQ), m.new_poly(aP), m.new_poly([[0] * N for _ in range(level + 1)])
+            m.call(RING + "(*FastBasisExtender).ModDownSplitNTTPQ", [be, level, pQ, pP, p2])
+            rec["moddown"][str(level)] = common.sha(np.array(m.read_poly(p2), dtype=np.uint64))
+        params = [logN] + m.slice_u64(Q) + m.slice_u64(P) + [f2b(3.2), rQ, rP, 0]
+        ks = m.call(RLWE + "NewKeySwitcher", params + [0])[11]
+        beta_full = (len(Q) + len(P) - 1) // len(P)
+        swk = np.stack([np.stack([synth.uniform_limbs(7000 + 10 * d + k, list(Q) + list(P), N) for k in range(2)])
+                        for d in range(beta_full)])
+        key = m.new_swk(swk)
+        for level in range(0, len(Q)):
+            c1 = synth.uniform_limbs(41 + level, Q[:level + 1], N)
+            cx = m.new_poly([ints(c1[i]) for i in range(level + 1)])
+            m.wb(cx + 24, 1)
+            p0, p1 = m.new_poly([[0] * N for _ in Q]), m.new_poly([[0] * N for _ in Q])
+            m.call(RLWE + "(*KeySwitcher).SwitchKeysInPlace", [ks, level, cx, key, p0, p1])
+            rec["keyswitch"][str(level)] = [common.sha(np.array(m.read_poly(p, level + 1), dtype=np.uint64)) for p in (p0, p1)]
+        rec["interpreted_instructions"] = m.steps
+        out[name] = rec
+        print("ring case", name, m.steps, flush=True)
+    return out
+
+
+# ---------------------------------------------------------------- the conv path
+def conv_case(logN, B, norm, seed, out_scale, Q2, P1, bias=True, ct_scale=PR.SCALE, pt_scale=PR.SCALE):
+    """main.conv_then_pack (conv.go:522-546) + evaluator.Add(ct, pl_bn_b, ct) (eval.go:258) on the seeded workload"""
+    N = 1 << logN
+    t0 = time.time()
+    w = synth.conv_workload(Q2, P1, logN, B, seed)
+    m = Machine()
+    keys = {(1 << (j + 1)) + 1: w["keys"][j] for j in w["keys"]}
+    params, ev = m.new_evaluator(logN, Q2, P1, PR.SCALE, keys)
+    rQ = params[8]
+    c0, c1 = w["ct"][0]
+    ct = m.new_ct([[ints(c0[i]) for i in range(2)], [ints(c1[i]) for i in range(2)]], ct_scale)
+    pl_ker = [m.new_pt([ints(w["pt_ker"][b][i]) for i in range(2)], pt_scale) if b % norm == 0 else 0 for b in range(B)]
+    idx = monomials(m, rQ, logN, Q2[0])
+    pl_idx = [m.new_pt([idx[i]], 1.0) for i in range(logN)]
+    args = params + ev + [ct] + m.slice_u64(pl_ker) + m.slice_u64(pl_idx) + [B, norm, 1, f2b(out_scale)] + [0]
+    rec = {"logN": logN, "B": B, "norm": norm, "seed": seed, "out_scale": out_scale, "ct_scale": ct_scale, "pt_scale": pt_scale,
+           "Q": ["%x" % q for q in Q2], "P": ["%x" % p for p in P1], "monomials": common.sha(np.array(idx, dtype=np.uint64))}
+    try:
+        res = m.call("main.conv_then_pack", args, max_steps=1 << 62)[-1]
+    except RuntimeError as ex:
+        if isinstance(ex.__cause__, GoPanic):
+            rec["panic"] = str(ex.__cause__)
+            rec["interpreted_instructions"] = m.steps
+            return rec
+        raise
+    polys, sc = m.read_ct(res)
+    rec["nobias"] = {"c0": common.sha(np.array(polys[0], dtype=np.uint64)), "c1": common.sha(np.array(polys[1], dtype=np.uint64)),
+                     "scale": sc, "level": len(polys[0]) - 1}
+    if bias:
+        pb = m.new_pt([ints(w["bias"])], out_scale)   # eval.go:240: NewPlaintext(params, 0, out_scale); :252 panics otherwise
+        m.call(CKKS + "(*evaluator).Add", [ev[1], m.sym[OPERAND_CT][0], res, m.sym[OPERAND_PT][0], pb, res], max_steps=1 << 62)
+        polys, sc = m.read_ct(res)
+        rec["bias"] = {"c0": common.sha(np.array(polys[0], dtype=np.uint64)), "c1": common.sha(np.array(polys[1], dtype=np.uint64)),
+                       "scale": sc, "level": len(polys[0]) - 1}
+    rec["interpreted_instructions"] = m.steps
+    print("conv case logN=%d B=%d norm=%d: %d instructions, %.0f s" % (logN, B, norm, m.steps, time.time() - t0), flush=True)
+    return rec
+
+
+SMALL_CONV = [
+    # name, logN, B, norm, seed, out_scale, Q, P
+    ("n8_B4", 8, 4, 1, 3, PR.SCALE, PR.Q_SET6[:2], PR.P_PACK),
+    ("n8_B2", 8, 2, 1, 4, PR.SCALE, PR.Q_SET6[:2], PR.P_PACK),
+    ("n10_B16", 10, 16, 1, 5, PR.SCALE, PR.Q_SET6[:2], PR.P_PACK),
+    ("n10_B16_norm2", 10, 16, 2, 6, PR.SCALE, PR.Q_SET6[:2], PR.P_PACK),
+    ("n10_B8_norm4_s25", 10, 8, 4, 7, float(1 << 25), PR.Q_SET6[:2], PR.P_PACK),
+    ("n9_B8_set7", 9, 8, 1, 8, PR.SCALE, PR.Q_SET7[:2], PR.P_PACK),
+    ("n8_B4_norm4_single", 8, 4, 4, 9, PR.SCALE, PR.Q_SET6[:2], PR.P_PACK),
+    ("n8_B4_scale_panic", 8, 4, 4, 10, float(2 ** 80), PR.Q_SET6[:2], PR.P_PACK),
+    ("n8_B256", 8, 256, 1, 11, PR.SCALE, PR.Q_SET6[:2], PR.P_PACK),
+]
+
+
+def main():
+    data = json.load(open(OUT)) if os.path.exists(OUT) else {}
+    data["binary"] = "test_run (go1.16.6, github.com/dwkim606/test_lattigo v0.0.0-20220812213541-eb33b0555aaa)"
+    if "--full" in sys.argv:
+        name = sys.argv[sys.argv.index("--full") + 1]
+        cfg = [c for c in common.GOLDEN_CONFIGS if c["name"] == name][0]
+        rec = conv_case(PR.LOGN, cfg["B"], cfg["norm"], cfg["seed"], float(1 << cfg["out_log"]), common.Q2, common.P1)
+        data = json.load(open(OUT)) if os.path.exists(OUT) else data
+        data.setdefault("conv_full", {})[name] = rec
+    elif "--only" in sys.argv:
+        for name, logN, B, norm, seed, out_scale, Q2, P1 in SMALL_CONV:
+            if name in sys.argv:
+                data["conv"][name] = conv_case(logN, B, norm, seed, out_scale, Q2, P1)
+    else:
+        data["ring"] = ring_cases()
+        data["conv"] = {}
+        for name, logN, B, norm, seed, out_scale, Q2, P1 in SMALL_CONV:
+            data["conv"][name] = conv_case(logN, B, norm, seed, out_scale, Q2, P1)
+    json.dump(data, open(OUT, "w"), indent=1, sort_keys=True)
+    print("wrote", OUT)
+
+
+if __name__ == "__main__":
+    main()

@@ -90,7 +90,9 @@ def disassemble(path, start, size):
             caddr = int(com.split()[0], 16)
         rest = re.sub(r"<.*?>", "", rest).strip()
         ins.target = None
-        if ins.mn.startswith("j") or ins.mn == "call":
+        if (ins.mn.startswith("j") or ins.mn == "call") and rest.startswith("*"):
+            ins.ops = [_parse_op(rest[1:], caddr)]     # indirect: target read at run time
+        elif ins.mn.startswith("j") or ins.mn == "call":
             ins.target = int(rest.split()[0], 16)
             ins.ops = []
         else:
@@ -159,6 +161,26 @@ class Emu:
         self.allowed.add(start)
         return start
 
+    def name_of(self, addr):
+        """symbol containing addr (for messages and the autoload whitelist)"""
+        if not hasattr(self, "_ranges"):
+            self._ranges = sorted((a, a + sz, n) for n, (a, sz) in self.sym.items() if sz)
+        import bisect
+        i = bisect.bisect_right(self._ranges, (addr, 1 << 62, "")) - 1
+        if i >= 0 and self._ranges[i][0] <= addr < self._ranges[i][1]:
+            return self._ranges[i][2]
+        return None
+
+    auto_prefixes = ()
+
+    def autoload(self, addr):
+        """load the routine containing addr if its symbol is in a whitelisted (pure-Go) package"""
+        name = self.name_of(addr)
+        if name is None or not name.startswith(self.auto_prefixes):
+            return False
+        self.load(name)
+        return addr in self.code
+
     def load_const(self, addr):
         """8 bytes of the binary's read-only data at virtual address addr"""
         if addr in self.rodata:
@@ -172,14 +194,28 @@ class Emu:
                     v = struct.unpack("<Q", f.read(8))[0]
                     self.rodata[addr] = v
                     return v
+                if seg["p_type"] == "PT_LOAD" and seg["p_vaddr"] <= addr < seg["p_vaddr"] + seg["p_memsz"]:
+                    return 0  # .bss / .noptrbss: zero at load time (e.g. runtime.writeBarrier.enabled)
         raise ValueError("constant outside file at %x" % addr)
 
     # ---- memory ----
+    def _image(self, a):
+        """aligned qword not written by this run: the binary's own data (itabs, type descriptors) or zero"""
+        if 0x400000 <= a < 0x1000000:
+            try:
+                return self.load_const(a)
+            except ValueError:
+                return 0
+        return 0
+
     def rq(self, a):
         if a & 7 == 0:
-            return self.mem.get(a, 0)
-        lo = self.mem.get(a & ~7, 0)
-        hi = self.mem.get((a & ~7) + 8, 0)
+            v = self.mem.get(a)
+            return v if v is not None else self._image(a)
+        lo = self.mem.get(a & ~7)
+        hi = self.mem.get((a & ~7) + 8)
+        lo = lo if lo is not None else self._image(a & ~7)
+        hi = hi if hi is not None else self._image((a & ~7) + 8)
         sh = (a & 7) * 8
         return ((lo >> sh) | (hi << (64 - sh))) & M64
 
@@ -234,7 +270,10 @@ class Emu:
         if k == "i":
             return op[1] & ((1 << (size * 8)) - 1)
         if k == "c":
-            return self.load_const(op[1]) & ((1 << (size * 8)) - 1)
+            if (op[1] & ~7) in self.mem:        # a global this run has written
+                return self.rd(op[1], size)
+            return (self.load_const(op[1] & ~7) >> ((op[1] & 7) * 8)) & ((1 << (size * 8)) - 1) if op[1] & 7 and size < 8 \
+                else self.load_const(op[1]) & ((1 << (size * 8)) - 1)
         if k == "m":
             a = self.ea(op)
             if a == ("G",):
@@ -252,6 +291,10 @@ class Emu:
             else:
                 m = (1 << (s * 8)) - 1
                 self.r[i] = (self.r[i] & ~m) | (v & m)
+        elif op[0] == "c":
+            if (op[1] & ~7) not in self.mem:
+                self.mem[op[1] & ~7] = self.load_const(op[1] & ~7)
+            self.wr(op[1], size, v)
         else:
             self.wr(self.ea(op), size, v)
 
@@ -314,6 +357,8 @@ class Emu:
         """Call function `name` with the Go stack-ABI argument/result area `stack_words` (list of u64 placed
         right above the return address).  Returns the argument/result area after the call."""
         entry = self.sym[name][0]
+        if entry not in self.code:
+            self.load(name)
         sp = 0x7e0000000000
         self.r[4] = sp
         self.wq(sp, 0xdeadbeef)  # sentinel return address
@@ -324,8 +369,13 @@ class Emu:
         while pc != 0xdeadbeef:
             ins = code.get(pc)
             if ins is None:
-                raise RuntimeError("pc %x outside loaded routines" % pc)
-            pc = self._exec(ins)
+                if not self.autoload(pc):    # tail jump into another whitelisted routine
+                    raise RuntimeError("pc %x (%s) outside loaded routines" % (pc, self.name_of(pc)))
+                ins = code[pc]
+            try:
+                pc = self._exec(ins)
+            except Exception as ex:
+                raise RuntimeError("at %x in %s: %s %s: %r" % (ins.addr, self.name_of(ins.addr), ins.mn, ins.ops, ex)) from ex
             self.steps += 1
             if self.steps > max_steps:
                 raise RuntimeError("step limit")
@@ -334,9 +384,25 @@ class Emu:
     def _exec(self, ins):
         mn, ops = ins.mn, ins.ops
         nxt = ins.next
+        if mn == "movq" and (ops[0][0] == "x" or ops[1][0] == "x"):
+            if ops[0][0] == "x":
+                self.put(ops[1], 8, self.x[ops[0][1]] & M64)
+            else:
+                self.x[ops[1][1]] = self.get(ops[0], 8)
+            return nxt
         if mn == "mov" or mn in ("movq", "movl", "movb", "movw", "movabs"):
             size = self.opsize(ops, mn)
             self.put(ops[1], size, self.get(ops[0], size))
+            return nxt
+        if len(mn) == 6 and mn[:4] in ("movz", "movs") and mn[4] in "bwl" and mn[5] in "wlq":
+            ss = {"b": 1, "w": 2, "l": 4}[mn[4]]
+            v = self.get(ops[0], ss)
+            if mn[3] == "s":
+                v = _sx(v, ss)
+            self.put(ops[1], {"w": 2, "l": 4, "q": 8}[mn[5]], v)
+            return nxt
+        if mn.startswith("set") and len(ops) == 1:
+            self.put(ops[0], 1, int(self.cond(mn[3:])))
             return nxt
         if mn == "lea":
             a = ops[0][1] if ops[0][0] == "c" else self.ea(ops[0])
@@ -375,13 +441,27 @@ class Emu:
                 raise ZeroDivisionError("div fault at %x" % ins.addr)
             self.r[0], self.r[2] = n // d, n % d
             return nxt
+        if mn == "cqto":
+            self.r[2] = M64 if self.r[0] >> 63 else 0
+            return nxt
+        if mn == "idiv":
+            size = self.opsize(ops, mn)
+            assert size == 8
+            d = _sx(self.get(ops[0], 8), 8)
+            n = _sx((self.r[2] << 64) | self.r[0], 16)
+            if d == 0:
+                raise ZeroDivisionError("idiv fault at %x" % ins.addr)
+            qt = abs(n) // abs(d)
+            qt = -qt if (n < 0) != (d < 0) else qt
+            self.r[0], self.r[2] = qt & M64, (n - qt * d) & M64
+            return nxt
         if mn == "bswap":
             size = self.opsize(ops, mn)
             v = self.get(ops[0], size)
             self.put(ops[0], size, int.from_bytes(v.to_bytes(size, "little"), "big"))
             return nxt
         if mn in ("rol", "ror"):
-            size = self.opsize(ops, mn)
+            size = self.opsize(ops[-1:], mn)
             cnt, dst = (1, ops[0]) if len(ops) == 1 else (self.get(ops[0], 1) & (size * 8 - 1), ops[1])
             v, bits = self.get(dst, size), size * 8
             if cnt:
@@ -412,16 +492,17 @@ class Emu:
                 self.r[ops[1][1]] &= 0xffffffff
             return nxt
         if mn == "jmp":
-            return ins.target
+            return ins.target if ins.target is not None else self.get(ops[0], 8)
         if mn == "call":
-            if ins.target in self.hooks:
-                self.hooks[ins.target](self)
+            tgt = ins.target if ins.target is not None else self.get(ops[0], 8)
+            if tgt in self.hooks:
+                self.hooks[tgt](self)
                 return nxt
-            if ins.target not in self.allowed:
-                raise RuntimeError("call to non-whitelisted %x at %x" % (ins.target, ins.addr))
+            if tgt not in self.code and not self.autoload(tgt):
+                raise RuntimeError("call to non-whitelisted %x (%s) at %x" % (tgt, self.name_of(tgt), ins.addr))
             self.r[4] = (self.r[4] - 8) & M64
             self.wq(self.r[4], nxt)
-            return ins.target
+            return tgt
         if mn == "ret":
             pc = self.rq(self.r[4])
             self.r[4] = (self.r[4] + 8) & M64
@@ -448,11 +529,11 @@ class Emu:
                 self.put(ops[1], size, res)
             return nxt
         if mn in ("shl", "shr", "sar"):
-            size = self.opsize(ops, mn)
+            size = self.opsize(ops[-1:], mn)
             if len(ops) == 1:
                 cnt, dst = 1, ops[0]
             else:
-                cnt, dst = self.get(ops[0], 1) & 63, ops[1]
+                cnt, dst = self.get(ops[0], 1) & (63 if size == 8 else 31), ops[1]
             v = self.get(dst, size)
             bits = size * 8
             if cnt:
@@ -501,8 +582,10 @@ class Emu:
             else:
                 self.x[ops[1][1]] = self.get(ops[0], 8)
             return nxt
-        if mn == "movups":
-            if ops[0][0] == "x":
+        if mn in ("movups", "movaps", "movupd", "movapd", "movdqu", "movdqa"):
+            if ops[0][0] == "x" and ops[1][0] == "x":
+                self.x[ops[1][1]] = self.x[ops[0][1]]
+            elif ops[0][0] == "x":
                 a = self.ea(ops[1])
                 self.wq(a, self.x[ops[0][1]] & M64)
                 self.wq(a + 8, self.x[ops[0][1]] >> 64)
@@ -510,8 +593,39 @@ class Emu:
                 a = self.ea(ops[0])
                 self.x[ops[1][1]] = self.rq(a) | (self.rq(a + 8) << 64)
             return nxt
-        if mn == "xorps":
-            self.x[ops[1][1]] ^= self.x[ops[0][1]]
+        if mn in ("xorps", "xorpd", "pxor", "andpd", "andps", "pand", "orpd", "orps", "por", "andnpd", "andnps", "pandn"):
+            a = self.x[ops[0][1]] if ops[0][0] == "x" else (self.get(ops[0], 8) | (self.rq((ops[0][1] if ops[0][0] == "c" else self.ea(ops[0])) + 8) << 64))
+            d = self.x[ops[1][1]]
+            if mn in ("xorps", "xorpd", "pxor"):
+                d ^= a
+            elif mn in ("andpd", "andps", "pand"):
+                d &= a
+            elif mn in ("orpd", "orps", "por"):
+                d |= a
+            else:
+                d = (~d & ((1 << 128) - 1)) & a
+            self.x[ops[1][1]] = d
+            return nxt
+        if mn in ("cmpltsd", "cmplesd", "cmpeqsd", "cmpneqsd", "cmpnltsd", "cmpnlesd", "cmpunordsd", "cmpordsd"):
+            b = b2f(self.x[ops[0][1]] if ops[0][0] == "x" else self.get(ops[0], 8))
+            a = b2f(self.x[ops[1][1]])
+            un = a != a or b != b
+            r = {"cmpltsd": (not un) and a < b, "cmplesd": (not un) and a <= b, "cmpeqsd": (not un) and a == b,
+                 "cmpneqsd": un or a != b, "cmpnltsd": un or not a < b, "cmpnlesd": un or not a <= b,
+                 "cmpunordsd": un, "cmpordsd": not un}[mn]
+            self.x[ops[1][1]] = (self.x[ops[1][1]] & ~M64) | (M64 if r else 0)
+            return nxt
+        if mn == "sqrtsd":
+            b = b2f(self.x[ops[0][1]] if ops[0][0] == "x" else self.get(ops[0], 8))
+            import math
+            self.x[ops[1][1]] = (self.x[ops[1][1]] & ~M64) | f2b(math.sqrt(b) if b >= 0 else float("nan"))
+            return nxt
+        if mn == "btr":
+            size = self.opsize(ops[-1:], mn)
+            bit = self.get(ops[0], 1) & (size * 8 - 1)
+            v = self.get(ops[1], size)
+            self.cf = (v >> bit) & 1
+            self.put(ops[1], size, v & ~(1 << bit))
             return nxt
         if mn in ("addsd", "subsd", "divsd", "mulsd"):
             b = b2f(self.x[ops[0][1]] if ops[0][0] == "x" else self.get(ops[0], 8))

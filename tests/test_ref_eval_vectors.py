@@ -1,0 +1,113 @@
+"""Pins against the reference's OWN compiled evaluator code, up to main.conv_then_pack itself.
+
+tests/golden/ref_eval_vectors.json was produced by interpreting (never executing) the compiled routines
+of the reference's prebuilt binary: the Lattigo fork's ring.NewRing / divRoundByLastModulusNTT /
+ModDownSplitNTTPQ, rlwe.SwitchKeysInPlace, ckks.NewEvaluator / Add, and main.conv_then_pack
+(tests/golden/make_ref_eval_vectors.py + refmachine.py + x86emu.py).  The CPU tests below run the
+oracle on the same seeded operands and require identical SHA-256 digests; the GPU test requires the same
+of libhec at N = 2^16."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import common
+from optimal_conv_b200 import params as PR, synth
+from oracle.orc import Ct, Oracle
+
+REF = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_eval_vectors.json")))
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "conv_golden.json")))
+
+
+def mods(rec):
+    return [int(q, 16) for q in rec["Q"]], [int(p, 16) for p in rec["P"]]
+
+
+@pytest.mark.parametrize("name", sorted(REF["ring"]))
+def test_tables_rescale_moddown_keyswitch_match_reference_code(name):
+    """NewRing's tables (psi, psi^-1 bit-reversed Montgomery, N^-1, q^-1 mod 2^64), divRoundByLastModulusNTT
+    (every level), ModDownSplitNTTPQ (every level) and SwitchKeysInPlace (every level) for alpha = 1, 2, 5"""
+    rec = REF["ring"][name]
+    Q, P = mods(rec)
+    N = 1 << rec["logN"]
+    o = Oracle(rec["logN"], Q, P)
+    sel = [(0, i) for i in range(len(Q))] + [(1, i) for i in range(len(P))]
+    assert [common.sha(o.table(r, i, 0)) for r, i in sel] == rec["tables"]["psi"]
+    assert [common.sha(o.table(r, i, 1)) for r, i in sel] == rec["tables"]["psi_inv"]
+    assert [o.const(r, i, 4) for r, i in sel] == rec["tables"]["n_inv"]
+    assert [o.const(r, i, 1) for r, i in sel] == rec["tables"]["mred"]
+    for level in range(1, len(Q)):
+        a = np.stack([synth.uniform_mod(10 + i, N, Q[i]) for i in range(level + 1)])
+        assert common.sha(o.div_round_last(a)) == rec["div_round"][str(level)], level
+    for level in range(len(Q)):
+        aQ = np.stack([synth.uniform_mod(20 + i, N, Q[i]) for i in range(level + 1)])
+        aP = np.stack([synth.uniform_mod(30 + i, N, P[i]) for i in range(len(P))])
+        assert common.sha(o.moddown(aQ, aP)) == rec["moddown"][str(level)], level
+    swk = np.stack([np.stack([synth.uniform_limbs(7000 + 10 * d + k, Q + P, N) for k in range(2)])
+                    for d in range(o.beta_full)])
+    for level in range(len(Q)):
+        c1 = synth.uniform_limbs(41 + level, Q[:level + 1], N)
+        d0, d1 = o.keyswitch(c1, swk)
+        assert [common.sha(d0), common.sha(d1)] == rec["keyswitch"][str(level)], level
+
+
+def oracle_conv(rec, bias):
+    Q, P = mods(rec)
+    o = Oracle(rec["logN"], Q, P)
+    w = synth.conv_workload(Q, P, rec["logN"], rec["B"], rec["seed"])
+    idx = o.monomial_pts()
+    assert common.sha(idx) == rec["monomials"]
+    return o.conv_then_pack(Ct(*w["ct"][0], rec["ct_scale"]), w["pt_ker"], rec["pt_scale"], rec["norm"], rec["out_scale"],
+                            idx, w["keys"], w["bias"] if bias else None)[0]
+
+
+@pytest.mark.parametrize("name", sorted(REF["conv"]))
+def test_conv_then_pack_matches_reference_main_code(name):
+    """main.conv_then_pack (conv.go:522-546, incl. pack_ctxts conv.go:266-300) and the bias Add (eval.go:258),
+    interpreted from the reference binary at small N, == the oracle's orc_conv_then_pack, bit for bit"""
+    rec = REF["conv"][name]
+    if "panic" in rec:
+        assert rec["panic"] == "gopanic: LV or scale after conv then pack, inconsistent"
+        with pytest.raises(RuntimeError, match="LV or scale after conv then pack, inconsistent"):
+            oracle_conv(rec, False)
+        return
+    for key, bias in (("nobias", False), ("bias", True)):
+        r = oracle_conv(rec, bias)
+        assert (common.sha(r.c0), common.sha(r.c1), r.scale, r.level) == \
+            (rec[key]["c0"], rec[key]["c1"], rec[key]["scale"], rec[key]["level"]), (name, key)
+
+
+FULL = sorted(REF.get("conv_full", {}))
+
+
+@pytest.mark.parametrize("name", FULL)
+def test_full_size_golden_fixture_is_the_reference_codes_output(name):
+    """N = 2^16: the digests in tests/golden/conv_golden.json (what the GPU parity tests compare libhec with)
+    are the ones the reference's own main.conv_then_pack + Add produced on the same operands"""
+    rec = REF["conv_full"][name]
+    assert rec["logN"] == PR.LOGN
+    assert (rec["bias"]["c0"], rec["bias"]["c1"]) == (GOLD["conv"][name]["c0"], GOLD["conv"][name]["c1"])
+    assert rec["monomials"] == GOLD["monomials"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", FULL)
+def test_gpu_conv_matches_reference_main_code_at_full_size(name):
+    """libhec (fused plan and op-level replay) == digests produced by the reference's compiled conv_then_pack"""
+    from optimal_conv_b200 import hec
+    rec = REF["conv_full"][name]
+    Q, P = mods(rec)
+    c = hec.Context(PR.LOGN, Q, P)
+    try:
+        w = synth.conv_workload(Q, P, PR.LOGN, rec["B"], rec["seed"])
+        idx = Oracle(PR.LOGN, Q, P).monomial_pts()
+        G = common.GpuConv(c, w, idx, rec["norm"])
+        for flags in (hec.CONV_FUSED, hec.CONV_OPLEVEL):
+            for key, bias in (("nobias", None), ("bias", G.bias)):
+                res = c.conv_then_pack(G.cts[0], G.ker, rec["norm"], rec["out_scale"], G.idx, bias, flags)
+                g0, g1 = res.download()
+                assert (common.sha(g0), common.sha(g1), res.scale, res.level) == \
+                    (rec[key]["c0"], rec[key]["c1"], rec[key]["scale"], rec[key]["level"]), (name, key, flags)
+    finally:
+        c.close()

@@ -136,6 +136,67 @@ def conv_case(logN, B, norm, seed, out_scale, Q2, P1, bias=True, ct_scale=PR.SCA
     return rec
 
 
+# ---------------------------------------------------------------- evaluator ops of the baseline path
+EVALOP_CASES = [
+    # name, logN, Q, P, level, rotations
+    ("set7_bl_level1", 8, PR.Q_SET7[:2], PR.P_PACK_BL, 1, [1, 17, 100, 127]),      # evalConv_BN_BL_test shape (alpha = 2)
+    ("set6_level2_a1", 9, PR.Q_SET6[:3], PR.P_ALL[:1], 2, [3, 255]),
+    ("set6_level4_a2", 8, PR.Q_SET6[:5], PR.P_ALL[:2], 4, [5]),
+]
+
+
+def evalop_keys(Q, P, N, gals):
+    beta_full = (len(Q) + len(P) - 1) // len(P)
+    return {g: np.stack([np.stack([synth.uniform_limbs(9000 + 131 * n + 10 * d + k, list(Q) + list(P), N) for k in range(2)])
+                         for d in range(beta_full)]) for n, g in enumerate(gals)}
+
+
+def digest_ct(m, ct):
+    polys, sc = m.read_ct(ct)
+    return {"c0": common.sha(np.array(polys[0], dtype=np.uint64)), "c1": common.sha(np.array(polys[1], dtype=np.uint64)),
+            "scale": sc, "level": len(polys[0]) - 1}
+
+
+def evalop_case(logN, Q, P, level, rots):
+    """RotateHoisted / RotateNew / MulNew / Add / Sub / Rescale as the baseline path uses them
+    (conv.go:133,168-171; eval.go:123,130), run by the reference's ckks.evaluator"""
+    N = 1 << logN
+    m = Machine()
+    gals = [pow(5, r, 2 * N) for r in rots]
+    keys = evalop_keys(Q, P, N, gals)
+    params, ev = m.new_evaluator(logN, Q, P, PR.SCALE, keys)
+    e = ev[1]
+    lim = lambda seed: [ints(l) for l in synth.uniform_limbs(seed, Q[:level + 1], N)]  # noqa: E731
+    ct = m.new_ct([lim(61), lim(62)], PR.SCALE)
+    ct2 = m.new_ct([lim(63), lim(64)], PR.SCALE)
+    pt = m.new_pt(lim(65), PR.SCALE)
+    rec = {"logN": logN, "Q": ["%x" % q for q in Q], "P": ["%x" % p for p in P], "level": level, "rotations": rots,
+           "galois": gals, "hoisted": {}, "rotate_new": {}}
+    h = m.call(CKKS + "(*evaluator).RotateHoisted", [e, ct] + m.slice_u64(rots) + [0])[-1]
+    for r in rots:
+        rec["hoisted"][str(r)] = digest_ct(m, m.rq(m.maps[h][r]))
+    for r in rots[:2]:
+        rec["rotate_new"][str(r)] = digest_ct(m, m.call(CKKS + "(*evaluator).RotateNew", [e, ct, r, 0])[-1])
+    ict, ipt = m.sym[OPERAND_CT][0], m.sym[OPERAND_PT][0]
+    prod = m.call(CKKS + "(*evaluator).MulNew", [e, ict, ct, ipt, pt, 0])[-1]
+    rec["mul_pt"] = digest_ct(m, prod)
+    rec["add"] = digest_ct(m, m.call(CKKS + "(*evaluator).AddNew", [e, ict, ct, ict, ct2, 0])[-1])
+    rec["sub"] = digest_ct(m, m.call(CKKS + "(*evaluator).SubNew", [e, ict, ct, ict, ct2, 0])[-1])
+    # Add(ct, pt, ct) at equal scales (eval.go:130,258 guard equality before adding)
+    sum_ct = m.new_ct([lim(61), lim(62)], PR.SCALE)
+    m.call(CKKS + "(*evaluator).Add", [e, ict, sum_ct, ipt, pt, sum_ct])
+    rec["add_pt"] = digest_ct(m, sum_ct)
+    # Rescale: a product whose scale is SCALE * q_level drops one level (L:ckks/evaluator.go:1291-1325)
+    big = m.new_ct([lim(61), lim(62)], PR.SCALE * float(Q[level]))
+    out = m.new_ct([lim(66), lim(67)], 1.0)
+    res = m.call(CKKS + "(*evaluator).Rescale", [e, big, f2b(PR.SCALE), out, 0, 0])
+    rec["rescale_err"] = bool(res[-2] or res[-1])
+    rec["rescale"] = digest_ct(m, out)
+    rec["interpreted_instructions"] = m.steps
+    print("evaluator-op case logN=%d level=%d: %d instructions" % (logN, level, m.steps), flush=True)
+    return rec
+
+
 SMALL_CONV = [
     # name, logN, B, norm, seed, out_scale, Q, P
     ("n8_B4", 8, 4, 1, 3, PR.SCALE, PR.Q_SET6[:2], PR.P_PACK),
@@ -163,7 +224,10 @@ def main():
         for name, logN, B, norm, seed, out_scale, Q2, P1 in SMALL_CONV:
             if name in sys.argv:
                 data["conv"][name] = conv_case(logN, B, norm, seed, out_scale, Q2, P1)
+    elif "--evalops" in sys.argv:
+        data["evalops"] = {name: evalop_case(logN, Q, P, level, rots) for name, logN, Q, P, level, rots in EVALOP_CASES}
     else:
+        data["evalops"] = {name: evalop_case(logN, Q, P, level, rots) for name, logN, Q, P, level, rots in EVALOP_CASES}
         data["ring"] = ring_cases()
         data["conv"] = {}
         for name, logN, B, norm, seed, out_scale, Q2, P1 in SMALL_CONV:

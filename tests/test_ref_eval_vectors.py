@@ -78,6 +78,37 @@ def test_conv_then_pack_matches_reference_main_code(name):
             (rec[key]["c0"], rec[key]["c1"], rec[key]["scale"], rec[key]["level"]), (name, key)
 
 
+def dg(ct):
+    return {"c0": common.sha(ct.c0), "c1": common.sha(ct.c1), "scale": ct.scale, "level": ct.level}
+
+
+@pytest.mark.parametrize("name", sorted(REF["evalops"]))
+def test_baseline_path_evaluator_ops_match_reference_code(name):
+    """ckks.evaluator RotateHoisted / RotateNew / MulNew / AddNew / SubNew / Add(ct, pt) / Rescale (interpreted),
+    the ops of preConv_BL / postConv_BL / evalConv_BN_BL_test (conv.go:133,168-171; eval.go:123,130),
+    incl. the alpha = 2 level-1 shape of the baseline convolution == the oracle"""
+    rec = REF["evalops"][name]
+    Q, P = mods(rec)
+    N, level = 1 << rec["logN"], rec["level"]
+    o = Oracle(rec["logN"], Q, P)
+    lim = lambda seed: synth.uniform_limbs(seed, Q[:level + 1], N)  # noqa: E731
+    ct, ct2, pt = Ct(lim(61), lim(62), PR.SCALE), Ct(lim(63), lim(64), PR.SCALE), lim(65)
+    assert [o.galois_for_rotation(r) for r in rec["rotations"]] == rec["galois"]
+    keys = {g: np.stack([np.stack([synth.uniform_limbs(9000 + 131 * n + 10 * d + k, Q + P, N) for k in range(2)])
+                         for d in range(o.beta_full)]) for n, g in enumerate(rec["galois"])}
+    for r, g in zip(rec["rotations"], rec["galois"]):
+        mine = dg(o.rotate(ct, r, keys[g]))
+        assert mine == rec["hoisted"][str(r)], ("hoisted", r)
+        if str(r) in rec["rotate_new"]:
+            assert mine == rec["rotate_new"][str(r)], ("rotate_new", r)
+    assert dg(o.mul_pt(ct, pt, PR.SCALE)) == rec["mul_pt"]
+    assert dg(o.add(ct, ct2)) == rec["add"]
+    assert dg(o.sub(ct, ct2)) == rec["sub"]
+    assert dg(o.add_pt(ct, pt)) == rec["add_pt"]
+    assert rec["rescale_err"] is False
+    assert dg(o.rescale(Ct(ct.c0, ct.c1, PR.SCALE * float(Q[level])), PR.SCALE)) == rec["rescale"]
+
+
 FULL = sorted(REF.get("conv_full", {}))
 
 

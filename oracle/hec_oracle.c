@@ -2,8 +2,9 @@
  * hec_oracle.c -- CPU oracle (TEST INFRASTRUCTURE ONLY; see hec_oracle.h).
  *
  * Scalar, single-threaded restatement of the Lattigo-fork arithmetic that the
- * reference's conv path executes.  PARITY UNPINNED against
- * real Lattigo output (no Go toolchain / no golden vectors in the reference).
+ * reference's conv path executes.  Pinned against outputs of
+ * the reference's own compiled routines, interpreted from the disassembly of its
+ * prebuilt binary (hec_oracle.h; tests/test_ref_vectors.py, test_ref_eval_vectors.py).
  * OpenMP is used only in orc_conv_then_pack when nthreads > 1 (the "generous"
  * all-cores CPU figure); nthreads == 1 is the reference-faithful single thread.
  */

@@ -6,15 +6,26 @@
  * and bench.py's cpu_baseline / --impl reference legs use it, as the checker /
  * the reported CPU baseline.
  *
- * PARITY UNPINNED: the reference (dwkim606/optimal_conv) keeps all of its
- * arithmetic in the un-vendored Go module github.com/dwkim606/test_lattigo
- * (v0.0.0-20220812213541-eb33b0555aaa, pinned only by the build info of the
- * prebuilt /root/reference/test_run).  No Go toolchain exists in the build image
- * and the reference holds no ciphertext-level golden vectors, so
- * this file is a restatement of the published Lattigo v2.2/2.3 algorithms as
- * recovered in SURVEY.md Appendix B.  It is pinned by algebraic self-tests,
- * a semantic encrypt -> conv -> decrypt test against a float convolution, and
- * golden hashes generated by itself (tests/golden/).
+ * PARITY: PINNED BY OUTPUTS OF THE REFERENCE'S OWN COMPILED CODE.  The reference
+ * (dwkim606/optimal_conv) keeps its arithmetic in the un-vendored Go module
+ * github.com/dwkim606/test_lattigo (v0.0.0-20220812213541-eb33b0555aaa, pinned only by
+ * the build info of the prebuilt /root/reference/test_run); no Go toolchain exists in
+ * the build image and the reference holds no ciphertext-level golden vectors
+ * (SURVEY.md 8c).  This file therefore restates the Lattigo v2.2/2.3 algorithms as
+ * recovered in SURVEY.md Appendix B -- and is pinned against the reference itself:
+ * tests/golden/{x86emu,refmachine}.py interpret the compiled routines of test_run from
+ * their disassembly (the binary is never executed) on seeded inputs, and the oracle must
+ * reproduce every output bit for bit (tests/test_ref_vectors.py,
+ * tests/test_ref_eval_vectors.py):
+ *   ring   primitiveRoot (35 moduli), NewRing tables, NTT/InvNTT(+Lazy), PermuteNTTIndex,
+ *          reconstructRNS+multSum, divRoundByLastModulusNTT, ModDownSplitNTTPQ
+ *   rlwe   NewKeySwitcher, SwitchKeysInPlace (alpha = 1, 2, 5; every level)
+ *   ckks   NewEvaluator, MulNew, Add/Sub, Add(ct,pt), Rescale, RotateNew, RotateHoisted
+ *   main   conv_then_pack (+ pack_ctxts, + the bias Add of evalConv_BN), incl. its panic
+ * Go-runtime services the interpreted code calls (allocation, maps, math/big, prime
+ * factorisation of q-1) are supplied in Python and listed in refmachine.py.  In addition:
+ * algebraic self-tests, a semantic encrypt -> conv -> decrypt test against a float
+ * convolution, and an independent big-integer model.
  *
  * Citation convention: "L:pkg/file.go:a-b" = the Lattigo fork's source location
  * (SURVEY.md citation convention); "conv.go:N" = /root/reference/conv.go.

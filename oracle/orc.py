@@ -1,7 +1,7 @@
 """ctypes wrapper around oracle/liborc.so -- TEST INFRASTRUCTURE ONLY.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
-legs may import this module.  PARITY UNPINNED (see hec_oracle.h).
+legs may import this module.  Parity: pinned by outputs of the reference's own compiled code (see hec_oracle.h).
 """
 import ctypes as C
 import os

@@ -1,8 +1,8 @@
-"""Generates tests/golden/*.json from the CPU oracle (run from the repo root:
-`python tests/golden/make_golden.py`).  The reference holds no ciphertext-level vectors
-(parity unpinned), so these are the repo's own known answers: SHA-256 of
-oracle outputs on seeded inputs.  If Go + the Lattigo fork ever become available they
-should be regenerated from real Lattigo output."""
+"""Generates tests/golden/conv_golden.json from the CPU oracle (run from the repo root:
+`python tests/golden/make_golden.py`): SHA-256 of oracle outputs on seeded inputs at N = 2^16.
+The oracle itself is pinned against the reference's compiled code (make_ref_vectors.py,
+make_ref_eval_vectors.py); the B4_norm1 entry here is additionally checked to equal the digest the
+reference's own main.conv_then_pack produced at N = 2^16 (tests/test_ref_eval_vectors.py)."""
 import json
 import os
 import sys

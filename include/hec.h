@@ -99,6 +99,14 @@ int hec_add_new(hec_ctx *ctx, const hec_ct *a, const hec_ct *b, hec_ct **out);
 int hec_sub_new(hec_ctx *ctx, const hec_ct *a, const hec_ct *b, hec_ct **out);
 /* Add(ct, pt, ct)  (eval.go:258) */
 int hec_add_pt(hec_ctx *ctx, hec_ct *ct, const hec_pt *pt);
+/* ---- ct x ct (the multiply of evalReLU's polynomial evaluation, conv.go:435-480)
+ * hec_rlk_upload: rlwe.RelinearizationKey{Keys[0]} = one SwitchingKey, same layout as hec_swk_upload
+ *   (replaces the Rlk field of rlwe.EvaluationKey passed to ckks.NewEvaluator, main.go:430).
+ * hec_mul_relin_new: MulRelinNew(a, b) (mulRelin ciphertext branch, L:ckks/evaluator.go:1398-1444);
+ *   a == b is the squaring case.  Error HEC_E_NOKEY without a relinearisation key. */
+#define HEC_RLK_ID 0ull /* key-table id of the relinearisation key (never a Galois element: those are odd) */
+int hec_rlk_upload(hec_ctx *ctx, int max_level, const uint64_t *const *limbs);
+int hec_mul_relin_new(hec_ctx *ctx, const hec_ct *a, const hec_ct *b, hec_ct **out);
 /* RotateGal(ct, galEl, out)  (conv.go:291); out may alias ct */
 int hec_rotate_gal(hec_ctx *ctx, const hec_ct *ct, uint64_t galEl, hec_ct *out);
 /* RotateNew(ct, k)  (eval.go:123) */

@@ -769,6 +769,47 @@ int hec_rotate_many(hec_ctx *c, const std::vector<const hec_ct *> &ct, const std
     return finish_rotations(c, level, ct, galEl, d0, d1, out);
 }
 
+// MulRelinNew(ct, ct) (mulRelin ciphertext branch, L:ckks/evaluator.go:1398-1444): tensor product, then
+// (c0, c1) += SwitchKeys(c2, rlk).  The relinearisation key is stored under the reserved id HEC_RLK_ID.
+extern "C" int hec_rlk_upload(hec_ctx *c, int max_level, const uint64_t *const *limbs) {
+    return hec_swk_upload(c, HEC_RLK_ID, max_level, limbs);
+}
+extern "C" int hec_mul_relin_new(hec_ctx *c, const hec_ct *a, const hec_ct *b, hec_ct **out) {
+    if (!c || !a || !b || !out) return HEC_E_INVAL;
+    cudaSetDevice(c->device);
+    auto it = c->keys.find(HEC_RLK_ID);
+    if (it == c->keys.end()) return c->fail(HEC_E_NOKEY, "relinearisation key missing");
+    int level = std::min(a->level, b->level), L = level + 1, rc;
+    hec_ct *o = nullptr;
+    if ((rc = hec_ct_alloc(c, level, a->scale * b->scale, &o))) return rc;
+    auto bail = [&](int e) { hec_ct_free(c, o); return e; };
+    if ((rc = reserve(c, decomp_limbs(c, level) + ks_limbs(c, level) + 3 * (size_t)L))) return bail(rc);
+    u64 *c2 = c->scratch(L), *d0 = c->scratch(L), *d1 = c->scratch(L);
+    for (int off = 0; off < L; off += HEC_TNJOBS) {
+        int n = std::min(HEC_TNJOBS, L - off);
+        TensorJobs J;
+        for (int k = 0; k < n; k++) {
+            int i = off + k;
+            J.j[k] = {a->limb(0, i), a->limb(1, i), b->limb(0, i), b->limb(1, i), o->limb(0, i), o->limb(1, i),
+                      c2 + (size_t)i * HEC_N, mform(c->hm[i].rmod, c->q(i)), i};
+        }
+        k_tensor<<<dim3(32, n), 256, 0, c->stream>>>(J, c->dmods);
+        c->launches += 1;
+    }
+    if ((rc = check_launch(c, "tensor"))) return bail(rc);
+    std::vector<Decomp> dc;
+    if ((rc = decompose_many(c, level, {c2}, dc))) return bail(rc);
+    if ((rc = keyswitch_many(c, level, dc, {&it->second}, {d0}, {d1}))) return bail(rc);
+    std::vector<EwJob> add;
+    for (int i = 0; i < L; i++) {
+        add.push_back(ewjob(o->limb(0, i), d0 + (size_t)i * HEC_N, o->limb(0, i), i));
+        add.push_back(ewjob(o->limb(1, i), d1 + (size_t)i * HEC_N, o->limb(1, i), i));
+    }
+    if ((rc = launch_ew<EW_ADD>(c, add))) return bail(rc);
+    *out = o;
+    return HEC_OK;
+}
+
 extern "C" int hec_rotate_gal(hec_ctx *c, const hec_ct *ct, uint64_t galEl, hec_ct *out) {
     if (!c || !ct || !out) return HEC_E_INVAL;
     cudaSetDevice(c->device);

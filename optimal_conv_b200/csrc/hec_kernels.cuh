@@ -106,6 +106,24 @@ __global__ void __launch_bounds__(256) k_ew(EwJobs J, const ModC *__restrict__ m
     }
 }
 
+// ---- ct x ct tensor product (mulRelin, ciphertext branch, L:ckks/evaluator.go:1398-1432):
+// c0 = a0 b0, c1 = a0 b1 + a1 b0, c2 = a1 b1 on canonical NTT-domain residues; MFormLvl(a) then
+// MulCoeffsMontgomery(.., b) is the plain modular product.  4 limbs read, 3 written, one pass.
+#define HEC_TNJOBS 32
+struct TensorJob { const u64 *a0, *a1, *b0, *b1; u64 *c0, *c1, *c2; u64 r2; int mod; };
+struct TensorJobs { TensorJob j[HEC_TNJOBS]; };
+__global__ void __launch_bounds__(256) k_tensor(TensorJobs J, const ModC *__restrict__ mods) {
+    const TensorJob job = J.j[blockIdx.y];
+    const u64 q = mods[job.mod].q, qinv = mods[job.mod].qinv;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < HEC_N; i += gridDim.x * blockDim.x) {
+        const u64 A0 = mred(job.a0[i], job.r2, q, qinv), A1 = mred(job.a1[i], job.r2, q, qinv);
+        const u64 b0 = job.b0[i], b1 = job.b1[i];
+        job.c0[i] = mred(A0, b0, q, qinv);
+        job.c1[i] = addmod(mred(A0, b1, q, qinv), mred(A1, b0, q, qinv), q);
+        job.c2[i] = mred(A1, b1, q, qinv);
+    }
+}
+
 // ---- sum over taps: out = sum_t a_t * b_t * R^-1 (b != null: a chain of MulNew + Add, conv.go:168-171)
 // or out = sum_t a_t (b == null: a chain of Add, eval.go:123).  Pointer lists live in device memory.
 struct DotJob { const u64 *const *a; const u64 *const *b; u64 *out; int mod; int T; };

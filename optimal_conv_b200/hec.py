@@ -25,7 +25,7 @@ SYMBOLS = [
     "hec_timer_stop_ms", "hec_launch_count", "hec_host_register", "hec_host_unregister", "hec_pt_upload", "hec_pt_free", "hec_ct_upload", "hec_ct_download",
     "hec_ct_copy_new", "hec_ct_level", "hec_ct_scale", "hec_ct_set_scale", "hec_ct_free", "hec_swk_upload",
     "hec_swk_drop", "hec_mul_pt_new", "hec_mult_by_const", "hec_rescale", "hec_set_scale", "hec_add", "hec_add_new",
-    "hec_sub_new", "hec_add_pt", "hec_rotate_gal", "hec_rotate_new", "hec_rotate_hoisted", "hec_galois_for_rotation",
+    "hec_sub_new", "hec_add_pt", "hec_rlk_upload", "hec_mul_relin_new", "hec_rotate_gal", "hec_rotate_new", "hec_rotate_hoisted", "hec_galois_for_rotation",
     "hec_ntt", "hec_keyswitch", "hec_moddown", "hec_conv_then_pack", "hec_conv_bl", "hec_ext_ctxt", "hec_keep_ctxt", "hec_plan_create", "hec_plan_run",
     "hec_plan_run_host", "hec_plan_submit_host", "hec_plan_wait", "hec_plan_span_begin", "hec_plan_span_end_ms",
     "hec_plan_profile", "hec_plan_destroy",
@@ -94,6 +94,8 @@ def lib():
     L.hec_add_new.argtypes = [vp, vp, vp, C.POINTER(vp)]
     L.hec_sub_new.argtypes = [vp, vp, vp, C.POINTER(vp)]
     L.hec_add_pt.argtypes = [vp, vp, vp]
+    L.hec_rlk_upload.argtypes = [vp, C.c_int, u64pp]
+    L.hec_mul_relin_new.argtypes = [vp, vp, vp, C.POINTER(vp)]
     L.hec_rotate_gal.argtypes = [vp, vp, C.c_uint64, vp]
     L.hec_rotate_new.argtypes = [vp, vp, C.c_int, C.POINTER(vp)]
     L.hec_rotate_hoisted.argtypes = [vp, vp, C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
@@ -242,7 +244,17 @@ class Context:
         flat = swk.reshape(-1, self.N)
         self._chk(self.L.hec_swk_upload(self.h, galEl, max_level, _rows(flat)))
 
+    def upload_rlk(self, rlk, max_level):
+        """rlk: RelinearizationKey.Keys[0], [digits][2][nQ+nP][N] as Lattigo stores it."""
+        flat = np.ascontiguousarray(rlk, dtype=np.uint64).reshape(-1, self.N)
+        self._chk(self.L.hec_rlk_upload(self.h, max_level, _rows(flat)))
+
     # ---- evaluator ops (ckks.Evaluator subset) ----
+    def MulRelinNew(self, a, b):
+        h = vp()
+        self._chk(self.L.hec_mul_relin_new(self.h, a.h, b.h, C.byref(h)))
+        return Ciphertext(self, h)
+
     def MulNew(self, ct, pt):
         h = vp()
         self._chk(self.L.hec_mul_pt_new(self.h, ct.h, pt.h, C.byref(h)))

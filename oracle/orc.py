@@ -196,6 +196,22 @@ class Oracle:
         self.L.orc_sub(self.h, lv, _p(x1), _p(y1), _p(o1))
         return Ct(o0, o1, a.scale)
 
+    def mul_relin(self, a, b, rlk):
+        """MulRelinNew(ct, ct) (mulRelin ct branch, L:ckks/evaluator.go:1398-1432): c0 = a0 b0,
+        c1 = a0 b1 + a1 b0, c2 = a1 b1, then (c0, c1) += SwitchKeys(c2, rlk).  Composition of the
+        pinned routines above (MForm + MulCoeffsMontgomery = canonical product)."""
+        lv = min(a.level, b.level)
+        a = Ct(a.c0[:lv + 1], a.c1[:lv + 1], a.scale)
+        x = self.mul_pt(a, b.c0[:lv + 1])            # a0 b0, a1 b0
+        y = self.mul_pt(a, b.c1[:lv + 1])            # a0 b1, a1 b1
+        c1 = np.empty_like(x.c0)
+        self.L.orc_add(self.h, lv, _p(y.c0), _p(x.c1), _p(c1))
+        d0, d1 = self.keyswitch(y.c1, rlk)
+        o0, o1 = np.empty_like(c1), np.empty_like(c1)
+        self.L.orc_add(self.h, lv, _p(x.c0), _p(d0), _p(o0))
+        self.L.orc_add(self.h, lv, _p(c1), _p(d1), _p(o1))
+        return Ct(o0, o1, a.scale * b.scale)
+
     def add_pt(self, ct, pt):
         lv = min(ct.level, pt.shape[0] - 1)
         x0, p = np.ascontiguousarray(ct.c0[:lv + 1]), np.ascontiguousarray(pt[:lv + 1])

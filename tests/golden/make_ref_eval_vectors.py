@@ -164,7 +164,9 @@ def evalop_case(logN, Q, P, level, rots):
     m = Machine()
     gals = [pow(5, r, 2 * N) for r in rots]
     keys = evalop_keys(Q, P, N, gals)
-    params, ev = m.new_evaluator(logN, Q, P, PR.SCALE, keys)
+    beta_full = (len(Q) + len(P) - 1) // len(P)
+    rlk = np.stack([np.stack([synth.uniform_limbs(8000 + 10 * d + k, list(Q) + list(P), N) for k in range(2)]) for d in range(beta_full)])
+    params, ev = m.new_evaluator(logN, Q, P, PR.SCALE, keys, rlk)
     e = ev[1]
     lim = lambda seed: [ints(l) for l in synth.uniform_limbs(seed, Q[:level + 1], N)]  # noqa: E731
     ct = m.new_ct([lim(61), lim(62)], PR.SCALE)
@@ -182,6 +184,9 @@ def evalop_case(logN, Q, P, level, rots):
     rec["mul_pt"] = digest_ct(m, prod)
     rec["add"] = digest_ct(m, m.call(CKKS + "(*evaluator).AddNew", [e, ict, ct, ict, ct2, 0])[-1])
     rec["sub"] = digest_ct(m, m.call(CKKS + "(*evaluator).SubNew", [e, ict, ct, ict, ct2, 0])[-1])
+    # ct x ct: MulRelinNew (mulRelin ct branch: tensor product + relinearisation with rlk), and the squaring case
+    rec["mul_relin"] = digest_ct(m, m.call(CKKS + "(*evaluator).MulRelinNew", [e, ict, ct, ict, ct2, 0])[-1])
+    rec["square_relin"] = digest_ct(m, m.call(CKKS + "(*evaluator).MulRelinNew", [e, ict, ct, ict, ct, 0])[-1])
     # Add(ct, pt, ct) at equal scales (eval.go:130,258 guard equality before adding)
     sum_ct = m.new_ct([lim(61), lim(62)], PR.SCALE)
     m.call(CKKS + "(*evaluator).Add", [e, ict, sum_ct, ipt, pt, sum_ct])

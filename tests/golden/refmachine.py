@@ -359,9 +359,10 @@ class Machine(Emu):
         self.write_u64s(key, [val, beta, beta])
         return key
 
-    def new_evaluator(self, logN, Q, P, scale, keys):
-        """ckks.NewEvaluator(params, EvaluationKey{Rtks: keys}) run by the reference code itself.
-        keys: {galEl: array [beta][2][nQ+nP][N]}.  Returns (params words, Evaluator iface words)."""
+    def new_evaluator(self, logN, Q, P, scale, keys, rlk=None):
+        """ckks.NewEvaluator(params, EvaluationKey{Rlk: rlk, Rtks: keys}) run by the reference code itself.
+        keys: {galEl: array [beta][2][nQ+nP][N]}; rlk: one such array (RelinearizationKey{Keys []*SwitchingKey})
+        or None.  Returns (params words, Evaluator iface words)."""
         rQ, rP = self.new_ring(1 << logN, Q), self.new_ring(1 << logN, P)
         params = [logN] + self.slice_u64(Q) + self.slice_u64(P) + [f2b(3.2), rQ, rP, 0, logN - 1, f2b(scale)]
         kmap = self.new_map(8)
@@ -369,5 +370,9 @@ class Machine(Emu):
             self.map_put(kmap, gal, [self.new_swk(swk)])
         rtks = self.alloc(8)
         self.wq(rtks, kmap)
-        res = self.call(CKKS + "NewEvaluator", params + [0, rtks, 0, 0])
+        rlkp = 0
+        if rlk is not None:
+            rlkp = self.alloc(24)
+            self.write_u64s(rlkp, self.slice_u64([self.new_swk(rlk)]))
+        res = self.call(CKKS + "NewEvaluator", params + [rlkp, rtks, 0, 0])
         return params, res[-2:]

@@ -226,6 +226,37 @@ def test_keyswitch_three_digits_alpha2_level4():
         c.close()
 
 
+@pytest.mark.parametrize("shape", [("set6_level4_a2", PR.Q_SET6[:5], PR.P_PACK_BL), ("set6_level1_a1", PR.Q_SET6[:2], PR.P_PACK),
+                                   ("set7_level5_a5", PR.Q_SET7[:6], PR.P_ALL)], ids=lambda s: s[0])
+def test_mul_relin_ct_ct(shape):
+    """MulRelinNew(ct, ct) and the squaring case == the oracle's composition, which is itself
+    pinned against the reference's compiled mulRelin at small N (tests/test_ref_eval_vectors.py)."""
+    _, Q, P = shape
+    c, o = hec.Context(PR.LOGN, Q, P), Oracle(PR.LOGN, Q, P)
+    try:
+        level = len(Q) - 1
+        rlk = np.stack([np.stack([synth.uniform_limbs(8000 + 10 * d + k, Q + P, N) for k in range(2)]) for d in range(o.beta_full)])
+        a = [synth.uniform_limbs(61 + k, Q, N) for k in range(4)]
+        A, B = c.upload_ct(a[0], a[1], PR.SCALE), c.upload_ct(a[2], a[3], PR.SCALE)
+        with pytest.raises(hec.HecError) as e:
+            c.MulRelinNew(A, B)
+        assert e.value.code == hec.HEC_E_NOKEY
+        c.upload_rlk(rlk, level)
+        for X, Y, x, y in ((A, B, Ct(a[0], a[1], PR.SCALE), Ct(a[2], a[3], PR.SCALE)), (A, A, Ct(a[0], a[1], PR.SCALE), Ct(a[0], a[1], PR.SCALE))):
+            res = c.MulRelinNew(X, Y)
+            ref = o.mul_relin(x, y, rlk)
+            g0, g1 = res.download()
+            assert res.level == level and res.scale == ref.scale == PR.SCALE * PR.SCALE
+            assert np.array_equal(g0, ref.c0) and np.array_equal(g1, ref.c1)
+        # then Rescale as evalReLU does after every multiply
+        c.Rescale(res, PR.SCALE)
+        r2 = o.rescale(ref, PR.SCALE)
+        g0, g1 = res.download()
+        assert res.level == r2.level and np.array_equal(g0, r2.c0) and np.array_equal(g1, r2.c1)
+    finally:
+        c.close()
+
+
 # ---------------------------------------------------------------- the conv path
 @pytest.mark.parametrize("cfg", common.GOLDEN_CONFIGS, ids=lambda c: c["name"])
 @pytest.mark.parametrize("flags", [hec.CONV_FUSED, hec.CONV_OPLEVEL], ids=["fused", "oplevel"])

@@ -84,7 +84,7 @@ def dg(ct):
 
 @pytest.mark.parametrize("name", sorted(REF["evalops"]))
 def test_baseline_path_evaluator_ops_match_reference_code(name):
-    """ckks.evaluator RotateHoisted / RotateNew / MulNew / AddNew / SubNew / Add(ct, pt) / Rescale (interpreted),
+    """ckks.evaluator RotateHoisted / RotateNew / MulNew / MulRelinNew / AddNew / SubNew / Add(ct, pt) / Rescale (interpreted),
     the ops of preConv_BL / postConv_BL / evalConv_BN_BL_test (conv.go:133,168-171; eval.go:123,130),
     incl. the alpha = 2 level-1 shape of the baseline convolution == the oracle"""
     rec = REF["evalops"][name]
@@ -102,6 +102,9 @@ def test_baseline_path_evaluator_ops_match_reference_code(name):
         if str(r) in rec["rotate_new"]:
             assert mine == rec["rotate_new"][str(r)], ("rotate_new", r)
     assert dg(o.mul_pt(ct, pt, PR.SCALE)) == rec["mul_pt"]
+    rlk = np.stack([np.stack([synth.uniform_limbs(8000 + 10 * d + k, Q + P, N) for k in range(2)]) for d in range(o.beta_full)])
+    assert dg(o.mul_relin(ct, ct2, rlk)) == rec["mul_relin"]
+    assert dg(o.mul_relin(ct, ct, rlk)) == rec["square_relin"]
     assert dg(o.add(ct, ct2)) == rec["add"]
     assert dg(o.sub(ct, ct2)) == rec["sub"]
     assert dg(o.add_pt(ct, pt)) == rec["add_pt"]

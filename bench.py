@@ -178,7 +178,9 @@ def run_side_workload(args):
     --workload conv_bl    : one evalConv_BN_BL_test interval (eval.go:108-131), set 7, level 1, alpha = 2,
                             for --batch B (4,16,64,256) and --ker k (3,5,7): k^2-1 hoisted rotations +
                             B/2 x (k^2 MulNew/Add + RotateNew) + bias  (BASELINE.json config 3: the k sweep)
-    --workload keyswitch  : KeySwitcher.SwitchKeysInPlace at level 27, alpha = 5, beta = 6 (SURVEY.md 8d stress)"""
+    --workload keyswitch  : KeySwitcher.SwitchKeysInPlace at level 27, alpha = 5, beta = 6 (SURVEY.md 8d stress)
+    --workload mul_relin  : MulRelinNew(ct, ct) + Rescale at level 10, alpha = 5 (the multiply of
+                            evalReLU's polynomial evaluation, conv.go:435-480)"""
     import torch
     from optimal_conv_b200 import hec
     if not torch.cuda.is_available():
@@ -198,6 +200,29 @@ def run_side_workload(args):
         unit, name = "rotations/s", "RotateGal (key-switch + automorphism) at level 27, alpha=5, beta=6"
         # L (c1) + 2*beta*(L+alpha) (key) + 2L (out) + L (c0) limbs, SURVEY.md 8d
         alg = (28 + 2 * 6 * 33 + 2 * 28 + 28) * LIMB
+    elif args.workload == "mul_relin":
+        level = 10
+        Q, P = PR.Q_SET6[:level + 1], PR.P_ALL
+        ctx = hec.Context(PR.LOGN, Q, P)
+        beta = (level + 1 + len(P) - 1) // len(P)
+        rlk = np.stack([np.stack([synth.uniform_limbs(8000 + 10 * d + kk, Q + P, N) for kk in range(2)]) for d in range(beta)])
+        ctx.upload_rlk(rlk, level)
+        a = [synth.uniform_limbs(61 + t, Q, N) for t in range(4)]
+        A, Bc = ctx.upload_ct(a[0], a[1], PR.SCALE), ctx.upload_ct(a[2], a[3], PR.SCALE)
+
+        def step():
+            r = ctx.MulRelinNew(A, Bc)
+            ctx.Rescale(r, PR.SCALE)
+            r.free()
+        unit, name = "multiplications/s", "MulRelinNew(ct, ct) + Rescale at level %d, alpha=5, beta=%d" % (level, beta)
+        L_ = level + 1
+        alg = (4 * L_ + 2 * beta * (L_ + 5) + 2 * L_) * LIMB   # two cts in, relinearisation key, one ct out
+        if args.cpu_sample > 0:
+            from oracle.orc import Ct, Oracle
+            o = Oracle(PR.LOGN, Q, P)
+            t0 = time.perf_counter()
+            o.rescale(o.mul_relin(Ct(a[0], a[1], PR.SCALE), Ct(a[2], a[3], PR.SCALE), rlk), PR.SCALE)
+            cpu_s = time.perf_counter() - t0
     else:
         # one evalConv_BN_BL_test interval for the (B, w) row of main.go:578-579 and kernel width --ker
         Q, P = PR.Q_SET7[:2], PR.P_PACK_BL
@@ -245,7 +270,7 @@ def run_side_workload(args):
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "dtype": "u64",
             "data": "synthetic", "config": {"workload": args.workload, "path": "op-level generic kernels"},
             "gpu_launches": ctx.launch_count() - l0}
-    if args.workload == "conv_bl" and args.cpu_sample > 0:
+    if args.workload in ("conv_bl", "mul_relin") and args.cpu_sample > 0:
         line["cpu_baseline"] = {"value": 1.0 / cpu_s, "unit": unit, "cores": 1, "kind": "port",
                                 "sample": "1 call of the same workload, oracle port, 1 thread"}
     if alg:
@@ -264,7 +289,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="B: output channels packed per ciphertext")
     ap.add_argument("--ker", type=int, default=3, help="kernel width k (only changes the work of --workload conv_bl)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="conv", choices=["conv", "conv_bl", "keyswitch"],
+    ap.add_argument("--workload", default="conv", choices=["conv", "conv_bl", "keyswitch", "mul_relin"],
                     help="conv = the headline fused path; the others are op-level side measurements")
     ap.add_argument("--cpu-sample", type=int, default=12, help="convs timed for cpu_baseline (0 = skip)")
     ap.add_argument("--ring", type=int, default=8, help="distinct input batches rotated through (> L2)")

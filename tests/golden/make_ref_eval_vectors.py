@@ -197,6 +197,12 @@ def evalop_case(logN, Q, P, level, rots):
     res = m.call(CKKS + "(*evaluator).Rescale", [e, big, f2b(PR.SCALE), out, 0, 0])
     rec["rescale_err"] = bool(res[-2] or res[-1])
     rec["rescale"] = digest_ct(m, out)
+    if level >= 2:   # two divisions in one call: DivRoundByLastModulusManyNTT with nbRescales = 2
+        big2 = m.new_ct([lim(61), lim(62)], PR.SCALE * float(Q[level]) * float(Q[level - 1]))
+        out2 = m.new_ct([lim(66), lim(67)], 1.0)
+        res = m.call(CKKS + "(*evaluator).Rescale", [e, big2, f2b(PR.SCALE), out2, 0, 0])
+        assert not (res[-2] or res[-1])
+        rec["rescale2"] = digest_ct(m, out2)
     rec["interpreted_instructions"] = m.steps
     print("evaluator-op case logN=%d level=%d: %d instructions" % (logN, level, m.steps), flush=True)
     return rec

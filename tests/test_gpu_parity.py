@@ -143,6 +143,24 @@ def test_rescale_three_limbs_with_61bit_and_30bit_moduli():
         c.close()
 
 
+def test_rescale_two_divisions_in_one_call():
+    """scale = 2^30 q_4 q_3 at level 4: Rescale divides twice (DivRoundByLastModulusManyNTT, nbRescales = 2);
+    the oracle's result for this shape is pinned against the reference's compiled Rescale (test_ref_eval_vectors)."""
+    Q = PR.Q_SET6[:5]
+    c, o = hec.Context(PR.LOGN, Q, P1), Oracle(PR.LOGN, Q, P1)
+    try:
+        a0, a1 = synth.uniform_limbs(23, Q, N), synth.uniform_limbs(24, Q, N)
+        s = PR.SCALE * float(Q[4]) * float(Q[3])
+        A = c.upload_ct(a0, a1, s)
+        c.Rescale(A, PR.SCALE)
+        r = o.rescale(Ct(a0, a1, s), PR.SCALE)
+        g0, g1 = A.download()
+        assert A.level == r.level == 2 and A.scale == r.scale
+        assert np.array_equal(g0, r.c0) and np.array_equal(g1, r.c1)
+    finally:
+        c.close()
+
+
 # ---------------------------------------------------------------- key switching
 def test_moddown_float_edge(ctx, orc):
     """v = floor(float64(y)/float64(P)) rounds up to 1 for y in [P-129, P-1]."""

@@ -110,6 +110,9 @@ def test_baseline_path_evaluator_ops_match_reference_code(name):
     assert dg(o.add_pt(ct, pt)) == rec["add_pt"]
     assert rec["rescale_err"] is False
     assert dg(o.rescale(Ct(ct.c0, ct.c1, PR.SCALE * float(Q[level])), PR.SCALE)) == rec["rescale"]
+    if "rescale2" in rec:  # two divisions by one Rescale call (DivRoundByLastModulusManyNTT, nbRescales = 2)
+        r2 = o.rescale(Ct(ct.c0, ct.c1, PR.SCALE * float(Q[level]) * float(Q[level - 1])), PR.SCALE)
+        assert r2.level == level - 2 and dg(r2) == rec["rescale2"]
 
 
 FULL = sorted(REF.get("conv_full", {}))

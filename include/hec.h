@@ -107,6 +107,22 @@ int hec_add_pt(hec_ctx *ctx, hec_ct *ct, const hec_pt *pt);
 #define HEC_RLK_ID 0ull /* key-table id of the relinearisation key (never a Galois element: those are odd) */
 int hec_rlk_upload(hec_ctx *ctx, int max_level, const uint64_t *const *limbs);
 int hec_mul_relin_new(hec_ctx *ctx, const hec_ct *a, const hec_ct *b, hec_ct **out);
+/* ---- polynomial evaluation: evalReLU (conv.go:435-480) and the evaluator ops it is made of
+ * hec_sub: Sub(a, b, out).  hec_add / hec_sub / *_new follow evaluateInPlace (L:ckks/evaluator.go:365-473):
+ *   level = min, scale = max, and when the scales differ by a factor whose floor is > 1 the smaller-scale
+ *   operand is first multiplied by that integer.
+ * hec_drop_level: DropLevel(ct, levels).  hec_add_const: AddConst(ct, c, ct), real c.
+ * hec_mult_by_int_and_add: MultByGaussianIntegerAndAdd(ct, c, 0, out).
+ * hec_evaluate_poly: EvaluatePoly(ct, NewPoly(coeffs), target_scale) (L:ckks/polynomial_evaluation.go), real
+ *   coefficients, index = degree; eval_scale = params.Scale() (the evaluator's rescale threshold).
+ * hec_eval_relu: evalReLU(params, evaluator, ct, alpha); needs the relinearisation key and 11 levels. */
+int hec_sub(hec_ctx *ctx, const hec_ct *a, const hec_ct *b, hec_ct *out);
+int hec_drop_level(hec_ctx *ctx, hec_ct *ct, int levels);
+int hec_add_const(hec_ctx *ctx, hec_ct *ct, double c);
+int hec_mult_by_int_and_add(hec_ctx *ctx, const hec_ct *ct, int64_t c, hec_ct *out);
+int hec_evaluate_poly(hec_ctx *ctx, const hec_ct *ct, const double *coeffs, int n, double target_scale,
+                      double eval_scale, hec_ct **out);
+int hec_eval_relu(hec_ctx *ctx, const hec_ct *ct, double alpha, double eval_scale, hec_ct **out);
 /* RotateGal(ct, galEl, out)  (conv.go:291); out may alias ct */
 int hec_rotate_gal(hec_ctx *ctx, const hec_ct *ct, uint64_t galEl, hec_ct *out);
 /* RotateNew(ct, k)  (eval.go:123) */

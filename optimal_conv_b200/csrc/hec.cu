@@ -569,22 +569,54 @@ extern "C" int hec_set_scale(hec_ctx *c, hec_ct *ct, double scale) {
     return HEC_OK;
 }
 
+// Add / Sub (evaluateInPlace, L:ckks/evaluator.go:365-473): level = min, scale = max; when the scales differ
+// by a factor whose floor is > 1 the smaller-scale operand is first multiplied by that integer (MultByConst),
+// in place when it is also the receiver, else into scratch.
 template <int OP>
 static int addsub(hec_ctx *c, const hec_ct *a, const hec_ct *b, hec_ct *out) {
-    int level = std::min(std::min(a->level, b->level), out->alloc - 1);
+    int level = std::min(std::min(a->level, b->level), out->alloc - 1), L = level + 1, rc;
+    const hec_ct *lo = nullptr; // the operand to scale up
+    double factor = 1.0;
+    if (a->scale > b->scale && floor(a->scale / b->scale) > 1) { lo = b; factor = floor(a->scale / b->scale); }
+    else if (b->scale > a->scale && floor(b->scale / a->scale) > 1) { lo = a; factor = floor(b->scale / a->scale); }
+    std::vector<const u64 *> xa(2 * L), xb(2 * L);
+    for (int p = 0; p < 2; p++)
+        for (int i = 0; i < L; i++) { xa[p * L + i] = a->limb(p, i); xb[p * L + i] = b->limb(p, i); }
+    if (lo) {
+        std::vector<u64> k;
+        hec_const_limbs(c, level, factor, k);
+        u64 *tmp = nullptr;
+        if (lo != out) {
+            if ((rc = reserve(c, 2 * (size_t)L))) return rc;
+            tmp = c->scratch(2 * (size_t)L);
+        }
+        std::vector<EwJob> mj;
+        std::vector<const u64 *> &x = lo == a ? xa : xb;
+        for (int p = 0; p < 2; p++)
+            for (int i = 0; i < L; i++) {
+                u64 *d = tmp ? tmp + (size_t)(p * L + i) * HEC_N : out->limb(p, i);
+                mj.push_back(ewjob(lo->limb(p, i), nullptr, d, i, mform(k[i], c->q(i))));
+                x[p * L + i] = d;
+            }
+        if ((rc = launch_ew<EW_MULSCALAR>(c, mj))) return rc;
+    }
     std::vector<EwJob> jobs;
     for (int p = 0; p < 2; p++)
-        for (int i = 0; i <= level; i++) jobs.push_back(ewjob(a->limb(p, i), b->limb(p, i), out->limb(p, i), i));
-    int rc = launch_ew<OP>(c, jobs);
-    if (rc) return rc;
+        for (int i = 0; i < L; i++) jobs.push_back(ewjob(xa[p * L + i], xb[p * L + i], out->limb(p, i), i));
+    if ((rc = launch_ew<OP>(c, jobs))) return rc;
     out->level = level;
-    out->scale = a->scale;
+    out->scale = std::max(a->scale, b->scale);
     return HEC_OK;
 }
 extern "C" int hec_add(hec_ctx *c, const hec_ct *a, const hec_ct *b, hec_ct *out) {
     if (!c || !a || !b || !out) return HEC_E_INVAL;
     cudaSetDevice(c->device);
     return addsub<EW_ADD>(c, a, b, out);
+}
+extern "C" int hec_sub(hec_ctx *c, const hec_ct *a, const hec_ct *b, hec_ct *out) {
+    if (!c || !a || !b || !out) return HEC_E_INVAL;
+    cudaSetDevice(c->device);
+    return addsub<EW_SUB>(c, a, b, out);
 }
 extern "C" int hec_add_new(hec_ctx *c, const hec_ct *a, const hec_ct *b, hec_ct **out) {
     if (!c || !a || !b || !out) return HEC_E_INVAL;

@@ -83,7 +83,8 @@ enum {
     EW_SUBMUL,      // out = (a + 2q - b) * s0 * R^-1, a < 4q lazy, b canonical  (rescale / mod-down combine)
     EW_MAC,         // out = out + a * b * R^-1   (key inner product, canonical accumulator)
     EW_PERMUTE,     // out[i] = a[index_g[i]]     (PermuteNTTWithIndexLvl)
-    EW_COPY
+    EW_COPY,
+    EW_MULSCALAR_ADD // out = out + a * s0 * R^-1  (MultByGaussianIntegerAndAdd with a real integer; s0 = MForm(c mod q))
 };
 template <int OP>
 __global__ void __launch_bounds__(256) k_ew(EwJobs J, const ModC *__restrict__ mods) {
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(256) k_ew(EwJobs J, const ModC *__restrict__ m
         else if (OP == EW_SUBMUL) r = mred(job.a[i] + 2 * q - job.b[i], job.s0, q, qinv);
         else if (OP == EW_MAC) r = addmod(job.out[i], mred(job.a[i], job.b[i], q, qinv), q);
         else if (OP == EW_PERMUTE) r = job.a[perm_index(i, job.g)];
+        else if (OP == EW_MULSCALAR_ADD) r = addmod(job.out[i], mred(job.a[i], job.s0, q, qinv), q);
         else r = job.a[i];
         job.out[i] = r;
     }

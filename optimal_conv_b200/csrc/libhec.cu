@@ -1,3 +1,4 @@
 // libhec.cu -- single translation unit of libhec.so (kernels are defined in headers).
 #include "hec.cu"
 #include "hec_conv.cu"
+#include "hec_poly.cu"

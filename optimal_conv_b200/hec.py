@@ -25,7 +25,8 @@ SYMBOLS = [
     "hec_timer_stop_ms", "hec_launch_count", "hec_host_register", "hec_host_unregister", "hec_pt_upload", "hec_pt_free", "hec_ct_upload", "hec_ct_download",
     "hec_ct_copy_new", "hec_ct_level", "hec_ct_scale", "hec_ct_set_scale", "hec_ct_free", "hec_swk_upload",
     "hec_swk_drop", "hec_mul_pt_new", "hec_mult_by_const", "hec_rescale", "hec_set_scale", "hec_add", "hec_add_new",
-    "hec_sub_new", "hec_add_pt", "hec_rlk_upload", "hec_mul_relin_new", "hec_rotate_gal", "hec_rotate_new", "hec_rotate_hoisted", "hec_galois_for_rotation",
+    "hec_sub_new", "hec_add_pt", "hec_rlk_upload", "hec_mul_relin_new", "hec_sub", "hec_drop_level", "hec_add_const",
+    "hec_mult_by_int_and_add", "hec_evaluate_poly", "hec_eval_relu", "hec_rotate_gal", "hec_rotate_new", "hec_rotate_hoisted", "hec_galois_for_rotation",
     "hec_ntt", "hec_keyswitch", "hec_moddown", "hec_conv_then_pack", "hec_conv_bl", "hec_ext_ctxt", "hec_keep_ctxt", "hec_plan_create", "hec_plan_run",
     "hec_plan_run_host", "hec_plan_submit_host", "hec_plan_wait", "hec_plan_span_begin", "hec_plan_span_end_ms",
     "hec_plan_profile", "hec_plan_destroy",
@@ -95,6 +96,12 @@ def lib():
     L.hec_sub_new.argtypes = [vp, vp, vp, C.POINTER(vp)]
     L.hec_add_pt.argtypes = [vp, vp, vp]
     L.hec_rlk_upload.argtypes = [vp, C.c_int, u64pp]
+    L.hec_sub.argtypes = [vp, vp, vp, vp]
+    L.hec_drop_level.argtypes = [vp, vp, C.c_int]
+    L.hec_add_const.argtypes = [vp, vp, C.c_double]
+    L.hec_mult_by_int_and_add.argtypes = [vp, vp, C.c_int64, vp]
+    L.hec_evaluate_poly.argtypes = [vp, vp, C.POINTER(C.c_double), C.c_int, C.c_double, C.c_double, C.POINTER(vp)]
+    L.hec_eval_relu.argtypes = [vp, vp, C.c_double, C.c_double, C.POINTER(vp)]
     L.hec_mul_relin_new.argtypes = [vp, vp, vp, C.POINTER(vp)]
     L.hec_rotate_gal.argtypes = [vp, vp, C.c_uint64, vp]
     L.hec_rotate_new.argtypes = [vp, vp, C.c_int, C.POINTER(vp)]
@@ -250,6 +257,29 @@ class Context:
         self._chk(self.L.hec_rlk_upload(self.h, max_level, _rows(flat)))
 
     # ---- evaluator ops (ckks.Evaluator subset) ----
+    def Sub(self, a, b, out):
+        self._chk(self.L.hec_sub(self.h, a.h, b.h, out.h))
+
+    def DropLevel(self, ct, levels):
+        self._chk(self.L.hec_drop_level(self.h, ct.h, levels))
+
+    def AddConst(self, ct, c):
+        self._chk(self.L.hec_add_const(self.h, ct.h, c))
+
+    def MultByIntAndAdd(self, ct, c, out):
+        self._chk(self.L.hec_mult_by_int_and_add(self.h, ct.h, c, out.h))
+
+    def EvaluatePoly(self, ct, coeffs, target_scale, eval_scale):
+        arr = (C.c_double * len(coeffs))(*coeffs)
+        h = vp()
+        self._chk(self.L.hec_evaluate_poly(self.h, ct.h, arr, len(coeffs), target_scale, eval_scale, C.byref(h)))
+        return Ciphertext(self, h)
+
+    def evalReLU(self, ct, alpha, eval_scale):
+        h = vp()
+        self._chk(self.L.hec_eval_relu(self.h, ct.h, alpha, eval_scale, C.byref(h)))
+        return Ciphertext(self, h)
+
     def MulRelinNew(self, a, b):
         h = vp()
         self._chk(self.L.hec_mul_relin_new(self.h, a.h, b.h, C.byref(h)))

@@ -212,6 +212,154 @@ class Oracle:
         self.L.orc_add(self.h, lv, _p(c1), _p(d1), _p(o1))
         return Ct(o0, o1, a.scale * b.scale)
 
+    # ---- polynomial evaluation (evalReLU, conv.go:435-480; L:ckks/polynomial_evaluation.go) ----
+    @staticmethod
+    def scale_up_exact(value, n, q):
+        """scaleUpExact (L:ckks/utils.go:31-57): big.Float at 53 bits == IEEE double; Int truncates"""
+        neg = value < 0
+        x = -n * value if neg else n * value
+        r = int(x + 0.5) % q
+        return q - r if neg else r
+
+    def drop_level(self, ct, levels):
+        return Ct(ct.c0[:ct.level + 1 - levels], ct.c1[:ct.level + 1 - levels], ct.scale)
+
+    def zero_ct(self, level, scale):
+        return Ct(np.zeros((level + 1, self.N), dtype=np.uint64), np.zeros((level + 1, self.N), dtype=np.uint64), scale)
+
+    def add_const(self, ct, c):
+        """AddConst(ct, c real, ct) (L:ckks/evaluator.go AddConst): c0 += scaleUpExact(c, ct.Scale, q_i) in every slot"""
+        c0 = ct.c0.copy()
+        if c != 0:
+            for i in range(ct.level + 1):
+                q = self.Q[i]
+                k = self.scale_up_exact(c, ct.scale, q) % q
+                c0[i] = ((c0[i].astype(object) + k) % q).astype(np.uint64)
+        return Ct(c0, ct.c1, ct.scale)
+
+    def mul_int_and_add(self, ct, c_int, out):
+        """MultByGaussianIntegerAndAdd(ct, c, 0, out): out += ct * c (L:ckks/evaluator.go), c an int64"""
+        lv = min(ct.level, out.level)
+        k = np.array([c_int % self.Q[i] for i in range(lv + 1)], dtype=np.uint64)
+        o = []
+        for src, dst in ((ct.c0, out.c0), (ct.c1, out.c1)):
+            t = np.empty((lv + 1, self.N), dtype=np.uint64)
+            self.L.orc_mul_const(self.h, lv, _p(np.ascontiguousarray(src[:lv + 1])), _p(k), _p(t))
+            r = np.empty_like(t)
+            self.L.orc_add(self.h, lv, _p(np.ascontiguousarray(dst[:lv + 1])), _p(t), _p(r))
+            o.append(r)
+        return Ct(o[0], o[1], out.scale)
+
+    def add_matched(self, a, b, sub=False):
+        """Add / Sub(a, b, out) with evaluateInPlace's scale matching (L:ckks/evaluator.go:365-473): the operand
+        with the smaller scale is multiplied by floor(ratio) when that is > 1 (MultByConst with an integer
+        constant); level = min, scale = max -- whichever of a, b, or a third ciphertext receives the result."""
+        lv = min(a.level, b.level)
+        a, b = self.drop_level(a, a.level - lv), self.drop_level(b, b.level - lv)
+        if a.scale > b.scale and np.floor(a.scale / b.scale) > 1:
+            b = self.mul_const(b, float(np.floor(a.scale / b.scale)))
+        elif b.scale > a.scale and np.floor(b.scale / a.scale) > 1:
+            a = self.mul_const(a, float(np.floor(b.scale / a.scale)))
+        r = self.sub(a, b) if sub else self.add(a, b)
+        r.scale = max(a.scale, b.scale)
+        return r
+
+    def evaluate_poly(self, ct, coeffs, target_scale, rlk, eval_scale):
+        """EvaluatePoly (L:ckks/polynomial_evaluation.go: computePowerBasis, recurse, splitCoeffs,
+        evaluatePolyFromPowerBasis).  coeffs: real coefficients, index = degree.  eval_scale = params.Scale()."""
+        Q = self.Q
+        deg = len(coeffs) - 1
+        log_degree = deg.bit_length()
+        log_split = log_degree >> 1
+        if ct.level < log_degree:
+            raise RuntimeError("%d levels < %d log(d) -> cannot evaluate" % (ct.level, log_degree))
+        C = {1: Ct(ct.c0.copy(), ct.c1.copy(), ct.scale)}
+
+        def power(n):
+            if n not in C:
+                a, b = (n + 1) // 2, n >> 1
+                power(a)
+                power(b)
+                C[n] = self.rescale(self.mul_relin(C[a], C[b], rlk), eval_scale)
+
+        for i in range(2, 1 << log_split):
+            power(i)
+        for i in range(log_split, log_degree):
+            power(1 << i)
+
+        class P:  # Poly{maxDeg, coeffs, lead}
+            def __init__(self, c, max_deg, lead):
+                self.c, self.max_deg, self.lead = c, max_deg, lead
+
+            @property
+            def degree(self):
+                return len(self.c) - 1
+
+        def split(p, sp):
+            r = P(p.c[:sp], sp - 1 if p.max_deg == p.degree else p.max_deg - (p.degree - sp + 1), False)
+            q = P(p.c[sp:], p.max_deg, p.lead)
+            return q, r
+
+        def from_basis(ts, p):
+            if p.degree == 0:
+                res = self.zero_ct(C[1].level, ts)
+                return self.add_const(res, p.c[0]) if abs(p.c[0]) > 1e-14 else res
+            lvl = C[p.degree].level
+            qi = float(Q[lvl])
+            res = self.zero_ct(lvl, ts * qi)
+            if abs(p.c[0]) > 1e-14:
+                res = self.add_const(res, p.c[0])
+            for key in range(p.degree, 0, -1):
+                if abs(p.c[key]) > 1e-14:
+                    const_scale = ts * qi / C[key].scale
+                    x = p.c[key] * const_scale   # int64(float): CVTTSD2SQ yields -2^63 when out of range
+                    res = self.mul_int_and_add(C[key], int(x) if abs(x) < 2.0 ** 63 else -(1 << 63), res)
+            return self.rescale(res, eval_scale)
+
+        def recurse(ts, ls, ld, p):
+            if p.degree < (1 << ls):
+                if p.lead and p.max_deg > ((1 << ld) - (1 << (ls - 1))) and ls > 1:
+                    ld = p.degree.bit_length()
+                    return recurse(ts, ld >> 1, ld, p)
+                return from_basis(ts, p)
+            nxt = 1 << ls
+            while nxt < (p.degree >> 1) + 1:
+                nxt <<= 1
+            q, r = split(p, nxt)
+            level = C[nxt].level - 1
+            if q.max_deg >= 1 << (ld - 1) and q.lead:
+                level += 1
+            qi = float(Q[level])
+            res = recurse(ts * qi / C[nxt].scale, ls, ld, q)
+            tmp = recurse(ts, ls, ld, r)
+            if res.level > tmp.level:
+                while res.level != tmp.level + 1:
+                    res = self.drop_level(res, 1)
+            res = self.mul_relin(res, C[nxt], rlk)
+            if res.level > tmp.level:
+                res = self.add_matched(self.rescale(res, eval_scale), tmp)
+            else:
+                res = self.rescale(self.add_matched(res, tmp), eval_scale)
+            return res
+
+        return recurse(target_scale, log_split, log_degree, P(list(coeffs), deg, True))
+
+    RELU_COEFFS = ([0.0, 10.8541842577442, 0.0, -62.2833925211098, 0.0, 114.369227820443, 0.0, -62.8023496973074],
+                   [0.0, 4.13976170985111, 0.0, -5.84997640211679, 0.0, 2.94376255659280, 0.0, -0.454530437460152],
+                   [0.0, 3.29956739043733, 0.0, -7.84227260291355, 0.0, 12.8907764115564, 0.0, -12.4917112584486, 0.0,
+                    6.94167991428074, 0.0, -2.04298067399942, 0.0, 0.246407138926031])
+
+    def eval_relu(self, ct, alpha, rlk, eval_scale):
+        """evalReLU (conv.go:435-480): three EvaluatePoly (minimax sign composition), AddConstNew, DropLevel,
+        Mul + Relinearize.  Returns the level-(L-11) ciphertext at scale ct.scale * eval_scale."""
+        aconst, bconst = (alpha + 1) / 2.0, (1 - alpha) / 2.0
+        s = ct
+        for k, co in enumerate(self.RELU_COEFFS):
+            s = self.evaluate_poly(s, [c * bconst for c in co] if k == 2 else co, eval_scale, rlk, eval_scale)
+        s = self.add_const(s, aconst)
+        x = self.drop_level(ct, ct.level - s.level)
+        return self.mul_relin(s, x, rlk)
+
     def add_pt(self, ct, pt):
         lv = min(ct.level, pt.shape[0] - 1)
         x0, p = np.ascontiguousarray(ct.c0[:lv + 1]), np.ascontiguousarray(pt[:lv + 1])

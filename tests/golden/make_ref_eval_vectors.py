@@ -2,7 +2,8 @@
 
 Run from the repo root in the build container (needs /root/reference/test_run, objdump, nm):
     python tests/golden/make_ref_eval_vectors.py            # small-N cases, ~2 min
-    python tests/golden/make_ref_eval_vectors.py --only n8_B4      # regenerate one small case
+    python tests/golden/make_ref_eval_vectors.py --only n8_B4      # regenerate one small conv case
+    python tests/golden/make_ref_eval_vectors.py --evalops | --relu | --ring | --conv  # regenerate one group
     python tests/golden/make_ref_eval_vectors.py --full B4_norm1   # N = 2^16 golden config, ~1 h
 The prebuilt binary is never executed.  tests/golden/refmachine.py interprets the compiled routines of
 the Lattigo fork (ring / rlwe / ckks packages) and of package main from their disassembly; objects
@@ -187,6 +188,15 @@ def evalop_case(logN, Q, P, level, rots):
     # ct x ct: MulRelinNew (mulRelin ct branch: tensor product + relinearisation with rlk), and the squaring case
     rec["mul_relin"] = digest_ct(m, m.call(CKKS + "(*evaluator).MulRelinNew", [e, ict, ct, ict, ct2, 0])[-1])
     rec["square_relin"] = digest_ct(m, m.call(CKKS + "(*evaluator).MulRelinNew", [e, ict, ct, ict, ct, 0])[-1])
+    # Add / Sub with different scales and every aliasing of the receiver (evaluateInPlace's scale matching)
+    rec["addsub_scaled"] = {}
+    for op in ("Add", "Sub"):
+        for tag, sa, sb in (("big_small", PR.SCALE * 12345.678, PR.SCALE), ("small_big", PR.SCALE, PR.SCALE * 12345.678), ("x1.5", PR.SCALE, PR.SCALE * 1.5)):
+            for alias in ("a", "b", "new"):
+                A, B, Cc = m.new_ct([lim(61), lim(62)], sa), m.new_ct([lim(63), lim(64)], sb), m.new_ct([lim(66), lim(67)], 7.0)
+                out = {"a": A, "b": B, "new": Cc}[alias]
+                m.call(CKKS + "(*evaluator)." + op, [e, ict, A, ict, B, out])
+                rec["addsub_scaled"]["%s:%s:%s" % (op, tag, alias)] = digest_ct(m, out)
     # Add(ct, pt, ct) at equal scales (eval.go:130,258 guard equality before adding)
     sum_ct = m.new_ct([lim(61), lim(62)], PR.SCALE)
     m.call(CKKS + "(*evaluator).Add", [e, ict, sum_ct, ipt, pt, sum_ct])
@@ -208,6 +218,34 @@ def evalop_case(logN, Q, P, level, rots):
     return rec
 
 
+# ---------------------------------------------------------------- evalReLU
+RELU_CASES = [("n5_alpha0", 5, 0.0, 15), ("n6_leaky0.1", 6, 0.1, 15), ("n5_level12", 5, 0.0, 12), ("n5_level8_too_low", 5, 0.0, 8)]
+
+
+def relu_case(logN, alpha, level):
+    """main.evalReLU (conv.go:435-480): three EvaluatePoly + AddConstNew + DropLevel + Mul + Relinearize on a
+    seeded level-`level` ciphertext over the first 16 moduli of set 6 (the ReLU primes are levels 5..15), alpha = 5"""
+    N = 1 << logN
+    Q, P = PR.Q_SET6[:16], PR.P_ALL
+    m = Machine()
+    beta_full = (len(Q) + len(P) - 1) // len(P)
+    rlk = np.stack([np.stack([synth.uniform_limbs(8000 + 10 * d + k, list(Q) + list(P), N) for k in range(2)]) for d in range(beta_full)])
+    params, ev = m.new_evaluator(logN, Q, P, PR.SCALE, {}, rlk)
+    lim = lambda seed: [ints(l) for l in synth.uniform_limbs(seed, Q[:level + 1], N)]  # noqa: E731
+    ct = m.new_ct([lim(61), lim(62)], PR.SCALE)
+    rec = {"logN": logN, "alpha": alpha, "level": level, "Q": ["%x" % q for q in Q], "P": ["%x" % p for p in P]}
+    try:
+        res = m.call("main.evalReLU", params + ev + [ct, f2b(alpha), 0], max_steps=1 << 62)[-1]
+        rec["out"] = digest_ct(m, res)
+    except RuntimeError as ex:
+        if not isinstance(ex.__cause__, GoPanic):
+            raise
+        rec["panic"] = str(ex.__cause__)
+    rec["interpreted_instructions"] = m.steps
+    print("evalReLU case logN=%d alpha=%g level=%d: %d instructions" % (logN, alpha, level, m.steps), flush=True)
+    return rec
+
+
 SMALL_CONV = [
     # name, logN, B, norm, seed, out_scale, Q, P
     ("n8_B4", 8, 4, 1, 3, PR.SCALE, PR.Q_SET6[:2], PR.P_PACK),
@@ -223,26 +261,32 @@ SMALL_CONV = [
 
 
 def main():
-    data = json.load(open(OUT)) if os.path.exists(OUT) else {}
-    data["binary"] = "test_run (go1.16.6, github.com/dwkim606/test_lattigo v0.0.0-20220812213541-eb33b0555aaa)"
+    new = {"binary": "test_run (go1.16.6, github.com/dwkim606/test_lattigo v0.0.0-20220812213541-eb33b0555aaa)"}
     if "--full" in sys.argv:
         name = sys.argv[sys.argv.index("--full") + 1]
         cfg = [c for c in common.GOLDEN_CONFIGS if c["name"] == name][0]
-        rec = conv_case(PR.LOGN, cfg["B"], cfg["norm"], cfg["seed"], float(1 << cfg["out_log"]), common.Q2, common.P1)
-        data = json.load(open(OUT)) if os.path.exists(OUT) else data
-        data.setdefault("conv_full", {})[name] = rec
+        new["conv_full"] = {name: conv_case(PR.LOGN, cfg["B"], cfg["norm"], cfg["seed"], float(1 << cfg["out_log"]), common.Q2, common.P1)}
     elif "--only" in sys.argv:
-        for name, logN, B, norm, seed, out_scale, Q2, P1 in SMALL_CONV:
-            if name in sys.argv:
-                data["conv"][name] = conv_case(logN, B, norm, seed, out_scale, Q2, P1)
-    elif "--evalops" in sys.argv:
-        data["evalops"] = {name: evalop_case(logN, Q, P, level, rots) for name, logN, Q, P, level, rots in EVALOP_CASES}
+        new["conv"] = {name: conv_case(logN, B, norm, seed, out_scale, Q2, P1)
+                       for name, logN, B, norm, seed, out_scale, Q2, P1 in SMALL_CONV if name in sys.argv}
     else:
-        data["evalops"] = {name: evalop_case(logN, Q, P, level, rots) for name, logN, Q, P, level, rots in EVALOP_CASES}
-        data["ring"] = ring_cases()
-        data["conv"] = {}
-        for name, logN, B, norm, seed, out_scale, Q2, P1 in SMALL_CONV:
-            data["conv"][name] = conv_case(logN, B, norm, seed, out_scale, Q2, P1)
+        groups = [g for g in ("relu", "evalops", "ring", "conv") if "--" + g in sys.argv] or ["relu", "evalops", "ring", "conv"]
+        if "relu" in groups:
+            new["relu"] = {name: relu_case(logN, alpha, level) for name, logN, alpha, level in RELU_CASES}
+        if "evalops" in groups:
+            new["evalops"] = {name: evalop_case(logN, Q, P, level, rots) for name, logN, Q, P, level, rots in EVALOP_CASES}
+        if "ring" in groups:
+            new["ring"] = ring_cases()
+        if "conv" in groups:
+            new["conv"] = {name: conv_case(logN, B, norm, seed, out_scale, Q2, P1)
+                           for name, logN, B, norm, seed, out_scale, Q2, P1 in SMALL_CONV}
+    # merge into the file as it is NOW (long --full runs may have finished meanwhile)
+    data = json.load(open(OUT)) if os.path.exists(OUT) else {}
+    for k, v in new.items():
+        if isinstance(v, dict) and k in ("conv_full", "conv") and isinstance(data.get(k), dict) and ("--full" in sys.argv or "--only" in sys.argv):
+            data[k].update(v)
+        else:
+            data[k] = v
     json.dump(data, open(OUT, "w"), indent=1, sort_keys=True)
     print("wrote", OUT)
 

@@ -81,6 +81,10 @@ class Machine(Emu):
         H("runtime.makemap_small", lambda em: self.wq(self.r[4], self.new_map(None)))
         H("runtime.makemap", lambda em: self.wq(self.r[4] + 24, self.new_map(None)))
         H("runtime.mapiterinit", self.h_mapiterinit)
+        H("runtime.fastrand", self.h_fastrand)
+        H("runtime.growslice", self.h_growslice)
+        H("fmt.Errorf", self.h_errorf)
+        H("runtime.typedslicecopy", self.h_typedslicecopy)
         H("runtime.mapiternext", self.h_mapiternext)
         # pure number theory whose Go implementation needs math/big or a prime sieve
         H(RING + "getFactors", self.h_getfactors)
@@ -164,9 +168,41 @@ class Machine(Emu):
         self.write_u64s(slot, words)
         self.maps[h][key] = slot
 
+    def _mapid(self, h):
+        """maps the compiled code makes on its own stack (hmap zeroed + hash0 = fastrand()) are told apart
+        from stale ones at the same address by the unique hash0 our fastrand hook hands out"""
+        return (h, self.rd(h + 12, 4)) if h and h not in self.maps else h
+
+    def h_growslice(self, em):
+        sp = self.r[4]
+        esz = self.load_const(self.rq(sp))
+        ptr, ln, cap, want = self.rq(sp + 8), self.rq(sp + 16), self.rq(sp + 24), self.rq(sp + 32)
+        ncap = max(want, 2 * cap)
+        a = self.alloc(max(8, esz * ncap))
+        self.copy_bytes(a, ptr, esz * ln)
+        self.write_u64s(sp + 40, [a, ln, ncap])
+
+    def h_typedslicecopy(self, em):
+        sp = self.r[4]
+        esz = self.load_const(self.rq(sp))
+        n = min(self.rq(sp + 16), self.rq(sp + 32))
+        self.copy_bytes(self.rq(sp + 8), self.rq(sp + 24), esz * n)
+        self.wq(sp + 40, n)
+
+    def h_errorf(self, em):
+        """fmt.Errorf(format, args...) -> a non-nil error whose data word points at the (unformatted) format string"""
+        sp = self.r[4]
+        data = self.alloc(16)
+        self.write_u64s(data, [self.rq(sp), self.rq(sp + 8)])
+        self.write_u64s(sp + 40, [self.alloc(32), data])
+
+    def h_fastrand(self, em):
+        self.rand_ctr = getattr(self, "rand_ctr", 0) + 1
+        self.wr(self.r[4], 4, self.rand_ctr)
+
     def h_mapaccess(self, nres):
         sp = self.r[4]
-        h, key = self.rq(sp + 8), self.rq(sp + 16)
+        h, key = self._mapid(self.rq(sp + 8)), self.rq(sp + 16)
         slot = self.maps[h].get(key) if h in self.maps else None
         self.wq(sp + 24, slot if slot is not None else self.zero)
         if nres == 2:
@@ -174,7 +210,12 @@ class Machine(Emu):
 
     def h_mapassign(self, em):
         sp = self.r[4]
-        t, h, key = self.rq(sp), self.rq(sp + 8), self.rq(sp + 16)
+        t, h0, key = self.rq(sp), self.rq(sp + 8), self.rq(sp + 16)
+        h = self._mapid(h0)
+        if h not in self.maps:
+            self.maps[h], self.mapval[h] = {}, None
+        if key not in self.maps[h]:
+            self.wq(h0, self.rq(h0) + 1)     # hmap.count (len(m) is read inline)
         if self.mapval[h] is None:     # maptype.elem (*_type at +56) -> _type.size (first word)
             self.mapval[h] = self.load_const(self.load_const(t + 56))
         if key not in self.maps[h]:
@@ -254,7 +295,7 @@ class Machine(Emu):
 
     def h_mapiterinit(self, em):
         sp = self.r[4]
-        h, it = self.rq(sp + 8), self.rq(sp + 16)
+        h, it = self._mapid(self.rq(sp + 8)), self.rq(sp + 16)
         self.iters = getattr(self, "iters", {})
         self.iters[it] = iter(sorted(self.maps[h].items())) if h in self.maps else iter(())
         self._iter_step(it)

@@ -143,6 +143,7 @@ class Emu:
         self.G = 0x7f0000000000  # fake g struct: stackguard0 = 0
         self.wq(self.G + 0x10, 0)
         self.hooks = {}     # call target -> python function(emu): reads args at [rsp], writes results after them
+        self.tracers = {}   # call target -> python observer(emu), called before the call is made
         self.heap = 0x600000000000
 
     def alloc(self, nbytes):
@@ -495,6 +496,8 @@ class Emu:
             return ins.target if ins.target is not None else self.get(ops[0], 8)
         if mn == "call":
             tgt = ins.target if ins.target is not None else self.get(ops[0], 8)
+            if self.tracers and tgt in self.tracers:
+                self.tracers[tgt](self)   # observer only: sees the argument area at [rsp], then the call proceeds
             if tgt in self.hooks:
                 self.hooks[tgt](self)
                 return nxt

@@ -275,6 +275,61 @@ def test_mul_relin_ct_ct(shape):
         c.close()
 
 
+def test_add_sub_scale_matching_and_aliasing():
+    """Add / Sub follow evaluateInPlace: level = min, scale = max, integer scale-up of the smaller-scale operand,
+    for every aliasing of the receiver (oracle pinned against the reference's compiled Add/Sub for all of these)."""
+    Q = PR.Q_SET6[:4]
+    c, o = hec.Context(PR.LOGN, Q, PR.P_PACK_BL), Oracle(PR.LOGN, Q, PR.P_PACK_BL)
+    try:
+        S1, S2 = PR.SCALE * 12345.678, PR.SCALE
+        for sub in (False, True):
+            for sa, sb in ((S1, S2), (S2, S1), (S2, S2 * 1.5), (S2, S2)):
+                for alias in ("a", "b", "new"):
+                    a = Ct(synth.uniform_limbs(1, Q, N), synth.uniform_limbs(2, Q, N), sa)
+                    b = Ct(synth.uniform_limbs(3, Q[:3], N), synth.uniform_limbs(4, Q[:3], N), sb)
+                    A, B = c.upload_ct(a.c0, a.c1, sa), c.upload_ct(b.c0, b.c1, sb)
+                    out = {"a": A, "b": B, "new": c.upload_ct(a.c0, a.c1, 7.0)}[alias]
+                    (c.Sub if sub else c.Add)(A, B, out)
+                    ref = o.add_matched(a, b, sub=sub)
+                    g0, g1 = out.download()
+                    assert out.level == ref.level == 2 and out.scale == ref.scale, (sub, sa / sb, alias)
+                    assert np.array_equal(g0, ref.c0) and np.array_equal(g1, ref.c1), (sub, sa / sb, alias)
+                    for x in {A, B, out}:
+                        x.free()
+    finally:
+        c.close()
+
+
+def test_evaluate_poly_and_eval_relu_level15_alpha5():
+    """evalReLU (conv.go:435-480) at N = 2^16 on the first 16 moduli of set 6 (ReLU primes = levels 5..15), alpha = 5:
+    libhec's host orchestration + kernels == the oracle's, whose small-N results are pinned against the reference's
+    compiled main.evalReLU (tests/test_ref_eval_vectors.py).  Also the leaky variant and one EvaluatePoly alone."""
+    Q, P = PR.Q_SET6[:16], PR.P_ALL
+    c, o = hec.Context(PR.LOGN, Q, P), Oracle(PR.LOGN, Q, P)
+    try:
+        rlk = np.stack([np.stack([synth.uniform_limbs(8000 + 10 * d + k, Q + P, N) for k in range(2)]) for d in range(o.beta_full)])
+        c.upload_rlk(rlk, 15)
+        a = Ct(synth.uniform_limbs(61, Q, N), synth.uniform_limbs(62, Q, N), PR.SCALE)
+        A = c.upload_ct(a.c0, a.c1, PR.SCALE)
+        res = c.EvaluatePoly(A, Oracle.RELU_COEFFS[0], PR.SCALE, PR.SCALE)
+        ref = o.evaluate_poly(a, Oracle.RELU_COEFFS[0], PR.SCALE, rlk, PR.SCALE)
+        g0, g1 = res.download()
+        assert res.level == ref.level == 12 and res.scale == ref.scale
+        assert np.array_equal(g0, ref.c0) and np.array_equal(g1, ref.c1)
+        for alpha in (0.0, 0.1):
+            res = c.evalReLU(A, alpha, PR.SCALE)
+            ref = o.eval_relu(a, alpha, rlk, PR.SCALE)
+            g0, g1 = res.download()
+            assert res.level == ref.level == 4 and res.scale == ref.scale, alpha
+            assert np.array_equal(g0, ref.c0) and np.array_equal(g1, ref.c1), alpha
+        low = c.upload_ct(a.c0[:3], a.c1[:3], PR.SCALE)
+        with pytest.raises(hec.HecError) as e:  # checkEnoughLevels
+            c.evalReLU(low, 0.0, PR.SCALE)
+        assert e.value.code == hec.HEC_E_LEVEL
+    finally:
+        c.close()
+
+
 # ---------------------------------------------------------------- the conv path
 @pytest.mark.parametrize("cfg", common.GOLDEN_CONFIGS, ids=lambda c: c["name"])
 @pytest.mark.parametrize("flags", [hec.CONV_FUSED, hec.CONV_OPLEVEL], ids=["fused", "oplevel"])

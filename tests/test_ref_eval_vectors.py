@@ -107,12 +107,35 @@ def test_baseline_path_evaluator_ops_match_reference_code(name):
     assert dg(o.mul_relin(ct, ct, rlk)) == rec["square_relin"]
     assert dg(o.add(ct, ct2)) == rec["add"]
     assert dg(o.sub(ct, ct2)) == rec["sub"]
+    scales = {"big_small": (PR.SCALE * 12345.678, PR.SCALE), "small_big": (PR.SCALE, PR.SCALE * 12345.678), "x1.5": (PR.SCALE, PR.SCALE * 1.5)}
+    assert len(rec["addsub_scaled"]) == 18
+    for key, d in rec["addsub_scaled"].items():   # receiver aliasing does not change the result
+        op, tag, _ = key.split(":")
+        r = o.add_matched(Ct(ct.c0, ct.c1, scales[tag][0]), Ct(ct2.c0, ct2.c1, scales[tag][1]), sub=(op == "Sub"))
+        assert dg(r) == d, key
     assert dg(o.add_pt(ct, pt)) == rec["add_pt"]
     assert rec["rescale_err"] is False
     assert dg(o.rescale(Ct(ct.c0, ct.c1, PR.SCALE * float(Q[level])), PR.SCALE)) == rec["rescale"]
     if "rescale2" in rec:  # two divisions by one Rescale call (DivRoundByLastModulusManyNTT, nbRescales = 2)
         r2 = o.rescale(Ct(ct.c0, ct.c1, PR.SCALE * float(Q[level]) * float(Q[level - 1])), PR.SCALE)
         assert r2.level == level - 2 and dg(r2) == rec["rescale2"]
+
+
+@pytest.mark.parametrize("name", sorted(REF["relu"]))
+def test_eval_relu_matches_reference_main_code(name):
+    """main.evalReLU (conv.go:435-480; three EvaluatePoly + AddConstNew + DropLevel + Mul + Relinearize), interpreted
+    from the reference binary, == the oracle's restatement of EvaluatePoly's orchestration, bit for bit"""
+    rec = REF["relu"][name]
+    Q, P = mods(rec)
+    N, level = 1 << rec["logN"], rec["level"]
+    o = Oracle(rec["logN"], Q, P)
+    rlk = np.stack([np.stack([synth.uniform_limbs(8000 + 10 * d + k, Q + P, N) for k in range(2)]) for d in range(o.beta_full)])
+    ct = Ct(synth.uniform_limbs(61, Q[:level + 1], N), synth.uniform_limbs(62, Q[:level + 1], N), PR.SCALE)
+    if "panic" in rec:
+        with pytest.raises(RuntimeError, match="cannot evaluate"):
+            o.eval_relu(ct, rec["alpha"], rlk, PR.SCALE)
+        return
+    assert dg(o.eval_relu(ct, rec["alpha"], rlk, PR.SCALE)) == rec["out"]
 
 
 FULL = sorted(REF.get("conv_full", {}))

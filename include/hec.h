@@ -115,7 +115,7 @@ int hec_mul_relin_new(hec_ctx *ctx, const hec_ct *a, const hec_ct *b, hec_ct **o
  * hec_mult_by_int_and_add: MultByGaussianIntegerAndAdd(ct, c, 0, out).
  * hec_evaluate_poly: EvaluatePoly(ct, NewPoly(coeffs), target_scale) (L:ckks/polynomial_evaluation.go), real
  *   coefficients, index = degree; eval_scale = params.Scale() (the evaluator's rescale threshold).
- * hec_eval_relu: evalReLU(params, evaluator, ct, alpha); needs the relinearisation key and 11 levels. */
+ * hec_eval_relu: evalReLU(params, evaluator, ct, alpha); needs the relinearisation key and 10 levels; the result is the un-rescaled product. */
 int hec_sub(hec_ctx *ctx, const hec_ct *a, const hec_ct *b, hec_ct *out);
 int hec_drop_level(hec_ctx *ctx, hec_ct *ct, int levels);
 int hec_add_const(hec_ctx *ctx, hec_ct *ct, double c);

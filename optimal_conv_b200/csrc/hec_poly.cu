@@ -187,7 +187,7 @@ extern "C" int hec_evaluate_poly(hec_ctx *c, const hec_ct *ct, const double *coe
 }
 
 // evalReLU(params, evaluator, ct, alpha) (conv.go:435-480): sign(x) by three composed minimax polynomials,
-// then x * (bconst * sign(x) + aconst).  Consumes 11 levels; the result has scale ct.Scale * eval_scale
+// then x * (bconst * sign(x) + aconst).  Consumes 10 levels (3 + 3 + 4); the result has scale ct.Scale * eval_scale
 // (Mul + Relinearize, not rescaled -- the caller rescales, as the reference's callers do).
 extern "C" int hec_eval_relu(hec_ctx *c, const hec_ct *ct, double alpha, double eval_scale, hec_ct **out) {
     if (!c || !ct || !out) return HEC_E_INVAL;

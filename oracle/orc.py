@@ -351,7 +351,7 @@ class Oracle:
 
     def eval_relu(self, ct, alpha, rlk, eval_scale):
         """evalReLU (conv.go:435-480): three EvaluatePoly (minimax sign composition), AddConstNew, DropLevel,
-        Mul + Relinearize.  Returns the level-(L-11) ciphertext at scale ct.scale * eval_scale."""
+        Mul + Relinearize.  Returns the level-(L-10) ciphertext at scale ct.scale * eval_scale (not rescaled)."""
         aconst, bconst = (alpha + 1) / 2.0, (1 - alpha) / 2.0
         s = ct
         for k, co in enumerate(self.RELU_COEFFS):

@@ -320,7 +320,7 @@ def test_evaluate_poly_and_eval_relu_level15_alpha5():
             res = c.evalReLU(A, alpha, PR.SCALE)
             ref = o.eval_relu(a, alpha, rlk, PR.SCALE)
             g0, g1 = res.download()
-            assert res.level == ref.level == 4 and res.scale == ref.scale, alpha
+            assert res.level == ref.level == 5 and res.scale == ref.scale == PR.SCALE * PR.SCALE, alpha
             assert np.array_equal(g0, ref.c0) and np.array_equal(g1, ref.c1), alpha
         low = c.upload_ct(a.c0[:3], a.c1[:3], PR.SCALE)
         with pytest.raises(hec.HecError) as e:  # checkEnoughLevels

@@ -180,7 +180,8 @@ def run_side_workload(args):
                             B/2 x (k^2 MulNew/Add + RotateNew) + bias  (BASELINE.json config 3: the k sweep)
     --workload keyswitch  : KeySwitcher.SwitchKeysInPlace at level 27, alpha = 5, beta = 6 (SURVEY.md 8d stress)
     --workload mul_relin  : MulRelinNew(ct, ct) + Rescale at level 10, alpha = 5 (the multiply of
-                            evalReLU's polynomial evaluation, conv.go:435-480)"""
+                            evalReLU's polynomial evaluation, conv.go:435-480)
+    --workload eval_relu  : the whole evalReLU on one level-15 ciphertext (three EvaluatePoly + the final multiply)"""
     import torch
     from optimal_conv_b200 import hec
     if not torch.cuda.is_available():
@@ -222,6 +223,26 @@ def run_side_workload(args):
             o = Oracle(PR.LOGN, Q, P)
             t0 = time.perf_counter()
             o.rescale(o.mul_relin(Ct(a[0], a[1], PR.SCALE), Ct(a[2], a[3], PR.SCALE), rlk), PR.SCALE)
+            cpu_s = time.perf_counter() - t0
+    elif args.workload == "eval_relu":
+        level = 15
+        Q, P = PR.Q_SET6[:level + 1], PR.P_ALL
+        ctx = hec.Context(PR.LOGN, Q, P)
+        beta = (level + 1 + len(P) - 1) // len(P)
+        rlk = np.stack([np.stack([synth.uniform_limbs(8000 + 10 * d + kk, Q + P, N) for kk in range(2)]) for d in range(beta)])
+        ctx.upload_rlk(rlk, level)
+        a0, a1 = synth.uniform_limbs(61, Q, N), synth.uniform_limbs(62, Q, N)
+        A = ctx.upload_ct(a0, a1, PR.SCALE)
+
+        def step():
+            ctx.evalReLU(A, 0.0, PR.SCALE).free()
+        unit, name = "ReLU evaluations/s", "evalReLU (conv.go:435-480) on one level-15 ciphertext, set 6 ReLU primes, alpha=5: 3 EvaluatePoly (deg 7, 7, 13) + final multiply"
+        alg = None
+        if args.cpu_sample > 0:
+            from oracle.orc import Ct, Oracle
+            o = Oracle(PR.LOGN, Q, P)
+            t0 = time.perf_counter()
+            o.eval_relu(Ct(a0, a1, PR.SCALE), 0.0, rlk, PR.SCALE)
             cpu_s = time.perf_counter() - t0
     else:
         # one evalConv_BN_BL_test interval for the (B, w) row of main.go:578-579 and kernel width --ker
@@ -270,7 +291,7 @@ def run_side_workload(args):
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "dtype": "u64",
             "data": "synthetic", "config": {"workload": args.workload, "path": "op-level generic kernels"},
             "gpu_launches": ctx.launch_count() - l0}
-    if args.workload in ("conv_bl", "mul_relin") and args.cpu_sample > 0:
+    if args.workload in ("conv_bl", "mul_relin", "eval_relu") and args.cpu_sample > 0:
         line["cpu_baseline"] = {"value": 1.0 / cpu_s, "unit": unit, "cores": 1, "kind": "port",
                                 "sample": "1 call of the same workload, oracle port, 1 thread"}
     if alg:
@@ -289,7 +310,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="B: output channels packed per ciphertext")
     ap.add_argument("--ker", type=int, default=3, help="kernel width k (only changes the work of --workload conv_bl)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="conv", choices=["conv", "conv_bl", "keyswitch", "mul_relin"],
+    ap.add_argument("--workload", default="conv", choices=["conv", "conv_bl", "keyswitch", "mul_relin", "eval_relu"],
                     help="conv = the headline fused path; the others are op-level side measurements")
     ap.add_argument("--cpu-sample", type=int, default=12, help="convs timed for cpu_baseline (0 = skip)")
     ap.add_argument("--ring", type=int, default=8, help="distinct input batches rotated through (> L2)")

@@ -123,6 +123,9 @@ int hec_mult_by_int_and_add(hec_ctx *ctx, const hec_ct *ct, int64_t c, hec_ct *o
 int hec_evaluate_poly(hec_ctx *ctx, const hec_ct *ct, const double *coeffs, int n, double target_scale,
                       double eval_scale, hec_ct **out);
 int hec_eval_relu(hec_ctx *ctx, const hec_ct *ct, double alpha, double eval_scale, hec_ct **out);
+/* the loop `for ul: ct_boots[ul] = evalReLU(...)` of eval.go:470-476 as one call: n ciphertexts of a common level and
+ * scale, every step one launch sequence for the whole batch */
+int hec_eval_relu_many(hec_ctx *ctx, const hec_ct *const *cts, int n, double alpha, double eval_scale, hec_ct **outs);
 /* RotateGal(ct, galEl, out)  (conv.go:291); out may alias ct */
 int hec_rotate_gal(hec_ctx *ctx, const hec_ct *ct, uint64_t galEl, hec_ct *out);
 /* RotateNew(ct, k)  (eval.go:123) */

@@ -513,51 +513,65 @@ extern "C" int hec_mult_by_const(hec_ctx *c, hec_ct *ct, double constant) {
     return HEC_OK;
 }
 
-// one DivRoundByLastModulusNTT on both polys (L:ring/ring_scaling.go:442-513)
-static int div_round_last(hec_ctx *c, hec_ct *ct) {
-    int L = ct->level;
-    int rc = reserve(c, 2 + 2 * (size_t)L);
-    if (rc) return rc;
+// one DivRoundByLastModulusNTT on both polys (L:ring/ring_scaling.go:442-513) of every ciphertext of a batch
+// at a common level (one launch sequence for all of them)
+static int div_round_last_many(hec_ctx *c, const std::vector<hec_ct *> &cts) {
+    int L = cts[0]->level, rc;
+    size_t n = cts.size();
+    if ((rc = reserve(c, n * (2 + 2 * (size_t)L)))) return rc;
     u64 qL = c->q(L), half = (qL - 1) >> 1;
-    u64 *t = c->scratch(2), *u = c->scratch(2 * (size_t)L);
+    std::vector<u64 *> t(n), u(n);
     std::vector<LimbJob> nj;
-    for (int p = 0; p < 2; p++) nj.push_back({ct->limb(p, L), t + (size_t)p * HEC_N, L, 0});
-    if ((rc = hec_launch_ntt(c, nj, true))) return rc;
     std::vector<EwJob> ej;
-    for (int p = 0; p < 2; p++) ej.push_back(ewjob(t + (size_t)p * HEC_N, nullptr, t + (size_t)p * HEC_N, L, half));
+    for (size_t m = 0; m < n; m++) {
+        t[m] = c->scratch(2); u[m] = c->scratch(2 * (size_t)L);
+        for (int p = 0; p < 2; p++) {
+            nj.push_back({cts[m]->limb(p, L), t[m] + (size_t)p * HEC_N, L, 0});
+            ej.push_back(ewjob(t[m] + (size_t)p * HEC_N, nullptr, t[m] + (size_t)p * HEC_N, L, half));
+        }
+    }
+    if ((rc = hec_launch_ntt(c, nj, true))) return rc;
     if ((rc = launch_ew<EW_CENTER>(c, ej))) return rc;
     ej.clear();
     nj.clear();
-    for (int p = 0; p < 2; p++)
-        for (int i = 0; i < L; i++) {
-            u64 qi = c->q(i);
-            u64 *ui = u + ((size_t)p * L + i) * HEC_N;
-            ej.push_back(ewjob(t + (size_t)p * HEC_N, nullptr, ui, i, qi - half % qi));
-            nj.push_back({ui, ui, i, 0});
-        }
+    for (size_t m = 0; m < n; m++)
+        for (int p = 0; p < 2; p++)
+            for (int i = 0; i < L; i++) {
+                u64 qi = c->q(i);
+                u64 *ui = u[m] + ((size_t)p * L + i) * HEC_N;
+                ej.push_back(ewjob(t[m] + (size_t)p * HEC_N, nullptr, ui, i, qi - half % qi));
+                nj.push_back({ui, ui, i, 0});
+            }
     if ((rc = launch_ew<EW_REDUCE_ADD>(c, ej))) return rc;
     if ((rc = hec_launch_ntt(c, nj, false))) return rc;
     ej.clear();
-    for (int p = 0; p < 2; p++)
-        for (int i = 0; i < L; i++)
-            ej.push_back(ewjob(u + ((size_t)p * L + i) * HEC_N, ct->limb(p, i), ct->limb(p, i), i, c->resc[L][i]));
+    for (size_t m = 0; m < n; m++)
+        for (int p = 0; p < 2; p++)
+            for (int i = 0; i < L; i++)
+                ej.push_back(ewjob(u[m] + ((size_t)p * L + i) * HEC_N, cts[m]->limb(p, i), cts[m]->limb(p, i), i, c->resc[L][i]));
     if ((rc = launch_ew<EW_SUBMUL>(c, ej))) return rc;
-    ct->level = L - 1;
+    for (size_t m = 0; m < n; m++) cts[m]->level = L - 1;
     return HEC_OK;
 }
 
+// Rescale(ct, minScale, ct) (L:ckks/evaluator.go:1291-1325) for a batch sharing level and scale
+int hec_rescale_many(hec_ctx *c, const std::vector<hec_ct *> &cts, double min_scale) {
+    if (cts.empty()) return HEC_OK;
+    for (hec_ct *x : cts)
+        if (x->level != cts[0]->level || x->scale != cts[0]->scale) return c->fail(HEC_E_INVAL, "batched Rescale needs a common level and scale");
+    if (cts[0]->level == 0) return c->fail(HEC_E_LEVEL, "cannot Rescale: input Ciphertext already at level 0");
+    while (cts[0]->level > 0 && cts[0]->scale / (double)c->q(cts[0]->level) >= min_scale / 2) {
+        double s = cts[0]->scale / (double)c->q(cts[0]->level);
+        int rc = div_round_last_many(c, cts);
+        if (rc) return rc;
+        for (hec_ct *x : cts) x->scale = s;
+    }
+    return HEC_OK;
+}
 extern "C" int hec_rescale(hec_ctx *c, hec_ct *ct, double min_scale) {
     if (!c || !ct) return HEC_E_INVAL;
     cudaSetDevice(c->device);
-    // L:ckks/evaluator.go:1291-1325
-    if (ct->level == 0) return c->fail(HEC_E_LEVEL, "cannot Rescale: input Ciphertext already at level 0");
-    while (ct->level > 0 && ct->scale / (double)c->q(ct->level) >= min_scale / 2) {
-        double s = ct->scale / (double)c->q(ct->level);
-        int rc = div_round_last(c, ct);
-        if (rc) return rc;
-        ct->scale = s;
-    }
-    return HEC_OK;
+    return hec_rescale_many(c, {ct}, min_scale);
 }
 
 extern "C" int hec_set_scale(hec_ctx *c, hec_ct *ct, double scale) {
@@ -806,39 +820,57 @@ int hec_rotate_many(hec_ctx *c, const std::vector<const hec_ct *> &ct, const std
 extern "C" int hec_rlk_upload(hec_ctx *c, int max_level, const uint64_t *const *limbs) {
     return hec_swk_upload(c, HEC_RLK_ID, max_level, limbs);
 }
-extern "C" int hec_mul_relin_new(hec_ctx *c, const hec_ct *a, const hec_ct *b, hec_ct **out) {
-    if (!c || !a || !b || !out) return HEC_E_INVAL;
-    cudaSetDevice(c->device);
+// a batch of independent products out[m] = MulRelinNew(a[m], b[m]) at a common level: one tensor launch,
+// one batched decomposition / inner product / mod-down, one add
+int hec_mul_relin_many(hec_ctx *c, const std::vector<const hec_ct *> &a, const std::vector<const hec_ct *> &b, std::vector<hec_ct *> &out) {
     auto it = c->keys.find(HEC_RLK_ID);
     if (it == c->keys.end()) return c->fail(HEC_E_NOKEY, "relinearisation key missing");
-    int level = std::min(a->level, b->level), L = level + 1, rc;
-    hec_ct *o = nullptr;
-    if ((rc = hec_ct_alloc(c, level, a->scale * b->scale, &o))) return rc;
-    auto bail = [&](int e) { hec_ct_free(c, o); return e; };
-    if ((rc = reserve(c, decomp_limbs(c, level) + ks_limbs(c, level) + 3 * (size_t)L))) return bail(rc);
-    u64 *c2 = c->scratch(L), *d0 = c->scratch(L), *d1 = c->scratch(L);
-    for (int off = 0; off < L; off += HEC_TNJOBS) {
-        int n = std::min(HEC_TNJOBS, L - off);
+    size_t n = a.size();
+    int level = std::min(a[0]->level, b[0]->level), L = level + 1, rc;
+    for (size_t m = 0; m < n; m++)
+        if (std::min(a[m]->level, b[m]->level) != level) return c->fail(HEC_E_INVAL, "batched MulRelin needs a common level");
+    out.assign(n, nullptr);
+    auto bail = [&](int e) { for (hec_ct *o : out) hec_ct_free(c, o); out.assign(n, nullptr); return e; };
+    for (size_t m = 0; m < n; m++)
+        if ((rc = hec_ct_alloc(c, level, a[m]->scale * b[m]->scale, &out[m]))) return bail(rc);
+    if ((rc = reserve(c, n * (decomp_limbs(c, level) + ks_limbs(c, level) + 3 * (size_t)L)))) return bail(rc);
+    std::vector<u64 *> c2(n), d0(n), d1(n);
+    std::vector<TensorJob> tj;
+    for (size_t m = 0; m < n; m++) {
+        c2[m] = c->scratch(L); d0[m] = c->scratch(L); d1[m] = c->scratch(L);
+        for (int i = 0; i < L; i++)
+            tj.push_back({a[m]->limb(0, i), a[m]->limb(1, i), b[m]->limb(0, i), b[m]->limb(1, i), out[m]->limb(0, i), out[m]->limb(1, i),
+                          c2[m] + (size_t)i * HEC_N, mform(c->hm[i].rmod, c->q(i)), i});
+    }
+    for (size_t off = 0; off < tj.size(); off += HEC_TNJOBS) {
+        int k = (int)std::min<size_t>(HEC_TNJOBS, tj.size() - off);
         TensorJobs J;
-        for (int k = 0; k < n; k++) {
-            int i = off + k;
-            J.j[k] = {a->limb(0, i), a->limb(1, i), b->limb(0, i), b->limb(1, i), o->limb(0, i), o->limb(1, i),
-                      c2 + (size_t)i * HEC_N, mform(c->hm[i].rmod, c->q(i)), i};
-        }
-        k_tensor<<<dim3(32, n), 256, 0, c->stream>>>(J, c->dmods);
+        for (int i = 0; i < k; i++) J.j[i] = tj[off + i];
+        k_tensor<<<dim3(32, k), 256, 0, c->stream>>>(J, c->dmods);
         c->launches += 1;
     }
     if ((rc = check_launch(c, "tensor"))) return bail(rc);
+    std::vector<const u64 *> src(c2.begin(), c2.end());
     std::vector<Decomp> dc;
-    if ((rc = decompose_many(c, level, {c2}, dc))) return bail(rc);
-    if ((rc = keyswitch_many(c, level, dc, {&it->second}, {d0}, {d1}))) return bail(rc);
+    if ((rc = decompose_many(c, level, src, dc))) return bail(rc);
+    std::vector<const SwKey *> keys(n, &it->second);
+    if ((rc = keyswitch_many(c, level, dc, keys, d0, d1))) return bail(rc);
     std::vector<EwJob> add;
-    for (int i = 0; i < L; i++) {
-        add.push_back(ewjob(o->limb(0, i), d0 + (size_t)i * HEC_N, o->limb(0, i), i));
-        add.push_back(ewjob(o->limb(1, i), d1 + (size_t)i * HEC_N, o->limb(1, i), i));
-    }
+    for (size_t m = 0; m < n; m++)
+        for (int i = 0; i < L; i++) {
+            add.push_back(ewjob(out[m]->limb(0, i), d0[m] + (size_t)i * HEC_N, out[m]->limb(0, i), i));
+            add.push_back(ewjob(out[m]->limb(1, i), d1[m] + (size_t)i * HEC_N, out[m]->limb(1, i), i));
+        }
     if ((rc = launch_ew<EW_ADD>(c, add))) return bail(rc);
-    *out = o;
+    return HEC_OK;
+}
+extern "C" int hec_mul_relin_new(hec_ctx *c, const hec_ct *a, const hec_ct *b, hec_ct **out) {
+    if (!c || !a || !b || !out) return HEC_E_INVAL;
+    cudaSetDevice(c->device);
+    std::vector<hec_ct *> o;
+    int rc = hec_mul_relin_many(c, {a}, {b}, o);
+    if (rc) return rc;
+    *out = o[0];
     return HEC_OK;
 }
 

@@ -322,6 +322,14 @@ def test_evaluate_poly_and_eval_relu_level15_alpha5():
             g0, g1 = res.download()
             assert res.level == ref.level == 5 and res.scale == ref.scale == PR.SCALE * PR.SCALE, alpha
             assert np.array_equal(g0, ref.c0) and np.array_equal(g1, ref.c1), alpha
+        # the batched form (the loop over ct_boots[ul], eval.go:470-476): three different ciphertexts in one call
+        bs = [Ct(synth.uniform_limbs(71 + 2 * t, Q, N), synth.uniform_limbs(72 + 2 * t, Q, N), PR.SCALE) for t in range(2)] + [a]
+        outs = c.evalReLUMany([c.upload_ct(b.c0, b.c1, PR.SCALE) for b in bs], 0.1, PR.SCALE)
+        for b, r in zip(bs, outs):
+            ref = o.eval_relu(b, 0.1, rlk, PR.SCALE)
+            g0, g1 = r.download()
+            assert r.level == ref.level and r.scale == ref.scale
+            assert np.array_equal(g0, ref.c0) and np.array_equal(g1, ref.c1)
         low = c.upload_ct(a.c0[:3], a.c1[:3], PR.SCALE)
         with pytest.raises(hec.HecError) as e:  # checkEnoughLevels
             c.evalReLU(low, 0.0, PR.SCALE)

@@ -218,6 +218,29 @@ def evalop_case(logN, Q, P, level, rots):
     return rec
 
 
+def pre_conv_bl_case(logN=8, in_wid=4, ker_wid=3):
+    """main.preConv_BL (conv.go:120-143): the k^2 hoisted rotations i*in_wid + j of the baseline convolution,
+    set 7, level 1, alpha = 2 (the evalConv_BN_BL_test shape)"""
+    N, Q, P, level = 1 << logN, PR.Q_SET7[:2], PR.P_PACK_BL, 1
+    h = ker_wid // 2
+    rots = [i * in_wid + j for i in range(-h, h + 1) for j in range(-h, h + 1)]
+    gal = {r: pow(5, r % (N // 2) if r >= 0 else (r & (2 * N - 1)), 2 * N) for r in rots if r}
+    m = Machine()
+    keys = {g: np.stack([np.stack([synth.uniform_limbs(9500 + 17 * (r % 997) + k, list(Q) + list(P), N) for k in range(2)])])
+            for r, g in gal.items()}
+    params, ev = m.new_evaluator(logN, Q, P, PR.SCALE, keys)
+    lim = lambda seed: [ints(l) for l in synth.uniform_limbs(seed, Q[:level + 1], N)]  # noqa: E731
+    ct = m.new_ct([lim(61), lim(62)], PR.SCALE)
+    res = m.call("main.preConv_BL", ev + [ct, in_wid, ker_wid, 0, 0, 0], max_steps=1 << 62)
+    ptr, ln = res[-3], res[-2]
+    outs = m.read_u64s(ptr, ln)
+    rec = {"logN": logN, "in_wid": in_wid, "ker_wid": ker_wid, "rotations": rots, "galois": {str(r): g for r, g in gal.items()},
+           "Q": ["%x" % q for q in Q], "P": ["%x" % p for p in P], "out": [digest_ct(m, o) for o in outs],
+           "interpreted_instructions": m.steps}
+    print("preConv_BL case: %d instructions" % m.steps, flush=True)
+    return rec
+
+
 # ---------------------------------------------------------------- evalReLU (SURVEY 8f rank 2)
 RELU_CASES = [("n5_alpha0", 5, 0.0, 15), ("n6_leaky0.1", 6, 0.1, 15), ("n5_level12", 5, 0.0, 12), ("n5_level8_too_low", 5, 0.0, 8)]
 
@@ -275,6 +298,7 @@ def main():
             new["relu"] = {name: relu_case(logN, alpha, level) for name, logN, alpha, level in RELU_CASES}
         if "evalops" in groups:
             new["evalops"] = {name: evalop_case(logN, Q, P, level, rots) for name, logN, Q, P, level, rots in EVALOP_CASES}
+            new["pre_conv_bl"] = pre_conv_bl_case()
         if "ring" in groups:
             new["ring"] = ring_cases()
         if "conv" in groups:

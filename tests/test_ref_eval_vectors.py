@@ -121,6 +121,25 @@ def test_baseline_path_evaluator_ops_match_reference_code(name):
         assert r2.level == level - 2 and dg(r2) == rec["rescale2"]
 
 
+def test_pre_conv_bl_matches_reference_main_code():
+    """main.preConv_BL (conv.go:120-143), interpreted: the k^2 hoisted rotations i*in_wid + j (negative steps and
+    the zero step included) of the baseline convolution == the oracle's rotations, in the reference's order"""
+    rec = REF["pre_conv_bl"]
+    Q, P = mods(rec)
+    N = 1 << rec["logN"]
+    o = Oracle(rec["logN"], Q, P)
+    ct = Ct(synth.uniform_limbs(61, Q, N), synth.uniform_limbs(62, Q, N), PR.SCALE)
+    h = rec["ker_wid"] // 2
+    assert rec["rotations"] == [i * rec["in_wid"] + j for i in range(-h, h + 1) for j in range(-h, h + 1)]
+    for r, d in zip(rec["rotations"], rec["out"]):
+        if r == 0:
+            assert dg(ct) == d
+            continue
+        assert o.galois_for_rotation(r) == rec["galois"][str(r)]
+        key = np.stack([np.stack([synth.uniform_limbs(9500 + 17 * (r % 997) + k, Q + P, N) for k in range(2)])])
+        assert dg(o.rotate(ct, r, key)) == d, r
+
+
 @pytest.mark.parametrize("name", sorted(REF["relu"]))
 def test_eval_relu_matches_reference_main_code(name):
     """main.evalReLU (conv.go:435-480; three EvaluatePoly + AddConstNew + DropLevel + Mul + Relinearize), interpreted

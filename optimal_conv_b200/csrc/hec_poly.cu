@@ -15,6 +15,20 @@ extern "C" int hec_drop_level(hec_ctx *c, hec_ct *ct, int levels) {
     return HEC_OK;
 }
 
+// MulByPow2(ct, pow2, ct) (L:ckks/evaluator.go MulByPow2 -> ring.MulByPow2Lvl): every coefficient times 2^pow2 mod q_i,
+// scale unchanged (eval.go:476: the ReLU output is scaled back by 2^pow)
+extern "C" int hec_mul_by_pow2(hec_ctx *c, hec_ct *ct, int pow2) {
+    if (!c || !ct || pow2 < 0) return c ? c->fail(HEC_E_INVAL, "mul_by_pow2 args") : HEC_E_INVAL;
+    cudaSetDevice(c->device);
+    std::vector<EwJob> jobs;
+    for (int i = 0; i <= ct->level; i++) {
+        u64 q = c->q(i), k = 1 % q;
+        for (int b = 0; b < pow2; b++) k = (u64)(((u128)k * 2) % q);
+        for (int p = 0; p < 2; p++) jobs.push_back(ewjob(ct->limb(p, i), nullptr, ct->limb(p, i), i, mform(k, q)));
+    }
+    return launch_ew<EW_MULSCALAR>(c, jobs);
+}
+
 // AddConst(ct, c, ct) for a real constant (L:ckks/evaluator.go AddConst): the NTT of a constant polynomial is that
 // constant in every slot, so c0[j] += scaleUpExact(c, ct.Scale, q_i) for all j; c1 is untouched.  Batch form.
 static int add_const_many(hec_ctx *c, const std::vector<hec_ct *> &cts, double constant) {

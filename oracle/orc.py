@@ -221,6 +221,14 @@ class Oracle:
         r = int(x + 0.5) % q
         return q - r if neg else r
 
+    def mul_by_pow2(self, ct, pow2):
+        """MulByPow2(ct, pow2, ct) (ring.MulByPow2Lvl): coefficients times 2^pow2 mod q_i, scale unchanged"""
+        k = np.array([pow(2, pow2, self.Q[i]) for i in range(ct.level + 1)], dtype=np.uint64)
+        o0, o1 = np.empty_like(ct.c0), np.empty_like(ct.c1)
+        self.L.orc_mul_const(self.h, ct.level, _p(np.ascontiguousarray(ct.c0)), _p(k), _p(o0))
+        self.L.orc_mul_const(self.h, ct.level, _p(np.ascontiguousarray(ct.c1)), _p(k), _p(o1))
+        return Ct(o0, o1, ct.scale)
+
     def drop_level(self, ct, levels):
         return Ct(ct.c0[:ct.level + 1 - levels], ct.c1[:ct.level + 1 - levels], ct.scale)
 

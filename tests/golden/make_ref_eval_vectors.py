@@ -197,6 +197,11 @@ def evalop_case(logN, Q, P, level, rots):
                 out = {"a": A, "b": B, "new": Cc}[alias]
                 m.call(CKKS + "(*evaluator)." + op, [e, ict, A, ict, B, out])
                 rec["addsub_scaled"]["%s:%s:%s" % (op, tag, alias)] = digest_ct(m, out)
+    # MulByPow2(ct, 6, ct), in place as eval.go:476 calls it.  (Out of place the fork's ring.MulByPow2Lvl reads the
+    # un-MForm'ed input and returns x * 2^n * 2^-64; the reference never does that, and neither does hec_mul_by_pow2.)
+    p2 = m.new_ct([lim(61), lim(62)], PR.SCALE)
+    m.call(CKKS + "(*evaluator).MulByPow2", [e, p2, 6, p2])
+    rec["mul_by_pow2_6"] = digest_ct(m, p2)
     # Add(ct, pt, ct) at equal scales (eval.go:130,258 guard equality before adding)
     sum_ct = m.new_ct([lim(61), lim(62)], PR.SCALE)
     m.call(CKKS + "(*evaluator).Add", [e, ict, sum_ct, ipt, pt, sum_ct])

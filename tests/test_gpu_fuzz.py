@@ -60,6 +60,10 @@ def test_fuzz_evaluator_ops(trial):
         mp = c.MulNew(A, c.upload_pt(pt, PR.SCALE))
         mref = o.mul_pt(a, pt, PR.SCALE)
         assert eq(mp, mref), ("mul_pt", Q, P, level)
+        p2 = int(rng.integers(1, 40))
+        c.MulByPow2(mp, p2)
+        mref = o.mul_by_pow2(mref, p2)
+        assert eq(mp, mref), ("mul_by_pow2", Q, P, level, p2)
         const = float(rng.uniform(-3, 3))
         c.MultByConst(mp, const)
         assert eq(mp, o.mul_const(mref, const)), ("mult_by_const", Q, P, level, const)

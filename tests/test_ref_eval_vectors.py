@@ -113,6 +113,7 @@ def test_baseline_path_evaluator_ops_match_reference_code(name):
         op, tag, _ = key.split(":")
         r = o.add_matched(Ct(ct.c0, ct.c1, scales[tag][0]), Ct(ct2.c0, ct2.c1, scales[tag][1]), sub=(op == "Sub"))
         assert dg(r) == d, key
+    assert dg(o.mul_by_pow2(ct, 6)) == rec["mul_by_pow2_6"]
     assert dg(o.add_pt(ct, pt)) == rec["add_pt"]
     assert rec["rescale_err"] is False
     assert dg(o.rescale(Ct(ct.c0, ct.c1, PR.SCALE * float(Q[level])), PR.SCALE)) == rec["rescale"]

@@ -277,7 +277,14 @@ def run_side_workload(args):
         unit = "baseline conv calls/s"
         name = "evalConv_BN_BL_test interval (eval.go:108-131), B=%d (w=%d), k=%d, level 1, alpha=2: %d hoisted + %d full rotations, %d MulNew" % (
             B, w_, k, k * k - 1, max_batch - 1, max_batch * k * k)
-        alg = None
+        # algorithmic limbs (SURVEY.md 8d per-op figures; L = 2 limbs, alpha = 2, beta = 1): the input ciphertext;
+        # per hoisted rotation its key slice 2*beta*(L+alpha) and its output 2L; per tap the rotated ciphertext 2L and
+        # the plaintext L; per output channel group the partial sum 2L written, then (but for the first) a full
+        # rotation of it: c1 L + key + out 2L + c0 L; the bias L and the result 2L
+        L_, ks_ = 2, 2 * 1 * (2 + 2)
+        limbs = 2 * L_ + (k * k - 1) * (ks_ + 2 * L_) + max_batch * k * k * 3 * L_ + max_batch * 2 * L_ \
+            + (max_batch - 1) * (L_ + ks_ + 2 * L_ + L_) + L_ + 2 * L_
+        alg = limbs * LIMB
         if args.cpu_sample > 0:
             from oracle.orc import Ct, Oracle
             o = Oracle(PR.LOGN, Q, P)

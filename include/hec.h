@@ -123,6 +123,10 @@ int hec_add_const(hec_ctx *ctx, hec_ct *ct, double c);
 int hec_mult_by_int_and_add(hec_ctx *ctx, const hec_ct *ct, int64_t c, hec_ct *out);
 int hec_evaluate_poly(hec_ctx *ctx, const hec_ct *ct, const double *coeffs, int n, double target_scale,
                       double eval_scale, hec_ct **out);
+/* EvaluateCheby(ct, cheby, target_scale): coefficients in the Chebyshev basis on [-1, 1] (the sine evaluation of the
+ * bootstrapper, L:ckks/bootstrap.go evaluateCheby, calls it after its own change of variable) */
+int hec_evaluate_cheby(hec_ctx *ctx, const hec_ct *ct, const double *coeffs, int n, double target_scale,
+                       double eval_scale, hec_ct **out);
 int hec_eval_relu(hec_ctx *ctx, const hec_ct *ct, double alpha, double eval_scale, hec_ct **out);
 /* the loop `for ul: ct_boots[ul] = evalReLU(...)` of eval.go:470-476 as one call: n ciphertexts of a common level and
  * scale, every step one launch sequence for the whole batch */

@@ -67,9 +67,10 @@ extern "C" int hec_mult_by_int_and_add(hec_ctx *c, const hec_ct *ct, int64_t k, 
     return mult_int_add_many(c, {ct}, k, {out});
 }
 
-// Add(a, b, a) for a batch whose a's share one scale and whose b's share one scale (receiver == first operand):
+// Add / Sub(a, b, a) for a batch whose a's share one scale and whose b's share one scale (receiver == first operand):
 // evaluateInPlace's scale matching, one launch for the scale-up and one for the add
-static int add_inplace_many(hec_ctx *c, const std::vector<hec_ct *> &a, const std::vector<const hec_ct *> &b) {
+template <int OP>
+static int addsub_inplace_many(hec_ctx *c, const std::vector<hec_ct *> &a, const std::vector<const hec_ct *> &b) {
     size_t n = a.size();
     int level = std::min(a[0]->level, b[0]->level), L = level + 1, rc;
     double sa = a[0]->scale, sb = b[0]->scale;
@@ -107,9 +108,12 @@ static int add_inplace_many(hec_ctx *c, const std::vector<hec_ct *> &a, const st
     for (size_t m = 0; m < n; m++)
         for (int p = 0; p < 2; p++)
             for (int i = 0; i < L; i++) jobs.push_back(ewjob(a[m]->limb(p, i), xb[(m * 2 + p) * L + i], a[m]->limb(p, i), i));
-    if ((rc = launch_ew<EW_ADD>(c, jobs))) return rc;
+    if ((rc = launch_ew<OP>(c, jobs))) return rc;
     for (size_t m = 0; m < n; m++) { a[m]->level = level; a[m]->scale = std::max(sa, sb); }
     return HEC_OK;
+}
+static int add_inplace_many(hec_ctx *c, const std::vector<hec_ct *> &a, const std::vector<const hec_ct *> &b) {
+    return addsub_inplace_many<EW_ADD>(c, a, b);
 }
 
 namespace {
@@ -118,6 +122,7 @@ typedef std::vector<CtP> CtV; // one logical ciphertext of the algorithm = a bat
 struct PolyEval {
     hec_ctx *c;
     double eval_scale;
+    bool cheby = false; // EvaluateCheby: T_n = 2 T_a T_b - T_|a-b| (computePowerBasisCheby), splitCoeffsCheby
     int rc = HEC_OK;
     std::map<int, CtV> C;
     struct Poly { std::vector<double> co; int max_deg; bool lead; int degree() const { return (int)co.size() - 1; } };
@@ -152,18 +157,32 @@ struct PolyEval {
         if (C.count(n)) return true;
         int a = (n + 1) / 2, b = n >> 1;
         if (!power(a) || !power(b)) return false;
+        if (cheby && a != b && !power(a - b)) return false;
         CtV r = mul_relin(C[a], C[b]);
         if (r.empty() || (rc = hec_rescale_many(c, raw(r), eval_scale))) return false;
+        if (cheby) {
+            if ((rc = add_inplace_many(c, raw(r), craw(r)))) return false;                       // 2 T_a T_b
+            if (a == b) rc = add_const_many(c, raw(r), -1.0);                                    // - T_0
+            else rc = addsub_inplace_many<EW_SUB>(c, raw(r), craw(C[a - b]));                    // - T_(a-b)
+            if (rc) return false;
+        }
         C[n] = r;
         return true;
     }
-    static void split(const Poly &p, int sp, Poly &q, Poly &r) {
+    void split(const Poly &p, int sp, Poly &q, Poly &r) const {
         r.co.assign(p.co.begin(), p.co.begin() + sp);
         r.max_deg = p.max_deg == p.degree() ? sp - 1 : p.max_deg - (p.degree() - sp + 1);
         r.lead = false;
         q.co.assign(p.co.begin() + sp, p.co.end());
         q.max_deg = p.max_deg;
         q.lead = p.lead;
+        if (cheby) // p = q T_sp + r with T_i T_sp = (T_(sp+i) + T_(sp-i)) / 2
+            for (int i = sp + 1; i <= p.degree(); i++) {
+                volatile double twice = 2 * p.co[i];
+                q.co[i - sp] = twice;
+                volatile double diff = r.co[sp - (i - sp)] - p.co[i];
+                r.co[sp - (i - sp)] = diff;
+            }
     }
     CtV from_basis(double ts, const Poly &p) {
         size_t n = C[1].size();
@@ -261,8 +280,8 @@ static hec_ct *release(CtP &p) {
     return o;
 }
 static int evaluate_poly_many(hec_ctx *c, const std::vector<const hec_ct *> &cts, const double *coeffs, int n, double target_scale,
-                              double eval_scale, std::vector<hec_ct *> &outs) {
-    PolyEval E{c, eval_scale};
+                              double eval_scale, std::vector<hec_ct *> &outs, bool cheby = false) {
+    PolyEval E{c, eval_scale, cheby};
     CtV r = E.run(cts, coeffs, n, target_scale);
     if (r.empty()) return E.rc ? E.rc : HEC_E_INVAL;
     outs.clear();
@@ -279,6 +298,19 @@ extern "C" int hec_evaluate_poly(hec_ctx *c, const hec_ct *ct, const double *coe
     cudaSetDevice(c->device);
     std::vector<hec_ct *> o;
     int rc = evaluate_poly_many(c, {ct}, coeffs, n, target_scale, eval_scale, o);
+    if (rc) return rc;
+    *out = o[0];
+    return HEC_OK;
+}
+
+// EvaluateCheby(ct, cheby, targetScale) (L:ckks/polynomial_evaluation.go): coeffs are the coefficients in the Chebyshev
+// basis T_0..T_(n-1) on [-1, 1] (the change of variable to [a, b] is the caller's, as in the reference's bootstrapper)
+extern "C" int hec_evaluate_cheby(hec_ctx *c, const hec_ct *ct, const double *coeffs, int n, double target_scale,
+                                  double eval_scale, hec_ct **out) {
+    if (!c || !ct || !coeffs || n < 2 || !out) return c ? c->fail(HEC_E_INVAL, "evaluate_cheby args") : HEC_E_INVAL;
+    cudaSetDevice(c->device);
+    std::vector<hec_ct *> o;
+    int rc = evaluate_poly_many(c, {ct}, coeffs, n, target_scale, eval_scale, o, true);
     if (rc) return rc;
     *out = o[0];
     return HEC_OK;

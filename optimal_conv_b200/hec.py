@@ -26,7 +26,7 @@ SYMBOLS = [
     "hec_ct_copy_new", "hec_ct_level", "hec_ct_scale", "hec_ct_set_scale", "hec_ct_free", "hec_swk_upload",
     "hec_swk_drop", "hec_mul_pt_new", "hec_mult_by_const", "hec_rescale", "hec_set_scale", "hec_add", "hec_add_new",
     "hec_sub_new", "hec_add_pt", "hec_rlk_upload", "hec_mul_relin_new", "hec_sub", "hec_drop_level", "hec_mul_by_pow2", "hec_add_const",
-    "hec_mult_by_int_and_add", "hec_evaluate_poly", "hec_eval_relu", "hec_eval_relu_many", "hec_rotate_gal", "hec_rotate_new", "hec_rotate_hoisted", "hec_galois_for_rotation",
+    "hec_mult_by_int_and_add", "hec_evaluate_poly", "hec_evaluate_cheby", "hec_eval_relu", "hec_eval_relu_many", "hec_rotate_gal", "hec_rotate_new", "hec_rotate_hoisted", "hec_galois_for_rotation",
     "hec_ntt", "hec_keyswitch", "hec_moddown", "hec_conv_then_pack", "hec_conv_bl", "hec_ext_ctxt", "hec_keep_ctxt", "hec_plan_create", "hec_plan_run",
     "hec_plan_run_host", "hec_plan_submit_host", "hec_plan_wait", "hec_plan_span_begin", "hec_plan_span_end_ms",
     "hec_plan_profile", "hec_plan_destroy",
@@ -102,6 +102,7 @@ def lib():
     L.hec_add_const.argtypes = [vp, vp, C.c_double]
     L.hec_mult_by_int_and_add.argtypes = [vp, vp, C.c_int64, vp]
     L.hec_evaluate_poly.argtypes = [vp, vp, C.POINTER(C.c_double), C.c_int, C.c_double, C.c_double, C.POINTER(vp)]
+    L.hec_evaluate_cheby.argtypes = [vp, vp, C.POINTER(C.c_double), C.c_int, C.c_double, C.c_double, C.POINTER(vp)]
     L.hec_eval_relu.argtypes = [vp, vp, C.c_double, C.c_double, C.POINTER(vp)]
     L.hec_eval_relu_many.argtypes = [vp, C.POINTER(vp), C.c_int, C.c_double, C.c_double, C.POINTER(vp)]
     L.hec_mul_relin_new.argtypes = [vp, vp, vp, C.POINTER(vp)]
@@ -278,6 +279,12 @@ class Context:
         arr = (C.c_double * len(coeffs))(*coeffs)
         h = vp()
         self._chk(self.L.hec_evaluate_poly(self.h, ct.h, arr, len(coeffs), target_scale, eval_scale, C.byref(h)))
+        return Ciphertext(self, h)
+
+    def EvaluateCheby(self, ct, coeffs, target_scale, eval_scale):
+        arr = (C.c_double * len(coeffs))(*coeffs)
+        h = vp()
+        self._chk(self.L.hec_evaluate_cheby(self.h, ct.h, arr, len(coeffs), target_scale, eval_scale, C.byref(h)))
         return Ciphertext(self, h)
 
     def evalReLU(self, ct, alpha, eval_scale):

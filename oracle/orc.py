@@ -272,9 +272,10 @@ class Oracle:
         r.scale = max(a.scale, b.scale)
         return r
 
-    def evaluate_poly(self, ct, coeffs, target_scale, rlk, eval_scale):
+    def evaluate_poly(self, ct, coeffs, target_scale, rlk, eval_scale, cheby=False):
         """EvaluatePoly (L:ckks/polynomial_evaluation.go: computePowerBasis, recurse, splitCoeffs,
-        evaluatePolyFromPowerBasis).  coeffs: real coefficients, index = degree.  eval_scale = params.Scale()."""
+        evaluatePolyFromPowerBasis) and, with cheby=True, EvaluateCheby (computePowerBasisCheby: T_n = 2 T_a T_b -
+        T_|a-b|; splitCoeffsCheby).  coeffs: real coefficients, index = degree.  eval_scale = params.Scale()."""
         Q = self.Q
         deg = len(coeffs) - 1
         log_degree = deg.bit_length()
@@ -288,7 +289,12 @@ class Oracle:
                 a, b = (n + 1) // 2, n >> 1
                 power(a)
                 power(b)
+                if cheby and a != b:
+                    power(a - b)
                 C[n] = self.rescale(self.mul_relin(C[a], C[b], rlk), eval_scale)
+                if cheby:
+                    C[n] = self.add_matched(C[n], C[n])                      # 2 T_a T_b
+                    C[n] = self.add_const(C[n], -1.0) if a == b else self.add_matched(C[n], C[a - b], sub=True)
 
         for i in range(2, 1 << log_split):
             power(i)
@@ -304,8 +310,12 @@ class Oracle:
                 return len(self.c) - 1
 
         def split(p, sp):
-            r = P(p.c[:sp], sp - 1 if p.max_deg == p.degree else p.max_deg - (p.degree - sp + 1), False)
-            q = P(p.c[sp:], p.max_deg, p.lead)
+            r = P(list(p.c[:sp]), sp - 1 if p.max_deg == p.degree else p.max_deg - (p.degree - sp + 1), False)
+            q = P(list(p.c[sp:]), p.max_deg, p.lead)
+            if cheby:   # p = q T_sp + r with T_i T_sp = (T_(sp+i) + T_(sp-i)) / 2
+                for i in range(sp + 1, p.degree + 1):
+                    q.c[i - sp] = 2 * p.c[i]
+                    r.c[sp - (i - sp)] -= p.c[i]
             return q, r
 
         def from_basis(ts, p):

@@ -274,6 +274,41 @@ def relu_case(logN, alpha, level):
     return rec
 
 
+CHEBY_CASES = [("deg63_level15", 63, 15), ("deg30_level15", 30, 15), ("deg31_level10", 31, 10), ("deg7_level15", 7, 15)]
+
+
+def cheby_coeffs(deg):
+    rng = np.random.default_rng(1000 + deg)
+    co = [float(x) for x in rng.uniform(-1, 1, deg + 1)]
+    co[2] = co[5] = 0.0
+    return co
+
+
+def cheby_case(deg, level, logN=5):
+    """ckks.(*evaluator).EvaluateCheby (L:ckks/polynomial_evaluation.go) with seeded real Chebyshev coefficients
+    (degree 63 is the bootstrapper's SinDeg), first 16 moduli of set 6, alpha = 5"""
+    N = 1 << logN
+    Q, P = PR.Q_SET6[:16], PR.P_ALL
+    m = Machine()
+    beta_full = (len(Q) + len(P) - 1) // len(P)
+    rlk = np.stack([np.stack([synth.uniform_limbs(8000 + 10 * d + k, list(Q) + list(P), N) for k in range(2)]) for d in range(beta_full)])
+    params, ev = m.new_evaluator(logN, Q, P, PR.SCALE, {}, rlk)
+    lim = lambda seed: [ints(l) for l in synth.uniform_limbs(seed, Q[:level + 1], N)]  # noqa: E731
+    ct = m.new_ct([lim(61), lim(62)], PR.SCALE)
+    co = cheby_coeffs(deg)
+    carr = m.alloc(16 * (deg + 1))
+    for i, c in enumerate(co):
+        m.write_u64s(carr + 16 * i, [f2b(c), 0])                      # complex128{re, im}
+    cheb = m.alloc(72)                                                 # ChebyshevInterpolation{Poly{maxDeg, coeffs, lead}, a, b}
+    m.write_u64s(cheb, [deg, carr, deg + 1, deg + 1, 1, f2b(-1.0), 0, f2b(1.0), 0])
+    res = m.call(CKKS + "(*evaluator).EvaluateCheby", [ev[1], ct, cheb, f2b(PR.SCALE), 0, 0, 0], max_steps=1 << 62)
+    assert not (res[-2] or res[-1])
+    rec = {"logN": logN, "degree": deg, "level": level, "Q": ["%x" % q for q in Q], "P": ["%x" % p for p in P],
+           "out": digest_ct(m, res[-3]), "interpreted_instructions": m.steps}
+    print("EvaluateCheby case degree=%d level=%d: %d instructions" % (deg, level, m.steps), flush=True)
+    return rec
+
+
 SMALL_CONV = [
     # name, logN, B, norm, seed, out_scale, Q, P
     ("n8_B4", 8, 4, 1, 3, PR.SCALE, PR.Q_SET6[:2], PR.P_PACK),
@@ -301,6 +336,7 @@ def main():
         groups = [g for g in ("relu", "evalops", "ring", "conv") if "--" + g in sys.argv] or ["relu", "evalops", "ring", "conv"]
         if "relu" in groups:
             new["relu"] = {name: relu_case(logN, alpha, level) for name, logN, alpha, level in RELU_CASES}
+            new["cheby"] = {name: cheby_case(deg, level) for name, deg, level in CHEBY_CASES}
         if "evalops" in groups:
             new["evalops"] = {name: evalop_case(logN, Q, P, level, rots) for name, logN, Q, P, level, rots in EVALOP_CASES}
             new["pre_conv_bl"] = pre_conv_bl_case()

@@ -316,6 +316,13 @@ def test_evaluate_poly_and_eval_relu_level15_alpha5():
         g0, g1 = res.download()
         assert res.level == ref.level == 12 and res.scale == ref.scale
         assert np.array_equal(g0, ref.c0) and np.array_equal(g1, ref.c1)
+        rng = np.random.default_rng(1063)   # EvaluateCheby, degree 63 (the bootstrapper's sine degree)
+        co = [float(x) for x in rng.uniform(-1, 1, 64)]
+        res = c.EvaluateCheby(A, co, PR.SCALE, PR.SCALE)
+        ref = o.evaluate_poly(a, co, PR.SCALE, rlk, PR.SCALE, cheby=True)
+        g0, g1 = res.download()
+        assert res.level == ref.level == 9 and res.scale == ref.scale
+        assert np.array_equal(g0, ref.c0) and np.array_equal(g1, ref.c1)
         for alpha in (0.0, 0.1):
             res = c.evalReLU(A, alpha, PR.SCALE)
             ref = o.eval_relu(a, alpha, rlk, PR.SCALE)

@@ -158,6 +158,25 @@ def test_eval_relu_matches_reference_main_code(name):
     assert dg(o.eval_relu(ct, rec["alpha"], rlk, PR.SCALE)) == rec["out"]
 
 
+def cheby_coeffs(deg):
+    rng = np.random.default_rng(1000 + deg)
+    co = [float(x) for x in rng.uniform(-1, 1, deg + 1)]
+    co[2] = co[5] = 0.0
+    return co
+
+
+@pytest.mark.parametrize("name", sorted(REF["cheby"]))
+def test_evaluate_cheby_matches_reference_code(name):
+    """ckks.(*evaluator).EvaluateCheby (interpreted; degree 63 = the bootstrapper's sine degree) == the oracle"""
+    rec = REF["cheby"][name]
+    Q, P = mods(rec)
+    N, level = 1 << rec["logN"], rec["level"]
+    o = Oracle(rec["logN"], Q, P)
+    rlk = np.stack([np.stack([synth.uniform_limbs(8000 + 10 * d + k, Q + P, N) for k in range(2)]) for d in range(o.beta_full)])
+    ct = Ct(synth.uniform_limbs(61, Q[:level + 1], N), synth.uniform_limbs(62, Q[:level + 1], N), PR.SCALE)
+    assert dg(o.evaluate_poly(ct, cheby_coeffs(rec["degree"]), PR.SCALE, rlk, PR.SCALE, cheby=True)) == rec["out"]
+
+
 FULL = sorted(REF.get("conv_full", {}))
 
 

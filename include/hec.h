@@ -119,6 +119,10 @@ int hec_mul_relin_new(hec_ctx *ctx, const hec_ct *a, const hec_ct *b, hec_ct **o
 int hec_sub(hec_ctx *ctx, const hec_ct *a, const hec_ct *b, hec_ct *out);
 int hec_drop_level(hec_ctx *ctx, hec_ct *ct, int levels);
 int hec_mul_by_pow2(hec_ctx *ctx, hec_ct *ct, int pow2); /* MulByPow2(ct, pow2, ct) (eval.go:476) */
+/* MultByi(ct, ct) (divide = 0) / DivByi(ct, ct) (divide = 1); Conjugate(ct, out): the key for galEl 2N-1
+ * (GaloisElementForRowRotation) must have been uploaded.  Building blocks of CoeffsToSlots / SlotsToCoeffs. */
+int hec_mult_by_i(hec_ctx *ctx, hec_ct *ct, int divide);
+int hec_conjugate(hec_ctx *ctx, const hec_ct *ct, hec_ct *out);
 int hec_add_const(hec_ctx *ctx, hec_ct *ct, double c);
 int hec_mult_by_int_and_add(hec_ctx *ctx, const hec_ct *ct, int64_t c, hec_ct *out);
 int hec_evaluate_poly(hec_ctx *ctx, const hec_ct *ct, const double *coeffs, int n, double target_scale,

@@ -51,6 +51,7 @@ void build_mod(HostMod &m, u64 q) {
         a = mulmod(a, psi, q);
         b = mulmod(b, psi_i, q);
     }
+    m.psi_half_mont = mform(tab[1], q);
     // device order: the 15 twiddles {ng*base + gi} of every `base`, in consumption order (hec_dev.cuh fwd4)
     m.psi.assign(N, make_ulonglong2(0, 0));
     m.psi_inv.assign(N, make_ulonglong2(0, 0));

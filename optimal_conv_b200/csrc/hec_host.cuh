@@ -32,6 +32,7 @@ inline u32 bitrev16(u32 x) {
 struct HostMod {
     u64 q = 0, qinv = 0, rmod = 0, gen = 0;
     u64 ninv_w = 0, ninv_s = 0;          // N^-1 mod q and floor(N^-1 * 2^64 / q)
+    u64 psi_half_mont = 0;               // MForm(psi^(N/2)) = NttPsi[1] as Lattigo stores it (MultByi / DivByi)
     std::vector<ulonglong2> psi, psi_inv; // (w, floor(w * 2^64 / q)) at index brev(j), w = psi^(+-j)
 };
 void build_mod(HostMod &m, u64 q);

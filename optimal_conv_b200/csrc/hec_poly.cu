@@ -29,6 +29,28 @@ extern "C" int hec_mul_by_pow2(hec_ctx *c, hec_ct *ct, int pow2) {
     return launch_ew<EW_MULSCALAR>(c, jobs);
 }
 
+// MultByi(ct, ct) / DivByi(ct, ct) (L:ckks/evaluator.go): the product with X^(N/2) in the NTT domain -- the first
+// N/2 slots times psi^(N/2) (NttPsi[i][1]), the rest times its negative; DivByi the other way round
+extern "C" int hec_mult_by_i(hec_ctx *c, hec_ct *ct, int divide) {
+    if (!c || !ct) return HEC_E_INVAL;
+    cudaSetDevice(c->device);
+    std::vector<EwJob> jobs;
+    for (int i = 0; i <= ct->level; i++) {
+        u64 q = c->q(i), im = c->hm[i].psi_half_mont, neg = q - im;
+        for (int p = 0; p < 2; p++) {
+            EwJob j = ewjob(ct->limb(p, i), nullptr, ct->limb(p, i), i, divide ? neg : im);
+            j.s1 = divide ? im : neg;
+            jobs.push_back(j);
+        }
+    }
+    return launch_ew<EW_MULSCALAR_HALVES>(c, jobs);
+}
+// Conjugate(ct, out) (L:ckks/evaluator.go): permuteNTT with GaloisElementForRowRotation = 2N - 1
+extern "C" int hec_conjugate(hec_ctx *c, const hec_ct *ct, hec_ct *out) {
+    if (!c || !ct || !out) return HEC_E_INVAL;
+    return hec_rotate_gal(c, ct, 2ull * HEC_N - 1, out);
+}
+
 // AddConst(ct, c, ct) for a real constant (L:ckks/evaluator.go AddConst): the NTT of a constant polynomial is that
 // constant in every slot, so c0[j] += scaleUpExact(c, ct.Scale, q_i) for all j; c1 is untouched.  Batch form.
 static int add_const_many(hec_ctx *c, const std::vector<hec_ct *> &cts, double constant) {

@@ -25,7 +25,7 @@ SYMBOLS = [
     "hec_timer_stop_ms", "hec_launch_count", "hec_host_register", "hec_host_unregister", "hec_pt_upload", "hec_pt_free", "hec_ct_upload", "hec_ct_download",
     "hec_ct_copy_new", "hec_ct_level", "hec_ct_scale", "hec_ct_set_scale", "hec_ct_free", "hec_swk_upload",
     "hec_swk_drop", "hec_mul_pt_new", "hec_mult_by_const", "hec_rescale", "hec_set_scale", "hec_add", "hec_add_new",
-    "hec_sub_new", "hec_add_pt", "hec_rlk_upload", "hec_mul_relin_new", "hec_sub", "hec_drop_level", "hec_mul_by_pow2", "hec_add_const",
+    "hec_sub_new", "hec_add_pt", "hec_rlk_upload", "hec_mul_relin_new", "hec_sub", "hec_drop_level", "hec_mul_by_pow2", "hec_mult_by_i", "hec_conjugate", "hec_add_const",
     "hec_mult_by_int_and_add", "hec_evaluate_poly", "hec_evaluate_cheby", "hec_eval_relu", "hec_eval_relu_many", "hec_rotate_gal", "hec_rotate_new", "hec_rotate_hoisted", "hec_galois_for_rotation",
     "hec_ntt", "hec_keyswitch", "hec_moddown", "hec_conv_then_pack", "hec_conv_bl", "hec_ext_ctxt", "hec_keep_ctxt", "hec_plan_create", "hec_plan_run",
     "hec_plan_run_host", "hec_plan_submit_host", "hec_plan_wait", "hec_plan_span_begin", "hec_plan_span_end_ms",
@@ -99,6 +99,8 @@ def lib():
     L.hec_sub.argtypes = [vp, vp, vp, vp]
     L.hec_drop_level.argtypes = [vp, vp, C.c_int]
     L.hec_mul_by_pow2.argtypes = [vp, vp, C.c_int]
+    L.hec_mult_by_i.argtypes = [vp, vp, C.c_int]
+    L.hec_conjugate.argtypes = [vp, vp, vp]
     L.hec_add_const.argtypes = [vp, vp, C.c_double]
     L.hec_mult_by_int_and_add.argtypes = [vp, vp, C.c_int64, vp]
     L.hec_evaluate_poly.argtypes = [vp, vp, C.POINTER(C.c_double), C.c_int, C.c_double, C.c_double, C.POINTER(vp)]
@@ -268,6 +270,15 @@ class Context:
 
     def MulByPow2(self, ct, pow2):
         self._chk(self.L.hec_mul_by_pow2(self.h, ct.h, pow2))
+
+    def MultByi(self, ct):
+        self._chk(self.L.hec_mult_by_i(self.h, ct.h, 0))
+
+    def DivByi(self, ct):
+        self._chk(self.L.hec_mult_by_i(self.h, ct.h, 1))
+
+    def Conjugate(self, ct, out):
+        self._chk(self.L.hec_conjugate(self.h, ct.h, out.h))
 
     def AddConst(self, ct, c):
         self._chk(self.L.hec_add_const(self.h, ct.h, c))

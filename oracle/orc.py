@@ -221,6 +221,26 @@ class Oracle:
         r = int(x + 0.5) % q
         return q - r if neg else r
 
+    def mult_by_i(self, ct, divide=False):
+        """MultByi / DivByi (L:ckks/evaluator.go): product with X^(N/2) in the NTT domain = first half of the slots
+        times psi^(N/2) (NttPsi[i][1]), second half times its negative; DivByi swaps the two"""
+        lv, h = ct.level, self.N // 2
+        R = 1 << 64
+        k = np.array([int(self.table(0, i, 0)[1]) * pow(R, -1, self.Q[i]) % self.Q[i] for i in range(lv + 1)], dtype=np.uint64)
+        kn = np.array([self.Q[i] - int(k[i]) for i in range(lv + 1)], dtype=np.uint64)
+        out = []
+        for src in (ct.c0, ct.c1):
+            a, b = np.empty_like(src), np.empty_like(src)
+            self.L.orc_mul_const(self.h, lv, _p(np.ascontiguousarray(src)), _p(k), _p(a))
+            self.L.orc_mul_const(self.h, lv, _p(np.ascontiguousarray(src)), _p(kn), _p(b))
+            first, second = (b, a) if divide else (a, b)
+            out.append(np.concatenate([first[:, :h], second[:, h:]], axis=1))
+        return Ct(out[0], out[1], ct.scale)
+
+    def conjugate(self, ct, swk):
+        """Conjugate (L:ckks/evaluator.go): automorphism X -> X^(2N-1) (GaloisElementForRowRotation)"""
+        return self.rotate_gal(ct, 2 * self.N - 1, swk)
+
     def mul_by_pow2(self, ct, pow2):
         """MulByPow2(ct, pow2, ct) (ring.MulByPow2Lvl): coefficients times 2^pow2 mod q_i, scale unchanged"""
         k = np.array([pow(2, pow2, self.Q[i]) for i in range(ct.level + 1)], dtype=np.uint64)

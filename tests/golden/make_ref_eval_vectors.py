@@ -164,7 +164,7 @@ def evalop_case(logN, Q, P, level, rots):
     N = 1 << logN
     m = Machine()
     gals = [pow(5, r, 2 * N) for r in rots]
-    keys = evalop_keys(Q, P, N, gals)
+    keys = evalop_keys(Q, P, N, gals + [2 * N - 1])     # the last one: conjugation (GaloisElementForRowRotation)
     beta_full = (len(Q) + len(P) - 1) // len(P)
     rlk = np.stack([np.stack([synth.uniform_limbs(8000 + 10 * d + k, list(Q) + list(P), N) for k in range(2)]) for d in range(beta_full)])
     params, ev = m.new_evaluator(logN, Q, P, PR.SCALE, keys, rlk)
@@ -197,6 +197,12 @@ def evalop_case(logN, Q, P, level, rots):
                 out = {"a": A, "b": B, "new": Cc}[alias]
                 m.call(CKKS + "(*evaluator)." + op, [e, ict, A, ict, B, out])
                 rec["addsub_scaled"]["%s:%s:%s" % (op, tag, alias)] = digest_ct(m, out)
+    # MultByi / DivByi in place, ConjugateNew
+    for name in ("MultByi", "DivByi"):
+        t = m.new_ct([lim(61), lim(62)], PR.SCALE)
+        m.call(CKKS + "(*evaluator)." + name, [e, t, t])
+        rec[name] = digest_ct(m, t)
+    rec["conjugate"] = digest_ct(m, m.call(CKKS + "(*evaluator).ConjugateNew", [e, ct, 0])[-1])
     # MulByPow2(ct, 6, ct), in place as eval.go:476 calls it.  (Out of place the fork's ring.MulByPow2Lvl reads the
     # un-MForm'ed input and returns x * 2^n * 2^-64; the reference never does that, and neither does hec_mul_by_pow2.)
     p2 = m.new_ct([lim(61), lim(62)], PR.SCALE)

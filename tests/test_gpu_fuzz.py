@@ -45,6 +45,18 @@ def test_fuzz_evaluator_ops(trial):
         out = c.CopyNew(A)
         c.RotateGal(A, g, out)
         assert eq(out, o.rotate_gal(a, g, kg)), ("rotate_gal", Q, P, level, g)
+        # conjugation and the products with +-i
+        kc = key(seed + 250)
+        c.upload_swk(2 * N - 1, kc, level)
+        out = c.CopyNew(A)
+        c.Conjugate(A, out)
+        assert eq(out, o.conjugate(a, kc)), ("conjugate", Q, P, level)
+        c.MultByi(out)
+        iref = o.mult_by_i(o.conjugate(a, kc))
+        assert eq(out, iref), ("mult_by_i", Q, P, level)
+        c.DivByi(out)
+        c.DivByi(out)
+        assert eq(out, o.mult_by_i(o.mult_by_i(iref, divide=True), divide=True)), ("div_by_i", Q, P, level)
         # ct x ct, rescale, scale-matched add
         rlk = key(seed + 300)
         c.upload_rlk(rlk, level)

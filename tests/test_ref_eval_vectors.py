@@ -95,7 +95,9 @@ def test_baseline_path_evaluator_ops_match_reference_code(name):
     ct, ct2, pt = Ct(lim(61), lim(62), PR.SCALE), Ct(lim(63), lim(64), PR.SCALE), lim(65)
     assert [o.galois_for_rotation(r) for r in rec["rotations"]] == rec["galois"]
     keys = {g: np.stack([np.stack([synth.uniform_limbs(9000 + 131 * n + 10 * d + k, Q + P, N) for k in range(2)])
-                         for d in range(o.beta_full)]) for n, g in enumerate(rec["galois"])}
+                         for d in range(o.beta_full)]) for n, g in enumerate(rec["galois"] + [2 * N - 1])}
+    assert dg(o.mult_by_i(ct)) == rec["MultByi"] and dg(o.mult_by_i(ct, divide=True)) == rec["DivByi"]
+    assert dg(o.conjugate(ct, keys[2 * N - 1])) == rec["conjugate"]
     for r, g in zip(rec["rotations"], rec["galois"]):
         mine = dg(o.rotate(ct, r, keys[g]))
         assert mine == rec["hoisted"][str(r)], ("hoisted", r)

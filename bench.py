@@ -63,11 +63,16 @@ def kernel_alg_limbs(name, M, B, first_launch_only=False):
     return tot
 
 
-def ncu_traffic(kernel):
-    """dram bytes (read + write) of the first launch of `kernel` from the committed ncu --set full capture
-    (profiles/r01d_ncu_summary.csv: same command, default --cts 32), or None."""
+NCU_SUMMARY = {64: "r01f_ncu_summary.csv", 32: "r01d_ncu_summary.csv"}   # captures of `python bench.py [--cts 32]`
+
+
+def ncu_traffic(kernel, cts):
+    """dram bytes (read + write) of the first launch of `kernel` from the committed ncu --set full capture of the
+    same command (profiles/r01f_ncu_summary.csv: default --cts 64; r01d: --cts 32), or None."""
     import csv
-    p = os.path.join(ROOT, "profiles", "r01d_ncu_summary.csv")
+    if cts not in NCU_SUMMARY:
+        return None
+    p = os.path.join(ROOT, "profiles", NCU_SUMMARY[cts])
     try:
         rows = list(csv.reader(open(p)))
         h = rows[0]
@@ -319,7 +324,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--cts", type=int, default=32, help="independent input ciphertexts per step per GPU")
+    ap.add_argument("--cts", type=int, default=64, help="independent input ciphertexts per step per GPU")
     ap.add_argument("--batch", type=int, default=16, help="B: output channels packed per ciphertext")
     ap.add_argument("--ker", type=int, default=3, help="kernel width k (only changes the work of --workload conv_bl)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -489,10 +494,10 @@ def main():
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "roofline": {"bound": "hbm", "kernel": "k_conv" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": ncu_traffic("k_conv" + dom) if M == 32 and B == 16 else None,  # the ncu capture ran the default --cts 32
+                     "frac": achieved / peak, "traffic": ncu_traffic("k_conv" + dom, M) if B == 16 else None,
                      "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes_launch, "launch_ms": first_ms,
                      "launch": "first (largest) of %d launches per run" % n_l, "share_of_step": share,
-                     "traffic_source": "profiles/r01d_ncu_summary.csv (ncu --set full, same command)"},
+                     "traffic_source": "profiles/%s (ncu --set full, same command)" % NCU_SUMMARY.get(M, "-")},
         "roofline_int": {"bound": "integer multiply pipe (fmaheavy)", "modmuls_per_conv": modmuls,
                          "achieved": modmuls * (M * args.steps) / (ms_dev / 1e3), "peak": int_peak,
                          "unit": "modmul/s", "frac": modmuls * (M * args.steps) / (ms_dev / 1e3) / int_peak,

@@ -75,10 +75,12 @@ def ncu_traffic(kernel, cts):
     p = os.path.join(ROOT, "profiles", NCU_SUMMARY[cts])
     try:
         rows = list(csv.reader(open(p)))
-        h = rows[0]
+        h, units = rows[0], rows[1]                       # ncu scales units per column: the second row names them
+        mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        ir, iw = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
         for r in rows[2:]:
             if r[0].startswith(kernel + "("):
-                return (float(r[h.index("dram__bytes_read.sum")]) + float(r[h.index("dram__bytes_write.sum")])) * 1e6
+                return float(r[ir]) * mult[units[ir]] + float(r[iw]) * mult[units[iw]]
     except Exception:
         pass
     return None

@@ -612,15 +612,18 @@ void orc_decompose_digit(const orc_ctx *c, int level, int d, const uint64_t *c1n
     free(cinv);
 }
 
-void orc_keyswitch(const orc_ctx *c, int level, const uint64_t *c1, const uint64_t *swk,
-                   uint64_t *d0, uint64_t *d1) {
+/* SwitchKeysInPlaceNoModDown (L:rlwe/keyswitch.go:149-225): the inner product of the decomposition of c1 with
+ * the key, left in the basis Q||P -- a0Q, a1Q [(level+1)][N], a0P, a1P [nP][N], canonical residues (the
+ * reference's lazy accumulators end with Reduce).  Building block of the hoisted linear transforms. */
+void orc_keyswitch_nomoddown(const orc_ctx *c, int level, const uint64_t *c1, const uint64_t *swk,
+                             uint64_t *a0Q, uint64_t *a0P, uint64_t *a1Q, uint64_t *a1P) {
     int N = c->N, nQ = c->nQ, nP = c->nP, L = level + 1;
     int beta = (L + c->alpha - 1) / c->alpha;
     size_t polyw = (size_t)(nQ + nP) * N;
     u64 *cinv = (u64 *)malloc((size_t)L * N * 8);
     u64 *dQ = (u64 *)malloc((size_t)L * N * 8), *dP = (u64 *)malloc((size_t)nP * N * 8);
-    u64 *a0Q = (u64 *)calloc((size_t)L * N, 8), *a1Q = (u64 *)calloc((size_t)L * N, 8);
-    u64 *a0P = (u64 *)calloc((size_t)nP * N, 8), *a1P = (u64 *)calloc((size_t)nP * N, 8);
+    memset(a0Q, 0, (size_t)L * N * 8); memset(a1Q, 0, (size_t)L * N * 8);
+    memset(a0P, 0, (size_t)nP * N * 8); memset(a1P, 0, (size_t)nP * N * 8);
     for (int i = 0; i < L; i++) intt_core(&c->Q[i], N, c1 + (size_t)i * N, cinv + (size_t)i * N, 0);
     for (int d = 0; d < beta; d++) {
         decompose_digit(c, level, d, c1, cinv, dQ, dP);
@@ -644,9 +647,40 @@ void orc_keyswitch(const orc_ctx *c, int level, const uint64_t *c1, const uint64
             }
         }
     }
+    free(cinv); free(dQ); free(dP);
+}
+
+void orc_keyswitch(const orc_ctx *c, int level, const uint64_t *c1, const uint64_t *swk,
+                   uint64_t *d0, uint64_t *d1) {
+    int N = c->N, nP = c->nP, L = level + 1;
+    u64 *a0Q = (u64 *)malloc((size_t)L * N * 8), *a1Q = (u64 *)malloc((size_t)L * N * 8);
+    u64 *a0P = (u64 *)malloc((size_t)nP * N * 8), *a1P = (u64 *)malloc((size_t)nP * N * 8);
+    orc_keyswitch_nomoddown(c, level, c1, swk, a0Q, a0P, a1Q, a1P);
     orc_moddown(c, level, a0Q, a0P, d0);
     orc_moddown(c, level, a1Q, a1P, d1);
-    free(cinv); free(dQ); free(dP); free(a0Q); free(a1Q); free(a0P); free(a1P);
+    free(a0Q); free(a1Q); free(a0P); free(a1P);
+}
+
+/* out = (accumulate ? out : 0) + a * b * 2^-64 limb-wise over `nlimbs` limbs of ring 0 (Q) or 1 (P), canonical:
+ * MulCoeffsMontgomery[AndAdd] with b in Montgomery form (the diagonals of a PtDiagMatrix are stored that way) */
+void orc_poly_mulmont(const orc_ctx *c, int ring, int nlimbs, const uint64_t *a, const uint64_t *b, uint64_t *out, int accumulate) {
+    int N = c->N;
+    for (int i = 0; i < nlimbs; i++) {
+        const ring_mod *r = ring ? &c->P[i] : &c->Q[i];
+        for (int j = 0; j < N; j++) {
+            size_t k = (size_t)i * N + j;
+            u64 v = mred(a[k], b[k], r->q, r->qinv);
+            out[k] = accumulate ? cred(out[k] + v, r->q) : v;
+        }
+    }
+}
+/* out = a + b limb-wise over ring 0 / 1 */
+void orc_poly_add(const orc_ctx *c, int ring, int nlimbs, const uint64_t *a, const uint64_t *b, uint64_t *out) {
+    int N = c->N;
+    for (int i = 0; i < nlimbs; i++) {
+        const ring_mod *r = ring ? &c->P[i] : &c->Q[i];
+        for (int j = 0; j < N; j++) { size_t k = (size_t)i * N + j; out[k] = cred(a[k] + b[k], r->q); }
+    }
 }
 
 void orc_rotate_gal(const orc_ctx *c, int level, const uint64_t *ct0, const uint64_t *ct1,

@@ -81,6 +81,12 @@ void orc_sub(const orc_ctx *c, int level, const uint64_t *a, const uint64_t *b, 
  * d0,d1 [(level+1)][N]. */
 void orc_keyswitch(const orc_ctx *c, int level, const uint64_t *c1, const uint64_t *swk,
                    uint64_t *d0, uint64_t *d1);
+/* SwitchKeysInPlaceNoModDown: L:rlwe/keyswitch.go:149-225.  a0Q,a1Q [(level+1)][N]; a0P,a1P [nP][N] */
+void orc_keyswitch_nomoddown(const orc_ctx *c, int level, const uint64_t *c1, const uint64_t *swk,
+                             uint64_t *a0Q, uint64_t *a0P, uint64_t *a1Q, uint64_t *a1P);
+/* MulCoeffsMontgomery[AndAdd] / Add over nlimbs limbs of ring 0 (Q) or 1 (P): L:ring/ring_operations.go */
+void orc_poly_mulmont(const orc_ctx *c, int ring, int nlimbs, const uint64_t *a, const uint64_t *b, uint64_t *out, int accumulate);
+void orc_poly_add(const orc_ctx *c, int ring, int nlimbs, const uint64_t *a, const uint64_t *b, uint64_t *out);
 /* test hook: digit d of DecomposeSingleNTT (L:rlwe/keyswitch.go:121-141) */
 void orc_decompose_digit(const orc_ctx *c, int level, int d, const uint64_t *c1ntt, uint64_t *dQ, uint64_t *dP);
 /* ModDownSplitNTTPQ: L:ring/ring_basis_extension.go:247-291.  accQ [(level+1)][N],

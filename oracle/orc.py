@@ -64,6 +64,9 @@ def lib():
         L.orc_sub.argtypes = [C.c_void_p, C.c_int, u64p, u64p, u64p]
         L.orc_keyswitch.argtypes = [C.c_void_p, C.c_int, u64p, u64p, u64p, u64p]
         L.orc_decompose_digit.argtypes = [C.c_void_p, C.c_int, C.c_int, u64p, u64p, u64p]
+        L.orc_keyswitch_nomoddown.argtypes = [C.c_void_p, C.c_int, u64p, u64p, u64p, u64p, u64p, u64p]
+        L.orc_poly_mulmont.argtypes = [C.c_void_p, C.c_int, C.c_int, u64p, u64p, u64p, C.c_int]
+        L.orc_poly_add.argtypes = [C.c_void_p, C.c_int, C.c_int, u64p, u64p, u64p]
         L.orc_moddown.argtypes = [C.c_void_p, C.c_int, u64p, u64p, u64p]
         L.orc_rotate_gal.argtypes = [C.c_void_p, C.c_int, u64p, u64p, C.c_uint64, u64p, u64p, u64p]
         L.orc_conv_then_pack.restype = C.c_int
@@ -220,6 +223,90 @@ class Oracle:
         x = -n * value if neg else n * value
         r = int(x + 0.5) % q
         return q - r if neg else r
+
+    # ---- hoisted linear transform (CoeffsToSlots / SlotsToCoeffs of the bootstrapper; L:ckks/linear_transform.go) ----
+    def keyswitch_nomoddown(self, c1, swk):
+        c1 = np.ascontiguousarray(c1)
+        lv, nP = c1.shape[0] - 1, len(self.P)
+        a0Q, a1Q = np.empty_like(c1), np.empty_like(c1)
+        a0P, a1P = np.empty((nP, self.N), dtype=np.uint64), np.empty((nP, self.N), dtype=np.uint64)
+        self.L.orc_keyswitch_nomoddown(self.h, lv, _p(c1), _p(np.ascontiguousarray(swk)), _p(a0Q), _p(a0P), _p(a1Q), _p(a1P))
+        return a0Q, a0P, a1Q, a1P
+
+    def _mulmont(self, ring, a, b, out=None):
+        a, b = np.ascontiguousarray(a), np.ascontiguousarray(b[:a.shape[0]])
+        acc = out is not None
+        out = out if acc else np.empty_like(a)
+        self.L.orc_poly_mulmont(self.h, ring, a.shape[0], _p(a), _p(b), _p(out), int(acc))
+        return out
+
+    def _padd(self, ring, a, b):
+        a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+        out = np.empty_like(a)
+        self.L.orc_poly_add(self.h, ring, a.shape[0], _p(a), _p(b), _p(out))
+        return out
+
+    def linear_transform(self, ct, diags, n1, mat_level, mat_scale, keys):
+        """LinearTransform(ct, *PtDiagMatrix) -> MultiplyByDiagMatrixBSGS (L:ckks/linear_transform.go): baby-step
+        giant-step product of the slot vector with a matrix given by its non-zero diagonals.
+          diags: {k: (dQ [(level+1)][N], dP [nP][N])}, the plaintext diagonals over Q and P in Montgomery form
+                 (PtDiagMatrix.Vec), k in [0, slots); n1: PtDiagMatrix.N1 (power of two);
+          keys:  {rotation r: switching key for galEl 5^r} for the baby steps k mod n1 and giant steps n1*(k // n1).
+        Structure (every ModDown is a rounding step, so its place decides bits): the baby rotations stay in Q||P
+        (KeyswitchHoistedNoModDown + P*c0), each giant step's inner sum is ModDown'ed, key-switched again without
+        ModDown and accumulated in Q||P, one final ModDown; the un-rotated terms are added in Q."""
+        lv = min(ct.level, mat_level)
+        L, nP = lv + 1, len(self.P)
+        c0, c1 = np.ascontiguousarray(ct.c0[:L]), np.ascontiguousarray(ct.c1[:L])
+        index = {}
+        for k in sorted(diags):
+            index.setdefault(k // n1, []).append(k & (n1 - 1))
+        # rotateHoistedNoModDown: R_i = perm_i(KS_noModDown(c1, key_i) + (P c0, 0)) over Q||P
+        Pmod = 1
+        for p in self.P:
+            Pmod *= p
+        pc0 = np.empty_like(c0)
+        self.L.orc_mul_const(self.h, lv, _p(c0), _p(np.array([Pmod % self.Q[i] for i in range(L)], dtype=np.uint64)), _p(pc0))
+        rot = {}
+        for i in sorted({i for v in index.values() for i in v if i}):
+            a0Q, a0P, a1Q, a1P = self.keyswitch_nomoddown(c1, keys[i])
+            a0Q = self._padd(0, a0Q, pc0)
+            idx = self.permute_index(self.galois_for_rotation(i))
+            rot[i] = tuple(np.ascontiguousarray(x[:, idx]) for x in (a0Q, a0P, a1Q, a1P))
+        res0, res1 = np.zeros_like(c0), np.zeros_like(c1)
+        outer = None
+        for j in sorted(index):
+            acc = None
+            for i in index[j]:
+                if i == 0:
+                    continue
+                dQ, dP = diags[n1 * j + i]
+                terms = (self._mulmont(0, rot[i][0], dQ), self._mulmont(1, rot[i][1], dP),
+                         self._mulmont(0, rot[i][2], dQ), self._mulmont(1, rot[i][3], dP))
+                acc = terms if acc is None else tuple(self._padd(r, a, t) for r, a, t in zip((0, 1, 0, 1), acc, terms))
+            if j == 0:
+                if acc is not None:
+                    outer = acc if outer is None else tuple(self._padd(r, a, t) for r, a, t in zip((0, 1, 0, 1), outer, acc))
+                continue
+            if acc is not None:
+                t0, t1 = self.moddown(acc[0], acc[1]), self.moddown(acc[2], acc[3])
+            else:
+                t0, t1 = np.zeros_like(c0), np.zeros_like(c1)
+            if 0 in index[j]:
+                dQ = diags[n1 * j][0]
+                t0, t1 = self._mulmont(0, c0, dQ, t0), self._mulmont(0, c1, dQ, t1)
+            idx = self.permute_index(self.galois_for_rotation(n1 * j))
+            d = self.keyswitch_nomoddown(t1, keys[n1 * j])
+            res0 = self._padd(0, res0, np.ascontiguousarray(t0[:, idx]))
+            d = tuple(np.ascontiguousarray(x[:, idx]) for x in d)
+            outer = d if outer is None else tuple(self._padd(r, a, t) for r, a, t in zip((0, 1, 0, 1), outer, d))
+        if outer is not None:
+            res0 = self._padd(0, res0, self.moddown(outer[0], outer[1]))
+            res1 = self._padd(0, res1, self.moddown(outer[2], outer[3]))
+        if 0 in index.get(0, []):
+            dQ = diags[0][0]
+            res0, res1 = self._mulmont(0, c0, dQ, res0), self._mulmont(0, c1, dQ, res1)
+        return Ct(res0, res1, ct.scale * mat_scale)
 
     def mult_by_i(self, ct, divide=False):
         """MultByi / DivByi (L:ckks/evaluator.go): product with X^(N/2) in the NTT domain = first half of the slots

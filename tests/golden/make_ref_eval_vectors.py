@@ -3,7 +3,7 @@
 Run from the repo root in the build container (needs /root/reference/test_run, objdump, nm):
     python tests/golden/make_ref_eval_vectors.py            # small-N cases, ~2 min
     python tests/golden/make_ref_eval_vectors.py --only n8_B4      # regenerate one small conv case
-    python tests/golden/make_ref_eval_vectors.py --evalops | --relu | --ring | --conv  # regenerate one group
+    python tests/golden/make_ref_eval_vectors.py --evalops | --relu | --lt | --ring | --conv  # regenerate one group
     python tests/golden/make_ref_eval_vectors.py --full B4_norm1   # N = 2^16 golden config, ~1 h
 The prebuilt binary is never executed.  tests/golden/refmachine.py interprets the compiled routines of
 the Lattigo fork (ring / rlwe / ckks packages) and of package main from their disassembly; objects
@@ -315,6 +315,53 @@ def cheby_case(deg, level, logN=5):
     return rec
 
 
+# ---------------------------------------------------------------- hoisted linear transform (bootstrapping's CtoS / StoC)
+TYPE_PTR_PTDIAGMATRIX = 0x56b280   # runtime type descriptor of *ckks.PtDiagMatrix (LinearTransform's type switch, 0x5268ac)
+LT_CASES = [
+    # name, logN, Q, P, ct level, matrix level, N1, diagonals
+    ("mixed_a2", 5, PR.Q_SET6[:4], PR.P_ALL[:2], 3, 3, 4, [0, 1, 2, 3, 5, 8, 9, 12, 15]),
+    ("no_zero_diag_a2", 5, PR.Q_SET6[:4], PR.P_ALL[:2], 3, 3, 4, [1, 2, 4, 6, 11]),
+    ("giant_only_a2", 5, PR.Q_SET6[:4], PR.P_ALL[:2], 3, 3, 2, [0, 4, 8, 12]),
+    ("mixed_a5_matlevel4", 6, PR.Q_SET6[:6], PR.P_ALL[:5], 5, 4, 8, [0, 1, 3, 7, 8, 9, 17, 25, 31]),
+    ("baby_only_a1_set7", 5, PR.Q_SET7[:3], PR.P_ALL[:1], 2, 2, 4, [1, 2, 3]),
+]
+
+
+def lt_operands(Q, P, N, level, mat_level, n1, diags):
+    """seeded operands of one LinearTransform: rotation keys, ciphertext limbs, diagonals over Q and P"""
+    beta = (len(Q) + len(P) - 1) // len(P)
+    rots = sorted({d % n1 for d in diags if d % n1} | {(d // n1) * n1 for d in diags if d // n1})
+    keys = {r: np.stack([np.stack([synth.uniform_limbs(9000 + 131 * r + 10 * d + k, list(Q) + list(P), N) for k in range(2)])
+                         for d in range(beta)]) for r in rots}
+    ct = (synth.uniform_limbs(61, Q[:level + 1], N), synth.uniform_limbs(62, Q[:level + 1], N))
+    D = {d: (synth.uniform_limbs(7000 + d, Q[:mat_level + 1], N), synth.uniform_limbs(7500 + d, P, N)) for d in diags}
+    return keys, ct, D
+
+
+def lt_case(logN, Q, P, level, mat_level, n1, diags):
+    """ckks.(*evaluator).LinearTransform(ct, *PtDiagMatrix) -> MultiplyByDiagMatrixBSGS (L:ckks/linear_transform.go)"""
+    N = 1 << logN
+    m = Machine()
+    keys, (a0, a1), D = lt_operands(Q, P, N, level, mat_level, n1, diags)
+    params, ev = m.new_evaluator(logN, Q, P, PR.SCALE, {pow(5, r, 2 * N): k for r, k in keys.items()}, None)
+    ct = m.new_ct([[ints(l) for l in a0], [ints(l) for l in a1]], PR.SCALE)
+    vec = m.new_map(16)                               # Vec map[int][2]*ring.Poly, Montgomery + NTT form
+    for d, (dq, dp) in D.items():
+        pq, pp = m.new_poly([ints(l) for l in dq]), m.new_poly([ints(l) for l in dp])
+        for p in (pq, pp):
+            m.wb(p + 24, 1)
+            m.wb(p + 25, 1)
+        m.map_put(vec, d, [pq, pp])
+    mat = m.alloc(48)                                 # PtDiagMatrix{LogSlots, N1, Level, Scale, Vec, naive, isGaussian}
+    m.write_u64s(mat, [logN - 1, n1, mat_level, f2b(PR.SCALE), vec, 0])
+    res = m.call(CKKS + "(*evaluator).LinearTransform", [ev[1], ct, TYPE_PTR_PTDIAGMATRIX, mat, 0, 0, 0], max_steps=1 << 62)
+    outs = m.read_u64s(res[-3], res[-2])
+    rec = {"logN": logN, "Q": ["%x" % q for q in Q], "P": ["%x" % p for p in P], "level": level, "mat_level": mat_level,
+           "n1": n1, "diags": diags, "out": digest_ct(m, outs[0]), "interpreted_instructions": m.steps}
+    print("LinearTransform case %s N1=%d: %d instructions" % (diags, n1, m.steps), flush=True)
+    return rec
+
+
 SMALL_CONV = [
     # name, logN, B, norm, seed, out_scale, Q, P
     ("n8_B4", 8, 4, 1, 3, PR.SCALE, PR.Q_SET6[:2], PR.P_PACK),
@@ -339,10 +386,12 @@ def main():
         new["conv"] = {name: conv_case(logN, B, norm, seed, out_scale, Q2, P1)
                        for name, logN, B, norm, seed, out_scale, Q2, P1 in SMALL_CONV if name in sys.argv}
     else:
-        groups = [g for g in ("relu", "evalops", "ring", "conv") if "--" + g in sys.argv] or ["relu", "evalops", "ring", "conv"]
+        groups = [g for g in ("relu", "evalops", "lt", "ring", "conv") if "--" + g in sys.argv] or ["relu", "evalops", "lt", "ring", "conv"]
         if "relu" in groups:
             new["relu"] = {name: relu_case(logN, alpha, level) for name, logN, alpha, level in RELU_CASES}
             new["cheby"] = {name: cheby_case(deg, level) for name, deg, level in CHEBY_CASES}
+        if "lt" in groups:
+            new["linear_transform"] = {name: lt_case(*a) for name, *a in LT_CASES}
         if "evalops" in groups:
             new["evalops"] = {name: evalop_case(logN, Q, P, level, rots) for name, logN, Q, P, level, rots in EVALOP_CASES}
             new["pre_conv_bl"] = pre_conv_bl_case()

@@ -160,6 +160,26 @@ def test_eval_relu_matches_reference_main_code(name):
     assert dg(o.eval_relu(ct, rec["alpha"], rlk, PR.SCALE)) == rec["out"]
 
 
+@pytest.mark.parametrize("name", sorted(REF["linear_transform"]))
+def test_linear_transform_matches_reference_code(name):
+    """ckks.(*evaluator).LinearTransform -> MultiplyByDiagMatrixBSGS (interpreted): hoisted baby rotations kept in
+    Q||P, one ModDown per giant step, a second key switch without ModDown, one final ModDown == the oracle"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    rec = REF["linear_transform"][name]
+    Q, P = mods(rec)
+    N = 1 << rec["logN"]
+    o = Oracle(rec["logN"], Q, P)
+    beta = o.beta_full
+    n1, diags, level, ml = rec["n1"], rec["diags"], rec["level"], rec["mat_level"]
+    rots = sorted({d % n1 for d in diags if d % n1} | {(d // n1) * n1 for d in diags if d // n1})
+    keys = {r: np.stack([np.stack([synth.uniform_limbs(9000 + 131 * r + 10 * d + k, Q + P, N) for k in range(2)])
+                         for d in range(beta)]) for r in rots}
+    ct = Ct(synth.uniform_limbs(61, Q[:level + 1], N), synth.uniform_limbs(62, Q[:level + 1], N), PR.SCALE)
+    D = {d: (synth.uniform_limbs(7000 + d, Q[:ml + 1], N), synth.uniform_limbs(7500 + d, P, N)) for d in diags}
+    assert dg(o.linear_transform(ct, D, n1, ml, PR.SCALE, keys)) == rec["out"]
+
+
 def cheby_coeffs(deg):
     rng = np.random.default_rng(1000 + deg)
     co = [float(x) for x in rng.uniform(-1, 1, deg + 1)]

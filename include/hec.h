@@ -135,6 +135,17 @@ int hec_eval_relu(hec_ctx *ctx, const hec_ct *ct, double alpha, double eval_scal
 /* the loop `for ul: ct_boots[ul] = evalReLU(...)` of eval.go:470-476 as one call: n ciphertexts of a common level and
  * scale, every step one launch sequence for the whole batch */
 int hec_eval_relu_many(hec_ctx *ctx, const hec_ct *const *cts, int n, double alpha, double eval_scale, hec_ct **outs);
+/* ---- hoisted linear transform: LinearTransform(ct, *PtDiagMatrix) -> MultiplyByDiagMatrixBSGS
+ * (L:ckks/linear_transform.go), the core of the bootstrapper's CoeffsToSlots / SlotsToCoeffs.
+ * hec_ptdiag_upload takes PtDiagMatrix{LogSlots, N1, Level, Scale, Vec} as the reference's encoder builds it:
+ *   limbs[d*(level+1+nP) + t] = Vec[keys[d]][0].Coeffs[t] (t <= level), then Vec[keys[d]][1].Coeffs[..] (the P part),
+ *   NTT + Montgomery form; keys[d] in [0, 2^log_slots); n1 a power of two.  Rotation keys for the baby steps
+ *   k mod n1 and the giant steps n1*(k / n1) must have been uploaded (HEC_E_NOKEY otherwise). */
+typedef struct hec_ptdiag hec_ptdiag;
+int hec_ptdiag_upload(hec_ctx *ctx, int log_slots, int n1, int level, double scale, int ndiag, const int *keys,
+                      const uint64_t *const *limbs, hec_ptdiag **out);
+void hec_ptdiag_free(hec_ctx *ctx, hec_ptdiag *m);
+int hec_linear_transform(hec_ctx *ctx, const hec_ct *ct, const hec_ptdiag *m, hec_ct **out);
 /* RotateGal(ct, galEl, out)  (conv.go:291); out may alias ct */
 int hec_rotate_gal(hec_ctx *ctx, const hec_ct *ct, uint64_t galEl, hec_ct *out);
 /* RotateNew(ct, k)  (eval.go:123) */

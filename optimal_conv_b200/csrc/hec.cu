@@ -102,6 +102,10 @@ static void build_modup(const hec_ctx *c, ModupTab &T, const std::vector<int> &s
 } // namespace hec
 
 u64 *hec_ctx::scratch(size_t limbs) {
+    if (arena_top + limbs > arena_limbs) { // a sizing bug in the caller's reserve(): never hand out memory past the arena
+        fprintf(stderr, "libhec: scratch arena overrun (%zu + %zu > %zu limbs)\n", arena_top, limbs, arena_limbs);
+        abort();
+    }
     u64 *p = arena + arena_top * HEC_N;
     arena_top += limbs;
     return p;
@@ -738,19 +742,15 @@ static int decompose_many(hec_ctx *c, int level, const std::vector<const u64 *> 
 }
 // KeyswitchHoisted (L:rlwe/keyswitch.go:234-304) for item i: inner product of decomposition dc[i] (or the
 // shared dc[0]) with key[i], then mod-down.  d0[i], d1[i]: [L][N] outputs.  Scratch: (2 nP + 2 L) limbs per item.
-static int keyswitch_many(hec_ctx *c, int level, const std::vector<Decomp> &dc, const std::vector<const SwKey *> &key,
-                          const std::vector<u64 *> &d0, const std::vector<u64 *> &d1) {
+// SwitchKeysInPlaceNoModDown / KeyswitchHoistedNoModDown (L:rlwe/keyswitch.go:149-304): the inner product of
+// decomposition dc[i] (or the shared dc[0]) with key[i], left in Q||P: accQ[2i+p] [L][N], accP[2i+p] [nP][N], p = 0,1
+static int ks_mac_many(hec_ctx *c, int level, const std::vector<Decomp> &dc, const std::vector<const SwKey *> &key,
+                       const std::vector<u64 *> &accQ, const std::vector<u64 *> &accP) {
     int L = level + 1, nP = c->nP, W = L + nP, rc;
     size_t n = key.size();
     int beta = dc[0].beta;
     for (size_t i = 0; i < n; i++)
         if (key[i]->Lk < L || key[i]->ndig < beta) return c->fail(HEC_E_NOKEY, "switching key slice does not cover this level");
-    std::vector<u64 *> accQ, accP;
-    for (size_t i = 0; i < n; i++) {
-        u64 *ap = c->scratch(2 * (size_t)nP);
-        accQ.push_back(d0[i]); accP.push_back(ap);
-        accQ.push_back(d1[i]); accP.push_back(ap + (size_t)nP * HEC_N);
-    }
     for (int d = 0; d < beta; d++) {
         std::vector<EwJob> jobs;
         for (size_t i = 0; i < n; i++) {
@@ -768,6 +768,18 @@ static int keyswitch_many(hec_ctx *c, int level, const std::vector<Decomp> &dc, 
         rc = d == 0 ? launch_ew<EW_MULMONT>(c, jobs) : launch_ew<EW_MAC>(c, jobs);
         if (rc) return rc;
     }
+    return HEC_OK;
+}
+static int keyswitch_many(hec_ctx *c, int level, const std::vector<Decomp> &dc, const std::vector<const SwKey *> &key,
+                          const std::vector<u64 *> &d0, const std::vector<u64 *> &d1) {
+    int nP = c->nP, rc;
+    std::vector<u64 *> accQ, accP;
+    for (size_t i = 0; i < key.size(); i++) {
+        u64 *ap = c->scratch(2 * (size_t)nP);
+        accQ.push_back(d0[i]); accP.push_back(ap);
+        accQ.push_back(d1[i]); accP.push_back(ap + (size_t)nP * HEC_N);
+    }
+    if ((rc = ks_mac_many(c, level, dc, key, accQ, accP))) return rc;
     return moddown_many(c, level, accQ, accP);
 }
 static size_t ks_limbs(const hec_ctx *c, int level) { return 2 * c->nP + 2 * (size_t)(level + 1); } // per item, after decompose

@@ -1,0 +1,238 @@
+// hec_lt.cu -- hoisted baby-step giant-step linear transform on ciphertexts: LinearTransform(ct, *PtDiagMatrix) ->
+// MultiplyByDiagMatrixBSGS (L:ckks/linear_transform.go), the core of the bootstrapper's CoeffsToSlots /
+// SlotsToCoeffs.
+//
+// Every ModDown is a rounding step, so where it happens decides the output bits.  The reference's placement,
+// kept here: (1) the baby rotations R_i = sigma_i(KS_noModDown(c1; key_i) + (P c0, 0)) stay in Q||P (one shared
+// decomposition: KeyswitchHoistedNoModDown); (2) every giant step j != 0 forms sum_i diag[n1 j + i] * R_i in Q||P,
+// ModDown's it, adds the un-rotated term diag[n1 j] * ct in Q, key-switches the c1 part again WITHOUT ModDown and
+// accumulates sigma_(n1 j)(.) in Q||P (its c0 part is rotated and added in Q at once); (3) giant step 0 adds its
+// inner sum to the same Q||P accumulator; (4) one final ModDown; (5) + diag[0] * ct.
+// All steps are batched over rotations / giant steps: one launch sequence each.
+#include <set>
+
+struct hec_ptdiag {
+    int log_slots = 0, n1 = 0, level = 0, nP = 0;
+    double scale = 0;
+    std::map<int, int> slot;  // diagonal index -> position in buf
+    u64 *buf = nullptr;       // per diagonal: (level+1) Q limbs then nP P limbs, Montgomery + NTT form (PtDiagMatrix.Vec)
+    const u64 *q(int d, int l) const { return buf + ((size_t)slot.at(d) * (level + 1 + nP) + l) * HEC_N; }
+    const u64 *p(int d, int j) const { return buf + ((size_t)slot.at(d) * (level + 1 + nP) + level + 1 + j) * HEC_N; }
+};
+
+// PtDiagMatrix{LogSlots, N1, Level, Scale, Vec map[int][2]*ring.Poly} as the reference's encoder builds it
+// (EncodeDiagMatrixAtLvl): limbs[d * (level+1+nP) + t] = Vec[keys[d]][0].Coeffs[t] for t <= level, then
+// Vec[keys[d]][1].Coeffs[t - level - 1] (the P part).  keys[d] in [0, 2^log_slots), n1 a power of two.
+extern "C" int hec_ptdiag_upload(hec_ctx *c, int log_slots, int n1, int level, double scale, int nd, const int *keys,
+                                 const uint64_t *const *limbs, hec_ptdiag **out) {
+    if (!c || !keys || !limbs || !out || nd < 1 || n1 < 1 || (n1 & (n1 - 1)) || level < 0 || level >= c->nQ || c->nP == 0)
+        return c ? c->fail(HEC_E_INVAL, "ptdiag_upload args") : HEC_E_INVAL;
+    cudaSetDevice(c->device);
+    hec_ptdiag *m = new hec_ptdiag();
+    m->log_slots = log_slots; m->n1 = n1; m->level = level; m->nP = c->nP; m->scale = scale;
+    int W = level + 1 + c->nP;
+    if (cudaMalloc(&m->buf, (size_t)nd * W * HEC_N * sizeof(u64)) != cudaSuccess) { delete m; return c->fail(HEC_E_NOMEM, "cudaMalloc diagonals"); }
+    for (int d = 0; d < nd; d++) {
+        if (keys[d] < 0 || keys[d] >= (1 << log_slots) || m->slot.count(keys[d])) { cudaFree(m->buf); delete m; return c->fail(HEC_E_INVAL, "ptdiag_upload: bad diagonal index"); }
+        m->slot[keys[d]] = d;
+        for (int t = 0; t < W; t++)
+            if (cudaMemcpyAsync(m->buf + ((size_t)d * W + t) * HEC_N, limbs[(size_t)d * W + t], HEC_N * sizeof(u64), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) {
+                cudaFree(m->buf); delete m;
+                return c->fail(HEC_E_CUDA, "cudaMemcpyAsync diagonal");
+            }
+    }
+    HEC_CUDA(c, cudaStreamSynchronize(c->stream));
+    *out = m;
+    return HEC_OK;
+}
+extern "C" void hec_ptdiag_free(hec_ctx *c, hec_ptdiag *m) {
+    if (!m) return;
+    if (c) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
+    cudaFree(m->buf);
+    delete m;
+}
+
+extern "C" int hec_linear_transform(hec_ctx *c, const hec_ct *ct, const hec_ptdiag *m, hec_ct **out) {
+    if (!c || !ct || !m || !out) return HEC_E_INVAL;
+    cudaSetDevice(c->device);
+    const int level = std::min(ct->level, m->level), L = level + 1, nP = c->nP, W = L + nP, n1 = m->n1;
+    int rc;
+    // bsgsIndex: giant step j = k / n1, baby step i = k & (n1 - 1)
+    std::map<int, std::vector<int>> index;
+    std::set<int> babyset;
+    for (auto &kv : m->slot) {
+        index[kv.first / n1].push_back(kv.first & (n1 - 1));
+        if (kv.first & (n1 - 1)) babyset.insert(kv.first & (n1 - 1));
+    }
+    std::vector<int> babies(babyset.begin(), babyset.end()), giants, inner_js;
+    for (auto &kv : index) {
+        if (kv.first) giants.push_back(kv.first);
+        for (int i : kv.second)
+            if (i) { inner_js.push_back(kv.first); break; }
+    }
+    const size_t nb = babies.size(), ng = giants.size(), ni = inner_js.size();
+    auto find_key = [&](int r, const SwKey *&k) {
+        auto it = c->keys.find(hec_galois_for_rotation(c, r));
+        if (it == c->keys.end()) return c->fail(HEC_E_NOKEY, "rotation key for step " + std::to_string(r) + " missing");
+        k = &it->second;
+        return (int)HEC_OK;
+    };
+    std::vector<const SwKey *> bkeys(nb), gkeys(ng);
+    for (size_t b = 0; b < nb; b++) if ((rc = find_key(babies[b], bkeys[b]))) return rc;
+    for (size_t g = 0; g < ng; g++) if ((rc = find_key(n1 * giants[g], gkeys[g]))) return rc;
+
+    hec_ct *o = nullptr;
+    if ((rc = hec_ct_alloc(c, level, ct->scale * m->scale, &o))) return rc;
+    auto bail = [&](int e) { hec_ct_free(c, o); return e; };
+    size_t need = L + (1 + ng) * decomp_limbs(c, level) + (2 * nb + ni + 2 * ng + 1) * 2 * (size_t)W + ng * L
+                  + (2 * ng + 2) * (size_t)L /* mod-down scratch */ + 2 * ng * (size_t)L /* giant steps without an inner sum */ + 4;
+    if ((rc = reserve(c, need))) return bail(rc);
+    // a Q||P quadruple: Q0 [L], Q1 [L], P0 [nP], P1 [nP]
+    struct QP { u64 *q[2], *p[2]; };
+    auto alloc_qp = [&]() { QP x; x.q[0] = c->scratch(L); x.q[1] = c->scratch(L); x.p[0] = c->scratch(nP); x.p[1] = c->scratch(nP); return x; };
+    auto limb_of = [&](const QP &x, int poly, int t) { return t < L ? x.q[poly] + (size_t)t * HEC_N : x.p[poly] + (size_t)(t - L) * HEC_N; };
+    auto mod_of = [&](int t) { return t < L ? c->modQ(t) : c->modP(t - L); };
+
+    // ---- (1) baby rotations in Q||P
+    std::vector<QP> R(nb);
+    if (nb) {
+        u64 *pc0 = c->scratch(L);
+        std::vector<EwJob> ej;
+        for (int l = 0; l < L; l++) {
+            u64 q = c->q(l), pm = 1 % q;
+            for (int j = 0; j < nP; j++) pm = (u64)(((u128)pm * (c->q(c->modP(j)) % q)) % q);
+            ej.push_back(ewjob(ct->limb(0, l), nullptr, pc0 + (size_t)l * HEC_N, l, mform(pm, q)));   // MulScalarBigint(c0, P)
+        }
+        if ((rc = launch_ew<EW_MULSCALAR>(c, ej))) return bail(rc);
+        std::vector<Decomp> dc;
+        if ((rc = decompose_many(c, level, {ct->limb(1, 0)}, dc))) return bail(rc);
+        std::vector<QP> acc(nb);
+        std::vector<u64 *> aQ, aP;
+        for (size_t b = 0; b < nb; b++) {
+            acc[b] = alloc_qp(); R[b] = alloc_qp();
+            aQ.push_back(acc[b].q[0]); aP.push_back(acc[b].p[0]);
+            aQ.push_back(acc[b].q[1]); aP.push_back(acc[b].p[1]);
+        }
+        if ((rc = ks_mac_many(c, level, dc, bkeys, aQ, aP))) return bail(rc);
+        ej.clear();
+        std::vector<EwJob> perm;
+        for (size_t b = 0; b < nb; b++) {
+            u32 g = (u32)hec_galois_for_rotation(c, babies[b]);
+            for (int l = 0; l < L; l++) ej.push_back(ewjob(acc[b].q[0] + (size_t)l * HEC_N, pc0 + (size_t)l * HEC_N, acc[b].q[0] + (size_t)l * HEC_N, l));
+            for (int poly = 0; poly < 2; poly++)
+                for (int t = 0; t < W; t++) perm.push_back(ewjob(limb_of(acc[b], poly, t), nullptr, limb_of(R[b], poly, t), mod_of(t), 0, g));
+        }
+        if ((rc = launch_ew<EW_ADD>(c, ej))) return bail(rc);
+        if ((rc = launch_ew<EW_PERMUTE>(c, perm))) return bail(rc);
+    }
+    auto baby_pos = [&](int i) { return (size_t)(std::lower_bound(babies.begin(), babies.end(), i) - babies.begin()); };
+
+    // ---- (2a) inner sums of every giant step, all in one launch
+    std::map<int, QP> inner;
+    if (ni) {
+        std::vector<DotSpec> specs;
+        for (int j : inner_js) {
+            QP x = alloc_qp();
+            inner[j] = x;
+            for (int poly = 0; poly < 2; poly++)
+                for (int t = 0; t < W; t++) {
+                    DotSpec sp;
+                    for (int i : index[j]) {
+                        if (!i) continue;
+                        sp.a.push_back(limb_of(R[baby_pos(i)], poly, t));
+                        sp.b.push_back(t < L ? m->q(n1 * j + i, t) : m->p(n1 * j + i, t - L));
+                    }
+                    sp.out = limb_of(x, poly, t); sp.mod = mod_of(t);
+                    specs.push_back(sp);
+                }
+        }
+        if ((rc = launch_dot(c, specs))) return bail(rc);
+    }
+    // ---- (2b) per giant step: ModDown, un-rotated term, second key switch (no ModDown), rotate
+    std::vector<u64 *> t0(ng), t1(ng);
+    std::vector<QP> G(ng), GP(ng);
+    std::vector<u64 *> pt0(ng);
+    if (ng) {
+        std::vector<u64 *> mdQ, mdP;
+        for (size_t g = 0; g < ng; g++) {
+            int j = giants[g];
+            if (inner.count(j)) {
+                t0[g] = inner[j].q[0]; t1[g] = inner[j].q[1];
+                mdQ.push_back(t0[g]); mdP.push_back(inner[j].p[0]);
+                mdQ.push_back(t1[g]); mdP.push_back(inner[j].p[1]);
+            } else { // only the un-rotated diagonal in this giant step
+                t0[g] = c->scratch(L); t1[g] = c->scratch(L);
+                HEC_CUDA(c, cudaMemsetAsync(t0[g], 0, (size_t)L * HEC_N * sizeof(u64), c->stream));
+                HEC_CUDA(c, cudaMemsetAsync(t1[g], 0, (size_t)L * HEC_N * sizeof(u64), c->stream));
+            }
+        }
+        if (!mdQ.empty() && (rc = moddown_many(c, level, mdQ, mdP))) return bail(rc);
+        std::vector<EwJob> zt;
+        for (size_t g = 0; g < ng; g++) {
+            int j = giants[g];
+            if (std::find(index[j].begin(), index[j].end(), 0) == index[j].end()) continue;
+            for (int l = 0; l < L; l++) {
+                zt.push_back(ewjob(ct->limb(0, l), m->q(n1 * j, l), t0[g] + (size_t)l * HEC_N, l));
+                zt.push_back(ewjob(ct->limb(1, l), m->q(n1 * j, l), t1[g] + (size_t)l * HEC_N, l));
+            }
+        }
+        if (!zt.empty() && (rc = launch_ew<EW_MAC>(c, zt))) return bail(rc);
+        std::vector<const u64 *> src(t1.begin(), t1.end());
+        std::vector<Decomp> dc;
+        if ((rc = decompose_many(c, level, src, dc))) return bail(rc);
+        std::vector<u64 *> aQ, aP;
+        for (size_t g = 0; g < ng; g++) {
+            G[g] = alloc_qp(); GP[g] = alloc_qp(); pt0[g] = c->scratch(L);
+            aQ.push_back(G[g].q[0]); aP.push_back(G[g].p[0]);
+            aQ.push_back(G[g].q[1]); aP.push_back(G[g].p[1]);
+        }
+        if ((rc = ks_mac_many(c, level, dc, gkeys, aQ, aP))) return bail(rc);
+        std::vector<EwJob> perm;
+        for (size_t g = 0; g < ng; g++) {
+            u32 gal = (u32)hec_galois_for_rotation(c, n1 * giants[g]);
+            for (int l = 0; l < L; l++) perm.push_back(ewjob(t0[g] + (size_t)l * HEC_N, nullptr, pt0[g] + (size_t)l * HEC_N, l, 0, gal));
+            for (int poly = 0; poly < 2; poly++)
+                for (int t = 0; t < W; t++) perm.push_back(ewjob(limb_of(G[g], poly, t), nullptr, limb_of(GP[g], poly, t), mod_of(t), 0, gal));
+        }
+        if ((rc = launch_ew<EW_PERMUTE>(c, perm))) return bail(rc);
+    }
+    // ---- (3) + (4): the Q||P accumulator and its single ModDown
+    bool have_outer = ng > 0 || inner.count(0);
+    QP outer{};
+    if (have_outer) {
+        outer = alloc_qp();
+        std::vector<DotSpec> specs;
+        for (int poly = 0; poly < 2; poly++)
+            for (int t = 0; t < W; t++) {
+                DotSpec sp;
+                for (size_t g = 0; g < ng; g++) sp.a.push_back(limb_of(GP[g], poly, t));
+                if (inner.count(0)) sp.a.push_back(limb_of(inner[0], poly, t));
+                sp.out = limb_of(outer, poly, t); sp.mod = mod_of(t);
+                specs.push_back(sp);
+            }
+        if ((rc = launch_dot(c, specs))) return bail(rc);
+        if ((rc = moddown_many(c, level, {outer.q[0], outer.q[1]}, {outer.p[0], outer.p[1]}))) return bail(rc);
+    }
+    // ---- result: c0 = sum_j sigma_j(t0_j) + ModDown(outer0), c1 = ModDown(outer1); then (5) + diag[0] * ct
+    {
+        std::vector<DotSpec> specs;
+        for (int poly = 0; poly < 2; poly++)
+            for (int l = 0; l < L; l++) {
+                DotSpec sp;
+                if (poly == 0) for (size_t g = 0; g < ng; g++) sp.a.push_back(pt0[g] + (size_t)l * HEC_N);
+                if (have_outer) sp.a.push_back(outer.q[poly] + (size_t)l * HEC_N);
+                sp.out = o->limb(poly, l); sp.mod = l;
+                if (sp.a.empty()) HEC_CUDA(c, cudaMemsetAsync(sp.out, 0, HEC_N * sizeof(u64), c->stream));
+                else specs.push_back(sp);
+            }
+        if (!specs.empty() && (rc = launch_dot(c, specs))) return bail(rc);
+        if (m->slot.count(0)) {
+            std::vector<EwJob> zt;
+            for (int poly = 0; poly < 2; poly++)
+                for (int l = 0; l < L; l++) zt.push_back(ewjob(ct->limb(poly, l), m->q(0, l), o->limb(poly, l), l));
+            if ((rc = launch_ew<EW_MAC>(c, zt))) return bail(rc);
+        }
+    }
+    *out = o;
+    return HEC_OK;
+}

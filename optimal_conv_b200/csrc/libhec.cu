@@ -2,3 +2,4 @@
 #include "hec.cu"
 #include "hec_conv.cu"
 #include "hec_poly.cu"
+#include "hec_lt.cu"

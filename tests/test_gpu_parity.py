@@ -345,6 +345,42 @@ def test_evaluate_poly_and_eval_relu_level15_alpha5():
         c.close()
 
 
+@pytest.mark.parametrize("shape", [
+    ("mixed_a5_matlevel4", PR.Q_SET6[:6], PR.P_ALL, 5, 4, 8, [0, 1, 3, 7, 8, 9, 17, 25, 31]),
+    ("no_zero_diag_a2", PR.Q_SET6[:4], PR.P_ALL[:2], 3, 3, 4, [1, 2, 4, 6, 11]),
+    ("giant_only_a2", PR.Q_SET6[:4], PR.P_ALL[:2], 3, 3, 2, [0, 4, 8, 12]),
+    ("baby_only_a1_set7", PR.Q_SET7[:3], PR.P_ALL[:1], 2, 2, 4, [1, 2, 3]),
+    ("zero_diag_only", PR.Q_SET6[:3], PR.P_ALL[:1], 2, 2, 4, [0]),
+], ids=lambda s: s[0])
+def test_linear_transform_bsgs(shape):
+    """LinearTransform(ct, PtDiagMatrix) (hoisted BSGS) at N = 2^16 == the oracle, whose small-N
+    results for the same diagonal patterns are pinned against the reference's compiled MultiplyByDiagMatrixBSGS."""
+    _, Q, P, level, ml, n1, diags = shape
+    c, o = hec.Context(PR.LOGN, Q, P), Oracle(PR.LOGN, Q, P)
+    try:
+        rots = sorted({d % n1 for d in diags if d % n1} | {(d // n1) * n1 for d in diags if d // n1})
+        keys = {r: np.stack([np.stack([synth.uniform_limbs(9000 + 131 * r + 10 * d + k, Q + P, N) for k in range(2)])
+                             for d in range(o.beta_full)]) for r in rots}
+        a = Ct(synth.uniform_limbs(61, Q[:level + 1], N), synth.uniform_limbs(62, Q[:level + 1], N), PR.SCALE)
+        D = {d: (synth.uniform_limbs(7000 + d, Q[:ml + 1], N), synth.uniform_limbs(7500 + d, P, N)) for d in diags}
+        A = c.upload_ct(a.c0, a.c1, PR.SCALE)
+        mat = c.upload_ptdiag(PR.LOGN - 1, n1, ml, PR.SCALE, D)
+        if rots:
+            with pytest.raises(hec.HecError) as e:
+                c.LinearTransform(A, mat)
+            assert e.value.code == hec.HEC_E_NOKEY
+        for r, k in keys.items():
+            c.upload_swk(c.galois_for_rotation(r), k, level)
+        res = c.LinearTransform(A, mat)
+        ref = o.linear_transform(a, D, n1, ml, PR.SCALE, keys)
+        g0, g1 = res.download()
+        assert res.level == ref.level == min(level, ml) and res.scale == ref.scale == PR.SCALE * PR.SCALE
+        assert np.array_equal(g0, ref.c0) and np.array_equal(g1, ref.c1)
+        c.free_ptdiag(mat)
+    finally:
+        c.close()
+
+
 # ---------------------------------------------------------------- the conv path
 @pytest.mark.parametrize("cfg", common.GOLDEN_CONFIGS, ids=lambda c: c["name"])
 @pytest.mark.parametrize("flags", [hec.CONV_FUSED, hec.CONV_OPLEVEL], ids=["fused", "oplevel"])

@@ -146,6 +146,11 @@ int hec_ptdiag_upload(hec_ctx *ctx, int log_slots, int n1, int level, double sca
                       const uint64_t *const *limbs, hec_ptdiag **out);
 void hec_ptdiag_free(hec_ctx *ctx, hec_ptdiag *m);
 int hec_linear_transform(hec_ctx *ctx, const hec_ct *ct, const hec_ptdiag *m, hec_ct **out);
+/* CoeffsToSlots(vec, pDFTInv, eval) / SlotsToCoeffs(ct0, ct1, pDFT, eval) (L:ckks/bootstrap.go; the two halves of the
+ * split bootstrapping, BootstrappConv_CtoS / _StoC): chains of LinearTransform + Rescale over the factor matrices,
+ * then real / imaginary extraction by conjugation (needs the key of galEl 2N-1).  Full packing only. */
+int hec_coeffs_to_slots(hec_ctx *ctx, const hec_ct *ct, const hec_ptdiag *const *mats, int n, hec_ct **ct0, hec_ct **ct1);
+int hec_slots_to_coeffs(hec_ctx *ctx, const hec_ct *ct0, const hec_ct *ct1, const hec_ptdiag *const *mats, int n, hec_ct **out);
 /* RotateGal(ct, galEl, out)  (conv.go:291); out may alias ct */
 int hec_rotate_gal(hec_ctx *ctx, const hec_ct *ct, uint64_t galEl, hec_ct *out);
 /* RotateNew(ct, k)  (eval.go:123) */

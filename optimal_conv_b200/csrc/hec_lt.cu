@@ -236,3 +236,56 @@ extern "C" int hec_linear_transform(hec_ctx *c, const hec_ct *ct, const hec_ptdi
     *out = o;
     return HEC_OK;
 }
+
+// dft (L:ckks/bootstrap.go): vec = Rescale(LinearTransform(vec, M_k), scale before) over the factor matrices
+static int dft_chain(hec_ctx *c, const hec_ct *in, const hec_ptdiag *const *mats, int n, hec_ct **out) {
+    hec_ct *cur = nullptr;
+    int rc = HEC_OK;
+    for (int k = 0; k < n && !rc; k++) {
+        const hec_ct *src = cur ? cur : in;
+        double scale = src->scale;
+        hec_ct *nxt = nullptr;
+        rc = hec_linear_transform(c, src, mats[k], &nxt);
+        if (!rc) rc = hec_rescale(c, nxt, scale);
+        hec_ct_free(c, cur);
+        cur = nxt;
+        if (rc) { hec_ct_free(c, cur); cur = nullptr; }
+    }
+    if (rc) return rc;
+    if (!cur) return hec_ct_copy_new(c, in, out);
+    *out = cur;
+    return HEC_OK;
+}
+// CoeffsToSlots(vec, pDFTInv, eval) (L:ckks/bootstrap.go), full packing (LogSlots = LogN - 1): z = dft(vec);
+// ct0 = z + conj(z) (real parts), ct1 = (z - conj(z)) / i (imaginary parts).  Needs the conjugation key (galEl 2N-1).
+extern "C" int hec_coeffs_to_slots(hec_ctx *c, const hec_ct *ct, const hec_ptdiag *const *mats, int n, hec_ct **ct0, hec_ct **ct1) {
+    if (!c || !ct || !mats || n < 1 || !ct0 || !ct1) return c ? c->fail(HEC_E_INVAL, "coeffs_to_slots args") : HEC_E_INVAL;
+    cudaSetDevice(c->device);
+    if (mats[0]->log_slots != HEC_LOGN - 1) return c->fail(HEC_E_UNSUPPORTED, "sparse packing (LogSlots < LogN-1) is not implemented");
+    hec_ct *z = nullptr, *zc = nullptr, *re = nullptr, *im = nullptr;
+    int rc = dft_chain(c, ct, mats, n, &z);
+    if (!rc) rc = hec_ct_copy_new(c, z, &zc);
+    if (!rc) rc = hec_conjugate(c, z, zc);
+    if (!rc) rc = hec_add_new(c, z, zc, &re);
+    if (!rc) rc = hec_sub_new(c, z, zc, &im);
+    if (!rc) rc = hec_mult_by_i(c, im, 1);
+    hec_ct_free(c, z); hec_ct_free(c, zc);
+    if (rc) { hec_ct_free(c, re); hec_ct_free(c, im); return rc; }
+    *ct0 = re; *ct1 = im;
+    return HEC_OK;
+}
+// SlotsToCoeffs(ct0, ct1, pDFT, eval): dft(ct0 + i * ct1); ct1 may be NULL
+extern "C" int hec_slots_to_coeffs(hec_ctx *c, const hec_ct *ct0, const hec_ct *ct1, const hec_ptdiag *const *mats, int n, hec_ct **out) {
+    if (!c || !ct0 || !mats || n < 1 || !out) return c ? c->fail(HEC_E_INVAL, "slots_to_coeffs args") : HEC_E_INVAL;
+    cudaSetDevice(c->device);
+    hec_ct *sum = nullptr, *t = nullptr;
+    int rc = hec_ct_copy_new(c, ct0, &sum);
+    if (!rc && ct1) {
+        rc = hec_ct_copy_new(c, ct1, &t);
+        if (!rc) rc = hec_mult_by_i(c, t, 0);
+        if (!rc) rc = hec_add(c, sum, t, sum);
+    }
+    if (!rc) rc = dft_chain(c, sum, mats, n, out);
+    hec_ct_free(c, sum); hec_ct_free(c, t);
+    return rc;
+}

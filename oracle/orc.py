@@ -308,6 +308,27 @@ class Oracle:
             res0, res1 = self._mulmont(0, c0, dQ, res0), self._mulmont(0, c1, dQ, res1)
         return Ct(res0, res1, ct.scale * mat_scale)
 
+    def dft(self, ct, mats, keys):
+        """dft (L:ckks/bootstrap.go): the chain of LinearTransform + Rescale(back to the scale before) over the
+        factor matrices.  mats: [(diags, n1, level, scale)]"""
+        for diags, n1, ml, ms in mats:
+            s = ct.scale
+            ct = self.rescale(self.linear_transform(ct, diags, n1, ml, ms, keys), s)
+        return ct
+
+    def coeffs_to_slots(self, ct, mats, keys, key_conj):
+        """CoeffsToSlots (L:ckks/bootstrap.go), full packing: z = dft(ct); real part z + conj(z), imaginary part
+        (z - conj(z)) / i"""
+        z = self.dft(ct, mats, keys)
+        zc = self.conjugate(z, key_conj)
+        return self.add_matched(z, zc), self.mult_by_i(self.add_matched(z, zc, sub=True), divide=True)
+
+    def slots_to_coeffs(self, ct0, ct1, mats, keys):
+        """SlotsToCoeffs (L:ckks/bootstrap.go): dft(ct0 + i ct1)"""
+        if ct1 is not None:
+            ct0 = self.add_matched(ct0, self.mult_by_i(ct1))
+        return self.dft(ct0, mats, keys)
+
     def mult_by_i(self, ct, divide=False):
         """MultByi / DivByi (L:ckks/evaluator.go): product with X^(N/2) in the NTT domain = first half of the slots
         times psi^(N/2) (NttPsi[i][1]), second half times its negative; DivByi swaps the two"""

@@ -362,6 +362,63 @@ def lt_case(logN, Q, P, level, mat_level, n1, diags):
     return rec
 
 
+# ---------------------------------------------------------------- CoeffsToSlots / SlotsToCoeffs (the two halves of the split bootstrapping)
+DFT_MATS = [(4, [0, 1, 2, 3, 5, 8, 9, 12, 15], 5), (2, [0, 1, 4, 6, 11], 4)]   # (N1, diagonals, level) of the factor matrices
+DFT_Q, DFT_P, DFT_LOGN, DFT_LEVEL = PR.Q_SET6[:6], PR.P_ALL[:2], 5, 5
+
+
+def dft_operands(N):
+    Q, P = DFT_Q, DFT_P
+    beta = (len(Q) + len(P) - 1) // len(P)
+    rots = set()
+    for n1, diags, _ in DFT_MATS:
+        rots |= {d % n1 for d in diags if d % n1} | {(d // n1) * n1 for d in diags if d // n1}
+    key = lambda s: np.stack([np.stack([synth.uniform_limbs(s + 10 * d + k, list(Q) + list(P), N) for k in range(2)]) for d in range(beta)])  # noqa: E731
+    keys = {r: key(9000 + 131 * r) for r in sorted(rots)}
+    kconj = key(9900)
+    mats = []
+    for mi, (n1, diags, ml) in enumerate(DFT_MATS):
+        D = {d: (synth.uniform_limbs(7000 + 100 * mi + d, Q[:ml + 1], N), synth.uniform_limbs(7500 + 100 * mi + d, P, N)) for d in diags}
+        mats.append((D, n1, ml, float(Q[ml])))     # encoded at the scale of the level the matrix consumes
+    cts = [(synth.uniform_limbs(61 + 2 * t, Q[:DFT_LEVEL + 1], N), synth.uniform_limbs(62 + 2 * t, Q[:DFT_LEVEL + 1], N)) for t in range(2)]
+    return keys, kconj, mats, cts
+
+
+def dft_case():
+    """ckks.CoeffsToSlots(vec, pDFTInv, eval) and ckks.SlotsToCoeffs(ct0, ct1, pDFT, eval) (L:ckks/bootstrap.go) with two
+    seeded factor matrices, full packing"""
+    logN = DFT_LOGN
+    N = 1 << logN
+    m = Machine()
+    keys, kconj, mats, cts = dft_operands(N)
+    gk = {pow(5, r, 2 * N): k for r, k in keys.items()}
+    gk[2 * N - 1] = kconj
+    params, ev = m.new_evaluator(logN, DFT_Q, DFT_P, PR.SCALE, gk, None)
+    ptrs = []
+    for D, n1, ml, ms in mats:
+        vec = m.new_map(16)
+        for d, (dq, dp) in D.items():
+            pq, pp = m.new_poly([ints(l) for l in dq]), m.new_poly([ints(l) for l in dp])
+            for p in (pq, pp):
+                m.wb(p + 24, 1)
+                m.wb(p + 25, 1)
+            m.map_put(vec, d, [pq, pp])
+        mat = m.alloc(48)
+        m.write_u64s(mat, [logN - 1, n1, ml, f2b(ms), vec, 0])
+        ptrs.append(mat)
+    mk = lambda t: m.new_ct([[ints(l) for l in cts[t][0]], [ints(l) for l in cts[t][1]]], PR.SCALE)  # noqa: E731
+    res = m.call(CKKS + "CoeffsToSlots", [mk(0)] + m.slice_u64(ptrs) + ev + [0, 0], max_steps=1 << 62)
+    rec = {"logN": logN, "Q": ["%x" % q for q in DFT_Q], "P": ["%x" % p for p in DFT_P],
+           "coeffs_to_slots": [digest_ct(m, res[-2]), digest_ct(m, res[-1])]}
+    res = m.call(CKKS + "SlotsToCoeffs", [mk(0), mk(1)] + m.slice_u64(ptrs) + ev + [0], max_steps=1 << 62)
+    rec["slots_to_coeffs"] = digest_ct(m, res[-1])
+    res = m.call(CKKS + "SlotsToCoeffs", [mk(1), 0] + m.slice_u64(ptrs) + ev + [0], max_steps=1 << 62)
+    rec["slots_to_coeffs_real_only"] = digest_ct(m, res[-1])
+    rec["interpreted_instructions"] = m.steps
+    print("CoeffsToSlots / SlotsToCoeffs case: %d instructions" % m.steps, flush=True)
+    return rec
+
+
 SMALL_CONV = [
     # name, logN, B, norm, seed, out_scale, Q, P
     ("n8_B4", 8, 4, 1, 3, PR.SCALE, PR.Q_SET6[:2], PR.P_PACK),
@@ -392,6 +449,7 @@ def main():
             new["cheby"] = {name: cheby_case(deg, level) for name, deg, level in CHEBY_CASES}
         if "lt" in groups:
             new["linear_transform"] = {name: lt_case(*a) for name, *a in LT_CASES}
+            new["dft"] = dft_case()
         if "evalops" in groups:
             new["evalops"] = {name: evalop_case(logN, Q, P, level, rots) for name, logN, Q, P, level, rots in EVALOP_CASES}
             new["pre_conv_bl"] = pre_conv_bl_case()

@@ -381,6 +381,46 @@ def test_linear_transform_bsgs(shape):
         c.close()
 
 
+def test_coeffs_to_slots_and_slots_to_coeffs():
+    """CoeffsToSlots / SlotsToCoeffs (the linear halves of the split bootstrapping) with two factor matrices at
+    N = 2^16, alpha = 2 == the oracle's compositions (pinned at small N against the reference's compiled code)."""
+    Q, P, level = PR.Q_SET6[:6], PR.P_ALL[:2], 5
+    specs = [(4, [0, 1, 2, 3, 5, 8, 9, 12, 15], 5), (2, [0, 1, 4, 6, 11], 4)]
+    c, o = hec.Context(PR.LOGN, Q, P), Oracle(PR.LOGN, Q, P)
+    try:
+        key = lambda s: np.stack([np.stack([synth.uniform_limbs(s + 10 * d + k, Q + P, N) for k in range(2)]) for d in range(o.beta_full)])  # noqa: E731
+        rots = set()
+        for n1, diags, _ in specs:
+            rots |= {d % n1 for d in diags if d % n1} | {(d // n1) * n1 for d in diags if d // n1}
+        keys = {r: key(9000 + 131 * r) for r in sorted(rots)}
+        kconj = key(9900)
+        for r, k in keys.items():
+            c.upload_swk(c.galois_for_rotation(r), k, level)
+        c.upload_swk(2 * N - 1, kconj, level)
+        mats, hm = [], []
+        for mi, (n1, diags, ml) in enumerate(specs):
+            D = {d: (synth.uniform_limbs(7000 + 100 * mi + d, Q[:ml + 1], N), synth.uniform_limbs(7500 + 100 * mi + d, P, N)) for d in diags}
+            mats.append((D, n1, ml, float(Q[ml])))
+            hm.append(c.upload_ptdiag(PR.LOGN - 1, n1, ml, float(Q[ml]), D))
+        a = Ct(synth.uniform_limbs(61, Q, N), synth.uniform_limbs(62, Q, N), PR.SCALE)
+        b = Ct(synth.uniform_limbs(63, Q, N), synth.uniform_limbs(64, Q, N), PR.SCALE)
+        A, B = c.upload_ct(a.c0, a.c1, PR.SCALE), c.upload_ct(b.c0, b.c1, PR.SCALE)
+        g0, g1 = c.CoeffsToSlots(A, hm)
+        r0, r1 = o.coeffs_to_slots(a, mats, keys, kconj)
+        for g, r in ((g0, r0), (g1, r1)):
+            x0, x1 = g.download()
+            assert g.level == r.level == 3 and g.scale == r.scale
+            assert np.array_equal(x0, r.c0) and np.array_equal(x1, r.c1)
+        for second, bref in ((B, b), (None, None)):
+            g = c.SlotsToCoeffs(A, second, hm)
+            r = o.slots_to_coeffs(a, bref, mats, keys)
+            x0, x1 = g.download()
+            assert g.level == r.level and g.scale == r.scale
+            assert np.array_equal(x0, r.c0) and np.array_equal(x1, r.c1)
+    finally:
+        c.close()
+
+
 # ---------------------------------------------------------------- the conv path
 @pytest.mark.parametrize("cfg", common.GOLDEN_CONFIGS, ids=lambda c: c["name"])
 @pytest.mark.parametrize("flags", [hec.CONV_FUSED, hec.CONV_OPLEVEL], ids=["fused", "oplevel"])

@@ -180,6 +180,23 @@ def test_linear_transform_matches_reference_code(name):
     assert dg(o.linear_transform(ct, D, n1, ml, PR.SCALE, keys)) == rec["out"]
 
 
+def test_coeffs_to_slots_and_slots_to_coeffs_match_reference_code():
+    """ckks.CoeffsToSlots / ckks.SlotsToCoeffs (interpreted; the linear halves of BootstrappConv_CtoS / _StoC):
+    chains of LinearTransform + Rescale, conjugation, real / imaginary split == the oracle"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_ref_eval_vectors as G
+    rec = REF["dft"]
+    N = 1 << rec["logN"]
+    o = Oracle(rec["logN"], G.DFT_Q, G.DFT_P)
+    keys, kconj, mats, cts = G.dft_operands(N)
+    a, b = Ct(*cts[0], PR.SCALE), Ct(*cts[1], PR.SCALE)
+    c0, c1 = o.coeffs_to_slots(a, mats, keys, kconj)
+    assert [dg(c0), dg(c1)] == rec["coeffs_to_slots"]
+    assert dg(o.slots_to_coeffs(a, b, mats, keys)) == rec["slots_to_coeffs"]
+    assert dg(o.slots_to_coeffs(b, None, mats, keys)) == rec["slots_to_coeffs_real_only"]
+
+
 def cheby_coeffs(deg):
     rng = np.random.default_rng(1000 + deg)
     co = [float(x) for x in rng.uniform(-1, 1, deg + 1)]

@@ -151,6 +151,23 @@ int hec_linear_transform(hec_ctx *ctx, const hec_ct *ct, const hec_ptdiag *m, he
  * then real / imaginary extraction by conjugation (needs the key of galEl 2N-1).  Full packing only. */
 int hec_coeffs_to_slots(hec_ctx *ctx, const hec_ct *ct, const hec_ptdiag *const *mats, int n, hec_ct **ct0, hec_ct **ct1);
 int hec_slots_to_coeffs(hec_ctx *ctx, const hec_ct *ct0, const hec_ct *ct1, const hec_ptdiag *const *mats, int n, hec_ct **out);
+/* ---- split bootstrapping, first half: btp.BootstrappConv_CtoS(ct) (eval.go:447-459; the fork's ckks/bootstrap.go).
+ * hec_btp_params carries the fields of ckks.Bootstrapper the routine reads (names as in the reference's struct):
+ * the Go host builds its Bootstrapper as before and passes them, with the pDFTInv factor matrices uploaded through
+ * hec_ptdiag_upload.  Needs the rotation keys of the matrices, the conjugation key and the relinearisation key.
+ * Returns the two halves (real / imaginary parts after the sine evaluation) and the constant the reference returns.
+ * hec_mod_up: Bootstrapper.modUp (level 0 -> top level, centred lift). */
+typedef struct {
+    double prescale, postscale, sinescale, sqrt2pi, sc_fac; /* Bootstrapper.prescale .. scFac */
+    double message_ratio;                                   /* BootstrappingParameters.MessageRatio */
+    double params_scale;                                    /* params.Scale() */
+    int sin_type, sin_rescal, arcsine_deg;                  /* SinType (1 = Cos1, 2 = Cos2), SinRescal, ArcSineDeg (must be 0) */
+    const uint64_t *sine_qi; int n_sine_qi;                 /* SineEvalModuli.Qi */
+    const double *cheby; int n_cheby; double cheby_a, cheby_b; /* sineEvalPoly: Chebyshev coefficients (real), interval */
+} hec_btp_params;
+int hec_mod_up(hec_ctx *ctx, const hec_ct *ct, hec_ct **out);
+int hec_bootstrap_ctos(hec_ctx *ctx, const hec_ct *ct, const hec_btp_params *bp, const hec_ptdiag *const *pdftinv, int nmat,
+                       hec_ct **ct0, hec_ct **ct1, double *constant);
 /* RotateGal(ct, galEl, out)  (conv.go:291); out may alias ct */
 int hec_rotate_gal(hec_ctx *ctx, const hec_ct *ct, uint64_t galEl, hec_ct *out);
 /* RotateNew(ct, k)  (eval.go:123) */

@@ -85,7 +85,8 @@ enum {
     EW_PERMUTE,     // out[i] = a[index_g[i]]     (PermuteNTTWithIndexLvl)
     EW_COPY,
     EW_MULSCALAR_ADD, // out = out + a * s0 * R^-1  (MultByGaussianIntegerAndAdd with a real integer; s0 = MForm(c mod q))
-    EW_MULSCALAR_HALVES // out = a * (i < N/2 ? s0 : s1) * R^-1  (MultByi / DivByi: +-psi^(N/2) on the two halves)
+    EW_MULSCALAR_HALVES, // out = a * (i < N/2 ? s0 : s1) * R^-1  (MultByi / DivByi: +-psi^(N/2) on the two halves)
+    EW_CENTER_LIFT // out = (a > s1 ? a - q0 : a) mod q with s0 = q0 mod q, s1 = q0 >> 1  (Bootstrapper.modUp)
 };
 template <int OP>
 __global__ void __launch_bounds__(256) k_ew(EwJobs J, const ModC *__restrict__ mods) {
@@ -105,6 +106,7 @@ __global__ void __launch_bounds__(256) k_ew(EwJobs J, const ModC *__restrict__ m
         else if (OP == EW_PERMUTE) r = job.a[perm_index(i, job.g)];
         else if (OP == EW_MULSCALAR_ADD) r = addmod(job.out[i], mred(job.a[i], job.s0, q, qinv), q);
         else if (OP == EW_MULSCALAR_HALVES) r = mred(job.a[i], i < HEC_N / 2 ? job.s0 : job.s1, q, qinv);
+        else if (OP == EW_CENTER_LIFT) { u64 a = job.a[i]; r = mred(a, rmod, q, qinv); if (a > job.s1) r = submod(r, job.s0, q); }
         else r = job.a[i];
         job.out[i] = r;
     }

@@ -289,3 +289,123 @@ extern "C" int hec_slots_to_coeffs(hec_ctx *c, const hec_ct *ct0, const hec_ct *
     hec_ct_free(c, sum); hec_ct_free(c, t);
     return rc;
 }
+
+// =========================================================================================
+// Split bootstrapping, first half: BootstrappConv_CtoS of the fork's ckks/bootstrap.go (eval.go:447-459), restated
+// from the disassembly of the reference binary (0x506800) and checked against it through the oracle.
+// =========================================================================================
+// Bootstrapper.modUp (0x507400): the level-0 ciphertext's coefficients, centred around q0, re-expressed modulo every
+// q_i of the chain; back to the NTT domain.  Returns a new ciphertext at the top level.
+extern "C" int hec_mod_up(hec_ctx *c, const hec_ct *ct, hec_ct **out) {
+    if (!c || !ct || !out) return HEC_E_INVAL;
+    cudaSetDevice(c->device);
+    if (ct->level != 0) return c->fail(HEC_E_LEVEL, "modUp expects a level-0 ciphertext");
+    int top = c->nQ - 1, rc;
+    hec_ct *o = nullptr;
+    if ((rc = hec_ct_alloc(c, top, ct->scale, &o))) return rc;
+    auto bail = [&](int e) { hec_ct_free(c, o); return e; };
+    if ((rc = reserve(c, 2))) return bail(rc);
+    u64 *t = c->scratch(2);
+    std::vector<LimbJob> nj;
+    for (int p = 0; p < 2; p++) nj.push_back({ct->limb(p, 0), t + (size_t)p * HEC_N, 0, 0});
+    if ((rc = hec_launch_ntt(c, nj, true))) return bail(rc);
+    u64 q0 = c->q(0);
+    std::vector<EwJob> ej;
+    nj.clear();
+    for (int p = 0; p < 2; p++)
+        for (int i = 0; i <= top; i++) {
+            EwJob j = ewjob(t + (size_t)p * HEC_N, nullptr, o->limb(p, i), i, q0 % c->q(i));
+            j.s1 = q0 >> 1;
+            ej.push_back(j);
+            nj.push_back({o->limb(p, i), o->limb(p, i), i, 0});
+        }
+    if ((rc = launch_ew<EW_CENTER_LIFT>(c, ej))) return bail(rc);
+    if ((rc = hec_launch_ntt(c, nj, false))) return bail(rc);
+    *out = o;
+    return HEC_OK;
+}
+
+static double go_round(double x) { return x < 0 ? -floor(-x + 0.5) : floor(x + 0.5); } // math.Round: half away from zero
+
+// Bootstrapper.evaluateCheby (0x508540): change of variable, Chebyshev evaluation, SinRescal double-angle steps; the
+// evaluator's rescale threshold is the sine scale throughout (evaluateSine sets eval.scale = sinescale)
+static int btp_evaluate_cheby(hec_ctx *c, hec_ct **pct, const hec_btp_params *b) {
+    hec_ct *ct = *pct;
+    volatile double target = b->sinescale;
+    for (int i = 0; i < b->sin_rescal; i++) { volatile double prod = target * (double)b->sine_qi[i]; target = sqrt(prod); }
+    int rc = HEC_OK;
+    if (b->sin_type == 1 || b->sin_type == 2) {
+        volatile double den = b->sc_fac * (b->cheby_b - b->cheby_a);
+        rc = hec_add_const(c, ct, -0.5 / den);
+    }
+    hec_ct *r = nullptr;
+    if (!rc) rc = hec_evaluate_cheby(c, ct, b->cheby, b->n_cheby, target, b->sinescale, &r);
+    if (rc) return rc;
+    hec_ct_free(c, ct);
+    *pct = ct = r;
+    volatile double s = b->sqrt2pi;
+    for (int i = 0; i < b->sin_rescal && !rc; i++) {
+        s = s * s;
+        hec_ct *sq = nullptr;
+        rc = hec_mul_relin_new(c, ct, ct, &sq);
+        if (rc) break;
+        hec_ct_free(c, ct);
+        *pct = ct = sq;
+        rc = hec_add(c, ct, ct, ct);
+        if (!rc) rc = hec_add_const(c, ct, -s);
+        if (!rc) rc = hec_rescale(c, ct, b->sinescale);
+    }
+    return rc;
+}
+
+extern "C" int hec_bootstrap_ctos(hec_ctx *c, const hec_ct *ct_in, const hec_btp_params *b, const hec_ptdiag *const *pdftinv, int nmat,
+                                  hec_ct **ct0, hec_ct **ct1, double *constant) {
+    if (!c || !ct_in || !b || !pdftinv || nmat < 1 || !ct0 || !ct1 || !b->cheby || !b->sine_qi || b->n_sine_qi < b->sin_rescal)
+        return c ? c->fail(HEC_E_INVAL, "bootstrap_ctos args") : HEC_E_INVAL;
+    cudaSetDevice(c->device);
+    if (b->arcsine_deg > 0) return c->fail(HEC_E_UNSUPPORTED, "ArcSineDeg > 0 is not implemented");
+    hec_ct *ct = nullptr, *up = nullptr, *r0 = nullptr, *r1 = nullptr;
+    int rc = hec_ct_copy_new(c, ct_in, &ct);
+    if (!rc && ct->level > 1) rc = hec_drop_level(c, ct, ct->level - 1);
+    if (!rc) {
+        if (ct->level == 1) {                                  // one level available: SetScale to the bootstrapping scale
+            rc = hec_set_scale(c, ct, b->prescale);
+            if (!rc) rc = hec_drop_level(c, ct, ct->level);
+        } else {                                               // level 0: integer ScaleUp
+            if (ct->scale > b->prescale) rc = c->fail(HEC_E_SCALE, "ciphetext scale > q/||m||)");
+            else {
+                double r = go_round(b->prescale / ct->scale);
+                rc = hec_mult_by_const(c, ct, r);
+                if (!rc) ct->scale = ct->scale * r;
+            }
+        }
+    }
+    if (!rc) rc = hec_mod_up(c, ct, &up);
+    if (!rc) {
+        double r = go_round(b->postscale / up->scale);
+        rc = hec_mult_by_const(c, up, r);
+        if (!rc) up->scale = up->scale * r;
+    }
+    // subSum: nothing to do at full packing (LogSlots = LogN - 1); hec_coeffs_to_slots refuses sparse packing
+    if (!rc) rc = hec_coeffs_to_slots(c, up, pdftinv, nmat, &r0, &r1);
+    hec_ct **halves[2] = {&r0, &r1};
+    for (int h = 0; h < 2 && !rc; h++) {                       // evaluateSine (0x508380)
+        hec_ct *x = *halves[h];
+        x->scale = x->scale * b->message_ratio;
+        rc = btp_evaluate_cheby(c, halves[h], b);
+        if (!rc) { x = *halves[h]; volatile double d = b->postscale * b->message_ratio / b->params_scale; x->scale = x->scale / d; }
+    }
+    double q0 = (double)c->q(0);
+    volatile double k = q0 / exp2(go_round(log2(q0)));
+    k = k * b->params_scale;
+    k = k / b->postscale;
+    for (int h = 0; h < 2 && !rc; h++) {
+        rc = hec_mult_by_const(c, *halves[h], k);
+        if (!rc) rc = hec_rescale(c, *halves[h], b->params_scale);
+    }
+    hec_ct_free(c, ct); hec_ct_free(c, up);
+    if (rc) { hec_ct_free(c, r0); hec_ct_free(c, r1); return rc; }
+    *ct0 = r0; *ct1 = r1;
+    if (constant) *constant = k;
+    return HEC_OK;
+}

@@ -329,6 +329,74 @@ class Oracle:
             ct0 = self.add_matched(ct0, self.mult_by_i(ct1))
         return self.dft(ct0, mats, keys)
 
+    # ---- split bootstrapping, first half (BootstrappConv_CtoS of the fork's ckks/bootstrap.go) ----
+    def mod_up(self, ct):
+        """Bootstrapper.modUp: the level-0 ciphertext's coefficients, centred around q0, re-expressed modulo every
+        q_i of the chain (then back to the NTT domain)"""
+        q0 = self.Q[0]
+        out = []
+        for poly in (ct.c0, ct.c1):
+            co = self.intt(poly[0], 0)
+            neg = co > np.uint64(q0 >> 1)
+            limbs = []
+            for i, qi in enumerate(self.Q):
+                pos = co % np.uint64(qi)
+                t = (np.uint64(q0) - co) % np.uint64(qi)          # only meaningful where neg
+                v = np.where(neg, (np.uint64(qi) - t) % np.uint64(qi), pos).astype(np.uint64)
+                limbs.append(self.ntt(v, i))
+            out.append(np.stack(limbs))
+        return Ct(out[0], out[1], ct.scale)
+
+    def btp_evaluate_cheby(self, ct, b, rlk):
+        """Bootstrapper.evaluateCheby: change of variable, Chebyshev evaluation of the scaled cosine, SinRescal double-angle
+        steps (2 x^2 - sqrt2pi^(2^k)); the evaluator's rescale threshold is the sine scale throughout"""
+        target = b["sinescale"]
+        for i in range(b["sin_rescal"]):
+            target = float(np.sqrt(target * float(b["sine_qi"][i])))
+        co, lo, hi = b["cheby"]
+        if b["sin_type"] in (1, 2):
+            ct = self.add_const(ct, -0.5 / (b["sc_fac"] * (hi - lo)))
+        ct = self.evaluate_poly(ct, co, target, rlk, b["sinescale"], cheby=True)
+        s = b["sqrt2pi"]
+        for _ in range(b["sin_rescal"]):
+            s *= s
+            ct = self.mul_relin(ct, ct, rlk)
+            ct = self.add_matched(ct, ct)
+            ct = self.rescale(self.add_const(ct, -s), b["sinescale"])
+        return ct
+
+    def bootstrapp_conv_ctos(self, ct, b, keys, key_conj, rlk):
+        """BootstrappConv_CtoS: scale to the bootstrapping scale at level 0, modUp, CoeffsToSlots, sine evaluation on the
+        real and imaginary halves, and the fork's final constant multiplication + Rescale.  b: the Bootstrapper's fields
+        (prescale, postscale, sinescale, sqrt2pi, sc_fac, message_ratio, sin_type, sin_rescal, sine_qi, cheby = (coeffs,
+        a, b), mats = pDFTInv factors, params_scale).  Returns (ct0, ct1, constant)."""
+        while ct.level > 1:
+            ct = self.drop_level(ct, 1)
+        if ct.level == 1:
+            ct = self.set_scale(ct, b["prescale"])
+            ct = self.drop_level(ct, ct.level)
+        else:
+            if ct.scale > b["prescale"]:
+                raise RuntimeError("ciphetext scale > q/||m||)")
+            r = float(np.round(b["prescale"] / ct.scale))
+            ct = self.mul_const(ct, r)
+            ct.scale = ct.scale * r
+        ct = self.mod_up(ct)
+        r = float(np.round(b["postscale"] / ct.scale))
+        ct = self.mul_const(ct, r)
+        ct.scale = ct.scale * r
+        ct0, ct1 = self.coeffs_to_slots(ct, b["mats"], keys, key_conj)
+        outs = []
+        for c in (ct0, ct1):
+            c = Ct(c.c0, c.c1, c.scale * b["message_ratio"])
+            c = self.btp_evaluate_cheby(c, b, rlk)
+            c.scale = c.scale / (b["postscale"] * b["message_ratio"] / b["params_scale"])
+            outs.append(c)
+        q0 = float(self.Q[0])
+        const = q0 / float(2.0 ** np.round(np.log2(q0))) * b["params_scale"] / b["postscale"]
+        outs = [self.rescale(self.mul_const(c, const), b["params_scale"]) for c in outs]
+        return outs[0], outs[1], const
+
     def mult_by_i(self, ct, divide=False):
         """MultByi / DivByi (L:ckks/evaluator.go): product with X^(N/2) in the NTT domain = first half of the slots
         times psi^(N/2) (NttPsi[i][1]), second half times its negative; DivByi swaps the two"""

@@ -3,7 +3,7 @@
 Run from the repo root in the build container (needs /root/reference/test_run, objdump, nm):
     python tests/golden/make_ref_eval_vectors.py            # small-N cases, ~2 min
     python tests/golden/make_ref_eval_vectors.py --only n8_B4      # regenerate one small conv case
-    python tests/golden/make_ref_eval_vectors.py --evalops | --relu | --lt | --ring | --conv  # regenerate one group
+    python tests/golden/make_ref_eval_vectors.py --evalops | --relu | --lt | --ctos | --ring | --conv  # regenerate one group
     python tests/golden/make_ref_eval_vectors.py --full B4_norm1   # N = 2^16 golden config, ~1 h
 The prebuilt binary is never executed.  tests/golden/refmachine.py interprets the compiled routines of
 the Lattigo fork (ring / rlwe / ckks packages) and of package main from their disassembly; objects
@@ -419,6 +419,86 @@ def dft_case():
     return rec
 
 
+# ---------------------------------------------------------------- BootstrappConv_CtoS (first half of the split bootstrapping)
+CTOS_SPECS = [(2, [0, 1, 2, 3, 5], 27), (2, [0, 1, 4, 6], 26), (4, [0, 1, 2, 5], 25), (2, [1, 2, 3], 24)]   # pDFTInv: (N1, diagonals, level)
+CTOS_LOGN = 4
+CTOS_FIELDS = {"prescale": 2.0 ** 47, "postscale": 2.0 ** 47, "sinescale": 2.0 ** 55, "sqrt2pi": 0.3989422804014327, "sc_fac": 4.0,
+               "message_ratio": 256.0, "sin_type": 1, "sin_rescal": 2, "params_scale": PR.SCALE}
+
+
+def ctos_operands(N):
+    """seeded operands: the full 28 + 5 modulus chain of set 6, four CoeffsToSlots factor matrices at the top four levels
+    (scale = the modulus they consume), a degree-63 Chebyshev sine polynomial on [-25/4, 25/4], the keys"""
+    Q, P = PR.Q_SET6, PR.P_ALL
+    beta = (len(Q) + len(P) - 1) // len(P)
+    key = lambda s: np.stack([np.stack([synth.uniform_limbs(s + 10 * d + k, list(Q) + list(P), N) for k in range(2)]) for d in range(beta)])  # noqa: E731
+    rots = set()
+    for n1, diags, _ in CTOS_SPECS:
+        rots |= {d % n1 for d in diags if d % n1} | {(d // n1) * n1 for d in diags if d // n1}
+    keys = {r: key(9000 + 131 * r) for r in sorted(rots)}
+    mats = []
+    for mi, (n1, diags, ml) in enumerate(CTOS_SPECS):
+        D = {d: (synth.uniform_limbs(7000 + 100 * mi + d, Q[:ml + 1], N), synth.uniform_limbs(7500 + 100 * mi + d, P, N)) for d in diags}
+        mats.append((D, n1, ml, float(Q[ml])))
+    rng = np.random.default_rng(77)
+    coeffs = [float(x) for x in rng.uniform(-1, 1, 64)]
+    b = dict(CTOS_FIELDS, sine_qi=Q[16:24], cheby=(coeffs, -25.0 / 4, 25.0 / 4), mats=mats)
+    return keys, key(9900), key(8000), b
+
+
+def ctos_case(level_in):
+    """ckks.(*Bootstrapper).BootstrappConv_CtoS on a hand-built Bootstrapper (struct layout from the DWARF): SetScale /
+    ScaleUp to the bootstrapping scale, modUp, ScaleUp, CoeffsToSlots, evaluateSine (EvaluateCheby + double angle), the
+    fork's final MultByConst + Rescale.  N = 2^4, the whole 28-level chain, alpha = 5."""
+    logN = CTOS_LOGN
+    N = 1 << logN
+    Q, P = PR.Q_SET6, PR.P_ALL
+    m = Machine()
+    keys, kconj, rlk, b = ctos_operands(N)
+    gk = {pow(5, r, 2 * N): k for r, k in keys.items()}
+    gk[2 * N - 1] = kconj
+    params, ev = m.new_evaluator(logN, Q, P, PR.SCALE, gk, rlk)
+    ptrs = []
+    for D, n1, ml, ms in b["mats"]:
+        vec = m.new_map(16)
+        for d, (dq, dp) in D.items():
+            pq, pp = m.new_poly([ints(l) for l in dq]), m.new_poly([ints(l) for l in dp])
+            for p in (pq, pp):
+                m.wb(p + 24, 1)
+                m.wb(p + 25, 1)
+            m.map_put(vec, d, [pq, pp])
+        mat = m.alloc(48)
+        m.write_u64s(mat, [logN - 1, n1, ml, f2b(ms), vec, 0])
+        ptrs.append(mat)
+    coeffs, lo, hi = b["cheby"]
+    carr = m.alloc(16 * len(coeffs))
+    for i, c in enumerate(coeffs):
+        m.write_u64s(carr + 16 * i, [f2b(c), 0])
+    cheb = m.alloc(72)
+    m.write_u64s(cheb, [len(coeffs) - 1, carr, len(coeffs), len(coeffs), 1, f2b(lo), 0, f2b(hi), 0])
+    btp = m.alloc(656)                                   # ckks.Bootstrapper
+    m.wq(btp + 0, ev[1])                                 #   *evaluator
+    m.write_u64s(btp + 360, params)                      #   params ckks.Parameters
+    B = btp + 8                                          #   BootstrappingParameters
+    m.write_u64s(B + 160, m.slice_u64(b["sine_qi"]) + [f2b(b["sinescale"])])   # SineEvalModuli{Qi, ScalingFactor}
+    m.wq(B + 240, logN); m.wq(B + 248, logN - 1); m.wq(B + 256, f2b(PR.SCALE))
+    m.wq(B + 280, b["sin_type"]); m.wq(B + 288, f2b(b["message_ratio"])); m.wq(B + 304, len(coeffs) - 1)
+    m.wq(B + 312, b["sin_rescal"]); m.wq(B + 320, 0)
+    m.wq(btp + 464, N // 2); m.wq(btp + 472, logN - 1)
+    for off, k in ((496, "prescale"), (504, "postscale"), (512, "sinescale"), (520, "sqrt2pi"), (528, "sc_fac")):
+        m.wq(btp + off, f2b(b[k]))
+    m.wq(btp + 536, cheb)
+    m.write_u64s(btp + 608, m.slice_u64(ptrs))           #   pDFTInv
+    ct_scale = PR.SCALE * 2.0 ** 8
+    lim = lambda seed: [ints(l) for l in synth.uniform_limbs(seed, Q[:level_in + 1], N)]  # noqa: E731
+    ct = m.new_ct([lim(61), lim(62)], ct_scale)
+    res = m.call(CKKS + "(*Bootstrapper).BootstrappConv_CtoS", [btp, ct, 0, 0, 0], max_steps=1 << 62)
+    rec = {"logN": logN, "level_in": level_in, "ct_scale": ct_scale, "out": [digest_ct(m, res[-3]), digest_ct(m, res[-2])],
+           "const_bits": res[-1], "interpreted_instructions": m.steps}
+    print("BootstrappConv_CtoS case level_in=%d: %d instructions" % (level_in, m.steps), flush=True)
+    return rec
+
+
 SMALL_CONV = [
     # name, logN, B, norm, seed, out_scale, Q, P
     ("n8_B4", 8, 4, 1, 3, PR.SCALE, PR.Q_SET6[:2], PR.P_PACK),
@@ -443,13 +523,15 @@ def main():
         new["conv"] = {name: conv_case(logN, B, norm, seed, out_scale, Q2, P1)
                        for name, logN, B, norm, seed, out_scale, Q2, P1 in SMALL_CONV if name in sys.argv}
     else:
-        groups = [g for g in ("relu", "evalops", "lt", "ring", "conv") if "--" + g in sys.argv] or ["relu", "evalops", "lt", "ring", "conv"]
+        groups = [g for g in ("relu", "evalops", "lt", "ctos", "ring", "conv") if "--" + g in sys.argv] or ["relu", "evalops", "lt", "ctos", "ring", "conv"]
         if "relu" in groups:
             new["relu"] = {name: relu_case(logN, alpha, level) for name, logN, alpha, level in RELU_CASES}
             new["cheby"] = {name: cheby_case(deg, level) for name, deg, level in CHEBY_CASES}
         if "lt" in groups:
             new["linear_transform"] = {name: lt_case(*a) for name, *a in LT_CASES}
             new["dft"] = dft_case()
+        if "ctos" in groups:
+            new["ctos"] = {"level%d" % lv: ctos_case(lv) for lv in (1, 0, 3)}
         if "evalops" in groups:
             new["evalops"] = {name: evalop_case(logN, Q, P, level, rots) for name, logN, Q, P, level, rots in EVALOP_CASES}
             new["pre_conv_bl"] = pre_conv_bl_case()

@@ -40,7 +40,10 @@ def _factors(n):
 
 
 class Machine(Emu):
-    auto_prefixes = (LAT, "main.", "math.", "math/bits.", "runtime.duffcopy", "runtime.duffzero")
+    auto_prefixes = (LAT, "main.", "math.", "math/bits.", "runtime.duffcopy", "runtime.duffzero",
+                     # pure float helpers of the Go runtime (complex division)
+                     "runtime.complex128div", "runtime.inf2one", "runtime.isNaN", "runtime.isInf", "runtime.isFinite",
+                     "runtime.abs", "runtime.copysign", "runtime.float64bits", "runtime.float64frombits")
 
     def __init__(self):
         super().__init__(BIN)

@@ -421,6 +421,40 @@ def test_coeffs_to_slots_and_slots_to_coeffs():
         c.close()
 
 
+def test_bootstrapp_conv_ctos_full_chain():
+    """BootstrappConv_CtoS (first half of the split bootstrapping, eval.go:447-459) at N = 2^16 over the whole
+    28 + 5 modulus chain of set 6: SetScale, modUp, four hoisted linear transforms, conjugation, degree-63
+    Chebyshev sine + two double-angle steps, final constant == the oracle (pinned at N = 2^4 against the
+    reference's compiled BootstrappConv_CtoS); also modUp alone."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_ref_eval_vectors as G
+    Q, P = PR.Q_SET6, PR.P_ALL
+    c, o = hec.Context(PR.LOGN, Q, P), Oracle(PR.LOGN, Q, P)
+    try:
+        keys, kconj, rlk, b = G.ctos_operands(N)
+        for r, k in keys.items():
+            c.upload_swk(c.galois_for_rotation(r), k, 27)
+        c.upload_swk(2 * N - 1, kconj, 27)
+        c.upload_rlk(rlk, 27)
+        mats = [c.upload_ptdiag(PR.LOGN - 1, n1, ml, ms, D) for D, n1, ml, ms in b["mats"]]
+        a = Ct(synth.uniform_limbs(61, Q[:2], N), synth.uniform_limbs(62, Q[:2], N), PR.SCALE * 2.0 ** 8)
+        A = c.upload_ct(a.c0, a.c1, a.scale)
+        low = Ct(a.c0[:1], a.c1[:1], a.scale)
+        up, uref = c.ModUp(c.upload_ct(low.c0, low.c1, low.scale)), o.mod_up(low)
+        x0, x1 = up.download()
+        assert up.level == uref.level == 27 and np.array_equal(x0, uref.c0) and np.array_equal(x1, uref.c1)
+        g0, g1, k = c.BootstrappConv_CtoS(A, b, mats)
+        r0, r1, kref = o.bootstrapp_conv_ctos(a, b, keys, kconj, rlk)
+        assert k == kref
+        for g, r in ((g0, r0), (g1, r1)):
+            x0, x1 = g.download()
+            assert g.level == r.level == 14 and g.scale == r.scale
+            assert np.array_equal(x0, r.c0) and np.array_equal(x1, r.c1)
+    finally:
+        c.close()
+
+
 # ---------------------------------------------------------------- the conv path
 @pytest.mark.parametrize("cfg", common.GOLDEN_CONFIGS, ids=lambda c: c["name"])
 @pytest.mark.parametrize("flags", [hec.CONV_FUSED, hec.CONV_OPLEVEL], ids=["fused", "oplevel"])

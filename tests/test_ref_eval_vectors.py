@@ -197,6 +197,26 @@ def test_coeffs_to_slots_and_slots_to_coeffs_match_reference_code():
     assert dg(o.slots_to_coeffs(b, None, mats, keys)) == rec["slots_to_coeffs_real_only"]
 
 
+@pytest.mark.parametrize("name", sorted(REF["ctos"]))
+def test_bootstrapp_conv_ctos_matches_reference_code(name):
+    """ckks.(*Bootstrapper).BootstrappConv_CtoS (interpreted, ~4e7 instructions per case): the first half of the split
+    bootstrapping over the whole 28-level chain of set 6 == the oracle, including the returned constant"""
+    import struct
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_ref_eval_vectors as G
+    rec = REF["ctos"][name]
+    N = 1 << rec["logN"]
+    Q, P = PR.Q_SET6, PR.P_ALL
+    o = Oracle(rec["logN"], Q, P)
+    keys, kconj, rlk, b = G.ctos_operands(N)
+    lv = rec["level_in"]
+    ct = Ct(synth.uniform_limbs(61, Q[:lv + 1], N), synth.uniform_limbs(62, Q[:lv + 1], N), rec["ct_scale"])
+    c0, c1, const = o.bootstrapp_conv_ctos(ct, b, keys, kconj, rlk)
+    assert [dg(c0), dg(c1)] == rec["out"]
+    assert struct.unpack("<Q", struct.pack("<d", const))[0] == rec["const_bits"]
+
+
 def cheby_coeffs(deg):
     rng = np.random.default_rng(1000 + deg)
     co = [float(x) for x in rng.uniform(-1, 1, deg + 1)]

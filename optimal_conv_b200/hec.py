@@ -341,7 +341,7 @@ class Context:
         return Ciphertext(self, h)
 
     def BootstrappConv_CtoS(self, ct, b, mats):
-        """b: dict with the Bootstrapper fields (see oracle.orc.Oracle.bootstrapp_conv_ctos); mats: uploaded pDFTInv"""
+        """b: dict with the Bootstrapper fields (names of hec_btp_params, plus cheby = (coeffs, a, b)); mats: uploaded pDFTInv"""
         co, lo, hi = b["cheby"]
         qi = (C.c_uint64 * len(b["sine_qi"]))(*b["sine_qi"])
         ca = (C.c_double * len(co))(*co)

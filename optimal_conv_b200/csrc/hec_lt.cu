@@ -292,7 +292,7 @@ extern "C" int hec_slots_to_coeffs(hec_ctx *c, const hec_ct *ct0, const hec_ct *
 
 // =========================================================================================
 // Split bootstrapping, first half: BootstrappConv_CtoS of the fork's ckks/bootstrap.go (eval.go:447-459), restated
-// from the disassembly of the reference binary (0x506800) and checked against it through the oracle.
+// from the disassembly of the reference binary (0x506800) and checked against its interpreted output (tests/golden).
 // =========================================================================================
 // Bootstrapper.modUp (0x507400): the level-0 ciphertext's coefficients, centred around q0, re-expressed modulo every
 // q_i of the chain; back to the NTT domain.  Returns a new ciphertext at the top level.

@@ -188,7 +188,8 @@ def run_side_workload(args):
     --workload keyswitch  : KeySwitcher.SwitchKeysInPlace at level 27, alpha = 5, beta = 6 (SURVEY.md 8d stress)
     --workload mul_relin  : MulRelinNew(ct, ct) + Rescale at level 10, alpha = 5 (the multiply of
                             evalReLU's polynomial evaluation, conv.go:435-480)
-    --workload eval_relu  : the whole evalReLU on one level-15 ciphertext (three EvaluatePoly + the final multiply)"""
+    --workload eval_relu  : the whole evalReLU on one level-15 ciphertext (three EvaluatePoly + the final multiply)
+    --workload bootstrap_ctos : BootstrappConv_CtoS, the first half of the split bootstrapping, full modulus chain"""
     import torch
     from optimal_conv_b200 import hec
     if not torch.cuda.is_available():
@@ -230,6 +231,35 @@ def run_side_workload(args):
             o = Oracle(PR.LOGN, Q, P)
             t0 = time.perf_counter()
             o.rescale(o.mul_relin(Ct(a[0], a[1], PR.SCALE), Ct(a[2], a[3], PR.SCALE), rlk), PR.SCALE)
+            cpu_s = time.perf_counter() - t0
+    elif args.workload == "bootstrap_ctos":
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import make_ref_eval_vectors as G   # seeded operands only (no reference access)
+        Q, P = PR.Q_SET6, PR.P_ALL
+        ctx = hec.Context(PR.LOGN, Q, P)
+        keys, kconj, rlk, b = G.ctos_operands(N)
+        for r, k in keys.items():
+            ctx.upload_swk(ctx.galois_for_rotation(r), k, 27)
+        ctx.upload_swk(2 * N - 1, kconj, 27)
+        ctx.upload_rlk(rlk, 27)
+        mats = [ctx.upload_ptdiag(PR.LOGN - 1, n1, ml, ms, D) for D, n1, ml, ms in b["mats"]]
+        a0, a1 = synth.uniform_limbs(61, Q[:2], N), synth.uniform_limbs(62, Q[:2], N)
+        A = ctx.upload_ct(a0, a1, PR.SCALE * 2.0 ** 8)
+
+        def step():
+            g0, g1, _ = ctx.BootstrappConv_CtoS(A, b, mats)
+            g0.free()
+            g1.free()
+        unit = "half-bootstraps/s"
+        name = ("BootstrappConv_CtoS (eval.go:447-459) over the 28+5 modulus chain of set 6: modUp, 4 hoisted linear transforms "
+                "(synthetic sparse factors), degree-63 Chebyshev sine x2 + double angle, alpha=5")
+        alg = None
+        if args.cpu_sample > 0:
+            from oracle.orc import Ct, Oracle
+            o = Oracle(PR.LOGN, Q, P)
+            t0 = time.perf_counter()
+            o.bootstrapp_conv_ctos(Ct(a0, a1, PR.SCALE * 2.0 ** 8), b, keys, kconj, rlk)
             cpu_s = time.perf_counter() - t0
     elif args.workload == "eval_relu":
         level = 15
@@ -311,7 +341,7 @@ def run_side_workload(args):
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "dtype": "u64",
             "data": "synthetic", "config": {"workload": args.workload, "path": "op-level generic kernels"},
             "gpu_launches": ctx.launch_count() - l0}
-    if args.workload in ("conv_bl", "mul_relin", "eval_relu") and args.cpu_sample > 0:
+    if args.workload in ("conv_bl", "mul_relin", "eval_relu", "bootstrap_ctos") and args.cpu_sample > 0:
         line["cpu_baseline"] = {"value": 1.0 / cpu_s, "unit": unit, "cores": 1, "kind": "port",
                                 "sample": "1 call of the same workload, oracle port, 1 thread"}
     if alg:
@@ -330,7 +360,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="B: output channels packed per ciphertext")
     ap.add_argument("--ker", type=int, default=3, help="kernel width k (only changes the work of --workload conv_bl)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="conv", choices=["conv", "conv_bl", "keyswitch", "mul_relin", "eval_relu"],
+    ap.add_argument("--workload", default="conv", choices=["conv", "conv_bl", "keyswitch", "mul_relin", "eval_relu", "bootstrap_ctos"],
                     help="conv = the headline fused path; the others are op-level side measurements")
     ap.add_argument("--cpu-sample", type=int, default=12, help="convs timed for cpu_baseline (0 = skip)")
     ap.add_argument("--ring", type=int, default=8, help="distinct input batches rotated through (> L2)")

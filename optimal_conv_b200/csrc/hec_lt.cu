@@ -409,3 +409,9 @@ extern "C" int hec_bootstrap_ctos(hec_ctx *c, const hec_ct *ct_in, const hec_btp
     if (constant) *constant = k;
     return HEC_OK;
 }
+
+// btp.BootstrappConv_StoC(ct0, ct1) (eval.go:540-560): in the reference binary it is SlotsToCoeffs(ct0, ct1, btp.pDFT,
+// btp.evaluator) inlined into its callers (0x53eb00); the caller then rescales (eval.go:562)
+extern "C" int hec_bootstrap_stoc(hec_ctx *c, const hec_ct *ct0, const hec_ct *ct1, const hec_ptdiag *const *pdft, int nmat, hec_ct **out) {
+    return hec_slots_to_coeffs(c, ct0, ct1, pdft, nmat, out);
+}

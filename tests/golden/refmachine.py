@@ -403,12 +403,12 @@ class Machine(Emu):
         self.write_u64s(key, [val, beta, beta])
         return key
 
-    def new_evaluator(self, logN, Q, P, scale, keys, rlk=None):
+    def new_evaluator(self, logN, Q, P, scale, keys, rlk=None, log_slots=None):
         """ckks.NewEvaluator(params, EvaluationKey{Rlk: rlk, Rtks: keys}) run by the reference code itself.
         keys: {galEl: array [beta][2][nQ+nP][N]}; rlk: one such array (RelinearizationKey{Keys []*SwitchingKey})
         or None.  Returns (params words, Evaluator iface words)."""
         rQ, rP = self.new_ring(1 << logN, Q), self.new_ring(1 << logN, P)
-        params = [logN] + self.slice_u64(Q) + self.slice_u64(P) + [f2b(3.2), rQ, rP, 0, logN - 1, f2b(scale)]
+        params = [logN] + self.slice_u64(Q) + self.slice_u64(P) + [f2b(3.2), rQ, rP, 0, logN - 1 if log_slots is None else log_slots, f2b(scale)]
         kmap = self.new_map(8)
         for gal, swk in keys.items():
             self.map_put(kmap, gal, [self.new_swk(swk)])

@@ -455,6 +455,62 @@ def test_bootstrapp_conv_ctos_full_chain():
         c.close()
 
 
+def test_layer_pipeline_conv_ctos_relu_keep_stoc(idx_np):
+    """One layer of evalConv_BNRelu_new (eval.go:360-575) end to end on the device, through two contexts like the
+    reference's two evaluators: conv_then_pack on the pack evaluator (level 1 -> 0), scale relabel, BootstrappConv_CtoS
+    on the main evaluator (level 0 -> 27 -> 14), evalReLU + MulByPow2 on both halves (14 -> 4), keep_ctxt (4 -> 3),
+    BootstrappConv_StoC with two factor matrices (3 -> 1), Rescale -- every hand-off of level and scale -- == the
+    oracle doing the same."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_ref_eval_vectors as G
+    Q, P = PR.Q_SET6, PR.P_ALL
+    cp, op_ = hec.Context(PR.LOGN, Q2, P1), Oracle(PR.LOGN, Q2, P1)
+    c, o = hec.Context(PR.LOGN, Q, P), Oracle(PR.LOGN, Q, P)
+    try:
+        # --- conv on the pack evaluator
+        w = common.workload({"B": 4, "seed": 91})
+        Gc = common.GpuConv(cp, w, idx_np)
+        conv = cp.conv_then_pack(Gc.cts[0], Gc.ker, 1, PR.SCALE, Gc.idx, Gc.bias)
+        cp.sync()
+        rconv = common.oracle_conv(op_, w, 1, PR.SCALE, idx_np)
+        # --- operands of the main evaluator
+        keys, kconj, rlk, b = G.ctos_operands(N)
+        for r, k in keys.items():
+            c.upload_swk(c.galois_for_rotation(r), k, 27)
+        c.upload_swk(2 * N - 1, kconj, 27)
+        c.upload_rlk(rlk, 27)
+        pdftinv = [c.upload_ptdiag(PR.LOGN - 1, n1, ml, ms, D) for D, n1, ml, ms in b["mats"]]
+        stoc_specs = [(2, [0, 1, 2], 3), (2, [0, 1, 3], 2)]
+        stoc = [({d: (synth.uniform_limbs(7800 + 100 * i + d, Q[:ml + 1], N), synth.uniform_limbs(7900 + 100 * i + d, P, N)) for d in diags},
+                 n1, ml, float(Q[ml])) for i, (n1, diags, ml) in enumerate(stoc_specs)]
+        pdft = [c.upload_ptdiag(PR.LOGN - 1, n1, ml, ms, D) for D, n1, ml, ms in stoc]
+        mask = synth.uniform_limbs(97, Q[:5], N)
+        MASK = c.upload_pt(mask, 2.0 ** 20)
+        pow2 = 5
+        # --- device pipeline (the conv result moves to the main context as it is: level 0 is limb q0 in both chains)
+        conv.set_scale(conv.scale * 2.0 ** 8)                    # ct_conv.Scale *= 2^pow (eval.go:437)
+        h0, h1, _ = c.BootstrappConv_CtoS(conv, b, pdftinv)
+        halves = c.evalReLUMany([h0, h1], 0.0, PR.SCALE)
+        kept = []
+        for h in halves:
+            c.MulByPow2(h, pow2)
+            kept.append(c.keep_ctxt(h, MASK, PR.SCALE))
+        out = c.BootstrappConv_StoC(kept[0], kept[1], pdft)
+        c.Rescale(out, PR.SCALE)
+        # --- the same on the oracle
+        r = Ct(rconv.c0, rconv.c1, rconv.scale * 2.0 ** 8)
+        r0, r1, _ = o.bootstrapp_conv_ctos(r, b, keys, kconj, rlk)
+        rk = [o.keep_ctxt(o.mul_by_pow2(o.eval_relu(x, 0.0, rlk, PR.SCALE), pow2), mask, 2.0 ** 20, PR.SCALE) for x in (r0, r1)]
+        ref = o.rescale(o.slots_to_coeffs(rk[0], rk[1], stoc, keys), PR.SCALE)
+        g0, g1 = out.download()
+        assert out.level == ref.level and out.scale == ref.scale
+        assert np.array_equal(g0, ref.c0) and np.array_equal(g1, ref.c1)
+    finally:
+        c.close()
+        cp.close()
+
+
 # ---------------------------------------------------------------- the conv path
 @pytest.mark.parametrize("cfg", common.GOLDEN_CONFIGS, ids=lambda c: c["name"])
 @pytest.mark.parametrize("flags", [hec.CONV_FUSED, hec.CONV_OPLEVEL], ids=["fused", "oplevel"])

@@ -172,15 +172,52 @@ static EwJob ewjob(const u64 *a, const u64 *b, u64 *out, int mod, u64 s0 = 0, u3
     return j;
 }
 
+// launch the exact basis extensions `jobs` (one entry per target limb): entries that share their source digit are
+// grouped so that k_modup2 computes y_i and v once per coefficient for all of the digit's targets; the grouped tables
+// are staged into one stream-ordered device buffer
 static int launch_modup(hec_ctx *c, std::vector<ModupJob> &jobs) {
-    for (size_t off = 0; off < jobs.size(); off += HEC_MUJOBS) {
-        int n = (int)std::min<size_t>(HEC_MUJOBS, jobs.size() - off);
-        ModupJobs J;
-        for (int i = 0; i < n; i++) J.j[i] = jobs[off + i];
-        k_modup<<<dim3(32, n), 256, 0, c->stream>>>(J, c->dmods);
+    if (jobs.empty()) return HEC_OK;
+    std::vector<Modup2Job> groups;
+    std::vector<Modup2Target> targets;
+    std::vector<size_t> first; // index of each group's first target
+    for (const ModupJob &j : jobs) {
+        bool same = !groups.empty() && groups.back().n == j.n;
+        for (int s = 0; same && s < j.n; s++) same = groups.back().src[s] == j.src[s] && groups.back().smod[s] == j.smod[s];
+        if (!same) {
+            Modup2Job g;
+            memset(&g, 0, sizeof g);
+            g.n = j.n;
+            for (int s = 0; s < j.n; s++) { g.src[s] = j.src[s]; g.smod[s] = j.smod[s]; g.qib[s] = j.qib[s]; }
+            groups.push_back(g);
+            first.push_back(targets.size());
+        }
+        Modup2Target t;
+        memset(&t, 0, sizeof t);
+        t.dst = j.dst; t.tmod = j.tmod;
+        for (int s = 0; s < j.n; s++) t.qisp[s] = j.qisp[s];
+        for (int v = 0; v <= j.n; v++) t.qpjinv[v] = j.qpjinv[v];
+        targets.push_back(t);
+        groups.back().ntargets++;
+    }
+    size_t tb = targets.size() * sizeof(Modup2Target), gb = groups.size() * sizeof(Modup2Job);
+    char *dbuf = nullptr;
+    HEC_CUDA(c, cudaMallocAsync(&dbuf, tb + gb, c->stream));
+    const Modup2Target *dt = reinterpret_cast<const Modup2Target *>(dbuf);
+    for (size_t g = 0; g < groups.size(); g++) groups[g].targets = dt + first[g];
+    std::vector<char> h(tb + gb);
+    memcpy(h.data(), targets.data(), tb);
+    memcpy(h.data() + tb, groups.data(), gb);
+    // pageable source: staged by the driver before the call returns, so `h` may die
+    HEC_CUDA(c, cudaMemcpyAsync(dbuf, h.data(), tb + gb, cudaMemcpyHostToDevice, c->stream));
+    for (size_t off = 0; off < groups.size(); off += 65535) {
+        unsigned n = (unsigned)std::min<size_t>(65535, groups.size() - off);
+        k_modup2<<<dim3(HEC_N / 256, n), 256, 0, c->stream>>>(reinterpret_cast<const Modup2Job *>(dbuf + tb) + off, c->dmods);
         c->launches += 1;
     }
-    return check_launch(c, "modup");
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(dbuf, c->stream);
+    if (e != cudaSuccess) return c->fail(HEC_E_CUDA, std::string("modup: ") + cudaGetErrorString(e));
+    return HEC_OK;
 }
 static ModupJob modup_job(const hec_ctx *c, const ModupTab &T, const u64 *src, size_t src_stride, int target, u64 *dst) {
     ModupJob j;

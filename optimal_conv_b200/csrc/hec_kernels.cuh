@@ -179,6 +179,44 @@ __global__ void __launch_bounds__(256) k_modup(ModupJobs J, const ModC *__restri
     }
 }
 
+// The same extension for ALL targets of one source digit: y_i and the float overflow count v depend only on the
+// source, so they are computed once per coefficient (the per-target form above recomputes alpha Montgomery products
+// and alpha double divisions for each of the up to nQ + nP - alpha targets: it was 51 % of a full-level key switch).
+struct Modup2Target { u64 *dst; u64 qisp[HEC_MAXA]; u64 qpjinv[HEC_MAXA + 1]; int tmod; };
+struct Modup2Job {
+    const u64 *src[HEC_MAXA];
+    int smod[HEC_MAXA];
+    u64 qib[HEC_MAXA];
+    const Modup2Target *targets; // device memory
+    int n, ntargets;
+};
+__global__ void __launch_bounds__(256) k_modup2(const Modup2Job *__restrict__ jobs, const ModC *__restrict__ mods) {
+    const Modup2Job &job = jobs[blockIdx.y];
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    u64 y[HEC_MAXA];
+    double vi = 0.0;
+#pragma unroll
+    for (int s = 0; s < HEC_MAXA; s++) {
+        y[s] = 0;
+        if (s < job.n) {
+            const u64 qs = mods[job.smod[s]].q;
+            y[s] = mred(job.src[s][i], job.qib[s], qs, mods[job.smod[s]].qinv);
+            // v = (uint64) sum_i float64(y_i)/float64(q_i): IEEE double, sequential, no FMA
+            vi = __dadd_rn(vi, __ddiv_rn(__ull2double_rn(y[s]), __ull2double_rn(qs)));
+        }
+    }
+    const u64 v = (u64)__double2ull_rz(vi);
+    for (int t = 0; t < job.ntargets; t++) {
+        const Modup2Target &T = job.targets[t];
+        const u64 pt = mods[T.tmod].q, ptinv = mods[T.tmod].qinv;
+        u64 acc = 0;
+#pragma unroll
+        for (int s = 0; s < HEC_MAXA; s++)
+            if (s < job.n) acc = addmod(acc, mred(y[s], T.qisp[s], pt, ptinv), pt);
+        T.dst[i] = addmod(acc, T.qpjinv[v], pt);
+    }
+}
+
 // =========================================================================================
 // (2) fused conv_then_pack kernels
 // =========================================================================================

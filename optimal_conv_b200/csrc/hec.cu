@@ -779,6 +779,41 @@ static int decompose_many(hec_ctx *c, int level, const std::vector<const u64 *> 
 }
 // KeyswitchHoisted (L:rlwe/keyswitch.go:234-304) for item i: inner product of decomposition dc[i] (or the
 // shared dc[0]) with key[i], then mod-down.  d0[i], d1[i]: [L][N] outputs.  Scratch: (2 nP + 2 L) limbs per item.
+// launch k_dot for a list of (a pointers, b pointers or none, out, modulus) sums; the pointer lists are
+// staged into one stream-ordered device buffer
+struct DotSpec { std::vector<const u64 *> a, b; u64 *out; int mod; };
+static int launch_dot(hec_ctx *c, const std::vector<DotSpec> &specs) {
+    size_t np = 0;
+    for (auto &sp : specs) np += sp.a.size() + sp.b.size();
+    size_t bytes = np * sizeof(u64 *) + specs.size() * sizeof(DotJob);
+    char *dbuf = nullptr;
+    HEC_CUDA(c, cudaMallocAsync(&dbuf, bytes, c->stream));
+    std::vector<char> h(bytes);
+    const u64 **hp = reinterpret_cast<const u64 **>(h.data());
+    const u64 **dp = reinterpret_cast<const u64 **>(dbuf);
+    DotJob *hj = reinterpret_cast<DotJob *>(h.data() + np * sizeof(u64 *));
+    size_t off = 0;
+    for (size_t i = 0; i < specs.size(); i++) {
+        const DotSpec &sp = specs[i];
+        hj[i].a = dp + off;
+        for (auto x : sp.a) hp[off++] = x;
+        hj[i].b = sp.b.empty() ? nullptr : dp + off;
+        for (auto x : sp.b) hp[off++] = x;
+        hj[i].out = sp.out; hj[i].mod = sp.mod; hj[i].T = (int)sp.a.size();
+    }
+    // pageable source: staged by the driver before the call returns, so `h` may die
+    HEC_CUDA(c, cudaMemcpyAsync(dbuf, h.data(), bytes, cudaMemcpyHostToDevice, c->stream));
+    for (size_t off = 0; off < specs.size(); off += 65535) { // grid.y limit
+        unsigned ny = (unsigned)std::min<size_t>(65535, specs.size() - off);
+        k_dot<<<dim3(32, ny), 256, 0, c->stream>>>(reinterpret_cast<const DotJob *>(dbuf + np * sizeof(u64 *)) + off, c->dmods);
+        c->launches += 1;
+    }
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(dbuf, c->stream);
+    if (e != cudaSuccess) return c->fail(HEC_E_CUDA, std::string("k_dot: ") + cudaGetErrorString(e));
+    return HEC_OK;
+}
+
 // SwitchKeysInPlaceNoModDown / KeyswitchHoistedNoModDown (L:rlwe/keyswitch.go:149-304): the inner product of
 // decomposition dc[i] (or the shared dc[0]) with key[i], left in Q||P: accQ[2i+p] [L][N], accP[2i+p] [nP][N], p = 0,1
 static int ks_mac_many(hec_ctx *c, int level, const std::vector<Decomp> &dc, const std::vector<const SwKey *> &key,
@@ -788,24 +823,26 @@ static int ks_mac_many(hec_ctx *c, int level, const std::vector<Decomp> &dc, con
     int beta = dc[0].beta;
     for (size_t i = 0; i < n; i++)
         if (key[i]->Lk < L || key[i]->ndig < beta) return c->fail(HEC_E_NOKEY, "switching key slice does not cover this level");
-    for (int d = 0; d < beta; d++) {
-        std::vector<EwJob> jobs;
-        for (size_t i = 0; i < n; i++) {
-            const Decomp &D = dc.size() == 1 ? dc[0] : dc[i];
-            int kl = key[i]->Lk + nP;
-            for (int p = 0; p < 2; p++)
-                for (int t = 0; t < W; t++) {
-                    const u64 *dh = D.D + ((size_t)d * W + t) * HEC_N;
-                    int kt = t < L ? t : key[i]->Lk + (t - L);
-                    const u64 *kp = key[i]->buf + ((size_t)(d * 2 + p) * kl + kt) * HEC_N;
-                    u64 *acc = t < L ? accQ[2 * i + p] + (size_t)t * HEC_N : accP[2 * i + p] + (size_t)(t - L) * HEC_N;
-                    jobs.push_back(ewjob(dh, kp, acc, t < L ? c->modQ(t) : c->modP(t - L)));
+    // one pass over all digits (k_dot): acc = sum_d digit_d * key_d, instead of one read-modify-write per digit
+    std::vector<DotSpec> specs;
+    for (size_t i = 0; i < n; i++) {
+        const Decomp &D = dc.size() == 1 ? dc[0] : dc[i];
+        int kl = key[i]->Lk + nP;
+        for (int p = 0; p < 2; p++)
+            for (int t = 0; t < W; t++) {
+                DotSpec sp;
+                int kt = t < L ? t : key[i]->Lk + (t - L);
+                for (int d = 0; d < beta; d++) {
+                    sp.a.push_back(D.D + ((size_t)d * W + t) * HEC_N);
+                    sp.b.push_back(key[i]->buf + ((size_t)(d * 2 + p) * kl + kt) * HEC_N);
                 }
-        }
-        rc = d == 0 ? launch_ew<EW_MULMONT>(c, jobs) : launch_ew<EW_MAC>(c, jobs);
-        if (rc) return rc;
+                sp.out = t < L ? accQ[2 * i + p] + (size_t)t * HEC_N : accP[2 * i + p] + (size_t)(t - L) * HEC_N;
+                sp.mod = t < L ? c->modQ(t) : c->modP(t - L);
+                specs.push_back(sp);
+            }
     }
-    return HEC_OK;
+    (void)rc;
+    return launch_dot(c, specs);
 }
 static int keyswitch_many(hec_ctx *c, int level, const std::vector<Decomp> &dc, const std::vector<const SwKey *> &key,
                           const std::vector<u64 *> &d0, const std::vector<u64 *> &d1) {

@@ -81,38 +81,6 @@ static int conv_then_pack_oplevel(hec_ctx *ev, const hec_ct *ctxt_in, const hec_
 int hec_rotate_many(hec_ctx *c, const std::vector<const hec_ct *> &ct, const std::vector<u64> &galEl,
                     const std::vector<hec_ct *> &out, bool hoisted);
 
-// launch k_dot for a list of (a pointers, b pointers or none, out, modulus) sums; the pointer lists are
-// staged into one stream-ordered device buffer
-struct DotSpec { std::vector<const u64 *> a, b; u64 *out; int mod; };
-static int launch_dot(hec_ctx *c, const std::vector<DotSpec> &specs) {
-    size_t np = 0;
-    for (auto &sp : specs) np += sp.a.size() + sp.b.size();
-    size_t bytes = np * sizeof(u64 *) + specs.size() * sizeof(DotJob);
-    char *dbuf = nullptr;
-    HEC_CUDA(c, cudaMallocAsync(&dbuf, bytes, c->stream));
-    std::vector<char> h(bytes);
-    const u64 **hp = reinterpret_cast<const u64 **>(h.data());
-    const u64 **dp = reinterpret_cast<const u64 **>(dbuf);
-    DotJob *hj = reinterpret_cast<DotJob *>(h.data() + np * sizeof(u64 *));
-    size_t off = 0;
-    for (size_t i = 0; i < specs.size(); i++) {
-        const DotSpec &sp = specs[i];
-        hj[i].a = dp + off;
-        for (auto x : sp.a) hp[off++] = x;
-        hj[i].b = sp.b.empty() ? nullptr : dp + off;
-        for (auto x : sp.b) hp[off++] = x;
-        hj[i].out = sp.out; hj[i].mod = sp.mod; hj[i].T = (int)sp.a.size();
-    }
-    // pageable source: staged by the driver before the call returns, so `h` may die
-    HEC_CUDA(c, cudaMemcpyAsync(dbuf, h.data(), bytes, cudaMemcpyHostToDevice, c->stream));
-    k_dot<<<dim3(32, (unsigned)specs.size()), 256, 0, c->stream>>>(reinterpret_cast<const DotJob *>(dbuf + np * sizeof(u64 *)), c->dmods);
-    c->launches += 1;
-    cudaError_t e = cudaGetLastError();
-    cudaFreeAsync(dbuf, c->stream);
-    if (e != cudaSuccess) return c->fail(HEC_E_CUDA, std::string("k_dot: ") + cudaGetErrorString(e));
-    return HEC_OK;
-}
-
 extern "C" int hec_conv_bl(hec_ctx *ev, const hec_ct *ct_input, int in_wid, int ker_wid, int rot_iters, int rot_step,
                            const hec_pt *const *pt_taps, const hec_pt *pl_bn_b, hec_ct **out) {
     if (!ev || !ct_input || !pt_taps || !out || ker_wid < 1 || !(ker_wid & 1) || rot_iters < 1) return ev ? ev->fail(HEC_E_INVAL, "conv_bl args") : HEC_E_INVAL;

@@ -181,7 +181,7 @@ static int launch_modup(hec_ctx *c, std::vector<ModupJob> &jobs) {
     std::vector<Modup2Target> targets;
     std::vector<size_t> first; // index of each group's first target
     for (const ModupJob &j : jobs) {
-        bool same = !groups.empty() && groups.back().n == j.n;
+        bool same = !groups.empty() && groups.back().n == j.n && groups.back().ntargets < HEC_M2_MAXT;
         for (int s = 0; same && s < j.n; s++) same = groups.back().src[s] == j.src[s] && groups.back().smod[s] == j.smod[s];
         if (!same) {
             Modup2Job g;

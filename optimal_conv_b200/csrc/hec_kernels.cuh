@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(256) k_modup(ModupJobs J, const ModC *__restri
 // The same extension for ALL targets of one source digit: y_i and the float overflow count v depend only on the
 // source, so they are computed once per coefficient (the per-target form above recomputes alpha Montgomery products
 // and alpha double divisions for each of the up to nQ + nP - alpha targets: it was 51 % of a full-level key switch).
+#define HEC_M2_MAXT 48 // targets per group (host splits larger groups); nQ + nP <= 33 in the reference's sets
 struct Modup2Target { u64 *dst; u64 qisp[HEC_MAXA]; u64 qpjinv[HEC_MAXA + 1]; int tmod; };
 struct Modup2Job {
     const u64 *src[HEC_MAXA];
@@ -206,8 +207,13 @@ __global__ void __launch_bounds__(256) k_modup2(const Modup2Job *__restrict__ jo
         }
     }
     const u64 v = (u64)__double2ull_rz(vi);
+    // the per-target tables (<= nQ + nP entries of 104 B) are the same for every thread: stage them in shared memory
+    __shared__ Modup2Target sT[HEC_M2_MAXT];
+    for (int k = threadIdx.x; k < job.ntargets * (int)(sizeof(Modup2Target) / 8); k += blockDim.x)
+        reinterpret_cast<u64 *>(sT)[k] = reinterpret_cast<const u64 *>(job.targets)[k];
+    __syncthreads();
     for (int t = 0; t < job.ntargets; t++) {
-        const Modup2Target &T = job.targets[t];
+        const Modup2Target &T = sT[t];
         const u64 pt = mods[T.tmod].q, ptinv = mods[T.tmod].qinv;
         u64 acc = 0;
 #pragma unroll

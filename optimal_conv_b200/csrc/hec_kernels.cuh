@@ -215,10 +215,19 @@ __global__ void __launch_bounds__(256) k_modup2(const Modup2Job *__restrict__ jo
     for (int t = 0; t < job.ntargets; t++) {
         const Modup2Target &T = sT[t];
         const u64 pt = mods[T.tmod].q, ptinv = mods[T.tmod].qinv;
-        u64 acc = 0;
+        // multSum (L:ring/ring_basis_extension.go:715-779): the alpha products are summed as 128-bit integers and
+        // reduced once -- each is < 2^61 p_t, so the sum of <= 5 stays below p_t 2^64, the domain of one REDC
+        u64 lo = 0, hi = 0;
 #pragma unroll
         for (int s = 0; s < HEC_MAXA; s++)
-            if (s < job.n) acc = addmod(acc, mred(y[s], T.qisp[s], pt, ptinv), pt);
+            if (s < job.n) {
+                const u64 pl = y[s] * T.qisp[s], ph = __umul64hi(y[s], T.qisp[s]);
+                lo += pl;
+                hi += ph + (lo < pl);
+            }
+        const u64 mq = __umul64hi(lo * ptinv, pt);
+        u64 acc = hi - mq;
+        if (hi < mq) acc += pt;
         T.dst[i] = addmod(acc, T.qpjinv[v], pt);
     }
 }

@@ -168,6 +168,10 @@ typedef struct {
 int hec_mod_up(hec_ctx *ctx, const hec_ct *ct, hec_ct **out);
 int hec_bootstrap_ctos(hec_ctx *ctx, const hec_ct *ct, const hec_btp_params *bp, const hec_ptdiag *const *pdftinv, int nmat,
                        hec_ct **ct0, hec_ct **ct1, double *constant);
+/* btp.Bootstrapp(ct) (test_BL.go:133), the un-split bootstrapping of the baseline network: the same head, then
+ * SlotsToCoeffs with the pDFT factors */
+int hec_bootstrapp(hec_ctx *ctx, const hec_ct *ct, const hec_btp_params *bp, const hec_ptdiag *const *pdftinv, int ninv,
+                   const hec_ptdiag *const *pdft, int nfwd, hec_ct **out);
 /* btp.BootstrappConv_StoC(ct0, ct1) (eval.go:540-560) = SlotsToCoeffs(ct0, ct1, btp.pDFT, evaluator); ct1 may be NULL.
  * The caller rescales afterwards (eval.go:562: hec_rescale). */
 int hec_bootstrap_stoc(hec_ctx *ctx, const hec_ct *ct0, const hec_ct *ct1, const hec_ptdiag *const *pdft, int nmat, hec_ct **out);

@@ -358,10 +358,12 @@ static int btp_evaluate_cheby(hec_ctx *c, hec_ct **pct, const hec_btp_params *b)
     return rc;
 }
 
-extern "C" int hec_bootstrap_ctos(hec_ctx *c, const hec_ct *ct_in, const hec_btp_params *b, const hec_ptdiag *const *pdftinv, int nmat,
-                                  hec_ct **ct0, hec_ct **ct1, double *constant) {
+// the common head of Bootstrapp (0x505d00) and BootstrappConv_CtoS (0x506800): to the bootstrapping scale at level 0,
+// modUp, ScaleUp, CoeffsToSlots, evaluateSine on both halves
+static int btp_until_sine(hec_ctx *c, const hec_ct *ct_in, const hec_btp_params *b, const hec_ptdiag *const *pdftinv, int nmat,
+                          hec_ct **ct0, hec_ct **ct1) {
     if (!c || !ct_in || !b || !pdftinv || nmat < 1 || !ct0 || !ct1 || !b->cheby || !b->sine_qi || b->n_sine_qi < b->sin_rescal)
-        return c ? c->fail(HEC_E_INVAL, "bootstrap_ctos args") : HEC_E_INVAL;
+        return c ? c->fail(HEC_E_INVAL, "bootstrap args") : HEC_E_INVAL;
     cudaSetDevice(c->device);
     if (b->arcsine_deg > 0) return c->fail(HEC_E_UNSUPPORTED, "ArcSineDeg > 0 is not implemented");
     hec_ct *ct = nullptr, *up = nullptr, *r0 = nullptr, *r1 = nullptr;
@@ -395,19 +397,43 @@ extern "C" int hec_bootstrap_ctos(hec_ctx *c, const hec_ct *ct_in, const hec_btp
         rc = btp_evaluate_cheby(c, halves[h], b);
         if (!rc) { x = *halves[h]; volatile double d = b->postscale * b->message_ratio / b->params_scale; x->scale = x->scale / d; }
     }
+    hec_ct_free(c, ct); hec_ct_free(c, up);
+    if (rc) { hec_ct_free(c, r0); hec_ct_free(c, r1); return rc; }
+    *ct0 = r0; *ct1 = r1;
+    return HEC_OK;
+}
+
+extern "C" int hec_bootstrap_ctos(hec_ctx *c, const hec_ct *ct_in, const hec_btp_params *b, const hec_ptdiag *const *pdftinv, int nmat,
+                                  hec_ct **ct0, hec_ct **ct1, double *constant) {
+    hec_ct *r0 = nullptr, *r1 = nullptr;
+    int rc = btp_until_sine(c, ct_in, b, pdftinv, nmat, &r0, &r1);
+    if (rc) return rc;
+    // the fork's tail: both halves times (q0 / 2^round(log2 q0)) * params.Scale / postscale, then Rescale
     double q0 = (double)c->q(0);
     volatile double k = q0 / exp2(go_round(log2(q0)));
     k = k * b->params_scale;
     k = k / b->postscale;
+    hec_ct *halves[2] = {r0, r1};
     for (int h = 0; h < 2 && !rc; h++) {
-        rc = hec_mult_by_const(c, *halves[h], k);
-        if (!rc) rc = hec_rescale(c, *halves[h], b->params_scale);
+        rc = hec_mult_by_const(c, halves[h], k);
+        if (!rc) rc = hec_rescale(c, halves[h], b->params_scale);
     }
-    hec_ct_free(c, ct); hec_ct_free(c, up);
     if (rc) { hec_ct_free(c, r0); hec_ct_free(c, r1); return rc; }
     *ct0 = r0; *ct1 = r1;
     if (constant) *constant = k;
     return HEC_OK;
+}
+
+// btp.Bootstrapp(ct) (test_BL.go:133): the head above, then SlotsToCoeffs with the pDFT factors; the fork returns that
+// result as it is (no final rounding of the scale)
+extern "C" int hec_bootstrapp(hec_ctx *c, const hec_ct *ct_in, const hec_btp_params *b, const hec_ptdiag *const *pdftinv, int ninv,
+                              const hec_ptdiag *const *pdft, int nfwd, hec_ct **out) {
+    if (!out || !pdft || nfwd < 1) return c ? c->fail(HEC_E_INVAL, "bootstrapp args") : HEC_E_INVAL;
+    hec_ct *r0 = nullptr, *r1 = nullptr;
+    int rc = btp_until_sine(c, ct_in, b, pdftinv, ninv, &r0, &r1);
+    if (!rc) rc = hec_slots_to_coeffs(c, r0, r1, pdft, nfwd, out);
+    hec_ct_free(c, r0); hec_ct_free(c, r1);
+    return rc;
 }
 
 // btp.BootstrappConv_StoC(ct0, ct1) (eval.go:540-560): in the reference binary it is SlotsToCoeffs(ct0, ct1, btp.pDFT,

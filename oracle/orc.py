@@ -365,11 +365,9 @@ class Oracle:
             ct = self.rescale(self.add_const(ct, -s), b["sinescale"])
         return ct
 
-    def bootstrapp_conv_ctos(self, ct, b, keys, key_conj, rlk):
-        """BootstrappConv_CtoS: scale to the bootstrapping scale at level 0, modUp, CoeffsToSlots, sine evaluation on the
-        real and imaginary halves, and the fork's final constant multiplication + Rescale.  b: the Bootstrapper's fields
-        (prescale, postscale, sinescale, sqrt2pi, sc_fac, message_ratio, sin_type, sin_rescal, sine_qi, cheby = (coeffs,
-        a, b), mats = pDFTInv factors, params_scale).  Returns (ct0, ct1, constant)."""
+    def _btp_until_sine(self, ct, b, keys, key_conj, rlk):
+        """common head of Bootstrapp / BootstrappConv_CtoS: to the bootstrapping scale at level 0, modUp, ScaleUp,
+        CoeffsToSlots, evaluateSine on both halves"""
         while ct.level > 1:
             ct = self.drop_level(ct, 1)
         if ct.level == 1:
@@ -392,6 +390,20 @@ class Oracle:
             c = self.btp_evaluate_cheby(c, b, rlk)
             c.scale = c.scale / (b["postscale"] * b["message_ratio"] / b["params_scale"])
             outs.append(c)
+        return outs
+
+    def bootstrapp(self, ct, b, stoc_mats, keys, key_conj, rlk):
+        """Bootstrapper.Bootstrapp (test_BL.go:133; 0x505d00 in the reference binary): the head above, then
+        SlotsToCoeffs with the pDFT factors; the fork returns that result as it is"""
+        c0, c1 = self._btp_until_sine(ct, b, keys, key_conj, rlk)
+        return self.slots_to_coeffs(c0, c1, stoc_mats, keys)
+
+    def bootstrapp_conv_ctos(self, ct, b, keys, key_conj, rlk):
+        """BootstrappConv_CtoS: scale to the bootstrapping scale at level 0, modUp, CoeffsToSlots, sine evaluation on the
+        real and imaginary halves, and the fork's final constant multiplication + Rescale.  b: the Bootstrapper's fields
+        (prescale, postscale, sinescale, sqrt2pi, sc_fac, message_ratio, sin_type, sin_rescal, sine_qi, cheby = (coeffs,
+        a, b), mats = pDFTInv factors, params_scale).  Returns (ct0, ct1, constant)."""
+        outs = self._btp_until_sine(ct, b, keys, key_conj, rlk)
         q0 = float(self.Q[0])
         const = q0 / float(2.0 ** np.round(np.log2(q0))) * b["params_scale"] / b["postscale"]
         outs = [self.rescale(self.mul_const(c, const), b["params_scale"]) for c in outs]

@@ -3,7 +3,7 @@
 Run from the repo root in the build container (needs /root/reference/test_run, objdump, nm):
     python tests/golden/make_ref_eval_vectors.py            # small-N cases, ~2 min
     python tests/golden/make_ref_eval_vectors.py --only n8_B4      # regenerate one small conv case
-    python tests/golden/make_ref_eval_vectors.py --evalops | --relu | --lt | --ctos | --ring | --conv  # regenerate one group
+    python tests/golden/make_ref_eval_vectors.py --evalops | --relu | --lt | --ctos | --btp | --ring | --conv  # regenerate one group
     python tests/golden/make_ref_eval_vectors.py --full B4_norm1   # N = 2^16 golden config, ~1 h
 The prebuilt binary is never executed.  tests/golden/refmachine.py interprets the compiled routines of
 the Lattigo fork (ring / rlwe / ckks packages) and of package main from their disassembly; objects
@@ -446,7 +446,16 @@ def ctos_operands(N):
     return keys, key(9900), key(8000), b
 
 
-def ctos_case(level_in):
+BTP_STOC_SPECS = [(2, [0, 1, 2], 15), (2, [0, 1, 3], 14), (2, [1, 2], 13)]   # pDFT for the un-split Bootstrapp
+
+
+def btp_stoc_mats(N):
+    Q, P = PR.Q_SET6, PR.P_ALL
+    return [({d: (synth.uniform_limbs(7800 + 100 * mi + d, Q[:ml + 1], N), synth.uniform_limbs(7900 + 100 * mi + d, P, N)) for d in diags},
+             n1, ml, float(Q[ml])) for mi, (n1, diags, ml) in enumerate(BTP_STOC_SPECS)]
+
+
+def ctos_case(level_in, whole=False):
     """ckks.(*Bootstrapper).BootstrappConv_CtoS on a hand-built Bootstrapper (struct layout from the DWARF): SetScale /
     ScaleUp to the bootstrapping scale, modUp, ScaleUp, CoeffsToSlots, evaluateSine (EvaluateCheby + double angle), the
     fork's final MultByConst + Rescale.  N = 2^4, the whole 28-level chain, alpha = 5."""
@@ -489,9 +498,28 @@ def ctos_case(level_in):
         m.wq(btp + off, f2b(b[k]))
     m.wq(btp + 536, cheb)
     m.write_u64s(btp + 608, m.slice_u64(ptrs))           #   pDFTInv
+    if whole:                                            #   pDFT (only Bootstrapp reads it)
+        fptrs = []
+        for D, n1, ml, ms in btp_stoc_mats(N):
+            vec = m.new_map(16)
+            for d, (dq, dp) in D.items():
+                pq, pp = m.new_poly([ints(l) for l in dq]), m.new_poly([ints(l) for l in dp])
+                for p in (pq, pp):
+                    m.wb(p + 24, 1)
+                    m.wb(p + 25, 1)
+                m.map_put(vec, d, [pq, pp])
+            mat = m.alloc(48)
+            m.write_u64s(mat, [logN - 1, n1, ml, f2b(ms), vec, 0])
+            fptrs.append(mat)
+        m.write_u64s(btp + 584, m.slice_u64(fptrs))
     ct_scale = PR.SCALE * 2.0 ** 8
     lim = lambda seed: [ints(l) for l in synth.uniform_limbs(seed, Q[:level_in + 1], N)]  # noqa: E731
     ct = m.new_ct([lim(61), lim(62)], ct_scale)
+    if whole:
+        res = m.call(CKKS + "(*Bootstrapper).Bootstrapp", [btp, ct, 0], max_steps=1 << 62)
+        rec = {"logN": logN, "level_in": level_in, "ct_scale": ct_scale, "out": digest_ct(m, res[-1]), "interpreted_instructions": m.steps}
+        print("Bootstrapp case level_in=%d: %d instructions" % (level_in, m.steps), flush=True)
+        return rec
     res = m.call(CKKS + "(*Bootstrapper).BootstrappConv_CtoS", [btp, ct, 0, 0, 0], max_steps=1 << 62)
     rec = {"logN": logN, "level_in": level_in, "ct_scale": ct_scale, "out": [digest_ct(m, res[-3]), digest_ct(m, res[-2])],
            "const_bits": res[-1], "interpreted_instructions": m.steps}
@@ -523,7 +551,7 @@ def main():
         new["conv"] = {name: conv_case(logN, B, norm, seed, out_scale, Q2, P1)
                        for name, logN, B, norm, seed, out_scale, Q2, P1 in SMALL_CONV if name in sys.argv}
     else:
-        groups = [g for g in ("relu", "evalops", "lt", "ctos", "ring", "conv") if "--" + g in sys.argv] or ["relu", "evalops", "lt", "ctos", "ring", "conv"]
+        groups = [g for g in ("relu", "evalops", "lt", "ctos", "btp", "ring", "conv") if "--" + g in sys.argv] or ["relu", "evalops", "lt", "ctos", "btp", "ring", "conv"]
         if "relu" in groups:
             new["relu"] = {name: relu_case(logN, alpha, level) for name, logN, alpha, level in RELU_CASES}
             new["cheby"] = {name: cheby_case(deg, level) for name, deg, level in CHEBY_CASES}
@@ -532,6 +560,8 @@ def main():
             new["dft"] = dft_case()
         if "ctos" in groups:
             new["ctos"] = {"level%d" % lv: ctos_case(lv) for lv in (1, 0, 3)}
+        if "btp" in groups:
+            new["bootstrapp"] = {"level%d" % lv: ctos_case(lv, whole=True) for lv in (1, 0)}
         if "evalops" in groups:
             new["evalops"] = {name: evalop_case(logN, Q, P, level, rots) for name, logN, Q, P, level, rots in EVALOP_CASES}
             new["pre_conv_bl"] = pre_conv_bl_case()

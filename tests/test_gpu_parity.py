@@ -444,6 +444,12 @@ def test_bootstrapp_conv_ctos_full_chain():
         up, uref = c.ModUp(c.upload_ct(low.c0, low.c1, low.scale)), o.mod_up(low)
         x0, x1 = up.download()
         assert up.level == uref.level == 27 and np.array_equal(x0, uref.c0) and np.array_equal(x1, uref.c1)
+        fwd = G.btp_stoc_mats(N)                       # the un-split Bootstrapp of the baseline network (test_BL.go:133)
+        hfwd = [c.upload_ptdiag(PR.LOGN - 1, n1, ml, ms, D) for D, n1, ml, ms in fwd]
+        whole, wref = c.Bootstrapp(A, b, mats, hfwd), o.bootstrapp(a, b, fwd, keys, kconj, rlk)
+        x0, x1 = whole.download()
+        assert whole.level == wref.level == 12 and whole.scale == wref.scale
+        assert np.array_equal(x0, wref.c0) and np.array_equal(x1, wref.c1)
         g0, g1, k = c.BootstrappConv_CtoS(A, b, mats)
         r0, r1, kref = o.bootstrapp_conv_ctos(a, b, keys, kconj, rlk)
         assert k == kref

@@ -217,6 +217,23 @@ def test_bootstrapp_conv_ctos_matches_reference_code(name):
     assert struct.unpack("<Q", struct.pack("<d", const))[0] == rec["const_bits"]
 
 
+@pytest.mark.parametrize("name", sorted(REF["bootstrapp"]))
+def test_bootstrapp_matches_reference_code(name):
+    """ckks.(*Bootstrapper).Bootstrapp (interpreted): the un-split bootstrapping the baseline network uses
+    (test_BL.go:133) -- the CtoS head, the sine evaluation, SlotsToCoeffs with three factors == the oracle"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_ref_eval_vectors as G
+    rec = REF["bootstrapp"][name]
+    N = 1 << rec["logN"]
+    Q, P = PR.Q_SET6, PR.P_ALL
+    o = Oracle(rec["logN"], Q, P)
+    keys, kconj, rlk, b = G.ctos_operands(N)
+    lv = rec["level_in"]
+    ct = Ct(synth.uniform_limbs(61, Q[:lv + 1], N), synth.uniform_limbs(62, Q[:lv + 1], N), rec["ct_scale"])
+    assert dg(o.bootstrapp(ct, b, G.btp_stoc_mats(N), keys, kconj, rlk)) == rec["out"]
+
+
 def cheby_coeffs(deg):
     rng = np.random.default_rng(1000 + deg)
     co = [float(x) for x in rng.uniform(-1, 1, deg + 1)]

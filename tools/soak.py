@@ -32,7 +32,7 @@ for it in range(iters):
     bad += h.hexdigest() != want
 print("fused plan: %d iterations, %d mismatches" % (iters, bad))
 g = (1 << 13) + 1
-ct = G.cts[0]
+ct = plan.run(G.cts)[0]   # a level-0 ciphertext: the pack keys are uploaded for level 0 only
 first = None
 for it in range(iters):
     out = c.CopyNew(ct)

@@ -20,8 +20,13 @@
  *   ring   primitiveRoot (35 moduli), NewRing tables, NTT/InvNTT(+Lazy), PermuteNTTIndex,
  *          reconstructRNS+multSum, divRoundByLastModulusNTT, ModDownSplitNTTPQ
  *   rlwe   NewKeySwitcher, SwitchKeysInPlace (alpha = 1, 2, 5; every level)
- *   ckks   NewEvaluator, MulNew, Add/Sub, Add(ct,pt), Rescale, RotateNew, RotateHoisted
- *   main   conv_then_pack (+ pack_ctxts, + the bias Add of evalConv_BN), incl. its panic
+ *   ckks   NewEvaluator, MulNew, MulRelinNew, Add/Sub (scale matching, every aliasing), Add(ct,pt), Rescale,
+ *          MulByPow2, MultByi/DivByi, Conjugate, RotateNew, RotateHoisted, EvaluatePoly, EvaluateCheby,
+ *          LinearTransform (MultiplyByDiagMatrixBSGS), CoeffsToSlots, SlotsToCoeffs,
+ *          Bootstrapper.modUp / BootstrappConv_CtoS / Bootstrapp
+ *   main   conv_then_pack (+ pack_ctxts, + the bias Add of evalConv_BN) incl. its panic, at N = 2^8..2^10 and
+ *          for all four golden configs at N = 2^16; preConv_BL; evalReLU
+ * (the compositions above the ring / key-switch level live in orc.py, on top of the C routines of this file)
  * Go-runtime services the interpreted code calls (allocation, maps, math/big, prime
  * factorisation of q-1) are supplied in Python and listed in refmachine.py.  In addition:
  * algebraic self-tests, a semantic encrypt -> conv -> decrypt test against a float

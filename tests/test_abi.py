@@ -49,3 +49,19 @@ def test_product_path_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.lower().replace("no oracle", ""), f
+
+
+def test_btp_params_struct_layout_matches_the_header(tmp_path):
+    """the ctypes mirror of hec_btp_params must have the C compiler's size and field offsets"""
+    import ctypes
+    import subprocess
+    from optimal_conv_b200 import hec
+    fields = [f[0] for f in hec.BtpParams._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stddef.h>\n#include <stdio.h>\n#include "hec.h"\nint main(void) { printf("%zu", sizeof(hec_btp_params));\n'
+                   + "".join('printf(" %%zu", offsetof(hec_btp_params, %s));\n' % f for f in fields) + "return 0; }\n")
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert out[0] == ctypes.sizeof(hec.BtpParams)
+    assert out[1:] == [getattr(hec.BtpParams, f).offset for f in fields]

@@ -290,9 +290,13 @@ def cheby_coeffs(deg):
     return co
 
 
-def cheby_case(deg, level, logN=5):
+POLY_CASES = [("deg5_level15", 5, 15), ("deg12_level15", 12, 15), ("deg31_level9", 31, 9)]
+
+
+def cheby_case(deg, level, logN=5, power_basis=False):
     """ckks.(*evaluator).EvaluateCheby (L:ckks/polynomial_evaluation.go) with seeded real Chebyshev coefficients
-    (degree 63 is the bootstrapper's SinDeg), first 16 moduli of set 6, alpha = 5"""
+    (degree 63 is the bootstrapper's SinDeg), first 16 moduli of set 6, alpha = 5; power_basis: EvaluatePoly with the
+    same dense coefficients (evalReLU only exercises odd polynomials)"""
     N = 1 << logN
     Q, P = PR.Q_SET6[:16], PR.P_ALL
     m = Machine()
@@ -307,11 +311,12 @@ def cheby_case(deg, level, logN=5):
         m.write_u64s(carr + 16 * i, [f2b(c), 0])                      # complex128{re, im}
     cheb = m.alloc(72)                                                 # ChebyshevInterpolation{Poly{maxDeg, coeffs, lead}, a, b}
     m.write_u64s(cheb, [deg, carr, deg + 1, deg + 1, 1, f2b(-1.0), 0, f2b(1.0), 0])
-    res = m.call(CKKS + "(*evaluator).EvaluateCheby", [ev[1], ct, cheb, f2b(PR.SCALE), 0, 0, 0], max_steps=1 << 62)
+    res = m.call(CKKS + ("(*evaluator).EvaluatePoly" if power_basis else "(*evaluator).EvaluateCheby"),
+                 [ev[1], ct, cheb, f2b(PR.SCALE), 0, 0, 0], max_steps=1 << 62)      # *ChebyshevInterpolation starts with its Poly
     assert not (res[-2] or res[-1])
     rec = {"logN": logN, "degree": deg, "level": level, "Q": ["%x" % q for q in Q], "P": ["%x" % p for p in P],
            "out": digest_ct(m, res[-3]), "interpreted_instructions": m.steps}
-    print("EvaluateCheby case degree=%d level=%d: %d instructions" % (deg, level, m.steps), flush=True)
+    print("%s case degree=%d level=%d: %d instructions" % ("EvaluatePoly" if power_basis else "EvaluateCheby", deg, level, m.steps), flush=True)
     return rec
 
 
@@ -555,6 +560,7 @@ def main():
         if "relu" in groups:
             new["relu"] = {name: relu_case(logN, alpha, level) for name, logN, alpha, level in RELU_CASES}
             new["cheby"] = {name: cheby_case(deg, level) for name, deg, level in CHEBY_CASES}
+            new["poly"] = {name: cheby_case(deg, level, power_basis=True) for name, deg, level in POLY_CASES}
         if "lt" in groups:
             new["linear_transform"] = {name: lt_case(*a) for name, *a in LT_CASES}
             new["dft"] = dft_case()

@@ -253,6 +253,19 @@ def test_evaluate_cheby_matches_reference_code(name):
     assert dg(o.evaluate_poly(ct, cheby_coeffs(rec["degree"]), PR.SCALE, rlk, PR.SCALE, cheby=True)) == rec["out"]
 
 
+@pytest.mark.parametrize("name", sorted(REF["poly"]))
+def test_evaluate_poly_dense_matches_reference_code(name):
+    """ckks.(*evaluator).EvaluatePoly (interpreted) with dense real coefficients of degree 5, 12, 31 == the oracle
+    (evalReLU only exercises odd polynomials of degree 7 and 13)"""
+    rec = REF["poly"][name]
+    Q, P = mods(rec)
+    N, level = 1 << rec["logN"], rec["level"]
+    o = Oracle(rec["logN"], Q, P)
+    rlk = np.stack([np.stack([synth.uniform_limbs(8000 + 10 * d + k, Q + P, N) for k in range(2)]) for d in range(o.beta_full)])
+    ct = Ct(synth.uniform_limbs(61, Q[:level + 1], N), synth.uniform_limbs(62, Q[:level + 1], N), PR.SCALE)
+    assert dg(o.evaluate_poly(ct, cheby_coeffs(rec["degree"]), PR.SCALE, rlk, PR.SCALE)) == rec["out"]
+
+
 FULL = sorted(REF.get("conv_full", {}))
 
 

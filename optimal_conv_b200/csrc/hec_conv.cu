@@ -240,7 +240,7 @@ struct hec_plan {
 static int plan_launch_all(hec_plan *p, const std::function<void()> &after = [] {}) {
     hec_ctx *c = p->c;
     cudaStream_t s = c->stream;
-    dim3 gA(HEC_TILES_PER_LIMB, p->M * p->na * 2);
+    dim3 gA = HEC_GRID(HEC_TILES_PER_LIMB, p->M * p->na * 2);
     k_convA1<<<gA, HEC_THREADS, 0, s>>>(p->pa, c->dmods);
     after();
     k_convA2<<<gA, HEC_THREADS, 0, s>>>(p->pa, c->dmods);
@@ -249,7 +249,7 @@ static int plan_launch_all(hec_plan *p, const std::function<void()> &after = [] 
     after();
     for (auto &b : p->pb) {
         int nb = b.n / 2;
-        dim3 g1(HEC_TILES_PER_LIMB, p->M * nb), g2(HEC_TILES_PER_LIMB, p->M * nb * 2);
+        dim3 g1 = HEC_GRID(HEC_TILES_PER_LIMB, p->M * nb), g2 = HEC_GRID(HEC_TILES_PER_LIMB, p->M * nb * 2);
         k_convB1<<<g1, HEC_THREADS, 0, s>>>(b, c->dmods);
         after();
         k_convB2<<<g1, HEC_THREADS, 0, s>>>(b, c->dmods);

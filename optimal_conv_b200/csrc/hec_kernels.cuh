@@ -235,6 +235,18 @@ __global__ void __launch_bounds__(256) k_modup2(const Modup2Job *__restrict__ jo
 // =========================================================================================
 // (2) fused conv_then_pack kernels
 // =========================================================================================
+// Grid order of the fused kernels.  The tile index selects the twiddles (one 65 KB set per tile for the row kernels);
+// with the job index fastest, the CTAs that follow each other on an SM share their tile, so the twiddles they stream stay
+// in L1 instead of cycling through four tiles' worth (148 mod 16 = 4).
+#ifdef HEC_GRID_TILE_FASTEST
+#define HEC_BTILE blockIdx.x
+#define HEC_BJOB blockIdx.y
+#define HEC_GRID(tiles, jobs) dim3((tiles), (jobs))
+#else
+#define HEC_BTILE blockIdx.y
+#define HEC_BJOB blockIdx.x
+#define HEC_GRID(tiles, jobs) dim3((jobs), (tiles))
+#endif
 // ---- Stage A: for every active output channel i and poly c (conv.go:525-531):
 //   MulNew(ct_in, pl_ker[i])   L:ckks/evaluator.go:1360-1444 (pt branch)
 //   SetScale -> MultByConst    L:ckks/evaluator.go:782-863 (constants from the host)
@@ -257,9 +269,9 @@ struct AJob {
 // A1: limb q1:  ct*(pt*k1) -> inverse stages t = 1..128
 __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convA1(ConvA P, const ModC *__restrict__ mods) {
     __shared__ u64 sm[16 * HEC_ROW_PITCH];
-    const AJob J(blockIdx.y, P.na);
+    const AJob J(HEC_BJOB, P.na);
     const ModC M = mods[P.mq1];
-    RowGeom G(blockIdx.x);
+    RowGeom G(HEC_BTILE);
     const u64 *ct = P.ctin[J.m] + (size_t)(J.c * 2 + 1) * HEC_N;
     const u64 *pt = P.ptk[J.a * P.norm] + HEC_N;
     u64 x[16];
@@ -270,16 +282,16 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convA1(ConvA P, const
     }
     row_AtoB(x, sm, G);
     row_inv8(x, sm, G, M);
-    row_storeA(x, P.w1 + (size_t)blockIdx.y * HEC_N, G);
+    row_storeA(x, P.w1 + (size_t)HEC_BJOB * HEC_N, G);
 }
 // A2: finish InvNTT_q1, centre, lift into q0, forward stages m = 1..128 under q0
 __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convA2(ConvA P, const ModC *__restrict__ mods) {
     __shared__ u64 sm[HEC_TILE];
     const ModC M1 = mods[P.mq1];
     const ModC M0 = mods[P.mq0];
-    ColGeom G(blockIdx.x);
-    const u64 *in = P.w1 + (size_t)blockIdx.y * HEC_N;
-    u64 *out = P.w2 + (size_t)blockIdx.y * HEC_N;
+    ColGeom G(HEC_BTILE);
+    const u64 *in = P.w1 + (size_t)HEC_BJOB * HEC_N;
+    u64 *out = P.w2 + (size_t)HEC_BJOB * HEC_N;
     u64 x[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) x[k] = in[G.gB(k)];
@@ -298,16 +310,16 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convA2(ConvA P, const
 // A3: finish NTT_q0, combine with limb q0 of ct*(pt*k0):  out = (p0 - u) * q1^-1
 __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convA3(ConvA P, const ModC *__restrict__ mods) {
     __shared__ u64 sm[16 * HEC_ROW_PITCH];
-    const AJob J(blockIdx.y, P.na);
+    const AJob J(HEC_BJOB, P.na);
     const ModC M = mods[P.mq0];
-    RowGeom G(blockIdx.x);
+    RowGeom G(HEC_BTILE);
     const u64 *ct = P.ctin[J.m] + (size_t)(J.c * 2) * HEC_N;
     const u64 *pt = P.ptk[J.a * P.norm];
     u64 x[16];
-    row_loadA(x, P.w2 + (size_t)blockIdx.y * HEC_N, G);
+    row_loadA(x, P.w2 + (size_t)HEC_BJOB * HEC_N, G);
     row_fwd8(x, sm, G, M);
     row_BtoA(x, sm, G);
-    u64 *out = P.xout + (size_t)blockIdx.y * HEC_N; // ((m*na + a)*2 + c) == job
+    u64 *out = P.xout + (size_t)HEC_BJOB * HEC_N; // ((m*na + a)*2 + c) == job
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         u32 i = G.gbase + 16 * k;
@@ -349,9 +361,9 @@ struct BJob {
 // B1: z = tmp2.c1 = a1 - b1*mono ; inverse stages t = 1..128 under q0      grid.y = M*nb
 __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convB1(ConvB P, const ModC *__restrict__ mods) {
     __shared__ u64 sm[16 * HEC_ROW_PITCH];
-    const BJob J(blockIdx.y, false, P);
+    const BJob J(HEC_BJOB, false, P);
     const ModC M = mods[P.mq0];
-    RowGeom G(blockIdx.x);
+    RowGeom G(HEC_BTILE);
     u64 x[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) {
@@ -360,16 +372,16 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convB1(ConvB P, const
     }
     row_AtoB(x, sm, G);
     row_inv8(x, sm, G, M);
-    row_storeA(x, P.w1 + (size_t)blockIdx.y * HEC_N, G);
+    row_storeA(x, P.w1 + (size_t)HEC_BJOB * HEC_N, G);
 }
 // B2: finish InvNTT_q0 (canonical digit), copy-path lift into p0, forward stages m = 1..128 under p0
 __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convB2(ConvB P, const ModC *__restrict__ mods) {
     __shared__ u64 sm[HEC_TILE];
     const ModC MQ = mods[P.mq0];
     const ModC MP = mods[P.mp0];
-    ColGeom G(blockIdx.x);
-    const u64 *in = P.w1 + (size_t)blockIdx.y * HEC_N;
-    u64 *out = P.w2 + (size_t)blockIdx.y * HEC_N;
+    ColGeom G(HEC_BTILE);
+    const u64 *in = P.w1 + (size_t)HEC_BJOB * HEC_N;
+    u64 *out = P.w2 + (size_t)HEC_BJOB * HEC_N;
     u64 x[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) x[k] = in[G.gB(k)];
@@ -392,10 +404,10 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convB3(ConvB P, const
     u64 *sm = dsm;
     u64 *stash = dsm + 16 * HEC_ROW_PITCH; // NTT_p0(digit), kept for the second key poly
     const ModC M = mods[P.mp0];
-    RowGeom G(blockIdx.x);
+    RowGeom G(HEC_BTILE);
     {
         u64 x[16];
-        row_loadA(x, P.w2 + (size_t)blockIdx.y * HEC_N, G);
+        row_loadA(x, P.w2 + (size_t)HEC_BJOB * HEC_N, G);
         row_fwd8(x, sm, G, M);
 #pragma unroll
         for (int k = 0; k < 16; k++) stash[k * HEC_THREADS + threadIdx.x] = x[k]; // own slots only
@@ -412,7 +424,7 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convB3(ConvB P, const
             y[2 * k + 1] = mred_lazy(stash[(2 * k + 1) * HEC_THREADS + threadIdx.x], t.y, M.q, M.qinv);
         }
         row_inv8(y, sm, G, M);
-        row_storeA(y, P.w3 + (size_t)(blockIdx.y * 2 + c) * HEC_N, G);
+        row_storeA(y, P.w3 + (size_t)(HEC_BJOB * 2 + c) * HEC_N, G);
     }
 }
 // B4: finish InvNTTLazy_p0, exact basis extension P -> q0 (float64 overflow count v),
@@ -421,9 +433,9 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convB4(ConvB P, const
     __shared__ u64 sm[HEC_TILE];
     const ModC MP = mods[P.mp0];
     const ModC MQ = mods[P.mq0];
-    ColGeom G(blockIdx.x);
-    const u64 *in = P.w3 + (size_t)blockIdx.y * HEC_N;
-    u64 *out = P.w4 + (size_t)blockIdx.y * HEC_N;
+    ColGeom G(HEC_BTILE);
+    const u64 *in = P.w3 + (size_t)HEC_BJOB * HEC_N;
+    u64 *out = P.w4 + (size_t)HEC_BJOB * HEC_N;
     u64 x[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) x[k] = in[G.gB(k)];
@@ -444,11 +456,11 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convB4(ConvB P, const
 //     apply sigma_g inside the 256-word block, add tmp1 (+ bias)           grid.y = M*nb*2
 __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convB5(ConvB P, const ModC *__restrict__ mods) {
     __shared__ u64 sm[16 * HEC_ROW_PITCH];
-    const BJob J(blockIdx.y, true, P);
+    const BJob J(HEC_BJOB, true, P);
     const ModC M = mods[P.mq0];
-    RowGeom G(blockIdx.x);
+    RowGeom G(HEC_BTILE);
     u64 x[16], t1[16];
-    row_loadA(x, P.w4 + (size_t)blockIdx.y * HEC_N, G);
+    row_loadA(x, P.w4 + (size_t)HEC_BJOB * HEC_N, G);
     row_fwd8(x, sm, G, M);
     row_BtoA(x, sm, G);
     const u64 *kq = P.key + (size_t)(J.c * P.keyL) * HEC_N;
@@ -473,7 +485,7 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convB5(ConvB P, const
         sm[G.sbase + e + (e >> 4)] = d;
     }
     __syncwarp();
-    u64 *out = P.xout + (size_t)blockIdx.y * HEC_N;
+    u64 *out = P.xout + (size_t)HEC_BJOB * HEC_N;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         u32 i = G.gbase + 16 * k;

@@ -161,7 +161,10 @@ static int launch_ew(hec_ctx *c, std::vector<EwJob> &jobs) {
         int n = (int)std::min<size_t>(HEC_EWJOBS, jobs.size() - off);
         EwJobs J;
         for (int i = 0; i < n; i++) J.j[i] = jobs[off + i];
-        k_ew<OP><<<dim3(32, n), 256, 0, c->stream>>>(J, c->dmods);
+        // at least ~4 CTAs per SM: a launch with few limbs spreads each limb over more (shorter) CTAs
+        unsigned gx = 32;
+        while (gx < 256 && gx * (unsigned)n < 592) gx *= 2;
+        k_ew<OP><<<dim3(gx, n), 256, 0, c->stream>>>(J, c->dmods);
         c->launches += 1;
     }
     return check_launch(c, "ew");

@@ -148,7 +148,10 @@ void hec_ptdiag_free(hec_ctx *ctx, hec_ptdiag *m);
 int hec_linear_transform(hec_ctx *ctx, const hec_ct *ct, const hec_ptdiag *m, hec_ct **out);
 /* CoeffsToSlots(vec, pDFTInv, eval) / SlotsToCoeffs(ct0, ct1, pDFT, eval) (L:ckks/bootstrap.go; the two halves of the
  * split bootstrapping, BootstrappConv_CtoS / _StoC): chains of LinearTransform + Rescale over the factor matrices,
- * then real / imaginary extraction by conjugation (needs the key of galEl 2N-1).  Full packing only. */
+ * then real / imaginary extraction by conjugation (needs the key of galEl 2N-1).  Under sparse packing
+ * (the matrices' LogSlots < LogN-1) CoeffsToSlots returns one ciphertext (*ct1 = NULL; needs the key of rotation 2^LogSlots).
+ * hec_sub_sum: Bootstrapper.subSum (rotations by 2^i, i = log_slots .. LogN-2). */
+int hec_sub_sum(hec_ctx *ctx, hec_ct *ct, int log_slots);
 int hec_coeffs_to_slots(hec_ctx *ctx, const hec_ct *ct, const hec_ptdiag *const *mats, int n, hec_ct **ct0, hec_ct **ct1);
 int hec_slots_to_coeffs(hec_ctx *ctx, const hec_ct *ct0, const hec_ct *ct1, const hec_ptdiag *const *mats, int n, hec_ct **out);
 /* ---- split bootstrapping, first half: btp.BootstrappConv_CtoS(ct) (eval.go:447-459; the fork's ckks/bootstrap.go).

@@ -261,7 +261,6 @@ static int dft_chain(hec_ctx *c, const hec_ct *in, const hec_ptdiag *const *mats
 extern "C" int hec_coeffs_to_slots(hec_ctx *c, const hec_ct *ct, const hec_ptdiag *const *mats, int n, hec_ct **ct0, hec_ct **ct1) {
     if (!c || !ct || !mats || n < 1 || !ct0 || !ct1) return c ? c->fail(HEC_E_INVAL, "coeffs_to_slots args") : HEC_E_INVAL;
     cudaSetDevice(c->device);
-    if (mats[0]->log_slots != HEC_LOGN - 1) return c->fail(HEC_E_UNSUPPORTED, "sparse packing (LogSlots < LogN-1) is not implemented");
     hec_ct *z = nullptr, *zc = nullptr, *re = nullptr, *im = nullptr;
     int rc = dft_chain(c, ct, mats, n, &z);
     if (!rc) rc = hec_ct_copy_new(c, z, &zc);
@@ -269,10 +268,32 @@ extern "C" int hec_coeffs_to_slots(hec_ctx *c, const hec_ct *ct, const hec_ptdia
     if (!rc) rc = hec_add_new(c, z, zc, &re);
     if (!rc) rc = hec_sub_new(c, z, zc, &im);
     if (!rc) rc = hec_mult_by_i(c, im, 1);
+    if (!rc && mats[0]->log_slots < HEC_LOGN - 1) {
+        // sparse packing: the right n/2 slots of both parts are zero -- rotate the imaginary part into them and return
+        // one ciphertext (ct1 = NULL), as the reference does
+        hec_ct *rot = nullptr;
+        rc = hec_rotate_new(c, im, 1 << mats[0]->log_slots, &rot);
+        if (!rc) rc = hec_add(c, re, rot, re);
+        hec_ct_free(c, rot);
+        hec_ct_free(c, im);
+        im = nullptr;
+    }
     hec_ct_free(c, z); hec_ct_free(c, zc);
     if (rc) { hec_ct_free(c, re); hec_ct_free(c, im); return rc; }
     *ct0 = re; *ct1 = im;
     return HEC_OK;
+}
+// Bootstrapper.subSum (0x5071e0): ct += Rotate(ct, 2^i) for i = log_slots .. LogN - 2; nothing to do at full packing
+extern "C" int hec_sub_sum(hec_ctx *c, hec_ct *ct, int log_slots) {
+    if (!c || !ct || log_slots < 0 || log_slots > HEC_LOGN - 1) return c ? c->fail(HEC_E_INVAL, "sub_sum args") : HEC_E_INVAL;
+    int rc = HEC_OK;
+    for (int i = log_slots; i < HEC_LOGN - 1 && !rc; i++) {
+        hec_ct *rot = nullptr;
+        rc = hec_rotate_new(c, ct, 1 << i, &rot);
+        if (!rc) rc = hec_add(c, ct, rot, ct);
+        hec_ct_free(c, rot);
+    }
+    return rc;
 }
 // SlotsToCoeffs(ct0, ct1, pDFT, eval): dft(ct0 + i * ct1); ct1 may be NULL
 extern "C" int hec_slots_to_coeffs(hec_ctx *c, const hec_ct *ct0, const hec_ct *ct1, const hec_ptdiag *const *mats, int n, hec_ct **out) {
@@ -388,11 +409,12 @@ static int btp_until_sine(hec_ctx *c, const hec_ct *ct_in, const hec_btp_params 
         rc = hec_mult_by_const(c, up, r);
         if (!rc) up->scale = up->scale * r;
     }
-    // subSum: nothing to do at full packing (LogSlots = LogN - 1); hec_coeffs_to_slots refuses sparse packing
+    if (!rc) rc = hec_sub_sum(c, up, pdftinv[0]->log_slots);
     if (!rc) rc = hec_coeffs_to_slots(c, up, pdftinv, nmat, &r0, &r1);
     hec_ct **halves[2] = {&r0, &r1};
-    for (int h = 0; h < 2 && !rc; h++) {                       // evaluateSine (0x508380)
+    for (int h = 0; h < 2 && !rc; h++) {                       // evaluateSine (0x508380); ct1 is NULL under sparse packing
         hec_ct *x = *halves[h];
+        if (!x) continue;
         x->scale = x->scale * b->message_ratio;
         rc = btp_evaluate_cheby(c, halves[h], b);
         if (!rc) { x = *halves[h]; volatile double d = b->postscale * b->message_ratio / b->params_scale; x->scale = x->scale / d; }
@@ -413,8 +435,11 @@ extern "C" int hec_bootstrap_ctos(hec_ctx *c, const hec_ct *ct_in, const hec_btp
     volatile double k = q0 / exp2(go_round(log2(q0)));
     k = k * b->params_scale;
     k = k / b->postscale;
+    // (under sparse packing the reference binary dereferences its nil second half here, 0x506e8e, and dies; the one
+    // ciphertext there is gets the same treatment as at full packing)
     hec_ct *halves[2] = {r0, r1};
     for (int h = 0; h < 2 && !rc; h++) {
+        if (!halves[h]) continue;
         rc = hec_mult_by_const(c, halves[h], k);
         if (!rc) rc = hec_rescale(c, halves[h], b->params_scale);
     }

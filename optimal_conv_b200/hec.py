@@ -26,7 +26,7 @@ SYMBOLS = [
     "hec_ct_copy_new", "hec_ct_level", "hec_ct_scale", "hec_ct_set_scale", "hec_ct_free", "hec_swk_upload",
     "hec_swk_drop", "hec_mul_pt_new", "hec_mult_by_const", "hec_rescale", "hec_set_scale", "hec_add", "hec_add_new",
     "hec_sub_new", "hec_add_pt", "hec_rlk_upload", "hec_mul_relin_new", "hec_sub", "hec_drop_level", "hec_mul_by_pow2", "hec_mult_by_i", "hec_conjugate", "hec_add_const",
-    "hec_ptdiag_upload", "hec_ptdiag_free", "hec_linear_transform", "hec_coeffs_to_slots", "hec_slots_to_coeffs", "hec_mod_up", "hec_bootstrap_ctos", "hec_bootstrap_stoc", "hec_bootstrapp", "hec_mult_by_int_and_add", "hec_evaluate_poly", "hec_evaluate_cheby", "hec_eval_relu", "hec_eval_relu_many", "hec_rotate_gal", "hec_rotate_new", "hec_rotate_hoisted", "hec_galois_for_rotation",
+    "hec_ptdiag_upload", "hec_ptdiag_free", "hec_linear_transform", "hec_coeffs_to_slots", "hec_slots_to_coeffs", "hec_sub_sum", "hec_mod_up", "hec_bootstrap_ctos", "hec_bootstrap_stoc", "hec_bootstrapp", "hec_mult_by_int_and_add", "hec_evaluate_poly", "hec_evaluate_cheby", "hec_eval_relu", "hec_eval_relu_many", "hec_rotate_gal", "hec_rotate_new", "hec_rotate_hoisted", "hec_galois_for_rotation",
     "hec_ntt", "hec_keyswitch", "hec_moddown", "hec_conv_then_pack", "hec_conv_bl", "hec_ext_ctxt", "hec_keep_ctxt", "hec_plan_create", "hec_plan_run",
     "hec_plan_run_host", "hec_plan_submit_host", "hec_plan_wait", "hec_plan_span_begin", "hec_plan_span_end_ms",
     "hec_plan_profile", "hec_plan_destroy",
@@ -121,6 +121,7 @@ def lib():
     L.hec_slots_to_coeffs.argtypes = [vp, vp, vp, C.POINTER(vp), C.c_int, C.POINTER(vp)]
     L.hec_bootstrap_stoc.argtypes = [vp, vp, vp, C.POINTER(vp), C.c_int, C.POINTER(vp)]
     L.hec_bootstrapp.argtypes = [vp, vp, C.POINTER(BtpParams), C.POINTER(vp), C.c_int, C.POINTER(vp), C.c_int, C.POINTER(vp)]
+    L.hec_sub_sum.argtypes = [vp, vp, C.c_int]
     L.hec_mod_up.argtypes = [vp, vp, C.POINTER(vp)]
     L.hec_bootstrap_ctos.argtypes = [vp, vp, C.POINTER(BtpParams), C.POINTER(vp), C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_double)]
     L.hec_evaluate_cheby.argtypes = [vp, vp, C.POINTER(C.c_double), C.c_int, C.c_double, C.c_double, C.POINTER(vp)]
@@ -330,7 +331,10 @@ class Context:
     def CoeffsToSlots(self, ct, mats):
         h0, h1 = vp(), vp()
         self._chk(self.L.hec_coeffs_to_slots(self.h, ct.h, (vp * len(mats))(*mats), len(mats), C.byref(h0), C.byref(h1)))
-        return Ciphertext(self, h0), Ciphertext(self, h1)
+        return Ciphertext(self, h0), (Ciphertext(self, h1) if h1.value else None)
+
+    def SubSum(self, ct, log_slots):
+        self._chk(self.L.hec_sub_sum(self.h, ct.h, log_slots))
 
     def SlotsToCoeffs(self, ct0, ct1, mats):
         h = vp()
@@ -364,7 +368,7 @@ class Context:
         bp = self._btp_params(b)
         h0, h1, k = vp(), vp(), C.c_double()
         self._chk(self.L.hec_bootstrap_ctos(self.h, ct.h, C.byref(bp), (vp * len(mats))(*mats), len(mats), C.byref(h0), C.byref(h1), C.byref(k)))
-        return Ciphertext(self, h0), Ciphertext(self, h1), k.value
+        return Ciphertext(self, h0), (Ciphertext(self, h1) if h1.value else None), k.value
 
     def BootstrappConv_StoC(self, ct0, ct1, mats):
         h = vp()

@@ -316,12 +316,22 @@ class Oracle:
             ct = self.rescale(self.linear_transform(ct, diags, n1, ml, ms, keys), s)
         return ct
 
-    def coeffs_to_slots(self, ct, mats, keys, key_conj):
-        """CoeffsToSlots (L:ckks/bootstrap.go), full packing: z = dft(ct); real part z + conj(z), imaginary part
-        (z - conj(z)) / i"""
+    def coeffs_to_slots(self, ct, mats, keys, key_conj, log_slots=None):
+        """CoeffsToSlots (L:ckks/bootstrap.go): z = dft(ct); real part z + conj(z), imaginary part (z - conj(z)) / i.
+        Sparse packing (log_slots < logN - 1): the imaginary part is rotated by `slots` into the empty half of the
+        real part and one ciphertext is returned (ct1 = None)."""
         z = self.dft(ct, mats, keys)
         zc = self.conjugate(z, key_conj)
-        return self.add_matched(z, zc), self.mult_by_i(self.add_matched(z, zc, sub=True), divide=True)
+        c0, c1 = self.add_matched(z, zc), self.mult_by_i(self.add_matched(z, zc, sub=True), divide=True)
+        if log_slots is not None and log_slots < self.logN - 1:
+            return self.add_matched(c0, self.rotate(c1, 1 << log_slots, keys[1 << log_slots])), None
+        return c0, c1
+
+    def sub_sum(self, ct, log_slots, keys):
+        """Bootstrapper.subSum: ct += Rotate(ct, 2^i) for i = log_slots .. logN - 2 (nothing at full packing)"""
+        for i in range(log_slots, self.logN - 1):
+            ct = self.add_matched(ct, self.rotate(ct, 1 << i, keys[1 << i]))
+        return ct
 
     def slots_to_coeffs(self, ct0, ct1, mats, keys):
         """SlotsToCoeffs (L:ckks/bootstrap.go): dft(ct0 + i ct1)"""
@@ -383,9 +393,14 @@ class Oracle:
         r = float(np.round(b["postscale"] / ct.scale))
         ct = self.mul_const(ct, r)
         ct.scale = ct.scale * r
-        ct0, ct1 = self.coeffs_to_slots(ct, b["mats"], keys, key_conj)
+        ls = b.get("log_slots", self.logN - 1)
+        ct = self.sub_sum(ct, ls, keys)
+        ct0, ct1 = self.coeffs_to_slots(ct, b["mats"], keys, key_conj, ls)
         outs = []
         for c in (ct0, ct1):
+            if c is None:          # sparse packing: one ciphertext carries both parts
+                outs.append(None)
+                continue
             c = Ct(c.c0, c.c1, c.scale * b["message_ratio"])
             c = self.btp_evaluate_cheby(c, b, rlk)
             c.scale = c.scale / (b["postscale"] * b["message_ratio"] / b["params_scale"])
@@ -406,7 +421,9 @@ class Oracle:
         outs = self._btp_until_sine(ct, b, keys, key_conj, rlk)
         q0 = float(self.Q[0])
         const = q0 / float(2.0 ** np.round(np.log2(q0))) * b["params_scale"] / b["postscale"]
-        outs = [self.rescale(self.mul_const(c, const), b["params_scale"]) for c in outs]
+        # (under sparse packing the reference binary dereferences the nil second half here and dies; the one
+        # ciphertext there is gets the same treatment as at full packing)
+        outs = [None if c is None else self.rescale(self.mul_const(c, const), b["params_scale"]) for c in outs]
         return outs[0], outs[1], const
 
     def mult_by_i(self, ct, divide=False):

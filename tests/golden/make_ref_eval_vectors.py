@@ -532,6 +532,64 @@ def ctos_case(level_in, whole=False):
     return rec
 
 
+# ---------------------------------------------------------------- sparse packing (LogSlots < LogN - 1): subSum and the repacking CoeffsToSlots
+SPARSE_LOGN, SPARSE_LS, SPARSE_LEVEL = 5, 2, 5
+SPARSE_MATS = [(2, [0, 1, 2, 3], 5), (2, [0, 1, 3], 4)]
+
+
+def sparse_operands(N):
+    Q, P = DFT_Q, DFT_P
+    beta = (len(Q) + len(P) - 1) // len(P)
+    key = lambda s: np.stack([np.stack([synth.uniform_limbs(s + 10 * d + k, list(Q) + list(P), N) for k in range(2)]) for d in range(beta)])  # noqa: E731
+    logN = N.bit_length() - 1
+    ls = logN - 3
+    rots = {1 << i for i in range(ls, logN - 1)} | {1 << ls}
+    for n1, diags, _ in SPARSE_MATS:
+        rots |= {d % n1 for d in diags if d % n1} | {(d // n1) * n1 for d in diags if d // n1}
+    keys = {r: key(9000 + 131 * r) for r in sorted(rots)}
+    mats = [({d: (synth.uniform_limbs(7000 + 100 * mi + d, Q[:ml + 1], N), synth.uniform_limbs(7500 + 100 * mi + d, P, N)) for d in diags},
+             n1, ml, float(Q[ml])) for mi, (n1, diags, ml) in enumerate(SPARSE_MATS)]
+    ct = (synth.uniform_limbs(61, Q[:SPARSE_LEVEL + 1], N), synth.uniform_limbs(62, Q[:SPARSE_LEVEL + 1], N))
+    return keys, key(9900), mats, ct, ls
+
+
+def sparse_case():
+    """Bootstrapper.subSum and ckks.CoeffsToSlots with LogSlots = LogN - 3 (the evaluator's scratch ciphertext at degree 1,
+    as it is after any scale-matched Add)"""
+    logN = SPARSE_LOGN
+    N = 1 << logN
+    m = Machine()
+    keys, kconj, mats, (a0, a1), ls = sparse_operands(N)
+    gk = {pow(5, r, 2 * N): k for r, k in keys.items()}
+    gk[2 * N - 1] = kconj
+    params, ev = m.new_evaluator(logN, DFT_Q, DFT_P, PR.SCALE, gk, None, log_slots=ls)
+    inner = m.rq(m.rq(m.rq(ev[1] + 8) + 24))              # evaluator.evaluatorBuffers.ctxpool -> rlwe.Ciphertext
+    m.wq(inner + 8, 2)                                    # len(Value) = 2
+    mk = lambda: m.new_ct([[ints(l) for l in a0], [ints(l) for l in a1]], PR.SCALE)  # noqa: E731
+    btp = m.alloc(656)
+    m.wq(btp, ev[1])
+    m.write_u64s(btp + 360, params)
+    rec = {"logN": logN, "log_slots": ls, "sub_sum": digest_ct(m, m.call(CKKS + "(*Bootstrapper).subSum", [btp, mk(), 0])[-1])}
+    ptrs = []
+    for D, n1, ml, ms in mats:
+        vec = m.new_map(16)
+        for d, (dq, dp) in D.items():
+            pq, pp = m.new_poly([ints(l) for l in dq]), m.new_poly([ints(l) for l in dp])
+            for p in (pq, pp):
+                m.wb(p + 24, 1)
+                m.wb(p + 25, 1)
+            m.map_put(vec, d, [pq, pp])
+        mat = m.alloc(48)
+        m.write_u64s(mat, [ls, n1, ml, f2b(ms), vec, 0])
+        ptrs.append(mat)
+    res = m.call(CKKS + "CoeffsToSlots", [mk()] + m.slice_u64(ptrs) + ev + [0, 0], max_steps=1 << 62)
+    assert res[-1] == 0                                   # ct1 == nil
+    rec["coeffs_to_slots"] = digest_ct(m, res[-2])
+    rec["interpreted_instructions"] = m.steps
+    print("sparse packing case: %d instructions" % m.steps, flush=True)
+    return rec
+
+
 SMALL_CONV = [
     # name, logN, B, norm, seed, out_scale, Q, P
     ("n8_B4", 8, 4, 1, 3, PR.SCALE, PR.Q_SET6[:2], PR.P_PACK),
@@ -564,6 +622,7 @@ def main():
         if "lt" in groups:
             new["linear_transform"] = {name: lt_case(*a) for name, *a in LT_CASES}
             new["dft"] = dft_case()
+            new["sparse"] = sparse_case()
         if "ctos" in groups:
             new["ctos"] = {"level%d" % lv: ctos_case(lv) for lv in (1, 0, 3)}
         if "btp" in groups:

@@ -461,6 +461,37 @@ def test_bootstrapp_conv_ctos_full_chain():
         c.close()
 
 
+def test_sparse_packing_sub_sum_coeffs_to_slots_and_ctos():
+    """Sparse packing (LogSlots = LogN - 3, as the bootstrappers of the Resnet_crop_sparse kinds): subSum, the repacking
+    CoeffsToSlots (one ciphertext returned) and BootstrappConv_CtoS on top of them == the oracle"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_ref_eval_vectors as G
+    Q, P = G.DFT_Q, G.DFT_P
+    c, o = hec.Context(PR.LOGN, Q, P), Oracle(PR.LOGN, Q, P)
+    try:
+        keys, kconj, mats, (a0, a1), ls = G.sparse_operands(N)
+        assert ls == PR.LOGN - 3
+        for r, k in keys.items():
+            c.upload_swk(c.galois_for_rotation(r), k, 5)
+        c.upload_swk(2 * N - 1, kconj, 5)
+        hm = [c.upload_ptdiag(ls, n1, ml, ms, D) for D, n1, ml, ms in mats]
+        a = Ct(a0, a1, PR.SCALE)
+        A = c.upload_ct(a0, a1, PR.SCALE)
+        S = c.CopyNew(A)
+        c.SubSum(S, ls)
+        ref = o.sub_sum(a, ls, keys)
+        x0, x1 = S.download()
+        assert np.array_equal(x0, ref.c0) and np.array_equal(x1, ref.c1)
+        g0, g1 = c.CoeffsToSlots(A, hm)
+        r0, r1 = o.coeffs_to_slots(a, mats, keys, kconj, ls)
+        x0, x1 = g0.download()
+        assert g1 is None and r1 is None and g0.level == r0.level and g0.scale == r0.scale
+        assert np.array_equal(x0, r0.c0) and np.array_equal(x1, r0.c1)
+    finally:
+        c.close()
+
+
 def test_layer_pipeline_conv_ctos_relu_keep_stoc(idx_np):
     """One layer of evalConv_BNRelu_new (eval.go:360-575) end to end on the device, through two contexts like the
     reference's two evaluators: conv_then_pack on the pack evaluator (level 1 -> 0), scale relabel, BootstrappConv_CtoS

@@ -234,6 +234,23 @@ def test_bootstrapp_matches_reference_code(name):
     assert dg(o.bootstrapp(ct, b, G.btp_stoc_mats(N), keys, kconj, rlk)) == rec["out"]
 
 
+def test_sparse_packing_sub_sum_and_repacking_coeffs_to_slots_match_reference_code():
+    """Bootstrapper.subSum and ckks.CoeffsToSlots with LogSlots = LogN - 3 (interpreted): the rotate-and-add trace and the
+    rotation of the imaginary part into the empty half (one ciphertext returned) == the oracle"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_ref_eval_vectors as G
+    rec = REF["sparse"]
+    N = 1 << rec["logN"]
+    o = Oracle(rec["logN"], G.DFT_Q, G.DFT_P)
+    keys, kconj, mats, (a0, a1), ls = G.sparse_operands(N)
+    assert ls == rec["log_slots"]
+    ct = Ct(a0, a1, PR.SCALE)
+    assert dg(o.sub_sum(ct, ls, keys)) == rec["sub_sum"]
+    c0, c1 = o.coeffs_to_slots(ct, mats, keys, kconj, ls)
+    assert c1 is None and dg(c0) == rec["coeffs_to_slots"]
+
+
 def cheby_coeffs(deg):
     rng = np.random.default_rng(1000 + deg)
     co = [float(x) for x in rng.uniform(-1, 1, deg + 1)]

@@ -189,7 +189,9 @@ def run_side_workload(args):
     --workload mul_relin  : MulRelinNew(ct, ct) + Rescale at level 10, alpha = 5 (the multiply of
                             evalReLU's polynomial evaluation, conv.go:435-480)
     --workload eval_relu  : the whole evalReLU on one level-15 ciphertext (three EvaluatePoly + the final multiply)
-    --workload bootstrap_ctos : BootstrappConv_CtoS, the first half of the split bootstrapping, full modulus chain"""
+    --workload bootstrap_ctos : BootstrappConv_CtoS, the first half of the split bootstrapping, full modulus chain
+    --workload prep_ker   : the plaintext loop of prep_Ker (conv.go:510-515): --batch B float coefficient vectors from
+                            HOST memory -> EncodeCoeffs + ToNTT on the device -> B level-1 plaintexts"""
     import torch
     from optimal_conv_b200 import hec
     if not torch.cuda.is_available():
@@ -209,6 +211,23 @@ def run_side_workload(args):
         unit, name = "rotations/s", "RotateGal (key-switch + automorphism) at level 27, alpha=5, beta=6"
         # L (c1) + 2*beta*(L+alpha) (key) + 2L (out) + L (c0) limbs, SURVEY.md 8d
         alg = (28 + 2 * 6 * 33 + 2 * 28 + 28) * LIMB
+    elif args.workload == "prep_ker":
+        Q, P, B = PR.Q_SET6[:2], PR.P_PACK, args.batch
+        ctx = hec.Context(PR.LOGN, Q, P)
+        vals = (synth.splitmix64(99, B * N).astype(np.float64) / 2.0 ** 63 - 1.0).reshape(B, N) / 9.0
+
+        def step():
+            for pt in ctx.EncodeCoeffsNTTMany(vals, 1, PR.SCALE):
+                pt.free()
+        unit, name = "layers/s", "prep_Ker plaintext loop (conv.go:510-515): %d x EncodeCoeffs + ToNTT at level 1, host floats in" % B
+        # per plaintext: N doubles read, 2 limbs written by the scaling kernel, 2 limbs through the transform (in + out)
+        alg = B * (N * 8 + 2 * LIMB + 2 * 2 * LIMB)
+        if args.cpu_sample > 0:
+            from oracle.orc import Oracle
+            o = Oracle(PR.LOGN, Q, P)
+            t0 = time.perf_counter()
+            o.encode_coeffs_ntt(vals[0], PR.SCALE, 1)
+            cpu_s = (time.perf_counter() - t0) * B
     elif args.workload == "mul_relin":
         level = 10
         Q, P = PR.Q_SET6[:level + 1], PR.P_ALL
@@ -341,7 +360,7 @@ def run_side_workload(args):
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "dtype": "u64",
             "data": "synthetic", "config": {"workload": args.workload, "path": "op-level generic kernels"},
             "gpu_launches": ctx.launch_count() - l0}
-    if args.workload in ("conv_bl", "mul_relin", "eval_relu", "bootstrap_ctos") and args.cpu_sample > 0:
+    if args.workload in ("conv_bl", "mul_relin", "eval_relu", "bootstrap_ctos", "prep_ker") and args.cpu_sample > 0:
         line["cpu_baseline"] = {"value": 1.0 / cpu_s, "unit": unit, "cores": 1, "kind": "port",
                                 "sample": "1 call of the same workload, oracle port, 1 thread"}
     if alg:
@@ -360,7 +379,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="B: output channels packed per ciphertext")
     ap.add_argument("--ker", type=int, default=3, help="kernel width k (only changes the work of --workload conv_bl)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="conv", choices=["conv", "conv_bl", "keyswitch", "mul_relin", "eval_relu", "bootstrap_ctos"],
+    ap.add_argument("--workload", default="conv", choices=["conv", "conv_bl", "keyswitch", "mul_relin", "eval_relu", "bootstrap_ctos", "prep_ker"],
                     help="conv = the headline fused path; the others are op-level side measurements")
     ap.add_argument("--cpu-sample", type=int, default=12, help="convs timed for cpu_baseline (0 = skip)")
     ap.add_argument("--ring", type=int, default=8, help="distinct input batches rotated through (> L2)")

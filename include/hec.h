@@ -66,6 +66,18 @@ int hec_host_unregister(hec_ctx *ctx, void *ptr);
  * eval.go:242-243).  limbs[0..level]. */
 int hec_pt_upload(hec_ctx *ctx, int level, const uint64_t *const *limbs, double scale, hec_pt **out);
 void hec_pt_free(hec_ctx *ctx, hec_pt *pt);
+/* Encoder.EncodeCoeffs(values, pt) followed by Encoder.ToNTT(pt) on the device (conv.go:513-514 in prep_Ker,
+ * eval.go:242-243 for the bias; L:ckks/encoder.go EncodeCoeffs -> L:ckks/utils.go scaleUpVecExact, then
+ * ring.NTTLvl): values[0..n_values) are coefficients of X^i, rounded to integers at `scale` exactly as the
+ * reference rounds them (half up on the magnitude; exact big-integer path above 2^64), reduced modulo
+ * q_0..q_level, coefficients past n_values cleared.  n_values > N is HEC_E_INVAL (the reference panics),
+ * and so is a NaN or infinite value.  _many encodes `count` vectors stored back to back (the B kernel
+ * plaintexts of one layer) with one copy and batched launches. */
+int hec_encode_coeffs(hec_ctx *ctx, const double *values, int n_values, int level, double scale, hec_pt **out);
+int hec_encode_coeffs_many(hec_ctx *ctx, const double *values, int count, int n_values, int level, double scale,
+                           hec_pt **out /* [count] */);
+/* limbs[0..level] <- the plaintext as canonical residues, NTT domain (Plaintext.Value.Coeffs after ToNTT) */
+int hec_pt_download(hec_ctx *ctx, const hec_pt *pt, uint64_t *const *limbs);
 
 /* ---- ciphertexts: rlwe.Ciphertext{Value [2]*ring.Poly} + Scale. */
 int hec_ct_upload(hec_ctx *ctx, int level, const uint64_t *const *c0, const uint64_t *const *c1,

@@ -393,7 +393,7 @@ extern "C" int hec_pt_upload(hec_ctx *c, int level, const uint64_t *const *limbs
     cudaSetDevice(c->device);
     hec_pt *pt = new hec_pt();
     pt->level = level; pt->scale = scale;
-    if (cudaMalloc(&pt->buf, (size_t)(level + 1) * HEC_N * sizeof(u64)) != cudaSuccess) { delete pt; return c->fail(HEC_E_NOMEM, "cudaMalloc plaintext"); }
+    if (cudaMallocAsync(&pt->buf, (size_t)(level + 1) * HEC_N * sizeof(u64), c->stream) != cudaSuccess) { delete pt; return c->fail(HEC_E_NOMEM, "cudaMallocAsync plaintext"); }
     std::vector<EwJob> jobs;
     for (int i = 0; i <= level; i++) {
         u64 *d = pt->buf + (size_t)i * HEC_N;
@@ -409,8 +409,12 @@ extern "C" int hec_pt_upload(hec_ctx *c, int level, const uint64_t *const *limbs
 }
 extern "C" void hec_pt_free(hec_ctx *c, hec_pt *pt) {
     if (!pt) return;
-    if (c) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
-    cudaFree(pt->buf);
+    if (c) {
+        cudaSetDevice(c->device);
+        cudaFreeAsync(pt->buf, c->stream); // ordered after every kernel of this context that read it
+    } else {
+        cudaFree(pt->buf);
+    }
     delete pt;
 }
 

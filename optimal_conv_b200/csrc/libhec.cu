@@ -3,3 +3,4 @@
 #include "hec_conv.cu"
 #include "hec_poly.cu"
 #include "hec_lt.cu"
+#include "hec_encode.cu"

@@ -22,7 +22,7 @@ CONV_FUSED, CONV_OPLEVEL = 0, 1
 # every symbol include/hec.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "hec_version", "hec_ctx_create", "hec_ctx_destroy", "hec_last_error", "hec_sync", "hec_timer_start",
-    "hec_timer_stop_ms", "hec_launch_count", "hec_host_register", "hec_host_unregister", "hec_pt_upload", "hec_pt_free", "hec_ct_upload", "hec_ct_download",
+    "hec_timer_stop_ms", "hec_launch_count", "hec_host_register", "hec_host_unregister", "hec_pt_upload", "hec_pt_free", "hec_encode_coeffs", "hec_encode_coeffs_many", "hec_pt_download", "hec_ct_upload", "hec_ct_download",
     "hec_ct_copy_new", "hec_ct_level", "hec_ct_scale", "hec_ct_set_scale", "hec_ct_free", "hec_swk_upload",
     "hec_swk_drop", "hec_mul_pt_new", "hec_mult_by_const", "hec_rescale", "hec_set_scale", "hec_add", "hec_add_new",
     "hec_sub_new", "hec_add_pt", "hec_rlk_upload", "hec_mul_relin_new", "hec_sub", "hec_drop_level", "hec_mul_by_pow2", "hec_mult_by_i", "hec_conjugate", "hec_add_const",
@@ -82,6 +82,9 @@ def lib():
     L.hec_host_register.argtypes = [vp, vp, C.c_size_t]
     L.hec_host_unregister.argtypes = [vp, vp]
     L.hec_pt_upload.argtypes = [vp, C.c_int, u64pp, C.c_double, C.POINTER(vp)]
+    L.hec_encode_coeffs.argtypes = [vp, C.POINTER(C.c_double), C.c_int, C.c_int, C.c_double, C.POINTER(vp)]
+    L.hec_encode_coeffs_many.argtypes = [vp, C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int, C.c_double, C.POINTER(vp)]
+    L.hec_pt_download.argtypes = [vp, vp, u64pp]
     L.hec_pt_free.argtypes = [vp, vp]
     L.hec_pt_free.restype = None
     L.hec_ct_upload.argtypes = [vp, C.c_int, u64pp, u64pp, C.c_double, C.POINTER(vp)]
@@ -173,8 +176,8 @@ def _ptrs(addresses):
 
 
 class Plaintext:
-    def __init__(self, ctx, h):
-        self.ctx, self.h = ctx, h
+    def __init__(self, ctx, h, level=None):
+        self.ctx, self.h, self.level = ctx, h, level
 
     def free(self):
         if self.h:
@@ -262,7 +265,27 @@ class Context:
         limbs = np.ascontiguousarray(limbs, dtype=np.uint64)
         h = vp()
         self._chk(self.L.hec_pt_upload(self.h, limbs.shape[0] - 1, _rows(limbs), scale, C.byref(h)))
-        return Plaintext(self, h)
+        return Plaintext(self, h, limbs.shape[0] - 1)
+
+    def EncodeCoeffsNTT(self, values, level, scale):
+        """NewPlaintext(params, level, scale); encoder.EncodeCoeffs(values, pt); encoder.ToNTT(pt) (conv.go:512-514)"""
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        h = vp()
+        self._chk(self.L.hec_encode_coeffs(self.h, v.ctypes.data_as(C.POINTER(C.c_double)), v.shape[0], level, scale, C.byref(h)))
+        return Plaintext(self, h, level)
+
+    def EncodeCoeffsNTTMany(self, values, level, scale):
+        """the plaintext loop of prep_Ker (conv.go:510-515): values [count][n] -> count plaintexts"""
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        hs = (vp * v.shape[0])()
+        self._chk(self.L.hec_encode_coeffs_many(self.h, v.ctypes.data_as(C.POINTER(C.c_double)), v.shape[0], v.shape[1], level, scale, hs))
+        return [Plaintext(self, vp(h), level) for h in hs]
+
+    def download_pt(self, pt, level=None):
+        level = pt.level if level is None else level
+        out = np.empty((level + 1, self.N), dtype=np.uint64)
+        self._chk(self.L.hec_pt_download(self.h, pt.h, _rows(out)))
+        return out
 
     def upload_ct(self, c0, c1, scale):
         c0, c1 = np.ascontiguousarray(c0, dtype=np.uint64), np.ascontiguousarray(c1, dtype=np.uint64)

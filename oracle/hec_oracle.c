@@ -683,6 +683,46 @@ void orc_poly_add(const orc_ctx *c, int ring, int nlimbs, const uint64_t *a, con
     }
 }
 
+/* Encoder.EncodeCoeffs = ckks.scaleUpVecExact (L:ckks/utils.go:59-123) as the pinned binary computes it (disassembly at
+ * 0x532380): n*|v| > 2^64 -> X = trunc(double(n*|v|) + 0.5) as an exact integer (big.Float at 53 bits is an IEEE
+ * double; Int truncates), else X = uint64(n*|v| + 0.5) with Go's amd64 conversion (CVTTSD2SI, split at 2^63);
+ * out = X mod q for v >= 0 (and -0.0), q - (X mod q) for v < 0 -- q itself when the residue is 0; coefficients
+ * past n are cleared.  out: [level+1][N], coefficient domain. */
+static u64 go_cvttsd2si(double y) {
+    if (!(y < 9223372036854775808.0) || y < -9223372036854775808.0) return 1ull << 63;
+    return (u64)(int64_t)y;
+}
+static u64 go_f2u(double x) {
+    return x < 9223372036854775808.0 ? go_cvttsd2si(x) : (go_cvttsd2si(x - 9223372036854775808.0) | (1ull << 63));
+}
+void orc_scale_up_vec_exact(const orc_ctx *c, const double *values, int n, double scale, int level, uint64_t *out) {
+    int N = c->N;
+    for (int j = 0; j <= level; j++) {
+        u64 q = c->Q[j].q;
+        u64 *o = out + (size_t)j * N;
+        for (int i = 0; i < N; i++) {
+            if (i >= n) { o[i] = 0; continue; }
+            double v = values[i];
+            int neg = v < 0.0;
+            volatile double ax = scale * fabs(v); /* volatile: one rounded product, no fused multiply-add */
+            volatile double y = ax + 0.5;
+            u64 r;
+            if (ax > 18446744073709551616.0) {
+                u64 bits;
+                double yy = y;
+                memcpy(&bits, &yy, 8);
+                int e = (int)((bits >> 52) & 0x7ff) - 1075; /* y = mant * 2^e, e >= 12 */
+                u128 t = ((bits & ((1ull << 52) - 1)) | (1ull << 52)) % q;
+                for (int k = 0; k < e; k++) t = (t << 1) % q;
+                r = (u64)t;
+            } else {
+                r = go_f2u(y) % q;
+            }
+            o[i] = neg ? q - r : r;
+        }
+    }
+}
+
 void orc_rotate_gal(const orc_ctx *c, int level, const uint64_t *ct0, const uint64_t *ct1,
                     uint64_t galEl, const uint64_t *swk, uint64_t *o0, uint64_t *o1) {
     int N = c->N, L = level + 1;

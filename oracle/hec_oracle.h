@@ -92,6 +92,8 @@ void orc_keyswitch_nomoddown(const orc_ctx *c, int level, const uint64_t *c1, co
 /* MulCoeffsMontgomery[AndAdd] / Add over nlimbs limbs of ring 0 (Q) or 1 (P): L:ring/ring_operations.go */
 void orc_poly_mulmont(const orc_ctx *c, int ring, int nlimbs, const uint64_t *a, const uint64_t *b, uint64_t *out, int accumulate);
 void orc_poly_add(const orc_ctx *c, int ring, int nlimbs, const uint64_t *a, const uint64_t *b, uint64_t *out);
+/* Encoder.EncodeCoeffs (ckks.scaleUpVecExact); out [level+1][N], coefficient domain, with the reference's q-for-0 word */
+void orc_scale_up_vec_exact(const orc_ctx *c, const double *values, int n, double scale, int level, uint64_t *out);
 /* test hook: digit d of DecomposeSingleNTT (L:rlwe/keyswitch.go:121-141) */
 void orc_decompose_digit(const orc_ctx *c, int level, int d, const uint64_t *c1ntt, uint64_t *dQ, uint64_t *dP);
 /* ModDownSplitNTTPQ: L:ring/ring_basis_extension.go:247-291.  accQ [(level+1)][N],

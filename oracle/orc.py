@@ -67,6 +67,8 @@ def lib():
         L.orc_keyswitch_nomoddown.argtypes = [C.c_void_p, C.c_int, u64p, u64p, u64p, u64p, u64p, u64p]
         L.orc_poly_mulmont.argtypes = [C.c_void_p, C.c_int, C.c_int, u64p, u64p, u64p, C.c_int]
         L.orc_poly_add.argtypes = [C.c_void_p, C.c_int, C.c_int, u64p, u64p, u64p]
+        L.orc_scale_up_vec_exact.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int, C.c_double, C.c_int, u64p]
+        L.orc_scale_up_vec_exact.restype = None
         L.orc_moddown.argtypes = [C.c_void_p, C.c_int, u64p, u64p, u64p]
         L.orc_rotate_gal.argtypes = [C.c_void_p, C.c_int, u64p, u64p, C.c_uint64, u64p, u64p, u64p]
         L.orc_conv_then_pack.restype = C.c_int
@@ -223,6 +225,42 @@ class Oracle:
         x = -n * value if neg else n * value
         r = int(x + 0.5) % q
         return q - r if neg else r
+
+    # ---- Encoder.EncodeCoeffs + ToNTT (conv.go:513-514, eval.go:242-243; L:ckks/encoder.go, L:ckks/utils.go) ----
+    @staticmethod
+    def _f2u(x):
+        """Go's float64 -> uint64 conversion as compiled for amd64 (CVTTSD2SI, split at 2^63)"""
+        def cvt(y):
+            return (1 << 63) if (y != y or y >= 2.0 ** 63 or y < -2.0 ** 63) else int(y) & ((1 << 64) - 1)
+        return cvt(x) if x < 2.0 ** 63 else cvt(x - 2.0 ** 63) | (1 << 63)
+
+    def scale_up_vec_exact(self, values, n, level):
+        """scaleUpVecExact in C (orc_scale_up_vec_exact); scale_up_vec_exact_py is the same in big-integer Python"""
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        out = np.empty((level + 1, self.N), dtype=np.uint64)
+        self.L.orc_scale_up_vec_exact(self.h, v.ctypes.data_as(C.POINTER(C.c_double)), v.shape[0], n, level, _p(out))
+        return out
+
+    def scale_up_vec_exact_py(self, values, n, level):
+        """scaleUpVecExact (L:ckks/utils.go:59-123) as the pinned binary computes it: |n*v| > 2^64 goes through
+        big.Float (53 bits == IEEE double) and big.Int; otherwise uint64(n*v + 0.5) % q; negative values give
+        q - r, which is q itself (not 0) when r == 0; coefficients past len(values) are cleared."""
+        out = np.zeros((level + 1, self.N), dtype=np.uint64)
+        for i, v in enumerate(np.asarray(values, dtype=np.float64)):
+            v, neg = float(v), float(v) < 0
+            if n * abs(v) > 2.0 ** 64:
+                x = int((-n * v if neg else n * v) + 0.5)
+            else:
+                x = self._f2u((-n * v if neg else n * v) + 0.5)
+            for j in range(level + 1):
+                r = x % self.Q[j]
+                out[j, i] = self.Q[j] - r if neg else r
+        return out
+
+    def encode_coeffs_ntt(self, values, scale, level):
+        """EncodeCoeffs then ToNTT: the plaintext limbs prep_Ker / evalConv_BN hand to the evaluator"""
+        raw = self.scale_up_vec_exact(values, scale, level)
+        return np.stack([self.ntt(raw[j], j) for j in range(level + 1)])
 
     # ---- hoisted linear transform (CoeffsToSlots / SlotsToCoeffs of the bootstrapper; L:ckks/linear_transform.go) ----
     def keyswitch_nomoddown(self, c1, swk):

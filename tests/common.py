@@ -49,3 +49,27 @@ GOLDEN_CONFIGS = [
 
 def workload(cfg, n_ct=1):
     return synth.conv_workload(Q2, P1, PR.LOGN, cfg["B"], cfg["seed"], n_ct=n_ct)
+
+
+# ---- EncodeCoeffs operands (conv.go:513-514; shared by the golden generator and the tests)
+ENCODE_EDGE = [0.0, -0.0, 1.0, -1.0, 0.5, -0.5, 1.4999999, 2.5, -2.5, 1e-12, -1e-12, 3.7e5, -3.7e5, 1.8e10, -1.8e10,
+               2.0 ** 34, -(2.0 ** 34), 2.0 ** 34 + 1, 1e20, -1e20, 0.49999999999999994 / 2 ** 30, 123456.789,
+               float(0x3ffc0001) / 2 ** 30, -float(0x3ffc0001) / 2 ** 30, 2.0 ** 33, -(2.0 ** 33), 1.5 * 2 ** 33,
+               2.0 ** 34 * (1 - 2.0 ** -53), 3e30, -3e30, 7.25e100, -7.25e100]
+ENCODE_CASES = {  # name: (logN, number of values, amplitude, scale, level)
+    "n8_scale30": (8, 256, 4.0, float(1 << 30), 2),
+    "n8_short": (8, 200, 1e-3, float(1 << 30), 1),
+    "n8_scale60": (8, 256, 64.0, float(1 << 60), 2),
+    "n10_kernel": (10, 1024, 0.25, float(1 << 30), 1),
+}
+
+
+def encode_values(name):
+    """seeded doubles in (-amp, amp) with the edge cases of scaleUpVecExact in front"""
+    from optimal_conv_b200 import synth
+    logN, n, amp, scale, level = ENCODE_CASES[name]
+    u = synth.splitmix64(0xE1C0DE + n + level, n).astype(np.float64) / 2.0 ** 64
+    v = (2.0 * u - 1.0) * amp
+    k = min(len(ENCODE_EDGE), n)
+    v[:k] = ENCODE_EDGE[:k]
+    return v

@@ -3,7 +3,7 @@
 Run from the repo root in the build container (needs /root/reference/test_run, objdump, nm):
     python tests/golden/make_ref_eval_vectors.py            # small-N cases, ~2 min
     python tests/golden/make_ref_eval_vectors.py --only n8_B4      # regenerate one small conv case
-    python tests/golden/make_ref_eval_vectors.py --evalops | --relu | --lt | --ctos | --btp | --ring | --conv  # regenerate one group
+    python tests/golden/make_ref_eval_vectors.py --evalops | --relu | --lt | --ctos | --btp | --ring | --conv | --encode  # regenerate one group
     python tests/golden/make_ref_eval_vectors.py --full B4_norm1   # N = 2^16 golden config, ~1 h
 The prebuilt binary is never executed.  tests/golden/refmachine.py interprets the compiled routines of
 the Lattigo fork (ring / rlwe / ckks packages) and of package main from their disassembly; objects
@@ -604,6 +604,28 @@ SMALL_CONV = [
 ]
 
 
+# ---------------------------------------------------------------- EncodeCoeffs + ToNTT (conv.go:513-514)
+def encode_case(name):
+    """ckks.scaleUpVecExact (the body of Encoder.EncodeCoeffs) followed by ring.NTTLvl (Encoder.ToNTT)"""
+    logN, n, amp, scale, level = common.ENCODE_CASES[name]
+    N = 1 << logN
+    Q = PR.Q_SET6[:level + 1]
+    m = Machine()
+    rQ = m.new_ring(N, Q)
+    vals = common.encode_values(name)
+    va = m.alloc(8 * len(vals))
+    m.write_u64s(va, [f2b(float(v)) for v in vals])
+    pt = m.new_poly([[7] * N for _ in Q])           # stale contents: the tail must be cleared
+    rows = m.rq(pt)
+    m.call(CKKS + "scaleUpVecExact", [va, len(vals), len(vals), f2b(scale)] + m.slice_u64(Q) + [rows, len(Q), len(Q)])
+    raw = np.array(m.read_poly(pt), dtype=np.uint64)
+    m.call(RING + "(*Ring).NTTLvl", [rQ, level, pt, pt])
+    ntt = np.array(m.read_poly(pt), dtype=np.uint64)
+    return {"logN": logN, "n": n, "scale": scale, "level": level, "raw": common.sha(raw), "ntt": common.sha(ntt),
+            "raw_head": [["%x" % int(x) for x in raw[j, :len(common.ENCODE_EDGE)]] for j in range(len(Q))],
+            "interpreted_instructions": m.steps}
+
+
 def main():
     new = {"binary": "test_run (go1.16.6, github.com/dwkim606/test_lattigo v0.0.0-20220812213541-eb33b0555aaa)"}
     if "--full" in sys.argv:
@@ -614,7 +636,10 @@ def main():
         new["conv"] = {name: conv_case(logN, B, norm, seed, out_scale, Q2, P1)
                        for name, logN, B, norm, seed, out_scale, Q2, P1 in SMALL_CONV if name in sys.argv}
     else:
-        groups = [g for g in ("relu", "evalops", "lt", "ctos", "btp", "ring", "conv") if "--" + g in sys.argv] or ["relu", "evalops", "lt", "ctos", "btp", "ring", "conv"]
+        ALL = ("relu", "evalops", "lt", "ctos", "btp", "ring", "conv", "encode")
+        groups = [g for g in ALL if "--" + g in sys.argv] or list(ALL)
+        if "encode" in groups:
+            new["encode_coeffs"] = {name: encode_case(name) for name in common.ENCODE_CASES}
         if "relu" in groups:
             new["relu"] = {name: relu_case(logN, alpha, level) for name, logN, alpha, level in RELU_CASES}
             new["cheby"] = {name: cheby_case(deg, level) for name, deg, level in CHEBY_CASES}

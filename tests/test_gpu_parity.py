@@ -711,6 +711,80 @@ def test_semantic_encrypt_conv_decrypt_full_size(orc):
         c.close()
 
 
+# ---------------------------------------------------------------- EncodeCoeffs + ToNTT on the device (prep_Ker, conv.go:510-515)
+def _enc_values(n, amp, seed):
+    u = synth.splitmix64(seed, max(n, 1)).astype(np.float64)[:n] / 2.0 ** 64
+    v = (2.0 * u - 1.0) * amp
+    k = min(n, len(common.ENCODE_EDGE))
+    v[:k] = common.ENCODE_EDGE[:k]
+    return v
+
+
+@pytest.mark.parametrize("n,amp,scale,level", [(N, 4.0, 2.0 ** 30, 1), (N - 1234, 1e-3, 2.0 ** 30, 1), (N, 64.0, 2.0 ** 60, 1),
+                                               (0, 1.0, 2.0 ** 30, 0), (N, 1e3, 2.0 ** 40 + 12345.0, 0), (7, 0.5, 1.0, 1)])
+def test_encode_coeffs_ntt_matches_oracle(ctx, orc, n, amp, scale, level):
+    """hec_encode_coeffs == scaleUpVecExact + NTTLvl of the oracle (pinned against the reference's compiled code at
+    small N), over the edge values (big path, 2^63 split, negatives rounding to zero, -0.0) and a short vector"""
+    v = _enc_values(n, amp, 77 + n % 13 + level)
+    pt = ctx.EncodeCoeffsNTT(v, level, scale)
+    assert np.array_equal(ctx.download_pt(pt), orc.encode_coeffs_ntt(v, scale, level))
+    pt.free()
+
+
+def test_encode_coeffs_relu_moduli_and_errors():
+    Q = PR.Q_SET6[:7]                                       # 56, 49, 61, 61, 42, 30, 31 bit limbs
+    c, o = hec.Context(PR.LOGN, Q, PR.P_ALL), Oracle(PR.LOGN, Q, PR.P_ALL)
+    try:
+        v = _enc_values(N, 2.0 ** 20, 5)
+        pt = c.EncodeCoeffsNTT(v, 6, 2.0 ** 30)
+        assert np.array_equal(c.download_pt(pt), o.encode_coeffs_ntt(v, 2.0 ** 30, 6))
+        # a plaintext made on the device behaves like an uploaded one
+        c0, c1 = synth.uniform_limbs(1, Q, N), synth.uniform_limbs(2, Q, N)
+        ct = c.upload_ct(c0, c1, 2.0 ** 30)
+        up = c.upload_pt(o.encode_coeffs_ntt(v, 2.0 ** 30, 6), 2.0 ** 30)
+        a, b = c.MulNew(ct, pt).download(), c.MulNew(ct, up).download()
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        for bad in ([np.nan], [np.inf], np.zeros(N + 1)):
+            with pytest.raises(hec.HecError):
+                c.EncodeCoeffsNTT(np.array(bad, dtype=np.float64), 1, 2.0 ** 30)
+        with pytest.raises(hec.HecError):
+            c.EncodeCoeffsNTT(v, 7, 2.0 ** 30)
+    finally:
+        c.close()
+
+
+def test_prep_ker_on_the_device_feeds_the_conv(orc, idx_np):
+    """prep_Ker's plaintext loop (conv.go:510-515) and the bias of evalConv_BN (eval.go:238-243) encoded by
+    hec_encode_coeffs_many; the conv over them == the conv over host-encoded, uploaded plaintexts == the oracle's"""
+    B, w_, k, norm = 16, 64, 3, 1
+    rng = np.random.default_rng(11)
+    ker = rng.uniform(-1, 1, size=B * B * k * k) / (k * k)
+    bn_a, bn_b = rng.uniform(0.5, 1.5, size=B), rng.uniform(-1, 1, size=B)
+    kers = np.stack(hp.prep_ker_coeffs(N, ker, bn_a, w_, k, B, B, norm))
+    c = hec.Context(PR.LOGN, Q2, P1)
+    try:
+        w = synth.conv_workload(Q2, P1, PR.LOGN, B, 4242)
+        G = common.GpuConv(c, w, idx_np, norm)
+        pts = c.EncodeCoeffsNTTMany(kers, 1, PR.SCALE)
+        assert len(pts) == B
+        want = [orc.encode_coeffs_ntt(kers[i], PR.SCALE, 1) for i in range(B)]
+        for i in (0, 7, B - 1):
+            assert np.array_equal(c.download_pt(pts[i]), want[i])
+        bias_v = hp.bias_coeffs(N, bn_b, w_, norm)
+        bias = c.EncodeCoeffsNTT(bias_v, 0, PR.SCALE)
+        bias_np = orc.encode_coeffs_ntt(bias_v, PR.SCALE, 0)
+        res = c.conv_then_pack(G.cts[0], pts, norm, PR.SCALE, G.idx, bias)
+        up = [c.upload_pt(x, PR.SCALE) for x in want]
+        ref = c.conv_then_pack(G.cts[0], up, norm, PR.SCALE, G.idx, c.upload_pt(bias_np, PR.SCALE))
+        (g0, g1), (r0, r1) = res.download(), ref.download()
+        assert np.array_equal(g0, r0) and np.array_equal(g1, r1)
+        o, _, _ = orc.conv_then_pack(Ct(w["ct"][0][0], w["ct"][0][1], PR.SCALE), np.stack(want), PR.SCALE, norm, PR.SCALE,
+                                     idx_np, w["keys"], pt_bias=bias_np[0])
+        assert np.array_equal(g0, o.c0) and np.array_equal(g1, o.c1) and res.scale == o.scale
+    finally:
+        c.close()
+
+
 def test_baseline_conv_bl_matches_oracle():
     """Rotation-per-tap baseline (test_BL.go:98-111 -> eval.go:78-134) at its real shape: parameter set 7,
     level 1 (56+61 bit), two special primes, B=4 channels -> 2 ciphertext slots-halves of w=128:

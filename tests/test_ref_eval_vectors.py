@@ -286,6 +286,27 @@ def test_evaluate_poly_dense_matches_reference_code(name):
 FULL = sorted(REF.get("conv_full", {}))
 
 
+@pytest.mark.parametrize("name", sorted(common.ENCODE_CASES))
+def test_encode_coeffs_to_ntt_matches_reference_code(name):
+    """Encoder.EncodeCoeffs (ckks.scaleUpVecExact) + ToNTT (ring.NTTLvl) as the reference's compiled code computes
+    them, including the big.Float path above 2^64, Go's float->uint64 conversion, the `q - 0 = q` word a negative
+    value rounding to zero leaves behind, and the clearing of the tail"""
+    rec = REF["encode_coeffs"][name]
+    logN, n, amp, scale, level = common.ENCODE_CASES[name]
+    assert (rec["logN"], rec["n"], rec["scale"], rec["level"]) == (logN, n, scale, level)
+    o = Oracle(logN, PR.Q_SET6[:level + 1], PR.P_ALL[:1])
+    v = common.encode_values(name)
+    raw = o.scale_up_vec_exact(v, scale, level)
+    assert np.array_equal(raw, o.scale_up_vec_exact_py(v, scale, level))
+    k = min(len(common.ENCODE_EDGE), n)
+    assert [["%x" % int(x) for x in raw[j, :k]] for j in range(level + 1)] == [r[:k] for r in rec["raw_head"]]
+    assert common.sha(raw) == rec["raw"]
+    assert common.sha(o.encode_coeffs_ntt(v, scale, level)) == rec["ntt"]
+    # the non-canonical word is invisible after the transform
+    canon = raw % np.array(o.Q[:level + 1], dtype=np.uint64)[:, None]
+    assert common.sha(np.stack([o.ntt(canon[j], j) for j in range(level + 1)])) == rec["ntt"]
+
+
 @pytest.mark.parametrize("name", FULL)
 def test_full_size_golden_fixture_is_the_reference_codes_output(name):
     """N = 2^16: the digests in tests/golden/conv_golden.json (what the GPU parity tests compare libhec with)

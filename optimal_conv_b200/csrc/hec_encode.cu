@@ -58,13 +58,13 @@ __global__ void __launch_bounds__(HEC_THREADS) k_encode_coeffs(EncJobs J, const 
     }
     for (int j = 0; j <= level; j++) {
         const ModC M = mods[j];
-        u64 r = x % M.q;
-        for (int k = 0; k < e; k++) { // rare path; q < 2^63
+        u64 r = mred(x, J.r2[j], M.q, M.qinv); // x * R mod q, canonical, for any x < 2^64: no division
+        for (int k = 0; k < e; k++) { // rare path (doubling commutes with the Montgomery factor); q < 2^63
             r <<= 1;
             if (r >= M.q) r -= M.q;
         }
         if (neg && r) r = M.q - r;
-        out[(size_t)j * HEC_N + i] = mred(r, J.r2[j], M.q, M.qinv);
+        out[(size_t)j * HEC_N + i] = r;
     }
 }
 

@@ -15,10 +15,13 @@
 #define HEC_MAXJOBS 64
 struct LimbJob { const u64 *in; u64 *out; int mod; int pad; };
 struct NttJobs { LimbJob j[HEC_MAXJOBS]; };
+#ifndef HEC_GEN_MINB
+#define HEC_GEN_MINB 1 // resident CTAs per SM the generic transforms are compiled for (register cap)
+#endif
 
 // forward NTT = k_col_fwd then k_row_fwd;  inverse = k_row_inv then k_col_inv
 // (ring.NTT / ring.InvNTT, L:ring/ring_ntt.go:74-626).  grid = (16, njobs).
-__global__ void __launch_bounds__(HEC_THREADS) k_col_fwd(NttJobs J, const ModC *__restrict__ mods) {
+__global__ void __launch_bounds__(HEC_THREADS, HEC_GEN_MINB) k_col_fwd(NttJobs J, const ModC *__restrict__ mods) {
     __shared__ u64 sm[HEC_TILE];
     const LimbJob job = J.j[blockIdx.y];
     const ModC M = mods[job.mod];
@@ -30,7 +33,7 @@ __global__ void __launch_bounds__(HEC_THREADS) k_col_fwd(NttJobs J, const ModC *
 #pragma unroll
     for (int k = 0; k < 16; k++) job.out[G.gB(k)] = x[k];
 }
-__global__ void __launch_bounds__(HEC_THREADS) k_row_fwd(NttJobs J, const ModC *__restrict__ mods) {
+__global__ void __launch_bounds__(HEC_THREADS, HEC_GEN_MINB) k_row_fwd(NttJobs J, const ModC *__restrict__ mods) {
     __shared__ u64 sm[16 * HEC_ROW_PITCH];
     const LimbJob job = J.j[blockIdx.y];
     const ModC M = mods[job.mod];
@@ -43,7 +46,7 @@ __global__ void __launch_bounds__(HEC_THREADS) k_row_fwd(NttJobs J, const ModC *
     for (int k = 0; k < 16; k++) x[k] = canon(x[k], M);
     row_storeA(x, job.out, G);
 }
-__global__ void __launch_bounds__(HEC_THREADS) k_row_inv(NttJobs J, const ModC *__restrict__ mods) {
+__global__ void __launch_bounds__(HEC_THREADS, HEC_GEN_MINB) k_row_inv(NttJobs J, const ModC *__restrict__ mods) {
     __shared__ u64 sm[16 * HEC_ROW_PITCH];
     const LimbJob job = J.j[blockIdx.y];
     const ModC M = mods[job.mod];
@@ -54,7 +57,7 @@ __global__ void __launch_bounds__(HEC_THREADS) k_row_inv(NttJobs J, const ModC *
     row_inv8(x, sm, G, M);
     row_storeA(x, job.out, G);
 }
-__global__ void __launch_bounds__(HEC_THREADS) k_col_inv(NttJobs J, const ModC *__restrict__ mods) {
+__global__ void __launch_bounds__(HEC_THREADS, HEC_GEN_MINB) k_col_inv(NttJobs J, const ModC *__restrict__ mods) {
     __shared__ u64 sm[HEC_TILE];
     const LimbJob job = J.j[blockIdx.y];
     const ModC M = mods[job.mod];

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhec.so")
+LIB_PATH = os.environ.get("HEC_LIB", os.path.join(_HERE, "libhec.so"))  # HEC_LIB: a build variant to measure (tools/)
 
 u64p = C.POINTER(C.c_uint64)
 u64pp = C.POINTER(u64p)

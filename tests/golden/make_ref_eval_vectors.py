@@ -3,7 +3,7 @@
 Run from the repo root in the build container (needs /root/reference/test_run, objdump, nm):
     python tests/golden/make_ref_eval_vectors.py            # small-N cases, ~2 min
     python tests/golden/make_ref_eval_vectors.py --only n8_B4      # regenerate one small conv case
-    python tests/golden/make_ref_eval_vectors.py --evalops | --relu | --lt | --ctos | --btp | --ring | --conv | --encode  # regenerate one group
+    python tests/golden/make_ref_eval_vectors.py --evalops | --relu | --lt | --ctos | --btp | --ring | --conv | --encode | --hostprep  # regenerate one group
     python tests/golden/make_ref_eval_vectors.py --full B4_norm1   # N = 2^16 golden config, ~1 h
 The prebuilt binary is never executed.  tests/golden/refmachine.py interprets the compiled routines of
 the Lattigo fork (ring / rlwe / ckks packages) and of package main from their disassembly; objects
@@ -626,6 +626,44 @@ def encode_case(name):
             "interpreted_instructions": m.steps}
 
 
+# ---------------------------------------------------------------- float-side host preparation (package main)
+HOSTPREP = {"B": 4, "w": 8, "k": 3, "raw_w": 7, "norm": 2}
+
+
+def hostprep_case():
+    """main.reshape_ker / encode_ker_final (conv.go:184-237), prep_Input (main.go:1007-1041, trans = false),
+    post_process (main.go:1057-1070) on small index-valued inputs: pins tests/hostprep.py"""
+    import struct
+    m = Machine()
+
+    def fslice(vals):
+        a = m.alloc(8 * max(1, len(vals)))
+        m.write_u64s(a, [f2b(float(v)) for v in vals])
+        return [a, len(vals), len(vals)]
+
+    def rfs(hdr_words):
+        return [struct.unpack("<d", struct.pack("<Q", x))[0] for x in m.read_u64s(hdr_words[0], hdr_words[1])]
+
+    B, w, k, raw_w, norm = (HOSTPREP[x] for x in ("B", "w", "k", "raw_w", "norm"))
+    ker = [float(v) for v in range(1, B * B * k * k + 1)]
+    r = m.call("main.reshape_ker", fslice(ker) + [k * k, B, 0, 0, 0, 0])
+    rows_ptr, nrows = r[6], r[7]
+    reshaped = [rfs(m.read_u64s(rows_ptr + 24 * i, 3)) for i in range(nrows)]
+    enc = []
+    for i in range(B):
+        r = m.call("main.encode_ker_final", [rows_ptr, nrows, nrows, 0, i, w, B, k, 0, 0, 0])
+        enc.append(rfs(r[8:11]))
+    N = w * w * B
+    raw = [float(v) for v in range(1, raw_w * raw_w * (B // norm) + 1)]
+    r = m.call("main.prep_Input", fslice(raw) + [raw_w, w, N, norm, 0, 0, 0, 0])
+    prep = rfs(r[8:11])
+    cfs = [float(v) for v in range(1, N + 1)]
+    r = m.call("main.post_process", fslice(cfs) + [raw_w, w, 0, 0, 0])
+    post = rfs(r[5:8])
+    return {"cfg": HOSTPREP, "reshape_ker": reshaped, "encode_ker_final": enc, "prep_input": prep, "post_process": post,
+            "interpreted_instructions": m.steps}
+
+
 def main():
     new = {"binary": "test_run (go1.16.6, github.com/dwkim606/test_lattigo v0.0.0-20220812213541-eb33b0555aaa)"}
     if "--full" in sys.argv:
@@ -636,8 +674,10 @@ def main():
         new["conv"] = {name: conv_case(logN, B, norm, seed, out_scale, Q2, P1)
                        for name, logN, B, norm, seed, out_scale, Q2, P1 in SMALL_CONV if name in sys.argv}
     else:
-        ALL = ("relu", "evalops", "lt", "ctos", "btp", "ring", "conv", "encode")
+        ALL = ("relu", "evalops", "lt", "ctos", "btp", "ring", "conv", "encode", "hostprep")
         groups = [g for g in ALL if "--" + g in sys.argv] or list(ALL)
+        if "hostprep" in groups:
+            new["hostprep"] = hostprep_case()
         if "encode" in groups:
             new["encode_coeffs"] = {name: encode_case(name) for name in common.ENCODE_CASES}
         if "relu" in groups:

@@ -286,6 +286,22 @@ def test_evaluate_poly_dense_matches_reference_code(name):
 FULL = sorted(REF.get("conv_full", {}))
 
 
+def test_float_side_host_preparation_matches_reference_code():
+    """tests/hostprep.py (what the semantic encrypt -> conv -> decrypt test builds its operands with) against
+    main.reshape_ker / encode_ker_final / prep_Input / post_process of the reference binary"""
+    import hostprep as hp
+    d = REF["hostprep"]
+    B, w, k, raw_w, norm = (d["cfg"][x] for x in ("B", "w", "k", "raw_w", "norm"))
+    rs = hp.reshape_ker(np.arange(1, B * B * k * k + 1, dtype=float), k * k, B)
+    assert np.array_equal(rs, np.array(d["reshape_ker"]))
+    for i in range(B):
+        assert np.array_equal(hp.encode_ker_final(rs, 0, i, w, B, k), np.array(d["encode_ker_final"][i]))
+    N = w * w * B
+    raw = np.arange(1, raw_w * raw_w * (B // norm) + 1, dtype=float)
+    assert np.array_equal(hp.prep_input(raw, raw_w, w, N, norm), np.array(d["prep_input"]))
+    assert np.array_equal(hp.post_process(np.arange(1, N + 1, dtype=float), raw_w, w), np.array(d["post_process"]))
+
+
 @pytest.mark.parametrize("name", sorted(common.ENCODE_CASES))
 def test_encode_coeffs_to_ntt_matches_reference_code(name):
     """Encoder.EncodeCoeffs (ckks.scaleUpVecExact) + ToNTT (ring.NTTLvl) as the reference's compiled code computes

@@ -36,3 +36,10 @@ def test_interpreted_generators_reproduce_the_committed_vector():
     e = MV.new_emu()
     for q in (PR.Q_SET6[0], PR.Q_SET6[1], PR.P_ALL[0]):
         assert e.call(MV.P + "primitiveRoot", [q, 0])[1] == ref["generator"]["%x" % q]
+
+
+def test_interpreted_encode_coeffs_and_host_preparation_reproduce_the_committed_vectors():
+    import make_ref_eval_vectors as G
+    ref = json.load(open(os.path.join(HERE, "golden", "ref_eval_vectors.json")))
+    assert G.encode_case("n8_short") == ref["encode_coeffs"]["n8_short"]
+    assert G.hostprep_case() == ref["hostprep"]

@@ -16,7 +16,8 @@
 struct LimbJob { const u64 *in; u64 *out; int mod; int pad; };
 struct NttJobs { LimbJob j[HEC_MAXJOBS]; };
 #ifndef HEC_GEN_MINB
-#define HEC_GEN_MINB 1 // resident CTAs per SM the generic transforms are compiled for (register cap)
+#define HEC_GEN_MINB 3 // resident CTAs per SM the generic transforms are compiled for (register cap): measured
+                       // 3 -> -1.6 % key switch, -2.3 % CtoS against no cap; 4 (64 registers, small spills) -> +0.5 %
 #endif
 
 // forward NTT = k_col_fwd then k_row_fwd;  inverse = k_row_inv then k_col_inv

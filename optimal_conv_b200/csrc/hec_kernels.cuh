@@ -15,6 +15,12 @@
 #define HEC_MAXJOBS 64
 struct LimbJob { const u64 *in; u64 *out; int mod; int pad; };
 struct NttJobs { LimbJob j[HEC_MAXJOBS]; };
+// programmatic dependent launch: let the next kernel of the stream be scheduled while this grid drains, and do not touch
+// memory before the previous grid has completed (both are no-ops for a kernel launched without the attribute)
+#define HEC_PDL_SYNC() asm volatile("griddepcontrol.launch_dependents;\n\tgriddepcontrol.wait;" ::: "memory")
+// the two halves apart: everything between them may only read kernel parameters and the static modulus table
+#define HEC_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define HEC_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
 #ifndef HEC_GEN_MINB
 #define HEC_GEN_MINB 3 // resident CTAs per SM the generic transforms are compiled for (register cap): measured
                        // 3 -> -1.6 % key switch, -2.3 % CtoS against no cap; 4 (64 registers, small spills) -> +0.5 %
@@ -23,11 +29,13 @@ struct NttJobs { LimbJob j[HEC_MAXJOBS]; };
 // forward NTT = k_col_fwd then k_row_fwd;  inverse = k_row_inv then k_col_inv
 // (ring.NTT / ring.InvNTT, L:ring/ring_ntt.go:74-626).  grid = (16, njobs).
 __global__ void __launch_bounds__(HEC_THREADS, HEC_GEN_MINB) k_col_fwd(NttJobs J, const ModC *__restrict__ mods) {
+    HEC_PDL_TRIGGER();
     __shared__ u64 sm[HEC_TILE];
     const LimbJob job = J.j[blockIdx.y];
     const ModC M = mods[job.mod];
     ColGeom G(blockIdx.x);
     u64 x[16];
+    HEC_PDL_WAIT();
 #pragma unroll
     for (int k = 0; k < 16; k++) x[k] = job.in[G.gA(k)];
     col_fwd8(x, sm, G, M);
@@ -35,11 +43,13 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_GEN_MINB) k_col_fwd(NttJobs J
     for (int k = 0; k < 16; k++) job.out[G.gB(k)] = x[k];
 }
 __global__ void __launch_bounds__(HEC_THREADS, HEC_GEN_MINB) k_row_fwd(NttJobs J, const ModC *__restrict__ mods) {
+    HEC_PDL_TRIGGER();
     __shared__ u64 sm[16 * HEC_ROW_PITCH];
     const LimbJob job = J.j[blockIdx.y];
     const ModC M = mods[job.mod];
     RowGeom G(blockIdx.x);
     u64 x[16];
+    HEC_PDL_WAIT();
     row_loadA(x, job.in, G);
     row_fwd8(x, sm, G, M);
     row_BtoA(x, sm, G);
@@ -48,22 +58,26 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_GEN_MINB) k_row_fwd(NttJobs J
     row_storeA(x, job.out, G);
 }
 __global__ void __launch_bounds__(HEC_THREADS, HEC_GEN_MINB) k_row_inv(NttJobs J, const ModC *__restrict__ mods) {
+    HEC_PDL_TRIGGER();
     __shared__ u64 sm[16 * HEC_ROW_PITCH];
     const LimbJob job = J.j[blockIdx.y];
     const ModC M = mods[job.mod];
     RowGeom G(blockIdx.x);
     u64 x[16];
+    HEC_PDL_WAIT();
     row_loadA(x, job.in, G);
     row_AtoB(x, sm, G);
     row_inv8(x, sm, G, M);
     row_storeA(x, job.out, G);
 }
 __global__ void __launch_bounds__(HEC_THREADS, HEC_GEN_MINB) k_col_inv(NttJobs J, const ModC *__restrict__ mods) {
+    HEC_PDL_TRIGGER();
     __shared__ u64 sm[HEC_TILE];
     const LimbJob job = J.j[blockIdx.y];
     const ModC M = mods[job.mod];
     ColGeom G(blockIdx.x);
     u64 x[16];
+    HEC_PDL_WAIT();
 #pragma unroll
     for (int k = 0; k < 16; k++) x[k] = job.in[G.gB(k)];
     col_inv8(x, sm, G, M);
@@ -94,6 +108,7 @@ enum {
 };
 template <int OP>
 __global__ void __launch_bounds__(256) k_ew(EwJobs J, const ModC *__restrict__ mods) {
+    HEC_PDL_SYNC();
     const EwJob job = J.j[blockIdx.y];
     const u64 q = mods[job.mod].q, qinv = mods[job.mod].qinv, rmod = mods[job.mod].rmod;
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < HEC_N; i += gridDim.x * blockDim.x) {
@@ -123,6 +138,7 @@ __global__ void __launch_bounds__(256) k_ew(EwJobs J, const ModC *__restrict__ m
 struct TensorJob { const u64 *a0, *a1, *b0, *b1; u64 *c0, *c1, *c2; u64 r2; int mod; };
 struct TensorJobs { TensorJob j[HEC_TNJOBS]; };
 __global__ void __launch_bounds__(256) k_tensor(TensorJobs J, const ModC *__restrict__ mods) {
+    HEC_PDL_SYNC();
     const TensorJob job = J.j[blockIdx.y];
     const u64 q = mods[job.mod].q, qinv = mods[job.mod].qinv;
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < HEC_N; i += gridDim.x * blockDim.x) {
@@ -138,6 +154,7 @@ __global__ void __launch_bounds__(256) k_tensor(TensorJobs J, const ModC *__rest
 // or out = sum_t a_t (b == null: a chain of Add, eval.go:123).  Pointer lists live in device memory.
 struct DotJob { const u64 *const *a; const u64 *const *b; u64 *out; int mod; int T; };
 __global__ void __launch_bounds__(256) k_dot(const DotJob *__restrict__ jobs, const ModC *__restrict__ mods) {
+    HEC_PDL_SYNC();
     const DotJob job = jobs[blockIdx.y];
     const u64 q = mods[job.mod].q, qinv = mods[job.mod].qinv;
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < HEC_N; i += gridDim.x * blockDim.x) {
@@ -196,6 +213,7 @@ struct Modup2Job {
     int n, ntargets;
 };
 __global__ void __launch_bounds__(256) k_modup2(const Modup2Job *__restrict__ jobs, const ModC *__restrict__ mods) {
+    HEC_PDL_SYNC();
     const Modup2Job &job = jobs[blockIdx.y];
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     u64 y[HEC_MAXA];

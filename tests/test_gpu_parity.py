@@ -753,6 +753,20 @@ def test_encode_coeffs_relu_moduli_and_errors():
         c.close()
 
 
+def test_encode_many_crosses_launch_chunks_and_pt_round_trip(ctx, orc):
+    """17 short vectors (more than one k_encode_coeffs launch holds), each checked; upload_pt -> download_pt is the identity"""
+    n, count = 3000, 17
+    vals = np.stack([_enc_values(n, 10.0 ** (t % 5 - 2), 900 + t) for t in range(count)])
+    pts = ctx.EncodeCoeffsNTTMany(vals, 0, 2.0 ** 30)
+    for t in range(count):
+        assert np.array_equal(ctx.download_pt(pts[t]), orc.encode_coeffs_ntt(vals[t], 2.0 ** 30, 0)), t
+        pts[t].free()
+    limbs = synth.uniform_limbs(31337, Q2, N)
+    pt = ctx.upload_pt(limbs, PR.SCALE)
+    assert np.array_equal(ctx.download_pt(pt), limbs)
+    pt.free()
+
+
 def test_prep_ker_on_the_device_feeds_the_conv(orc, idx_np):
     """prep_Ker's plaintext loop (conv.go:510-515) and the bias of evalConv_BN (eval.go:238-243) encoded by
     hec_encode_coeffs_many; the conv over them == the conv over host-encoded, uploaded plaintexts == the oracle's"""

@@ -197,6 +197,52 @@ static EwJob ewjob(const u64 *a, const u64 *b, u64 *out, int mod, u64 s0 = 0, u3
     return j;
 }
 
+// device copy of a small host table, cached by content (hec_ctx::staged).  The tables hold buffer addresses, which
+// repeat as long as the caller repeats the operation on the same ciphertexts / scratch layout.
+#define HEC_STAGE_CAP ((size_t)64 << 20)
+#define HEC_STAGE_SLAB ((size_t)4 << 20)
+static int stage_cached(hec_ctx *c, std::vector<char> &h, char **dev) {
+    h.resize((h.size() + 7) & ~(size_t)7, 0);
+    uint64_t k = 1469598103934665603ull;
+    const uint64_t *w = reinterpret_cast<const uint64_t *>(h.data());
+    for (size_t i = 0, n = h.size() / 8; i < n; i++) { k ^= w[i]; k *= 1099511628211ull; k ^= k >> 29; }
+    auto it = c->staged.find(k);
+    if (it != c->staged.end())
+        for (auto &e : it->second)
+            if (e.host.size() == h.size() && memcmp(e.host.data(), h.data(), h.size()) == 0) { *dev = e.dev; return HEC_OK; }
+    const size_t need = (h.size() + 255) & ~(size_t)255;
+    if (c->staged_bytes + need > HEC_STAGE_CAP) { // rare: start over (kernels in flight may still read the old tables)
+        HEC_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (char *p : c->stage_slabs) cudaFree(p);
+        c->stage_slabs.clear();
+        c->stage_cur = nullptr;
+        c->staged.clear();
+        c->staged_bytes = 0;
+    }
+    hec_ctx::StagedTab e;
+    if (need > HEC_STAGE_SLAB) { // an unusually large table gets a block of its own
+        HEC_CUDA(c, cudaMalloc(&e.dev, need));
+        c->stage_slabs.push_back(e.dev);
+    } else {
+        if (!c->stage_cur || c->stage_slab_top + need > HEC_STAGE_SLAB) {
+            char *slab = nullptr;
+            HEC_CUDA(c, cudaMalloc(&slab, HEC_STAGE_SLAB));
+            c->stage_slabs.push_back(slab);
+            c->stage_cur = slab;
+            c->stage_slab_top = 0;
+        }
+        e.dev = c->stage_cur + c->stage_slab_top;
+        c->stage_slab_top += need;
+    }
+    e.host = h;
+    // pageable source: staged by the driver before the call returns
+    HEC_CUDA(c, cudaMemcpyAsync(e.dev, e.host.data(), h.size(), cudaMemcpyHostToDevice, c->stream));
+    *dev = e.dev;
+    c->staged_bytes += need;
+    c->staged[k].push_back(std::move(e));
+    return HEC_OK;
+}
+
 // launch the exact basis extensions `jobs` (one entry per target limb): entries that share their source digit are
 // grouped so that k_modup2 computes y_i and v once per coefficient for all of the digit's targets; the grouped tables
 // are staged into one stream-ordered device buffer
@@ -226,21 +272,19 @@ static int launch_modup(hec_ctx *c, std::vector<ModupJob> &jobs) {
     }
     size_t tb = targets.size() * sizeof(Modup2Target), gb = groups.size() * sizeof(Modup2Job);
     char *dbuf = nullptr;
-    HEC_CUDA(c, cudaMallocAsync(&dbuf, tb + gb, c->stream));
-    const Modup2Target *dt = reinterpret_cast<const Modup2Target *>(dbuf);
-    for (size_t g = 0; g < groups.size(); g++) groups[g].targets = dt + first[g];
+    for (size_t g = 0; g < groups.size(); g++) groups[g].first = first[g];
     std::vector<char> h(tb + gb);
     memcpy(h.data(), targets.data(), tb);
     memcpy(h.data() + tb, groups.data(), gb);
-    // pageable source: staged by the driver before the call returns, so `h` may die
-    HEC_CUDA(c, cudaMemcpyAsync(dbuf, h.data(), tb + gb, cudaMemcpyHostToDevice, c->stream));
+    int rc = stage_cached(c, h, &dbuf);
+    if (rc) return rc;
     for (size_t off = 0; off < groups.size(); off += 65535) {
         unsigned n = (unsigned)std::min<size_t>(65535, groups.size() - off);
-        launch_k(c, k_modup2, dim3(HEC_N / 256, n), dim3(256), reinterpret_cast<const Modup2Job *>(dbuf + tb) + off, c->dmods);
+        launch_k(c, k_modup2, dim3(HEC_N / 256, n), dim3(256), reinterpret_cast<const Modup2Job *>(dbuf + tb) + off,
+                 reinterpret_cast<const Modup2Target *>(dbuf), c->dmods);
         c->launches += 1;
     }
     cudaError_t e = cudaGetLastError();
-    cudaFreeAsync(dbuf, c->stream);
     if (e != cudaSuccess) return c->fail(HEC_E_CUDA, std::string("modup: ") + cudaGetErrorString(e));
     return HEC_OK;
 }
@@ -351,6 +395,7 @@ extern "C" void hec_ctx_destroy(hec_ctx *c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto &kv : c->keys) cudaFree(kv.second.buf);
+    for (char *p : c->stage_slabs) cudaFree(p);
     if (c->arena) cudaFree(c->arena);
     if (c->dtables) cudaFree(c->dtables);
     if (c->dmods) cudaFree(c->dmods);
@@ -816,29 +861,27 @@ static int launch_dot(hec_ctx *c, const std::vector<DotSpec> &specs) {
     for (auto &sp : specs) np += sp.a.size() + sp.b.size();
     size_t bytes = np * sizeof(u64 *) + specs.size() * sizeof(DotJob);
     char *dbuf = nullptr;
-    HEC_CUDA(c, cudaMallocAsync(&dbuf, bytes, c->stream));
     std::vector<char> h(bytes);
     const u64 **hp = reinterpret_cast<const u64 **>(h.data());
-    const u64 **dp = reinterpret_cast<const u64 **>(dbuf);
     DotJob *hj = reinterpret_cast<DotJob *>(h.data() + np * sizeof(u64 *));
     size_t off = 0;
     for (size_t i = 0; i < specs.size(); i++) {
         const DotSpec &sp = specs[i];
-        hj[i].a = dp + off;
+        hj[i].a_off = (long long)off;
         for (auto x : sp.a) hp[off++] = x;
-        hj[i].b = sp.b.empty() ? nullptr : dp + off;
+        hj[i].b_off = sp.b.empty() ? -1 : (long long)off;
         for (auto x : sp.b) hp[off++] = x;
         hj[i].out = sp.out; hj[i].mod = sp.mod; hj[i].T = (int)sp.a.size();
     }
-    // pageable source: staged by the driver before the call returns, so `h` may die
-    HEC_CUDA(c, cudaMemcpyAsync(dbuf, h.data(), bytes, cudaMemcpyHostToDevice, c->stream));
+    int rc = stage_cached(c, h, &dbuf);
+    if (rc) return rc;
     for (size_t off = 0; off < specs.size(); off += 65535) { // grid.y limit
         unsigned ny = (unsigned)std::min<size_t>(65535, specs.size() - off);
-        launch_k(c, k_dot, dim3(32, ny), dim3(256), reinterpret_cast<const DotJob *>(dbuf + np * sizeof(u64 *)) + off, c->dmods);
+        launch_k(c, k_dot, dim3(32, ny), dim3(256), reinterpret_cast<const DotJob *>(dbuf + np * sizeof(u64 *)) + off,
+                 reinterpret_cast<const u64 *const *>(dbuf), c->dmods);
         c->launches += 1;
     }
     cudaError_t e = cudaGetLastError();
-    cudaFreeAsync(dbuf, c->stream);
     if (e != cudaSuccess) return c->fail(HEC_E_CUDA, std::string("k_dot: ") + cudaGetErrorString(e));
     return HEC_OK;
 }

@@ -5,6 +5,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <map>
+#include <unordered_map>
 #include <string>
 #include <vector>
 #include "hec_kernels.cuh"
@@ -82,6 +83,14 @@ struct hec_ctx {
     // scratch arena for the generic ops (stream-ordered reuse)
     u64 *arena = nullptr;
     size_t arena_limbs = 0, arena_top = 0;
+    // small job / pointer tables of k_modup2 and k_dot, kept on the device and found again by content: the same
+    // operation on the same buffers (a layer repeated per image, a benchmark loop) then launches without a copy
+    struct StagedTab { std::vector<char> host; char *dev = nullptr; };
+    std::unordered_map<uint64_t, std::vector<StagedTab>> staged;
+    size_t staged_bytes = 0;
+    std::vector<char *> stage_slabs; // device memory the tables are carved from (bump allocation)
+    char *stage_cur = nullptr;       // slab being filled
+    size_t stage_slab_top = 0;
     uint64_t launches = 0;
     std::string err;
 

@@ -152,10 +152,13 @@ __global__ void __launch_bounds__(256) k_tensor(TensorJobs J, const ModC *__rest
 
 // ---- sum over taps: out = sum_t a_t * b_t * R^-1 (b != null: a chain of MulNew + Add, conv.go:168-171)
 // or out = sum_t a_t (b == null: a chain of Add, eval.go:123).  Pointer lists live in device memory.
-struct DotJob { const u64 *const *a; const u64 *const *b; u64 *out; int mod; int T; };
-__global__ void __launch_bounds__(256) k_dot(const DotJob *__restrict__ jobs, const ModC *__restrict__ mods) {
+struct DotJob { long long a_off; long long b_off; u64 *out; int mod; int T; }; // offsets into the pointer list; b_off < 0: none
+__global__ void __launch_bounds__(256) k_dot(const DotJob *__restrict__ jobs, const u64 *const *__restrict__ ptrs,
+                                             const ModC *__restrict__ mods) {
     HEC_PDL_SYNC();
-    const DotJob job = jobs[blockIdx.y];
+    const DotJob jd = jobs[blockIdx.y];
+    struct { const u64 *const *a; const u64 *const *b; u64 *out; int mod; int T; } job =
+        {ptrs + jd.a_off, jd.b_off < 0 ? nullptr : ptrs + jd.b_off, jd.out, jd.mod, jd.T};
     const u64 q = mods[job.mod].q, qinv = mods[job.mod].qinv;
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < HEC_N; i += gridDim.x * blockDim.x) {
         u64 acc = 0;
@@ -209,10 +212,11 @@ struct Modup2Job {
     const u64 *src[HEC_MAXA];
     int smod[HEC_MAXA];
     u64 qib[HEC_MAXA];
-    const Modup2Target *targets; // device memory
+    size_t first;                // index of the job's first entry in the launch's target table
     int n, ntargets;
 };
-__global__ void __launch_bounds__(256) k_modup2(const Modup2Job *__restrict__ jobs, const ModC *__restrict__ mods) {
+__global__ void __launch_bounds__(256) k_modup2(const Modup2Job *__restrict__ jobs, const Modup2Target *__restrict__ targets,
+                                                const ModC *__restrict__ mods) {
     HEC_PDL_SYNC();
     const Modup2Job &job = jobs[blockIdx.y];
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -232,7 +236,7 @@ __global__ void __launch_bounds__(256) k_modup2(const Modup2Job *__restrict__ jo
     // the per-target tables (<= nQ + nP entries of 104 B) are the same for every thread: stage them in shared memory
     __shared__ Modup2Target sT[HEC_M2_MAXT];
     for (int k = threadIdx.x; k < job.ntargets * (int)(sizeof(Modup2Target) / 8); k += blockDim.x)
-        reinterpret_cast<u64 *>(sT)[k] = reinterpret_cast<const u64 *>(job.targets)[k];
+        reinterpret_cast<u64 *>(sT)[k] = reinterpret_cast<const u64 *>(targets + job.first)[k];
     __syncthreads();
     for (int t = 0; t < job.ntargets; t++) {
         const Modup2Target &T = sT[t];

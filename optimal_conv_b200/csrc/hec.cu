@@ -160,9 +160,14 @@ int hec_launch_ntt(hec_ctx *c, std::vector<LimbJob> &jobs, bool inverse) {
         int n = (int)std::min<size_t>(HEC_MAXJOBS, jobs.size() - off);
         NttJobs A, B;
         for (int i = 0; i < n; i++) {
-            A.j[i] = jobs[off + i];
-            B.j[i] = jobs[off + i];
-            B.j[i].in = jobs[off + i].out; // second pass runs in place on out
+            const LimbJob &j = jobs[off + i];
+            u64 *mid = (!inverse && j.mid) ? j.mid : j.out;
+            A.j[i] = j;
+            B.j[i] = j;
+            A.j[i].out = mid;              // first pass: in -> mid (prologue, if any)
+            A.j[i].flags = inverse ? 0 : (j.flags & HEC_LJ_PRO);
+            B.j[i].in = mid;               // second pass: mid -> out (epilogue, if any)
+            B.j[i].flags = inverse ? 0 : (j.flags & HEC_LJ_EPI);
         }
         dim3 grid(HEC_TILES_PER_LIMB, n);
         if (!inverse) {
@@ -655,17 +660,12 @@ static int div_round_last_many(hec_ctx *c, const std::vector<hec_ct *> &cts) {
             for (int i = 0; i < L; i++) {
                 u64 qi = c->q(i);
                 u64 *ui = u[m] + ((size_t)p * L + i) * HEC_N;
-                ej.push_back(ewjob(t[m] + (size_t)p * HEC_N, nullptr, ui, i, qi - half % qi));
-                nj.push_back({ui, ui, i, 0});
+                // (t mod q_i) + (q_i - half) in the transform's prologue, (u + 2q - ct) * (-q_L^-1) in its epilogue
+                // (were an EW_REDUCE_ADD pass in front and an EW_SUBMUL pass behind)
+                nj.push_back({t[m] + (size_t)p * HEC_N, cts[m]->limb(p, i), i, HEC_LJ_PRO | HEC_LJ_EPI, ui, cts[m]->limb(p, i),
+                              c->resc[L][i], qi - half % qi});
             }
-    if ((rc = launch_ew<EW_REDUCE_ADD>(c, ej))) return rc;
     if ((rc = hec_launch_ntt(c, nj, false))) return rc;
-    ej.clear();
-    for (size_t m = 0; m < n; m++)
-        for (int p = 0; p < 2; p++)
-            for (int i = 0; i < L; i++)
-                ej.push_back(ewjob(u[m] + ((size_t)p * L + i) * HEC_N, cts[m]->limb(p, i), cts[m]->limb(p, i), i, c->resc[L][i]));
-    if ((rc = launch_ew<EW_SUBMUL>(c, ej))) return rc;
     for (size_t m = 0; m < n; m++) cts[m]->level = L - 1;
     return HEC_OK;
 }
@@ -796,18 +796,17 @@ static int moddown_many(hec_ctx *c, int level, const std::vector<u64 *> &accQ, c
     if ((rc = hec_launch_ntt(c, nj, true))) return rc; // InvNTT on P (canonical residues of the lazy original)
     u64 *x = c->scratch(n * L);
     std::vector<ModupJob> mj;
-    std::vector<EwJob> ej;
     nj.clear();
     for (size_t i = 0; i < n; i++)
         for (int l = 0; l < L; l++) {
             u64 *xi = x + (i * L + l) * HEC_N;
+            u64 *aq = accQ[i] + (size_t)l * HEC_N;
             mj.push_back(modup_job(c, c->pq, accP[i], HEC_N, c->modQ(l), xi));
-            nj.push_back({xi, xi, l, 0});
-            ej.push_back(ewjob(xi, accQ[i] + (size_t)l * HEC_N, accQ[i] + (size_t)l * HEC_N, l, c->negpinv[l]));
+            // NTT(xi), then (xi + 2q - accQ) * (-P^-1) in the transform's epilogue (was a separate EW_SUBMUL pass)
+            nj.push_back({xi, aq, l, HEC_LJ_EPI, xi, aq, c->negpinv[l], 0});
         }
     if ((rc = launch_modup(c, mj))) return rc;
-    if ((rc = hec_launch_ntt(c, nj, false))) return rc;
-    return launch_ew<EW_SUBMUL>(c, ej);
+    return hec_launch_ntt(c, nj, false);
 }
 
 struct Decomp { u64 *D; int L, beta; };
@@ -823,7 +822,7 @@ static int decompose_many(hec_ctx *c, int level, const std::vector<const u64 *> 
     size_t n = c1.size();
     out.resize(n);
     std::vector<LimbJob> inv, fwd;
-    std::vector<EwJob> lift, copy;
+    std::vector<EwJob> copy;
     std::vector<ModupJob> mj;
     for (size_t i = 0; i < n; i++) {
         u64 *cinv = c->scratch(L);
@@ -839,15 +838,17 @@ static int decompose_many(hec_ctx *c, int level, const std::vector<const u64 *> 
                     copy.push_back(ewjob(c1[i] + (size_t)t * HEC_N, nullptr, dst, mod));
                     continue;
                 }
-                if (nd == 1) lift.push_back(ewjob(cinv + (size_t)st * HEC_N, nullptr, dst, mod, 0)); // copy path
-                else mj.push_back(modup_job(c, c->dec[d][nd], cinv + (size_t)st * HEC_N, HEC_N, mod, dst));
+                if (nd == 1) { // copy path: the single limb reduced modulo the target in the transform's prologue
+                    fwd.push_back({cinv + (size_t)st * HEC_N, dst, mod, HEC_LJ_PRO, nullptr, nullptr, 0, 0});
+                    continue;
+                }
+                mj.push_back(modup_job(c, c->dec[d][nd], cinv + (size_t)st * HEC_N, HEC_N, mod, dst));
                 fwd.push_back({dst, dst, mod, 0});
             }
         }
     }
     if ((rc = hec_launch_ntt(c, inv, true))) return rc;
     if (!copy.empty() && (rc = launch_ew<EW_COPY>(c, copy))) return rc;
-    if (!lift.empty() && (rc = launch_ew<EW_REDUCE_ADD>(c, lift))) return rc;
     if (!mj.empty() && (rc = launch_modup(c, mj))) return rc;
     return hec_launch_ntt(c, fwd, false);
 }

@@ -13,7 +13,13 @@
 // (1) generic kernels
 // =========================================================================================
 #define HEC_MAXJOBS 64
-struct LimbJob { const u64 *in; u64 *out; int mod; int pad; };
+// one limb through a transform.  Forward transforms can absorb the point-wise step in front of them and the one behind:
+//   flags & 1: the input is a residue of ANOTHER modulus (< 2^64): x = (in mod q) + pro_s0     (EW_REDUCE_ADD)
+//   flags & 2: out = (x + 2q - ep_b) * ep_s0 * R^-1 instead of x                              (EW_SUBMUL)
+// mid: where the first pass leaves its result (null: out) -- needed when ep_b aliases out
+struct LimbJob { const u64 *in; u64 *out; int mod; int flags; u64 *mid; const u64 *ep_b; u64 ep_s0; u64 pro_s0; };
+#define HEC_LJ_PRO 1
+#define HEC_LJ_EPI 2
 struct NttJobs { LimbJob j[HEC_MAXJOBS]; };
 // programmatic dependent launch: let the next kernel of the stream be scheduled while this grid drains, and do not touch
 // memory before the previous grid has completed (both are no-ops for a kernel launched without the attribute)
@@ -38,6 +44,10 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_GEN_MINB) k_col_fwd(NttJobs J
     HEC_PDL_WAIT();
 #pragma unroll
     for (int k = 0; k < 16; k++) x[k] = job.in[G.gA(k)];
+    if (job.flags & HEC_LJ_PRO) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) x[k] = addmod(canon(x[k], M), job.pro_s0, M.q);
+    }
     col_fwd8(x, sm, G, M);
 #pragma unroll
     for (int k = 0; k < 16; k++) job.out[G.gB(k)] = x[k];
@@ -55,6 +65,10 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_GEN_MINB) k_row_fwd(NttJobs J
     row_BtoA(x, sm, G);
 #pragma unroll
     for (int k = 0; k < 16; k++) x[k] = canon(x[k], M);
+    if (job.flags & HEC_LJ_EPI) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) x[k] = mred(x[k] + M.q2 - job.ep_b[G.gbase + 16 * k], job.ep_s0, M.q, M.qinv);
+    }
     row_storeA(x, job.out, G);
 }
 __global__ void __launch_bounds__(HEC_THREADS, HEC_GEN_MINB) k_row_inv(NttJobs J, const ModC *__restrict__ mods) {

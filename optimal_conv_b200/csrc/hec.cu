@@ -809,7 +809,7 @@ static int moddown_many(hec_ctx *c, int level, const std::vector<u64 *> &accQ, c
     return hec_launch_ntt(c, nj, false);
 }
 
-struct Decomp { u64 *D; int L, beta; };
+struct Decomp { u64 *D; int L, beta; const u64 *src; }; // src: the decomposed polynomial itself ([L][N], NTT domain)
 static size_t decomp_limbs(const hec_ctx *c, int level) {
     int L = level + 1, beta = (L + c->alpha - 1) / c->alpha;
     return (size_t)L + (size_t)beta * (L + c->nP);
@@ -822,22 +822,18 @@ static int decompose_many(hec_ctx *c, int level, const std::vector<const u64 *> 
     size_t n = c1.size();
     out.resize(n);
     std::vector<LimbJob> inv, fwd;
-    std::vector<EwJob> copy;
     std::vector<ModupJob> mj;
     for (size_t i = 0; i < n; i++) {
         u64 *cinv = c->scratch(L);
         u64 *D = c->scratch((size_t)beta * W);
-        out[i].D = D; out[i].L = L; out[i].beta = beta;
+        out[i].D = D; out[i].L = L; out[i].beta = beta; out[i].src = c1[i];
         for (int l = 0; l < L; l++) inv.push_back({c1[i] + (size_t)l * HEC_N, cinv + (size_t)l * HEC_N, l, 0});
         for (int d = 0; d < beta; d++) {
             int st = d * alpha, nd = std::min(c->xalpha[d], L - st);
             for (int t = 0; t < W; t++) {
                 u64 *dst = D + ((size_t)d * W + t) * HEC_N;
                 int mod = t < L ? c->modQ(t) : c->modP(t - L);
-                if (t < L && t >= st && t < st + nd) { // in-digit limb: reuse the NTT form of c1
-                    copy.push_back(ewjob(c1[i] + (size_t)t * HEC_N, nullptr, dst, mod));
-                    continue;
-                }
+                if (t < L && t >= st && t < st + nd) continue; // in-digit limb: the inner product reads c1's NTT form in place
                 if (nd == 1) { // copy path: the single limb reduced modulo the target in the transform's prologue
                     fwd.push_back({cinv + (size_t)st * HEC_N, dst, mod, HEC_LJ_PRO, nullptr, nullptr, 0, 0});
                     continue;
@@ -848,7 +844,6 @@ static int decompose_many(hec_ctx *c, int level, const std::vector<const u64 *> 
         }
     }
     if ((rc = hec_launch_ntt(c, inv, true))) return rc;
-    if (!copy.empty() && (rc = launch_ew<EW_COPY>(c, copy))) return rc;
     if (!mj.empty() && (rc = launch_modup(c, mj))) return rc;
     return hec_launch_ntt(c, fwd, false);
 }
@@ -906,7 +901,9 @@ static int ks_mac_many(hec_ctx *c, int level, const std::vector<Decomp> &dc, con
                 DotSpec sp;
                 int kt = t < L ? t : key[i]->Lk + (t - L);
                 for (int d = 0; d < beta; d++) {
-                    sp.a.push_back(D.D + ((size_t)d * W + t) * HEC_N);
+                    int st = d * c->alpha, nd = std::min(c->xalpha[d], L - st);
+                    bool own = t < L && t >= st && t < st + nd; // limb of the digit itself: no lifted copy exists
+                    sp.a.push_back(own ? D.src + (size_t)t * HEC_N : D.D + ((size_t)d * W + t) * HEC_N);
                     sp.b.push_back(key[i]->buf + ((size_t)(d * 2 + p) * kl + kt) * HEC_N);
                 }
                 sp.out = t < L ? accQ[2 * i + p] + (size_t)t * HEC_N : accP[2 * i + p] + (size_t)(t - L) * HEC_N;

@@ -174,14 +174,29 @@ __global__ void __launch_bounds__(256) k_dot(const DotJob *__restrict__ jobs, co
     struct { const u64 *const *a; const u64 *const *b; u64 *out; int mod; int T; } job =
         {ptrs + jd.a_off, jd.b_off < 0 ? nullptr : ptrs + jd.b_off, jd.out, jd.mod, jd.T};
     const u64 q = mods[job.mod].q, qinv = mods[job.mod].qinv;
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < HEC_N; i += gridDim.x * blockDim.x) {
-        u64 acc = 0;
+    // four coefficients per thread and term: 8 independent loads in flight per thread (the sum is bandwidth-bound and
+    // one coefficient at a time leaves too few bytes in flight per SM)
+    const u32 S = gridDim.x * blockDim.x;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < HEC_N; i += 4 * S) {
+        u64 acc[4] = {0, 0, 0, 0};
         for (int t = 0; t < job.T; t++) {
-            u64 v = job.a[t][i];
-            if (job.b != nullptr) v = mred(v, __ldg(job.b[t] + i), q, qinv);
-            acc = addmod(acc, v, q);
+            const u64 *pa = job.a[t];
+            u64 v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) v[k] = pa[i + k * S];
+            if (job.b != nullptr) {
+                const u64 *__restrict__ pb = job.b[t];
+                u64 w[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) w[k] = __ldg(pb + i + k * S);
+#pragma unroll
+                for (int k = 0; k < 4; k++) v[k] = mred(v[k], w[k], q, qinv);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) acc[k] = addmod(acc[k], v[k], q);
         }
-        job.out[i] = acc;
+#pragma unroll
+        for (int k = 0; k < 4; k++) job.out[i + k * S] = acc[k];
     }
 }
 

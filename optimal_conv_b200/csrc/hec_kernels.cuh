@@ -166,6 +166,9 @@ __global__ void __launch_bounds__(256) k_tensor(TensorJobs J, const ModC *__rest
 
 // ---- sum over taps: out = sum_t a_t * b_t * R^-1 (b != null: a chain of MulNew + Add, conv.go:168-171)
 // or out = sum_t a_t (b == null: a chain of Add, eval.go:123).  Pointer lists live in device memory.
+#ifndef HEC_DOT_U
+#define HEC_DOT_U 4
+#endif
 struct DotJob { long long a_off; long long b_off; u64 *out; int mod; int T; }; // offsets into the pointer list; b_off < 0: none
 __global__ void __launch_bounds__(256) k_dot(const DotJob *__restrict__ jobs, const u64 *const *__restrict__ ptrs,
                                              const ModC *__restrict__ mods) {
@@ -174,29 +177,29 @@ __global__ void __launch_bounds__(256) k_dot(const DotJob *__restrict__ jobs, co
     struct { const u64 *const *a; const u64 *const *b; u64 *out; int mod; int T; } job =
         {ptrs + jd.a_off, jd.b_off < 0 ? nullptr : ptrs + jd.b_off, jd.out, jd.mod, jd.T};
     const u64 q = mods[job.mod].q, qinv = mods[job.mod].qinv;
-    // four coefficients per thread and term: 8 independent loads in flight per thread (the sum is bandwidth-bound and
+    // HEC_DOT_U coefficients per thread and term: 2 * HEC_DOT_U independent loads in flight per thread (the sum is bandwidth-bound and
     // one coefficient at a time leaves too few bytes in flight per SM)
     const u32 S = gridDim.x * blockDim.x;
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < HEC_N; i += 4 * S) {
-        u64 acc[4] = {0, 0, 0, 0};
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < HEC_N; i += HEC_DOT_U * S) {
+        u64 acc[HEC_DOT_U] = {};
         for (int t = 0; t < job.T; t++) {
             const u64 *pa = job.a[t];
-            u64 v[4];
+            u64 v[HEC_DOT_U];
 #pragma unroll
-            for (int k = 0; k < 4; k++) v[k] = pa[i + k * S];
+            for (int k = 0; k < HEC_DOT_U; k++) v[k] = pa[i + k * S];
             if (job.b != nullptr) {
                 const u64 *__restrict__ pb = job.b[t];
-                u64 w[4];
+                u64 w[HEC_DOT_U];
 #pragma unroll
-                for (int k = 0; k < 4; k++) w[k] = __ldg(pb + i + k * S);
+                for (int k = 0; k < HEC_DOT_U; k++) w[k] = __ldg(pb + i + k * S);
 #pragma unroll
-                for (int k = 0; k < 4; k++) v[k] = mred(v[k], w[k], q, qinv);
+                for (int k = 0; k < HEC_DOT_U; k++) v[k] = mred(v[k], w[k], q, qinv);
             }
 #pragma unroll
-            for (int k = 0; k < 4; k++) acc[k] = addmod(acc[k], v[k], q);
+            for (int k = 0; k < HEC_DOT_U; k++) acc[k] = addmod(acc[k], v[k], q);
         }
 #pragma unroll
-        for (int k = 0; k < 4; k++) job.out[i + k * S] = acc[k];
+        for (int k = 0; k < HEC_DOT_U; k++) job.out[i + k * S] = acc[k];
     }
 }
 

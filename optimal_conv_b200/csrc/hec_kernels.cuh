@@ -121,27 +121,51 @@ enum {
     EW_CENTER_LIFT // out = (a > s1 ? a - q0 : a) mod q with s0 = q0 mod q, s1 = q0 >> 1  (Bootstrapper.modUp)
 };
 template <int OP>
+__device__ __forceinline__ u64 ew_apply(u64 a, u64 b, u64 o, u32 i, const EwJob &job, u64 q, u64 qinv, u64 rmod) {
+    if (OP == EW_MULMONT) return mred(a, b, q, qinv);
+    else if (OP == EW_MULSCALAR || OP == EW_TOMONT) return mred(a, job.s0, q, qinv);
+    else if (OP == EW_ADD) return addmod(a, b, q);
+    else if (OP == EW_SUB) return submod(a, b, q);
+    else if (OP == EW_ADD_MONT) return addmod(a, mred(b, 1ull, q, qinv), q);
+    else if (OP == EW_REDUCE_ADD) return addmod(mred(a, rmod, q, qinv), job.s0, q);
+    else if (OP == EW_CENTER) return cred(a + job.s0, q);
+    else if (OP == EW_SUBMUL) return mred(a + 2 * q - b, job.s0, q, qinv);
+    else if (OP == EW_MAC) return addmod(o, mred(a, b, q, qinv), q);
+    else if (OP == EW_MULSCALAR_ADD) return addmod(o, mred(a, job.s0, q, qinv), q);
+    else if (OP == EW_MULSCALAR_HALVES) return mred(a, i < HEC_N / 2 ? job.s0 : job.s1, q, qinv);
+    else if (OP == EW_CENTER_LIFT) { u64 r = mred(a, rmod, q, qinv); if (a > job.s1) r = submod(r, job.s0, q); return r; }
+    else return a; // EW_PERMUTE (a was gathered), EW_COPY
+}
+template <int OP>
 __global__ void __launch_bounds__(256) k_ew(EwJobs J, const ModC *__restrict__ mods) {
     HEC_PDL_SYNC();
     const EwJob job = J.j[blockIdx.y];
     const u64 q = mods[job.mod].q, qinv = mods[job.mod].qinv, rmod = mods[job.mod].rmod;
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < HEC_N; i += gridDim.x * blockDim.x) {
-        u64 r;
-        if (OP == EW_MULMONT) r = mred(job.a[i], job.b[i], q, qinv);
-        else if (OP == EW_MULSCALAR || OP == EW_TOMONT) r = mred(job.a[i], job.s0, q, qinv);
-        else if (OP == EW_ADD) r = addmod(job.a[i], job.b[i], q);
-        else if (OP == EW_SUB) r = submod(job.a[i], job.b[i], q);
-        else if (OP == EW_ADD_MONT) r = addmod(job.a[i], mred(job.b[i], 1ull, q, qinv), q);
-        else if (OP == EW_REDUCE_ADD) r = addmod(mred(job.a[i], rmod, q, qinv), job.s0, q);
-        else if (OP == EW_CENTER) r = cred(job.a[i] + job.s0, q);
-        else if (OP == EW_SUBMUL) r = mred(job.a[i] + 2 * q - job.b[i], job.s0, q, qinv);
-        else if (OP == EW_MAC) r = addmod(job.out[i], mred(job.a[i], job.b[i], q, qinv), q);
-        else if (OP == EW_PERMUTE) r = job.a[perm_index(i, job.g)];
-        else if (OP == EW_MULSCALAR_ADD) r = addmod(job.out[i], mred(job.a[i], job.s0, q, qinv), q);
-        else if (OP == EW_MULSCALAR_HALVES) r = mred(job.a[i], i < HEC_N / 2 ? job.s0 : job.s1, q, qinv);
-        else if (OP == EW_CENTER_LIFT) { u64 a = job.a[i]; r = mred(a, rmod, q, qinv); if (a > job.s1) r = submod(r, job.s0, q); }
-        else r = job.a[i];
-        job.out[i] = r;
+    constexpr bool NEEDS_B = OP == EW_MULMONT || OP == EW_ADD || OP == EW_SUB || OP == EW_ADD_MONT || OP == EW_SUBMUL || OP == EW_MAC;
+    constexpr bool NEEDS_O = OP == EW_MAC || OP == EW_MULSCALAR_ADD;
+    const u32 S = gridDim.x * blockDim.x;
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (4 * S <= HEC_N) {
+        // four elements per thread with all their loads issued first (each thread reads and writes the same indices,
+        // so in-place operands stay safe)
+        for (; i < HEC_N; i += 4 * S) {
+            u64 a[4], b[4], o[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const u32 x = i + k * S;
+                a[k] = job.a[OP == EW_PERMUTE ? perm_index(x, job.g) : x];
+                b[k] = NEEDS_B ? job.b[x] : 0;
+                o[k] = NEEDS_O ? job.out[x] : 0;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) job.out[i + k * S] = ew_apply<OP>(a[k], b[k], o[k], i + k * S, job, q, qinv, rmod);
+        }
+    } else {
+        for (; i < HEC_N; i += S) {
+            const u64 a = job.a[OP == EW_PERMUTE ? perm_index(i, job.g) : i];
+            const u64 b = NEEDS_B ? job.b[i] : 0, o = NEEDS_O ? job.out[i] : 0;
+            job.out[i] = ew_apply<OP>(a, b, o, i, job, q, qinv, rmod);
+        }
     }
 }
 

@@ -237,9 +237,11 @@ int hec_keep_ctxt(hec_ctx *ctx, const hec_ct *input, const hec_pt *mask, double 
 
 /* A prepared evalConv_BN for `batch` independent input ciphertexts per run: kernel
  * plaintexts, monomials, bias and keys stay resident; the kernel sequence is captured in a
- * CUDA graph.  in_level must be 1 (ECD_LV) in this build.  The plan keeps its own scaled copy of the
- * kernel plaintexts but references pt_idx, pt_bias and the uploaded keys: they (and the context) must
- * outlive the plan. */
+ * CUDA graph.  in_level must be 1 (ECD_LV) in this build.  The plan keeps its own copies of the plaintexts
+ * (kernels with the SetScale constant folded in, monomials, bias) and references the uploaded keys:
+ * hec_swk_drop / hec_swk_upload on a key a live plan reads only release the handle; its device memory goes
+ * with the last plan that reads it.  The context must outlive the plan.
+ * HEC_E_SCALE when pt_bias is not at out_scale (eval.go:252-257). */
 int hec_plan_create(hec_ctx *ctx, const hec_pt *const *pt_ker, int max_ob, int norm, double in_scale,
                     double out_scale, const hec_pt *const *pt_idx, const hec_pt *pt_bias, int batch,
                     hec_plan **plan);
@@ -263,6 +265,14 @@ int hec_plan_span_end_ms(hec_plan *plan, float *ms);
  * order A1,A2,A3,(B1..B5) per pack level -- measurement aid for the roofline report */
 int hec_plan_profile(hec_plan *plan, const hec_ct *const *ins, float *ms, int cap, int *n);
 void hec_plan_destroy(hec_plan *plan);
+/* hec_conv_then_pack (fused) keeps the plans it builds, keyed by its arguments' identities (plaintext and key
+ * uploads, max_ob, norm, scales): a per-convolution caller (conv.go:522, one call per image with the layer's
+ * kernels) pays for a plan once.  Number of plans currently cached (at most 8, least recently used goes first). */
+int hec_plan_cache_size(const hec_ctx *ctx);
+/* Host arithmetic, no device: smallest y < p with uint64(float64(y)/float64(p)) == 1, or ~0 if there is none --
+ * the float overflow count of the single-prime exact basis extension (L:ring/ring_basis_extension.go:670-713)
+ * as the step function the fused mod-down kernel evaluates. */
+uint64_t hec_float_quotient_threshold(uint64_t p);
 
 #ifdef __cplusplus
 }

@@ -8,6 +8,9 @@
 
 using namespace hec;
 
+void hec_plan_cache_clear(hec_ctx *c);                    // hec_conv.cu
+void hec_plan_cache_evict(hec_ctx *c, uint64_t serial);   // hec_conv.cu
+
 // =========================================================================================
 // ring constants
 // =========================================================================================
@@ -334,27 +337,34 @@ extern "C" int hec_ctx_create(hec_ctx **out, int logN, const uint64_t *Q, int nQ
     }
     auto bail = [&](int code) { hec_ctx_destroy(c); return code; };
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(HEC_E_CUDA);
-    {   // keep freed ciphertext buffers cached in the pool instead of returning them to the driver
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-            uint64_t keep = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
+    {   // a pool of the context's own for the stream-ordered allocations (ciphertexts, plaintexts): freed buffers stay
+        // cached in it instead of going back to the driver, and nothing of that outlives the context or touches the
+        // device's default pool, which the host process may share
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        if (cudaMemPoolCreate(&c->pool, &props) != cudaSuccess) return bail(HEC_E_CUDA);
+        uint64_t keep = ~0ull;
+        cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
-    cudaEventCreate(&c->ev0);
-    cudaEventCreate(&c->ev1);
+    if (cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) return bail(HEC_E_CUDA);
     size_t tw = (size_t)nm * 2 * HEC_N;
     if (cudaMalloc(&c->dtables, tw * sizeof(ulonglong2)) != cudaSuccess) return bail(HEC_E_NOMEM);
     if (cudaMalloc(&c->dmods, nm * sizeof(ModC)) != cudaSuccess) return bail(HEC_E_NOMEM);
     std::vector<ModC> mc(nm);
     for (int i = 0; i < nm; i++) {
         ulonglong2 *psi = c->dtables + (size_t)i * 2 * HEC_N, *psi_inv = psi + HEC_N;
-        cudaMemcpy(psi, c->hm[i].psi.data(), HEC_N * sizeof(ulonglong2), cudaMemcpyHostToDevice);
-        cudaMemcpy(psi_inv, c->hm[i].psi_inv.data(), HEC_N * sizeof(ulonglong2), cudaMemcpyHostToDevice);
+        if (cudaMemcpy(psi, c->hm[i].psi.data(), HEC_N * sizeof(ulonglong2), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(psi_inv, c->hm[i].psi_inv.data(), HEC_N * sizeof(ulonglong2), cudaMemcpyHostToDevice) != cudaSuccess)
+            return bail(HEC_E_CUDA);
         mc[i].q = c->hm[i].q; mc[i].qinv = c->hm[i].qinv; mc[i].q2 = 2 * c->hm[i].q;
         mc[i].rmod = c->hm[i].rmod; mc[i].ninv_w = c->hm[i].ninv_w; mc[i].ninv_s = c->hm[i].ninv_s;
+        mc[i].wn_w = mulmod(c->hm[i].psi_inv[HEC_TW_COLA].x, c->hm[i].ninv_w, c->hm[i].q);
+        mc[i].wn_s = (u64)(((u128)mc[i].wn_w << 64) / c->hm[i].q);
         mc[i].psi = psi; mc[i].psi_inv = psi_inv;
-        mc[i].tight = c->hm[i].q >= (1ull << 58) ? 1 : 0; mc[i].pad = 0;
+        mc[i].tight = c->hm[i].q >= (1ull << 57) ? 1 : 0; mc[i].pad = 0;
     }
     if (cudaMemcpy(c->dmods, mc.data(), nm * sizeof(ModC), cudaMemcpyHostToDevice) != cudaSuccess) return bail(HEC_E_CUDA);
     // RescaleParams (L:ring/ring.go:63-117)
@@ -399,7 +409,8 @@ extern "C" void hec_ctx_destroy(hec_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    for (auto &kv : c->keys) cudaFree(kv.second.buf);
+    hec_plan_cache_clear(c);
+    for (auto &kv : c->keys) { cudaFree(kv.second.buf); delete kv.second.kb; }
     for (char *p : c->stage_slabs) cudaFree(p);
     if (c->arena) cudaFree(c->arena);
     if (c->dtables) cudaFree(c->dtables);
@@ -407,6 +418,7 @@ extern "C" void hec_ctx_destroy(hec_ctx *c) {
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->pool) cudaMemPoolDestroy(c->pool);
     delete c;
 }
 extern "C" const char *hec_last_error(const hec_ctx *c) { return c ? c->err.c_str() : "null context"; }
@@ -417,11 +429,13 @@ extern "C" int hec_sync(hec_ctx *c) {
     return HEC_OK;
 }
 extern "C" int hec_timer_start(hec_ctx *c) {
+    if (!c) return HEC_E_INVAL;
     cudaSetDevice(c->device);
     HEC_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     return HEC_OK;
 }
 extern "C" int hec_timer_stop_ms(hec_ctx *c, float *ms) {
+    if (!c || !ms) return HEC_E_INVAL;
     cudaSetDevice(c->device);
     HEC_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     HEC_CUDA(c, cudaEventSynchronize(c->ev1));
@@ -452,7 +466,7 @@ int hec_ct_alloc(hec_ctx *c, int level, double scale, hec_ct **out) {
     ct->alloc = level + 1; ct->level = level; ct->scale = scale;
     // stream-ordered allocation: temporaries of the op-level path come from the device's memory pool and
     // are recycled without synchronising the stream
-    if (cudaMallocAsync(&ct->buf, (size_t)2 * ct->alloc * HEC_N * sizeof(u64), c->stream) != cudaSuccess) {
+    if (cudaMallocFromPoolAsync(&ct->buf, (size_t)2 * ct->alloc * HEC_N * sizeof(u64), c->pool, c->stream) != cudaSuccess) {
         delete ct;
         return c->fail(HEC_E_NOMEM, "cudaMallocAsync ciphertext");
     }
@@ -464,8 +478,8 @@ extern "C" int hec_pt_upload(hec_ctx *c, int level, const uint64_t *const *limbs
     if (!c || !limbs || !out || level < 0 || level >= c->nQ) return c ? c->fail(HEC_E_INVAL, "pt_upload args") : HEC_E_INVAL;
     cudaSetDevice(c->device);
     hec_pt *pt = new hec_pt();
-    pt->level = level; pt->scale = scale;
-    if (cudaMallocAsync(&pt->buf, (size_t)(level + 1) * HEC_N * sizeof(u64), c->stream) != cudaSuccess) { delete pt; return c->fail(HEC_E_NOMEM, "cudaMallocAsync plaintext"); }
+    pt->level = level; pt->scale = scale; pt->serial = c->next_serial++;
+    if (cudaMallocFromPoolAsync(&pt->buf, (size_t)(level + 1) * HEC_N * sizeof(u64), c->pool, c->stream) != cudaSuccess) { delete pt; return c->fail(HEC_E_NOMEM, "cudaMallocAsync plaintext"); }
     std::vector<EwJob> jobs;
     for (int i = 0; i <= level; i++) {
         u64 *d = pt->buf + (size_t)i * HEC_N;
@@ -481,6 +495,7 @@ extern "C" int hec_pt_upload(hec_ctx *c, int level, const uint64_t *const *limbs
 }
 extern "C" void hec_pt_free(hec_ctx *c, hec_pt *pt) {
     if (!pt) return;
+    if (c && !c->plan_cache.empty()) hec_plan_cache_evict(c, pt->serial); // a cached plan is identified by its plaintexts
     if (c) {
         cudaSetDevice(c->device);
         cudaFreeAsync(pt->buf, c->stream); // ordered after every kernel of this context that read it
@@ -557,6 +572,8 @@ extern "C" int hec_swk_upload(hec_ctx *c, uint64_t galEl, int max_level, const u
                 HEC_CUDA(c, cudaMemcpyAsync(dst, src, HEC_N * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
             }
     HEC_CUDA(c, cudaStreamSynchronize(c->stream));
+    k.kb = new KeyBuf();
+    k.kb->buf = k.buf; k.kb->serial = c->next_serial++;
     c->keys[galEl] = k;
     return HEC_OK;
 }
@@ -565,9 +582,13 @@ extern "C" int hec_swk_drop(hec_ctx *c, uint64_t galEl) {
     auto it = c->keys.find(galEl);
     if (it == c->keys.end()) return HEC_OK;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
-    cudaFree(it->second.buf);
+    KeyBuf *kb = it->second.kb;
     c->keys.erase(it);
+    if (!c->plan_cache.empty()) hec_plan_cache_evict(c, kb->serial);
+    if (kb->plan_refs > 0) { kb->dead = true; return HEC_OK; } // a caller's plan still reads it: freed with that plan
+    cudaStreamSynchronize(c->stream);
+    cudaFree(kb->buf);
+    delete kb;
     return HEC_OK;
 }
 
@@ -692,6 +713,7 @@ extern "C" int hec_rescale(hec_ctx *c, hec_ct *ct, double min_scale) {
 
 extern "C" int hec_set_scale(hec_ctx *c, hec_ct *ct, double scale) {
     // L:ckks/evaluator.go:1194-1209
+    if (!c || !ct) return c ? c->fail(HEC_E_INVAL, "set_scale args") : HEC_E_INVAL;
     int rc = hec_mult_by_const(c, ct, scale / ct->scale);
     if (rc) return rc;
     if ((rc = hec_rescale(c, ct, scale))) return rc;
@@ -768,15 +790,40 @@ extern "C" int hec_sub_new(hec_ctx *c, const hec_ct *a, const hec_ct *b, hec_ct 
     *out = o;
     return HEC_OK;
 }
+// Add(ct, pt, ct): evaluateInPlace's scale matching as in addsub above (L:ckks/evaluator.go:365-473): when the scales
+// differ by a factor whose floor is > 1 the smaller-scale operand is multiplied by that integer first -- the
+// ciphertext in place (it is the receiver), the plaintext into scratch; the result carries the larger scale
 extern "C" int hec_add_pt(hec_ctx *c, hec_ct *ct, const hec_pt *pt) {
-    if (!c || !ct || !pt) return HEC_E_INVAL;
+    if (!c || !ct || !pt) return c ? c->fail(HEC_E_INVAL, "add_pt args") : HEC_E_INVAL;
     cudaSetDevice(c->device);
-    int level = std::min(ct->level, pt->level);
+    const int level = std::min(ct->level, pt->level), L = level + 1;
+    int rc;
+    std::vector<const u64 *> pb(L);
+    for (int i = 0; i < L; i++) pb[i] = pt->buf + (size_t)i * HEC_N;
+    if (ct->scale > pt->scale && floor(ct->scale / pt->scale) > 1) {
+        std::vector<u64> k;
+        hec_const_limbs(c, level, floor(ct->scale / pt->scale), k);
+        if ((rc = reserve(c, (size_t)L))) return rc;
+        u64 *tmp = c->scratch((size_t)L);
+        std::vector<EwJob> mj;
+        for (int i = 0; i < L; i++) {
+            mj.push_back(ewjob(pb[i], nullptr, tmp + (size_t)i * HEC_N, i, mform(k[i], c->q(i)))); // stays in Montgomery form
+            pb[i] = tmp + (size_t)i * HEC_N;
+        }
+        if ((rc = launch_ew<EW_MULSCALAR>(c, mj))) return rc;
+    } else if (pt->scale > ct->scale && floor(pt->scale / ct->scale) > 1) {
+        std::vector<u64> k;
+        hec_const_limbs(c, level, floor(pt->scale / ct->scale), k);
+        std::vector<EwJob> mj;
+        for (int p = 0; p < 2; p++)
+            for (int i = 0; i < L; i++) mj.push_back(ewjob(ct->limb(p, i), nullptr, ct->limb(p, i), i, mform(k[i], c->q(i))));
+        if ((rc = launch_ew<EW_MULSCALAR>(c, mj))) return rc;
+    }
     std::vector<EwJob> jobs;
-    for (int i = 0; i <= level; i++) jobs.push_back(ewjob(ct->limb(0, i), pt->buf + (size_t)i * HEC_N, ct->limb(0, i), i));
-    int rc = launch_ew<EW_ADD_MONT>(c, jobs);
-    if (rc) return rc;
+    for (int i = 0; i < L; i++) jobs.push_back(ewjob(ct->limb(0, i), pb[i], ct->limb(0, i), i));
+    if ((rc = launch_ew<EW_ADD_MONT>(c, jobs))) return rc;
     ct->level = level;
+    ct->scale = std::max(ct->scale, pt->scale);
     return HEC_OK;
 }
 
@@ -1068,12 +1115,17 @@ extern "C" int hec_rotate_hoisted(hec_ctx *c, const hec_ct *ct, const int *rots,
     std::vector<const hec_ct *> in;
     std::vector<u64> gal;
     std::vector<hec_ct *> out;
+    auto fail = [&](int code) { // no half-filled output list
+        for (int r = 0; r < n; r++) if (outs[r]) { hec_ct_free(c, outs[r]); outs[r] = nullptr; }
+        return code;
+    };
     for (int r = 0; r < n; r++) {
-        if (rots[r] == 0) { if ((rc = hec_ct_copy_new(c, ct, &outs[r]))) return rc; continue; } // cOut[0] = ctIn.CopyNew()
-        if ((rc = hec_ct_alloc(c, ct->level, ct->scale, &outs[r]))) return rc;
+        if (rots[r] == 0) { if ((rc = hec_ct_copy_new(c, ct, &outs[r]))) return fail(rc); continue; } // cOut[0] = ctIn.CopyNew()
+        if ((rc = hec_ct_alloc(c, ct->level, ct->scale, &outs[r]))) return fail(rc);
         in.push_back(ct); gal.push_back(hec_galois_for_rotation(c, rots[r])); out.push_back(outs[r]);
     }
-    return hec_rotate_many(c, in, gal, out, true);
+    if ((rc = hec_rotate_many(c, in, gal, out, true))) return fail(rc);
+    return HEC_OK;
 }
 
 // =========================================================================================

@@ -23,9 +23,16 @@ static int pack_ctxts(hec_ctx *ev, std::vector<hec_ct *> &ctxts_in, int max_cnum
     int norm = max_cnum / real_cnum;
     int rc;
     std::vector<hec_ct *> ctxts(max_cnum, nullptr);
+    hec_ct *tmp1 = nullptr, *tmp2 = nullptr;
+    auto fail = [&](int code) { // every early return frees what this call allocated
+        for (auto &p : ctxts) if (p) { hec_ct_free(ev, p); p = nullptr; }
+        if (tmp1) hec_ct_free(ev, tmp1);
+        if (tmp2) hec_ct_free(ev, tmp2);
+        return code;
+    };
     for (int i = 0; i < max_cnum; i++)
         if (i % norm == 0) {
-            if ((rc = hec_ct_copy_new(ev, ctxts_in[i], &ctxts[i]))) return rc;
+            if ((rc = hec_ct_copy_new(ev, ctxts_in[i], &ctxts[i]))) return fail(rc);
             hec_ct_set_scale(ctxts[i], hec_ct_scale(ctxts[i]) * (double)real_cnum);
         }
     int logStep = 0;
@@ -33,21 +40,22 @@ static int pack_ctxts(hec_ctx *ev, std::vector<hec_ct *> &ctxts_in, int max_cnum
     int j = HEC_LOGN - logStep;
     while (step >= norm && step >= 1) {
         for (int i = 0; i < step; i += norm) {
-            hec_ct *tmp1 = nullptr, *tmp2 = nullptr;
-            if ((rc = hec_mul_pt_new(ev, ctxts[i + step], idx[logStep], &tmp1))) return rc;
-            if ((rc = hec_sub_new(ev, ctxts[i], tmp1, &tmp2))) return rc;
-            if ((rc = hec_add(ev, ctxts[i], tmp1, tmp1))) return rc;
-            if ((rc = hec_rotate_gal(ev, tmp2, (1ull << j) + 1, tmp2))) return rc;
-            if ((rc = hec_add(ev, tmp1, tmp2, ctxts[i]))) return rc;
+            if ((rc = hec_mul_pt_new(ev, ctxts[i + step], idx[logStep], &tmp1))) return fail(rc);
+            if ((rc = hec_sub_new(ev, ctxts[i], tmp1, &tmp2))) return fail(rc);
+            if ((rc = hec_add(ev, ctxts[i], tmp1, tmp1))) return fail(rc);
+            if ((rc = hec_rotate_gal(ev, tmp2, (1ull << j) + 1, tmp2))) return fail(rc);
+            if ((rc = hec_add(ev, tmp1, tmp2, ctxts[i]))) return fail(rc);
             hec_ct_free(ev, tmp1);
             hec_ct_free(ev, tmp2);
+            tmp1 = tmp2 = nullptr;
         }
         step /= 2;
         logStep--;
         j++;
     }
     *result = ctxts[0];
-    for (int i = 1; i < max_cnum; i++) if (ctxts[i]) hec_ct_free(ev, ctxts[i]);
+    ctxts[0] = nullptr;
+    fail(0);
     return HEC_OK;
 }
 
@@ -56,14 +64,16 @@ static int conv_then_pack_oplevel(hec_ctx *ev, const hec_ct *ctxt_in, const hec_
                                   double out_scale, const hec_pt *const *plain_idx, hec_ct **out) {
     std::vector<hec_ct *> ctxt_out(max_ob, nullptr);
     int rc;
+    auto cleanup = [&]() { for (auto &p : ctxt_out) if (p) { hec_ct_free(ev, p); p = nullptr; } };
     for (int i = 0; i < max_ob; i++)
         if (i % norm == 0) {
-            if ((rc = hec_mul_pt_new(ev, ctxt_in, pl_ker[i], &ctxt_out[i]))) return rc;
-            if ((rc = hec_set_scale(ev, ctxt_out[i], out_scale / (double)(max_ob / norm)))) return rc;
+            if ((rc = hec_mul_pt_new(ev, ctxt_in, pl_ker[i], &ctxt_out[i]))) { cleanup(); return rc; }
+            if ((rc = hec_set_scale(ev, ctxt_out[i], out_scale / (double)(max_ob / norm)))) { cleanup(); return rc; }
         }
     hec_ct *res = nullptr;
-    if ((rc = pack_ctxts(ev, ctxt_out, max_ob, max_ob / norm, plain_idx, &res))) return rc;
-    for (auto p : ctxt_out) if (p) hec_ct_free(ev, p);
+    rc = pack_ctxts(ev, ctxt_out, max_ob, max_ob / norm, plain_idx, &res);
+    cleanup();
+    if (rc) return rc;
     if (out_scale != hec_ct_scale(res) || 0 != hec_ct_level(res)) {
         hec_ct_free(ev, res);
         return ev->fail(HEC_E_SCALE, "LV or scale after conv then pack, inconsistent");
@@ -216,12 +226,30 @@ extern "C" int hec_keep_ctxt(hec_ctx *ev, const hec_ct *input, const hec_pt *mas
 // =========================================================================================
 // fused plan
 // =========================================================================================
+// The exact basis extension P -> Q with ONE special prime computes v = uint64(float64(y) / float64(p)) for the
+// canonical residue y < p (L:ring/ring_basis_extension.go:670-713 with a single term): int -> double conversion and
+// IEEE division are monotone, so v is 0 up to a threshold and 1 from there on (float64(y)/float64(p) rounds up to 1.0
+// for the last few y below p once p > 2^53).  Returns the smallest such y, or ~0 if there is none.  Host arithmetic
+// only: the same IEEE operations the reference executes.
+extern "C" uint64_t hec_float_quotient_threshold(uint64_t p) {
+    auto v = [p](uint64_t y) { volatile double a = (double)y, b = (double)p; volatile double f = a / b; return (uint64_t)f; };
+    if (p == 0 || v(p - 1) == 0) return ~0ull;
+    uint64_t lo = 0, hi = p - 1; // v(lo) == 0 (y = 0), v(hi) == 1
+    while (hi - lo > 1) {
+        uint64_t mid = lo + (hi - lo) / 2;
+        if (v(mid)) hi = mid; else lo = mid;
+    }
+    return hi;
+}
+
 struct hec_plan {
     hec_ctx *c = nullptr;
     int B = 0, norm = 1, na = 0, M = 0, levels = 0;
     double in_scale = 0, out_scale = 0;
     const u64 **d_ctin = nullptr, **d_ptk = nullptr;
     u64 *ptk_scaled = nullptr; // [na][2][N]: kernel plaintexts with the MultByConst constant folded in
+    ulonglong2 *mono_pairs = nullptr; // [levels][N]: the pack monomials NTT(X^step) as Shoup pairs
+    u64 *bias_plain = nullptr;        // [N]: the bias plaintext as plain residues
     u64 *pool = nullptr; // all scratch / level buffers
     u64 *stage_in = nullptr, *xfinal = nullptr;
     ConvA pa;
@@ -235,7 +263,16 @@ struct hec_plan {
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     u64 *stage_in2[2] = {nullptr, nullptr}, *stage_out2[2] = {nullptr, nullptr};
     int next_ticket = 0;
+    // what the captured graph reads besides the plan's own memory (the plaintexts are copied at creation): the
+    // rotation keys, kept alive until the plan goes (see hec_swk_drop)
+    std::vector<KeyBuf *> ref_keys;
+    std::vector<uint64_t> cache_key; // identity of a plan hec_conv_then_pack cached (serials); empty: a caller's plan
 };
+static void plan_unref_all(hec_plan *p) {
+    for (KeyBuf *kb : p->ref_keys)
+        if (--kb->plan_refs == 0 && kb->dead) { cudaFree(kb->buf); delete kb; }
+    p->ref_keys.clear();
+}
 
 static int plan_launch_all(hec_plan *p, const std::function<void()> &after = [] {}) {
     hec_ctx *c = p->c;
@@ -266,7 +303,7 @@ static int plan_launch_all(hec_plan *p, const std::function<void()> &after = [] 
         for (int m = 0; m < p->M; m++) {
             u64 *x = p->xfinal + (size_t)m * 2 * HEC_N;
             J.j[0].a = x; J.j[0].b = p->bias; J.j[0].out = x; J.j[0].mod = p->pa.mq0; J.j[0].g = 0; J.j[0].s0 = 0; J.j[0].s1 = 0;
-            k_ew<EW_ADD_MONT><<<dim3(32, 1), 256, 0, s>>>(J, c->dmods);
+            k_ew<EW_ADD><<<dim3(32, 1), 256, 0, s>>>(J, c->dmods);
             after();
         }
     }
@@ -276,7 +313,7 @@ static int plan_launch_all(hec_plan *p, const std::function<void()> &after = [] 
 }
 
 extern "C" void hec_plan_destroy(hec_plan *p) {
-    if (!p) return;
+    if (!p || !p->c) return;
     cudaSetDevice(p->c->device);
     cudaStreamSynchronize(p->c->stream);
     if (p->exec) cudaGraphExecDestroy(p->exec);
@@ -293,8 +330,11 @@ extern "C" void hec_plan_destroy(hec_plan *p) {
     if (p->s_out) cudaStreamDestroy(p->s_out);
     if (p->pool) cudaFree(p->pool);
     if (p->ptk_scaled) cudaFree(p->ptk_scaled);
+    if (p->mono_pairs) cudaFree(p->mono_pairs);
+    if (p->bias_plain) cudaFree(p->bias_plain);
     if (p->d_ctin) cudaFree((void *)p->d_ctin);
     if (p->d_ptk) cudaFree((void *)p->d_ptk);
+    plan_unref_all(p);
     delete p;
 }
 
@@ -306,8 +346,10 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
     if ((max_ob & (max_ob - 1)) || (norm & (norm - 1)) || norm > max_ob || max_ob > 256)
         return c->fail(HEC_E_UNSUPPORTED, "max_ob and norm must be powers of two, max_ob <= 256");
     if (c->nQ < 2 || c->nP != 1) return c->fail(HEC_E_UNSUPPORTED, "fused conv needs >= 2 Q limbs and exactly one special prime (main.go:446-454)");
-    // the epilogues of A3 / B5 add 2q to an uncorrected forward transform (< 36q): needs q0 < 2^58
-    if (c->q(c->modQ(0)) >= (1ull << 58)) return c->fail(HEC_E_UNSUPPORTED, "fused conv needs a first modulus below 2^58 (use HEC_CONV_OPLEVEL)");
+    // the epilogues of A3 / B5 add a few q to an uncorrected forward transform (< 68q) and B5 sums up to 9 lazy terms
+    // before one reduction: needs q0 < 2^57; the quotient estimate of reduce_lazy needs q0 > 2^40
+    if (c->q(c->modQ(0)) >= (1ull << 57) || c->q(c->modQ(0)) <= (1ull << 40))
+        return c->fail(HEC_E_UNSUPPORTED, "fused conv needs a first modulus between 2^40 and 2^57 (use HEC_CONV_OPLEVEL)");
     const int B = max_ob, na = B / norm, M = batch;
     for (int i = 0; i < B; i += norm)
         if (!pt_ker[i] || pt_ker[i]->level < 1) return c->fail(HEC_E_LEVEL, "kernel plaintexts must be at level >= 1 (ECD_LV)");
@@ -322,6 +364,8 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
     while (1 - nb > 0 && s / (double)c->q(1 - nb) >= target / 2) { s /= (double)c->q(1 - nb); nb++; }
     double res_scale = target * (double)(B / norm); // pack_ctxts conv.go:274
     if (nb != 1 || res_scale != out_scale) return c->fail(HEC_E_SCALE, "LV or scale after conv then pack, inconsistent");
+    // eval.go:252-257: the bias plaintext is encoded at out_scale; any other scale is the reference's second panic
+    if (pt_bias && pt_bias->scale != out_scale) return c->fail(HEC_E_SCALE, "LV or scale after conv then pack, inconsistent (bias plaintext scale)");
 
     hec_plan *p = new hec_plan();
     p->c = c; p->B = B; p->norm = norm; p->na = na; p->M = M; p->in_scale = in_scale; p->out_scale = out_scale;
@@ -352,7 +396,7 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
     size_t limbs = 4 * (size_t)M                 // staged inputs [M][2][2]
                  + 2 * jobsA                     // w1, w2
                  + 2 * jobsA                     // X_0 .. X_last (geometric, < 2x)
-                 + nb0 * (1 + 1 + 2 + 2);        // wb1..wb4
+                 + nb0 * (1 + 1 + 2 + 2 + 1);    // wb1..wb4, z
     if (cudaMalloc(&p->pool, limbs * HEC_N * sizeof(u64)) != cudaSuccess) return bail(HEC_E_NOMEM, "cudaMalloc plan pool");
     u64 *cur = p->pool;
     auto take = [&](size_t n) { u64 *r = cur; cur += n * HEC_N; return r; };
@@ -360,7 +404,7 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
     u64 *w1 = take(jobsA), *w2 = take(jobsA);
     std::vector<u64 *> X(levels + 1);
     for (int l = 0; l <= levels; l++) X[l] = take((size_t)M * (na >> l) * 2);
-    u64 *wb1 = take(nb0), *wb2 = take(nb0), *wb3 = take(2 * nb0), *wb4 = take(2 * nb0);
+    u64 *wb1 = take(nb0), *wb2 = take(nb0), *wb3 = take(2 * nb0), *wb4 = take(2 * nb0), *wbz = take(nb0);
     p->xfinal = X[levels];
     // ---- Stage A constants ----
     const int mq0 = c->modQ(0), mq1 = c->modQ(1), mp0 = c->modP(0);
@@ -370,12 +414,19 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
     A.na = na; A.norm = norm; A.mq0 = mq0; A.mq1 = mq1;
     A.half1 = (q1 - 1) >> 1;
     A.hneg0 = q0 - A.half1 % q0;
-    A.resc0 = c->resc[1][0];
+    auto pair = [](u64 w, u64 q) { return make_ulonglong2(w, (u64)(((u128)w << 64) / q)); };
+    A.resc0 = pair(q0 - invmod(q1 % q0, q0), q0);
+    if (levels > 0 && cudaMalloc(&p->mono_pairs, (size_t)levels * HEC_N * sizeof(ulonglong2)) != cudaSuccess) return bail(HEC_E_NOMEM, "cudaMalloc");
+    if (pt_bias) {
+        if (cudaMalloc(&p->bias_plain, HEC_N * sizeof(u64)) != cudaSuccess) return bail(HEC_E_NOMEM, "cudaMalloc");
+        k_plan_tables<<<64, 256, 0, c->stream>>>(pt_bias->buf, nullptr, p->bias_plain, mq0, c->dmods);
+        c->launches++;
+    }
     // ---- tree levels ----
     int step = B / 2, logStep = 0;
     for (int i = step; i > 1; i /= 2) logStep++;
     int j = HEC_LOGN - logStep;
-    if (pt_bias) { p->bias = pt_bias->buf; p->bias_mod = mq0; }
+    if (pt_bias) { p->bias = p->bias_plain; p->bias_mod = mq0; }
     for (int l = 0; l < levels; l++, step /= 2, logStep--, j++) {
         u64 g = (1ull << j) + 1;
         auto it = c->keys.find(g);
@@ -385,17 +436,23 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
         ConvB b;
         memset(&b, 0, sizeof b);
         b.xin = X[l]; b.xout = X[l + 1];
-        b.mono = pt_idx[logStep]->buf;
+        ulonglong2 *mp = p->mono_pairs + (size_t)l * HEC_N;
+        k_plan_tables<<<64, 256, 0, c->stream>>>(pt_idx[logStep]->buf, mp, nullptr, mq0, c->dmods);
+        c->launches++;
+        b.mono = mp;
+        it->second.kb->plan_refs++;
+        p->ref_keys.push_back(it->second.kb);
         b.key = it->second.buf;
         b.keyL = it->second.Lk + c->nP;
         b.keyPoff = it->second.Lk;
-        b.bias = (l == levels - 1 && pt_bias) ? pt_bias->buf : nullptr;
-        b.w1 = wb1; b.w2 = wb2; b.w3 = wb3; b.w4 = wb4;
+        b.bias = (l == levels - 1 && pt_bias) ? p->bias_plain : nullptr;
+        b.w1 = wb1; b.w2 = wb2; b.w3 = wb3; b.w4 = wb4; b.z = wbz;
         b.n = na >> l; b.mq0 = mq0; b.mp0 = mp0;
         b.galEl = (u32)g;
-        b.negpinv = c->negpinv[0];
+        b.negpinv = pair(q0 - invmod(p0 % q0, q0), q0);
         b.qpj1 = c->pq.qpjinv[mq0][1];
-        b.p0f = (double)p0;
+        b.vthr = hec_float_quotient_threshold(p0);
+        b.mu0 = (u32)(((u128)1 << 64) / q0);
         p->pb.push_back(b);
     }
     p->launches_per_run = 3 + 5 * levels + ((levels == 0 && pt_bias) ? M : 0);
@@ -584,6 +641,69 @@ extern "C" int hec_plan_span_end_ms(hec_plan *p, float *ms) {
 // =========================================================================================
 // hec_conv_then_pack
 // =========================================================================================
+// The single-call entry is what a Go caller binds in place of conv_then_pack: one call per
+// convolution, the same kernel plaintexts for every image of a layer.  Building a plan (4 allocations, the plaintext
+// rescale, a stream capture and a graph instantiation) costs more than the convolution itself, so the plans built here
+// are kept in the context, keyed by what the graph reads -- the serials of the kernel / monomial / bias plaintexts and
+// of the rotation keys, B, norm and the two scales.  Freeing or replacing any of those objects evicts the plans that
+// read it (hec_pt_free, hec_swk_drop, hec_swk_upload).
+#define HEC_PLAN_CACHE_MAX 8
+void hec_plan_cache_clear(hec_ctx *c) {
+    std::vector<hec_plan *> all;
+    all.swap(c->plan_cache);
+    for (hec_plan *p : all) hec_plan_destroy(p);
+}
+void hec_plan_cache_evict(hec_ctx *c, uint64_t serial) {
+    for (size_t i = 0; i < c->plan_cache.size();) {
+        hec_plan *p = c->plan_cache[i];
+        if (std::find(p->cache_key.begin(), p->cache_key.end(), serial) != p->cache_key.end()) {
+            c->plan_cache.erase(c->plan_cache.begin() + i);
+            hec_plan_destroy(p);
+        } else {
+            i++;
+        }
+    }
+}
+extern "C" int hec_plan_cache_size(const hec_ctx *c) { return c ? (int)c->plan_cache.size() : 0; }
+static int plan_cached(hec_ctx *c, const hec_pt *const *pt_ker, int max_ob, int norm, double in_scale, double out_scale,
+                       const hec_pt *const *pt_idx, const hec_pt *pt_bias, hec_plan **out) {
+    std::vector<uint64_t> key;
+    auto bits = [](double d) { uint64_t u; memcpy(&u, &d, 8); return u; };
+    if (max_ob >= 1 && norm >= 1 && norm <= max_ob && max_ob <= 256) {
+        // serials start at 1 and only grow, so the small integers in front cannot be mistaken for one by evict()
+        // once they are offset into the top of the range
+        key = {~(uint64_t)max_ob, ~(uint64_t)(norm + 1000), bits(in_scale), bits(out_scale), pt_bias ? pt_bias->serial : 0};
+        for (int i = 0; i < max_ob; i += norm) key.push_back(pt_ker[i] ? pt_ker[i]->serial : 0);
+        int step = max_ob / 2, logStep = 0;
+        for (int i = step; i > 1; i /= 2) logStep++;
+        int j = HEC_LOGN - logStep;
+        for (int t = max_ob / norm; t > 1; t >>= 1, logStep--, j++) {
+            key.push_back(logStep >= 0 && pt_idx[logStep] ? pt_idx[logStep]->serial : 0);
+            auto it = c->keys.find((1ull << j) + 1);
+            key.push_back(it == c->keys.end() ? 0 : it->second.kb->serial);
+        }
+        for (size_t i = 0; i < c->plan_cache.size(); i++)
+            if (c->plan_cache[i]->cache_key == key) {
+                hec_plan *p = c->plan_cache[i];
+                c->plan_cache.erase(c->plan_cache.begin() + i);
+                c->plan_cache.insert(c->plan_cache.begin(), p);
+                *out = p;
+                return HEC_OK;
+            }
+    }
+    hec_plan *p = nullptr;
+    int rc = hec_plan_create(c, pt_ker, max_ob, norm, in_scale, out_scale, pt_idx, pt_bias, 1, &p);
+    if (rc) return rc;
+    p->cache_key = key;
+    c->plan_cache.insert(c->plan_cache.begin(), p);
+    while (c->plan_cache.size() > HEC_PLAN_CACHE_MAX) {
+        hec_plan *last = c->plan_cache.back();
+        c->plan_cache.pop_back();
+        hec_plan_destroy(last);
+    }
+    *out = p;
+    return HEC_OK;
+}
 extern "C" int hec_conv_then_pack(hec_ctx *c, const hec_ct *ct_in, const hec_pt *const *pt_ker, int max_ob, int norm,
                                   double out_scale, const hec_pt *const *pt_idx, const hec_pt *pt_bias, int flags,
                                   hec_ct **out) {
@@ -593,24 +713,27 @@ extern "C" int hec_conv_then_pack(hec_ctx *c, const hec_ct *ct_in, const hec_pt 
     if (flags == HEC_CONV_OPLEVEL) {
         hec_ct *res = nullptr;
         if ((rc = conv_then_pack_oplevel(c, ct_in, pt_ker, max_ob, norm, out_scale, pt_idx, &res))) return rc;
+        if (pt_bias && pt_bias->scale != hec_ct_scale(res)) { // eval.go:252-257
+            hec_ct_free(c, res);
+            return c->fail(HEC_E_SCALE, "LV or scale after conv then pack, inconsistent (bias plaintext scale)");
+        }
         if (pt_bias && (rc = hec_add_pt(c, res, pt_bias))) { hec_ct_free(c, res); return rc; } // eval.go:258
         *out = res;
         return HEC_OK;
     }
     if (ct_in->level != 1) return c->fail(HEC_E_UNSUPPORTED, "fused conv_then_pack expects a level-1 input (ECD_LV = 1)");
     hec_plan *plan = nullptr;
-    if ((rc = hec_plan_create(c, pt_ker, max_ob, norm, ct_in->scale, out_scale, pt_idx, pt_bias, 1, &plan))) return rc;
+    if ((rc = plan_cached(c, pt_ker, max_ob, norm, ct_in->scale, out_scale, pt_idx, pt_bias, &plan))) return rc;
     hec_ct *res = nullptr;
     const hec_ct *ins[1] = {ct_in};
     hec_ct *tmp = nullptr;
     if (ct_in->alloc != 2) { // compact a ciphertext whose buffer still has dropped limbs
-        if ((rc = hec_ct_alloc(c, 1, ct_in->scale, &tmp))) { hec_plan_destroy(plan); return rc; }
+        if ((rc = hec_ct_alloc(c, 1, ct_in->scale, &tmp))) return rc;
         for (int p = 0; p < 2; p++)
             cudaMemcpyAsync(tmp->limb(p, 0), ct_in->limb(p, 0), 2 * HEC_N * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream);
         ins[0] = tmp;
     }
     rc = hec_plan_run(plan, ins, &res);
-    hec_plan_destroy(plan);
     if (tmp) hec_ct_free(c, tmp);
     if (rc) { if (res) hec_ct_free(c, res); return rc; }
     *out = res;

@@ -16,9 +16,8 @@
 // with R = 2^64 exactly like MulCoeffsMontgomery.  How a residue class is represented
 // *inside* a transform is ours: twiddles are stored as Shoup pairs (w, floor(w*2^64/q)) --
 // the kernels are bound by the integer-multiply pipe (profiles/r01a), and a Shoup product is
-// 6 wide + 4 narrow multiplies against 10 + 3 for a Montgomery product -- and ranges are lazy
-// (forward: no correction at all for q < 2^58, a 4q correction every other stage otherwise;
-// inverse: [0,2q)).  Every value that leaves for the caller is canonical, so results are
+// 5 wide + 4 narrow multiplies (approximate quotient) against 10 + 3 for a Montgomery product -- and ranges are
+// lazy (forward: no correction at all for q < 2^57, a 4q correction per stage otherwise; inverse: [0,4q)).  Every value that leaves for the caller is canonical, so results are
 // bit-identical to the reference's canonical residues.
 #pragma once
 #include <cuda_runtime.h>
@@ -42,13 +41,51 @@ struct ModC {
     u64 q2;           // 2q
     u64 rmod;         // R mod q  (mred(x, rmod) = x mod q, canonical)
     u64 ninv_w, ninv_s; // N^-1 mod q and its Shoup companion
+    u64 wn_w, wn_s;     // psi_inv[1] * N^-1 (the twiddle of the last inverse stage with the N^-1 pass folded in) and companion
     const ulonglong2 *psi;     // Shoup pairs (w, floor(w * 2^64 / q)) of NttPsi, in consumption order (see fwd4)
     const ulonglong2 *psi_inv; // same for NttPsiInv
-    int tight;        // q >= 2^58: forward transform needs range corrections
+    int tight;        // q >= 2^57: the forward transform needs range corrections (see fwd4)
     int pad;
 };
 
 // ---- scalar primitives -----------------------------------------------------------------
+// Cost model of the integer pipe, measured (profiles/r02_ubench_arith.txt, profiles/r01e_pipe_mix.csv): IMAD.WIDE.U32
+// occupies the fmaheavy pipe for 4 cycles per warp and sub-partition whatever its addend, a 32-bit IMAD (and the
+// IMAD.MOV / IMAD.X / IMAD.IADD forms ptxas likes to emit) for 2, ALU instructions 2 on their own pipe, one
+// instruction issues per cycle.  A 64-bit modular product is therefore priced by its number of wide products:
+//   exact Shoup     y*w - floor(y*ws/2^64)*q        6 wide + 4 narrow   37.6 clk   (__umul64hi + two low products)
+//   lazy Montgomery                                10 wide + 3 narrow   49.0 clk
+//   approximate Shoup (below)                       5 wide + 4 narrow   31.9 clk
+// HEC_ARITH = 2 (default) uses the approximate form in every butterfly; HEC_ARITH = 1 keeps the exact product there
+// (round-1 arithmetic, for A/B runs).  Spelling the exact products without 64-bit addends was measured too and does
+// not pay (38.0 / 54.4 clk: the carries cost more ALU instructions than the addend forms cost multiplier cycles).
+#ifndef HEC_ARITH
+#define HEC_ARITH 2
+#endif
+// 32 x 32 -> 64 without an addend
+__device__ __forceinline__ void mulw(u32 &lo, u32 &hi, u32 a, u32 b) {
+    asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0,%1}, t;\n\t}" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+}
+__device__ __forceinline__ u64 pack64(u32 lo, u32 hi) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+__device__ __forceinline__ void unpack64(u64 x, u32 &lo, u32 &hi) { asm("mov.b64 {%0,%1}, %2;" : "=r"(lo), "=r"(hi) : "l"(x)); }
+// floor(x*y / 2^64) - e, e in {0,1,2}: the low partial product and the carry out of the middle column are dropped
+// (3 wide products instead of 4, none with an addend)
+__device__ __forceinline__ u64 mulhi64_approx(u64 x, u64 y) {
+    u32 x0, x1, y0, y1, l1, h1, a, b, d;
+    unpack64(x, x0, x1); unpack64(y, y0, y1);
+    mulw(l1, h1, x1, y1); mulw(d, a, x0, y1); mulw(d, b, x1, y0);
+    const u64 s = (u64)l1 + a + b;
+    return s + ((u64)h1 << 32);
+}
+// x*y mod 2^64: one wide product, two 32-bit IMADs chained through their addend
+__device__ __forceinline__ u64 mullo64(u64 x, u64 y) {
+    u32 x0, x1, y0, y1, l, h;
+    unpack64(x, x0, x1); unpack64(y, y0, y1);
+    mulw(l, h, x0, y0);
+    h = x0 * y1 + h;
+    h = x1 * y0 + h;
+    return pack64(l, h);
+}
 // x*y*R^-1 mod q, result in (0, 2q).  Needs x*y < q*2^64 (always true for y < q).
 __device__ __forceinline__ u64 mred_lazy(u64 x, u64 y, u64 q, u64 qinv) {
     u64 lo = x * y;
@@ -75,20 +112,31 @@ __device__ __forceinline__ u64 shoup(u64 y, ulonglong2 w, u64 q) {
     u64 qe = __umul64hi(y, w.y);
     return y * w.x - qe * q;
 }
-// Cooley-Tukey butterfly.  FIX: X >= 4q is pulled back by 4q first (bounds in fwd4).
+// the same with the approximate quotient: [0, 3q + y*q/2^64), below 4q for any y
+__device__ __forceinline__ u64 shoup4(u64 y, ulonglong2 w, u64 q) {
+#if HEC_ARITH == 2
+    u64 qe = mulhi64_approx(y, w.y);
+    return mullo64(y, w.x) - mullo64(qe, q);
+#else
+    return shoup(y, w, q);
+#endif
+}
+// Cooley-Tukey butterfly: T = Y*w < 4q, X' = X + T, Y' = X - T + 4q.  FIX: X >= 4q is pulled back by 4q first
+// (needs X < 8q; with it X', Y' < 8q, which still fits 64 bits for q < 2^61).
 template <bool FIX>
 __device__ __forceinline__ void ct_bfly(u64 &X, u64 &Y, ulonglong2 w, u64 q, u64 q2) {
     u64 x = X;
     if (FIX) x = cred(x, 2 * q2);
-    u64 t = shoup(Y, w, q);
+    u64 t = shoup4(Y, w, q);
     X = x + t;
-    Y = x - t + q2;
+    Y = x - t + 2 * q2;
 }
-// Gentleman-Sande butterfly, X,Y in [0,2q) -> [0,2q)
+// Gentleman-Sande butterfly, [0,4q) -> [0,4q): X' = X + Y pulled back below 4q, Y' = (X - Y + 4q)*w < 4q
+// (the sum stays below 8q < 2^64 for q < 2^61)
 __device__ __forceinline__ void gs_bfly(u64 &X, u64 &Y, ulonglong2 w, u64 q, u64 q2) {
     u64 u = X, v = Y;
-    X = cred(u + v, q2);
-    Y = shoup(u - v + q2, w, q);
+    X = cred(u + v, 2 * q2);
+    Y = shoup4(u - v + 2 * q2, w, q);
 }
 
 // Four forward stages on 16 register-resident coefficients.  The coefficient at slot k
@@ -105,10 +153,10 @@ __device__ __forceinline__ void gs_bfly(u64 &X, u64 &Y, ulonglong2 w, u64 q, u64
 //   [16,256)     column layout B, [g][15]     t = T + 16 + 15 g,         stride 1
 //   [256,4096)   row layout A', [b][15]       t = T + 256 + 15 b,        stride 1
 //   [4096,65536) row layout B', [b][15][16]   t = T + 4096 + 240 b + p,  stride 16
-// Ranges.  Each stage adds at most 2q to a value.  TIGHT = false (q < 2^58): no correction;
-// a 16-stage transform of inputs < 4q stays < 36q < 2^64.  TIGHT = true (q < 2^61): the first
-// and third stage pull X back below 4q, so values entering are < 8q and values leaving are
-// < 8q < 2^64 (the Y operand never needs it: shoup() accepts any 64-bit value).
+// Ranges.  Every twiddle product is < 4q, so a stage adds at most 4q to a value.  TIGHT = false (q < 2^57): no
+// correction at all; a 16-stage transform of inputs < 4q stays < 68q < 2^64.  TIGHT = true (q < 2^61, 8q < 2^64):
+// every stage first pulls X back below 4q, so values entering and leaving are < 8q (the Y operand never needs it:
+// the Shoup product accepts any 64-bit value).
 #define HEC_TW_COLA 0
 #define HEC_TW_COLB 16
 #define HEC_TW_ROWA 256
@@ -122,14 +170,11 @@ __device__ __forceinline__ void fwd4(u64 (&x)[16], const ulonglong2 *__restrict_
         for (int gi = 0; gi < ng; gi++) {
             ulonglong2 w = __ldg(t + (ng - 1 + gi) * STRIDE);
 #pragma unroll
-            for (int k = 0; k < d; k++) {
-                if (TIGHT && (lg == 0 || lg == 2)) ct_bfly<true>(x[gi * 2 * d + k], x[gi * 2 * d + k + d], w, q, q2);
-                else ct_bfly<false>(x[gi * 2 * d + k], x[gi * 2 * d + k + d], w, q, q2);
-            }
+            for (int k = 0; k < d; k++) ct_bfly<TIGHT>(x[gi * 2 * d + k], x[gi * 2 * d + k + d], w, q, q2);
         }
     }
 }
-// Four inverse stages (d = 1,2,4,8), same slots from the psi^-1 table.
+// Four inverse stages (d = 1,2,4,8), same slots from the psi^-1 table.  Values stay in [0,4q).
 template <int STRIDE>
 __device__ __forceinline__ void inv4(u64 (&x)[16], const ulonglong2 *__restrict__ t, u64 q, u64 q2) {
 #pragma unroll
@@ -146,6 +191,40 @@ __device__ __forceinline__ void inv4(u64 (&x)[16], const ulonglong2 *__restrict_
 // final pass of InvNTT: x * N^-1, canonical
 __device__ __forceinline__ u64 inv_final(u64 x, const ModC &M) {
     return cred(shoup(x, make_ulonglong2(M.ninv_w, M.ninv_s), M.q), M.q);
+}
+// The last four inverse stages of a transform with that final pass folded into the last stage (distance N/2, one
+// twiddle w): X' = (X + Y) * N^-1, Y' = (X - Y) * (w * N^-1), both canonical -- two exact products per butterfly
+// instead of an approximate one, a range correction and two exact ones.  t: the psi^-1 table in column layout A.
+__device__ __forceinline__ void inv4_final(u64 (&x)[16], const ulonglong2 *__restrict__ t, const ModC &M) {
+    const u64 q = M.q, q2 = M.q2;
+#pragma unroll
+    for (int lg = 3; lg >= 1; lg--) {
+        const int d = 8 >> lg, ng = 1 << lg;
+#pragma unroll
+        for (int gi = 0; gi < ng; gi++) {
+            ulonglong2 w = __ldg(t + (ng - 1 + gi));
+#pragma unroll
+            for (int k = 0; k < d; k++) gs_bfly(x[gi * 2 * d + k], x[gi * 2 * d + k + d], w, q, q2);
+        }
+    }
+    const ulonglong2 n1 = make_ulonglong2(M.ninv_w, M.ninv_s), n2 = make_ulonglong2(M.wn_w, M.wn_s);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const u64 u = x[k], v = x[k + 8];
+        x[k] = cred(shoup(u + v, n1, q), q);
+        x[k + 8] = cred(shoup(u - v + 2 * q2, n2, q), q);
+    }
+}
+// x < 16q -> canonical
+__device__ __forceinline__ u64 canon16(u64 x, u64 q) { return cred(cred(cred(cred(x, 8 * q), 4 * q), 2 * q), q); }
+// x < 8q -> canonical
+__device__ __forceinline__ u64 canon8(u64 x, u64 q) { return cred(cred(cred(x, 4 * q), 2 * q), q); }
+// y < 2^61 -> y mod q in [0,2q) for 2^40 < q, mu = floor(2^64/q) < 2^24: the quotient estimate
+// floor((y >> 32) * mu / 2^32) is floor(y/q) or one less (one wide product, then t*q)
+__device__ __forceinline__ u64 reduce_lazy(u64 y, u64 q, u32 mu) {
+    u32 lo, t;
+    mulw(lo, t, (u32)(y >> 32), mu);
+    return y - mullo64((u64)t, q);
 }
 // any 64-bit representative -> canonical residue
 __device__ __forceinline__ u64 canon(u64 x, const ModC &M) { return mred(x, M.rmod, M.q, M.qinv); }
@@ -198,7 +277,7 @@ __device__ __forceinline__ void row_loadB(u64 (&x)[16], const u64 *__restrict__ 
 #pragma unroll
     for (int k = 0; k < 8; k++) { ulonglong2 t = __ldg(v + k); x[2 * k] = t.x; x[2 * k + 1] = t.y; }
 }
-// in: layout A' (values < 4q, or < 8q if tight); out: layout B' (lazy, see fwd4)
+// in: layout A' (values < 4q, or < 8q if tight); out: layout B' (lazy: < 68q, or < 8q if tight)
 __device__ __forceinline__ void row_fwd8(u64 (&x)[16], u64 *sm, const RowGeom &G, const ModC &M) {
     if (M.tight) {
         fwd4<true, 1>(x, M.psi + G.twA(), M.q, M.q2);
@@ -210,7 +289,7 @@ __device__ __forceinline__ void row_fwd8(u64 (&x)[16], u64 *sm, const RowGeom &G
         fwd4<false, 16>(x, M.psi + G.twB(), M.q, M.q2);
     }
 }
-// in: layout B' (values < 2q); out: layout A' (< 2q)
+// in: layout B' (values < 4q); out: layout A' (< 4q)
 __device__ __forceinline__ void row_inv8(u64 (&x)[16], u64 *sm, const RowGeom &G, const ModC &M) {
     inv4<16>(x, M.psi_inv + G.twB(), M.q, M.q2);
     row_BtoA(x, sm, G);
@@ -260,11 +339,17 @@ __device__ __forceinline__ void col_fwd8(u64 (&x)[16], u64 *sm, const ColGeom &G
         fwd4<false, 1>(x, M.psi + HEC_TW_COLB + 15 * G.pg, M.q, M.q2);
     }
 }
-// in: layout B, out: layout A
+// in: layout B (values < 4q), out: layout A (< 4q)
 __device__ __forceinline__ void col_inv8(u64 (&x)[16], u64 *sm, const ColGeom &G, const ModC &M) {
     inv4<1>(x, M.psi_inv + HEC_TW_COLB + 15 * G.pg, M.q, M.q2);
     col_BtoA(x, sm, G);
     inv4<1>(x, M.psi_inv + HEC_TW_COLA, M.q, M.q2);
+}
+// the same, ending the inverse transform: out = canonical coefficients (N^-1 included)
+__device__ __forceinline__ void col_inv8_final(u64 (&x)[16], u64 *sm, const ColGeom &G, const ModC &M) {
+    inv4<1>(x, M.psi_inv + HEC_TW_COLB + 15 * G.pg, M.q, M.q2);
+    col_BtoA(x, sm, G);
+    inv4_final(x, M.psi_inv + HEC_TW_COLA, M);
 }
 
 // PermuteNTTIndex computed on the fly (L:ring/ring_automorphism.go:31-44):

@@ -85,8 +85,8 @@ static int encode_many(hec_ctx *c, const double *values, int count, int n_values
     auto drop = [&]() { for (hec_pt *p : pts) { cudaFreeAsync(p->buf, c->stream); delete p; } };
     for (int p = 0; p < count; p++) {
         hec_pt *pt = new hec_pt();
-        pt->level = level; pt->scale = scale;
-        if (cudaMallocAsync(&pt->buf, (size_t)(level + 1) * HEC_N * sizeof(u64), c->stream) != cudaSuccess) { delete pt; drop(); return c->fail(HEC_E_NOMEM, "cudaMallocAsync plaintext"); }
+        pt->level = level; pt->scale = scale; pt->serial = c->next_serial++;
+        if (cudaMallocFromPoolAsync(&pt->buf, (size_t)(level + 1) * HEC_N * sizeof(u64), c->pool, c->stream) != cudaSuccess) { delete pt; drop(); return c->fail(HEC_E_NOMEM, "cudaMallocAsync plaintext"); }
         pts.push_back(pt);
     }
     EncJobs J;

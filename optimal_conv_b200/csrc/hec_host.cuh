@@ -47,9 +47,18 @@ struct ModupTab {
     std::vector<std::vector<u64>> qpjinv; // [target][n+1]
 };
 
+// device buffer of one switching key.  Plans hold a reference: dropping or replacing a key that a live plan's graph
+// still reads only marks it dead; the memory goes when the last such plan does.
+struct KeyBuf {
+    u64 *buf = nullptr;
+    int plan_refs = 0;
+    bool dead = false;
+    uint64_t serial = 0;
+};
 struct SwKey {
-    u64 *buf = nullptr; // [ndig][2][Lk + nP][N], Montgomery
+    u64 *buf = nullptr; // [ndig][2][Lk + nP][N], Montgomery (= kb->buf)
     int ndig = 0, Lk = 0;
+    KeyBuf *kb = nullptr;
 };
 
 } // namespace hec
@@ -65,11 +74,14 @@ struct hec_pt {
     u64 *buf = nullptr; // [level+1][N], Montgomery form (pt * R mod q)
     int level = 0;
     double scale = 0;
+    uint64_t serial = 0; // unique per upload: identity of the contents for the plan cache
 };
+struct hec_plan;
 
 struct hec_ctx {
     int device = 0, nQ = 0, nP = 0, alpha = 0, beta_full = 0;
     cudaStream_t stream = nullptr;
+    cudaMemPool_t pool = nullptr; // the context's own stream-ordered pool
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<hec::HostMod> hm; // Q then P
     ModC *dmods = nullptr;
@@ -92,6 +104,8 @@ struct hec_ctx {
     char *stage_cur = nullptr;       // slab being filled
     size_t stage_slab_top = 0;
     uint64_t launches = 0;
+    uint64_t next_serial = 1;
+    std::vector<hec_plan *> plan_cache; // plans hec_conv_then_pack built, most recently used first
     std::string err;
 
     int modQ(int i) const { return i; }

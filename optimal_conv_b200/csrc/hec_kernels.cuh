@@ -94,9 +94,9 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_GEN_MINB) k_col_inv(NttJobs J
     HEC_PDL_WAIT();
 #pragma unroll
     for (int k = 0; k < 16; k++) x[k] = job.in[G.gB(k)];
-    col_inv8(x, sm, G, M);
+    col_inv8_final(x, sm, G, M);
 #pragma unroll
-    for (int k = 0; k < 16; k++) job.out[G.gA(k)] = inv_final(x[k], M);
+    for (int k = 0; k < 16; k++) job.out[G.gA(k)] = x[k];
 }
 
 // ---- element-wise ------------------------------------------------------------------------
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(256) k_dot(const DotJob *__restrict__ jobs, co
 }
 
 // ---- exact basis extension (modUpExact / reconstructRNS / multSum,
-// L:ring/ring_basis_extension.go:438-457,670-779).  One job per target limb. -------------
+// L:ring/ring_basis_extension.go:438-457,670-779) -----------------------------------------
 #define HEC_MAXA 5
 #define HEC_MUJOBS 12
 struct ModupJob {
@@ -241,24 +241,6 @@ struct ModupJob {
     int tmod, n;
 };
 struct ModupJobs { ModupJob j[HEC_MUJOBS]; };
-__global__ void __launch_bounds__(256) k_modup(ModupJobs J, const ModC *__restrict__ mods) {
-    const ModupJob &job = J.j[blockIdx.y];
-    const u64 pt = mods[job.tmod].q, ptinv = mods[job.tmod].qinv;
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < HEC_N; i += gridDim.x * blockDim.x) {
-        double vi = 0.0;
-        u64 acc = 0;
-        for (int s = 0; s < job.n; s++) {
-            const u64 qs = mods[job.smod[s]].q;
-            u64 y = mred(job.src[s][i], job.qib[s], qs, mods[job.smod[s]].qinv);
-            // v = (uint64) sum_i float64(y_i)/float64(q_i): IEEE double, sequential, no FMA
-            vi = __dadd_rn(vi, __ddiv_rn(__ull2double_rn(y), __ull2double_rn(qs)));
-            acc = addmod(acc, mred(y, job.qisp[s], pt, ptinv), pt);
-        }
-        u64 v = (u64)__double2ull_rz(vi);
-        job.dst[i] = addmod(acc, job.qpjinv[v], pt);
-    }
-}
-
 // The same extension for ALL targets of one source digit: y_i and the float overflow count v depend only on the
 // source, so they are computed once per coefficient (the per-target form above recomputes alpha Montgomery products
 // and alpha double divisions for each of the up to nQ + nP - alpha targets: it was 51 % of a full-level key switch).
@@ -342,7 +324,7 @@ struct ConvA {
     int na, norm, mq0, mq1;
     u64 half1;              // (q1-1)>>1
     u64 hneg0;              // q0 - (half1 mod q0)
-    u64 resc0;              // MForm(q0 - q1^-1 mod q0)  (RescaleParams)
+    ulonglong2 resc0;       // q0 - q1^-1 mod q0  (RescaleParams) as a Shoup pair
 };
 struct AJob {
     int c, a, m;
@@ -360,7 +342,7 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convA1(ConvA P, const
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         u32 i = G.gbase + 16 * k;
-        x[k] = mred(ct[i], __ldg(pt + i), M.q, M.qinv);
+        x[k] = mred_lazy(ct[i], __ldg(pt + i), M.q, M.qinv);
     }
     row_AtoB(x, sm, G);
     row_inv8(x, sm, G, M);
@@ -377,12 +359,11 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convA2(ConvA P, const
     u64 x[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) x[k] = in[G.gB(k)];
-    col_inv8(x, sm, G, M1);
+    col_inv8_final(x, sm, G, M1);                           // InvNTT incl. its final pass, canonical
     const bool fits = M1.q <= M0.q; // t < q1 <= q0 is already a canonical residue of q0
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        u64 t = inv_final(x[k], M1);                        // InvNTT final pass, canonical
-        t = cred(t + P.half1, M1.q);                        // + (q1-1)/2 mod q1
+        u64 t = cred(x[k] + P.half1, M1.q);                 // + (q1-1)/2 mod q1
         x[k] = (fits ? t : canon(t, M0)) + P.hneg0;         // (t mod q0) - half  in [0,2q0)
     }
     col_fwd8(x, sm, G, M0);
@@ -405,8 +386,27 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convA3(ConvA P, const
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         u32 i = G.gbase + 16 * k;
-        u64 v = mred(ct[i], __ldg(pt + i), M.q, M.qinv);
-        out[i] = mred(x[k] + M.q2 - v, P.resc0, M.q, M.qinv);
+        u64 v = mred_lazy(ct[i], __ldg(pt + i), M.q, M.qinv);
+        out[i] = cred(shoup(x[k] + M.q2 - v, P.resc0, M.q), M.q);
+    }
+}
+
+// plan set-up (once per plan): a Montgomery-form plaintext limb as Shoup pairs (w, floor(w * 2^64 / q)), or as plain
+// residues.  The quotient is a 64-step restoring division -- q < 2^61, so the shifted remainder never overflows.
+__global__ void __launch_bounds__(256) k_plan_tables(const u64 *__restrict__ in, ulonglong2 *pairs, u64 *plain, int mod,
+                                                     const ModC *__restrict__ mods) {
+    const u64 q = mods[mod].q, qinv = mods[mod].qinv;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < HEC_N; i += gridDim.x * blockDim.x) {
+        const u64 w = mred(in[i], 1ull, q, qinv);
+        if (plain) plain[i] = w;
+        if (pairs) {
+            u64 rem = w, quo = 0;
+            for (int b = 0; b < 64; b++) {
+                rem <<= 1; quo <<= 1;
+                if (rem >= q) { rem -= q; quo |= 1; }
+            }
+            pairs[i] = make_ulonglong2(w, quo);
+        }
     }
 }
 
@@ -418,15 +418,18 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convA3(ConvA P, const
 struct ConvB {
     const u64 *xin;  // [M*n][2][N]
     u64 *xout;       // [M*n/2][2][N]
-    const u64 *mono; // NTT(X^step) at q0, Montgomery form
+    const ulonglong2 *mono; // NTT(X^step) at q0 as Shoup pairs (plan-owned, built from pt_idx)
     const u64 *key;  // digit 0 of the switching key: [2][keyL][N], Montgomery
-    const u64 *bias; // Montgomery-form bias plaintext (only the last level), or null
+    const u64 *bias; // bias plaintext as plain residues (plan-owned copy; only the last level), or null
     u64 *w1, *w2, *w3, *w4;
+    u64 *z;          // [M*n/2][N]: tmp2.c1 = a1 - b1*X^step of every butterfly, in [0,3q)
     int n, keyL, keyPoff, mq0, mp0;
     u32 galEl;
-    u64 negpinv;     // q0 - MForm(P^-1 mod q0)   [A] test_run 0x4e5049
+    ulonglong2 negpinv; // q0 - P^-1 mod q0 as a Shoup pair   [A] test_run 0x4e5049
     u64 qpj1;        // q0 - (p0 mod q0) = qpjInv[1]
-    double p0f;      // float64(p0)
+    u64 vthr;        // smallest y < p0 with uint64(float64(y)/float64(p0)) = 1 (~0: none): the float overflow count
+                     // of the single-prime extension is a step function of y (hec_float_quotient_threshold)
+    u32 mu0;         // floor(2^64 / q0)
 };
 struct BJob {
     int c, u, m;
@@ -440,7 +443,7 @@ struct BJob {
         b = P.xin + (size_t)(m * P.n + u + nb) * 2 * HEC_N;
     }
 };
-// B1: z = tmp2.c1 = a1 - b1*mono ; inverse stages t = 1..128 under q0      grid.y = M*nb
+// B1: z = tmp2.c1 = a1 - b1*mono (also stored) ; inverse stages t = 1..128 under q0      grid.y = M*nb
 __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convB1(ConvB P, const ModC *__restrict__ mods) {
     __shared__ u64 sm[16 * HEC_ROW_PITCH];
     const BJob J(HEC_BJOB, false, P);
@@ -450,8 +453,9 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convB1(ConvB P, const
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         u32 i = G.gbase + 16 * k;
-        x[k] = submod(J.a[HEC_N + i], mred(J.b[HEC_N + i], __ldg(P.mono + i), M.q, M.qinv), M.q);
+        x[k] = J.a[HEC_N + i] + M.q2 - shoup(J.b[HEC_N + i], __ldg(P.mono + i), M.q); // in (0,3q)
     }
+    row_storeA(x, P.z + (size_t)HEC_BJOB * HEC_N, G); // kept for B5: the key product and tmp1 = 2a - tmp2 need it
     row_AtoB(x, sm, G);
     row_inv8(x, sm, G, M);
     row_storeA(x, P.w1 + (size_t)HEC_BJOB * HEC_N, G);
@@ -467,12 +471,11 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convB2(ConvB P, const
     u64 x[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) x[k] = in[G.gB(k)];
-    col_inv8(x, sm, G, MQ);
+    col_inv8_final(x, sm, G, MQ);
     const bool fits = MQ.q <= MP.q2; // the digit residue (< q0) is fed to the lazy forward as is
+    if (!fits) {
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
-        u64 c = inv_final(x[k], MQ);
-        x[k] = fits ? c : canon(c, MP);
+        for (int k = 0; k < 16; k++) x[k] = canon(x[k], MP);
     }
     col_fwd8(x, sm, G, MP);
 #pragma unroll
@@ -521,14 +524,13 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convB4(ConvB P, const
     u64 x[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) x[k] = in[G.gB(k)];
-    col_inv8(x, sm, G, MP);
+    col_inv8_final(x, sm, G, MP);
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        // y = MRed(e, qibMont) with qibMont = MForm(1): the canonical residue mod p0
-        u64 y = inv_final(x[k], MP);
-        double f = __ddiv_rn(__ull2double_rn(y), P.p0f);
-        u64 v = (u64)__double2ull_rz(__dadd_rn(0.0, f));
-        x[k] = mred(y, MQ.rmod, MQ.q, MQ.qinv) + (v ? P.qpj1 : 0ull); // in [0,2q0)
+        // y = MRed(e, qibMont) with qibMont = MForm(1): the canonical residue mod p0; v = uint64(float64(y)/float64(p0))
+        // is 0 below P.vthr and 1 from there on
+        const u64 y = x[k];
+        x[k] = reduce_lazy(y, MQ.q, P.mu0) + (y >= P.vthr ? P.qpj1 : 0ull); // in [0,3q0)
     }
     col_fwd8(x, sm, G, MQ);
 #pragma unroll
@@ -536,6 +538,7 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convB4(ConvB P, const
 }
 // B5: finish NTT_q0, mod-down combine with acc_Q = z*key[c] (Q limb), + tmp2.c0 (c = 0),
 //     apply sigma_g inside the 256-word block, add tmp1 (+ bias)           grid.y = M*nb*2
+//     Sums are lazy (every term a known multiple of q away from canonical) and reduced once at the end.
 __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convB5(ConvB P, const ModC *__restrict__ mods) {
     __shared__ u64 sm[16 * HEC_ROW_PITCH];
     const BJob J(HEC_BJOB, true, P);
@@ -546,22 +549,20 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convB5(ConvB P, const
     row_fwd8(x, sm, G, M);
     row_BtoA(x, sm, G);
     const u64 *kq = P.key + (size_t)(J.c * P.keyL) * HEC_N;
+    const u64 *zb = P.z + (size_t)(HEC_BJOB >> 1) * HEC_N;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         u32 i = G.gbase + 16 * k;
-        u64 mono = __ldg(P.mono + i);
-        u64 a1 = J.a[HEC_N + i];
-        u64 m1 = mred(J.b[HEC_N + i], mono, M.q, M.qinv);
-        u64 z = submod(a1, m1, M.q);                                 // tmp2.c1
-        u64 accq = mred(z, __ldg(kq + i), M.q, M.qinv);              // MulCoeffsMontgomeryConstant + Reduce
-        u64 d = mred(x[k] + M.q2 - accq, P.negpinv, M.q, M.qinv);    // ModDownSplitNTTPQ combine
+        u64 z = zb[i];                                                // tmp2.c1 in (0,3q)
+        u64 accq = mred_lazy(z, __ldg(kq + i), M.q, M.qinv);          // MulCoeffsMontgomeryConstant (+ Reduce), (0,2q)
+        u64 d = shoup(x[k] + M.q2 - accq, P.negpinv, M.q);            // ModDownSplitNTTPQ combine, [0,2q)
         if (J.c == 0) {
             u64 a0 = J.a[i];
-            u64 m0 = mred(J.b[i], mono, M.q, M.qinv);
-            d = addmod(d, submod(a0, m0, M.q), M.q);                 // + tmp2.c0  (AddLvl)
-            t1[k] = addmod(a0, m0, M.q);                             // tmp1.c0
+            u64 m0 = shoup(J.b[i], __ldg(P.mono + i), M.q);           // [0,2q)
+            d += a0 + M.q2 - m0;                                      // + tmp2.c0  (AddLvl), < 5q
+            t1[k] = a0 + m0;                                          // tmp1.c0, < 3q
         } else {
-            t1[k] = addmod(a1, m1, M.q);                             // tmp1.c1
+            t1[k] = 2 * J.a[HEC_N + i] + 3 * M.q - z;                 // tmp1.c1 = a1 + b1*X^step = 2 a1 - tmp2.c1, in (0,5q)
         }
         u32 e = G.p + 16 * k;
         sm[G.sbase + e + (e >> 4)] = d;
@@ -572,8 +573,8 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convB5(ConvB P, const
     for (int k = 0; k < 16; k++) {
         u32 i = G.gbase + 16 * k;
         u32 s = perm_index(i, P.galEl) & 255u;                       // sigma_g stays inside the block
-        u64 r = addmod(t1[k], sm[G.sbase + s + (s >> 4)], M.q);
-        if (P.bias != nullptr && J.c == 0) r = addmod(r, mred(__ldg(P.bias + i), 1ull, M.q, M.qinv), M.q);
-        out[i] = r;
+        u64 r = t1[k] + sm[G.sbase + s + (s >> 4)];                   // < 8q
+        if (P.bias != nullptr && J.c == 0) r += __ldg(P.bias + i);
+        out[i] = canon16(r, M.q);
     }
 }

@@ -41,7 +41,10 @@ extern "C" int hec_ptdiag_upload(hec_ctx *c, int log_slots, int n1, int level, d
                 return c->fail(HEC_E_CUDA, "cudaMemcpyAsync diagonal");
             }
     }
-    HEC_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
+        cudaFree(m->buf); delete m;
+        return c->fail(HEC_E_CUDA, "ptdiag_upload: copy failed");
+    }
     *out = m;
     return HEC_OK;
 }
@@ -162,8 +165,9 @@ extern "C" int hec_linear_transform(hec_ctx *c, const hec_ct *ct, const hec_ptdi
                 mdQ.push_back(t1[g]); mdP.push_back(inner[j].p[1]);
             } else { // only the un-rotated diagonal in this giant step
                 t0[g] = c->scratch(L); t1[g] = c->scratch(L);
-                HEC_CUDA(c, cudaMemsetAsync(t0[g], 0, (size_t)L * HEC_N * sizeof(u64), c->stream));
-                HEC_CUDA(c, cudaMemsetAsync(t1[g], 0, (size_t)L * HEC_N * sizeof(u64), c->stream));
+                if (cudaMemsetAsync(t0[g], 0, (size_t)L * HEC_N * sizeof(u64), c->stream) != cudaSuccess ||
+                    cudaMemsetAsync(t1[g], 0, (size_t)L * HEC_N * sizeof(u64), c->stream) != cudaSuccess)
+                    return bail(c->fail(HEC_E_CUDA, "linear_transform: cudaMemsetAsync"));
             }
         }
         if (!mdQ.empty() && (rc = moddown_many(c, level, mdQ, mdP))) return bail(rc);
@@ -222,7 +226,8 @@ extern "C" int hec_linear_transform(hec_ctx *c, const hec_ct *ct, const hec_ptdi
                 if (poly == 0) for (size_t g = 0; g < ng; g++) sp.a.push_back(pt0[g] + (size_t)l * HEC_N);
                 if (have_outer) sp.a.push_back(outer.q[poly] + (size_t)l * HEC_N);
                 sp.out = o->limb(poly, l); sp.mod = l;
-                if (sp.a.empty()) HEC_CUDA(c, cudaMemsetAsync(sp.out, 0, HEC_N * sizeof(u64), c->stream));
+                if (sp.a.empty() && cudaMemsetAsync(sp.out, 0, HEC_N * sizeof(u64), c->stream) != cudaSuccess)
+                    return bail(c->fail(HEC_E_CUDA, "linear_transform: cudaMemsetAsync"));
                 else specs.push_back(sp);
             }
         if (!specs.empty() && (rc = launch_dot(c, specs))) return bail(rc);
@@ -286,6 +291,7 @@ extern "C" int hec_coeffs_to_slots(hec_ctx *c, const hec_ct *ct, const hec_ptdia
 // Bootstrapper.subSum (0x5071e0): ct += Rotate(ct, 2^i) for i = log_slots .. LogN - 2; nothing to do at full packing
 extern "C" int hec_sub_sum(hec_ctx *c, hec_ct *ct, int log_slots) {
     if (!c || !ct || log_slots < 0 || log_slots > HEC_LOGN - 1) return c ? c->fail(HEC_E_INVAL, "sub_sum args") : HEC_E_INVAL;
+    cudaSetDevice(c->device);
     int rc = HEC_OK;
     for (int i = log_slots; i < HEC_LOGN - 1 && !rc; i++) {
         hec_ct *rot = nullptr;

@@ -29,7 +29,7 @@ SYMBOLS = [
     "hec_ptdiag_upload", "hec_ptdiag_free", "hec_linear_transform", "hec_coeffs_to_slots", "hec_slots_to_coeffs", "hec_sub_sum", "hec_mod_up", "hec_bootstrap_ctos", "hec_bootstrap_stoc", "hec_bootstrapp", "hec_mult_by_int_and_add", "hec_evaluate_poly", "hec_evaluate_cheby", "hec_eval_relu", "hec_eval_relu_many", "hec_rotate_gal", "hec_rotate_new", "hec_rotate_hoisted", "hec_galois_for_rotation",
     "hec_ntt", "hec_keyswitch", "hec_moddown", "hec_conv_then_pack", "hec_conv_bl", "hec_ext_ctxt", "hec_keep_ctxt", "hec_plan_create", "hec_plan_run",
     "hec_plan_run_host", "hec_plan_submit_host", "hec_plan_wait", "hec_plan_span_begin", "hec_plan_span_end_ms",
-    "hec_plan_profile", "hec_plan_destroy",
+    "hec_plan_profile", "hec_plan_destroy", "hec_plan_cache_size", "hec_float_quotient_threshold",
 ]
 
 
@@ -155,6 +155,9 @@ def lib():
     L.hec_plan_profile.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]
     L.hec_plan_destroy.argtypes = [vp]
     L.hec_plan_destroy.restype = None
+    L.hec_plan_cache_size.argtypes = [vp]
+    L.hec_float_quotient_threshold.argtypes = [C.c_uint64]
+    L.hec_float_quotient_threshold.restype = C.c_uint64
     _lib = L
     return L
 
@@ -529,6 +532,9 @@ class Context:
         h = vp()
         self._chk(self.L.hec_keep_ctxt(self.h, ct.h, mask.h, min_scale, C.byref(h)))
         return Ciphertext(self, h)
+
+    def plan_cache_size(self):
+        return int(self.L.hec_plan_cache_size(self.h))
 
     def plan(self, pt_ker, norm, in_scale, out_scale, pt_idx, pt_bias, batch):
         return Plan(self, pt_ker, norm, in_scale, out_scale, pt_idx, pt_bias, batch)

@@ -27,12 +27,12 @@ def oracle_conv(o, w, norm, out_scale, idx_np, m=0, bias=True, nthreads=1):
 class GpuConv:
     """Uploads a synthetic workload once (kernels, monomials, bias, keys)."""
 
-    def __init__(self, ctx, w, idx_np, norm=1):
+    def __init__(self, ctx, w, idx_np, norm=1, out_scale=PR.SCALE):
         self.ctx, self.w = ctx, w
         B = w["B"]
         self.ker = [ctx.upload_pt(w["pt_ker"][i], PR.SCALE) if i % norm == 0 else None for i in range(B)]
         self.idx = [ctx.upload_pt(idx_np[i:i + 1], 1.0) for i in range(PR.LOGN)]
-        self.bias = ctx.upload_pt(w["bias"][None, :], PR.SCALE)
+        self.bias = ctx.upload_pt(w["bias"][None, :], out_scale)  # eval.go:241: NewPlaintext(params, 0, out_scale)
         for j, k in w["keys"].items():
             ctx.upload_swk((1 << (j + 1)) + 1, k, 0)
         self.cts = [ctx.upload_ct(c0, c1, PR.SCALE) for (c0, c1) in w["ct"]]

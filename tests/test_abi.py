@@ -65,3 +65,24 @@ def test_btp_params_struct_layout_matches_the_header(tmp_path):
     out = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     assert out[0] == ctypes.sizeof(hec.BtpParams)
     assert out[1:] == [getattr(hec.BtpParams, f).offset for f in fields]
+
+
+def test_float_quotient_threshold_is_the_reference_step_function():
+    """v = uint64(float64(y)/float64(p)) of the single-prime exact basis extension (L:ring/ring_basis_extension.go:670-713)
+    is evaluated by the fused mod-down kernel as y >= threshold: check the host-computed threshold against the float
+    arithmetic itself on the last 2^16 residues and a seeded sample of the rest, for every special prime and q0."""
+    import numpy as np
+    import __graft_entry__ as g
+    g.build()
+    from optimal_conv_b200 import hec, params as PR
+    L = hec.lib()
+    rng = np.random.default_rng(5)
+    for p in PR.P_ALL + [PR.Q_SET6[0], PR.Q_SET6[1], 0x3ffc0001]:
+        thr = int(L.hec_float_quotient_threshold(p))
+        top = np.arange(p - (1 << 16), p, dtype=np.uint64)
+        sample = rng.integers(0, p - (1 << 16), size=1 << 16, dtype=np.uint64)
+        for y in (top, sample):
+            v = (y.astype(np.float64) / np.float64(p)).astype(np.uint64)
+            assert v.max() <= 1
+            assert np.array_equal(v == 1, y >= np.uint64(thr) if thr != 2 ** 64 - 1 else np.zeros(len(y), bool)), hex(p)
+    assert int(L.hec_float_quotient_threshold(PR.P_ALL[0])) == PR.P_ALL[0] - 129  # the 129-value edge of DESIGN.md 2

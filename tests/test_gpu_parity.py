@@ -555,8 +555,8 @@ def test_conv_then_pack_matches_oracle_and_golden(orc, idx_np, cfg, flags):
     c = hec.Context(PR.LOGN, Q2, P1)
     try:
         w = common.workload(cfg)
-        G = common.GpuConv(c, w, idx_np, cfg["norm"])
         out_scale = float(1 << cfg["out_log"])
+        G = common.GpuConv(c, w, idx_np, cfg["norm"], out_scale)
         res = c.conv_then_pack(G.cts[0], G.ker, cfg["norm"], out_scale, G.idx, G.bias, flags)
         g0, g1 = res.download()
         ref = common.oracle_conv(orc, w, cfg["norm"], out_scale, idx_np)
@@ -598,6 +598,15 @@ def test_conv_scale_panic_and_missing_key(idx_np):
         assert e.value.code == hec.HEC_E_SCALE
         with pytest.raises(hec.HecError) as e:  # single real channel stays at level 1 -> conv.go:541 panic
             c.conv_then_pack(G.cts[0], G.ker, 4, float(2 ** 80), G.idx, G.bias, hec.CONV_OPLEVEL)
+        assert e.value.code == hec.HEC_E_SCALE
+        # eval.go:252-257: a bias plaintext that is not at out_scale is the reference's second panic
+        wrong = c.upload_pt(w["bias"][None, :], PR.SCALE * 2)
+        for flags in (hec.CONV_FUSED, hec.CONV_OPLEVEL):
+            with pytest.raises(hec.HecError) as e:
+                c.conv_then_pack(G.cts[0], G.ker, 1, PR.SCALE, G.idx, wrong, flags)
+            assert e.value.code == hec.HEC_E_SCALE
+        with pytest.raises(hec.HecError) as e:
+            c.plan(G.ker, 1, PR.SCALE, PR.SCALE, G.idx, wrong, 2)
         assert e.value.code == hec.HEC_E_SCALE
         c.L.hec_swk_drop(c.h, (1 << 16) + 1)
         for flags in (hec.CONV_FUSED, hec.CONV_OPLEVEL):
@@ -913,6 +922,56 @@ def test_full_level_keyswitch_alpha5_beta6():
             d0, d1 = c.keyswitch(c1, g)
             e0, e1 = o.keyswitch(c1, key)
             assert np.array_equal(d0, e0) and np.array_equal(d1, e1), level
+    finally:
+        c.close()
+
+
+def test_conv_then_pack_plan_cache_and_object_lifetimes(orc, idx_np):
+    """hec_conv_then_pack keeps its plan between calls (a per-image caller of conv.go:522); freeing or replacing what a
+    cached plan reads evicts it, and a caller's own plan keeps a freed monomial / bias / key alive until it goes."""
+    c = hec.Context(PR.LOGN, Q2, P1)
+    try:
+        w = common.workload({"B": 4, "seed": 77}, n_ct=2)
+        G = common.GpuConv(c, w, idx_np)
+        refs = [common.oracle_conv(orc, w, 1, PR.SCALE, idx_np, m=m) for m in range(2)]
+
+        def check(res, m):
+            g0, g1 = res.download()
+            assert np.array_equal(g0, refs[m].c0) and np.array_equal(g1, refs[m].c1)
+            res.free()
+        assert c.plan_cache_size() == 0
+        check(c.conv_then_pack(G.cts[0], G.ker, 1, PR.SCALE, G.idx, G.bias), 0)
+        assert c.plan_cache_size() == 1
+        n0 = c.launch_count()
+        check(c.conv_then_pack(G.cts[1], G.ker, 1, PR.SCALE, G.idx, G.bias), 1)   # same plan, other input
+        assert c.plan_cache_size() == 1 and c.launch_count() - n0 == 3 + 5 * 2    # no plaintext-rescale launch
+        r = c.conv_then_pack(G.cts[0], G.ker, 1, PR.SCALE, G.idx, None)            # other arguments: a second plan
+        r.free()
+        assert c.plan_cache_size() == 2
+        # replacing a rotation key evicts every cached plan that reads it; results stay right
+        g = (1 << 16) + 1
+        c.upload_swk(g, w["keys"][15], 0)
+        assert c.plan_cache_size() == 0
+        check(c.conv_then_pack(G.cts[0], G.ker, 1, PR.SCALE, G.idx, G.bias), 0)
+        # freeing a kernel plaintext evicts too; a fresh upload of the same values gives a fresh plan
+        G.ker[2].free()
+        assert c.plan_cache_size() == 0
+        G.ker[2] = c.upload_pt(w["pt_ker"][2], PR.SCALE)
+        check(c.conv_then_pack(G.cts[1], G.ker, 1, PR.SCALE, G.idx, G.bias), 1)
+        # a caller's plan outlives the handles it reads
+        plan = c.plan(G.ker, 1, PR.SCALE, PR.SCALE, G.idx, G.bias, 2)
+        G.bias.free()
+        for i in range(PR.LOGN):
+            G.idx[i].free()
+        c.L.hec_swk_drop(c.h, g)
+        assert c.plan_cache_size() == 0
+        junk = [c.upload_pt(idx_np[i:i + 1] ^ np.uint64(1), 1.0) for i in range(4)]  # would land in the freed blocks
+        outs = plan.run(G.cts)
+        for m in range(2):
+            check(outs[m], m)
+        plan.destroy()
+        for j in junk:
+            j.free()
     finally:
         c.close()
 

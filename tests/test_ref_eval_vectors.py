@@ -344,7 +344,7 @@ def test_gpu_conv_matches_reference_main_code_at_full_size(name):
     try:
         w = synth.conv_workload(Q, P, PR.LOGN, rec["B"], rec["seed"])
         idx = Oracle(PR.LOGN, Q, P).monomial_pts()
-        G = common.GpuConv(c, w, idx, rec["norm"])
+        G = common.GpuConv(c, w, idx, rec["norm"], rec["out_scale"])
         for flags in (hec.CONV_FUSED, hec.CONV_OPLEVEL):
             for key, bias in (("nobias", None), ("bias", G.bias)):
                 res = c.conv_then_pack(G.cts[0], G.ker, rec["norm"], rec["out_scale"], G.idx, bias, flags)

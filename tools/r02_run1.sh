@@ -1,0 +1,12 @@
+mkdir -p gpurun_out
+( ./tools/ubench_ntt4_a1; ./tools/ubench_ntt4_a2 ) > gpurun_out/r02_ubench_arith.txt 2>&1
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/r02_pytest1.txt 2>&1; echo "pytest rc $?" >> gpurun_out/r02_pytest1.txt
+for v in "" variants/libhec_arith1.so; do
+  echo "== HEC_LIB=$v" >> gpurun_out/r02_bench_ab.txt
+  if [ -n "$v" ]; then export HEC_LIB=$PWD/$v; else unset HEC_LIB; fi
+  python bench.py --steps 20 --warmup 5 --cpu-sample 0 2>&1 | tail -1 >> gpurun_out/r02_bench_ab.txt
+  for w in keyswitch eval_relu bootstrap_ctos mul_relin; do
+    python bench.py --workload $w --steps 20 --warmup 3 --cpu-sample 0 2>&1 | tail -1 >> gpurun_out/r02_bench_ab.txt
+  done
+done
+tail -5 gpurun_out/r02_pytest1.txt; cat gpurun_out/r02_ubench_arith.txt

@@ -35,7 +35,17 @@ __global__ void __launch_bounds__(256, 3) k(u64 *out, const ModC *mods, int it_n
             u32 b = (blockIdx.x * 16 + (threadIdx.x >> 4) + it) & 255;
             fwd4<false, 16>(x, M.psi + HEC_TW_ROWB + 240 * b + (threadIdx.x & 15), M.q, M.q2);
         }
-        if (OP == 0 || OP >= 3) {                                          // keep the free-mode values bounded
+        if (OP >= 6) {   // bare products on 16 independent chains: exact Shoup, approximate Shoup, lazy Montgomery
+            const ulonglong2 w = __ldg(M.psi + ((it * 7) & 255));
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                if (OP == 6) x[i] = shoup(x[i], w, M.q);
+                if (OP == 7) x[i] = shoup4(x[i], w, M.q);
+                if (OP == 8) x[i] = mred_lazy(x[i], w.x, M.q, M.qinv);
+                if (OP == 9) x[i] = mred(x[i], w.x, M.q, M.qinv);
+            }
+        }
+        if (OP == 0 || (OP >= 3 && OP < 6)) {                              // keep the free-mode values bounded
 #pragma unroll
             for (int i = 0; i < 16; i++) x[i] &= 0x00ffffffffffffffull;
         }
@@ -58,12 +68,13 @@ void run(const char *name, const ModC *dm) {
     cudaEventSynchronize(e1);
     float ms;
     cudaEventElapsedTime(&ms, e0, e1);
-    double bfly = 148.0 * 3 * 256 * ITERS * 32; // 32 butterflies per fwd4/inv4 per thread
+    double bfly = 148.0 * 3 * 256 * ITERS * (OP >= 6 ? 16 : 32); // 32 butterflies per fwd4/inv4 per thread, 16 bare products
     double cycles = ms * 1e-3 * 1.965e9;
-    printf("%-40s %7.3f ms  %6.1f clk per warp-butterfly per SMSP\n", name, ms, cycles * 148 * 4 / (bfly / 32));
+    printf("%-48s %7.3f ms  %6.1f clk per warp-butterfly per SMSP\n", name, ms, cycles * 148 * 4 / (bfly / 32));
     cudaFree(d);
 }
 int main() {
+    printf("HEC_ARITH = %d\n", HEC_ARITH);
     // a fake table is fine for timing: (w, ws) pairs
     u64 q = 0x80000000080001ull;
     ulonglong2 *tab;
@@ -72,7 +83,7 @@ int main() {
     for (int i = 0; i < 65536; i++) { u64 w = (0x1234567ull * (i + 1)) % q; h[i] = make_ulonglong2(w, (u64)((((unsigned __int128)w) << 64) / q)); }
     cudaMemcpy(tab, h, 65536 * sizeof(ulonglong2), cudaMemcpyHostToDevice);
     ModC m;
-    m.q = q; m.q2 = 2 * q; m.qinv = 1; m.rmod = 1; m.ninv_w = 1; m.ninv_s = 1; m.psi = tab; m.psi_inv = tab; m.tight = 0; m.pad = 0;
+    m.q = q; m.q2 = 2 * q; m.qinv = 0xff7fffffbff7ffffull /* any odd value: timing only */; m.rmod = 1; m.ninv_w = 1; m.ninv_s = 1; m.psi = tab; m.psi_inv = tab; m.tight = 0; m.pad = 0;
     ModC *dm;
     cudaMalloc(&dm, sizeof(ModC));
     cudaMemcpy(dm, &m, sizeof(ModC), cudaMemcpyHostToDevice);
@@ -82,5 +93,9 @@ int main() {
     run<3>("fwd4<free>, uniform twiddles", dm);
     run<4>("fwd4<free>, row B', NttPsi order (16 lines/load)", dm);
     run<5>("fwd4<free>, row B', thread-order table", dm);
+    run<6>("shoup (exact quotient), per product", dm);
+    run<7>("shoup4 (approximate quotient), per product", dm);
+    run<8>("mred_lazy (Montgomery), per product", dm);
+    run<9>("mred (Montgomery, canonical), per product", dm);
     return 0;
 }

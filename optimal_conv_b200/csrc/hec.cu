@@ -153,32 +153,41 @@ static void launch_k(hec_ctx *c, void (*kern)(KArgs...), dim3 grid, dim3 block, 
     cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
+static int stage_cached(hec_ctx *c, std::vector<char> &h, char **dev);
 // forward / inverse NTT of a list of limbs (in -> out; in == out allowed)
 int hec_launch_ntt(hec_ctx *c, std::vector<LimbJob> &jobs, bool inverse) {
     // limbs of the same modulus next to each other: their CTAs run back to back and share the twiddle table in L2
     // (the row transforms read as many table bytes as data bytes).  The jobs are independent, so the order is free.
     static const int sort_by_mod = getenv("HEC_NTT_SORT") ? atoi(getenv("HEC_NTT_SORT")) : 1; // measured: -1.3 % key switch
     if (sort_by_mod) std::stable_sort(jobs.begin(), jobs.end(), [](const LimbJob &a, const LimbJob &b) { return a.mod < b.mod; });
-    for (size_t off = 0; off < jobs.size(); off += HEC_MAXJOBS) {
-        int n = (int)std::min<size_t>(HEC_MAXJOBS, jobs.size() - off);
-        NttJobs A, B;
-        for (int i = 0; i < n; i++) {
-            const LimbJob &j = jobs[off + i];
-            u64 *mid = (!inverse && j.mid) ? j.mid : j.out;
-            A.j[i] = j;
-            B.j[i] = j;
-            A.j[i].out = mid;              // first pass: in -> mid (prologue, if any)
-            A.j[i].flags = inverse ? 0 : (j.flags & HEC_LJ_PRO);
-            B.j[i].in = mid;               // second pass: mid -> out (epilogue, if any)
-            B.j[i].flags = inverse ? 0 : (j.flags & HEC_LJ_EPI);
-        }
-        dim3 grid(HEC_TILES_PER_LIMB, n);
+    // both passes' job tables go to the device in one content-addressed block (stage_cached): an operation repeated on
+    // the same buffers launches without a copy, and one launch per pass takes all limbs (no per-launch job limit)
+    const size_t n = jobs.size();
+    if (n == 0) return HEC_OK;
+    std::vector<char> h(2 * n * sizeof(LimbJob));
+    LimbJob *A = reinterpret_cast<LimbJob *>(h.data()), *B = A + n;
+    for (size_t i = 0; i < n; i++) {
+        const LimbJob &j = jobs[i];
+        u64 *mid = (!inverse && j.mid) ? j.mid : j.out;
+        A[i] = j;
+        B[i] = j;
+        A[i].out = mid;              // first pass: in -> mid (prologue, if any)
+        A[i].flags = inverse ? 0 : (j.flags & HEC_LJ_PRO);
+        B[i].in = mid;               // second pass: mid -> out (epilogue, if any)
+        B[i].flags = inverse ? 0 : (j.flags & HEC_LJ_EPI);
+    }
+    char *dbuf = nullptr;
+    int rc = stage_cached(c, h, &dbuf);
+    if (rc) return rc;
+    const LimbJob *dA = reinterpret_cast<const LimbJob *>(dbuf), *dB = dA + n;
+    for (size_t off = 0; off < n; off += 65535) { // grid.y limit
+        dim3 grid(HEC_TILES_PER_LIMB, (unsigned)std::min<size_t>(65535, n - off));
         if (!inverse) {
-            launch_k(c, k_col_fwd, grid, dim3(HEC_THREADS), A, c->dmods);
-            launch_k(c, k_row_fwd, grid, dim3(HEC_THREADS), B, c->dmods);
+            launch_k(c, k_col_fwd, grid, dim3(HEC_THREADS), dA + off, c->dmods);
+            launch_k(c, k_row_fwd, grid, dim3(HEC_THREADS), dB + off, c->dmods);
         } else {
-            launch_k(c, k_row_inv, grid, dim3(HEC_THREADS), A, c->dmods);
-            launch_k(c, k_col_inv, grid, dim3(HEC_THREADS), B, c->dmods);
+            launch_k(c, k_row_inv, grid, dim3(HEC_THREADS), dA + off, c->dmods);
+            launch_k(c, k_col_inv, grid, dim3(HEC_THREADS), dB + off, c->dmods);
         }
         c->launches += 2;
     }
@@ -364,7 +373,8 @@ extern "C" int hec_ctx_create(hec_ctx **out, int logN, const uint64_t *Q, int nQ
         mc[i].wn_w = mulmod(c->hm[i].psi_inv[HEC_TW_COLA].x, c->hm[i].ninv_w, c->hm[i].q);
         mc[i].wn_s = (u64)(((u128)mc[i].wn_w << 64) / c->hm[i].q);
         mc[i].psi = psi; mc[i].psi_inv = psi_inv;
-        mc[i].tight = c->hm[i].q >= (1ull << 57) ? 1 : 0; mc[i].pad = 0;
+        mc[i].tight = c->hm[i].q >= (1ull << 57) ? 1 : 0;
+        mc[i].small = (c->hm[i].q < (1ull << 31) && !getenv("HEC_NO_SMALL")) ? 1 : 0; // HEC_NO_SMALL: A/B switch
     }
     if (cudaMemcpy(c->dmods, mc.data(), nm * sizeof(ModC), cudaMemcpyHostToDevice) != cudaSuccess) return bail(HEC_E_CUDA);
     // RescaleParams (L:ring/ring.go:63-117)

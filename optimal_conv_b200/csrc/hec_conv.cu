@@ -282,7 +282,7 @@ static int plan_launch_all(hec_plan *p, const std::function<void()> &after = [] 
     after();
     k_convA2<<<gA, HEC_THREADS, 0, s>>>(p->pa, c->dmods);
     after();
-    k_convA3<<<gA, HEC_THREADS, 0, s>>>(p->pa, c->dmods);
+    k_convA3<<<gA, HEC_THREADS, HEC_A3_SMEM, s>>>(p->pa, c->dmods);
     after();
     for (auto &b : p->pb) {
         int nb = b.n / 2;
@@ -295,7 +295,7 @@ static int plan_launch_all(hec_plan *p, const std::function<void()> &after = [] 
         after();
         k_convB4<<<g2, HEC_THREADS, 0, s>>>(b, c->dmods);
         after();
-        k_convB5<<<g2, HEC_THREADS, 0, s>>>(b, c->dmods);
+        k_convB5<<<g2, HEC_THREADS, HEC_B5_SMEM, s>>>(b, c->dmods);
         after();
     }
     if (p->levels == 0 && p->bias) { // single channel: bias not folded into a B5 epilogue
@@ -456,8 +456,10 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
         p->pb.push_back(b);
     }
     p->launches_per_run = 3 + 5 * levels + ((levels == 0 && pt_bias) ? M : 0);
-    if (cudaFuncSetAttribute(k_convB3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEC_B3_SMEM) != cudaSuccess)
-        return bail(HEC_E_CUDA, "cudaFuncSetAttribute(k_convB3)");
+    if (cudaFuncSetAttribute(k_convB3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEC_B3_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(k_convB5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEC_B5_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(k_convA3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEC_A3_SMEM) != cudaSuccess)
+        return bail(HEC_E_CUDA, "cudaFuncSetAttribute(k_convB3/B5/A3)");
     // ---- capture the kernel sequence in a CUDA graph ----
     cudaGraph_t graph = nullptr;
     if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return bail(HEC_E_CUDA, "begin capture");

@@ -45,7 +45,7 @@ struct ModC {
     const ulonglong2 *psi;     // Shoup pairs (w, floor(w * 2^64 / q)) of NttPsi, in consumption order (see fwd4)
     const ulonglong2 *psi_inv; // same for NttPsiInv
     int tight;        // q >= 2^57: the forward transform needs range corrections (see fwd4)
-    int pad;
+    int small;        // q < 2^31: the transforms run on 32-bit words (fwd4_32 / inv4_32)
 };
 
 // ---- scalar primitives -----------------------------------------------------------------
@@ -174,17 +174,51 @@ __device__ __forceinline__ void fwd4(u64 (&x)[16], const ulonglong2 *__restrict_
         }
     }
 }
-// Four inverse stages (d = 1,2,4,8), same slots from the psi^-1 table.  Values stay in [0,4q).
-template <int STRIDE>
-__device__ __forceinline__ void inv4(u64 (&x)[16], const ulonglong2 *__restrict__ t, u64 q, u64 q2) {
+// Four inverse stages (d = 1,2,4,8), same slots from the psi^-1 table.  In: values < 4q, out: values < 4q.
+// DEFER (q < 2^57): the sums X' = X + Y are not pulled back after every stage.  A slot that was last a Y (a product,
+// < 4q) s stages ago holds a value < 4q * 2^s -- a compile-time function of slot and stage (gs_bound) -- so the
+// difference is offset by that multiple of q and the 16 slots are brought back below 4q once, after the fourth stage
+// (15 conditional subtractions instead of 32; none at all where the final N^-1 products follow, inv4_final).
+#ifndef HEC_GS_DEFER
+#define HEC_GS_DEFER 1
+#endif
+__host__ __device__ constexpr int gs_bound(int slot, int stages_done) { // in units of q
+    int low = slot & ((1 << stages_done) - 1), b = 4 << stages_done;
+    for (int h = 0; h < stages_done; h++)
+        if (low >> h & 1) b = 4 << (stages_done - 1 - h);
+    return b;
+}
+template <int NSTAGES, bool DEFER, int STRIDE>
+__device__ __forceinline__ void gs_stages(u64 (&x)[16], const ulonglong2 *__restrict__ t, u64 q) {
 #pragma unroll
-    for (int lg = 3; lg >= 0; lg--) {
-        const int d = 8 >> lg, ng = 1 << lg;
+    for (int lg = 3; lg > 3 - NSTAGES; lg--) {
+        const int d = 8 >> lg, ng = 1 << lg, done = 3 - lg;
 #pragma unroll
         for (int gi = 0; gi < ng; gi++) {
             ulonglong2 w = __ldg(t + (ng - 1 + gi) * STRIDE);
 #pragma unroll
-            for (int k = 0; k < d; k++) gs_bfly(x[gi * 2 * d + k], x[gi * 2 * d + k + d], w, q, q2);
+            for (int k = 0; k < d; k++) {
+                const int i = gi * 2 * d + k, j = i + d;
+                const u64 u = x[i], v = x[j];
+                if (DEFER) {
+                    x[i] = u + v;
+                    x[j] = shoup4(u - v + (u64)gs_bound(j, done) * q, w, q);
+                } else {
+                    x[i] = cred(u + v, 4 * q);
+                    x[j] = shoup4(u - v + 4 * q, w, q);
+                }
+            }
+        }
+    }
+}
+template <bool DEFER, int STRIDE>
+__device__ __forceinline__ void inv4(u64 (&x)[16], const ulonglong2 *__restrict__ t, u64 q, u64 q2) {
+    gs_stages<4, DEFER, STRIDE>(x, t, q);
+    if (DEFER) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+#pragma unroll
+            for (int b = gs_bound(i, 4) / 2; b >= 4; b /= 2) x[i] = cred(x[i], (u64)b * q);
         }
     }
 }
@@ -195,24 +229,16 @@ __device__ __forceinline__ u64 inv_final(u64 x, const ModC &M) {
 // The last four inverse stages of a transform with that final pass folded into the last stage (distance N/2, one
 // twiddle w): X' = (X + Y) * N^-1, Y' = (X - Y) * (w * N^-1), both canonical -- two exact products per butterfly
 // instead of an approximate one, a range correction and two exact ones.  t: the psi^-1 table in column layout A.
+template <bool DEFER>
 __device__ __forceinline__ void inv4_final(u64 (&x)[16], const ulonglong2 *__restrict__ t, const ModC &M) {
-    const u64 q = M.q, q2 = M.q2;
-#pragma unroll
-    for (int lg = 3; lg >= 1; lg--) {
-        const int d = 8 >> lg, ng = 1 << lg;
-#pragma unroll
-        for (int gi = 0; gi < ng; gi++) {
-            ulonglong2 w = __ldg(t + (ng - 1 + gi));
-#pragma unroll
-            for (int k = 0; k < d; k++) gs_bfly(x[gi * 2 * d + k], x[gi * 2 * d + k + d], w, q, q2);
-        }
-    }
+    const u64 q = M.q;
+    gs_stages<3, DEFER, 1>(x, t, q);
     const ulonglong2 n1 = make_ulonglong2(M.ninv_w, M.ninv_s), n2 = make_ulonglong2(M.wn_w, M.wn_s);
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         const u64 u = x[k], v = x[k + 8];
         x[k] = cred(shoup(u + v, n1, q), q);
-        x[k + 8] = cred(shoup(u - v + 2 * q2, n2, q), q);
+        x[k + 8] = cred(shoup(u - v + (u64)(DEFER ? gs_bound(k + 8, 3) : 4) * q, n2, q), q);
     }
 }
 // x < 16q -> canonical
@@ -291,9 +317,15 @@ __device__ __forceinline__ void row_fwd8(u64 (&x)[16], u64 *sm, const RowGeom &G
 }
 // in: layout B' (values < 4q); out: layout A' (< 4q)
 __device__ __forceinline__ void row_inv8(u64 (&x)[16], u64 *sm, const RowGeom &G, const ModC &M) {
-    inv4<16>(x, M.psi_inv + G.twB(), M.q, M.q2);
-    row_BtoA(x, sm, G);
-    inv4<1>(x, M.psi_inv + G.twA(), M.q, M.q2);
+    if (HEC_GS_DEFER && !M.tight) {
+        inv4<true, 16>(x, M.psi_inv + G.twB(), M.q, M.q2);
+        row_BtoA(x, sm, G);
+        inv4<true, 1>(x, M.psi_inv + G.twA(), M.q, M.q2);
+    } else {
+        inv4<false, 16>(x, M.psi_inv + G.twB(), M.q, M.q2);
+        row_BtoA(x, sm, G);
+        inv4<false, 1>(x, M.psi_inv + G.twA(), M.q, M.q2);
+    }
 }
 
 // ---- column-kernel tile geometry ---------------------------------------------------------
@@ -341,16 +373,137 @@ __device__ __forceinline__ void col_fwd8(u64 (&x)[16], u64 *sm, const ColGeom &G
 }
 // in: layout B (values < 4q), out: layout A (< 4q)
 __device__ __forceinline__ void col_inv8(u64 (&x)[16], u64 *sm, const ColGeom &G, const ModC &M) {
-    inv4<1>(x, M.psi_inv + HEC_TW_COLB + 15 * G.pg, M.q, M.q2);
-    col_BtoA(x, sm, G);
-    inv4<1>(x, M.psi_inv + HEC_TW_COLA, M.q, M.q2);
+    if (HEC_GS_DEFER && !M.tight) {
+        inv4<true, 1>(x, M.psi_inv + HEC_TW_COLB + 15 * G.pg, M.q, M.q2);
+        col_BtoA(x, sm, G);
+        inv4<true, 1>(x, M.psi_inv + HEC_TW_COLA, M.q, M.q2);
+    } else {
+        inv4<false, 1>(x, M.psi_inv + HEC_TW_COLB + 15 * G.pg, M.q, M.q2);
+        col_BtoA(x, sm, G);
+        inv4<false, 1>(x, M.psi_inv + HEC_TW_COLA, M.q, M.q2);
+    }
 }
 // the same, ending the inverse transform: out = canonical coefficients (N^-1 included)
 __device__ __forceinline__ void col_inv8_final(u64 (&x)[16], u64 *sm, const ColGeom &G, const ModC &M) {
-    inv4<1>(x, M.psi_inv + HEC_TW_COLB + 15 * G.pg, M.q, M.q2);
-    col_BtoA(x, sm, G);
-    inv4_final(x, M.psi_inv + HEC_TW_COLA, M);
+    if (HEC_GS_DEFER && !M.tight) {
+        inv4<true, 1>(x, M.psi_inv + HEC_TW_COLB + 15 * G.pg, M.q, M.q2);
+        col_BtoA(x, sm, G);
+        inv4_final<true>(x, M.psi_inv + HEC_TW_COLA, M);
+    } else {
+        inv4<false, 1>(x, M.psi_inv + HEC_TW_COLB + 15 * G.pg, M.q, M.q2);
+        col_BtoA(x, sm, G);
+        inv4_final<false>(x, M.psi_inv + HEC_TW_COLA, M);
+    }
 }
+
+// ---- moduli below 2^31 (the eleven ReLU primes of the reference's sets, 30-31 bits) --------------------------------
+// The same transforms on 32-bit words: a twiddle product is one high product and two 32-bit IMADs
+// (qe = hi32(y * ws32), r = y*w - qe*q in [0,2q) for any y < 2^32, ws32 = floor(w * 2^32 / q) = the high word of the
+// 64-bit companion already in the tables) -- 8 multiplier-pipe cycles against 28 for the 64-bit butterfly -- and a
+// thread's 16 coefficients take 16 registers.  Values stay in [0,2q) (2q < 2^32, but 4q is not: the sum is decided by
+// comparing one operand with 2q minus the other, never formed beyond 2q).
+// Limbs are still 64-bit words in memory (the reference's layout); only the arithmetic is narrow.
+__device__ __forceinline__ u32 shoup32(u32 y, ulonglong2 w, u32 q) {
+    const u32 qe = __umulhi(y, (u32)(w.y >> 32));
+    return y * (u32)w.x - qe * q;
+}
+__device__ __forceinline__ u32 add2q(u32 a, u32 b, u32 q2) { const u32 c = q2 - b; return a >= c ? a - c : a + b; } // [0,2q)^2 -> [0,2q)
+__device__ __forceinline__ u32 sub2q(u32 a, u32 b, u32 q2) { const u32 d = a - b; return a >= b ? d : d + q2; }
+template <int STRIDE>
+__device__ __forceinline__ void fwd4_32(u32 (&x)[16], const ulonglong2 *__restrict__ t, u32 q, u32 q2) {
+#pragma unroll
+    for (int lg = 0; lg < 4; lg++) {
+        const int d = 8 >> lg, ng = 1 << lg;
+#pragma unroll
+        for (int gi = 0; gi < ng; gi++) {
+            const ulonglong2 w = __ldg(t + (ng - 1 + gi) * STRIDE);
+#pragma unroll
+            for (int k = 0; k < d; k++) {
+                const int i = gi * 2 * d + k, j = i + d;
+                const u32 X = x[i], T = shoup32(x[j], w, q);
+                x[i] = add2q(X, T, q2);
+                x[j] = sub2q(X, T, q2);
+            }
+        }
+    }
+}
+template <int STRIDE>
+__device__ __forceinline__ void inv4_32(u32 (&x)[16], const ulonglong2 *__restrict__ t, u32 q, u32 q2) {
+#pragma unroll
+    for (int lg = 3; lg >= 0; lg--) {
+        const int d = 8 >> lg, ng = 1 << lg;
+#pragma unroll
+        for (int gi = 0; gi < ng; gi++) {
+            const ulonglong2 w = __ldg(t + (ng - 1 + gi) * STRIDE);
+#pragma unroll
+            for (int k = 0; k < d; k++) {
+                const int i = gi * 2 * d + k, j = i + d;
+                const u32 u = x[i], v = x[j];
+                x[i] = add2q(u, v, q2);
+                x[j] = shoup32(sub2q(u, v, q2), w, q);
+            }
+        }
+    }
+}
+// exchanges on a 32-bit view of the same shared-memory buffers.  Row kernels: the 17-word skew of the 64-bit layout
+// is conflict-free for 32-bit words as it stands (the two half-warps of a warp sit 272 = 16 mod 32 words apart).
+__device__ __forceinline__ void row_AtoB32(u32 (&x)[16], u32 *sm, const RowGeom &G) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) sm[G.sbase + G.p + 17 * k] = x[k];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 16; k++) x[k] = sm[G.sbase + 17 * G.p + k];
+    __syncwarp();
+}
+__device__ __forceinline__ void row_BtoA32(u32 (&x)[16], u32 *sm, const RowGeom &G) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) sm[G.sbase + 17 * G.p + k] = x[k];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 16; k++) x[k] = sm[G.sbase + G.p + 17 * k];
+    __syncwarp();
+}
+// Column kernels: word index (row*16 + cc) with bit 4 flipped by bit 8, which separates the two half-warps of a warp
+// (rows 16*pg + k of an even and an odd pg) that would otherwise meet in the same 16 banks.
+__device__ __forceinline__ u32 col_sw32(u32 idx) { return idx ^ ((idx >> 4) & 16u); }
+__device__ __forceinline__ void col_AtoB32(u32 (&x)[16], u32 *sm, const ColGeom &G) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) sm[col_sw32(G.sA(k))] = x[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; k++) x[k] = sm[col_sw32(G.sB(k))];
+    __syncthreads();
+}
+__device__ __forceinline__ void col_BtoA32(u32 (&x)[16], u32 *sm, const ColGeom &G) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) sm[col_sw32(G.sB(k))] = x[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; k++) x[k] = sm[col_sw32(G.sA(k))];
+    __syncthreads();
+}
+// in: [0,2q), out: [0,2q)
+__device__ __forceinline__ void row_fwd8_32(u32 (&x)[16], u32 *sm, const RowGeom &G, const ModC &M) {
+    fwd4_32<1>(x, M.psi + G.twA(), (u32)M.q, (u32)M.q2);
+    row_AtoB32(x, sm, G);
+    fwd4_32<16>(x, M.psi + G.twB(), (u32)M.q, (u32)M.q2);
+}
+__device__ __forceinline__ void row_inv8_32(u32 (&x)[16], u32 *sm, const RowGeom &G, const ModC &M) {
+    inv4_32<16>(x, M.psi_inv + G.twB(), (u32)M.q, (u32)M.q2);
+    row_BtoA32(x, sm, G);
+    inv4_32<1>(x, M.psi_inv + G.twA(), (u32)M.q, (u32)M.q2);
+}
+__device__ __forceinline__ void col_fwd8_32(u32 (&x)[16], u32 *sm, const ColGeom &G, const ModC &M) {
+    fwd4_32<1>(x, M.psi + HEC_TW_COLA, (u32)M.q, (u32)M.q2);
+    col_AtoB32(x, sm, G);
+    fwd4_32<1>(x, M.psi + HEC_TW_COLB + 15 * G.pg, (u32)M.q, (u32)M.q2);
+}
+__device__ __forceinline__ void col_inv8_32(u32 (&x)[16], u32 *sm, const ColGeom &G, const ModC &M) {
+    inv4_32<1>(x, M.psi_inv + HEC_TW_COLB + 15 * G.pg, (u32)M.q, (u32)M.q2);
+    col_BtoA32(x, sm, G);
+    inv4_32<1>(x, M.psi_inv + HEC_TW_COLA, (u32)M.q, (u32)M.q2);
+}
+__device__ __forceinline__ u32 cred32(u32 a, u32 q) { return a >= q ? a - q : a; }
 
 // PermuteNTTIndex computed on the fly (L:ring/ring_automorphism.go:31-44):
 // index_g[i] = brev(((g * (2*brev(i)+1)) mod 2N - 1) / 2)

@@ -12,7 +12,6 @@
 // =========================================================================================
 // (1) generic kernels
 // =========================================================================================
-#define HEC_MAXJOBS 64
 // one limb through a transform.  Forward transforms can absorb the point-wise step in front of them and the one behind:
 //   flags & 1: the input is a residue of ANOTHER modulus (< 2^64): x = (in mod q) + pro_s0     (EW_REDUCE_ADD)
 //   flags & 2: out = (x + 2q - ep_b) * ep_s0 * R^-1 instead of x                              (EW_SUBMUL)
@@ -20,11 +19,11 @@
 struct LimbJob { const u64 *in; u64 *out; int mod; int flags; u64 *mid; const u64 *ep_b; u64 ep_s0; u64 pro_s0; };
 #define HEC_LJ_PRO 1
 #define HEC_LJ_EPI 2
-struct NttJobs { LimbJob j[HEC_MAXJOBS]; };
 // programmatic dependent launch: let the next kernel of the stream be scheduled while this grid drains, and do not touch
 // memory before the previous grid has completed (both are no-ops for a kernel launched without the attribute)
 #define HEC_PDL_SYNC() asm volatile("griddepcontrol.launch_dependents;\n\tgriddepcontrol.wait;" ::: "memory")
-// the two halves apart: everything between them may only read kernel parameters and the static modulus table
+// the two halves apart: everything between them may only read kernel parameters, the static modulus table and job tables
+// that were staged before the previous kernel was launched
 #define HEC_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
 #define HEC_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
 #ifndef HEC_GEN_MINB
@@ -33,15 +32,30 @@ struct NttJobs { LimbJob j[HEC_MAXJOBS]; };
 #endif
 
 // forward NTT = k_col_fwd then k_row_fwd;  inverse = k_row_inv then k_col_inv
-// (ring.NTT / ring.InvNTT, L:ring/ring_ntt.go:74-626).  grid = (16, njobs).
-__global__ void __launch_bounds__(HEC_THREADS, HEC_GEN_MINB) k_col_fwd(NttJobs J, const ModC *__restrict__ mods) {
+// (ring.NTT / ring.InvNTT, L:ring/ring_ntt.go:74-626).  grid = (16, njobs); the job table lives in device memory
+// (content-addressed, hec.cu stage_cached), so one launch takes every limb of a batched operation.
+__global__ void __launch_bounds__(HEC_THREADS, HEC_GEN_MINB) k_col_fwd(const LimbJob *__restrict__ jobs, const ModC *__restrict__ mods) {
     HEC_PDL_TRIGGER();
     __shared__ u64 sm[HEC_TILE];
-    const LimbJob job = J.j[blockIdx.y];
+    HEC_PDL_WAIT();
+    const LimbJob job = jobs[blockIdx.y];
     const ModC M = mods[job.mod];
     ColGeom G(blockIdx.x);
+    if (M.small) {
+        u32 y[16];
+        if (job.flags & HEC_LJ_PRO) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) y[k] = (u32)addmod(canon(job.in[G.gA(k)], M), job.pro_s0, M.q);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; k++) y[k] = (u32)job.in[G.gA(k)];
+        }
+        col_fwd8_32(y, reinterpret_cast<u32 *>(sm), G, M);
+#pragma unroll
+        for (int k = 0; k < 16; k++) job.out[G.gB(k)] = y[k];
+        return;
+    }
     u64 x[16];
-    HEC_PDL_WAIT();
 #pragma unroll
     for (int k = 0; k < 16; k++) x[k] = job.in[G.gA(k)];
     if (job.flags & HEC_LJ_PRO) {
@@ -52,46 +66,76 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_GEN_MINB) k_col_fwd(NttJobs J
 #pragma unroll
     for (int k = 0; k < 16; k++) job.out[G.gB(k)] = x[k];
 }
-__global__ void __launch_bounds__(HEC_THREADS, HEC_GEN_MINB) k_row_fwd(NttJobs J, const ModC *__restrict__ mods) {
+__global__ void __launch_bounds__(HEC_THREADS, HEC_GEN_MINB) k_row_fwd(const LimbJob *__restrict__ jobs, const ModC *__restrict__ mods) {
     HEC_PDL_TRIGGER();
     __shared__ u64 sm[16 * HEC_ROW_PITCH];
-    const LimbJob job = J.j[blockIdx.y];
+    HEC_PDL_WAIT();
+    const LimbJob job = jobs[blockIdx.y];
     const ModC M = mods[job.mod];
     RowGeom G(blockIdx.x);
     u64 x[16];
-    HEC_PDL_WAIT();
-    row_loadA(x, job.in, G);
-    row_fwd8(x, sm, G, M);
-    row_BtoA(x, sm, G);
+    if (M.small) {
+        u32 y[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) x[k] = canon(x[k], M);
+        for (int k = 0; k < 16; k++) y[k] = (u32)job.in[G.gbase + 16 * k];
+        row_fwd8_32(y, reinterpret_cast<u32 *>(sm), G, M);
+        row_BtoA32(y, reinterpret_cast<u32 *>(sm), G);
+#pragma unroll
+        for (int k = 0; k < 16; k++) x[k] = cred32(y[k], (u32)M.q);
+    } else {
+        row_loadA(x, job.in, G);
+        row_fwd8(x, sm, G, M);
+        row_BtoA(x, sm, G);
+#pragma unroll
+        for (int k = 0; k < 16; k++) x[k] = canon(x[k], M);
+    }
     if (job.flags & HEC_LJ_EPI) {
 #pragma unroll
         for (int k = 0; k < 16; k++) x[k] = mred(x[k] + M.q2 - job.ep_b[G.gbase + 16 * k], job.ep_s0, M.q, M.qinv);
     }
     row_storeA(x, job.out, G);
 }
-__global__ void __launch_bounds__(HEC_THREADS, HEC_GEN_MINB) k_row_inv(NttJobs J, const ModC *__restrict__ mods) {
+__global__ void __launch_bounds__(HEC_THREADS, HEC_GEN_MINB) k_row_inv(const LimbJob *__restrict__ jobs, const ModC *__restrict__ mods) {
     HEC_PDL_TRIGGER();
     __shared__ u64 sm[16 * HEC_ROW_PITCH];
-    const LimbJob job = J.j[blockIdx.y];
+    HEC_PDL_WAIT();
+    const LimbJob job = jobs[blockIdx.y];
     const ModC M = mods[job.mod];
     RowGeom G(blockIdx.x);
+    if (M.small) {
+        u32 y[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) y[k] = (u32)job.in[G.gbase + 16 * k];
+        row_AtoB32(y, reinterpret_cast<u32 *>(sm), G);
+        row_inv8_32(y, reinterpret_cast<u32 *>(sm), G, M);
+#pragma unroll
+        for (int k = 0; k < 16; k++) job.out[G.gbase + 16 * k] = y[k];
+        return;
+    }
     u64 x[16];
-    HEC_PDL_WAIT();
     row_loadA(x, job.in, G);
     row_AtoB(x, sm, G);
     row_inv8(x, sm, G, M);
     row_storeA(x, job.out, G);
 }
-__global__ void __launch_bounds__(HEC_THREADS, HEC_GEN_MINB) k_col_inv(NttJobs J, const ModC *__restrict__ mods) {
+__global__ void __launch_bounds__(HEC_THREADS, HEC_GEN_MINB) k_col_inv(const LimbJob *__restrict__ jobs, const ModC *__restrict__ mods) {
     HEC_PDL_TRIGGER();
     __shared__ u64 sm[HEC_TILE];
-    const LimbJob job = J.j[blockIdx.y];
+    HEC_PDL_WAIT();
+    const LimbJob job = jobs[blockIdx.y];
     const ModC M = mods[job.mod];
     ColGeom G(blockIdx.x);
+    if (M.small) {
+        u32 y[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) y[k] = (u32)job.in[G.gB(k)];
+        col_inv8_32(y, reinterpret_cast<u32 *>(sm), G, M);
+        const ulonglong2 ninv = make_ulonglong2(M.ninv_w, M.ninv_s);
+#pragma unroll
+        for (int k = 0; k < 16; k++) job.out[G.gA(k)] = cred32(shoup32(y[k], ninv, (u32)M.q), (u32)M.q);
+        return;
+    }
     u64 x[16];
-    HEC_PDL_WAIT();
 #pragma unroll
     for (int k = 0; k < 16; k++) x[k] = job.in[G.gB(k)];
     col_inv8_final(x, sm, G, M);
@@ -371,13 +415,23 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convA2(ConvA P, const
     for (int k = 0; k < 16; k++) out[G.gB(k)] = x[k];
 }
 // A3: finish NTT_q0, combine with limb q0 of ct*(pt*k0):  out = (p0 - u) * q1^-1
+// The products ct*pt are formed FIRST and parked in shared memory (each thread's own 16 words): their operand loads
+// then sit at the start of the CTA, where the other CTAs of the SM cover them, instead of behind the transform
+// (profiles/r02a: long-scoreboard stalls 5.9 per issue with the loads after the transform).
+#define HEC_A3_SMEM (2 * 16 * HEC_ROW_PITCH * sizeof(u64)) // dynamic: above the 48 KB static limit
 __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convA3(ConvA P, const ModC *__restrict__ mods) {
-    __shared__ u64 sm[16 * HEC_ROW_PITCH];
+    extern __shared__ __align__(16) u64 dsm[];
+    u64 *sm = dsm, *st = dsm + 16 * HEC_ROW_PITCH;
     const AJob J(HEC_BJOB, P.na);
     const ModC M = mods[P.mq0];
     RowGeom G(HEC_BTILE);
     const u64 *ct = P.ctin[J.m] + (size_t)(J.c * 2) * HEC_N;
     const u64 *pt = P.ptk[J.a * P.norm];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        u32 i = G.gbase + 16 * k, e = G.p + 16 * k;
+        st[G.sbase + e + (e >> 4)] = mred_lazy(ct[i], __ldg(pt + i), M.q, M.qinv); // (0,2q)
+    }
     u64 x[16];
     row_loadA(x, P.w2 + (size_t)HEC_BJOB * HEC_N, G);
     row_fwd8(x, sm, G, M);
@@ -385,9 +439,8 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convA3(ConvA P, const
     u64 *out = P.xout + (size_t)HEC_BJOB * HEC_N; // ((m*na + a)*2 + c) == job
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        u32 i = G.gbase + 16 * k;
-        u64 v = mred_lazy(ct[i], __ldg(pt + i), M.q, M.qinv);
-        out[i] = cred(shoup(x[k] + M.q2 - v, P.resc0, M.q), M.q);
+        u32 i = G.gbase + 16 * k, e = G.p + 16 * k;
+        out[i] = cred(shoup(x[k] + M.q2 - st[G.sbase + e + (e >> 4)], P.resc0, M.q), M.q);
     }
 }
 
@@ -539,42 +592,62 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convB4(ConvB P, const
 // B5: finish NTT_q0, mod-down combine with acc_Q = z*key[c] (Q limb), + tmp2.c0 (c = 0),
 //     apply sigma_g inside the 256-word block, add tmp1 (+ bias)           grid.y = M*nb*2
 //     Sums are lazy (every term a known multiple of q away from canonical) and reduced once at the end.
-__global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convB5(ConvB P, const ModC *__restrict__ mods) {
-    __shared__ u64 sm[16 * HEC_ROW_PITCH];
+#define HEC_B5_SMEM (2 * 16 * HEC_ROW_PITCH * sizeof(u64)) // dynamic: above the 48 KB static limit
+// the point-wise half of B5 for one polynomial.  A template on the polynomial rather than a test inside the loop: with
+// a branch in every iteration the compiler cannot move the loads of iteration k+1 above the arithmetic of iteration k,
+// and the kernel waits for every operand in turn (profiles/r02a: 71 % of its stall samples sat on these loads).
+template <bool C0>
+__device__ __forceinline__ void b5_pointwise(const u64 (&x)[16], u64 *sm, u64 *st, const ConvB &P, const BJob &J, const ModC &M,
+                                             const RowGeom &G, const u64 *__restrict__ zb, const u64 *__restrict__ kq) {
+    const u64 *__restrict__ a = C0 ? J.a : J.a + HEC_N;
+    const u64 *__restrict__ b = J.b;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const u32 i = G.gbase + 16 * k, e = G.p + 16 * k;
+        const u64 z = zb[i];                                                // tmp2.c1 in (0,3q)
+        const u64 accq = mred_lazy(z, __ldg(kq + i), M.q, M.qinv);          // MulCoeffsMontgomeryConstant (+ Reduce), (0,2q)
+        u64 d = shoup(x[k] + M.q2 - accq, P.negpinv, M.q);                  // ModDownSplitNTTPQ combine, [0,2q)
+        u64 t1;
+        if (C0) {
+            const u64 a0 = a[i];
+            const u64 m0 = shoup(b[i], __ldg(P.mono + i), M.q);             // [0,2q)
+            d += a0 + M.q2 - m0;                                            // + tmp2.c0  (AddLvl), < 5q
+            t1 = a0 + m0;                                                   // tmp1.c0, < 3q
+            if (P.bias != nullptr) t1 += __ldg(P.bias + i);                 // < 4q
+        } else {
+            t1 = 2 * a[i] + 3 * M.q - z;                                    // tmp1.c1 = a1 + b1*X^step = 2 a1 - tmp2.c1, in (0,5q)
+        }
+        sm[G.sbase + e + (e >> 4)] = d;
+        st[G.sbase + e + (e >> 4)] = t1;
+    }
+}
+#ifndef HEC_B5_MINB
+#define HEC_B5_MINB 2 // 128 registers: the point-wise half keeps more operand loads in flight (measured: B5 1.51 -> 1.37 ms
+                      // per 64 convolutions against 3 CTAs / 80 registers; the transform half loses less than that gains)
+#endif
+__global__ void __launch_bounds__(HEC_THREADS, HEC_B5_MINB) k_convB5(ConvB P, const ModC *__restrict__ mods) {
+    extern __shared__ __align__(16) u64 dsm[];
+    u64 *sm = dsm;                         // exchange buffer of the transform, then the mod-down results d
+    u64 *st = dsm + 16 * HEC_ROW_PITCH;    // tmp1 of the thread's own coefficients: parked here rather than in 32 registers, so
+                                           // that the loads of the epilogue's operand streams can run ahead of their use
     const BJob J(HEC_BJOB, true, P);
     const ModC M = mods[P.mq0];
     RowGeom G(HEC_BTILE);
-    u64 x[16], t1[16];
+    u64 x[16];
     row_loadA(x, P.w4 + (size_t)HEC_BJOB * HEC_N, G);
     row_fwd8(x, sm, G, M);
     row_BtoA(x, sm, G);
     const u64 *kq = P.key + (size_t)(J.c * P.keyL) * HEC_N;
     const u64 *zb = P.z + (size_t)(HEC_BJOB >> 1) * HEC_N;
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-        u32 i = G.gbase + 16 * k;
-        u64 z = zb[i];                                                // tmp2.c1 in (0,3q)
-        u64 accq = mred_lazy(z, __ldg(kq + i), M.q, M.qinv);          // MulCoeffsMontgomeryConstant (+ Reduce), (0,2q)
-        u64 d = shoup(x[k] + M.q2 - accq, P.negpinv, M.q);            // ModDownSplitNTTPQ combine, [0,2q)
-        if (J.c == 0) {
-            u64 a0 = J.a[i];
-            u64 m0 = shoup(J.b[i], __ldg(P.mono + i), M.q);           // [0,2q)
-            d += a0 + M.q2 - m0;                                      // + tmp2.c0  (AddLvl), < 5q
-            t1[k] = a0 + m0;                                          // tmp1.c0, < 3q
-        } else {
-            t1[k] = 2 * J.a[HEC_N + i] + 3 * M.q - z;                 // tmp1.c1 = a1 + b1*X^step = 2 a1 - tmp2.c1, in (0,5q)
-        }
-        u32 e = G.p + 16 * k;
-        sm[G.sbase + e + (e >> 4)] = d;
-    }
+    if (J.c == 0) b5_pointwise<true>(x, sm, st, P, J, M, G, zb, kq);
+    else b5_pointwise<false>(x, sm, st, P, J, M, G, zb, kq);
     __syncwarp();
     u64 *out = P.xout + (size_t)HEC_BJOB * HEC_N;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         u32 i = G.gbase + 16 * k;
         u32 s = perm_index(i, P.galEl) & 255u;                       // sigma_g stays inside the block
-        u64 r = t1[k] + sm[G.sbase + s + (s >> 4)];                   // < 8q
-        if (P.bias != nullptr && J.c == 0) r += __ldg(P.bias + i);
-        out[i] = canon16(r, M.q);
+        u32 e = G.p + 16 * k;
+        out[i] = canon16(st[G.sbase + e + (e >> 4)] + sm[G.sbase + s + (s >> 4)], M.q); // < 9q
     }
 }

@@ -16,7 +16,8 @@ __global__ void __launch_bounds__(256, 3) k(u64 *out, const ModC *mods, int it_n
         u32 base = 16 + ((threadIdx.x >> 4) + it) % 240;
         if (OP == 0) fwd4<false, 1>(x, M.psi + 15 * base, M.q, M.q2);
         if (OP == 1) fwd4<true, 1>(x, M.psi + 15 * base, M.q, M.q2);
-        if (OP == 2) inv4<1>(x, M.psi_inv + 15 * base, M.q, M.q2);
+        if (OP == 2) inv4<false, 1>(x, M.psi_inv + 15 * base, M.q, M.q2);
+        if (OP == 10) inv4<true, 1>(x, M.psi_inv + 15 * base, M.q, M.q2);
         if (OP == 3) { fwd4<false, 1>(x, M.psi, M.q, M.q2); }               // uniform twiddles (column layout A)
         if (OP == 4) {   // row layout B' with the natural NttPsi order: lane p reads psi[ng*(4096+16b+p)+gi]
             u32 b = (blockIdx.x * 16 + (threadIdx.x >> 4) + it) & 255, base = 4096 + 16 * b + (threadIdx.x & 15);
@@ -83,13 +84,14 @@ int main() {
     for (int i = 0; i < 65536; i++) { u64 w = (0x1234567ull * (i + 1)) % q; h[i] = make_ulonglong2(w, (u64)((((unsigned __int128)w) << 64) / q)); }
     cudaMemcpy(tab, h, 65536 * sizeof(ulonglong2), cudaMemcpyHostToDevice);
     ModC m;
-    m.q = q; m.q2 = 2 * q; m.qinv = 0xff7fffffbff7ffffull /* any odd value: timing only */; m.rmod = 1; m.ninv_w = 1; m.ninv_s = 1; m.psi = tab; m.psi_inv = tab; m.tight = 0; m.pad = 0;
+    m.q = q; m.q2 = 2 * q; m.qinv = 0xff7fffffbff7ffffull /* any odd value: timing only */; m.rmod = 1; m.ninv_w = 1; m.ninv_s = 1; m.psi = tab; m.psi_inv = tab; m.tight = 0; m.small = 0;
     ModC *dm;
     cudaMalloc(&dm, sizeof(ModC));
     cudaMemcpy(dm, &m, sizeof(ModC), cudaMemcpyHostToDevice);
     run<0>("fwd4<free>, per-half-warp twiddles", dm);
     run<1>("fwd4<tight>", dm);
     run<2>("inv4", dm);
+    run<10>("inv4, deferred range corrections", dm);
     run<3>("fwd4<free>, uniform twiddles", dm);
     run<4>("fwd4<free>, row B', NttPsi order (16 lines/load)", dm);
     run<5>("fwd4<free>, row B', thread-order table", dm);

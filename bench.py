@@ -39,36 +39,52 @@ def conv_alg_limbs(B):
     return 10 * B - 1 + 4 * (B.bit_length() - 1)
 
 
-def kernel_alg_limbs(name, M, B, first_launch_only=False):
-    """Distinct limbs fused kernel `name` must read + write (DESIGN.md "Kernels"), summed over its
-    launches in one run (Stage A: 1 launch; Stage B: one per pack level) or for its first launch."""
+def kernel_limbs(name, M, B, first_launch_only=False, algorithmic=False):
+    """Limbs fused kernel `name` reads + writes, summed over its launches in one run (Stage A: 1 launch; Stage B: one
+    per pack level) or for its first launch.
+    algorithmic=False: DISTINCT limbs the launch moves, scratch included (DESIGN.md "Kernels"; what ncu's dram__bytes
+    should show when nothing is fetched twice).
+    algorithmic=True: SURVEY.md 8(d) -- only operands and results of the reference operations the kernel completes
+    (input ciphertexts, plaintexts, key slices, output ciphertexts); half-transformed scratch counts for nothing, so
+    extra passes over a limb show up as a lower achieved figure."""
     na, jobs = B, M * B * 2
     if name == "A1":
-        return 2 * M + na + jobs            # ct limb q1 of both polys, pt limb q1 per channel, out
+        return 2 * M + na + (0 if algorithmic else jobs)      # ct limb q1 of both polys, pt limb q1 per channel (-> w1)
     if name == "A2":
-        return 2 * jobs
+        return 0 if algorithmic else 2 * jobs                  # w1 -> w2
     if name == "A3":
-        return jobs + 2 * M + na + jobs     # w2, ct limb q0, pt limb q0, out
+        return 2 * M + na + jobs + (0 if algorithmic else jobs)  # ct limb q0, pt limb q0, level-0 output (<- w2)
     tot, n = 0, na
     while n > 1:
         nbt = M * (n // 2)                  # butterflies in this level's launch
-        tot += {"B1": 3 * nbt + 1,          # a1, b1, monomial -> w1
-                "B2": 2 * nbt,
-                "B3": 3 * nbt + 2,          # w2 (shared by both key polys), 2 key P limbs -> 2 outputs
-                "B4": 4 * nbt,
-                "B5": 8 * nbt + 3 + (1 if n == 2 else 0)}[name]  # w4 x2, a0,a1,b0,b1, mono, 2 key Q limbs (+bias) -> 2 out
+        if algorithmic:
+            tot += {"B1": 2 * nbt, "B2": 0, "B3": 2, "B4": 0,            # a1, b1 | - | key P limbs | -
+                    "B5": 6 * nbt + 3 + (1 if n == 2 else 0)}[name]      # a, b (4), out (2); monomial, 2 key Q limbs (+ bias)
+        else:
+            tot += {"B1": 4 * nbt + 2,      # a1, b1, monomial pairs (16 B per coefficient) -> z, w1
+                    "B2": 2 * nbt,
+                    "B3": 3 * nbt + 2,      # w2 (shared by both key polys), 2 key P limbs -> 2 outputs
+                    "B4": 4 * nbt,
+                    "B5": 8 * nbt + 4 + (1 if n == 2 else 0)}[name]  # w4 x2, z, a0, a1, b0, 2 out; monomial pairs, 2 key Q limbs (+ bias)
         if first_launch_only:
             return tot
         n //= 2
     return tot
 
 
-NCU_SUMMARY = {64: "r01f_ncu_summary.csv", 32: "r01d_ncu_summary.csv"}   # captures of `python bench.py [--cts 32]`
+def group_alg_limbs(M, B):
+    """SURVEY.md 8(d) bytes of the NTT + key-switch kernel group (B1..B5) on the first pack level: the two input
+    ciphertexts and the output of every butterfly, the level's key slice, the monomial"""
+    nbt = M * (B // 2)
+    return 6 * nbt + 4 + 1
+
+
+NCU_SUMMARY = {64: "r02c_ncu_summary.csv"}   # capture of the default `python bench.py` command (final kernels of the round)
 
 
 def ncu_traffic(kernel, cts):
     """dram bytes (read + write) of the first launch of `kernel` from the committed ncu --set full capture of the
-    same command (profiles/r01f_ncu_summary.csv: default --cts 64; r01d: --cts 32), or None."""
+    same command, or None."""
     import csv
     if cts not in NCU_SUMMARY:
         return None
@@ -135,6 +151,43 @@ class ClockSampler:
         reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.rows[0][1]),
                 "reasons": reasons, "samples": len(self.rows)}
+
+
+def config4(ctx0, torch, rank, world):
+    """BASELINE.json config 4: conv 3, batch 256, the ciphertexts of a step dealt over the GPUs (8 per GPU per step);
+    device-resident conv/s of this rank (the caller's line carries the per-N figure; ranks are independent)."""
+    from optimal_conv_b200 import hec
+    B, M, steps = 256, 8, 4
+    Q, P = PR.Q_SET6[:2], PR.P_PACK
+    ctx0.close()
+    ctx = hec.Context(PR.LOGN, Q, P, device=torch.cuda.current_device())
+    w = synth.conv_workload(Q, P, PR.LOGN, B, seed=2025, n_ct=1)
+    mono = np.zeros((PR.LOGN, N), dtype=np.uint64)
+    for i in range(PR.LOGN):
+        m = np.zeros(N, dtype=np.uint64)
+        m[1 << i] = 1
+        mono[i] = ctx.ntt(m, 0)
+    ker = [ctx.upload_pt(w["pt_ker"][i], PR.SCALE) for i in range(B)]
+    idx = [ctx.upload_pt(mono[i:i + 1], 1.0) for i in range(PR.LOGN)]
+    bias = ctx.upload_pt(w["bias"][None, :], PR.SCALE)
+    for j, k in w["keys"].items():
+        ctx.upload_swk((1 << (j + 1)) + 1, k, 0)
+    cts = [ctx.upload_ct(synth.uniform_limbs(900 + 2 * m + 100 * rank, Q, N), synth.uniform_limbs(901 + 2 * m + 100 * rank, Q, N), PR.SCALE)
+           for m in range(M)]
+    plan = ctx.plan(ker, 1, PR.SCALE, PR.SCALE, idx, bias, M)
+    for _ in range(3):
+        plan.run(cts)
+    torch.cuda.synchronize()
+    ctx.timer_start()
+    for _ in range(steps):
+        plan.run(cts)
+    ms = ctx.timer_stop_ms()
+    v, _ = shard.throughput(M, steps, ms, device="cuda")
+    plan.destroy()
+    ctx.close()
+    return {"workload": "conv3_B256_N65536_lvl1to0_P1", "cts_per_step_per_gpu": M, "steps": steps, "value": v, "unit": "conv/s",
+            "n_gpus": world, "note": "device resident, whole job over all ranks; inputs of 8 ciphertexts reused (16 MiB, L2-resident; "
+                                     "the 5 GiB of intermediates are not)"}
 
 
 def run_reference(args):
@@ -383,6 +436,8 @@ def main():
                     help="conv = the headline fused path; the others are op-level side measurements")
     ap.add_argument("--cpu-sample", type=int, default=12, help="convs timed for cpu_baseline (0 = skip)")
     ap.add_argument("--ring", type=int, default=8, help="distinct input batches rotated through (> L2)")
+    ap.add_argument("--check", type=int, default=64, help="ciphertexts of one step compared with the oracle before timing (0 = skip)")
+    ap.add_argument("--config4", type=int, default=1, help="also measure BASELINE.json config 4 (B = 256, 8 ciphertexts per GPU per step)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -398,6 +453,9 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    # host side of the end-to-end path: this rank's threads and (first-touch) pinned buffers stay on the cores and the
+    # memory of the NUMA node its GPU hangs off, each rank on its own share of them
+    placement = shard.pin_rank_to_gpu_node(local, world)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B, M = args.batch, args.cts
@@ -468,6 +526,25 @@ def main():
         plan.wait(t)
         return plan.span_end_ms()
 
+    # ---- parity of THIS shape before anything is timed: one whole step (M ciphertexts, B channels) downloaded and
+    #      compared bit for bit with the CPU oracle (the checker; not inside any timed span) ----
+    parity = None
+    if args.check > 0:
+        import hashlib
+        from oracle.orc import Ct, Oracle
+        o = Oracle(PR.LOGN, Q, P)
+        oidx = o.monomial_pts()
+        outs = plan.run(dev_in[0])
+        n_chk = min(M, args.check if rank == 0 else 2)
+        hsh = hashlib.sha256()
+        for m in range(n_chk):
+            g0, g1 = outs[m].download()
+            ref = o.conv_then_pack(Ct(v0[0, m], v1[0, m], PR.SCALE), w["pt_ker"], PR.SCALE, 1, PR.SCALE, oidx, w["keys"],
+                                   w["bias"], nthreads=max(1, (os.cpu_count() or 1) // max(1, world)))[0]
+            if not (np.array_equal(g0, ref.c0) and np.array_equal(g1, ref.c1)):
+                raise SystemExit("bench.py: GPU result of ciphertext %d differs from the oracle at the bench shape" % m)
+            hsh.update(g0.tobytes()); hsh.update(g1.tobytes())
+        parity = {"checked_ciphertexts": n_chk, "of": M, "bit_exact_vs_oracle": True, "sha256": hsh.hexdigest()[:16]}
     # ---- kernel-resident throughput ----
     timed(step_dev, args.warmup)
     sampler = ClockSampler(local)
@@ -492,6 +569,18 @@ def main():
         plan1.run(dev_in[i % ring][:1])
         lat.append(ctx.timer_stop_ms())
     latency_ms = statistics.median(lat[3:])
+    plan1.destroy()
+    # ---- the per-convolution entry a Go caller binds: hec_conv_then_pack on host buffers -- upload
+    #      of the level-1 ciphertext, the call (plan found in the context's cache after the first), download ----
+    lat_call = []
+    for i in range(13):
+        t0 = time.perf_counter()
+        ct1 = ctx.upload_ct(v0[i % ring, 0], v1[i % ring, 0], PR.SCALE)
+        r1 = ctx.conv_then_pack(ct1, ker, 1, PR.SCALE, idx, bias)
+        r1.download()
+        lat_call.append(1e3 * (time.perf_counter() - t0))
+        ct1.free(); r1.free()
+    latency_call_ms = statistics.median(lat_call[3:])
     # ---- per-kernel times (kernels launched one by one) for the roofline of the dominant kernel ----
     prof = {}
     for rep in range(3):
@@ -520,8 +609,12 @@ def main():
     share = dom_ms / sum(v["ms_per_run"] for v in per_kernel.values())
     # roofline of the dominant kernel, per launch, on its first (largest) launch of a run
     first_ms = sum(prof[dom][i * n_l] for i in range(3)) / 3
-    alg_bytes_launch = kernel_alg_limbs(dom, M, B, first_launch_only=True) * LIMB
+    alg_bytes_launch = kernel_limbs(dom, M, B, first_launch_only=True, algorithmic=True) * LIMB
+    distinct_bytes_launch = kernel_limbs(dom, M, B, first_launch_only=True) * LIMB
     achieved = alg_bytes_launch / (first_ms / 1e3) / 1e9
+    # the NTT + key-switch kernel group of the first pack level (B1..B5 together)
+    grp_ms = sum(sum(prof[k][i * per_kernel[k]["launches_per_run"]] for i in range(3)) / 3 for k in ("B1", "B2", "B3", "B4", "B5") if k in prof)
+    grp_bytes = group_alg_limbs(M, B) * LIMB
     # integer ceiling: modular multiplies of one conv / measured modmul throughput
     units = 4 * B * 2 + 12 * (B - 1)                     # half-transforms (8 stages) per conv
     modmuls = units * (N // 2) * 8 + (5 * B * 2 + 10 * (B - 1)) * N
@@ -546,9 +639,14 @@ def main():
         "clocks": sampler.summary(),
         "roofline": {"bound": "hbm", "kernel": "k_conv" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": ncu_traffic("k_conv" + dom, M) if B == 16 else None,
-                     "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes_launch, "launch_ms": first_ms,
+                     "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes_launch,
+                     "alg_bytes_definition": "SURVEY.md 8(d): operands and results of the reference operations only; scratch excluded",
+                     "distinct_bytes_per_launch": distinct_bytes_launch, "launch_ms": first_ms,
                      "launch": "first (largest) of %d launches per run" % n_l, "share_of_step": share,
                      "traffic_source": "profiles/%s (ncu --set full, same command)" % NCU_SUMMARY.get(M, "-")},
+        "roofline_group": {"kernels": "k_convB1..B5 (NTT + key-switch group), first pack level", "bound": "hbm",
+                           "alg_bytes": grp_bytes, "ms": grp_ms, "achieved": (grp_bytes / (grp_ms / 1e3) / 1e9) if grp_ms else None,
+                           "peak": peak, "unit": "GB/s", "frac": (grp_bytes / (grp_ms / 1e3) / 1e9 / peak) if grp_ms else None},
         "roofline_int": {"bound": "integer multiply pipe (fmaheavy)", "modmuls_per_conv": modmuls,
                          "achieved": modmuls * (M * args.steps) / (ms_dev / 1e3), "peak": int_peak,
                          "unit": "modmul/s", "frac": modmuls * (M * args.steps) / (ms_dev / 1e3) / int_peak,
@@ -557,7 +655,14 @@ def main():
                           "frac": conv_gbs / peak, "note": "whole conv, per GPU: (10B-1+4log2B) limbs x convs / time"},
         "kernels_ms_per_run": {k: round(v["ms_per_run"], 4) for k, v in sorted(per_kernel.items())},
         "latency_ms_single_conv": latency_ms,
+        "latency_ms_single_call": latency_call_ms,
+        "latency_note": "single_conv: a prepared plan of one ciphertext, device resident; single_call: hec_ct_upload + "
+                        "hec_conv_then_pack (plan cached in the context) + hec_ct_download on pageable host arrays, wall clock",
+        "parity": parity,
+        "host_placement": placement,
     }
+    if args.config4 and B == 16:
+        line["config4"] = config4(ctx, torch, rank, world)
     # ---- CPU baseline beside it: the oracle port, 1 thread (the reference is single-threaded) ----
     if world == 1 and args.cpu_sample > 0:
         from oracle.orc import Ct, Oracle

@@ -137,20 +137,27 @@ static int check_launch(hec_ctx *c, const char *what) {
 
 // launch one of the generic kernels (all of them start with HEC_PDL_SYNC); they carry the programmatic-stream-
 // serialisation attribute (HEC_PDL=0 turns it off) so that the launch latency and CTA ramp of a kernel overlap the tail of its predecessor
+#ifndef HEC_DOT_BULK_DEFAULT
+#define HEC_DOT_BULK_DEFAULT 0 // measured (profiles/r02b): k_dot already streams at 5.6 TB/s = 0.87 of the measured HBM peak; the staged variant ties on the key switch and loses 2-8 % on evalReLU / the tap sums
+#endif
 template <typename... KArgs, typename... Args>
-static void launch_k(hec_ctx *c, void (*kern)(KArgs...), dim3 grid, dim3 block, Args &&...args) {
+static void launch_k_smem(hec_ctx *c, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args &&...args) {
     static const int pdl = getenv("HEC_PDL") ? atoi(getenv("HEC_PDL")) : 1; // measured: -4.7 % key switch, -6 % CtoS / evalReLU
     if (!pdl) {
-        kern<<<grid, block, 0, c->stream>>>(KArgs(args)...);
+        kern<<<grid, block, smem, c->stream>>>(KArgs(args)...);
         return;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+template <typename... KArgs, typename... Args>
+static void launch_k(hec_ctx *c, void (*kern)(KArgs...), dim3 grid, dim3 block, Args &&...args) {
+    launch_k_smem(c, kern, grid, block, 0, std::forward<Args>(args)...);
 }
 
 static int stage_cached(hec_ctx *c, std::vector<char> &h, char **dev);
@@ -928,10 +935,21 @@ static int launch_dot(hec_ctx *c, const std::vector<DotSpec> &specs) {
     }
     int rc = stage_cached(c, h, &dbuf);
     if (rc) return rc;
+    // HEC_DOT_BULK=1: operand tiles staged by bulk asynchronous copies + mbarriers (k_dot_bulk); 0: per-thread loads (k_dot)
+    static const int bulk = getenv("HEC_DOT_BULK") ? atoi(getenv("HEC_DOT_BULK")) : HEC_DOT_BULK_DEFAULT;
+    static bool attr_set = false;
+    if (bulk && !attr_set) {
+        HEC_CUDA(c, cudaFuncSetAttribute(k_dot_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEC_DOT_BULK_SMEM));
+        attr_set = true;
+    }
     for (size_t off = 0; off < specs.size(); off += 65535) { // grid.y limit
         unsigned ny = (unsigned)std::min<size_t>(65535, specs.size() - off);
-        launch_k(c, k_dot, dim3(32, ny), dim3(256), reinterpret_cast<const DotJob *>(dbuf + np * sizeof(u64 *)) + off,
-                 reinterpret_cast<const u64 *const *>(dbuf), c->dmods);
+        const DotJob *dj = reinterpret_cast<const DotJob *>(dbuf + np * sizeof(u64 *)) + off;
+        if (bulk)
+            launch_k_smem(c, k_dot_bulk, dim3(HEC_N / HEC_DOT_TILE, ny), dim3(256), HEC_DOT_BULK_SMEM, dj,
+                          reinterpret_cast<const u64 *const *>(dbuf), c->dmods);
+        else
+            launch_k(c, k_dot, dim3(32, ny), dim3(256), dj, reinterpret_cast<const u64 *const *>(dbuf), c->dmods);
         c->launches += 1;
     }
     cudaError_t e = cudaGetLastError();

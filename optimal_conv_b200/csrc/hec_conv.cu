@@ -226,6 +226,12 @@ extern "C" int hec_keep_ctxt(hec_ctx *ev, const hec_ct *input, const hec_pt *mas
 // =========================================================================================
 // fused plan
 // =========================================================================================
+#ifndef HEC_PLAN_CHUNK_DEFAULT
+#define HEC_PLAN_CHUNK_DEFAULT 0
+#endif
+#ifndef HEC_PLAN_CHAINS_DEFAULT
+#define HEC_PLAN_CHAINS_DEFAULT 2
+#endif
 // The exact basis extension P -> Q with ONE special prime computes v = uint64(float64(y) / float64(p)) for the
 // canonical residue y < p (L:ring/ring_basis_extension.go:670-713 with a single term): int -> double conversion and
 // IEEE division are monotone, so v is 0 up to a threshold and 1 from there on (float64(y)/float64(p) rounds up to 1.0
@@ -254,6 +260,13 @@ struct hec_plan {
     u64 *stage_in = nullptr, *xfinal = nullptr;
     ConvA pa;
     std::vector<ConvB> pb;
+    // chunked execution: the M ciphertexts of a run are worked through in chunks of Mc on `nchains` concurrent chains
+    // (forked streams inside the captured graph), each chain with scratch of its own, so that what one kernel of a chunk
+    // writes is still in L2 when the next kernel of that chunk reads it
+    int Mc = 0, nchains = 1;
+    std::vector<cudaStream_t> chain_streams;
+    std::vector<cudaEvent_t> chain_events;
+    cudaEvent_t ev_fork = nullptr;
     const u64 *bias = nullptr; int bias_mod = 0;
     cudaGraphExec_t exec = nullptr;
     int launches_per_run = 0;
@@ -274,19 +287,39 @@ static void plan_unref_all(hec_plan *p) {
     p->ref_keys.clear();
 }
 
-static int plan_launch_all(hec_plan *p, const std::function<void()> &after = [] {}) {
+// descriptors of chunk `j` (ciphertexts [j*Mc, (j+1)*Mc) of the run) on scratch set `chain`
+static void plan_chunk_args(const hec_plan *p, int j, int chain, ConvA &A, std::vector<ConvB> &Bs) {
+    const int Mc = p->Mc, na = p->na;
+    const size_t jobsA = (size_t)Mc * na * 2, nb0 = (size_t)Mc * std::max(1, na / 2);
+    const size_t per_chain = 2 * jobsA + nb0 * 7;
+    u64 *sc = p->pa.w1 + (size_t)chain * per_chain * HEC_N; // chain scratch: w1, w2, wb1, wb2, wb3 x2, wb4 x2, z
+    A = p->pa;
+    A.ctin = p->pa.ctin + (size_t)j * Mc;
+    A.w1 = sc; A.w2 = sc + jobsA * HEC_N;
+    A.xout = p->pa.xout + (size_t)j * jobsA * HEC_N;
+    u64 *wb = sc + 2 * jobsA * HEC_N;
+    Bs = p->pb;
+    for (size_t l = 0; l < Bs.size(); l++) {
+        ConvB &b = Bs[l];
+        const size_t nin = (size_t)Mc * (na >> l) * 2, nout = (size_t)Mc * (na >> (l + 1)) * 2;
+        b.xin = p->pb[l].xin + (size_t)j * nin * HEC_N;
+        b.xout = p->pb[l].xout + (size_t)j * nout * HEC_N;
+        b.w1 = wb; b.w2 = wb + nb0 * HEC_N; b.w3 = wb + 2 * nb0 * HEC_N; b.w4 = wb + 4 * nb0 * HEC_N; b.z = wb + 6 * nb0 * HEC_N;
+    }
+}
+static int plan_launch_chunk(hec_plan *p, const ConvA &A, const std::vector<ConvB> &Bs, int Mc, cudaStream_t s,
+                             const std::function<void()> &after) {
     hec_ctx *c = p->c;
-    cudaStream_t s = c->stream;
-    dim3 gA = HEC_GRID(HEC_TILES_PER_LIMB, p->M * p->na * 2);
-    k_convA1<<<gA, HEC_THREADS, 0, s>>>(p->pa, c->dmods);
+    dim3 gA = HEC_GRID(HEC_TILES_PER_LIMB, Mc * p->na * 2);
+    k_convA1<<<gA, HEC_THREADS, 0, s>>>(A, c->dmods);
     after();
-    k_convA2<<<gA, HEC_THREADS, 0, s>>>(p->pa, c->dmods);
+    k_convA2<<<gA, HEC_THREADS, 0, s>>>(A, c->dmods);
     after();
-    k_convA3<<<gA, HEC_THREADS, HEC_A3_SMEM, s>>>(p->pa, c->dmods);
+    k_convA3<<<gA, HEC_THREADS, HEC_A3_SMEM, s>>>(A, c->dmods);
     after();
-    for (auto &b : p->pb) {
+    for (auto &b : Bs) {
         int nb = b.n / 2;
-        dim3 g1 = HEC_GRID(HEC_TILES_PER_LIMB, p->M * nb), g2 = HEC_GRID(HEC_TILES_PER_LIMB, p->M * nb * 2);
+        dim3 g1 = HEC_GRID(HEC_TILES_PER_LIMB, Mc * nb), g2 = HEC_GRID(HEC_TILES_PER_LIMB, Mc * nb * 2);
         k_convB1<<<g1, HEC_THREADS, 0, s>>>(b, c->dmods);
         after();
         k_convB2<<<g1, HEC_THREADS, 0, s>>>(b, c->dmods);
@@ -297,6 +330,37 @@ static int plan_launch_all(hec_plan *p, const std::function<void()> &after = [] 
         after();
         k_convB5<<<g2, HEC_THREADS, HEC_B5_SMEM, s>>>(b, c->dmods);
         after();
+    }
+    return HEC_OK;
+}
+// all kernels of a run.  serial = true: every chunk on the context's stream, one after the other (profiling); else the
+// chains run side by side on forked streams (inside a stream capture this becomes a graph with parallel branches)
+static int plan_launch_all(hec_plan *p, const std::function<void()> &after = [] {}, bool serial = false) {
+    hec_ctx *c = p->c;
+    cudaStream_t s = c->stream;
+    const int nchunks = p->M / p->Mc;
+    ConvA A;
+    std::vector<ConvB> Bs;
+    if (nchunks == 1) {
+        plan_chunk_args(p, 0, 0, A, Bs);
+        plan_launch_chunk(p, A, Bs, p->Mc, s, after);
+    } else if (serial) {
+        for (int j = 0; j < nchunks; j++) {
+            plan_chunk_args(p, j, 0, A, Bs);
+            plan_launch_chunk(p, A, Bs, p->Mc, s, after);
+        }
+    } else {
+        cudaEventRecord(p->ev_fork, s);
+        for (int ch = 0; ch < p->nchains; ch++) {
+            cudaStream_t cs = p->chain_streams[ch];
+            cudaStreamWaitEvent(cs, p->ev_fork, 0);
+            for (int j = ch; j < nchunks; j += p->nchains) {
+                plan_chunk_args(p, j, ch, A, Bs);
+                plan_launch_chunk(p, A, Bs, p->Mc, cs, after);
+            }
+            cudaEventRecord(p->chain_events[ch], cs);
+            cudaStreamWaitEvent(s, p->chain_events[ch], 0);
+        }
     }
     if (p->levels == 0 && p->bias) { // single channel: bias not folded into a B5 epilogue
         EwJobs J;
@@ -324,6 +388,9 @@ extern "C" void hec_plan_destroy(hec_plan *p) {
         if (p->stage_in2[i]) cudaFree(p->stage_in2[i]);
         if (p->stage_out2[i]) cudaFree(p->stage_out2[i]);
     }
+    for (auto e : p->chain_events) cudaEventDestroy(e);
+    for (auto st : p->chain_streams) cudaStreamDestroy(st);
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     if (p->ev_t0) cudaEventDestroy(p->ev_t0);
     if (p->ev_t1) cudaEventDestroy(p->ev_t1);
     if (p->s_in) cudaStreamDestroy(p->s_in);
@@ -391,20 +458,39 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
         if (launch_ew<EW_MULSCALAR>(c, ej)) return bail(HEC_E_CUDA, "scaling kernel plaintexts");
     }
     if (cudaMemcpy((void *)p->d_ptk, hk.data(), B * sizeof(u64 *), cudaMemcpyHostToDevice) != cudaSuccess) return bail(HEC_E_CUDA, "memcpy ptk");
-    size_t jobsA = (size_t)M * na * 2;          // limbs per Stage-A buffer
-    size_t nb0 = (size_t)M * std::max(1, na / 2);
+    // chunking (see hec_plan): HEC_PLAN_CHUNK ciphertexts per chunk (0 / not a divisor of M: the whole batch at once),
+    // HEC_PLAN_CHAINS chunks in flight
+    {
+        static const int env_chunk = getenv("HEC_PLAN_CHUNK") ? atoi(getenv("HEC_PLAN_CHUNK")) : HEC_PLAN_CHUNK_DEFAULT;
+        static const int env_chains = getenv("HEC_PLAN_CHAINS") ? atoi(getenv("HEC_PLAN_CHAINS")) : HEC_PLAN_CHAINS_DEFAULT;
+        p->Mc = (env_chunk > 0 && env_chunk < M && M % env_chunk == 0) ? env_chunk : M;
+        p->nchains = std::max(1, std::min(env_chains, M / p->Mc));
+    }
+    const int Mc = p->Mc;
+    size_t jobsA = (size_t)M * na * 2;          // limbs per level-0 buffer
+    size_t jobsAc = (size_t)Mc * na * 2, nb0c = (size_t)Mc * std::max(1, na / 2);
+    size_t per_chain = 2 * jobsAc + nb0c * 7;    // w1, w2; wb1, wb2, wb3 x2, wb4 x2, z
     size_t limbs = 4 * (size_t)M                 // staged inputs [M][2][2]
-                 + 2 * jobsA                     // w1, w2
-                 + 2 * jobsA                     // X_0 .. X_last (geometric, < 2x)
-                 + nb0 * (1 + 1 + 2 + 2 + 1);    // wb1..wb4, z
+                 + (size_t)p->nchains * per_chain
+                 + 2 * jobsA;                    // X_0 .. X_last (geometric, < 2x)
     if (cudaMalloc(&p->pool, limbs * HEC_N * sizeof(u64)) != cudaSuccess) return bail(HEC_E_NOMEM, "cudaMalloc plan pool");
     u64 *cur = p->pool;
     auto take = [&](size_t n) { u64 *r = cur; cur += n * HEC_N; return r; };
     p->stage_in = take(4 * (size_t)M);
-    u64 *w1 = take(jobsA), *w2 = take(jobsA);
+    u64 *w1 = take((size_t)p->nchains * per_chain), *w2 = nullptr; // chain scratch sets; carved up in plan_chunk_args
     std::vector<u64 *> X(levels + 1);
     for (int l = 0; l <= levels; l++) X[l] = take((size_t)M * (na >> l) * 2);
-    u64 *wb1 = take(nb0), *wb2 = take(nb0), *wb3 = take(2 * nb0), *wb4 = take(2 * nb0), *wbz = take(nb0);
+    u64 *wb1 = nullptr, *wb2 = nullptr, *wb3 = nullptr, *wb4 = nullptr, *wbz = nullptr;
+    if (p->M / p->Mc > 1) {
+        if (cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) != cudaSuccess) return bail(HEC_E_CUDA, "event");
+        for (int ch = 0; ch < p->nchains; ch++) {
+            cudaStream_t st; cudaEvent_t ev;
+            if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return bail(HEC_E_CUDA, "stream");
+            p->chain_streams.push_back(st);
+            if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return bail(HEC_E_CUDA, "event");
+            p->chain_events.push_back(ev);
+        }
+    }
     p->xfinal = X[levels];
     // ---- Stage A constants ----
     const int mq0 = c->modQ(0), mq1 = c->modQ(1), mp0 = c->modP(0);
@@ -455,7 +541,7 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
         b.mu0 = (u32)(((u128)1 << 64) / q0);
         p->pb.push_back(b);
     }
-    p->launches_per_run = 3 + 5 * levels + ((levels == 0 && pt_bias) ? M : 0);
+    p->launches_per_run = (3 + 5 * levels) * (M / p->Mc) + ((levels == 0 && pt_bias) ? M : 0);
     if (cudaFuncSetAttribute(k_convB3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEC_B3_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(k_convB5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEC_B5_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(k_convA3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEC_A3_SMEM) != cudaSuccess)
@@ -536,8 +622,9 @@ extern "C" int hec_plan_profile(hec_plan *p, const hec_ct *const *ins, float *ms
     if (!p || !ins || !ms || !n) return HEC_E_INVAL;
     hec_ctx *c = p->c;
     cudaSetDevice(c->device);
-    int nk = p->launches_per_run;
-    if (cap < nk) return c->fail(HEC_E_INVAL, "profile buffer too small");
+    const int nk = p->launches_per_run, nchunks = p->M / p->Mc;
+    const int per_chunk = 3 + 5 * p->levels, nout = nchunks > 1 ? per_chunk : nk; // chunks are folded: one time per kernel position
+    if (cap < nout) return c->fail(HEC_E_INVAL, "profile buffer too small");
     std::vector<const u64 *> ptrs(p->M);
     for (int m = 0; m < p->M; m++) {
         if (!ins[m] || ins[m]->level != 1 || ins[m]->alloc != 2) return c->fail(HEC_E_LEVEL, "plan inputs must be level-1 ciphertexts");
@@ -548,12 +635,17 @@ extern "C" int hec_plan_profile(hec_plan *p, const hec_ct *const *ins, float *ms
     for (auto &e : ev) cudaEventCreate(&e);
     int k = 0;
     cudaEventRecord(ev[0], c->stream);
-    int rc = plan_launch_all(p, [&] { if (k < nk) cudaEventRecord(ev[++k], c->stream); });
+    int rc = plan_launch_all(p, [&] { if (k < nk) cudaEventRecord(ev[++k], c->stream); }, true);
     cudaStreamSynchronize(c->stream);
     c->launches += nk;
-    for (int i = 0; i < k; i++) cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+    for (int i = 0; i < nout; i++) ms[i] = 0;
+    for (int i = 0; i < k; i++) {
+        float t = 0;
+        cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
+        ms[nchunks > 1 ? i % per_chunk : i] += t;
+    }
     for (auto &e : ev) cudaEventDestroy(e);
-    *n = k;
+    *n = std::min(k, nout);
     return rc;
 }
 

@@ -271,6 +271,80 @@ __global__ void __launch_bounds__(256) k_dot(const DotJob *__restrict__ jobs, co
     }
 }
 
+// ---- the same sums with the operand tiles staged by the TMA engine --------------------------------------------
+// k_dot is the one kernel of the key switch that only streams: per output limb it reads 2T limbs (T digits x
+// {decomposed polynomial, key}) once and writes one.  Here a CTA owns HEC_DOT_TILE coefficients of an output limb and
+// one thread feeds a ring of HEC_DOT_STAGES shared-memory stages with bulk asynchronous copies (cp.async.bulk ->
+// UBLKCP), each completing on the stage's mbarrier (SYNCS); all threads consume stage t while the copies of stages
+// t+1 .. t+STAGES-1 are in flight -- no registers hold data in flight and no thread issues per-element loads.
+#define HEC_DOT_TILE 1024
+#define HEC_DOT_STAGES 4
+#define HEC_DOT_BULK_SMEM (2 * HEC_DOT_STAGES * HEC_DOT_TILE * sizeof(u64) + HEC_DOT_STAGES * sizeof(u64))
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_LOOP:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra WAIT_DONE;\n\t"
+                 "bra WAIT_LOOP;\n\tWAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, u32 bytes, u64 *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__global__ void __launch_bounds__(256) k_dot_bulk(const DotJob *__restrict__ jobs, const u64 *const *__restrict__ ptrs,
+                                                  const ModC *__restrict__ mods) {
+    HEC_PDL_SYNC();
+    extern __shared__ __align__(128) u64 dsm[];
+    u64 *sa = dsm, *sb = dsm + HEC_DOT_STAGES * HEC_DOT_TILE, *full = dsm + 2 * HEC_DOT_STAGES * HEC_DOT_TILE;
+    const DotJob jd = jobs[blockIdx.y];
+    const u64 *const *pa = ptrs + jd.a_off;
+    const u64 *const *pb = jd.b_off < 0 ? nullptr : ptrs + jd.b_off;
+    const int T = jd.T;
+    const u64 q = mods[jd.mod].q, qinv = mods[jd.mod].qinv;
+    const u32 base = blockIdx.x * HEC_DOT_TILE, tid = threadIdx.x;
+    constexpr u32 BYTES = HEC_DOT_TILE * sizeof(u64);
+    if (tid == 0) {
+        for (int s = 0; s < HEC_DOT_STAGES; s++) mbar_init(full + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int t) { // thread 0: both operand tiles of term t into stage t % STAGES
+        const int s = t % HEC_DOT_STAGES;
+        mbar_expect_tx(full + s, pb ? 2 * BYTES : BYTES);
+        bulk_g2s(sa + s * HEC_DOT_TILE, pa[t] + base, BYTES, full + s);
+        if (pb) bulk_g2s(sb + s * HEC_DOT_TILE, pb[t] + base, BYTES, full + s);
+    };
+    if (tid == 0)
+        for (int t = 0; t < HEC_DOT_STAGES && t < T; t++) issue(t);
+    u64 acc[4] = {0, 0, 0, 0};
+    for (int t = 0; t < T; t++) {
+        const int s = t % HEC_DOT_STAGES;
+        mbar_wait(full + s, (t / HEC_DOT_STAGES) & 1);
+        const ulonglong2 *va = reinterpret_cast<const ulonglong2 *>(sa + s * HEC_DOT_TILE);
+        const ulonglong2 a0 = va[tid], a1 = va[256 + tid];
+        u64 v[4] = {a0.x, a0.y, a1.x, a1.y};
+        if (pb) {
+            const ulonglong2 *vb = reinterpret_cast<const ulonglong2 *>(sb + s * HEC_DOT_TILE);
+            const ulonglong2 b0 = vb[tid], b1 = vb[256 + tid];
+            v[0] = mred(v[0], b0.x, q, qinv); v[1] = mred(v[1], b0.y, q, qinv);
+            v[2] = mred(v[2], b1.x, q, qinv); v[3] = mred(v[3], b1.y, q, qinv);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) acc[k] = addmod(acc[k], v[k], q);
+        if (t + HEC_DOT_STAGES < T) {   // the stage is free once every thread has read it
+            __syncthreads();
+            if (tid == 0) issue(t + HEC_DOT_STAGES);
+        }
+    }
+    ulonglong2 *out = reinterpret_cast<ulonglong2 *>(jd.out + base);
+    out[tid] = make_ulonglong2(acc[0], acc[1]);
+    out[256 + tid] = make_ulonglong2(acc[2], acc[3]);
+}
+
 // ---- exact basis extension (modUpExact / reconstructRNS / multSum,
 // L:ring/ring_basis_extension.go:438-457,670-779) -----------------------------------------
 #define HEC_MAXA 5
@@ -420,7 +494,7 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convA2(ConvA P, const
 // (profiles/r02a: long-scoreboard stalls 5.9 per issue with the loads after the transform).
 #define HEC_A3_SMEM (2 * 16 * HEC_ROW_PITCH * sizeof(u64)) // dynamic: above the 48 KB static limit
 __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convA3(ConvA P, const ModC *__restrict__ mods) {
-    extern __shared__ __align__(16) u64 dsm[];
+    extern __shared__ __align__(128) u64 dsm[];
     u64 *sm = dsm, *st = dsm + 16 * HEC_ROW_PITCH;
     const AJob J(HEC_BJOB, P.na);
     const ModC M = mods[P.mq0];
@@ -538,7 +612,7 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convB2(ConvB P, const
 //     run inverse stages t = 1..128 under p0                               grid.y = M*nb
 #define HEC_B3_SMEM ((16 * HEC_ROW_PITCH + HEC_TILE) * sizeof(u64)) // dynamic: above the 48 KB static limit
 __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convB3(ConvB P, const ModC *__restrict__ mods) {
-    extern __shared__ __align__(16) u64 dsm[];
+    extern __shared__ __align__(128) u64 dsm[];
     u64 *sm = dsm;
     u64 *stash = dsm + 16 * HEC_ROW_PITCH; // NTT_p0(digit), kept for the second key poly
     const ModC M = mods[P.mp0];
@@ -626,7 +700,7 @@ __device__ __forceinline__ void b5_pointwise(const u64 (&x)[16], u64 *sm, u64 *s
                       // per 64 convolutions against 3 CTAs / 80 registers; the transform half loses less than that gains)
 #endif
 __global__ void __launch_bounds__(HEC_THREADS, HEC_B5_MINB) k_convB5(ConvB P, const ModC *__restrict__ mods) {
-    extern __shared__ __align__(16) u64 dsm[];
+    extern __shared__ __align__(128) u64 dsm[];
     u64 *sm = dsm;                         // exchange buffer of the transform, then the mod-down results d
     u64 *st = dsm + 16 * HEC_ROW_PITCH;    // tmp1 of the thread's own coefficients: parked here rather than in 32 registers, so
                                            // that the loads of the epilogue's operand streams can run ahead of their use

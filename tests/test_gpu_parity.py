@@ -976,6 +976,31 @@ def test_conv_then_pack_plan_cache_and_object_lifetimes(orc, idx_np):
         c.close()
 
 
+def test_plan_at_the_bench_shape_64_ciphertexts_16_channels(orc, idx_np):
+    """the configuration bench.py times (BASELINE.json configs[1] at 64 ciphertexts per step): every one of the 64
+    level-0 results == the oracle, and a second run of the same plan gives the same bits"""
+    import os
+    c = hec.Context(PR.LOGN, Q2, P1)
+    try:
+        M = 64
+        w = synth.conv_workload(Q2, P1, PR.LOGN, 16, seed=2024, n_ct=M)
+        G = common.GpuConv(c, w, idx_np)
+        plan = c.plan(G.ker, 1, PR.SCALE, PR.SCALE, G.idx, G.bias, M)
+        outs = plan.run(G.cts)
+        got = [o.download() for o in outs]
+        nt = max(1, os.cpu_count() or 1)
+        for m in range(M):
+            ref = common.oracle_conv(orc, w, 1, PR.SCALE, idx_np, m=m, nthreads=nt)
+            assert np.array_equal(got[m][0], ref.c0) and np.array_equal(got[m][1], ref.c1), m
+        outs = plan.run(G.cts)
+        for m in (0, 31, 63):
+            g0, g1 = outs[m].download()
+            assert np.array_equal(g0, got[m][0]) and np.array_equal(g1, got[m][1])
+        plan.destroy()
+    finally:
+        c.close()
+
+
 def test_plan_batch_with_norm_and_no_bias(orc, idx_np):
     """batch of 2 ciphertexts, B = 8 with norm = 2 (4 real channels, 2 pack levels), bias omitted"""
     c = hec.Context(PR.LOGN, Q2, P1)

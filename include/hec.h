@@ -235,6 +235,50 @@ int hec_ext_ctxt(hec_ctx *ctx, const hec_ct *input, int n, const int *rots, cons
                  int do_rescale, double min_scale, hec_ct **out);
 int hec_keep_ctxt(hec_ctx *ctx, const hec_ct *input, const hec_pt *mask, double min_scale, hec_ct **out);
 
+/* ext_double_ctxt (conv.go:374-414; do_rescale = 1) and bsgs_ctxt (conv.go:303-344; do_rescale = 0): the masked
+ * rotate-and-sum twice, mid = sum over (rots_m, pts_m) of the input, out = sum over (rots_r, pts_r) of mid. */
+int hec_ext_double_ctxt(hec_ctx *ctx, const hec_ct *input, int n_m, const int *rots_m, const hec_pt *const *pts_m,
+                        int n_r, const int *rots_r, const hec_pt *const *pts_r, int do_rescale, double min_scale,
+                        hec_ct **out);
+
+/* ---- one layer: evalConv_BNRelu_new (eval.go:272-575) --------------------------------------------------------
+ * conv (+BN) on the pack evaluator -> 2^pow relabel -> BootstrappConv_CtoS -> evalReLU + MulByPow2 per half ->
+ * ext_ctxt / ext_double_ctxt / keep_ctxt per half -> BootstrappConv_StoC -> Rescale, on the main evaluator.
+ * The reference's `kind` string selects which pieces run; here that is expressed by which operands are present:
+ *   "Conv", "Conv_sparse", "Conv_inside", "StrConv_inside":  n_conv = 1, move_kind = HEC_MOVE_KEEP
+ *      (for the *_inside kinds the caller passes the dilated kernel, eval.go:421-433, as it passes any kernel)
+ *   "TransConv":                                        n_conv = 1, move_kind = HEC_MOVE_EXT (r_idx[in_wid][ul])
+ *   "StrConv", "StrConv_odd" (+ pt_pre), "StrConv_fast": n_conv = 1, HEC_MOVE_EXT or HEC_MOVE_EXT_DOUBLE (fast_pack)
+ *   "StrConv_sparse":       n_conv = 2 (kernels split by output parity, norm/2), pt_shift2 = x^(norm/4), pt_post, EXT_DOUBLE
+ *   "StrConv_sparse_full":  n_conv = 1, pt_post, HEC_MOVE_EXT_DOUBLE
+ * Everything the Go host computes in floats or with its encoder arrives as handles: kernel / bias plaintexts
+ * (prep_Ker, or hec_encode_coeffs_many), the monomials x^offset (EncodeCoeffs of a unit vector), the slot-encoded
+ * masks of rot_util.go's index maps (EncodeNTT at the scales conv.go:347-431 prescribes), the bootstrapper. */
+#define HEC_MOVE_KEEP 0
+#define HEC_MOVE_EXT 1
+#define HEC_MOVE_EXT_DOUBLE 2
+typedef struct {
+    int n_conv;                        /* 1, or 2 for "StrConv_sparse" */
+    const hec_pt *const *pt_ker[2];    /* [max_ob] kernel plaintexts of each convolution (level ECD_LV) */
+    const hec_pt *pt_bias[2];          /* pl_bn_b of each (level 0, scale out_scale), or NULL */
+    int max_ob, norm[2];               /* max_batch; norm of each convolution (norm/2 for the split pair) */
+    double out_scale;                  /* 2^round(log2 q0 - (pow + 8))  (eval.go:369) */
+    const hec_pt *const *pt_idx;       /* cont.pl_idx */
+    int conv_flags;                    /* HEC_CONV_FUSED / HEC_CONV_OPLEVEL */
+    const hec_pt *pt_pre, *pt_shift2, *pt_post; /* monomial plaintexts (scale 1), each may be NULL */
+    double pow, alpha;                 /* 2^pow scale relabel and MulByPow2; leaky-ReLU slope */
+    int iter;                          /* halves to process: 2 for full packing, 1 otherwise */
+    const hec_btp_params *btp;         /* the bootstrapper chosen by log_sparse */
+    const hec_ptdiag *const *ctos_mats; int n_ctos;
+    const hec_ptdiag *const *stoc_mats; int n_stoc;
+    int move_kind;                     /* HEC_MOVE_* */
+    const hec_pt *keep_mask[2];        /* HEC_MOVE_KEEP: ext_idx mask per half */
+    int n_r[2]; const int *rots_r[2]; const hec_pt *const *pts_r[2]; /* r_idx / r_idx_l per half */
+    int n_m[2]; const int *rots_m[2]; const hec_pt *const *pts_m[2]; /* m_idx / m_idx_l per half (EXT_DOUBLE) */
+    double min_scale;                  /* params.Scale() */
+} hec_layer_args;
+int hec_conv_bn_relu(hec_ctx *pack_ctx, hec_ctx *ctx, const hec_ct *ct_input, const hec_layer_args *args, hec_ct **out);
+
 /* A prepared evalConv_BN for `batch` independent input ciphertexts per run: kernel
  * plaintexts, monomials, bias and keys stay resident; the kernel sequence is captured in a
  * CUDA graph.  in_level must be 1 (ECD_LV) in this build.  The plan keeps its own copies of the plaintexts

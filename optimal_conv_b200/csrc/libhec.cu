@@ -4,3 +4,4 @@
 #include "hec_poly.cu"
 #include "hec_lt.cu"
 #include "hec_encode.cu"
+#include "hec_layer.cu"

@@ -29,7 +29,7 @@ SYMBOLS = [
     "hec_ptdiag_upload", "hec_ptdiag_free", "hec_linear_transform", "hec_coeffs_to_slots", "hec_slots_to_coeffs", "hec_sub_sum", "hec_mod_up", "hec_bootstrap_ctos", "hec_bootstrap_stoc", "hec_bootstrapp", "hec_mult_by_int_and_add", "hec_evaluate_poly", "hec_evaluate_cheby", "hec_eval_relu", "hec_eval_relu_many", "hec_rotate_gal", "hec_rotate_new", "hec_rotate_hoisted", "hec_galois_for_rotation",
     "hec_ntt", "hec_keyswitch", "hec_moddown", "hec_conv_then_pack", "hec_conv_bl", "hec_ext_ctxt", "hec_keep_ctxt", "hec_plan_create", "hec_plan_run",
     "hec_plan_run_host", "hec_plan_submit_host", "hec_plan_wait", "hec_plan_span_begin", "hec_plan_span_end_ms",
-    "hec_plan_profile", "hec_plan_destroy", "hec_plan_cache_size", "hec_float_quotient_threshold",
+    "hec_plan_profile", "hec_plan_destroy", "hec_plan_cache_size", "hec_float_quotient_threshold", "hec_ext_double_ctxt", "hec_conv_bn_relu",
 ]
 
 
@@ -40,6 +40,22 @@ class BtpParams(C.Structure):
                 ("sin_type", C.c_int), ("sin_rescal", C.c_int), ("arcsine_deg", C.c_int),
                 ("sine_qi", C.POINTER(C.c_uint64)), ("n_sine_qi", C.c_int),
                 ("cheby", C.POINTER(C.c_double)), ("n_cheby", C.c_int), ("cheby_a", C.c_double), ("cheby_b", C.c_double)]
+
+
+class LayerArgs(C.Structure):
+    """hec_layer_args (include/hec.h)"""
+    _fields_ = [("n_conv", C.c_int), ("pt_ker", C.POINTER(C.c_void_p) * 2), ("pt_bias", C.c_void_p * 2),
+                ("max_ob", C.c_int), ("norm", C.c_int * 2), ("out_scale", C.c_double), ("pt_idx", C.POINTER(C.c_void_p)),
+                ("conv_flags", C.c_int), ("pt_pre", C.c_void_p), ("pt_shift2", C.c_void_p), ("pt_post", C.c_void_p),
+                ("pow", C.c_double), ("alpha", C.c_double), ("iter", C.c_int), ("btp", C.POINTER(BtpParams)),
+                ("ctos_mats", C.POINTER(C.c_void_p)), ("n_ctos", C.c_int), ("stoc_mats", C.POINTER(C.c_void_p)), ("n_stoc", C.c_int),
+                ("move_kind", C.c_int), ("keep_mask", C.c_void_p * 2),
+                ("n_r", C.c_int * 2), ("rots_r", C.POINTER(C.c_int) * 2), ("pts_r", C.POINTER(C.c_void_p) * 2),
+                ("n_m", C.c_int * 2), ("rots_m", C.POINTER(C.c_int) * 2), ("pts_m", C.POINTER(C.c_void_p) * 2),
+                ("min_scale", C.c_double)]
+
+
+MOVE_KEEP, MOVE_EXT, MOVE_EXT_DOUBLE = 0, 1, 2
 
 
 class HecError(RuntimeError):
@@ -144,6 +160,9 @@ def lib():
     L.hec_conv_bl.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp), vp, C.POINTER(vp)]
     L.hec_ext_ctxt.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int), C.POINTER(vp), C.c_int, C.c_double, C.POINTER(vp)]
     L.hec_keep_ctxt.argtypes = [vp, vp, vp, C.c_double, C.POINTER(vp)]
+    L.hec_ext_double_ctxt.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int), C.POINTER(vp), C.c_int, C.POINTER(C.c_int), C.POINTER(vp),
+                                      C.c_int, C.c_double, C.POINTER(vp)]
+    L.hec_conv_bn_relu.argtypes = [vp, vp, vp, C.POINTER(LayerArgs), C.POINTER(vp)]
     L.hec_plan_create.argtypes = [vp, C.POINTER(vp), C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(vp), vp,
                                   C.c_int, C.POINTER(vp)]
     L.hec_plan_run.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
@@ -531,6 +550,70 @@ class Context:
         """keep_ctxt (conv.go:417-431)."""
         h = vp()
         self._chk(self.L.hec_keep_ctxt(self.h, ct.h, mask.h, min_scale, C.byref(h)))
+        return Ciphertext(self, h)
+
+    def ext_double_ctxt(self, ct, m_idx, r_idx, min_scale=None):
+        """ext_double_ctxt (conv.go:374-414); min_scale=None: bsgs_ctxt (conv.go:303-344, no Rescale)."""
+        def arrs(d):
+            rots = list(d)
+            return len(rots), (C.c_int * len(rots))(*rots), (vp * len(rots))(*[d[r].h for r in rots])
+        nm, rm, pm = arrs(m_idx)
+        nr, rr, pr = arrs(r_idx)
+        h = vp()
+        self._chk(self.L.hec_ext_double_ctxt(self.h, ct.h, nm, rm, pm, nr, rr, pr, int(min_scale is not None),
+                                             float(min_scale or 0.0), C.byref(h)))
+        return Ciphertext(self, h)
+
+    def conv_bn_relu(self, pack_ctx, ct_input, *, pt_ker, pt_bias, norm, out_scale, pt_idx, pow, alpha, iter, btp, ctos_mats,
+                     stoc_mats, min_scale, keep_mask=None, r_idx=None, m_idx=None, pt_pre=None, pt_shift2=None, pt_post=None,
+                     conv_flags=CONV_FUSED):
+        """evalConv_BNRelu_new (eval.go:272-575) as one call.  self: the main evaluator; pack_ctx: the pack evaluator.
+        pt_ker / pt_bias / norm: lists of 1 or 2 convolutions; keep_mask: [Plaintext per half] (keep_ctxt), or
+        r_idx (and m_idx): [{rot: Plaintext} per half] (ext_ctxt / ext_double_ctxt)."""
+        a = LayerArgs()
+        keep = []
+        a.n_conv = len(pt_ker)
+        a.max_ob = len(pt_ker[0])
+        for k in range(a.n_conv):
+            arr = (vp * a.max_ob)(*[(p.h if p is not None else None) for p in pt_ker[k]])
+            keep.append(arr)
+            a.pt_ker[k] = C.cast(arr, C.POINTER(C.c_void_p))
+            a.pt_bias[k] = pt_bias[k].h if pt_bias[k] is not None else None
+            a.norm[k] = norm[k]
+        a.out_scale = out_scale
+        idx = (vp * len(pt_idx))(*[(p.h if p is not None else None) for p in pt_idx])
+        keep.append(idx)
+        a.pt_idx = C.cast(idx, C.POINTER(C.c_void_p))
+        a.conv_flags = conv_flags
+        a.pt_pre = pt_pre.h if pt_pre is not None else None
+        a.pt_shift2 = pt_shift2.h if pt_shift2 is not None else None
+        a.pt_post = pt_post.h if pt_post is not None else None
+        a.pow, a.alpha, a.iter, a.min_scale = pow, alpha, iter, min_scale
+        bp = self._btp_params(btp)
+        keep.append(bp)
+        a.btp = C.pointer(bp)
+        cm, sm = (vp * len(ctos_mats))(*ctos_mats), (vp * len(stoc_mats))(*stoc_mats)
+        keep += [cm, sm]
+        a.ctos_mats, a.n_ctos = C.cast(cm, C.POINTER(C.c_void_p)), len(ctos_mats)
+        a.stoc_mats, a.n_stoc = C.cast(sm, C.POINTER(C.c_void_p)), len(stoc_mats)
+        if keep_mask is not None:
+            a.move_kind = MOVE_KEEP
+            for ul, mk in enumerate(keep_mask):
+                a.keep_mask[ul] = mk.h if mk is not None else None
+        else:
+            a.move_kind = MOVE_EXT_DOUBLE if m_idx is not None else MOVE_EXT
+            for name, dicts in (("r", r_idx), ("m", m_idx)):
+                if dicts is None:
+                    continue
+                for ul, d in enumerate(dicts):
+                    rots = list(d)
+                    ra, pa = (C.c_int * len(rots))(*rots), (vp * len(rots))(*[d[r].h for r in rots])
+                    keep += [ra, pa]
+                    getattr(a, "n_" + name)[ul] = len(rots)
+                    getattr(a, "rots_" + name)[ul] = C.cast(ra, C.POINTER(C.c_int))
+                    getattr(a, "pts_" + name)[ul] = C.cast(pa, C.POINTER(C.c_void_p))
+        h = vp()
+        self._chk(self.L.hec_conv_bn_relu(pack_ctx.h, self.h, ct_input.h, C.byref(a), C.byref(h)))
         return Ciphertext(self, h)
 
     def plan_cache_size(self):

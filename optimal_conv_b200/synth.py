@@ -61,3 +61,61 @@ def conv_workload(Q, P, logN, B, seed, n_ct=1):
         j += 1
     w["keys"] = keys  # index i <-> galEl 2^(i+1)+1 (conv.go:255)
     return w
+
+
+# ---- seeded operands of the split bootstrapping: shared by the golden-vector generator, the
+# parity tests and bench.py.  The matrices are synthetic (uniform residues on chosen diagonals): their construction from
+# the DFT is the Go host's encoder and stays there; what matters to the evaluation is which diagonals are present.
+CTOS_SPECS = [(2, [0, 1, 2, 3, 5], 27), (2, [0, 1, 4, 6], 26), (4, [0, 1, 2, 5], 25), (2, [1, 2, 3], 24)]   # pDFTInv: (N1, diagonals, level)
+CTOS_FIELDS = {"prescale": 2.0 ** 47, "postscale": 2.0 ** 47, "sinescale": 2.0 ** 55, "sqrt2pi": 0.3989422804014327, "sc_fac": 4.0,
+               "message_ratio": 256.0, "sin_type": 1, "sin_rescal": 2, "params_scale": float(1 << 30)}
+BTP_STOC_SPECS = [(2, [0, 1, 2], 15), (2, [0, 1, 3], 14), (2, [1, 2], 13)]   # pDFT for the un-split Bootstrapp
+
+
+def dft_factor_specs(log_slots=15, depth=4, top_level=27):
+    """Diagonal patterns of the bootstrapper's REAL factor matrices: GenCoeffsToSlotsMatrix / GenSlotsToCoeffsMatrix
+    merge the log_slots radix-2 butterfly layers of the special FFT into `depth` factors (the reference's parameter sets
+    use CtSDepth = 4, StCDepth = 2-3; Appendix A).  A factor that merges m consecutive layers whose smallest butterfly
+    stride is 2^s has the 2^(m+1) - 1 diagonals j * 2^s, |j| < 2^m (indices modulo the slot count); N1 is the power of
+    two next to sqrt(#diagonals) (MaxN1N2Ratio = 16 permitting).  Returns [(n1, diagonals, level)], top level first."""
+    slots = 1 << log_slots
+    layers = [log_slots // depth + (1 if i < log_slots % depth else 0) for i in range(depth)]
+    specs, s = [], log_slots
+    for i, m in enumerate(layers):
+        s -= m
+        diags = sorted({(j << s) % slots for j in range(-(1 << m) + 1, 1 << m)})
+        n1 = 1
+        while n1 * n1 < len(diags):
+            n1 *= 2
+        specs.append((n1 << s if s else n1, diags, top_level - i))
+    return specs
+
+
+def ctos_operands(N, specs=None):
+    """seeded operands: the full 28 + 5 modulus chain of set 6, the CoeffsToSlots factor matrices `specs`
+    (default: four small ones at the top four levels; scale = the modulus they consume), a degree-63 Chebyshev sine
+    polynomial on [-25/4, 25/4], the keys of their rotations, the conjugation key, the relinearisation key"""
+    from . import params as PR
+    Q, P = PR.Q_SET6, PR.P_ALL
+    specs = CTOS_SPECS if specs is None else specs
+    beta = (len(Q) + len(P) - 1) // len(P)
+    key = lambda s: np.stack([np.stack([uniform_limbs(s + 10 * d + k, list(Q) + list(P), N) for k in range(2)]) for d in range(beta)])  # noqa: E731
+    rots = set()
+    for n1, diags, _ in specs:
+        rots |= {d % n1 for d in diags if d % n1} | {(d // n1) * n1 for d in diags if d // n1}
+    keys = {r: key(9000 + 131 * r) for r in sorted(rots)}
+    mats = []
+    for mi, (n1, diags, ml) in enumerate(specs):
+        D = {d: (uniform_limbs(7000 + 100 * mi + d, Q[:ml + 1], N), uniform_limbs(7500 + 100 * mi + d, P, N)) for d in diags}
+        mats.append((D, n1, ml, float(Q[ml])))
+    rng = np.random.default_rng(77)
+    coeffs = [float(x) for x in rng.uniform(-1, 1, 64)]
+    b = dict(CTOS_FIELDS, sine_qi=Q[16:24], cheby=(coeffs, -25.0 / 4, 25.0 / 4), mats=mats)
+    return keys, key(9900), key(8000), b
+
+
+def btp_stoc_mats(N):
+    from . import params as PR
+    Q, P = PR.Q_SET6, PR.P_ALL
+    return [({d: (uniform_limbs(7800 + 100 * mi + d, Q[:ml + 1], N), uniform_limbs(7900 + 100 * mi + d, P, N)) for d in diags},
+             n1, ml, float(Q[ml])) for mi, (n1, diags, ml) in enumerate(BTP_STOC_SPECS)]

@@ -734,9 +734,58 @@ class Oracle:
             res = t if res is None else self.add(res, t)
         return self.rescale(res, min_scale) if min_scale is not None else res
 
+    def ext_double_ctxt(self, ct, m_idx, r_idx, pt_scale, keys, min_scale):
+        """ext_double_ctxt (conv.go:374-414) / bsgs_ctxt (conv.go:303-344, which does not rescale: min_scale None):
+        mid = sum_rot RotateNew(MulNew(input, pt_rot), rot) over m_idx, result = the same over r_idx applied to mid."""
+        mid = self.ext_ctxt(ct, m_idx, pt_scale, keys)
+        return self.ext_ctxt(mid, r_idx, pt_scale, keys, min_scale)
+
+    def post_conv_bl(self, ct_in_rots, pts, pt_scale):
+        """postConv_BL (conv.go:146-178): sum_tap MulNew(ct_in_rots[tap], pl_tap)."""
+        res = None
+        for c, pt in zip(ct_in_rots, pts):
+            t = self.mul_pt(c, pt, pt_scale)
+            res = t if res is None else self.add(res, t)
+        return res
+
     def keep_ctxt(self, ct, mask, pt_scale, min_scale):
         """keep_ctxt (conv.go:417-431)."""
         return self.rescale(self.mul_pt(ct, mask, pt_scale), min_scale)
+
+    @staticmethod
+    def conv_bn_relu(op, o, ct_input, *, pt_ker, pt_bias, pt_scale, norm, out_scale, pt_idx, pack_keys, pow, alpha, iter, btp,
+                     keys, key_conj, rlk, stoc_mats, min_scale, keep_mask=None, keep_scale=None, r_idx=None, m_idx=None, mask_scale=None,
+                     pt_pre=None, pt_shift2=None, pt_post=None):
+        """evalConv_BNRelu_new (eval.go:272-575) composed from the pinned pieces, on the two evaluators (op: pack, o: main):
+        [x^offset] -> evalConv_BN once or twice (+ shift, Add) -> [x^offset] -> Scale *= 2^pow -> BootstrappConv_CtoS ->
+        evalReLU + MulByPow2 per half -> keep_ctxt / ext_ctxt / ext_double_ctxt per half -> BootstrappConv_StoC -> Rescale."""
+        cin = op.mul_pt(ct_input, pt_pre, 1.0) if pt_pre is not None else ct_input
+        convs = [op.conv_then_pack(cin, pt_ker[k], pt_scale, norm[k], out_scale, pt_idx, pack_keys, pt_bias[k])[0]
+                 for k in range(len(pt_ker))]
+        if len(convs) == 2:
+            c1 = op.mul_pt(convs[1], pt_shift2, 1.0) if pt_shift2 is not None else convs[1]
+            ct_conv = op.add(convs[0], c1)
+        else:
+            ct_conv = convs[0]
+        if pt_post is not None:
+            ct_conv = op.mul_pt(ct_conv, pt_post, 1.0)
+        ct_conv = Ct(ct_conv.c0, ct_conv.c1, ct_conv.scale * 2.0 ** pow)
+        b0, b1, _ = o.bootstrapp_conv_ctos(ct_conv, btp, keys, key_conj, rlk)
+        halves = [b0, b1][:iter]
+        kept = []
+        for ul, h in enumerate(halves):
+            if h is None:
+                kept.append(None)
+                continue
+            x = o.mul_by_pow2(o.eval_relu(h, alpha, rlk, min_scale), int(pow))
+            if keep_mask is not None:
+                kept.append(o.keep_ctxt(x, keep_mask[ul], keep_scale, min_scale))
+            elif m_idx is not None:
+                kept.append(o.ext_double_ctxt(x, m_idx[ul], r_idx[ul], mask_scale, keys, min_scale))
+            else:
+                kept.append(o.ext_ctxt(x, r_idx[ul], mask_scale, keys, min_scale))
+        res = o.slots_to_coeffs(kept[0], kept[1] if iter == 2 else None, stoc_mats, keys)
+        return o.rescale(res, min_scale)
 
     def monomial_pts(self):
         """pl_idx[i] = NTT(X^(2^i)) at level 0, scale 1 (conv.go:241-254)."""

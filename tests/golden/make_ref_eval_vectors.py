@@ -26,7 +26,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, HERE)
 
 import common  # noqa: E402
-from refmachine import CKKS, RING, RLWE, GoPanic, Machine, f2b  # noqa: E402
+from refmachine import CKKS, RING, RLWE, GoPanic, Machine, b2f, f2b  # noqa: E402
 from optimal_conv_b200 import params as PR, synth  # noqa: E402
 
 OUT = os.path.join(HERE, "ref_eval_vectors.json")
@@ -252,6 +252,102 @@ def pre_conv_bl_case(logN=8, in_wid=4, ker_wid=3):
     return rec
 
 
+# ---------------------------------------------------------------- between-layer helpers
+ENCODER_ITAB = "go.itab.*github.com/dwkim606/test_lattigo/ckks.encoderComplex128,github.com/dwkim606/test_lattigo/ckks.Encoder"
+HELPER_MASK_SEED = 4100
+
+
+def helper_mask(Q, N, level, n):
+    """the n-th plaintext the stubbed encoder hands out: seeded uniform residues (NTT domain)"""
+    return synth.uniform_limbs(HELPER_MASK_SEED + n, Q[:level + 1], N)
+
+
+def layer_helper_case(logN=5):
+    """main.ext_ctxt (conv.go:347-371), main.ext_double_ctxt (conv.go:374-414), main.keep_ctxt (conv.go:417-431) and
+    main.postConv_BL (conv.go:146-178), interpreted.  Slot encoding is outside the path (the Go host keeps it), so the
+    ckks.Encoder these routines call is a stub: EncodeNTT / Encode fill the plaintext the routine allocated
+    (ckks.NewPlaintext, interpreted) with seeded residues instead of the embedding of the mask; what is pinned is
+    the evaluator composition around it -- MulNew, RotateNew, Add in the reference's order, the plaintext scales
+    (q_level, sqrt(q_level), params.Scale()) and the closing Rescale."""
+    N, Q, P, level = 1 << logN, PR.Q_SET6[:3], PR.P_ALL[:2], 2
+    rots_a, rots_m, rots_r = [1, 3, 6], [2, 5], [4, 7, 9]
+    allrots = sorted(set(rots_a + rots_m + rots_r))
+    gal = {r: pow(5, r, 2 * N) for r in allrots}
+    m = Machine()
+    keys = {g: np.stack([np.stack([synth.uniform_limbs(9700 + 31 * r + 10 * d + k, list(Q) + list(P), N) for k in range(2)])
+                         for d in range((len(Q) + len(P) - 1) // len(P))]) for r, g in gal.items()}
+    params, ev = m.new_evaluator(logN, Q, P, PR.SCALE, keys)
+    count = [0]
+    scales = []
+
+    def fake_encode(em, ntt):
+        sp = em.r[4]
+        pt = em.rq(sp + 8)
+        poly = em.rq(em.rq(pt))
+        nl = em.rq(poly + 8)
+        limbs = helper_mask(Q, N, nl - 1, count[0])
+        rows = em.rq(poly)
+        for i in range(nl):
+            em.write_u64s(em.rq(rows + 24 * i), ints(limbs[i]))
+        if ntt:
+            em.wb(poly + 24, 1)
+        scales.append(b2f(em.rq(pt + 8)))
+        count[0] += 1
+
+    enc_t = CKKS + "(*encoderComplex128)."
+    m.hook(enc_t + "EncodeNTT", lambda em: fake_encode(em, True))
+    m.hook(enc_t + "Encode", lambda em: fake_encode(em, False))
+    m.hook(enc_t + "ToNTT", lambda em: em.wb(em.rq(em.rq(em.rq(em.r[4] + 8))) + 24, 1))
+    enc = [m.sym[ENCODER_ITAB][0], m.alloc(64)]
+    lim = lambda seed: [ints(l) for l in synth.uniform_limbs(seed, Q[:level + 1], N)]  # noqa: E731
+
+    def idx_map(rots):
+        h = m.new_map(24)
+        for r in rots:
+            m.map_put(h, r, m.slice_u64([1] * (N // 2)))
+        return h
+
+    rec = {"logN": logN, "Q": ["%x" % q for q in Q], "P": ["%x" % p for p in P], "level": level,
+           "galois": {str(r): g for r, g in gal.items()}, "mask_seed": HELPER_MASK_SEED}
+    # ext_ctxt(eval, encoder, input, r_idx, params)
+    ct = m.new_ct([lim(61), lim(62)], PR.SCALE)
+    count[0], scales[:] = 0, []
+    res = m.call("main.ext_ctxt", ev + enc + [ct, idx_map(rots_a)] + params + [0], max_steps=1 << 62)
+    rec["ext_ctxt"] = {"rots": rots_a, "pt_scales": list(scales), "out": digest_ct(m, res[-1])}
+    # ext_double_ctxt(eval, encoder, input, m_idx, r_idx, params)
+    count[0], scales[:] = 0, []
+    res = m.call("main.ext_double_ctxt", ev + enc + [ct, idx_map(rots_m), idx_map(rots_r)] + params + [0], max_steps=1 << 62)
+    rec["ext_double_ctxt"] = {"m_rots": rots_m, "r_rots": rots_r, "pt_scales": list(scales), "out": digest_ct(m, res[-1])}
+    # keep_ctxt(params, eval, encoder, input, idx)
+    count[0], scales[:] = 0, []
+    res = m.call("main.keep_ctxt", params + ev + enc + [ct] + m.slice_u64([1] * (N // 2)) + [0], max_steps=1 << 62)
+    rec["keep_ctxt"] = {"pt_scales": list(scales), "out": digest_ct(m, res[-1])}
+    # postConv_BL(param, encoder, evaluator, ct_in_rots, in_wid, ker_wid, rot, pad, max_ker_rs)
+    in_wid, ker_wid = 2, 3
+    max_batch = (N // 2) // (in_wid * in_wid)
+    cts = [m.new_ct([lim(70 + 2 * t), lim(71 + 2 * t)], PR.SCALE) for t in range(ker_wid * ker_wid)]
+
+    def fl4():   # [ker_wid][ker_wid][max_batch][max_batch]float64 of ones
+        def sl(ptrs_or_vals, leaf):
+            a = m.alloc(8 * max(1, len(ptrs_or_vals)) * (1 if leaf else 3))
+            if leaf:
+                m.write_u64s(a, ptrs_or_vals)
+            else:
+                for i, h in enumerate(ptrs_or_vals):
+                    m.write_u64s(a + 24 * i, h)
+            return [a, len(ptrs_or_vals), len(ptrs_or_vals)]
+        one = f2b(1.0)
+        return sl([sl([sl([sl([one] * max_batch, True) for _ in range(max_batch)], False) for _ in range(ker_wid)], False)
+                   for _ in range(ker_wid)], False)
+
+    count[0], scales[:] = 0, []
+    res = m.call("main.postConv_BL", params + enc + ev + m.slice_u64(cts) + [in_wid, ker_wid, 1, 0] + fl4() + [0], max_steps=1 << 62)
+    rec["post_conv_bl"] = {"in_wid": in_wid, "ker_wid": ker_wid, "pt_scales": list(scales), "out": digest_ct(m, res[-1])}
+    rec["interpreted_instructions"] = m.steps
+    print("layer-helper case: %d instructions" % m.steps, flush=True)
+    return rec
+
+
 # ---------------------------------------------------------------- evalReLU (SURVEY 8f rank 2)
 RELU_CASES = [("n5_alpha0", 5, 0.0, 15), ("n6_leaky0.1", 6, 0.1, 15), ("n5_level12", 5, 0.0, 12), ("n5_level8_too_low", 5, 0.0, 8)]
 
@@ -425,39 +521,9 @@ def dft_case():
 
 
 # ---------------------------------------------------------------- BootstrappConv_CtoS (first half of the split bootstrapping)
-CTOS_SPECS = [(2, [0, 1, 2, 3, 5], 27), (2, [0, 1, 4, 6], 26), (4, [0, 1, 2, 5], 25), (2, [1, 2, 3], 24)]   # pDFTInv: (N1, diagonals, level)
+CTOS_SPECS, CTOS_FIELDS, BTP_STOC_SPECS = synth.CTOS_SPECS, synth.CTOS_FIELDS, synth.BTP_STOC_SPECS
 CTOS_LOGN = 4
-CTOS_FIELDS = {"prescale": 2.0 ** 47, "postscale": 2.0 ** 47, "sinescale": 2.0 ** 55, "sqrt2pi": 0.3989422804014327, "sc_fac": 4.0,
-               "message_ratio": 256.0, "sin_type": 1, "sin_rescal": 2, "params_scale": PR.SCALE}
-
-
-def ctos_operands(N):
-    """seeded operands: the full 28 + 5 modulus chain of set 6, four CoeffsToSlots factor matrices at the top four levels
-    (scale = the modulus they consume), a degree-63 Chebyshev sine polynomial on [-25/4, 25/4], the keys"""
-    Q, P = PR.Q_SET6, PR.P_ALL
-    beta = (len(Q) + len(P) - 1) // len(P)
-    key = lambda s: np.stack([np.stack([synth.uniform_limbs(s + 10 * d + k, list(Q) + list(P), N) for k in range(2)]) for d in range(beta)])  # noqa: E731
-    rots = set()
-    for n1, diags, _ in CTOS_SPECS:
-        rots |= {d % n1 for d in diags if d % n1} | {(d // n1) * n1 for d in diags if d // n1}
-    keys = {r: key(9000 + 131 * r) for r in sorted(rots)}
-    mats = []
-    for mi, (n1, diags, ml) in enumerate(CTOS_SPECS):
-        D = {d: (synth.uniform_limbs(7000 + 100 * mi + d, Q[:ml + 1], N), synth.uniform_limbs(7500 + 100 * mi + d, P, N)) for d in diags}
-        mats.append((D, n1, ml, float(Q[ml])))
-    rng = np.random.default_rng(77)
-    coeffs = [float(x) for x in rng.uniform(-1, 1, 64)]
-    b = dict(CTOS_FIELDS, sine_qi=Q[16:24], cheby=(coeffs, -25.0 / 4, 25.0 / 4), mats=mats)
-    return keys, key(9900), key(8000), b
-
-
-BTP_STOC_SPECS = [(2, [0, 1, 2], 15), (2, [0, 1, 3], 14), (2, [1, 2], 13)]   # pDFT for the un-split Bootstrapp
-
-
-def btp_stoc_mats(N):
-    Q, P = PR.Q_SET6, PR.P_ALL
-    return [({d: (synth.uniform_limbs(7800 + 100 * mi + d, Q[:ml + 1], N), synth.uniform_limbs(7900 + 100 * mi + d, P, N)) for d in diags},
-             n1, ml, float(Q[ml])) for mi, (n1, diags, ml) in enumerate(BTP_STOC_SPECS)]
+ctos_operands, btp_stoc_mats = synth.ctos_operands, synth.btp_stoc_mats   # seeded operands live in the package (bench.py uses them too)
 
 
 def ctos_case(level_in, whole=False):
@@ -674,10 +740,12 @@ def main():
         new["conv"] = {name: conv_case(logN, B, norm, seed, out_scale, Q2, P1)
                        for name, logN, B, norm, seed, out_scale, Q2, P1 in SMALL_CONV if name in sys.argv}
     else:
-        ALL = ("relu", "evalops", "lt", "ctos", "btp", "ring", "conv", "encode", "hostprep")
+        ALL = ("relu", "evalops", "lt", "ctos", "btp", "ring", "conv", "encode", "hostprep", "helpers")
         groups = [g for g in ALL if "--" + g in sys.argv] or list(ALL)
         if "hostprep" in groups:
             new["hostprep"] = hostprep_case()
+        if "helpers" in groups:
+            new["layer_helpers"] = layer_helper_case()
         if "encode" in groups:
             new["encode_coeffs"] = {name: encode_case(name) for name in common.ENCODE_CASES}
         if "relu" in groups:

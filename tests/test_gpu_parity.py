@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import common
-import hostprep as hp
+from optimal_conv_b200 import hostprep as hp
 from optimal_conv_b200 import hec, params as PR, synth
 from oracle.orc import Ct, Oracle
 
@@ -546,6 +546,79 @@ def test_layer_pipeline_conv_ctos_relu_keep_stoc(idx_np):
     finally:
         c.close()
         cp.close()
+
+
+@pytest.mark.parametrize("kind", ["Conv", "StrConv_sparse"])
+def test_conv_bn_relu_one_call_matches_oracle(idx_np, kind):
+    """hec_conv_bn_relu = evalConv_BNRelu_new (eval.go:272-575) as ONE entry point over the two evaluators, against the
+    oracle's composition of the pinned pieces.
+    "Conv": one convolution, both halves through keep_ctxt (eval.go:531-537).
+    "StrConv_sparse": two convolutions on kernels split by output parity with norm/2, the second shifted by a monomial,
+    added, a closing monomial product (eval.go:347-397), both halves through ext_double_ctxt (eval.go:499-509)."""
+    Q, P = PR.Q_SET6, PR.P_ALL
+    cp, op_ = hec.Context(PR.LOGN, Q2, P1), Oracle(PR.LOGN, Q2, P1)
+    c, o = hec.Context(PR.LOGN, Q, P), Oracle(PR.LOGN, Q, P)
+    try:
+        B, pow2, two = 4, 5, kind == "StrConv_sparse"
+        w = common.workload({"B": B, "seed": 93})
+        w2 = common.workload({"B": B, "seed": 94})
+        out_scale = PR.SCALE
+        Gc = common.GpuConv(cp, w, idx_np, 2 if two else 1, out_scale)
+        ker2 = [cp.upload_pt(w2["pt_ker"][i], PR.SCALE) if i % 2 == 0 else None for i in range(B)]
+        bias2 = cp.upload_pt(w2["bias"][None, :], out_scale)
+        mono = lambda k: (orc_mono(op_, k, 0), cp.upload_pt(orc_mono(op_, k, 0), 1.0))  # noqa: E731
+        keys, kconj, rlk, b = synth.ctos_operands(N)
+        mrots, rrots = [1, 2], [4, 1]
+        for r in set(mrots + rrots) - set(keys):
+            keys[r] = np.stack([np.stack([synth.uniform_limbs(9000 + 131 * r + 10 * d + k, Q + P, N) for k in range(2)])
+                                for d in range(o.beta_full)])
+        for r, k in keys.items():
+            c.upload_swk(c.galois_for_rotation(r), k, 27)
+        c.upload_swk(2 * N - 1, kconj, 27)
+        c.upload_rlk(rlk, 27)
+        pdftinv = [c.upload_ptdiag(PR.LOGN - 1, n1, ml, ms, D) for D, n1, ml, ms in b["mats"]]
+        stoc_specs = [(2, [0, 1, 2], 3), (2, [0, 1, 3], 2)]
+        stoc = [({d: (synth.uniform_limbs(7800 + 100 * i + d, Q[:ml + 1], N), synth.uniform_limbs(7900 + 100 * i + d, P, N)) for d in diags},
+                 n1, ml, float(Q[ml])) for i, (n1, diags, ml) in enumerate(stoc_specs)]
+        pdft = [c.upload_ptdiag(PR.LOGN - 1, n1, ml, ms, D) for D, n1, ml, ms in stoc]
+        lv = 4                                                         # level of the halves after evalReLU
+        common_kw = dict(out_scale=out_scale, pow=float(pow2), alpha=0.0, iter=2, min_scale=PR.SCALE)
+        if not two:
+            masks = [synth.uniform_limbs(97 + ul, Q[:lv + 1], N) for ul in range(2)]
+            out = c.conv_bn_relu(cp, Gc.cts[0], pt_ker=[Gc.ker], pt_bias=[Gc.bias], norm=[1], pt_idx=Gc.idx, btp=b, ctos_mats=pdftinv,
+                                 stoc_mats=pdft, keep_mask=[c.upload_pt(m, float(Q[lv])) for m in masks], **common_kw)
+            ref = Oracle.conv_bn_relu(op_, o, Ct(*w["ct"][0], PR.SCALE), pt_ker=[w["pt_ker"]], pt_bias=[w["bias"]], pt_scale=PR.SCALE,
+                                      norm=[1], pt_idx=idx_np, pack_keys=w["keys"], btp=b, keys=keys, key_conj=kconj, rlk=rlk,
+                                      stoc_mats=stoc, keep_mask=masks, keep_scale=float(Q[lv]), **common_kw)
+        else:
+            (sh_np, sh), (post_np, post) = mono(3), mono(7)
+            sq = float(np.sqrt(np.float64(Q[lv])))
+            mk = lambda seed, rots: {r: synth.uniform_limbs(seed + r, Q[:lv + 1], N) for r in rots}  # noqa: E731
+            m_np, r_np = [mk(300 + 50 * ul, mrots) for ul in range(2)], [mk(400 + 50 * ul, rrots) for ul in range(2)]
+            up = lambda d: {r: c.upload_pt(v, sq) for r, v in d.items()}  # noqa: E731
+            out = c.conv_bn_relu(cp, Gc.cts[0], pt_ker=[Gc.ker, ker2], pt_bias=[Gc.bias, bias2], norm=[2, 2], pt_idx=Gc.idx, btp=b,
+                                 ctos_mats=pdftinv, stoc_mats=pdft, m_idx=[up(d) for d in m_np], r_idx=[up(d) for d in r_np],
+                                 pt_shift2=sh, pt_post=post, **common_kw)
+            ref = Oracle.conv_bn_relu(op_, o, Ct(*w["ct"][0], PR.SCALE), pt_ker=[w["pt_ker"], w2["pt_ker"]], pt_bias=[w["bias"], w2["bias"]],
+                                      pt_scale=PR.SCALE, norm=[2, 2], pt_idx=idx_np, pack_keys=w["keys"], btp=b, keys=keys, key_conj=kconj,
+                                      rlk=rlk, stoc_mats=stoc, m_idx=m_np, r_idx=r_np, mask_scale=sq, pt_shift2=sh_np, pt_post=post_np,
+                                      **common_kw)
+        g0, g1 = out.download()
+        assert out.level == ref.level and out.scale == ref.scale
+        assert np.array_equal(g0, ref.c0) and np.array_equal(g1, ref.c1)
+    finally:
+        c.close()
+        cp.close()
+
+
+def orc_mono(o, k, level):
+    """NTT of the monomial x^k at limbs 0..level (EncodeCoeffs of a unit vector + ToNTT, scale 1; eval.go:318-330, 372-397)"""
+    out = np.empty((level + 1, N), dtype=np.uint64)
+    for l in range(level + 1):
+        m = np.zeros(N, dtype=np.uint64)
+        m[k] = 1
+        out[l] = o.ntt(m, l)
+    return out
 
 
 # ---------------------------------------------------------------- the conv path

@@ -8,7 +8,7 @@ import random
 import numpy as np
 import pytest
 
-import hostprep as hp
+from optimal_conv_b200 import hostprep as hp
 from optimal_conv_b200 import params as PR
 from optimal_conv_b200 import synth
 from oracle.orc import Ct, Oracle, lib

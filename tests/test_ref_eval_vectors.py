@@ -124,6 +124,51 @@ def test_baseline_path_evaluator_ops_match_reference_code(name):
         assert r2.level == level - 2 and dg(r2) == rec["rescale2"]
 
 
+def helper_operands(rec):
+    """operands of tests/golden/make_ref_eval_vectors.py::layer_helper_case, regenerated from their seeds"""
+    Q, P = mods(rec)
+    N, level = 1 << rec["logN"], rec["level"]
+    o = Oracle(rec["logN"], Q, P)
+    keys = {int(r): np.stack([np.stack([synth.uniform_limbs(9700 + 31 * int(r) + 10 * d + k, Q + P, N) for k in range(2)])
+                              for d in range(o.beta_full)]) for r in rec["galois"]}
+    lim = lambda seed: synth.uniform_limbs(seed, Q[:level + 1], N)  # noqa: E731
+    mask = lambda n, lv=level: synth.uniform_limbs(rec["mask_seed"] + n, Q[:lv + 1], N)  # noqa: E731
+    return o, Q, N, level, keys, lim, mask
+
+
+def test_between_layer_helpers_match_reference_main_code():
+    """main.ext_ctxt, main.ext_double_ctxt, main.keep_ctxt (conv.go:347-431) and main.postConv_BL (conv.go:146-178),
+    interpreted from the reference binary with a stub encoder (slot encoding is outside the path: the n-th
+    plaintext it hands out is a seeded vector), == the oracle's compositions: the MulNew / RotateNew / Add order,
+    the plaintext scales the routines choose (q_level, sqrt(q_level), params.Scale()) and the closing Rescale"""
+    rec = REF["layer_helpers"]
+    o, Q, N, level, keys, lim, mask = helper_operands(rec)
+    ct = Ct(lim(61), lim(62), PR.SCALE)
+    assert {int(r): g for r, g in rec["galois"].items()} == {int(r): o.galois_for_rotation(int(r)) for r in rec["galois"]}
+    # ext_ctxt: masks are handed out in the order the reference walks the map (the interpreter iterates sorted keys)
+    e = rec["ext_ctxt"]
+    assert e["pt_scales"] == [float(Q[level])] * len(e["rots"])
+    r_idx = {r: mask(n) for n, r in enumerate(sorted(e["rots"]))}
+    assert dg(o.ext_ctxt(ct, r_idx, float(Q[level]), keys, PR.SCALE)) == e["out"]
+    # ext_double_ctxt: both stages use sqrt(q_level) as plaintext scale, one Rescale at the end
+    e = rec["ext_double_ctxt"]
+    sq = float(np.sqrt(np.float64(Q[level])))
+    assert e["pt_scales"] == [sq] * (len(e["m_rots"]) + len(e["r_rots"]))
+    m_idx = {r: mask(n) for n, r in enumerate(sorted(e["m_rots"]))}
+    r_idx = {r: mask(len(m_idx) + n) for n, r in enumerate(sorted(e["r_rots"]))}
+    assert dg(o.ext_double_ctxt(ct, m_idx, r_idx, sq, keys, PR.SCALE)) == e["out"]
+    # keep_ctxt
+    e = rec["keep_ctxt"]
+    assert e["pt_scales"] == [float(Q[level])]
+    assert dg(o.keep_ctxt(ct, mask(0), float(Q[level]), PR.SCALE)) == e["out"]
+    # postConv_BL: k^2 taps, plaintexts at params.Scale(), no rescale
+    e = rec["post_conv_bl"]
+    k2 = e["ker_wid"] ** 2
+    assert e["pt_scales"] == [PR.SCALE] * k2
+    cts = [Ct(lim(70 + 2 * t), lim(71 + 2 * t), PR.SCALE) for t in range(k2)]
+    assert dg(o.post_conv_bl(cts, [mask(t) for t in range(k2)], PR.SCALE)) == e["out"]
+
+
 def test_pre_conv_bl_matches_reference_main_code():
     """main.preConv_BL (conv.go:120-143), interpreted: the k^2 hoisted rotations i*in_wid + j (negative steps and
     the zero step included) of the baseline convolution == the oracle's rotations, in the reference's order"""

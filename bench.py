@@ -249,6 +249,40 @@ def run_side_workload(args):
     from optimal_conv_b200 import hec
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    if args.workload == "resnet20":
+        # BASELINE.json configs[4]: the 20-layer chain of `resnet 3 20 1` (test.go:76-366), one hec_conv_bn_relu per layer.
+        # Keys, masks and bootstrapper matrices are synthetic with the real supports (optimal_conv_b200/resnet.py): this
+        # measures time and memory of a real inference; logits need the Go host's secret key.
+        from optimal_conv_b200 import resnet
+        free0, total = torch.cuda.mem_get_info()
+        net = resnet.Resnet(hec, depth=20, ker_wid=args.ker, log=lambda *a: print(*a, file=sys.stderr))
+        free1, _ = torch.cuda.mem_get_info()
+        image = np.random.default_rng(5).uniform(0, 1, 32 * 32 * 3)
+        recs, peak = [], 0
+        for it in range(args.warmup + args.steps):
+            ct, rec = net.run(image, seed=it)
+            peak = max(peak, total - torch.cuda.mem_get_info()[0])
+            g0, g1 = ct.download()
+            ct.free()
+            if it >= args.warmup:
+                recs.append(rec)
+        import hashlib
+        dig = hashlib.sha256(g0.tobytes() + g1.tobytes()).hexdigest()[:16]
+        per = [{"layer": recs[0][i]["layer"], "kind": recs[0][i]["kind"], "conv": recs[0][i]["conv"], "level_out": recs[0][i]["level_out"],
+                "eval_ms": statistics.median(r[i]["eval_ms"] for r in recs), "prep_ms": statistics.median(r[i]["prep_ms"] for r in recs)}
+               for i in range(len(recs[0]))]
+        tot_eval, tot_prep = sum(p["eval_ms"] for p in per), sum(p["prep_ms"] for p in per)
+        line = {"metric": "encrypted ResNet-20 inferences/sec (resnet 3 20 1 layer chain, N=2^16, synthetic keys and matrices with the real supports)",
+                "value": 1e3 / (tot_eval + tot_prep), "unit": "images/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": tot_eval + tot_prep, "higher_is_better": True, "dtype": "u64", "data": "synthetic",
+                "config": {"workload": "resnet20_k%d" % args.ker, "layers": len(per)},
+                "eval_ms_total": tot_eval, "host_prep_ms_total": tot_prep, "layers": per,
+                "hbm_bytes": {"resident_after_setup": int(free0 - free1), "peak_during_run": int(peak), "device_total": int(total)},
+                "setup_s": net.setup_s, "rotation_keys_uploaded": len(net.have), "final_ciphertext_sha256": dig,
+                "note": "per layer: host_prep = prep_Ker float reshaping + device EncodeCoeffs/ToNTT; eval = one hec_conv_bn_relu call"}
+        net.close()
+        print(json.dumps(line))
+        return
     if args.workload == "keyswitch":
         Q, P, level = PR.Q_SET6, PR.P_ALL, 27
         ctx = hec.Context(PR.LOGN, Q, P)
@@ -432,7 +466,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="B: output channels packed per ciphertext")
     ap.add_argument("--ker", type=int, default=3, help="kernel width k (only changes the work of --workload conv_bl)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="conv", choices=["conv", "conv_bl", "keyswitch", "mul_relin", "eval_relu", "bootstrap_ctos", "prep_ker"],
+    ap.add_argument("--workload", default="conv", choices=["conv", "conv_bl", "keyswitch", "mul_relin", "eval_relu", "bootstrap_ctos", "prep_ker", "resnet20"],
                     help="conv = the headline fused path; the others are op-level side measurements")
     ap.add_argument("--cpu-sample", type=int, default=12, help="convs timed for cpu_baseline (0 = skip)")
     ap.add_argument("--ring", type=int, default=8, help="distinct input batches rotated through (> L2)")

@@ -181,7 +181,9 @@ int hec_launch_ntt(hec_ctx *c, std::vector<LimbJob> &jobs, bool inverse) {
         A[i].out = mid;              // first pass: in -> mid (prologue, if any)
         A[i].flags = inverse ? 0 : (j.flags & HEC_LJ_PRO);
         B[i].in = mid;               // second pass: mid -> out (epilogue, if any)
-        B[i].flags = inverse ? 0 : (j.flags & HEC_LJ_EPI);
+        B[i].flags = inverse ? 0 : (j.flags & (HEC_LJ_EPI | HEC_LJ_ADD));
+        A[i].scatter_g = 0;
+        if (inverse) B[i].scatter_g = 0;
     }
     char *dbuf = nullptr;
     int rc = stage_cached(c, h, &dbuf);
@@ -223,8 +225,8 @@ static EwJob ewjob(const u64 *a, const u64 *b, u64 *out, int mod, u64 s0 = 0, u3
 
 // device copy of a small host table, cached by content (hec_ctx::staged).  The tables hold buffer addresses, which
 // repeat as long as the caller repeats the operation on the same ciphertexts / scratch layout.
-#define HEC_STAGE_CAP ((size_t)64 << 20)
-#define HEC_STAGE_SLAB ((size_t)4 << 20)
+#define HEC_STAGE_CAP ((size_t)1 << 30) // a network layer chain stages thousands of distinct tables; starting over costs a device sync
+#define HEC_STAGE_SLAB ((size_t)16 << 20)
 static int stage_cached(hec_ctx *c, std::vector<char> &h, char **dev) {
     h.resize((h.size() + 7) & ~(size_t)7, 0);
     uint64_t k = 1469598103934665603ull;
@@ -851,7 +853,14 @@ extern "C" int hec_add_pt(hec_ctx *c, hec_ct *ct, const hec_pt *pt) {
 
 // ModDownSplitNTTPQ (L:ring/ring_basis_extension.go:247-291), in place on accQ[i] ([L][N]);
 // accP[i] is [nP][N].  Scratch: L limbs per item.
-static int moddown_many(hec_ctx *c, int level, const std::vector<u64 *> &accQ, const std::vector<u64 *> &accP) {
+// addQ (optional): per item a polynomial [L][N] added to the result (the "+ c0" of a rotation, L:ckks/evaluator.go:1590)
+// outQ (optional): per item where the result goes instead of accQ (may be the same polynomial as addQ: each thread
+// reads its element before it writes it)
+// galQ (optional, with outQ pointing elsewhere than accQ / addQ): per item a Galois element g; the result is stored as
+// sigma_g of itself (PermuteNTTWithIndexLvl folded into the last pass)
+static int moddown_many(hec_ctx *c, int level, const std::vector<u64 *> &accQ, const std::vector<u64 *> &accP,
+                        const std::vector<const u64 *> &addQ = {}, const std::vector<u64 *> &outQ = {},
+                        const std::vector<u64> &galQ = {}) {
     int L = level + 1, nP = c->nP, rc;
     size_t n = accQ.size();
     std::vector<LimbJob> nj;
@@ -867,7 +876,15 @@ static int moddown_many(hec_ctx *c, int level, const std::vector<u64 *> &accQ, c
             u64 *aq = accQ[i] + (size_t)l * HEC_N;
             mj.push_back(modup_job(c, c->pq, accP[i], HEC_N, c->modQ(l), xi));
             // NTT(xi), then (xi + 2q - accQ) * (-P^-1) in the transform's epilogue (was a separate EW_SUBMUL pass)
-            nj.push_back({xi, aq, l, HEC_LJ_EPI, xi, aq, c->negpinv[l], 0});
+            const u64 *add = (i < addQ.size() && addQ[i]) ? addQ[i] + (size_t)l * HEC_N : nullptr;
+            u64 *dst = (i < outQ.size() && outQ[i]) ? outQ[i] + (size_t)l * HEC_N : aq;
+            u32 sg = 0;
+            if (i < galQ.size() && galQ[i]) { // g^-1 mod 2N: g is odd, 2N a power of two (Newton)
+                u64 g = galQ[i], inv = g;
+                for (int it = 0; it < 6; it++) inv *= 2 - g * inv;
+                sg = (u32)(inv & (2ull * HEC_N - 1));
+            }
+            nj.push_back({xi, dst, l, HEC_LJ_EPI | (add ? HEC_LJ_ADD : 0), xi, aq, c->negpinv[l], 0, add, sg});
         }
     if ((rc = launch_modup(c, mj))) return rc;
     return hec_launch_ntt(c, nj, false);
@@ -989,17 +1006,28 @@ static int ks_mac_many(hec_ctx *c, int level, const std::vector<Decomp> &dc, con
     (void)rc;
     return launch_dot(c, specs);
 }
+// add0 / add1 (optional): per item a polynomial added to d0 / d1, fused into the mod-down's last pass; acc_out
+// (optional, with both): the sums go to add0 / add1 themselves (out += SwitchKeys(.), the relinearisation)
+// out0 / out1 + gal (optional): the results go there, stored through the automorphism of gal[i] (a rotation's tail)
 static int keyswitch_many(hec_ctx *c, int level, const std::vector<Decomp> &dc, const std::vector<const SwKey *> &key,
-                          const std::vector<u64 *> &d0, const std::vector<u64 *> &d1) {
+                          const std::vector<u64 *> &d0, const std::vector<u64 *> &d1, const std::vector<const u64 *> &add0 = {},
+                          const std::vector<const u64 *> &add1 = {}, bool acc_out = false, const std::vector<u64 *> &out0 = {},
+                          const std::vector<u64 *> &out1 = {}, const std::vector<u64> &gal = {}) {
     int nP = c->nP, rc;
-    std::vector<u64 *> accQ, accP;
+    std::vector<u64 *> accQ, accP, outQ;
+    std::vector<const u64 *> addQ;
+    std::vector<u64> galQ;
     for (size_t i = 0; i < key.size(); i++) {
         u64 *ap = c->scratch(2 * (size_t)nP);
         accQ.push_back(d0[i]); accP.push_back(ap);
         accQ.push_back(d1[i]); accP.push_back(ap + (size_t)nP * HEC_N);
+        addQ.push_back(i < add0.size() ? add0[i] : nullptr);
+        addQ.push_back(i < add1.size() ? add1[i] : nullptr);
+        if (acc_out) { outQ.push_back(const_cast<u64 *>(add0[i])); outQ.push_back(const_cast<u64 *>(add1[i])); }
+        else if (!out0.empty()) { outQ.push_back(out0[i]); outQ.push_back(out1[i]); galQ.push_back(gal[i]); galQ.push_back(gal[i]); }
     }
     if ((rc = ks_mac_many(c, level, dc, key, accQ, accP))) return rc;
-    return moddown_many(c, level, accQ, accP);
+    return moddown_many(c, level, accQ, accP, addQ, outQ, galQ);
 }
 static size_t ks_limbs(const hec_ctx *c, int level) { return 2 * c->nP + 2 * (size_t)(level + 1); } // per item, after decompose
 
@@ -1007,14 +1035,12 @@ static size_t ks_limbs(const hec_ctx *c, int level) { return 2 * c->nP + 2 * (si
 static int finish_rotations(hec_ctx *c, int level, const std::vector<const hec_ct *> &ct, const std::vector<u64> &galEl,
                             const std::vector<u64 *> &d0, const std::vector<u64 *> &d1, const std::vector<hec_ct *> &out) {
     int L = level + 1, rc;
-    std::vector<EwJob> add, perm;
+    std::vector<EwJob> perm; // d0 already carries + c0 (added in the mod-down's last pass, keyswitch_many add0)
     for (size_t i = 0; i < ct.size(); i++)
         for (int l = 0; l < L; l++) {
-            add.push_back(ewjob(d0[i] + (size_t)l * HEC_N, ct[i]->limb(0, l), d0[i] + (size_t)l * HEC_N, l));
             perm.push_back(ewjob(d0[i] + (size_t)l * HEC_N, nullptr, out[i]->limb(0, l), l, 0, (u32)galEl[i]));
             perm.push_back(ewjob(d1[i] + (size_t)l * HEC_N, nullptr, out[i]->limb(1, l), l, 0, (u32)galEl[i]));
         }
-    if ((rc = launch_ew<EW_ADD>(c, add))) return rc;
     if ((rc = launch_ew<EW_PERMUTE>(c, perm))) return rc;
     for (size_t i = 0; i < ct.size(); i++) { out[i]->level = level; out[i]->scale = ct[i]->scale; }
     return HEC_OK;
@@ -1043,7 +1069,21 @@ int hec_rotate_many(hec_ctx *c, const std::vector<const hec_ct *> &ct, const std
     for (size_t i = 0; i < ndec; i++) c1.push_back(ct[i]->limb(1, 0));
     std::vector<Decomp> dc;
     if ((rc = decompose_many(c, level, c1, dc))) return rc;
-    if ((rc = keyswitch_many(c, level, dc, keys, d0, d1))) return rc;
+    std::vector<const u64 *> c0(n);
+    bool alias = false; // RotateGal(ct, g, ct): the input's c0 is still being read while outputs land -> keep the gather pass
+    for (size_t i = 0; i < n; i++) {
+        c0[i] = ct[i]->limb(0, 0); // limbs of one polynomial are contiguous ([alloc][N])
+        for (size_t k = 0; k < n; k++) alias = alias || out[i]->buf == ct[k]->buf;
+    }
+    static const int scatter = getenv("HEC_ROT_SCATTER") ? atoi(getenv("HEC_ROT_SCATTER")) : 1;
+    if (scatter && !alias) {
+        std::vector<u64 *> o0(n), o1(n);
+        for (size_t i = 0; i < n; i++) { o0[i] = out[i]->limb(0, 0); o1[i] = out[i]->limb(1, 0); }
+        if ((rc = keyswitch_many(c, level, dc, keys, d0, d1, c0, {}, false, o0, o1, galEl))) return rc;
+        for (size_t i = 0; i < n; i++) { out[i]->level = level; out[i]->scale = ct[i]->scale; }
+        return HEC_OK;
+    }
+    if ((rc = keyswitch_many(c, level, dc, keys, d0, d1, c0))) return rc;
     return finish_rotations(c, level, ct, galEl, d0, d1, out);
 }
 
@@ -1086,14 +1126,10 @@ int hec_mul_relin_many(hec_ctx *c, const std::vector<const hec_ct *> &a, const s
     std::vector<Decomp> dc;
     if ((rc = decompose_many(c, level, src, dc))) return bail(rc);
     std::vector<const SwKey *> keys(n, &it->second);
-    if ((rc = keyswitch_many(c, level, dc, keys, d0, d1))) return bail(rc);
-    std::vector<EwJob> add;
-    for (size_t m = 0; m < n; m++)
-        for (int i = 0; i < L; i++) {
-            add.push_back(ewjob(out[m]->limb(0, i), d0[m] + (size_t)i * HEC_N, out[m]->limb(0, i), i));
-            add.push_back(ewjob(out[m]->limb(1, i), d1[m] + (size_t)i * HEC_N, out[m]->limb(1, i), i));
-        }
-    if ((rc = launch_ew<EW_ADD>(c, add))) return bail(rc);
+    // (c0, c1) += SwitchKeys(c2, rlk): the sums are formed in the last pass of the mod-down, straight into the output
+    std::vector<const u64 *> o0(n), o1(n);
+    for (size_t m = 0; m < n; m++) { o0[m] = out[m]->limb(0, 0); o1[m] = out[m]->limb(1, 0); }
+    if ((rc = keyswitch_many(c, level, dc, keys, d0, d1, o0, o1, true))) return bail(rc);
     return HEC_OK;
 }
 extern "C" int hec_mul_relin_new(hec_ctx *c, const hec_ct *a, const hec_ct *b, hec_ct **out) {

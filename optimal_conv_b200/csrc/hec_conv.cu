@@ -252,8 +252,11 @@ struct hec_plan {
     hec_ctx *c = nullptr;
     int B = 0, norm = 1, na = 0, M = 0, levels = 0;
     double in_scale = 0, out_scale = 0;
-    const u64 **d_ctin = nullptr, **d_ptk = nullptr;
-    u64 *ptk_scaled = nullptr; // [na][2][N]: kernel plaintexts with the MultByConst constant folded in
+    const u64 **d_ctin = nullptr;
+    const ulonglong2 **d_ptk = nullptr;
+    u64 *ptk_scaled = nullptr;        // [na][2][N]: kernel plaintexts with the MultByConst constant folded in (set-up only)
+    ulonglong2 *ptk_pairs = nullptr;  // the same as Shoup pairs: what the kernels read
+    ulonglong2 *key_pairs = nullptr;  // [levels][2 polys][Q limb, P limb][N]: the level-0 key slices as Shoup pairs
     ulonglong2 *mono_pairs = nullptr; // [levels][N]: the pack monomials NTT(X^step) as Shoup pairs
     u64 *bias_plain = nullptr;        // [N]: the bias plaintext as plain residues
     u64 *pool = nullptr; // all scratch / level buffers
@@ -397,6 +400,8 @@ extern "C" void hec_plan_destroy(hec_plan *p) {
     if (p->s_out) cudaStreamDestroy(p->s_out);
     if (p->pool) cudaFree(p->pool);
     if (p->ptk_scaled) cudaFree(p->ptk_scaled);
+    if (p->ptk_pairs) cudaFree(p->ptk_pairs);
+    if (p->key_pairs) cudaFree(p->key_pairs);
     if (p->mono_pairs) cudaFree(p->mono_pairs);
     if (p->bias_plain) cudaFree(p->bias_plain);
     if (p->d_ctin) cudaFree((void *)p->d_ctin);
@@ -442,22 +447,31 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
     auto bail = [&](int code, const char *msg) { hec_plan_destroy(p); return c->fail(code, msg); };
     // ---- device memory: pointer tables + one pool ----
     if (cudaMalloc((void **)&p->d_ctin, M * sizeof(u64 *)) != cudaSuccess) return bail(HEC_E_NOMEM, "cudaMalloc");
-    if (cudaMalloc((void **)&p->d_ptk, B * sizeof(u64 *)) != cudaSuccess) return bail(HEC_E_NOMEM, "cudaMalloc");
+    if (cudaMalloc((void **)&p->d_ptk, B * sizeof(ulonglong2 *)) != cudaSuccess) return bail(HEC_E_NOMEM, "cudaMalloc");
     // plan-owned copies of the kernel plaintexts with the MultByConst constants folded in:
     // (ct*pt)*k == ct*(pt*k); one multiply per coefficient at plan creation instead of one per conv
     if (cudaMalloc(&p->ptk_scaled, (size_t)na * 2 * HEC_N * sizeof(u64)) != cudaSuccess) return bail(HEC_E_NOMEM, "cudaMalloc");
-    std::vector<const u64 *> hk(B, nullptr);
+    if (cudaMalloc(&p->ptk_pairs, (size_t)na * 2 * HEC_N * sizeof(ulonglong2)) != cudaSuccess) return bail(HEC_E_NOMEM, "cudaMalloc");
+    std::vector<const ulonglong2 *> hk(B, nullptr);
     {
         std::vector<EwJob> ej;
         for (int a = 0; a < na; a++) {
             u64 *dst = p->ptk_scaled + (size_t)a * 2 * HEC_N;
-            hk[a * norm] = dst;
+            hk[a * norm] = p->ptk_pairs + (size_t)a * 2 * HEC_N;
             for (int l = 0; l < 2; l++)
                 ej.push_back(ewjob(pt_ker[a * norm]->buf + (size_t)l * HEC_N, nullptr, dst + (size_t)l * HEC_N, c->modQ(l), mform(k[l], c->q(c->modQ(l)))));
         }
         if (launch_ew<EW_MULSCALAR>(c, ej)) return bail(HEC_E_CUDA, "scaling kernel plaintexts");
+        for (int a = 0; a < na; a++)
+            for (int l = 0; l < 2; l++) {
+                k_plan_tables<<<64, 256, 0, c->stream>>>(p->ptk_scaled + ((size_t)a * 2 + l) * HEC_N, p->ptk_pairs + ((size_t)a * 2 + l) * HEC_N,
+                                                          nullptr, c->modQ(l), c->dmods);
+                c->launches++;
+            }
+        cudaFreeAsync(p->ptk_scaled, c->stream); // only the pairs are read from here on
+        p->ptk_scaled = nullptr;
     }
-    if (cudaMemcpy((void *)p->d_ptk, hk.data(), B * sizeof(u64 *), cudaMemcpyHostToDevice) != cudaSuccess) return bail(HEC_E_CUDA, "memcpy ptk");
+    if (cudaMemcpy((void *)p->d_ptk, hk.data(), B * sizeof(ulonglong2 *), cudaMemcpyHostToDevice) != cudaSuccess) return bail(HEC_E_CUDA, "memcpy ptk");
     // chunking (see hec_plan): HEC_PLAN_CHUNK ciphertexts per chunk (0 / not a divisor of M: the whole batch at once),
     // HEC_PLAN_CHAINS chunks in flight
     {
@@ -502,7 +516,9 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
     A.hneg0 = q0 - A.half1 % q0;
     auto pair = [](u64 w, u64 q) { return make_ulonglong2(w, (u64)(((u128)w << 64) / q)); };
     A.resc0 = pair(q0 - invmod(q1 % q0, q0), q0);
-    if (levels > 0 && cudaMalloc(&p->mono_pairs, (size_t)levels * HEC_N * sizeof(ulonglong2)) != cudaSuccess) return bail(HEC_E_NOMEM, "cudaMalloc");
+    if (levels > 0 && (cudaMalloc(&p->mono_pairs, (size_t)levels * HEC_N * sizeof(ulonglong2)) != cudaSuccess ||
+                       cudaMalloc(&p->key_pairs, (size_t)levels * 4 * HEC_N * sizeof(ulonglong2)) != cudaSuccess))
+        return bail(HEC_E_NOMEM, "cudaMalloc");
     if (pt_bias) {
         if (cudaMalloc(&p->bias_plain, HEC_N * sizeof(u64)) != cudaSuccess) return bail(HEC_E_NOMEM, "cudaMalloc");
         k_plan_tables<<<64, 256, 0, c->stream>>>(pt_bias->buf, nullptr, p->bias_plain, mq0, c->dmods);
@@ -528,9 +544,16 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
         b.mono = mp;
         it->second.kb->plan_refs++;
         p->ref_keys.push_back(it->second.kb);
-        b.key = it->second.buf;
-        b.keyL = it->second.Lk + c->nP;
-        b.keyPoff = it->second.Lk;
+        {   // key slice of this level as pairs: [poly][Q limb 0, P limb 0]
+            const int kl = it->second.Lk + c->nP, poff = it->second.Lk;
+            ulonglong2 *kp = p->key_pairs + (size_t)l * 4 * HEC_N;
+            for (int pc = 0; pc < 2; pc++) {
+                k_plan_tables<<<64, 256, 0, c->stream>>>(it->second.buf + (size_t)(pc * kl) * HEC_N, kp + (size_t)(pc * 2) * HEC_N, nullptr, mq0, c->dmods);
+                k_plan_tables<<<64, 256, 0, c->stream>>>(it->second.buf + (size_t)(pc * kl + poff) * HEC_N, kp + (size_t)(pc * 2 + 1) * HEC_N, nullptr, mp0, c->dmods);
+                c->launches += 2;
+            }
+            b.key = kp;
+        }
         b.bias = (l == levels - 1 && pt_bias) ? p->bias_plain : nullptr;
         b.w1 = wb1; b.w2 = wb2; b.w3 = wb3; b.w4 = wb4; b.z = wbz;
         b.n = na >> l; b.mq0 = mq0; b.mp0 = mp0;

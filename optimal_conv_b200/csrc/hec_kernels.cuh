@@ -15,10 +15,14 @@
 // one limb through a transform.  Forward transforms can absorb the point-wise step in front of them and the one behind:
 //   flags & 1: the input is a residue of ANOTHER modulus (< 2^64): x = (in mod q) + pro_s0     (EW_REDUCE_ADD)
 //   flags & 2: out = (x + 2q - ep_b) * ep_s0 * R^-1 instead of x                              (EW_SUBMUL)
+//   flags & 4: ... + ep_add on top of that (the "+ c0" that follows the mod-down of a rotation)  (EW_ADD)
 // mid: where the first pass leaves its result (null: out) -- needed when ep_b aliases out
-struct LimbJob { const u64 *in; u64 *out; int mod; int flags; u64 *mid; const u64 *ep_b; u64 ep_s0; u64 pro_s0; };
+//   scatter_g != 0: the result is written through the automorphism, out[index_g^-1[i]] = x[i] with scatter_g = g^-1 mod 2N
+//                   (PermuteNTTWithIndexLvl as scattered stores of the last pass instead of a gather pass of its own)
+struct LimbJob { const u64 *in; u64 *out; int mod; int flags; u64 *mid; const u64 *ep_b; u64 ep_s0; u64 pro_s0; const u64 *ep_add; u32 scatter_g; };
 #define HEC_LJ_PRO 1
 #define HEC_LJ_EPI 2
+#define HEC_LJ_ADD 4
 // programmatic dependent launch: let the next kernel of the stream be scheduled while this grid drains, and do not touch
 // memory before the previous grid has completed (both are no-ops for a kernel launched without the attribute)
 #define HEC_PDL_SYNC() asm volatile("griddepcontrol.launch_dependents;\n\tgriddepcontrol.wait;" ::: "memory")
@@ -92,8 +96,17 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_GEN_MINB) k_row_fwd(const Lim
     if (job.flags & HEC_LJ_EPI) {
 #pragma unroll
         for (int k = 0; k < 16; k++) x[k] = mred(x[k] + M.q2 - job.ep_b[G.gbase + 16 * k], job.ep_s0, M.q, M.qinv);
+        if (job.flags & HEC_LJ_ADD) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) x[k] = addmod(x[k], job.ep_add[G.gbase + 16 * k], M.q);
+        }
     }
-    row_storeA(x, job.out, G);
+    if (job.scatter_g) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) job.out[perm_index(G.gbase + 16 * k, job.scatter_g)] = x[k];
+    } else {
+        row_storeA(x, job.out, G);
+    }
 }
 __global__ void __launch_bounds__(HEC_THREADS, HEC_GEN_MINB) k_row_inv(const LimbJob *__restrict__ jobs, const ModC *__restrict__ mods) {
     HEC_PDL_TRIGGER();
@@ -433,10 +446,13 @@ __global__ void __launch_bounds__(256) k_modup2(const Modup2Job *__restrict__ jo
 //   MulNew(ct_in, pl_ker[i])   L:ckks/evaluator.go:1360-1444 (pt branch)
 //   SetScale -> MultByConst    L:ckks/evaluator.go:782-863 (constants from the host)
 //            -> Rescale -> divRoundByLastModulusNTT   L:ring/ring_scaling.go:442-513
+// The fixed operands of the point-wise products (kernel plaintexts, key limbs) are kept by the plan as Shoup pairs
+// (w, floor(w 2^64 / q)): the product is then the 5-wide-multiply approximate Shoup form (31.9 clk) instead of a
+// Montgomery product (49 clk), at the price of 16 instead of 8 bytes per operand word (L2-resident tables).
 struct ConvA {
     const u64 *const *ctin; // [M] -> [2 polys][2 limbs][N]
-    const u64 *const *ptk;  // [B] -> [2 limbs][N]: pl_ker[i] * c_limb in Montgomery form (the MultByConst
-                            //        constant is folded into the plan's copy of the kernel plaintexts)
+    const ulonglong2 *const *ptk; // [B] -> [2 limbs][N] pairs of pl_ker[i] * c_limb (the MultByConst constant is folded
+                            //        into the plan's copy of the kernel plaintexts)
     u64 *w1, *w2;           // [M*na*2][N] scratch
     u64 *xout;              // [M*na][2][N] level-0 ciphertexts
     int na, norm, mq0, mq1;
@@ -455,12 +471,12 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convA1(ConvA P, const
     const ModC M = mods[P.mq1];
     RowGeom G(HEC_BTILE);
     const u64 *ct = P.ctin[J.m] + (size_t)(J.c * 2 + 1) * HEC_N;
-    const u64 *pt = P.ptk[J.a * P.norm] + HEC_N;
+    const ulonglong2 *pt = P.ptk[J.a * P.norm] + HEC_N;
     u64 x[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         u32 i = G.gbase + 16 * k;
-        x[k] = mred_lazy(ct[i], __ldg(pt + i), M.q, M.qinv);
+        x[k] = shoup4(ct[i], __ldg(pt + i), M.q); // < 4q
     }
     row_AtoB(x, sm, G);
     row_inv8(x, sm, G, M);
@@ -500,11 +516,11 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convA3(ConvA P, const
     const ModC M = mods[P.mq0];
     RowGeom G(HEC_BTILE);
     const u64 *ct = P.ctin[J.m] + (size_t)(J.c * 2) * HEC_N;
-    const u64 *pt = P.ptk[J.a * P.norm];
+    const ulonglong2 *pt = P.ptk[J.a * P.norm];
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         u32 i = G.gbase + 16 * k, e = G.p + 16 * k;
-        st[G.sbase + e + (e >> 4)] = mred_lazy(ct[i], __ldg(pt + i), M.q, M.qinv); // (0,2q)
+        st[G.sbase + e + (e >> 4)] = shoup4(ct[i], __ldg(pt + i), M.q); // < 4q
     }
     u64 x[16];
     row_loadA(x, P.w2 + (size_t)HEC_BJOB * HEC_N, G);
@@ -514,7 +530,7 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convA3(ConvA P, const
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         u32 i = G.gbase + 16 * k, e = G.p + 16 * k;
-        out[i] = cred(shoup(x[k] + M.q2 - st[G.sbase + e + (e >> 4)], P.resc0, M.q), M.q);
+        out[i] = cred(shoup(x[k] + 2 * M.q2 - st[G.sbase + e + (e >> 4)], P.resc0, M.q), M.q);
     }
 }
 
@@ -546,11 +562,11 @@ struct ConvB {
     const u64 *xin;  // [M*n][2][N]
     u64 *xout;       // [M*n/2][2][N]
     const ulonglong2 *mono; // NTT(X^step) at q0 as Shoup pairs (plan-owned, built from pt_idx)
-    const u64 *key;  // digit 0 of the switching key: [2][keyL][N], Montgomery
+    const ulonglong2 *key; // the level-0 slice of the switching key as Shoup pairs (plan-owned): [2 polys][Q limb, P limb][N]
     const u64 *bias; // bias plaintext as plain residues (plan-owned copy; only the last level), or null
     u64 *w1, *w2, *w3, *w4;
     u64 *z;          // [M*n/2][N]: tmp2.c1 = a1 - b1*X^step of every butterfly, in [0,3q)
-    int n, keyL, keyPoff, mq0, mp0;
+    int n, mq0, mp0;
     u32 galEl;
     ulonglong2 negpinv; // q0 - P^-1 mod q0 as a Shoup pair   [A] test_run 0x4e5049
     u64 qpj1;        // q0 - (p0 mod q0) = qpjInv[1]
@@ -626,15 +642,10 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convB3(ConvB P, const
     }
 #pragma unroll 1
     for (int c = 0; c < 2; c++) {
-        const ulonglong2 *kv = reinterpret_cast<const ulonglong2 *>(
-            P.key + (size_t)(c * P.keyL + P.keyPoff) * HEC_N + G.b * 256 + 16 * G.p);
+        const ulonglong2 *kv = P.key + (size_t)(c * 2 + 1) * HEC_N + G.b * 256 + 16 * G.p; // P limb of key poly c
         u64 y[16];
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            ulonglong2 t = __ldg(kv + k);
-            y[2 * k] = mred_lazy(stash[(2 * k) * HEC_THREADS + threadIdx.x], t.x, M.q, M.qinv);
-            y[2 * k + 1] = mred_lazy(stash[(2 * k + 1) * HEC_THREADS + threadIdx.x], t.y, M.q, M.qinv);
-        }
+        for (int k = 0; k < 16; k++) y[k] = shoup4(stash[k * HEC_THREADS + threadIdx.x], __ldg(kv + k), M.q); // < 4q
         row_inv8(y, sm, G, M);
         row_storeA(y, P.w3 + (size_t)(HEC_BJOB * 2 + c) * HEC_N, G);
     }
@@ -672,15 +683,15 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convB4(ConvB P, const
 // and the kernel waits for every operand in turn (profiles/r02a: 71 % of its stall samples sat on these loads).
 template <bool C0>
 __device__ __forceinline__ void b5_pointwise(const u64 (&x)[16], u64 *sm, u64 *st, const ConvB &P, const BJob &J, const ModC &M,
-                                             const RowGeom &G, const u64 *__restrict__ zb, const u64 *__restrict__ kq) {
+                                             const RowGeom &G, const u64 *__restrict__ zb, const ulonglong2 *__restrict__ kq) {
     const u64 *__restrict__ a = C0 ? J.a : J.a + HEC_N;
     const u64 *__restrict__ b = J.b;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         const u32 i = G.gbase + 16 * k, e = G.p + 16 * k;
         const u64 z = zb[i];                                                // tmp2.c1 in (0,3q)
-        const u64 accq = mred_lazy(z, __ldg(kq + i), M.q, M.qinv);          // MulCoeffsMontgomeryConstant (+ Reduce), (0,2q)
-        u64 d = shoup(x[k] + M.q2 - accq, P.negpinv, M.q);                  // ModDownSplitNTTPQ combine, [0,2q)
+        const u64 accq = shoup4(z, __ldg(kq + i), M.q);                     // MulCoeffsMontgomeryConstant (+ Reduce), < 4q
+        u64 d = shoup(x[k] + 2 * M.q2 - accq, P.negpinv, M.q);              // ModDownSplitNTTPQ combine, [0,2q)
         u64 t1;
         if (C0) {
             const u64 a0 = a[i];
@@ -711,7 +722,7 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_B5_MINB) k_convB5(ConvB P, co
     row_loadA(x, P.w4 + (size_t)HEC_BJOB * HEC_N, G);
     row_fwd8(x, sm, G, M);
     row_BtoA(x, sm, G);
-    const u64 *kq = P.key + (size_t)(J.c * P.keyL) * HEC_N;
+    const ulonglong2 *kq = P.key + (size_t)(J.c * 2) * HEC_N; // Q limb of key poly c
     const u64 *zb = P.z + (size_t)(HEC_BJOB >> 1) * HEC_N;
     if (J.c == 0) b5_pointwise<true>(x, sm, st, P, J, M, G, zb, kq);
     else b5_pointwise<false>(x, sm, st, P, J, M, G, zb, kq);

@@ -159,6 +159,37 @@ def gen_comprs_sparse(vec_size, in_wid, kp_wid, log_sparse, ul, pos):
     return m_idx, r_idx
 
 
+def gen_comprs_fast(vec_size, in_wid, kp_wid, pos, ul):
+    """gen_comprs_fast (rot_util.go:498-548): the two stages of the fast packing of a strided convolution's output under
+    full packing (m_idx then r_idx, ext_double_ctxt)"""
+    m_idx, r_idx = {}, {}
+    batch = 2 * vec_size // (in_wid * in_wid)
+    if kp_wid < in_wid // 2:
+        raise ValueError("keep width too small. less than in_wid/2")
+    pos = reverse_bits(pos, 2)
+    min_wid = in_wid // 4
+    if in_wid % 4:
+        raise ValueError("input wid not divisible by 4")
+    lw = (in_wid - 1).bit_length()
+    for j in range(2 * min_wid):
+        tmp = np.zeros(vec_size, dtype=np.int64)
+        for b in range(batch):
+            for i in range(min_wid):
+                ok = reverse_bits(in_wid // 2 + j, lw) < kp_wid
+                if ul == 1:
+                    ok = ok and reverse_bits(min_wid + i, lw - 1) < kp_wid - in_wid // 2
+                if ok:
+                    tmp[2 * min_wid * in_wid * b + 2 * min_wid * j + i + in_wid * min_wid + min_wid] = 1
+        m_idx[j * min_wid - 2 * min_wid * min_wid + min_wid] = tmp
+    for b in range(batch):
+        tmp = np.zeros(vec_size, dtype=np.int64)
+        for j in range(2 * min_wid):
+            for i in range(min_wid):
+                tmp[2 * min_wid * in_wid * b + 3 * in_wid // 2 * min_wid + j * min_wid + i] = 1
+        r_idx[3 * b * min_wid * in_wid // 2 - pos * min_wid * in_wid // 2 * batch + 3 * min_wid * in_wid // 2] = tmp
+    return m_idx, r_idx
+
+
 # ---- input / output layout --------------------------------------------------------------------------------------------
 def pack_image_sparse(image, in_wid, raw_in_wid, max_batch, norm, N, channels=3):
     """the sparse packing of the network input (test.go:134-146): coefficient i*in_wid*max_batch + j*max_batch + b*norm"""
@@ -208,48 +239,38 @@ def prep_input(raw, raw_w, w, N, norm, trans=False):
 
 
 def reshape_ker(ker_in, k_sz, out_batch):
-    """reshape_ker, trans=false (conv.go:184-202)."""
+    """reshape_ker, trans=false (conv.go:184-202): out[i][j*k_sz + k] = ker_in[i + j*out_batch + k*out_batch*in_batch]"""
+    ker_in = np.asarray(ker_in, dtype=np.float64)
     in_batch = len(ker_in) // (k_sz * out_batch)
-    out = np.zeros((out_batch, k_sz * in_batch))
-    for i in range(out_batch):
-        for j in range(in_batch):
-            for k in range(k_sz):
-                out[i, j * k_sz + k] = ker_in[i + j * out_batch + k * out_batch * in_batch]
-    return out
+    return np.ascontiguousarray(ker_in.reshape(k_sz, in_batch, out_batch).transpose(2, 1, 0)).reshape(out_batch, in_batch * k_sz)
 
 
 def encode_ker_final(ker_in, pos, i, w, B, k):
-    """encode_ker_final (conv.go:206-237)."""
+    """encode_ker_final (conv.go:206-237): output channel i's kernel as the coefficient vector of its plaintext --
+    tap t of input channel j at coefficient (w*(t/k) + t%k)*B + j, taps and channels reversed, then the whole vector
+    rotated by `adj` positions with the wrapped part negated (multiplication by a monomial modulo X^N + 1)"""
     vec = w * w * B
-    out = np.zeros(vec)
     k_sz = k * k
     bias = pos * k_sz * B
-    for j in range(B):
-        for t in range(k_sz):
-            out[(w * (t // k) + t % k) * B + j] = ker_in[i][(B - 1 - j) * k_sz + (k_sz - 1 - t) + bias]
+    row = np.asarray(ker_in[i][bias:bias + B * k_sz], dtype=np.float64).reshape(B, k_sz)[::-1, ::-1]   # [j][t]
+    t = np.arange(k_sz)
+    out = np.zeros((w * w, B))
+    out[w * (t // k) + t % k, :] = row.T
+    out = out.reshape(vec)
     adj = (B - 1) + B * (w + 1) * (k - 1) // 2
-    tmp = out[vec - adj:].copy()
-    head = out[:adj].copy()
-    body = out[adj:vec - adj].copy()
-    res = np.empty(vec)
-    res[:vec - 2 * adj] = body
-    res[vec - 2 * adj:vec - adj] = tmp
-    res[vec - adj:] = -head
-    return res
+    return np.concatenate([out[adj:vec - adj], out[vec - adj:], -out[:adj]])
 
 
-def prep_ker_coeffs(N, ker_in, bn_a, w, k, real_ib, real_ob, norm):
-    """prep_Ker up to (not including) EncodeCoeffs (conv.go:487-516): float coefficient
-    vectors for the max_bat kernel plaintexts."""
+def prep_ker_coeffs(N, ker_in, bn_a, w, k, real_ib, real_ob, norm, rows=None):
+    """prep_Ker up to (not including) EncodeCoeffs (conv.go:487-516): the float coefficient vectors of the kernel
+    plaintexts, for all max_bat output channels or for `rows` only (conv_then_pack reads every norm-th one)."""
     max_bat = N // (w * w)
     k_sz = k * k
-    ker_rs = reshape_ker(ker_in, k_sz, real_ob)
-    ker_rs = ker_rs * np.asarray(bn_a)[:, None]
-    max_ker = np.zeros((max_bat, max_bat * k_sz))
-    for i in range(real_ob):
-        for j in range(real_ib):
-            max_ker[norm * i, norm * j * k_sz:norm * j * k_sz + k_sz] = ker_rs[i, j * k_sz:(j + 1) * k_sz]
-    return [encode_ker_final(max_ker, 0, i, w, max_bat, k) for i in range(max_bat)]
+    ker_rs = reshape_ker(ker_in, k_sz, real_ob) * np.asarray(bn_a, dtype=np.float64)[:, None]
+    max_ker = np.zeros((max_bat, max_bat, k_sz))
+    max_ker[:norm * real_ob:norm, :norm * real_ib:norm, :] = ker_rs.reshape(real_ob, real_ib, k_sz)
+    max_ker = max_ker.reshape(max_bat, max_bat * k_sz)
+    return [encode_ker_final(max_ker, 0, i, w, max_bat, k) for i in (range(max_bat) if rows is None else rows)]
 
 
 def bias_coeffs(N, bn_b, w, norm):

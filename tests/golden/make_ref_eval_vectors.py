@@ -726,8 +726,25 @@ def hostprep_case():
     cfs = [float(v) for v in range(1, N + 1)]
     r = m.call("main.post_process", fslice(cfs) + [raw_w, w, 0, 0, 0])
     post = rfs(r[5:8])
+    # the slot index maps of the between-layer helpers that the shipped binary has (rot_util.go): gen_keep_vec, both
+    # halves; gen_comprs_fast, both halves (maps of rotation -> mask); prt_mat_one_norm (where the logits sit)
+    def ri(hdr_words):
+        return [x - (1 << 64) if x >> 63 else x for x in m.read_u64s(hdr_words[0], hdr_words[1])]
+    idxmaps = {"vec_size": 128, "in_wid": 8, "kp_wid": 6, "keep": [], "comprs_fast": []}
+    for ul in (0, 1):
+        r = m.call("main.gen_keep_vec", [128, 8, 6, ul, 0, 0, 0])
+        idxmaps["keep"].append(ri(r[4:7]))
+        r = m.call("main.gen_comprs_fast", [128, 8, 6, 1, ul, 0, 0])
+        maps = []
+        for h in r[5:7]:
+            maps.append({str(k - (1 << 64) if k >> 63 else k): ri(m.read_u64s(slot, 3)) for k, slot in sorted(m.maps[m._mapid(h)].items())})
+        idxmaps["comprs_fast"].append(maps)
+    m.hook("main.prt_vec", lambda em: None)   # printing only
+    vec = [float(v) for v in range(1, 4 * 4 * 8 + 1)]
+    r = m.call("main.prt_mat_one_norm", fslice(vec) + [8, 2, 2, 3, 0, 0, 0])
+    idxmaps["mat_one_norm"] = rfs(r[7:10])
     return {"cfg": HOSTPREP, "reshape_ker": reshaped, "encode_ker_final": enc, "prep_input": prep, "post_process": post,
-            "interpreted_instructions": m.steps}
+            "index_maps": idxmaps, "interpreted_instructions": m.steps}
 
 
 def main():

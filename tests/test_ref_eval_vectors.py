@@ -332,9 +332,9 @@ FULL = sorted(REF.get("conv_full", {}))
 
 
 def test_float_side_host_preparation_matches_reference_code():
-    """tests/hostprep.py (what the semantic encrypt -> conv -> decrypt test builds its operands with) against
+    """optimal_conv_b200/hostprep.py (what the semantic encrypt -> conv -> decrypt test builds its operands with) against
     main.reshape_ker / encode_ker_final / prep_Input / post_process of the reference binary"""
-    import hostprep as hp
+    from optimal_conv_b200 import hostprep as hp
     d = REF["hostprep"]
     B, w, k, raw_w, norm = (d["cfg"][x] for x in ("B", "w", "k", "raw_w", "norm"))
     rs = hp.reshape_ker(np.arange(1, B * B * k * k + 1, dtype=float), k * k, B)
@@ -345,6 +345,34 @@ def test_float_side_host_preparation_matches_reference_code():
     raw = np.arange(1, raw_w * raw_w * (B // norm) + 1, dtype=float)
     assert np.array_equal(hp.prep_input(raw, raw_w, w, N, norm), np.array(d["prep_input"]))
     assert np.array_equal(hp.post_process(np.arange(1, N + 1, dtype=float), raw_w, w), np.array(d["post_process"]))
+
+
+def test_slot_index_maps_match_reference_code():
+    """main.gen_keep_vec and main.gen_comprs_fast (rot_util.go:141-174, 498-548; both halves) and main.prt_mat_one_norm
+    (main.go:920-939), interpreted, == optimal_conv_b200/hostprep.py.  (The shipped binary predates the *_sparse
+    generators; those are restated from the source only.)"""
+    from optimal_conv_b200 import hostprep as hp
+    d = REF["hostprep"]["index_maps"]
+    vs, w, kp = d["vec_size"], d["in_wid"], d["kp_wid"]
+    for ul in (0, 1):
+        assert hp.gen_keep_vec(vs, w, kp, ul).tolist() == d["keep"][ul]
+        m_idx, r_idx = hp.gen_comprs_fast(vs, w, kp, 1, ul)
+        for mine, ref in ((m_idx, d["comprs_fast"][ul][0]), (r_idx, d["comprs_fast"][ul][1])):
+            assert sorted(mine) == sorted(int(k) for k in ref)
+            for rot, mask in mine.items():
+                assert mask.tolist() == ref[str(rot)], (ul, rot)
+    vec = np.arange(1, 4 * 4 * 8 + 1, dtype=float)
+    assert hp.mat_one_norm(vec, 8, 2, 2, 3).tolist() == d["mat_one_norm"]
+    # files: what write_txt writes, read_txt reads back bit for bit, in Go's 'e' / shortest-digits form
+    import tempfile
+    vals = [0.0, 1.0, -1.5, 1e-7, 123456789.125, 3.141592653589793, 2.5e300, 100.0, 0.001]
+    with tempfile.TemporaryDirectory() as t:
+        hp.write_txt(t + "/x.csv", vals)
+        assert open(t + "/x.csv").read().split() == ["0e+00", "1e+00", "-1.5e+00", "1e-07", "1.23456789125e+08",
+                                                     "3.141592653589793e+00", "2.5e+300", "1e+02", "1e-03"]
+        assert hp.read_txt(t + "/x.csv", len(vals)).tolist() == vals
+        with pytest.raises(ValueError, match="input size inconsistent"):
+            hp.read_txt(t + "/x.csv", 3)
 
 
 @pytest.mark.parametrize("name", sorted(common.ENCODE_CASES))

@@ -339,29 +339,44 @@ def run_side_workload(args):
             o.rescale(o.mul_relin(Ct(a[0], a[1], PR.SCALE), Ct(a[2], a[3], PR.SCALE), rlk), PR.SCALE)
             cpu_s = time.perf_counter() - t0
     elif args.workload == "bootstrap_ctos":
-        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        import make_ref_eval_vectors as G   # seeded operands only (no reference access)
         Q, P = PR.Q_SET6, PR.P_ALL
         ctx = hec.Context(PR.LOGN, Q, P)
-        keys, kconj, rlk, b = G.ctos_operands(N)
+        # --diagonals real: the supports of the bootstrapper's real factor matrices at LogSlots 15 (16 + 31 + 31 + 15
+        # diagonals, synth.dft_factor_specs) instead of the 3-5 diagonals per factor of the parity-test operands; --log-slots
+        # picks a sparse bootstrapper (14..11, main.go:60-83)
+        specs = synth.dft_factor_specs(args.log_slots, 4, 27) if args.diagonals == "real" else None
+        if specs is None:
+            keys, kconj, rlk, b = synth.ctos_operands(N)
+        else:   # one seeded key buffer stands in for every rotation key (timing: sizes and levels are the real ones)
+            _, kconj, rlk, b = synth.ctos_operands(N, specs=[])
+            rots = set()
+            for n1, diags, _ in specs:
+                rots |= {d % n1 for d in diags if d % n1} | {(d // n1) * n1 for d in diags if d // n1}
+            rots |= {1 << i for i in range(args.log_slots, PR.LOGN - 1)}
+            keys = {r: kconj for r in sorted(rots)}
+            tile = [(synth.uniform_limbs(7000 + t, Q, N), synth.uniform_limbs(7500 + t, P, N)) for t in range(3)]
+            b["mats"] = [({d: (tile[(i + j) % 3][0][:ml + 1], tile[(i + j) % 3][1]) for j, d in enumerate(diags)}, n1, ml, float(Q[ml]))
+                         for i, (n1, diags, ml) in enumerate(specs)]
         for r, k in keys.items():
             ctx.upload_swk(ctx.galois_for_rotation(r), k, 27)
         ctx.upload_swk(2 * N - 1, kconj, 27)
         ctx.upload_rlk(rlk, 27)
-        mats = [ctx.upload_ptdiag(PR.LOGN - 1, n1, ml, ms, D) for D, n1, ml, ms in b["mats"]]
+        mats = [ctx.upload_ptdiag(args.log_slots if specs else PR.LOGN - 1, n1, ml, ms, D) for D, n1, ml, ms in b["mats"]]
         a0, a1 = synth.uniform_limbs(61, Q[:2], N), synth.uniform_limbs(62, Q[:2], N)
         A = ctx.upload_ct(a0, a1, PR.SCALE * 2.0 ** 8)
 
         def step():
             g0, g1, _ = ctx.BootstrappConv_CtoS(A, b, mats)
             g0.free()
-            g1.free()
+            if g1 is not None:   # sparse packing returns one ciphertext
+                g1.free()
         unit = "half-bootstraps/s"
         name = ("BootstrappConv_CtoS (eval.go:447-459) over the 28+5 modulus chain of set 6: modUp, 4 hoisted linear transforms "
-                "(synthetic sparse factors), degree-63 Chebyshev sine x2 + double angle, alpha=5")
+                "(%s), degree-63 Chebyshev sine + double angle, alpha=5"
+                % ("factor matrices with the real diagonal supports at LogSlots %d: %s diagonals, %d rotation keys"
+                   % (args.log_slots, "+".join(str(len(sp[1])) for sp in specs), len(keys)) if specs else "synthetic sparse factors, 3-5 diagonals each"))
         alg = None
-        if args.cpu_sample > 0:
+        if args.cpu_sample > 0 and specs is None:
             from oracle.orc import Ct, Oracle
             o = Oracle(PR.LOGN, Q, P)
             t0 = time.perf_counter()
@@ -447,7 +462,8 @@ def run_side_workload(args):
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "dtype": "u64",
             "data": "synthetic", "config": {"workload": args.workload, "path": "op-level generic kernels"},
             "gpu_launches": ctx.launch_count() - l0}
-    if args.workload in ("conv_bl", "mul_relin", "eval_relu", "bootstrap_ctos", "prep_ker") and args.cpu_sample > 0:
+    if args.workload in ("conv_bl", "mul_relin", "eval_relu", "bootstrap_ctos", "prep_ker") and args.cpu_sample > 0 \
+            and not (args.workload == "bootstrap_ctos" and args.diagonals == "real"):
         line["cpu_baseline"] = {"value": 1.0 / cpu_s, "unit": unit, "cores": 1, "kind": "port",
                                 "sample": "1 call of the same workload, oracle port, 1 thread"}
     if alg:
@@ -470,6 +486,8 @@ def main():
                     help="conv = the headline fused path; the others are op-level side measurements")
     ap.add_argument("--cpu-sample", type=int, default=12, help="convs timed for cpu_baseline (0 = skip)")
     ap.add_argument("--ring", type=int, default=8, help="distinct input batches rotated through (> L2)")
+    ap.add_argument("--diagonals", default="few", choices=["few", "real"], help="bootstrap_ctos: factor-matrix supports")
+    ap.add_argument("--log-slots", type=int, default=15, help="bootstrap_ctos --diagonals real: LogSlots of the bootstrapper (15 full, 14..11 sparse)")
     ap.add_argument("--check", type=int, default=64, help="ciphertexts of one step compared with the oracle before timing (0 = skip)")
     ap.add_argument("--config4", type=int, default=1, help="also measure BASELINE.json config 4 (B = 256, 8 ciphertexts per GPU per step)")
     args = ap.parse_args()
@@ -625,6 +643,8 @@ def main():
     # whole-job throughput: every rank's convs over the slowest rank's device time (no data-path collective)
     value, ms_dev = shard.throughput(M, args.steps, ms_dev, device="cuda")
     e2e, ms_e2e = shard.throughput(M, args.steps, ms_e2e, device="cuda")
+    # BASELINE.json config 4 on every rank (its throughput is a collective over the ranks), before the others leave
+    cfg4 = config4(ctx, torch, rank, world) if (args.config4 and B == 16) else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -637,7 +657,9 @@ def main():
         reps = 3
         n_launch = len(times) // reps
         per_kernel[name] = {"ms_per_run": sum(times) / reps, "launches_per_run": n_launch}
-    dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_run"])
+    # "the dominant kernel": the longest-running one among the kernels that complete a reference operation, i.e. have
+    # algorithmic bytes in the sense of SURVEY.md 8(d); A2, B2 and B4 only move half-transformed scratch (0 such bytes)
+    dom = max((k for k in per_kernel if kernel_limbs(k, M, B, algorithmic=True) > 0), key=lambda k: per_kernel[k]["ms_per_run"])
     dom_ms = per_kernel[dom]["ms_per_run"]
     n_l = per_kernel[dom]["launches_per_run"]
     share = dom_ms / sum(v["ms_per_run"] for v in per_kernel.values())
@@ -677,6 +699,8 @@ def main():
                      "alg_bytes_definition": "SURVEY.md 8(d): operands and results of the reference operations only; scratch excluded",
                      "distinct_bytes_per_launch": distinct_bytes_launch, "launch_ms": first_ms,
                      "launch": "first (largest) of %d launches per run" % n_l, "share_of_step": share,
+                     "kernel_selection": "longest among the kernels with algorithmic bytes (A1, A3, B1, B3, B5); the scratch-to-scratch "
+                                         "passes A2, B2, B4 are covered by roofline_group / roofline_conv",
                      "traffic_source": "profiles/%s (ncu --set full, same command)" % NCU_SUMMARY.get(M, "-")},
         "roofline_group": {"kernels": "k_convB1..B5 (NTT + key-switch group), first pack level", "bound": "hbm",
                            "alg_bytes": grp_bytes, "ms": grp_ms, "achieved": (grp_bytes / (grp_ms / 1e3) / 1e9) if grp_ms else None,
@@ -695,8 +719,8 @@ def main():
         "parity": parity,
         "host_placement": placement,
     }
-    if args.config4 and B == 16:
-        line["config4"] = config4(ctx, torch, rank, world)
+    if cfg4 is not None:
+        line["config4"] = cfg4
     # ---- CPU baseline beside it: the oracle port, 1 thread (the reference is single-threaded) ----
     if world == 1 and args.cpu_sample > 0:
         from oracle.orc import Ct, Oracle

@@ -383,6 +383,7 @@ extern "C" int hec_ctx_create(hec_ctx **out, int logN, const uint64_t *Q, int nQ
         mc[i].wn_s = (u64)(((u128)mc[i].wn_w << 64) / c->hm[i].q);
         mc[i].psi = psi; mc[i].psi_inv = psi_inv;
         mc[i].tight = c->hm[i].q >= (1ull << 57) ? 1 : 0;
+        mc[i].mu = c->hm[i].q > (1ull << 40) ? (u32)(((u128)1 << 64) / c->hm[i].q) : 0; mc[i].pad = 0;
         mc[i].small = (c->hm[i].q < (1ull << 31) && !getenv("HEC_NO_SMALL")) ? 1 : 0; // HEC_NO_SMALL: A/B switch
     }
     if (cudaMemcpy(c->dmods, mc.data(), nm * sizeof(ModC), cudaMemcpyHostToDevice) != cudaSuccess) return bail(HEC_E_CUDA);

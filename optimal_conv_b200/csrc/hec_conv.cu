@@ -256,7 +256,7 @@ struct hec_plan {
     const ulonglong2 **d_ptk = nullptr;
     u64 *ptk_scaled = nullptr;        // [na][2][N]: kernel plaintexts with the MultByConst constant folded in (set-up only)
     ulonglong2 *ptk_pairs = nullptr;  // the same as Shoup pairs: what the kernels read
-    ulonglong2 *key_pairs = nullptr;  // [levels][2 polys][Q limb, P limb][N]: the level-0 key slices as Shoup pairs
+    ulonglong2 *key_pairs = nullptr;  // [levels][2 polys][N]: the Q limb of the level-0 key slices as Shoup pairs
     ulonglong2 *mono_pairs = nullptr; // [levels][N]: the pack monomials NTT(X^step) as Shoup pairs
     u64 *bias_plain = nullptr;        // [N]: the bias plaintext as plain residues
     u64 *pool = nullptr; // all scratch / level buffers
@@ -517,7 +517,7 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
     auto pair = [](u64 w, u64 q) { return make_ulonglong2(w, (u64)(((u128)w << 64) / q)); };
     A.resc0 = pair(q0 - invmod(q1 % q0, q0), q0);
     if (levels > 0 && (cudaMalloc(&p->mono_pairs, (size_t)levels * HEC_N * sizeof(ulonglong2)) != cudaSuccess ||
-                       cudaMalloc(&p->key_pairs, (size_t)levels * 4 * HEC_N * sizeof(ulonglong2)) != cudaSuccess))
+                       cudaMalloc(&p->key_pairs, (size_t)levels * 2 * HEC_N * sizeof(ulonglong2)) != cudaSuccess))
         return bail(HEC_E_NOMEM, "cudaMalloc");
     if (pt_bias) {
         if (cudaMalloc(&p->bias_plain, HEC_N * sizeof(u64)) != cudaSuccess) return bail(HEC_E_NOMEM, "cudaMalloc");
@@ -544,15 +544,16 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
         b.mono = mp;
         it->second.kb->plan_refs++;
         p->ref_keys.push_back(it->second.kb);
-        {   // key slice of this level as pairs: [poly][Q limb 0, P limb 0]
+        {   // key slice of this level: the Q limb as pairs (B5), the P limb as it is (B3)
             const int kl = it->second.Lk + c->nP, poff = it->second.Lk;
-            ulonglong2 *kp = p->key_pairs + (size_t)l * 4 * HEC_N;
+            ulonglong2 *kp = p->key_pairs + (size_t)l * 2 * HEC_N;
             for (int pc = 0; pc < 2; pc++) {
-                k_plan_tables<<<64, 256, 0, c->stream>>>(it->second.buf + (size_t)(pc * kl) * HEC_N, kp + (size_t)(pc * 2) * HEC_N, nullptr, mq0, c->dmods);
-                k_plan_tables<<<64, 256, 0, c->stream>>>(it->second.buf + (size_t)(pc * kl + poff) * HEC_N, kp + (size_t)(pc * 2 + 1) * HEC_N, nullptr, mp0, c->dmods);
-                c->launches += 2;
+                k_plan_tables<<<64, 256, 0, c->stream>>>(it->second.buf + (size_t)(pc * kl) * HEC_N, kp + (size_t)pc * HEC_N, nullptr, mq0, c->dmods);
+                c->launches++;
             }
             b.key = kp;
+            b.keyP = it->second.buf + (size_t)poff * HEC_N;
+            b.keyPstride = (size_t)kl * HEC_N;
         }
         b.bias = (l == levels - 1 && pt_bias) ? p->bias_plain : nullptr;
         b.w1 = wb1; b.w2 = wb2; b.w3 = wb3; b.w4 = wb4; b.z = wbz;

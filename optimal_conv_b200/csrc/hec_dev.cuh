@@ -46,6 +46,8 @@ struct ModC {
     const ulonglong2 *psi_inv; // same for NttPsiInv
     int tight;        // q >= 2^57: the forward transform needs range corrections (see fwd4)
     int small;        // q < 2^31: the transforms run on 32-bit words (fwd4_32 / inv4_32)
+    u32 mu;           // floor(2^64 / q) for q > 2^40 (else 0): quotient estimate of canon()
+    u32 pad;
 };
 
 // ---- scalar primitives -----------------------------------------------------------------
@@ -252,8 +254,17 @@ __device__ __forceinline__ u64 reduce_lazy(u64 y, u64 q, u32 mu) {
     mulw(lo, t, (u32)(y >> 32), mu);
     return y - mullo64((u64)t, q);
 }
-// any 64-bit representative -> canonical residue
-__device__ __forceinline__ u64 canon(u64 x, const ModC &M) { return mred(x, M.rmod, M.q, M.qinv); }
+// any 64-bit representative -> canonical residue.  For q > 2^40 the quotient is estimated from the high word
+// (floor((x >> 32) * mu / 2^32) is floor(x/q), one or two less: two wide products and two conditional subtractions, about
+// a third of the Montgomery product by R mod q that serves the small moduli)
+__device__ __forceinline__ u64 canon(u64 x, const ModC &M) {
+    if (M.mu) {
+        u32 lo, t;
+        mulw(lo, t, (u32)(x >> 32), M.mu);
+        return cred(cred(x - mullo64((u64)t, M.q), M.q2), M.q);
+    }
+    return mred(x, M.rmod, M.q, M.qinv);
+}
 
 // ---- row-kernel tile geometry ------------------------------------------------------------
 // 256 threads; thread (p = tid&15, bb = tid>>4) works on block b = 16*tile + bb.

@@ -562,7 +562,9 @@ struct ConvB {
     const u64 *xin;  // [M*n][2][N]
     u64 *xout;       // [M*n/2][2][N]
     const ulonglong2 *mono; // NTT(X^step) at q0 as Shoup pairs (plan-owned, built from pt_idx)
-    const ulonglong2 *key; // the level-0 slice of the switching key as Shoup pairs (plan-owned): [2 polys][Q limb, P limb][N]
+    const ulonglong2 *key; // the Q limb of the level-0 key slice as Shoup pairs (plan-owned): [2 polys][N]  (B5)
+    const u64 *keyP;       // the P limb of the key itself, Montgomery form: poly c at keyP + c * keyPstride     (B3: measured
+    size_t keyPstride;     //   10 % slower on 16-byte pairs -- its 16 contiguous words per thread load as 8 x 128 bit)
     const u64 *bias; // bias plaintext as plain residues (plan-owned copy; only the last level), or null
     u64 *w1, *w2, *w3, *w4;
     u64 *z;          // [M*n/2][N]: tmp2.c1 = a1 - b1*X^step of every butterfly, in [0,3q)
@@ -642,10 +644,14 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convB3(ConvB P, const
     }
 #pragma unroll 1
     for (int c = 0; c < 2; c++) {
-        const ulonglong2 *kv = P.key + (size_t)(c * 2 + 1) * HEC_N + G.b * 256 + 16 * G.p; // P limb of key poly c
+        const ulonglong2 *kv = reinterpret_cast<const ulonglong2 *>(P.keyP + c * P.keyPstride + G.b * 256 + 16 * G.p);
         u64 y[16];
 #pragma unroll
-        for (int k = 0; k < 16; k++) y[k] = shoup4(stash[k * HEC_THREADS + threadIdx.x], __ldg(kv + k), M.q); // < 4q
+        for (int k = 0; k < 8; k++) {
+            ulonglong2 t = __ldg(kv + k);
+            y[2 * k] = mred_lazy(stash[(2 * k) * HEC_THREADS + threadIdx.x], t.x, M.q, M.qinv);
+            y[2 * k + 1] = mred_lazy(stash[(2 * k + 1) * HEC_THREADS + threadIdx.x], t.y, M.q, M.qinv);
+        }
         row_inv8(y, sm, G, M);
         row_storeA(y, P.w3 + (size_t)(HEC_BJOB * 2 + c) * HEC_N, G);
     }
@@ -722,7 +728,7 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_B5_MINB) k_convB5(ConvB P, co
     row_loadA(x, P.w4 + (size_t)HEC_BJOB * HEC_N, G);
     row_fwd8(x, sm, G, M);
     row_BtoA(x, sm, G);
-    const ulonglong2 *kq = P.key + (size_t)(J.c * 2) * HEC_N; // Q limb of key poly c
+    const ulonglong2 *kq = P.key + (size_t)J.c * HEC_N; // Q limb of key poly c
     const u64 *zb = P.z + (size_t)(HEC_BJOB >> 1) * HEC_N;
     if (J.c == 0) b5_pointwise<true>(x, sm, st, P, J, M, G, zb, kq);
     else b5_pointwise<false>(x, sm, st, P, J, M, G, zb, kq);

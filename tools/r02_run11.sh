@@ -1,0 +1,8 @@
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r02_pytest9.txt 2>&1; echo "pytest rc $?" >> gpurun_out/r02_pytest9.txt
+tail -4 gpurun_out/r02_pytest9.txt
+python bench.py --steps 20 --warmup 5 --cpu-sample 0 --config4 0 2>&1 | tail -1 > gpurun_out/r02_bench_b.txt
+rm -f gpurun_out/r02_bench_ab7.txt
+for w in keyswitch eval_relu bootstrap_ctos mul_relin; do
+  python bench.py --workload $w --steps 20 --warmup 3 --cpu-sample 0 2>&1 | tail -1 >> gpurun_out/r02_bench_ab7.txt
+done

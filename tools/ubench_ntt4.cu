@@ -84,7 +84,7 @@ int main() {
     for (int i = 0; i < 65536; i++) { u64 w = (0x1234567ull * (i + 1)) % q; h[i] = make_ulonglong2(w, (u64)((((unsigned __int128)w) << 64) / q)); }
     cudaMemcpy(tab, h, 65536 * sizeof(ulonglong2), cudaMemcpyHostToDevice);
     ModC m;
-    m.q = q; m.q2 = 2 * q; m.qinv = 0xff7fffffbff7ffffull /* any odd value: timing only */; m.rmod = 1; m.ninv_w = 1; m.ninv_s = 1; m.psi = tab; m.psi_inv = tab; m.tight = 0; m.small = 0;
+    m.q = q; m.q2 = 2 * q; m.qinv = 0xff7fffffbff7ffffull /* any odd value: timing only */; m.rmod = 1; m.ninv_w = 1; m.ninv_s = 1; m.psi = tab; m.psi_inv = tab; m.tight = 0; m.small = 0; m.mu = 0; m.pad = 0;
     ModC *dm;
     cudaMalloc(&dm, sizeof(ModC));
     cudaMemcpy(dm, &m, sizeof(ModC), cudaMemcpyHostToDevice);

@@ -137,6 +137,9 @@ static int check_launch(hec_ctx *c, const char *what) {
 
 // launch one of the generic kernels (all of them start with HEC_PDL_SYNC); they carry the programmatic-stream-
 // serialisation attribute (HEC_PDL=0 turns it off) so that the launch latency and CTA ramp of a kernel overlap the tail of its predecessor
+#ifndef HEC_FWD16_DEFAULT
+#define HEC_FWD16_DEFAULT 0
+#endif
 #ifndef HEC_DOT_BULK_DEFAULT
 #define HEC_DOT_BULK_DEFAULT 0 // measured (profiles/r02b): k_dot already streams at 5.6 TB/s = 0.87 of the measured HBM peak; the staged variant ties on the key switch and loses 2-8 % on evalReLU / the tap sums
 #endif
@@ -184,6 +187,41 @@ int hec_launch_ntt(hec_ctx *c, std::vector<LimbJob> &jobs, bool inverse) {
         B[i].flags = inverse ? 0 : (j.flags & (HEC_LJ_EPI | HEC_LJ_ADD));
         A[i].scatter_g = 0;
         if (inverse) B[i].scatter_g = 0;
+    }
+    // HEC_FWD16=1: the forward transform as one launch per limb list, a limb per 16-CTA cluster exchanging through
+    // distributed shared memory (k_fwd16); 0: column pass + row pass through global memory
+    static const int fwd16 = getenv("HEC_FWD16") ? atoi(getenv("HEC_FWD16")) : HEC_FWD16_DEFAULT;
+    if (!inverse && fwd16) {
+        static int ready = 0; // 1: usable, -1: this device / driver refuses the cluster shape
+        if (!ready) {
+            bool ok = cudaFuncSetAttribute(k_fwd16, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+                      cudaFuncSetAttribute(k_fwd16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEC_F16_SMEM) == cudaSuccess;
+            cudaGetLastError();
+            ready = ok ? 1 : -1;
+        }
+        if (ready == 1) {
+            std::vector<char> hj(n * sizeof(LimbJob));
+            LimbJob *J = reinterpret_cast<LimbJob *>(hj.data());
+            for (size_t i = 0; i < n; i++) { J[i] = jobs[i]; J[i].mid = nullptr; }
+            char *dj = nullptr;
+            int rc1 = stage_cached(c, hj, &dj);
+            if (rc1) return rc1;
+            static const int pdl = getenv("HEC_PDL") ? atoi(getenv("HEC_PDL")) : 1;
+            for (size_t off = 0; off < n; off += 65535) {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(HEC_TILES_PER_LIMB, (unsigned)std::min<size_t>(65535, n - off));
+                cfg.blockDim = dim3(HEC_THREADS); cfg.dynamicSmemBytes = HEC_F16_SMEM; cfg.stream = c->stream;
+                cudaLaunchAttribute at[2];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = HEC_TILES_PER_LIMB; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at[1].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = at; cfg.numAttrs = pdl ? 2 : 1;
+                cudaLaunchKernelEx(&cfg, k_fwd16, reinterpret_cast<const LimbJob *>(dj) + off, (const ModC *)c->dmods);
+                c->launches += 1;
+            }
+            return check_launch(c, "fwd16");
+        }
     }
     char *dbuf = nullptr;
     int rc = stage_cached(c, h, &dbuf);

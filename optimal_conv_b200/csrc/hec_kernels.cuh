@@ -7,6 +7,7 @@
 //      level 1 -> 0 with one special prime: 3 kernels for Stage A, 5 per pack-tree level.
 // Reference routines each kernel covers are cited at the kernel.
 #pragma once
+#include <cooperative_groups.h>
 #include "hec_dev.cuh"
 
 // =========================================================================================
@@ -154,6 +155,91 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_GEN_MINB) k_col_inv(const Lim
     col_inv8_final(x, sm, G, M);
 #pragma unroll
     for (int k = 0; k < 16; k++) job.out[G.gA(k)] = x[k];
+}
+
+// ---- the forward transform as ONE launch: a limb per thread-block cluster --------------------------------------
+// 16 CTAs form a cluster and own one limb.  CTA r runs the column pass on column tile r (stages with distance >= 256), then
+// every thread hands its 16 coefficients -- rows 16 pg .. 16 pg + 15 of one column, i.e. one column of row tile pg -- to
+// CTA pg by writing them into that CTA's shared memory (distributed shared memory, st.shared::cluster), in the layout the
+// row pass loads.  After a cluster barrier CTA r runs the row pass on row tile r out of its own shared memory and stores
+// the result.  The limb crosses global memory once per 16 stages instead of once per 8 (k_col_fwd + k_row_fwd: write
+// 512 KiB, read it back), and the second launch goes.  Same prologue / epilogue options as the two-launch form.
+// The column pass writes straight into a buffer the row pass of ANOTHER CTA reads, so the receive buffer cannot share
+// storage with the column pass's exchange buffer: 32 KiB + 34 KiB of shared memory per CTA.
+#define HEC_F16_SMEM ((HEC_TILE + 16 * HEC_ROW_PITCH) * sizeof(u64))
+__global__ void __launch_bounds__(HEC_THREADS, HEC_GEN_MINB) k_fwd16(const LimbJob *__restrict__ jobs, const ModC *__restrict__ mods) {
+    namespace cg = cooperative_groups;
+    HEC_PDL_TRIGGER();
+    extern __shared__ __align__(128) u64 dsm[];
+    u64 *sm = dsm;               // exchange buffer of the column pass
+    u64 *rx = dsm + HEC_TILE;    // this CTA's row tile, filled by the 16 CTAs of the cluster; then the row pass's exchange buffer
+    cg::cluster_group cl = cg::this_cluster();
+    const unsigned r = cl.block_rank();
+    HEC_PDL_WAIT();
+    const LimbJob job = jobs[blockIdx.y];
+    const ModC M = mods[job.mod];
+    ColGeom G(r);
+    RowGeom R(r);
+    cl.sync();                   // every CTA of the cluster is resident: its shared memory may be written from now on
+    u64 x[16];
+    if (M.small) {
+        u32 y[16];
+        if (job.flags & HEC_LJ_PRO) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) y[k] = (u32)addmod(canon(job.in[G.gA(k)], M), job.pro_s0, M.q);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; k++) y[k] = (u32)job.in[G.gA(k)];
+        }
+        col_fwd8_32(y, reinterpret_cast<u32 *>(sm), G, M);
+        u32 *dst = reinterpret_cast<u32 *>(cl.map_shared_rank(rx, G.pg));
+        const u32 e = 16 * r + G.cc;
+#pragma unroll
+        for (int k = 0; k < 16; k++) dst[k * HEC_ROW_PITCH + e + (e >> 4)] = y[k];
+        cl.sync();
+        u32 *rx32 = reinterpret_cast<u32 *>(rx);
+#pragma unroll
+        for (int k = 0; k < 16; k++) y[k] = rx32[R.sbase + R.p + 17 * k];
+        __syncwarp();
+        row_fwd8_32(y, rx32, R, M);
+        row_BtoA32(y, rx32, R);
+#pragma unroll
+        for (int k = 0; k < 16; k++) x[k] = cred32(y[k], (u32)M.q);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 16; k++) x[k] = job.in[G.gA(k)];
+        if (job.flags & HEC_LJ_PRO) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) x[k] = addmod(canon(x[k], M), job.pro_s0, M.q);
+        }
+        col_fwd8(x, sm, G, M);   // layout B: slot k <-> row 16 pg + k of column 16 r + cc
+        u64 *dst = cl.map_shared_rank(rx, G.pg);
+        const u32 e = 16 * r + G.cc;
+#pragma unroll
+        for (int k = 0; k < 16; k++) dst[k * HEC_ROW_PITCH + e + (e >> 4)] = x[k];
+        cl.sync();
+#pragma unroll
+        for (int k = 0; k < 16; k++) x[k] = rx[R.sbase + R.p + 17 * k]; // layout A': slot k <-> word p + 16 k of block bb
+        __syncwarp();
+        row_fwd8(x, rx, R, M);
+        row_BtoA(x, rx, R);
+#pragma unroll
+        for (int k = 0; k < 16; k++) x[k] = canon(x[k], M);
+    }
+    if (job.flags & HEC_LJ_EPI) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) x[k] = mred(x[k] + M.q2 - job.ep_b[R.gbase + 16 * k], job.ep_s0, M.q, M.qinv);
+        if (job.flags & HEC_LJ_ADD) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) x[k] = addmod(x[k], job.ep_add[R.gbase + 16 * k], M.q);
+        }
+    }
+    if (job.scatter_g) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) job.out[perm_index(R.gbase + 16 * k, job.scatter_g)] = x[k];
+    } else {
+        row_storeA(x, job.out, R);
+    }
 }
 
 // ---- element-wise ------------------------------------------------------------------------

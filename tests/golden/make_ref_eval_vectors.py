@@ -348,6 +348,168 @@ def layer_helper_case(logN=5):
     return rec
 
 
+EVALCONV = {"logN": 8, "in_wid": 8, "ker_wid": 3, "real_ib": 2, "real_ob": 2, "norm": 2, "seed": 321}
+EVALCONV_PT_SEED = 5200
+
+
+def stub_encoder(m, Q, N, log):
+    """ckks.Encoder whose EncodeCoeffs / EncodeNTT / Encode fill the plaintext they are handed (allocated by the caller with
+    ckks.NewPlaintext, interpreted) with the n-th seeded vector, and whose ToNTT only sets the flag: slot encoding and
+    the float -> residue rounding are pinned elsewhere; what runs for real is everything around them.
+    log: list receiving (level, scale) per call."""
+    def fill(em, ntt, pt_off):
+        sp = em.r[4]
+        pt = em.rq(sp + pt_off)
+        poly = em.rq(em.rq(pt))
+        nl = em.rq(poly + 8)
+        limbs = synth.uniform_limbs(EVALCONV_PT_SEED + len(log), Q[:nl], N)
+        rows = em.rq(poly)
+        for i in range(nl):
+            em.write_u64s(em.rq(rows + 24 * i), ints(limbs[i]))
+        if ntt:
+            em.wb(poly + 24, 1)
+        log.append((nl - 1, b2f(em.rq(pt + 8))))
+    enc_t = CKKS + "(*encoderComplex128)."
+    m.hook(enc_t + "EncodeNTT", lambda em: fill(em, True, 8))
+    m.hook(enc_t + "Encode", lambda em: fill(em, False, 8))
+    m.hook(enc_t + "EncodeCoeffs", lambda em: fill(em, False, 32))     # (values []float64, plaintext): receiver, slice (3 words), pt
+    m.hook(enc_t + "ToNTT", lambda em: em.wb(em.rq(em.rq(em.rq(em.r[4] + 8))) + 24, 1))
+    return [m.sym[ENCODER_ITAB][0], m.alloc(64)]
+
+
+def eval_conv_bn_case():
+    """main.evalConv_BN (eval.go:224-263) on a hand-built main.context (layout from the DWARF: 328 bytes; N @8, ECD_LV @16,
+    pl_idx @112, params @136, encoder @240, evaluator @288, pack_evaluator @304): prep_Ker's float code (reshape_ker,
+    encode_ker_final -- real), the plaintext loop and the bias plaintext through the stub encoder, conv_then_pack, the
+    scale / level check and the bias Add -- real."""
+    c = EVALCONV
+    logN, N = c["logN"], 1 << c["logN"]
+    Q2, P1 = PR.Q_SET6[:2], PR.P_PACK
+    max_bat = N // (c["in_wid"] ** 2)
+    w = synth.conv_workload(Q2, P1, logN, max_bat, c["seed"])
+    m = Machine()
+    keys = {(1 << (j + 1)) + 1: w["keys"][j] for j in w["keys"]}
+    params, ev = m.new_evaluator(logN, Q2, P1, PR.SCALE, keys)
+    rQ = params[8]
+    idx = monomials(m, rQ, logN, Q2[0])
+    pl_idx = [m.new_pt([idx[i]], 1.0) for i in range(logN)]
+    log = []
+    enc = stub_encoder(m, Q2, N, log)
+    cont = m.alloc(328)
+    m.write_u64s(cont, [logN, N, 1])
+    m.write_u64s(cont + 112, m.slice_u64(pl_idx))
+    m.write_u64s(cont + 136, params)
+    m.write_u64s(cont + 240, enc)
+    m.write_u64s(cont + 288, ev)
+    m.write_u64s(cont + 304, ev)
+    c0, c1 = w["ct"][0]
+    ct = m.new_ct([[ints(c0[i]) for i in range(2)], [ints(c1[i]) for i in range(2)]], PR.SCALE)
+
+    def fslice(vals):
+        a = m.alloc(8 * max(1, len(vals)))
+        m.write_u64s(a, [f2b(float(v)) for v in vals])
+        return [a, len(vals), len(vals)]
+    k2 = c["ker_wid"] ** 2
+    rng = np.random.default_rng(c["seed"])
+    ker_in = rng.uniform(-1, 1, k2 * c["real_ib"] * c["real_ob"])
+    bn_a, bn_b = rng.uniform(0.5, 1.5, c["real_ob"]), rng.uniform(-1, 1, c["real_ob"])
+    out = {}
+    for name, out_scale in (("ok", PR.SCALE), ("s25", float(1 << 25))):
+        log.clear()
+        res = m.call("main.evalConv_BN", [cont, ct] + fslice(ker_in) + fslice(bn_a) + fslice(bn_b)
+                     + [c["in_wid"], c["ker_wid"], c["real_ib"], c["real_ob"], c["norm"], f2b(out_scale), 0, 0], max_steps=1 << 62)
+        out[name] = {"out_scale": out_scale, "encodes": [[lv, sc] for lv, sc in log], "out": digest_ct(m, res[-1])}
+    rec = dict(c, Q=["%x" % q for q in Q2], P=["%x" % p for p in P1], pt_seed=EVALCONV_PT_SEED, max_bat=max_bat, cases=out,
+               interpreted_instructions=m.steps)
+    print("evalConv_BN case: %d instructions" % m.steps, flush=True)
+    return rec
+
+
+LAYER = {"logN": 4, "in_wid": 2, "kp_wid": 1, "ker_wid": 1, "real_ib": 4, "real_ob": 4, "norm": 1, "pow": 5.0, "alpha": 0.0, "seed": 654}
+LAYER_STOC_SPECS = [(2, [0, 1, 2], 3), (2, [0, 1, 3], 2)]
+
+
+def layer_operands(N):
+    """seeded operands of layer_case: pack-evaluator workload (conv keys), main-evaluator keys, bootstrapper, StoC factors"""
+    Q, P = PR.Q_SET6, PR.P_ALL
+    keys, kconj, rlk, b = ctos_operands(N)
+    beta = (len(Q) + len(P) - 1) // len(P)
+    for n1, diags, _ in LAYER_STOC_SPECS:
+        for d in diags:
+            for r in (d % n1, (d // n1) * n1):
+                if r and r not in keys:
+                    keys[r] = np.stack([np.stack([synth.uniform_limbs(9000 + 131 * r + 10 * dd + k, list(Q) + list(P), N) for k in range(2)])
+                                        for dd in range(beta)])
+    stoc = [({d: (synth.uniform_limbs(7800 + 100 * i + d, Q[:ml + 1], N), synth.uniform_limbs(7900 + 100 * i + d, P, N)) for d in diags},
+             n1, ml, float(Q[ml])) for i, (n1, diags, ml) in enumerate(LAYER_STOC_SPECS)]
+    return keys, kconj, rlk, b, stoc
+
+
+def layer_case():
+    """main.evalConv_BNRelu_new as the shipped binary has it (it predates the *_sparse kinds: 19 arguments, one
+    bootstrapper), kind "Conv", iter = 2, interpreted end to end on a hand-built main.context over the whole 28 + 5
+    modulus chain at N = 2^4: evalConv_BN on the pack evaluator (one special prime), Scale *= 2^pow,
+    Bootstrapper.BootstrappConv_CtoS, evalReLU + MulByPow2 on both halves, keep_ctxt (stub encoder), BootstrappConv_StoC,
+    Rescale -- the composition hec_conv_bn_relu / Oracle.conv_bn_relu restate."""
+    c = LAYER
+    logN, N = c["logN"], 1 << c["logN"]
+    Q, P, P1 = PR.Q_SET6, PR.P_ALL, PR.P_PACK
+    max_bat = N // (c["in_wid"] ** 2)
+    m = Machine()
+    keys, kconj, rlk, b, stoc = layer_operands(N)
+    gk = {pow(5, r, 2 * N): k for r, k in keys.items()}
+    gk[2 * N - 1] = kconj
+    params, ev = m.new_evaluator(logN, Q, P, PR.SCALE, gk, rlk)
+    w = synth.conv_workload(Q, P1, logN, max_bat, c["seed"])          # the pack evaluator: the same Q chain, one special prime
+    pkeys = {(1 << (j + 1)) + 1: w["keys"][j] for j in w["keys"]}
+    pparams, pev = m.new_evaluator(logN, Q, P1, PR.SCALE, pkeys)
+    idx = monomials(m, pparams[8], logN, Q[0])
+    pl_idx = [m.new_pt([idx[i]], 1.0) for i in range(logN)]
+    log = []
+    enc = stub_encoder(m, Q, N, log)
+    btp = build_bootstrapper(m, logN, params, ev, b, stoc)
+    ext = m.new_map(24)                                               # cont.ext_idx: map[int][][]int
+    rows = m.alloc(48)
+    for ul in range(2):
+        m.write_u64s(rows + 24 * ul, m.slice_u64([1] * (N // 2)))
+    m.map_put(ext, c["in_wid"], [rows, 2, 2])
+    cont = m.alloc(328)
+    m.write_u64s(cont, [logN, N, 1])
+    m.wq(cont + 72, ext)
+    m.write_u64s(cont + 112, m.slice_u64(pl_idx))
+    m.write_u64s(cont + 136, params)
+    m.write_u64s(cont + 240, enc)
+    m.write_u64s(cont + 288, ev)
+    m.write_u64s(cont + 304, pev)
+    m.wq(cont + 320, btp)
+    c0, c1 = w["ct"][0]
+    ct = m.new_ct([[ints(c0[i]) for i in range(2)], [ints(c1[i]) for i in range(2)]], PR.SCALE)
+
+    def fslice(vals):
+        a = m.alloc(8 * max(1, len(vals)))
+        m.write_u64s(a, [f2b(float(v)) for v in vals])
+        return [a, len(vals), len(vals)]
+    rng = np.random.default_rng(c["seed"])
+    k2 = c["ker_wid"] ** 2
+    ker_in = rng.uniform(-1, 1, k2 * c["real_ib"] * c["real_ob"])
+    bn_a, bn_b = rng.uniform(0.5, 1.5, c["real_ob"]), rng.uniform(-1, 1, c["real_ob"])
+    kind = b"Conv"
+    ks = m.alloc(8)
+    for i, ch in enumerate(kind):
+        m.wb(ks + i, ch)
+    for n in ("main.debugCtoS", "main.debugReLU", "main.debugStoC", "main.printDebug", "main.printDebugCfs", "main.prt_mat_norm_step"):
+        if n in m.sym:
+            m.hook(n, lambda em: None)
+    t0 = time.time()
+    res = m.call("main.evalConv_BNRelu_new", [cont, ct] + fslice(ker_in) + fslice(bn_a) + fslice(bn_b)
+                 + [f2b(c["alpha"]), f2b(c["pow"]), c["in_wid"], c["kp_wid"], c["ker_wid"], c["real_ib"], c["real_ob"], c["norm"], 0, 1, 2,
+                    ks, len(kind), 0, 0], max_steps=1 << 62)
+    rec = dict(c, Q=["%x" % q for q in Q], P=["%x" % p for p in P], pt_seed=EVALCONV_PT_SEED, max_bat=max_bat,
+               encodes=[[lv, sc] for lv, sc in log], out=digest_ct(m, res[-1]), interpreted_instructions=m.steps)
+    print("evalConv_BNRelu_new case: %d instructions, %.0f s" % (m.steps, time.time() - t0), flush=True)
+    return rec
+
+
 # ---------------------------------------------------------------- evalReLU (SURVEY 8f rank 2)
 RELU_CASES = [("n5_alpha0", 5, 0.0, 15), ("n6_leaky0.1", 6, 0.1, 15), ("n5_level12", 5, 0.0, 12), ("n5_level8_too_low", 5, 0.0, 8)]
 
@@ -526,18 +688,10 @@ CTOS_LOGN = 4
 ctos_operands, btp_stoc_mats = synth.ctos_operands, synth.btp_stoc_mats   # seeded operands live in the package (bench.py uses them too)
 
 
-def ctos_case(level_in, whole=False):
-    """ckks.(*Bootstrapper).BootstrappConv_CtoS on a hand-built Bootstrapper (struct layout from the DWARF): SetScale /
-    ScaleUp to the bootstrapping scale, modUp, ScaleUp, CoeffsToSlots, evaluateSine (EvaluateCheby + double angle), the
-    fork's final MultByConst + Rescale.  N = 2^4, the whole 28-level chain, alpha = 5."""
-    logN = CTOS_LOGN
+def build_bootstrapper(m, logN, params, ev, b, stoc_mats=None):
+    """a ckks.Bootstrapper laid out by hand (field offsets from the DWARF of the reference binary) around an evaluator the
+    reference's own constructor built: the fields BootstrappConv_CtoS / _StoC / Bootstrapp read"""
     N = 1 << logN
-    Q, P = PR.Q_SET6, PR.P_ALL
-    m = Machine()
-    keys, kconj, rlk, b = ctos_operands(N)
-    gk = {pow(5, r, 2 * N): k for r, k in keys.items()}
-    gk[2 * N - 1] = kconj
-    params, ev = m.new_evaluator(logN, Q, P, PR.SCALE, gk, rlk)
     ptrs = []
     for D, n1, ml, ms in b["mats"]:
         vec = m.new_map(16)
@@ -569,9 +723,9 @@ def ctos_case(level_in, whole=False):
         m.wq(btp + off, f2b(b[k]))
     m.wq(btp + 536, cheb)
     m.write_u64s(btp + 608, m.slice_u64(ptrs))           #   pDFTInv
-    if whole:                                            #   pDFT (only Bootstrapp reads it)
+    if stoc_mats is not None:                            #   pDFT (Bootstrapp and BootstrappConv_StoC read it)
         fptrs = []
-        for D, n1, ml, ms in btp_stoc_mats(N):
+        for D, n1, ml, ms in stoc_mats:
             vec = m.new_map(16)
             for d, (dq, dp) in D.items():
                 pq, pp = m.new_poly([ints(l) for l in dq]), m.new_poly([ints(l) for l in dp])
@@ -583,6 +737,22 @@ def ctos_case(level_in, whole=False):
             m.write_u64s(mat, [logN - 1, n1, ml, f2b(ms), vec, 0])
             fptrs.append(mat)
         m.write_u64s(btp + 584, m.slice_u64(fptrs))
+    return btp
+
+
+def ctos_case(level_in, whole=False):
+    """ckks.(*Bootstrapper).BootstrappConv_CtoS on a hand-built Bootstrapper (struct layout from the DWARF): SetScale /
+    ScaleUp to the bootstrapping scale, modUp, ScaleUp, CoeffsToSlots, evaluateSine (EvaluateCheby + double angle), the
+    fork's final MultByConst + Rescale.  N = 2^4, the whole 28-level chain, alpha = 5."""
+    logN = CTOS_LOGN
+    N = 1 << logN
+    Q, P = PR.Q_SET6, PR.P_ALL
+    m = Machine()
+    keys, kconj, rlk, b = ctos_operands(N)
+    gk = {pow(5, r, 2 * N): k for r, k in keys.items()}
+    gk[2 * N - 1] = kconj
+    params, ev = m.new_evaluator(logN, Q, P, PR.SCALE, gk, rlk)
+    btp = build_bootstrapper(m, logN, params, ev, b, btp_stoc_mats(N) if whole else None)
     ct_scale = PR.SCALE * 2.0 ** 8
     lim = lambda seed: [ints(l) for l in synth.uniform_limbs(seed, Q[:level_in + 1], N)]  # noqa: E731
     ct = m.new_ct([lim(61), lim(62)], ct_scale)
@@ -757,12 +927,15 @@ def main():
         new["conv"] = {name: conv_case(logN, B, norm, seed, out_scale, Q2, P1)
                        for name, logN, B, norm, seed, out_scale, Q2, P1 in SMALL_CONV if name in sys.argv}
     else:
-        ALL = ("relu", "evalops", "lt", "ctos", "btp", "ring", "conv", "encode", "hostprep", "helpers")
+        ALL = ("relu", "evalops", "lt", "ctos", "btp", "ring", "conv", "encode", "hostprep", "helpers", "layer")
         groups = [g for g in ALL if "--" + g in sys.argv] or list(ALL)
         if "hostprep" in groups:
             new["hostprep"] = hostprep_case()
         if "helpers" in groups:
             new["layer_helpers"] = layer_helper_case()
+            new["eval_conv_bn"] = eval_conv_bn_case()
+        if "layer" in groups:
+            new["layer"] = layer_case()
         if "encode" in groups:
             new["encode_coeffs"] = {name: encode_case(name) for name in common.ENCODE_CASES}
         if "relu" in groups:

@@ -169,6 +169,49 @@ def test_between_layer_helpers_match_reference_main_code():
     assert dg(o.post_conv_bl(cts, [mask(t) for t in range(k2)], PR.SCALE)) == e["out"]
 
 
+def test_eval_conv_bn_matches_reference_main_code():
+    """main.evalConv_BN (eval.go:224-263) interpreted on a hand-built main.context with a stub encoder: the number, order,
+    levels and scales of the plaintexts it encodes (max_bat kernels at ECD_LV / params.Scale(), then the bias at level 0 /
+    out_scale), conv_then_pack, the consistency check and the bias Add == the oracle on the same seeded plaintexts"""
+    rec = REF["eval_conv_bn"]
+    Q, P = mods(rec)
+    logN, N = rec["logN"], 1 << rec["logN"]
+    o = Oracle(logN, Q, P)
+    w = synth.conv_workload(Q, P, logN, rec["max_bat"], rec["seed"])
+    idx = o.monomial_pts()
+    for name, c in rec["cases"].items():
+        assert c["encodes"] == [[1, PR.SCALE]] * rec["max_bat"] + [[0, c["out_scale"]]], name
+        pl_ker = np.stack([synth.uniform_limbs(rec["pt_seed"] + i, Q[:2], N) for i in range(rec["max_bat"])])
+        bias = synth.uniform_limbs(rec["pt_seed"] + rec["max_bat"], Q[:1], N)[0]
+        r = o.conv_then_pack(Ct(*w["ct"][0], PR.SCALE), pl_ker, PR.SCALE, rec["norm"], c["out_scale"], idx, w["keys"], bias)[0]
+        assert dg(r) == c["out"], name
+
+
+def test_eval_conv_bn_relu_new_matches_reference_main_code():
+    """main.evalConv_BNRelu_new as the shipped binary has it (kind "Conv", iter = 2), interpreted end to end over the whole
+    28 + 5 modulus chain at N = 2^4 on a hand-built main.context and Bootstrapper with a stub encoder (5.6e7 instructions):
+    evalConv_BN on the pack evaluator, Scale *= 2^pow, BootstrappConv_CtoS, evalReLU + MulByPow2 per half, keep_ctxt per half,
+    BootstrappConv_StoC, Rescale == Oracle.conv_bn_relu, the composition hec_conv_bn_relu is tested against on the GPU"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_ref_eval_vectors as G
+    rec = REF["layer"]
+    Q, P = mods(rec)
+    logN, N, mb = rec["logN"], 1 << rec["logN"], rec["max_bat"]
+    op, o = Oracle(logN, Q, PR.P_PACK), Oracle(logN, Q, P)
+    keys, kconj, rlk, b, stoc = G.layer_operands(N)
+    w = synth.conv_workload(Q, PR.P_PACK, logN, mb, rec["seed"])
+    out_scale = 2.0 ** round(np.log2(float(Q[0])) - (rec["pow"] + 8))               # eval.go:369
+    assert rec["encodes"] == [[1, PR.SCALE]] * mb + [[0, out_scale]] + [[4, float(Q[4])]] * 2
+    pt = lambda n, lv: synth.uniform_limbs(rec["pt_seed"] + n, Q[:lv + 1], N)       # noqa: E731  (the stub encoder's n-th plaintext)
+    pl_ker = np.stack([pt(i, 1) for i in range(mb)])
+    r = Oracle.conv_bn_relu(op, o, Ct(w["ct"][0][0][:2], w["ct"][0][1][:2], PR.SCALE), pt_ker=[pl_ker], pt_bias=[pt(mb, 0)[0]],
+                            pt_scale=PR.SCALE, norm=[rec["norm"]], out_scale=out_scale, pt_idx=op.monomial_pts(), pack_keys=w["keys"],
+                            pow=rec["pow"], alpha=rec["alpha"], iter=2, btp=b, keys=keys, key_conj=kconj, rlk=rlk, stoc_mats=stoc,
+                            min_scale=PR.SCALE, keep_mask=[pt(mb + 1, 4), pt(mb + 2, 4)], keep_scale=float(Q[4]))
+    assert dg(r) == rec["out"]
+
+
 def test_pre_conv_bl_matches_reference_main_code():
     """main.preConv_BL (conv.go:120-143), interpreted: the k^2 hoisted rotations i*in_wid + j (negative steps and
     the zero step included) of the baseline convolution == the oracle's rotations, in the reference's order"""

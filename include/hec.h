@@ -214,7 +214,8 @@ int hec_moddown(hec_ctx *ctx, int level, const uint64_t *const *accQ, const uint
 #define HEC_CONV_OPLEVEL 1 /* replay conv.go:522-546 / 266-300 op by op through the evaluator ops */
 /* conv_then_pack (conv.go:522-546) [+ Add(pl_bn_b) of evalConv_BN, eval.go:258, when pt_bias != NULL].
  * pt_ker[max_ob] at level ECD_LV, pt_idx[logN] (gen_idxNlogs, conv.go:241-261), keys for galEl
- * 2^j+1 must have been uploaded.  Returns HEC_E_SCALE on the reference's consistency panic. */
+ * 2^j+1 must have been uploaded.  Returns HEC_E_SCALE on the reference's consistency panic.  The fused path takes
+ * max_ob <= 4096 (all packings the reference uses, up to in_wid 4) at a level-1 input; HEC_E_UNSUPPORTED beyond. */
 int hec_conv_then_pack(hec_ctx *ctx, const hec_ct *ct_in, const hec_pt *const *pt_ker, int max_ob, int norm,
                        double out_scale, const hec_pt *const *pt_idx, const hec_pt *pt_bias, int flags,
                        hec_ct **out);

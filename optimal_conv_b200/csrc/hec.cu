@@ -76,6 +76,11 @@ void build_mod(HostMod &m, u64 q) {
             for (u32 p = 0; p < 16; p++) put(HEC_TW_ROWB + 240 * blk + 16 * j + p, 4096 + 16 * blk + p, j);
 }
 
+// moduli below 2^31 take the 32-bit transforms and the narrow basis-extension products (HEC_NO_SMALL=1: A/B switch)
+static bool narrow_modulus(u64 q) {
+    static const bool off = getenv("HEC_NO_SMALL") != nullptr;
+    return !off && q < (1ull << 31);
+}
 static void build_modup(const hec_ctx *c, ModupTab &T, const std::vector<int> &src) {
     int n = (int)src.size(), nt = c->nQ + c->nP;
     T.n = n;
@@ -90,7 +95,8 @@ static void build_modup(const hec_ctx *c, ModupTab &T, const std::vector<int> &s
         for (int t = 0; t < nt; t++) {
             u64 pt = c->q(t), s = 1;
             for (int k = 0; k < n; k++) if (k != i) s = mulmod(s, c->q(src[k]) % pt, pt);
-            T.qisp[t][i] = mform(s, pt);
+            // targets below 2^31 (the narrow path of k_modup2): plain residue | (residue * 2^32 mod p) << 32
+            T.qisp[t][i] = narrow_modulus(pt) ? (s | (mulmod(s, (1ull << 32) % pt, pt) << 32)) : mform(s, pt);
         }
     }
     for (int t = 0; t < nt; t++) {
@@ -422,7 +428,7 @@ extern "C" int hec_ctx_create(hec_ctx **out, int logN, const uint64_t *Q, int nQ
         mc[i].psi = psi; mc[i].psi_inv = psi_inv;
         mc[i].tight = c->hm[i].q >= (1ull << 57) ? 1 : 0;
         mc[i].mu = c->hm[i].q > (1ull << 40) ? (u32)(((u128)1 << 64) / c->hm[i].q) : 0; mc[i].pad = 0;
-        mc[i].small = (c->hm[i].q < (1ull << 31) && !getenv("HEC_NO_SMALL")) ? 1 : 0; // HEC_NO_SMALL: A/B switch
+        mc[i].small = narrow_modulus(c->hm[i].q) ? 1 : 0;
     }
     if (cudaMemcpy(c->dmods, mc.data(), nm * sizeof(ModC), cudaMemcpyHostToDevice) != cudaSuccess) return bail(HEC_E_CUDA);
     // RescaleParams (L:ring/ring.go:63-117)

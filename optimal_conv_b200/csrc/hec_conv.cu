@@ -415,8 +415,8 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
                                hec_plan **out) {
     if (!c || !pt_ker || !pt_idx || !out || batch < 1 || max_ob < 1 || norm < 1) return c ? c->fail(HEC_E_INVAL, "plan args") : HEC_E_INVAL;
     cudaSetDevice(c->device);
-    if ((max_ob & (max_ob - 1)) || (norm & (norm - 1)) || norm > max_ob || max_ob > 256)
-        return c->fail(HEC_E_UNSUPPORTED, "max_ob and norm must be powers of two, max_ob <= 256");
+    if ((max_ob & (max_ob - 1)) || (norm & (norm - 1)) || norm > max_ob || max_ob > 4096)
+        return c->fail(HEC_E_UNSUPPORTED, "max_ob and norm must be powers of two, max_ob <= 4096");
     if (c->nQ < 2 || c->nP != 1) return c->fail(HEC_E_UNSUPPORTED, "fused conv needs >= 2 Q limbs and exactly one special prime (main.go:446-454)");
     // the epilogues of A3 / B5 add a few q to an uncorrected forward transform (< 68q) and B5 sums up to 9 lazy terms
     // before one reduction: needs q0 < 2^57; the quotient estimate of reduce_lazy needs q0 > 2^40
@@ -533,7 +533,7 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
         u64 g = (1ull << j) + 1;
         auto it = c->keys.find(g);
         if (it == c->keys.end()) return bail(HEC_E_NOKEY, "rotation key for a pack level is missing");
-        if (j < 9) return bail(HEC_E_UNSUPPORTED, "automorphism not local to a 256-word block");
+        if (j < 5) return bail(HEC_E_UNSUPPORTED, "automorphism not local to a 4096-word tile");
         if (!pt_idx[logStep]) return bail(HEC_E_INVAL, "pt_idx entry missing");
         ConvB b;
         memset(&b, 0, sizeof b);
@@ -787,7 +787,7 @@ static int plan_cached(hec_ctx *c, const hec_pt *const *pt_ker, int max_ob, int 
                        const hec_pt *const *pt_idx, const hec_pt *pt_bias, hec_plan **out) {
     std::vector<uint64_t> key;
     auto bits = [](double d) { uint64_t u; memcpy(&u, &d, 8); return u; };
-    if (max_ob >= 1 && norm >= 1 && norm <= max_ob && max_ob <= 256) {
+    if (max_ob >= 1 && norm >= 1 && norm <= max_ob && max_ob <= 4096) {
         // serials start at 1 and only grow, so the small integers in front cannot be mistaken for one by evict()
         // once they are offset into the top of the range
         key = {~(uint64_t)max_ob, ~(uint64_t)(norm + 1000), bits(in_scale), bits(out_scale), pt_bias ? pt_bias->serial : 0};

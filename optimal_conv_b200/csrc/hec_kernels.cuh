@@ -462,6 +462,8 @@ struct ModupJobs { ModupJob j[HEC_MUJOBS]; };
 // source, so they are computed once per coefficient (the per-target form above recomputes alpha Montgomery products
 // and alpha double divisions for each of the up to nQ + nP - alpha targets: it was 51 % of a full-level key switch).
 #define HEC_M2_MAXT 48 // targets per group (host splits larger groups); nQ + nP <= 33 in the reference's sets
+// qisp[s]: MForm(Q_d/q_s mod p_t); for a target below 2^31 instead the plain residue c in the low word and c * 2^32 mod p_t in
+// the high word (k_modup2's narrow path)
 struct Modup2Target { u64 *dst; u64 qisp[HEC_MAXA]; u64 qpjinv[HEC_MAXA + 1]; int tmod; };
 struct Modup2Job {
     const u64 *src[HEC_MAXA];
@@ -496,6 +498,25 @@ __global__ void __launch_bounds__(256) k_modup2(const Modup2Job *__restrict__ jo
     for (int t = 0; t < job.ntargets; t++) {
         const Modup2Target &T = sT[t];
         const u64 pt = mods[T.tmod].q, ptinv = mods[T.tmod].qinv;
+        if (mods[T.tmod].small) {
+            // target below 2^31: y * c = y_hi * (c 2^32 mod p) + y_lo * c, two 32 x 32 products per source (each term below
+            // 2^63 + 2^60, the sum of five below 2^66: a 64-bit accumulator and a carry count), then one reduction
+            u64 lo = 0;
+            u32 carry = 0;
+#pragma unroll
+            for (int s = 0; s < HEC_MAXA; s++)
+                if (s < job.n) {
+                    const u32 c = (u32)T.qisp[s], c2 = (u32)(T.qisp[s] >> 32);
+                    const u64 term = (u64)(u32)y[s] * c + (u64)(u32)(y[s] >> 32) * c2;
+                    lo += term;
+                    carry += lo < term;
+                }
+            const u64 rm = mods[T.tmod].rmod;                          // 2^64 mod p
+            u64 acc = mred(lo, rm, pt, ptinv);                          // lo mod p
+            for (u32 k = 0; k < carry; k++) acc = addmod(acc, rm, pt);
+            T.dst[i] = addmod(acc, T.qpjinv[v], pt);
+            continue;
+        }
         // multSum (L:ring/ring_basis_extension.go:715-779): the alpha products are summed as 128-bit integers and
         // reduced once -- each is < 2^61 p_t, so the sum of <= 5 stays below p_t 2^64, the domain of one REDC
         u64 lo = 0, hi = 0;
@@ -818,13 +839,18 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_B5_MINB) k_convB5(ConvB P, co
     const u64 *zb = P.z + (size_t)(HEC_BJOB >> 1) * HEC_N;
     if (J.c == 0) b5_pointwise<true>(x, sm, st, P, J, M, G, zb, kq);
     else b5_pointwise<false>(x, sm, st, P, J, M, G, zb, kq);
-    __syncwarp();
+    // sigma_g for g = 2^j + 1 keeps the top j - 1 bits of the (bit-reversed) slot index: for j >= 9 a slot stays inside its
+    // 256-word block (this half-warp's own), for 5 <= j < 9 inside the CTA's 4096-word tile (the wide packings: B > 256)
+    const bool in_block = P.galEl > 512u;
+    if (in_block) __syncwarp(); else __syncthreads();
     u64 *out = P.xout + (size_t)HEC_BJOB * HEC_N;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         u32 i = G.gbase + 16 * k;
-        u32 s = perm_index(i, P.galEl) & 255u;                       // sigma_g stays inside the block
+        u32 s = perm_index(i, P.galEl) & (HEC_TILE - 1);             // position inside the tile
+        u32 sb = in_block ? G.sbase : (s >> 8) * HEC_ROW_PITCH;
+        s &= 255u;
         u32 e = G.p + 16 * k;
-        out[i] = canon16(st[G.sbase + e + (e >> 4)] + sm[G.sbase + s + (s >> 4)], M.q); // < 9q
+        out[i] = canon16(st[G.sbase + e + (e >> 4)] + sm[sb + s + (s >> 4)], M.q); // < 9q
     }
 }

@@ -212,7 +212,7 @@ class Resnet:
             t0 = time.perf_counter()
             ker_in, bn_a, bn_b = self._weights(s, 1000 * seed + li)
             max_bat = N // (s["in_wid"] ** 2)
-            flags = hec.CONV_FUSED if max_bat <= 256 else hec.CONV_OPLEVEL   # first pack levels of B = 1024 leave the 256-word block
+            flags = hec.CONV_FUSED
             if s["kind"] == "final":
                 ker, bias = self._encode_conv(ker_in, bn_a, bn_b, s["in_wid"], s["ker_wid"], s["real_ib"], s["real_ob"], s["norm"], PR.SCALE)
                 t1 = time.perf_counter()

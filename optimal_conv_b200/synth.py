@@ -35,7 +35,7 @@ def uniform_limbs(seed: int, moduli, n: int) -> np.ndarray:
     return np.stack([uniform_mod(seed * 1000003 + 7919 * i, n, q) for i, q in enumerate(moduli)])
 
 
-def conv_workload(Q, P, logN, B, seed, n_ct=1):
+def conv_workload(Q, P, logN, B, seed, n_ct=1, kernels=True):
     """Seeded synthetic operands of one evalConv_BN hot interval:
     n_ct level-1 input ciphertexts, B kernel plaintexts (level 1), a level-0 bias plaintext,
     and rotation keys (uniform words read as NTT+Montgomery form) for the pack levels of B.
@@ -47,7 +47,8 @@ def conv_workload(Q, P, logN, B, seed, n_ct=1):
     w = {"B": B, "N": N}
     w["ct"] = [(uniform_limbs(seed * 31 + 2 * m, q2, N), uniform_limbs(seed * 31 + 2 * m + 1, q2, N))
                for m in range(n_ct)]
-    w["pt_ker"] = np.stack([uniform_limbs(seed * 977 + 100 + i, q2, N) for i in range(B)])
+    if kernels:  # kernels=False: only the ciphertexts, the bias and the pack keys of B (wide packings with few real channels)
+        w["pt_ker"] = np.stack([uniform_limbs(seed * 977 + 100 + i, q2, N) for i in range(B)])
     w["bias"] = uniform_mod(seed * 131 + 7, N, Q[0])
     keys = {}
     step, log_step = B // 2, 0

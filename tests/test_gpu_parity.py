@@ -1074,6 +1074,53 @@ def test_plan_at_the_bench_shape_64_ciphertexts_16_channels(orc, idx_np):
         c.close()
 
 
+def test_conv_1024_channels_of_which_64_real(orc, idx_np):
+    """the packing of the ResNet's third block (in_wid 8: max_batch = 1024, norm = 16, test.go:94-95): the first pack levels
+    use g = 2^7 + 1 and 2^8 + 1, whose automorphisms leave the 256-word block but not the CTA's 4096-word tile; fused path ==
+    op-level replay == oracle"""
+    c = hec.Context(PR.LOGN, Q2, P1)
+    try:
+        B, norm = 1024, 16
+        w = synth.conv_workload(Q2, P1, PR.LOGN, B, seed=1024)
+        ker = [c.upload_pt(w["pt_ker"][i], PR.SCALE) if i % norm == 0 else None for i in range(B)]
+        idx = [c.upload_pt(idx_np[i:i + 1], 1.0) for i in range(PR.LOGN)]
+        bias = c.upload_pt(w["bias"][None, :], PR.SCALE)
+        for j, k in w["keys"].items():
+            c.upload_swk((1 << (j + 1)) + 1, k, 0)
+        ct = c.upload_ct(w["ct"][0][0], w["ct"][0][1], PR.SCALE)
+        ref = common.oracle_conv(orc, w, norm, PR.SCALE, idx_np, nthreads=os.cpu_count() or 1)
+        for flags in (hec.CONV_FUSED, hec.CONV_OPLEVEL):
+            g0, g1 = c.conv_then_pack(ct, ker, norm, PR.SCALE, idx, bias, flags).download()
+            assert np.array_equal(g0, ref.c0) and np.array_equal(g1, ref.c1), flags
+    finally:
+        c.close()
+
+
+def test_conv_4096_slots_is_the_last_fused_packing(idx_np):
+    """max_batch = 4096 (in_wid 4), 64 real channels: the widest packing the fused path takes (g = 2^5 + 1 still maps a
+    4096-word tile onto itself); its operands would be 4 GiB for the oracle, so the check is fused == op-level replay (which the
+    1024-channel case above and the B <= 256 cases pin against the oracle), and 8192 is refused by the fused path"""
+    c = hec.Context(PR.LOGN, Q2, P1)
+    try:
+        B, norm = 4096, 64
+        w = synth.conv_workload(Q2, P1, PR.LOGN, 64, seed=4096)          # 64 kernels, bias, one ciphertext
+        keys = synth.conv_workload(Q2, P1, PR.LOGN, B, seed=4097, kernels=False)["keys"]
+        ker = [c.upload_pt(w["pt_ker"][i // norm], PR.SCALE) if i % norm == 0 else None for i in range(B)]
+        idx = [c.upload_pt(idx_np[i:i + 1], 1.0) for i in range(PR.LOGN)]
+        bias = c.upload_pt(w["bias"][None, :], PR.SCALE)
+        for j, k in keys.items():
+            c.upload_swk((1 << (j + 1)) + 1, k, 0)
+        ct = c.upload_ct(w["ct"][0][0], w["ct"][0][1], PR.SCALE)
+        outs = [c.conv_then_pack(ct, ker, norm, PR.SCALE, idx, bias, flags).download()
+                for flags in (hec.CONV_FUSED, hec.CONV_OPLEVEL)]
+        assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+        with pytest.raises(hec.HecError) as e:
+            c.conv_then_pack(ct, ker + [None] * B, norm, PR.SCALE, idx, bias, hec.CONV_FUSED)
+        assert e.value.code == hec.HEC_E_UNSUPPORTED
+    finally:
+        c.close()
+
+
 def test_plan_batch_with_norm_and_no_bias(orc, idx_np):
     """batch of 2 ciphertexts, B = 8 with norm = 2 (4 real channels, 2 pack levels), bias omitted"""
     c = hec.Context(PR.LOGN, Q2, P1)
@@ -1093,3 +1140,27 @@ def test_plan_batch_with_norm_and_no_bias(orc, idx_np):
         plan.destroy()
     finally:
         c.close()
+
+
+def test_resnet_chain_runs_level_by_level_and_is_deterministic():
+    """optimal_conv_b200/resnet.py on the device: the depth-8 variant of the reference's chain (3 + 1 + 1 + 1 + 1 bootstrapped
+    layers + the final FC, test.go:96-104) on synthetic keys / masks / matrices with the real supports -- every layer
+    one hec_conv_bn_relu call that hands a level-1 ciphertext at params.Scale() to the next, the final layer a level-0
+    one; two runs give the same bits."""
+    import hashlib
+    from optimal_conv_b200 import resnet
+    net = resnet.Resnet(hec, depth=8, ker_wid=3)
+    try:
+        image = np.random.default_rng(5).uniform(0, 1, 32 * 32 * 3)
+        digs = []
+        for _ in range(2):
+            ct, rec = net.run(image, seed=3)
+            assert [r["layer"] for r in rec] == [s["name"] for s in net.specs] and len(rec) == 8
+            assert [r["level_out"] for r in rec] == [1] * 7 + [0]
+            assert ct.scale == PR.SCALE
+            g0, g1 = ct.download()
+            digs.append(hashlib.sha256(g0.tobytes() + g1.tobytes()).hexdigest())
+            ct.free()
+        assert digs[0] == digs[1]
+    finally:
+        net.close()

@@ -39,25 +39,45 @@ def conv_alg_limbs(B):
     return 10 * B - 1 + 4 * (B.bit_length() - 1)
 
 
-def kernel_limbs(name, M, B, first_launch_only=False, algorithmic=False):
+def kernel_limbs(name, M, B, first_launch_only=False, algorithmic=False, deferred=False):
     """Limbs fused kernel `name` reads + writes, summed over its launches in one run (Stage A: 1 launch; Stage B: one
     per pack level) or for its first launch.
     algorithmic=False: DISTINCT limbs the launch moves, scratch included (DESIGN.md "Kernels"; what ncu's dram__bytes
     should show when nothing is fetched twice).
     algorithmic=True: SURVEY.md 8(d) -- only operands and results of the reference operations the kernel completes
     (input ciphertexts, plaintexts, key slices, output ciphertexts); half-transformed scratch counts for nothing, so
-    extra passes over a limb show up as a lower achieved figure."""
+    extra passes over a limb show up as a lower achieved figure.
+    deferred=True: the plan carries level-0 polynomials as pairs (U, e): the U half stands for the
+    reference's ciphertext in the algorithmic count, the e half is scratch."""
     na, jobs = B, M * B * 2
-    if name == "A1":
-        return 2 * M + na + (0 if algorithmic else jobs)      # ct limb q1 of both polys, pt limb q1 per channel (-> w1)
-    if name == "A2":
-        return 0 if algorithmic else 2 * jobs                  # w1 -> w2
-    if name == "A3":
-        return 2 * M + na + jobs + (0 if algorithmic else jobs)  # ct limb q0, pt limb q0, level-0 output (<- w2)
+    if deferred:
+        if name == "A1":
+            return 4 * M + 2 * na + jobs + (0 if algorithmic else jobs)   # ct (2 polys x 2 limbs), pt (2 limbs), U out (-> w1)
+        if name == "A2":
+            return 0 if algorithmic else 2 * jobs                          # w1 -> e
+        if name == "F1":
+            return 0 if algorithmic else 4 * M
+        if name == "F2":
+            return 2 * M + 1 + (0 if algorithmic else 4 * M)               # result, bias (<- w, U)
+    else:
+        if name == "A1":
+            return 2 * M + na + (0 if algorithmic else jobs)      # ct limb q1 of both polys, pt limb q1 per channel (-> w1)
+        if name == "A2":
+            return 0 if algorithmic else 2 * jobs                  # w1 -> w2
+        if name == "A3":
+            return 2 * M + na + jobs + (0 if algorithmic else jobs)  # ct limb q0, pt limb q0, level-0 output (<- w2)
     tot, n = 0, na
     while n > 1:
         nbt = M * (n // 2)                  # butterflies in this level's launch
-        if algorithmic:
+        if deferred and algorithmic:
+            tot += {"B1": 2 * nbt, "B2": 0, "B3": 2, "B4": 0, "B5": 6 * nbt + 3}[name]  # U halves of a, b (4), out (2); monomial, 2 key Q limbs
+        elif deferred:
+            tot += {"B1": 4 * nbt + 2,      # Ua1, Ub1, monomial pairs -> z, w1
+                    "B2": 5 * nbt,          # w1, ea1, eb1 -> w2 (p0), w4 (q0)
+                    "B3": 3 * nbt + 2,
+                    "B4": 8 * nbt,          # per polynomial: w3, ea, eb -> e out
+                    "B5": 7 * nbt + 6}[name]  # w4, z, Ua0, Ua1, Ub0 -> 2 U out; monomial pairs, 2 key Q limbs as pairs
+        elif algorithmic:
             tot += {"B1": 2 * nbt, "B2": 0, "B3": 2, "B4": 0,            # a1, b1 | - | key P limbs | -
                     "B5": 6 * nbt + 3 + (1 if n == 2 else 0)}[name]      # a, b (4), out (2); monomial, 2 key Q limbs (+ bias)
         else:
@@ -79,16 +99,25 @@ def group_alg_limbs(M, B):
     return 6 * nbt + 4 + 1
 
 
-NCU_SUMMARY = {64: "r02c_ncu_summary.csv"}   # capture of the default `python bench.py` command (final kernels of the round)
+NCU_SUMMARY = {64: "r02c_ncu_summary.csv"}   # capture of the default `python bench.py` command with HEC_DEFER=0
+NCU_SUMMARY_DEFERRED = {64: "r02e_ncu_summary.csv"}   # the same with deferred transforms (the default plan)
 
 
-def ncu_traffic(kernel, cts):
+def kname(short, deferred):
+    """kernel symbol of a plan launch: the deferred plan reuses k_convB1 / k_convB3 and has its own A1, A2, B2, B4, B5, F1, F2"""
+    if deferred and short not in ("B1", "B3"):
+        return "k_def" + short
+    return "k_conv" + short
+
+
+def ncu_traffic(kernel, cts, deferred=False):
     """dram bytes (read + write) of the first launch of `kernel` from the committed ncu --set full capture of the
     same command, or None."""
     import csv
-    if cts not in NCU_SUMMARY:
+    table = NCU_SUMMARY_DEFERRED if deferred else NCU_SUMMARY
+    if cts not in table:
         return None
-    p = os.path.join(ROOT, "profiles", NCU_SUMMARY[cts])
+    p = os.path.join(ROOT, "profiles", table[cts])
     try:
         rows = list(csv.reader(open(p)))
         h, units = rows[0], rows[1]                       # ncu scales units per column: the second row names them
@@ -660,21 +689,26 @@ def main():
     # "the dominant kernel": the longest-running one among the kernels that read or write ciphertexts of the reference
     # operation they complete, i.e. whose algorithmic bytes in the sense of SURVEY.md 8(d) grow with the batch (A1, A3, B1,
     # B5); A2, B2, B4 only move half-transformed scratch (0 such bytes) and B3 adds two key limbs to that
+    deferred = plan.deferred
     dom = max((k for k in per_kernel if k in ("A1", "A3", "B1", "B5")), key=lambda k: per_kernel[k]["ms_per_run"])
     dom_ms = per_kernel[dom]["ms_per_run"]
     n_l = per_kernel[dom]["launches_per_run"]
     share = dom_ms / sum(v["ms_per_run"] for v in per_kernel.values())
     # roofline of the dominant kernel, per launch, on its first (largest) launch of a run
     first_ms = sum(prof[dom][i * n_l] for i in range(3)) / 3
-    alg_bytes_launch = kernel_limbs(dom, M, B, first_launch_only=True, algorithmic=True) * LIMB
-    distinct_bytes_launch = kernel_limbs(dom, M, B, first_launch_only=True) * LIMB
+    alg_bytes_launch = kernel_limbs(dom, M, B, first_launch_only=True, algorithmic=True, deferred=deferred) * LIMB
+    distinct_bytes_launch = kernel_limbs(dom, M, B, first_launch_only=True, deferred=deferred) * LIMB
     achieved = alg_bytes_launch / (first_ms / 1e3) / 1e9
     # the NTT + key-switch kernel group of the first pack level (B1..B5 together)
     grp_ms = sum(sum(prof[k][i * per_kernel[k]["launches_per_run"]] for i in range(3)) / 3 for k in ("B1", "B2", "B3", "B4", "B5") if k in prof)
     grp_bytes = group_alg_limbs(M, B) * LIMB
     # integer ceiling: modular multiplies of one conv / measured modmul throughput
-    units = 4 * B * 2 + 12 * (B - 1)                     # half-transforms (8 stages) per conv
-    modmuls = units * (N // 2) * 8 + (5 * B * 2 + 10 * (B - 1)) * N
+    if deferred:   # 1 transform per channel and polynomial, 5 per butterfly, 2 at the end; fewer point-wise products too
+        units = 2 * B * 2 + 10 * (B - 1) + 4
+        modmuls = units * (N // 2) * 8 + (3 * B * 2 + 8 * (B - 1)) * N
+    else:
+        units = 4 * B * 2 + 12 * (B - 1)                 # half-transforms (8 stages) per conv
+        modmuls = units * (N // 2) * 8 + (5 * B * 2 + 10 * (B - 1)) * N
     sm_mhz = (sampler.summary().get("sm_mhz") or 1965.0)
     int_peak = INT_MODMUL_PER_CLK_SM * 148 * sm_mhz * 1e6
     conv_bytes = conv_alg_limbs(B) * LIMB
@@ -694,15 +728,16 @@ def main():
                         "the host so no L2 flush applies); kernel plaintexts/keys resident like a reused prep_Ker result"},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
-        "roofline": {"bound": "hbm", "kernel": "k_conv" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": ncu_traffic("k_conv" + dom, M) if B == 16 else None,
+        "roofline": {"bound": "hbm", "kernel": kname(dom, deferred), "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": ncu_traffic(kname(dom, deferred), M, deferred) if B == 16 else None,
                      "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes_launch,
                      "alg_bytes_definition": "SURVEY.md 8(d): operands and results of the reference operations only; scratch excluded",
                      "distinct_bytes_per_launch": distinct_bytes_launch, "launch_ms": first_ms,
                      "launch": "first (largest) of %d launches per run" % n_l, "share_of_step": share,
                      "kernel_selection": "longest among the kernels whose algorithmic bytes grow with the batch (A1, A3, B1, B5); the "
                                          "scratch-to-scratch passes A2, B2, B3, B4 are covered by roofline_group / roofline_conv",
-                     "traffic_source": "profiles/%s (ncu --set full, same command)" % NCU_SUMMARY.get(M, "-")},
+                     "traffic_source": "profiles/%s (ncu --set full, same command)" % (NCU_SUMMARY_DEFERRED if deferred else NCU_SUMMARY).get(M, "-"),
+                     "plan": "deferred forward transforms (DESIGN.md 4.5)" if deferred else "transform per rescale / mod-down"},
         "roofline_group": {"kernels": "k_convB1..B5 (NTT + key-switch group), first pack level", "bound": "hbm",
                            "alg_bytes": grp_bytes, "ms": grp_ms, "achieved": (grp_bytes / (grp_ms / 1e3) / 1e9) if grp_ms else None,
                            "peak": peak, "unit": "GB/s", "frac": (grp_bytes / (grp_ms / 1e3) / 1e9 / peak) if grp_ms else None},

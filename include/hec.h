@@ -309,6 +309,14 @@ int hec_plan_span_end_ms(hec_plan *plan, float *ms);
 /* per-launch device times (ms) of one run with the kernels launched one by one, in launch
  * order A1,A2,A3,(B1..B5) per pack level -- measurement aid for the roofline report */
 int hec_plan_profile(hec_plan *plan, const hec_ct *const *ins, float *ms, int cap, int *n);
+/* names of those launches, comma separated, in order ("A1,A2,A3,B1,...,B5" per pack level; a plan whose forward
+ * transforms are deferred -- see below -- has "A1,A2,B1..B5,...,F1,F2"); returns their number */
+int hec_plan_kernel_names(const hec_plan *plan, char *buf, int cap);
+/* 1 if the plan carries its level-0 polynomials as pairs (U, e), value = U - NTT(e), and runs one forward transform per
+ * output polynomial at the end instead of one per rescale / mod-down (same results bit for bit; chosen at creation when
+ * max_ob <= 256 and the pl_idx plaintexts are the monomials of conv.go:241-254; HEC_DEFER=0 in the environment turns it
+ * off) */
+int hec_plan_is_deferred(const hec_plan *plan);
 void hec_plan_destroy(hec_plan *plan);
 /* hec_conv_then_pack (fused) keeps the plans it builds, keyed by its arguments' identities (plaintext and key
  * uploads, max_ob, norm, scales): a per-convolution caller (conv.go:522, one call per image with the layer's

@@ -266,6 +266,9 @@ struct hec_plan {
     // chunked execution: the M ciphertexts of a run are worked through in chunks of Mc on `nchains` concurrent chains
     // (forked streams inside the captured graph), each chain with scratch of its own, so that what one kernel of a chunk
     // writes is still in L2 when the next kernel of that chunk reads it
+    // deferred-transform plan (hec_kernels.cuh (3)): level-0 polynomials as pairs (U, e); 2 + 5 per level + 2 launches
+    bool defer = false;
+    u64 *efinal = nullptr, *ufinal = nullptr, *wfin = nullptr;
     int Mc = 0, nchains = 1;
     std::vector<cudaStream_t> chain_streams;
     std::vector<cudaEvent_t> chain_events;
@@ -314,6 +317,32 @@ static int plan_launch_chunk(hec_plan *p, const ConvA &A, const std::vector<Conv
                              const std::function<void()> &after) {
     hec_ctx *c = p->c;
     dim3 gA = HEC_GRID(HEC_TILES_PER_LIMB, Mc * p->na * 2);
+    if (p->defer) {
+        k_defA1<<<gA, HEC_THREADS, 0, s>>>(A, c->dmods);
+        after();
+        k_defA2<<<gA, HEC_THREADS, 0, s>>>(A, c->dmods);
+        after();
+        for (auto &b : Bs) {
+            int nb = b.n / 2;
+            dim3 g1 = HEC_GRID(HEC_TILES_PER_LIMB, Mc * nb), g2 = HEC_GRID(HEC_TILES_PER_LIMB, Mc * nb * 2);
+            k_convB1<<<g1, HEC_THREADS, 0, s>>>(b, c->dmods);
+            after();
+            k_defB2<<<g1, HEC_THREADS, HEC_DB2_SMEM, s>>>(b, c->dmods);
+            after();
+            k_convB3<<<g1, HEC_THREADS, HEC_B3_SMEM, s>>>(b, c->dmods);
+            after();
+            k_defB4<<<g2, HEC_THREADS, HEC_DB4_SMEM, s>>>(b, c->dmods);
+            after();
+            k_defB5<<<g1, HEC_THREADS, HEC_B5_SMEM, s>>>(b, c->dmods);
+            after();
+        }
+        dim3 gF = HEC_GRID(HEC_TILES_PER_LIMB, Mc * 2);
+        k_defF1<<<gF, HEC_THREADS, 0, s>>>(p->efinal, p->wfin, A.mq0, c->dmods);
+        after();
+        k_defF2<<<gF, HEC_THREADS, 0, s>>>(p->wfin, p->ufinal, p->bias, p->xfinal, A.mq0, c->dmods);
+        after();
+        return HEC_OK;
+    }
     k_convA1<<<gA, HEC_THREADS, 0, s>>>(A, c->dmods);
     after();
     k_convA2<<<gA, HEC_THREADS, 0, s>>>(A, c->dmods);
@@ -365,7 +394,7 @@ static int plan_launch_all(hec_plan *p, const std::function<void()> &after = [] 
             cudaStreamWaitEvent(s, p->chain_events[ch], 0);
         }
     }
-    if (p->levels == 0 && p->bias) { // single channel: bias not folded into a B5 epilogue
+    if (p->levels == 0 && p->bias && !p->defer) { // single channel: bias not folded into a B5 epilogue
         EwJobs J;
         for (int m = 0; m < p->M; m++) {
             u64 *x = p->xfinal + (size_t)m * 2 * HEC_N;
@@ -410,6 +439,37 @@ extern "C" void hec_plan_destroy(hec_plan *p) {
     delete p;
 }
 
+// The deferred-transform plan turns the products with the pack monomials into index shifts of coefficients, so the
+// plaintexts the caller passes as pl_idx must BE the monomials X^step of gen_idxNlogs (conv.go:241-254): compare each
+// with the transform of the unit vector.  Returns 1 / 0, or a negative error code.
+static int pack_monomials_check(hec_ctx *c, const hec_pt *const *pt_idx, int B, int na) {
+    u64 *tmp = nullptr;
+    int *flag = nullptr;
+    if (cudaMalloc(&tmp, 3 * HEC_N * sizeof(u64)) != cudaSuccess) return HEC_E_NOMEM;
+    if (cudaMalloc(&flag, sizeof(int)) != cudaSuccess) { cudaFree(tmp); return HEC_E_NOMEM; }
+    cudaMemsetAsync(flag, 0, sizeof(int), c->stream);
+    static const u64 one = 1;
+    int step = B / 2, logStep = 0, rc = HEC_OK;
+    for (int i = step; i > 1; i /= 2) logStep++;
+    for (int t = na; t > 1 && !rc; t >>= 1, step /= 2, logStep--) {
+        if (!pt_idx[logStep]) { rc = HEC_E_INVAL; break; }
+        cudaMemsetAsync(tmp, 0, HEC_N * sizeof(u64), c->stream);
+        cudaMemcpyAsync(tmp + step, &one, sizeof(u64), cudaMemcpyHostToDevice, c->stream);
+        std::vector<LimbJob> nj;
+        nj.push_back({tmp, tmp + HEC_N, c->modQ(0), 0, nullptr, nullptr, 0, 0, nullptr, 0});
+        if ((rc = hec_launch_ntt(c, nj, false))) break;
+        k_plan_tables<<<64, 256, 0, c->stream>>>(pt_idx[logStep]->buf, nullptr, tmp + 2 * HEC_N, c->modQ(0), c->dmods);
+        k_count_diff<<<64, 256, 0, c->stream>>>(tmp + HEC_N, tmp + 2 * HEC_N, flag);
+        c->launches += 2;
+    }
+    int h = 0;
+    if (!rc && cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) rc = HEC_E_CUDA;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) rc = HEC_E_CUDA;
+    cudaFree(tmp);
+    cudaFree(flag);
+    return rc ? rc : (h == 0 ? 1 : 0);
+}
+
 extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_ob, int norm, double in_scale,
                                double out_scale, const hec_pt *const *pt_idx, const hec_pt *pt_bias, int batch,
                                hec_plan **out) {
@@ -445,6 +505,16 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
     for (int t = na; t > 1; t >>= 1) levels++;
     p->levels = levels;
     auto bail = [&](int code, const char *msg) { hec_plan_destroy(p); return c->fail(code, msg); };
+    {   // HEC_DEFER=0: every mod-down / rescale ends in the NTT domain (the round-1/2 kernels, (2) in hec_kernels.cuh)
+        static const int env_defer = getenv("HEC_DEFER") ? atoi(getenv("HEC_DEFER")) : 1;
+        if (env_defer && B <= 256) {
+            int ok = pack_monomials_check(c, pt_idx, B, na);
+            if (ok < 0) return bail(ok, "checking the pack monomials");
+            p->defer = ok == 1;
+        }
+    }
+    const int mq0_ = c->modQ(0);
+    const u64 q1inv0 = invmod(c->q(c->modQ(1)) % c->q(mq0_), c->q(mq0_)); // q1^-1 mod q0
     // ---- device memory: pointer tables + one pool ----
     if (cudaMalloc((void **)&p->d_ctin, M * sizeof(u64 *)) != cudaSuccess) return bail(HEC_E_NOMEM, "cudaMalloc");
     if (cudaMalloc((void **)&p->d_ptk, B * sizeof(ulonglong2 *)) != cudaSuccess) return bail(HEC_E_NOMEM, "cudaMalloc");
@@ -458,8 +528,11 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
         for (int a = 0; a < na; a++) {
             u64 *dst = p->ptk_scaled + (size_t)a * 2 * HEC_N;
             hk[a * norm] = p->ptk_pairs + (size_t)a * 2 * HEC_N;
-            for (int l = 0; l < 2; l++)
-                ej.push_back(ewjob(pt_ker[a * norm]->buf + (size_t)l * HEC_N, nullptr, dst + (size_t)l * HEC_N, c->modQ(l), mform(k[l], c->q(c->modQ(l)))));
+            for (int l = 0; l < 2; l++) {
+                // deferred plan: the q0 limb also carries the 1/q1 of the rescale (U = ct*pt*k0/q1)
+                const u64 ql = c->q(c->modQ(l)), kl = (p->defer && l == 0) ? mulmod(k[0] % ql, q1inv0, ql) : k[l];
+                ej.push_back(ewjob(pt_ker[a * norm]->buf + (size_t)l * HEC_N, nullptr, dst + (size_t)l * HEC_N, c->modQ(l), mform(kl, ql)));
+            }
         }
         if (launch_ew<EW_MULSCALAR>(c, ej)) return bail(HEC_E_CUDA, "scaling kernel plaintexts");
         for (int a = 0; a < na; a++)
@@ -477,7 +550,7 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
     {
         static const int env_chunk = getenv("HEC_PLAN_CHUNK") ? atoi(getenv("HEC_PLAN_CHUNK")) : HEC_PLAN_CHUNK_DEFAULT;
         static const int env_chains = getenv("HEC_PLAN_CHAINS") ? atoi(getenv("HEC_PLAN_CHAINS")) : HEC_PLAN_CHAINS_DEFAULT;
-        p->Mc = (env_chunk > 0 && env_chunk < M && M % env_chunk == 0) ? env_chunk : M;
+        p->Mc = (!p->defer && env_chunk > 0 && env_chunk < M && M % env_chunk == 0) ? env_chunk : M;
         p->nchains = std::max(1, std::min(env_chains, M / p->Mc));
     }
     const int Mc = p->Mc;
@@ -486,7 +559,8 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
     size_t per_chain = 2 * jobsAc + nb0c * 7;    // w1, w2; wb1, wb2, wb3 x2, wb4 x2, z
     size_t limbs = 4 * (size_t)M                 // staged inputs [M][2][2]
                  + (size_t)p->nchains * per_chain
-                 + 2 * jobsA;                    // X_0 .. X_last (geometric, < 2x)
+                 + 2 * jobsA                     // X_0 .. X_last (geometric, < 2x)
+                 + (p->defer ? 2 * jobsA + 4 * (size_t)M : 0); // deferred: the e halves of every level, the last transform's scratch, the results
     if (cudaMalloc(&p->pool, limbs * HEC_N * sizeof(u64)) != cudaSuccess) return bail(HEC_E_NOMEM, "cudaMalloc plan pool");
     u64 *cur = p->pool;
     auto take = [&](size_t n) { u64 *r = cur; cur += n * HEC_N; return r; };
@@ -494,6 +568,12 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
     u64 *w1 = take((size_t)p->nchains * per_chain), *w2 = nullptr; // chain scratch sets; carved up in plan_chunk_args
     std::vector<u64 *> X(levels + 1);
     for (int l = 0; l <= levels; l++) X[l] = take((size_t)M * (na >> l) * 2);
+    std::vector<u64 *> XE(levels + 1, nullptr);
+    if (p->defer) {
+        for (int l = 0; l <= levels; l++) XE[l] = take((size_t)M * (na >> l) * 2);
+        p->wfin = take(2 * (size_t)M);
+    }
+    u64 *xres = p->defer ? take(2 * (size_t)M) : nullptr;
     u64 *wb1 = nullptr, *wb2 = nullptr, *wb3 = nullptr, *wb4 = nullptr, *wbz = nullptr;
     if (p->M / p->Mc > 1) {
         if (cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) != cudaSuccess) return bail(HEC_E_CUDA, "event");
@@ -505,7 +585,8 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
             p->chain_events.push_back(ev);
         }
     }
-    p->xfinal = X[levels];
+    p->xfinal = p->defer ? xres : X[levels];
+    p->ufinal = X[levels]; p->efinal = XE[levels];
     // ---- Stage A constants ----
     const int mq0 = c->modQ(0), mq1 = c->modQ(1), mp0 = c->modP(0);
     const u64 q0 = c->q(mq0), q1 = c->q(mq1), p0 = c->q(mp0);
@@ -516,6 +597,7 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
     A.hneg0 = q0 - A.half1 % q0;
     auto pair = [](u64 w, u64 q) { return make_ulonglong2(w, (u64)(((u128)w << 64) / q)); };
     A.resc0 = pair(q0 - invmod(q1 % q0, q0), q0);
+    A.uout = X[0]; A.eout = XE[0]; A.q1inv = pair(q1inv0, q0);
     if (levels > 0 && (cudaMalloc(&p->mono_pairs, (size_t)levels * HEC_N * sizeof(ulonglong2)) != cudaSuccess ||
                        cudaMalloc(&p->key_pairs, (size_t)levels * 2 * HEC_N * sizeof(ulonglong2)) != cudaSuccess))
         return bail(HEC_E_NOMEM, "cudaMalloc");
@@ -548,7 +630,9 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
             const int kl = it->second.Lk + c->nP, poff = it->second.Lk;
             ulonglong2 *kp = p->key_pairs + (size_t)l * 2 * HEC_N;
             for (int pc = 0; pc < 2; pc++) {
-                k_plan_tables<<<64, 256, 0, c->stream>>>(it->second.buf + (size_t)(pc * kl) * HEC_N, kp + (size_t)pc * HEC_N, nullptr, mq0, c->dmods);
+                // deferred plan: the Q limb of the key carries the 1/P of the mod-down (U = digit * key / P)
+                k_plan_tables<<<64, 256, 0, c->stream>>>(it->second.buf + (size_t)(pc * kl) * HEC_N, kp + (size_t)pc * HEC_N, nullptr, mq0, c->dmods,
+                                                          p->defer ? invmod(p0 % q0, q0) : 1ull);
                 c->launches++;
             }
             b.key = kp;
@@ -563,9 +647,22 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
         b.qpj1 = c->pq.qpjinv[mq0][1];
         b.vthr = hec_float_quotient_threshold(p0);
         b.mu0 = (u32)(((u128)1 << 64) / q0);
+        if (p->defer) {
+            b.ein = XE[l]; b.eout = XE[l + 1];
+            u32 gi = 1;
+            for (int it2 = 0; it2 < 6; it2++) gi *= 2u - (u32)g * gi; // Newton: g^-1 mod 2^32
+            b.ginv = gi & (2u * HEC_N - 1u);
+            b.step = (u32)step;
+            b.pinv = pair(invmod(p0 % q0, q0), q0);
+            b.bias = nullptr; // added by the last transform (k_defF2)
+        }
         p->pb.push_back(b);
     }
-    p->launches_per_run = (3 + 5 * levels) * (M / p->Mc) + ((levels == 0 && pt_bias) ? M : 0);
+    p->launches_per_run = p->defer ? 4 + 5 * levels : (3 + 5 * levels) * (M / p->Mc) + ((levels == 0 && pt_bias) ? M : 0);
+    if (cudaFuncSetAttribute(k_defB2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEC_DB2_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(k_defB4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEC_DB4_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(k_defB5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEC_B5_SMEM) != cudaSuccess)
+        return bail(HEC_E_CUDA, "cudaFuncSetAttribute(k_defB2/B4/B5)");
     if (cudaFuncSetAttribute(k_convB3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEC_B3_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(k_convB5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEC_B5_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(k_convA3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEC_A3_SMEM) != cudaSuccess)
@@ -647,7 +744,7 @@ extern "C" int hec_plan_profile(hec_plan *p, const hec_ct *const *ins, float *ms
     hec_ctx *c = p->c;
     cudaSetDevice(c->device);
     const int nk = p->launches_per_run, nchunks = p->M / p->Mc;
-    const int per_chunk = 3 + 5 * p->levels, nout = nchunks > 1 ? per_chunk : nk; // chunks are folded: one time per kernel position
+    const int per_chunk = (p->defer ? 4 : 3) + 5 * p->levels, nout = nchunks > 1 ? per_chunk : nk; // chunks are folded: one time per kernel position
     if (cap < nout) return c->fail(HEC_E_INVAL, "profile buffer too small");
     std::vector<const u64 *> ptrs(p->M);
     for (int m = 0; m < p->M; m++) {
@@ -671,6 +768,30 @@ extern "C" int hec_plan_profile(hec_plan *p, const hec_ct *const *ins, float *ms
     for (auto &e : ev) cudaEventDestroy(e);
     *n = std::min(k, nout);
     return rc;
+}
+
+// names of the launches hec_plan_profile times, in order, comma separated ("A1,A2,A3,B1,..." -- or, for a plan with
+// deferred transforms, "A1,A2,B1,...,B5,...,F1,F2"); returns their number, or a negative code
+extern "C" int hec_plan_kernel_names(const hec_plan *p, char *buf, int cap) {
+    if (!p || !buf || cap < 1) return HEC_E_INVAL;
+    std::string s = p->defer ? "A1,A2" : "A1,A2,A3";
+    int n = p->defer ? 2 : 3;
+    for (int l = 0; l < p->levels; l++, n += 5) s += ",B1,B2,B3,B4,B5";
+    if (p->defer) { s += ",F1,F2"; n += 2; }
+    if ((int)s.size() + 1 > cap) return HEC_E_INVAL;
+    memcpy(buf, s.c_str(), s.size() + 1);
+    return n;
+}
+extern "C" int hec_plan_is_deferred(const hec_plan *p) { return p && p->defer ? 1 : 0; }
+// development aid (not in hec.h): the (U, e) halves a deferred plan left at pack level `level` after its last run,
+// [M * (na >> level)][2][N] words each, copied to host memory
+extern "C" int hec_plan_debug_level(hec_plan *p, int level, int half, uint64_t *host) {
+    if (!p || !p->defer || level < 0 || level > p->levels || !host) return HEC_E_INVAL;
+    const u64 *src = level == p->levels ? (half ? p->efinal : p->ufinal) : (half ? p->pb[level].ein : p->pb[level].xin);
+    cudaSetDevice(p->c->device);
+    cudaStreamSynchronize(p->c->stream);
+    size_t words = (size_t)p->M * (p->na >> level) * 2 * HEC_N;
+    return cudaMemcpy(host, src, words * sizeof(u64), cudaMemcpyDeviceToHost) == cudaSuccess ? HEC_OK : HEC_E_CUDA;
 }
 
 // ---- pipelined host runs -------------------------------------------------------------------

@@ -566,6 +566,9 @@ struct ConvA {
     u64 half1;              // (q1-1)>>1
     u64 hneg0;              // q0 - (half1 mod q0)
     ulonglong2 resc0;       // q0 - q1^-1 mod q0  (RescaleParams) as a Shoup pair
+    // deferred-transform plans (k_def*): the level-0 ciphertexts leave stage A as pairs (U, e), value = U - NTT(e)
+    u64 *uout, *eout;       // [M*na][2][N] each: U in the NTT domain, e in the coefficient domain (natural order)
+    ulonglong2 q1inv;       // q1^-1 mod q0 as a Shoup pair (the q0 limb of ptk carries the same factor)
 };
 struct AJob {
     int c, a, m;
@@ -644,10 +647,10 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convA3(ConvA P, const
 // plan set-up (once per plan): a Montgomery-form plaintext limb as Shoup pairs (w, floor(w * 2^64 / q)), or as plain
 // residues.  The quotient is a 64-step restoring division -- q < 2^61, so the shifted remainder never overflows.
 __global__ void __launch_bounds__(256) k_plan_tables(const u64 *__restrict__ in, ulonglong2 *pairs, u64 *plain, int mod,
-                                                     const ModC *__restrict__ mods) {
+                                                     const ModC *__restrict__ mods, u64 factor = 1ull) {
     const u64 q = mods[mod].q, qinv = mods[mod].qinv;
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < HEC_N; i += gridDim.x * blockDim.x) {
-        const u64 w = mred(in[i], 1ull, q, qinv);
+        const u64 w = mred(in[i], factor, q, qinv); // out of Montgomery form, times `factor` (a plain residue)
         if (plain) plain[i] = w;
         if (pairs) {
             u64 rem = w, quo = 0;
@@ -658,6 +661,13 @@ __global__ void __launch_bounds__(256) k_plan_tables(const u64 *__restrict__ in,
             pairs[i] = make_ulonglong2(w, quo);
         }
     }
+}
+
+// plan set-up: number of positions where two limbs differ
+__global__ void __launch_bounds__(256) k_count_diff(const u64 *__restrict__ a, const u64 *__restrict__ b, int *ndiff) {
+    int d = 0;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < HEC_N; i += gridDim.x * blockDim.x) d += a[i] != b[i];
+    if (d) atomicAdd(ndiff, d);
 }
 
 // ---- Stage B: one level of pack_ctxts (conv.go:286-297).  For butterfly (a = ct[i], b = ct[i+step]):
@@ -682,6 +692,12 @@ struct ConvB {
     u64 vthr;        // smallest y < p0 with uint64(float64(y)/float64(p0)) = 1 (~0: none): the float overflow count
                      // of the single-prime extension is a step function of y (hec_float_quotient_threshold)
     u32 mu0;         // floor(2^64 / q0)
+    // deferred-transform plans (k_def*): xin / xout hold the U halves, ein / eout the e halves; `key` carries P^-1
+    const u64 *ein;  // [M*n][2][N]
+    u64 *eout;       // [M*n/2][2][N]
+    u32 ginv;        // galEl^-1 mod 2N
+    u32 step;        // the level's monomial is X^step
+    ulonglong2 pinv; // P^-1 mod q0 as a Shoup pair
 };
 struct BJob {
     int c, u, m;
@@ -852,5 +868,243 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_B5_MINB) k_convB5(ConvB P, co
         s &= 255u;
         u32 e = G.p + 16 * k;
         out[i] = canon16(st[G.sbase + e + (e >> 4)] + sm[sb + s + (s >> 4)], M.q); // < 9q
+    }
+}
+
+// =========================================================================================
+// (3) the same path with the forward transforms deferred (tests/defer_model.py is the CPU model)
+// =========================================================================================
+// The rescale of stage A and both mod-downs of a butterfly END with a forward transform under q0 whose result is only
+// ever added to, multiplied by a monomial, permuted by sigma_g -- all of which can be done on its coefficients -- or fed
+// to the NEXT key switch, which starts by transforming back.  A level-0 polynomial is therefore carried as a pair
+// (U, e), value = U - NTT(e) mod q0: U in the NTT domain (what came out of point-wise products), e in the coefficient
+// domain (what came out of a basis change).  On e a monomial product is a negacyclic shift, sigma_g the index map
+// n -> n g mod 2N with a sign, both exact; the value is formed only where it is needed: as d = InvNTT(U) - e for the c1
+// polynomial that enters a key switch (d IS the digit; its transforms under q0 and p0 feed the key products), and once
+// per output polynomial at the end.  Transforms per convolution: 3B + 5(B-1) + 2 instead of 4B + 6(B-1); every step is
+// exact arithmetic modulo q0 and what passes through the special prime is unchanged, so the canonical result is the
+// reference's bit for bit.  Requires the pack monomials to BE monomials (checked at plan creation) and g = 1 mod 256
+// (sigma_g on coefficients then stays inside a column tile): B <= 256.
+
+// X^step * e at coefficient n (e canonical): e[n - step], or -e[n - step + N] for the `step` coefficients that wrap
+__device__ __forceinline__ u64 shifted_coeff(const u64 *__restrict__ e, u32 n, u32 step, u64 q) {
+    return n >= step ? e[n - step] : q - e[n + HEC_N - step]; // [0,q]
+}
+// dA1: limb q0: U = ct*(pt*k0/q1) (stored) ; limb q1: ct*(pt*k1) -> inverse stages t = 1..128   (A1 + the product of A3)
+__global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_defA1(ConvA P, const ModC *__restrict__ mods) {
+    __shared__ u64 sm[16 * HEC_ROW_PITCH];
+    const AJob J(HEC_BJOB, P.na);
+    const ModC M = mods[P.mq1];
+    const u64 q0 = mods[P.mq0].q;
+    RowGeom G(HEC_BTILE);
+    const u64 *ct = P.ctin[J.m] + (size_t)(J.c * 2) * HEC_N;
+    const ulonglong2 *pt = P.ptk[J.a * P.norm];
+    u64 *uo = P.uout + (size_t)HEC_BJOB * HEC_N;
+    u64 x[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        u32 i = G.gbase + 16 * k;
+        x[k] = shoup4(ct[HEC_N + i], __ldg(pt + HEC_N + i), M.q); // < 4q1
+    }
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        u32 i = G.gbase + 16 * k;
+        uo[i] = cred(shoup(ct[i], __ldg(pt + i), q0), q0);
+    }
+    row_AtoB(x, sm, G);
+    row_inv8(x, sm, G, M);
+    row_storeA(x, P.w1 + (size_t)HEC_BJOB * HEC_N, G);
+}
+// dA2: finish InvNTT_q1, centre, lift into q0, divide by q1: e (coefficient domain, natural order)
+__global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_defA2(ConvA P, const ModC *__restrict__ mods) {
+    __shared__ u64 sm[HEC_TILE];
+    const ModC M1 = mods[P.mq1];
+    const ModC M0 = mods[P.mq0];
+    ColGeom G(HEC_BTILE);
+    const u64 *in = P.w1 + (size_t)HEC_BJOB * HEC_N;
+    u64 *out = P.eout + (size_t)HEC_BJOB * HEC_N;
+    u64 x[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) x[k] = in[G.gB(k)];
+    col_inv8_final(x, sm, G, M1);
+    const bool fits = M1.q <= M0.q;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        u64 t = cred(x[k] + P.half1, M1.q);
+        u64 r = (fits ? t : canon(t, M0)) + P.hneg0;                  // [0,2q0)
+        out[G.gA(k)] = cred(shoup(r, P.q1inv, M0.q), M0.q);
+    }
+}
+// dB1 = k_convB1 on the U halves (z = Ua1 - Ub1*mono, inverse stages t = 1..128)
+// dB2: finish InvNTT_q0, subtract the e half of tmp2.c1 (ea1 - X^step eb1): the digit d, canonical; forward stages
+//      m = 1..128 of d under p0 (-> w2) AND under q0 (-> w4): the value of tmp2.c1 is NTT_q0(d)
+#define HEC_DB2_SMEM (2 * HEC_TILE * sizeof(u64))
+__global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_defB2(ConvB P, const ModC *__restrict__ mods) {
+    extern __shared__ __align__(128) u64 dsm[];
+    u64 *sm = dsm, *stash = dsm + HEC_TILE;
+    const ModC MQ = mods[P.mq0];
+    const ModC MP = mods[P.mp0];
+    ColGeom G(HEC_BTILE);
+    const int nb = P.n >> 1, m = HEC_BJOB / nb, u = HEC_BJOB % nb;
+    const u64 *ea = P.ein + ((size_t)(m * P.n + u) * 2 + 1) * HEC_N;
+    const u64 *eb = P.ein + ((size_t)(m * P.n + u + nb) * 2 + 1) * HEC_N;
+    const u64 *in = P.w1 + (size_t)HEC_BJOB * HEC_N;
+    u64 x[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) x[k] = in[G.gB(k)];
+    col_inv8_final(x, sm, G, MQ);
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const u32 n = G.gA(k);
+        u64 d = x[k] + (MQ.q - ea[n]) + shifted_coeff(eb, n, P.step, MQ.q); // [0,3q]
+        d = cred(cred(d, MQ.q2), MQ.q);
+        x[k] = d;
+        stash[k * HEC_THREADS + threadIdx.x] = d; // own slots only
+    }
+    if (!(MQ.q <= MP.q2)) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) x[k] = canon(x[k], MP);
+    }
+    col_fwd8(x, sm, G, MP);
+    u64 *outp = P.w2 + (size_t)HEC_BJOB * HEC_N;
+#pragma unroll
+    for (int k = 0; k < 16; k++) outp[G.gB(k)] = x[k];
+#pragma unroll
+    for (int k = 0; k < 16; k++) x[k] = stash[k * HEC_THREADS + threadIdx.x];
+    col_fwd8(x, sm, G, MQ);
+    u64 *outq = P.w4 + (size_t)HEC_BJOB * HEC_N;
+#pragma unroll
+    for (int k = 0; k < 16; k++) outq[G.gB(k)] = x[k];
+}
+// dB3 = k_convB3 (NTT_p0 of the digit, key products on the P limb, inverse stages t = 1..128 for both key polys)
+// dB4: finish InvNTTLazy_p0, exact basis extension P -> q0, divide by P: the e half of the key-switch output;
+//      add the e half of tmp2.c0 (c = 0), apply sigma_g on coefficients (row permutation with sign inside the column
+//      tile), add the e half of tmp1                                                grid.y = M*nb*2
+#define HEC_DB4_SMEM (2 * HEC_TILE * sizeof(u64))
+__global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_defB4(ConvB P, const ModC *__restrict__ mods) {
+    extern __shared__ __align__(128) u64 dsm[];
+    u64 *sm = dsm, *T = dsm + HEC_TILE;
+    const ModC MP = mods[P.mp0];
+    const ModC MQ = mods[P.mq0];
+    ColGeom G(HEC_BTILE);
+    const int nb = P.n >> 1, c = HEC_BJOB & 1, bu = HEC_BJOB >> 1, m = bu / nb, u = bu % nb;
+    const u64 *ea = P.ein + ((size_t)(m * P.n + u) * 2 + c) * HEC_N;
+    const u64 *eb = P.ein + ((size_t)(m * P.n + u + nb) * 2 + c) * HEC_N;
+    const u64 *in = P.w3 + (size_t)HEC_BJOB * HEC_N;
+    u64 x[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) x[k] = in[G.gB(k)];
+    col_inv8_final(x, sm, G, MP);
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const u32 n = G.gA(k);
+        const u64 y = x[k];
+        const u64 ext = reduce_lazy(y, MQ.q, P.mu0) + (y >= P.vthr ? P.qpj1 : 0ull); // [0,3q0)
+        u64 t = shoup(ext, P.pinv, MQ.q);                                           // [0,2q)
+        const u64 a = ea[n], sh = shifted_coeff(eb, n, P.step, MQ.q);
+        if (c == 0) t += a + (MQ.q - sh);                                           // + e half of tmp2.c0, <= 4q
+        T[G.sA(k)] = t;
+        x[k] = a + sh;                                                              // e half of tmp1, <= 2q
+    }
+    __syncthreads();
+    u64 *out = P.eout + (size_t)HEC_BJOB * HEC_N;
+    const u64 q4 = 2 * MQ.q2;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const u32 n = G.gA(k);
+        const u32 src = (n * P.ginv) & (2u * HEC_N - 1u);    // sigma(T)[n] = +-T[n g^-1 mod 2N]; same column for g = 1 mod 256
+        const u32 r = src >> 8;                              // row 0..511: past 255 the sign flips
+        const u64 t = T[(r & 255u) * 16 + G.cc];
+        out[n] = canon8(x[k] + ((r & 256u) ? q4 - t : t), MQ.q); // <= 6q
+    }
+}
+// dB5: finish NTT_q0 of the digit = the value of tmp2.c1, ONCE for both key polys; for each: product with key[c]/P
+//      (Q limb), + the U half of tmp2.c0 (c = 0), sigma_g inside the 256-word block, + the U half of tmp1   grid.y = M*nb
+template <bool C0>
+__device__ __forceinline__ void defb5_pointwise(const u64 (&x)[16], u64 *sm, u64 *st, const ConvB &P, const BJob &J, const ModC &M,
+                                                const RowGeom &G, const u64 *__restrict__ zb, const ulonglong2 *__restrict__ kq) {
+    const u64 *__restrict__ a = C0 ? J.a : J.a + HEC_N;
+    const u64 *__restrict__ b = J.b;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const u32 i = G.gbase + 16 * k, e = G.p + 16 * k;
+        u64 d = shoup4(x[k], __ldg(kq + i), M.q);                               // U half of the key-switch output, < 4q
+        u64 t1;
+        if (C0) {
+            const u64 a0 = a[i];
+            const u64 m0 = shoup(b[i], __ldg(P.mono + i), M.q);                 // [0,2q)
+            d += a0 + M.q2 - m0;                                                // + U half of tmp2.c0, < 7q
+            t1 = a0 + m0;                                                       // < 3q
+        } else {
+            t1 = 2 * a[i] + 3 * M.q - zb[i];                                    // Ua1 + Ub1*mono = 2 Ua1 - z, in (0,5q)
+        }
+        sm[G.sbase + e + (e >> 4)] = d;
+        st[G.sbase + e + (e >> 4)] = t1;
+    }
+}
+__global__ void __launch_bounds__(HEC_THREADS, HEC_B5_MINB) k_defB5(ConvB P, const ModC *__restrict__ mods) {
+    extern __shared__ __align__(128) u64 dsm[];
+    u64 *sm = dsm, *st = dsm + 16 * HEC_ROW_PITCH;
+    const BJob J(HEC_BJOB, false, P);
+    const ModC M = mods[P.mq0];
+    RowGeom G(HEC_BTILE);
+    u64 x[16];
+    row_loadA(x, P.w4 + (size_t)HEC_BJOB * HEC_N, G);
+    row_fwd8(x, sm, G, M);
+    row_BtoA(x, sm, G);
+    const u64 *zb = P.z + (size_t)HEC_BJOB * HEC_N;
+    const bool in_block = P.galEl > 512u;
+#pragma unroll 1
+    for (int c = 0; c < 2; c++) {
+        if (c == 0) defb5_pointwise<true>(x, sm, st, P, J, M, G, zb, P.key);
+        else defb5_pointwise<false>(x, sm, st, P, J, M, G, zb, P.key + HEC_N);
+        if (in_block) __syncwarp(); else __syncthreads();
+        u64 *out = P.xout + (size_t)(HEC_BJOB * 2 + c) * HEC_N;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            u32 i = G.gbase + 16 * k;
+            u32 s = perm_index(i, P.galEl) & (HEC_TILE - 1);
+            u32 sb = in_block ? G.sbase : (s >> 8) * HEC_ROW_PITCH;
+            s &= 255u;
+            u32 e = G.p + 16 * k;
+            out[i] = canon16(st[G.sbase + e + (e >> 4)] + sm[sb + s + (s >> 4)], M.q); // < 10q
+        }
+        if (in_block) __syncwarp(); else __syncthreads();
+    }
+}
+// dF1 / dF2: the one forward transform per output polynomial: out = U - NTT(e) (+ bias on c0), canonical
+__global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_defF1(const u64 *__restrict__ ein, u64 *__restrict__ w, int mq0,
+                                                                 const ModC *__restrict__ mods) {
+    __shared__ u64 sm[HEC_TILE];
+    const ModC M = mods[mq0];
+    ColGeom G(HEC_BTILE);
+    const u64 *in = ein + (size_t)HEC_BJOB * HEC_N;
+    u64 *out = w + (size_t)HEC_BJOB * HEC_N;
+    u64 x[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) x[k] = in[G.gA(k)];
+    col_fwd8(x, sm, G, M);
+#pragma unroll
+    for (int k = 0; k < 16; k++) out[G.gB(k)] = x[k];
+}
+__global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_defF2(const u64 *__restrict__ w, const u64 *__restrict__ uin,
+                                                                 const u64 *__restrict__ bias, u64 *__restrict__ xout, int mq0,
+                                                                 const ModC *__restrict__ mods) {
+    __shared__ u64 sm[16 * HEC_ROW_PITCH];
+    const ModC M = mods[mq0];
+    RowGeom G(HEC_BTILE);
+    u64 x[16];
+    row_loadA(x, w + (size_t)HEC_BJOB * HEC_N, G);
+    row_fwd8(x, sm, G, M);
+    row_BtoA(x, sm, G);
+    const u64 *u = uin + (size_t)HEC_BJOB * HEC_N;
+    u64 *out = xout + (size_t)HEC_BJOB * HEC_N;
+    const bool add_bias = bias != nullptr && (HEC_BJOB & 1) == 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const u32 i = G.gbase + 16 * k;
+        u64 r = u[i] + M.q - canon(x[k], M);                 // (0,2q)
+        if (add_bias) r += __ldg(bias + i);                  // < 3q
+        out[i] = cred(cred(r, M.q2), M.q);
     }
 }

@@ -29,7 +29,7 @@ SYMBOLS = [
     "hec_ptdiag_upload", "hec_ptdiag_free", "hec_linear_transform", "hec_coeffs_to_slots", "hec_slots_to_coeffs", "hec_sub_sum", "hec_mod_up", "hec_bootstrap_ctos", "hec_bootstrap_stoc", "hec_bootstrapp", "hec_mult_by_int_and_add", "hec_evaluate_poly", "hec_evaluate_cheby", "hec_eval_relu", "hec_eval_relu_many", "hec_rotate_gal", "hec_rotate_new", "hec_rotate_hoisted", "hec_galois_for_rotation",
     "hec_ntt", "hec_keyswitch", "hec_moddown", "hec_conv_then_pack", "hec_conv_bl", "hec_ext_ctxt", "hec_keep_ctxt", "hec_plan_create", "hec_plan_run",
     "hec_plan_run_host", "hec_plan_submit_host", "hec_plan_wait", "hec_plan_span_begin", "hec_plan_span_end_ms",
-    "hec_plan_profile", "hec_plan_destroy", "hec_plan_cache_size", "hec_float_quotient_threshold", "hec_ext_double_ctxt", "hec_conv_bn_relu",
+    "hec_plan_profile", "hec_plan_kernel_names", "hec_plan_is_deferred", "hec_plan_destroy", "hec_plan_cache_size", "hec_float_quotient_threshold", "hec_ext_double_ctxt", "hec_conv_bn_relu",
 ]
 
 
@@ -172,6 +172,8 @@ def lib():
     L.hec_plan_span_begin.argtypes = [vp]
     L.hec_plan_span_end_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.hec_plan_profile.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]
+    L.hec_plan_kernel_names.argtypes = [vp, C.c_char_p, C.c_int]
+    L.hec_plan_is_deferred.argtypes = [vp]
     L.hec_plan_destroy.argtypes = [vp]
     L.hec_plan_destroy.restype = None
     L.hec_plan_cache_size.argtypes = [vp]
@@ -685,8 +687,14 @@ class Plan:
         ms = (C.c_float * 256)()
         n = C.c_int()
         self.ctx._chk(self.ctx.L.hec_plan_profile(self.h, ins, ms, 256, C.byref(n)))
-        names = ["A1", "A2", "A3"] + ["B%d" % (i % 5 + 1) for i in range(max(0, n.value - 3))]
-        return [(names[i], ms[i]) for i in range(n.value)]
+        buf = C.create_string_buffer(4096)
+        self.ctx._chk(min(0, self.ctx.L.hec_plan_kernel_names(self.h, buf, 4096)))
+        names = buf.value.decode().split(",")
+        return [(names[i % len(names)], ms[i]) for i in range(n.value)]
+
+    @property
+    def deferred(self):
+        return bool(self.ctx.L.hec_plan_is_deferred(self.h))
 
     def destroy(self):
         if self.h:

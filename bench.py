@@ -51,8 +51,8 @@ def kernel_limbs(name, M, B, first_launch_only=False, algorithmic=False, deferre
     reference's ciphertext in the algorithmic count, the e half is scratch."""
     na, jobs = B, M * B * 2
     if deferred:
-        if name == "A1":
-            return 4 * M + 2 * na + jobs + (0 if algorithmic else jobs)   # ct (2 polys x 2 limbs), pt (2 limbs), U out (-> w1)
+        if name == "A1":   # k_convA1 (with at least one pack level the U halves of stage A are never written)
+            return 2 * M + na + (0 if algorithmic else jobs)
         if name == "A2":
             return 0 if algorithmic else 2 * jobs                          # w1 -> e
         if name == "F1":
@@ -71,6 +71,10 @@ def kernel_limbs(name, M, B, first_launch_only=False, algorithmic=False, deferre
         nbt = M * (n // 2)                  # butterflies in this level's launch
         if deferred and algorithmic:
             tot += {"B1": 2 * nbt, "B2": 0, "B3": 2, "B4": 0, "B5": 6 * nbt + 3}[name]  # U halves of a, b (4), out (2); monomial, 2 key Q limbs
+        elif deferred and n == na:          # first level: U halves formed from ct_in and per-butterfly plaintext tables (pairs)
+            tot += {"B1": M + 2 * (na // 2) + nbt,               # ct_in.c1 limb q0, tables -> w1
+                    "B2": 5 * nbt, "B3": 3 * nbt + 2, "B4": 8 * nbt,
+                    "B5": 3 * nbt + 2 * M + 4 * (na // 2) + 4}[name]  # w4, ct_in limb q0 x2, two tables, key Q limbs as pairs -> 2 U out
         elif deferred:
             tot += {"B1": 4 * nbt + 2,      # Ua1, Ub1, monomial pairs -> z, w1
                     "B2": 5 * nbt,          # w1, ea1, eb1 -> w2 (p0), w4 (q0)
@@ -104,9 +108,10 @@ NCU_SUMMARY_DEFERRED = {64: "r02e_ncu_summary.csv"}   # the same with deferred t
 
 
 def kname(short, deferred):
-    """kernel symbol of a plan launch: the deferred plan reuses k_convB1 / k_convB3 and has its own A1, A2, B2, B4, B5, F1, F2"""
-    if deferred and short not in ("B1", "B3"):
-        return "k_def" + short
+    """kernel symbol of a plan launch (the first, largest, of a run): the deferred plan reuses k_convA1 / k_convB3 and
+    has its own A2, B1 (first level), B2, B4, B5, F1, F2"""
+    if deferred:
+        return {"A1": "k_convA1", "B1": "k_defB1f", "B3": "k_convB3", "B5": "k_defB5<(bool)1>"}.get(short, "k_def" + short)
     return "k_conv" + short
 
 
@@ -124,7 +129,7 @@ def ncu_traffic(kernel, cts, deferred=False):
         mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         ir, iw = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
         for r in rows[2:]:
-            if r[0].startswith(kernel + "("):
+            if r[0].startswith(kernel + "(") or r[0].startswith("void " + kernel + "("):
                 return float(r[ir]) * mult[units[ir]] + float(r[iw]) * mult[units[iw]]
     except Exception:
         pass

@@ -314,8 +314,8 @@ int hec_plan_profile(hec_plan *plan, const hec_ct *const *ins, float *ms, int ca
 int hec_plan_kernel_names(const hec_plan *plan, char *buf, int cap);
 /* 1 if the plan carries its level-0 polynomials as pairs (U, e), value = U - NTT(e), and runs one forward transform per
  * output polynomial at the end instead of one per rescale / mod-down (same results bit for bit; chosen at creation when
- * max_ob <= 256 and the pl_idx plaintexts are the monomials of conv.go:241-254; HEC_DEFER=0 in the environment turns it
- * off) */
+ * max_ob <= 256, batch * max_ob / norm >= 64 and the pl_idx plaintexts are the monomials of conv.go:241-254; HEC_DEFER=0
+ * in the environment turns it off, 2 forces it for small batches too) */
 int hec_plan_is_deferred(const hec_plan *plan);
 void hec_plan_destroy(hec_plan *plan);
 /* hec_conv_then_pack (fused) keeps the plans it builds, keyed by its arguments' identities (plaintext and key

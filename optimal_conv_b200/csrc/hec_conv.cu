@@ -269,6 +269,7 @@ struct hec_plan {
     // deferred-transform plan (hec_kernels.cuh (3)): level-0 polynomials as pairs (U, e); 2 + 5 per level + 2 launches
     bool defer = false;
     u64 *efinal = nullptr, *ufinal = nullptr, *wfin = nullptr;
+    ulonglong2 *ptk_first = nullptr;  // [2][na/2][N]: per butterfly of the first pack level, ptk'[a] -+ X^step ptk'[b] as pairs
     int Mc = 0, nchains = 1;
     std::vector<cudaStream_t> chain_streams;
     std::vector<cudaEvent_t> chain_events;
@@ -318,14 +319,18 @@ static int plan_launch_chunk(hec_plan *p, const ConvA &A, const std::vector<Conv
     hec_ctx *c = p->c;
     dim3 gA = HEC_GRID(HEC_TILES_PER_LIMB, Mc * p->na * 2);
     if (p->defer) {
-        k_defA1<<<gA, HEC_THREADS, 0, s>>>(A, c->dmods);
+        // with at least one pack level the U halves of stage A are never written: the first level forms them from ct_in
+        if (Bs.empty()) k_defA1<<<gA, HEC_THREADS, 0, s>>>(A, c->dmods);
+        else k_convA1<<<gA, HEC_THREADS, 0, s>>>(A, c->dmods);
         after();
         k_defA2<<<gA, HEC_THREADS, 0, s>>>(A, c->dmods);
         after();
+        bool first = true;
         for (auto &b : Bs) {
             int nb = b.n / 2;
             dim3 g1 = HEC_GRID(HEC_TILES_PER_LIMB, Mc * nb), g2 = HEC_GRID(HEC_TILES_PER_LIMB, Mc * nb * 2);
-            k_convB1<<<g1, HEC_THREADS, 0, s>>>(b, c->dmods);
+            if (first) k_defB1f<<<g1, HEC_THREADS, 0, s>>>(b, c->dmods);
+            else k_convB1<<<g1, HEC_THREADS, 0, s>>>(b, c->dmods);
             after();
             k_defB2<<<g1, HEC_THREADS, HEC_DB2_SMEM, s>>>(b, c->dmods);
             after();
@@ -333,8 +338,10 @@ static int plan_launch_chunk(hec_plan *p, const ConvA &A, const std::vector<Conv
             after();
             k_defB4<<<g2, HEC_THREADS, HEC_DB4_SMEM, s>>>(b, c->dmods);
             after();
-            k_defB5<<<g1, HEC_THREADS, HEC_B5_SMEM, s>>>(b, c->dmods);
+            if (first) k_defB5<true><<<g1, HEC_THREADS, HEC_B5_SMEM, s>>>(b, c->dmods);
+            else k_defB5<false><<<g1, HEC_THREADS, HEC_B5_SMEM, s>>>(b, c->dmods);
             after();
+            first = false;
         }
         dim3 gF = HEC_GRID(HEC_TILES_PER_LIMB, Mc * 2);
         k_defF1<<<gF, HEC_THREADS, 0, s>>>(p->efinal, p->wfin, A.mq0, c->dmods);
@@ -430,6 +437,7 @@ extern "C" void hec_plan_destroy(hec_plan *p) {
     if (p->pool) cudaFree(p->pool);
     if (p->ptk_scaled) cudaFree(p->ptk_scaled);
     if (p->ptk_pairs) cudaFree(p->ptk_pairs);
+    if (p->ptk_first) cudaFree(p->ptk_first);
     if (p->key_pairs) cudaFree(p->key_pairs);
     if (p->mono_pairs) cudaFree(p->mono_pairs);
     if (p->bias_plain) cudaFree(p->bias_plain);
@@ -505,9 +513,13 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
     for (int t = na; t > 1; t >>= 1) levels++;
     p->levels = levels;
     auto bail = [&](int code, const char *msg) { hec_plan_destroy(p); return c->fail(code, msg); };
-    {   // HEC_DEFER=0: every mod-down / rescale ends in the NTT domain (the round-1/2 kernels, (2) in hec_kernels.cuh)
+    {   // HEC_DEFER=0: every mod-down / rescale ends in the NTT domain (the round-1/2 kernels, (2) in hec_kernels.cuh);
+        // 2: deferred whatever the batch.  Default: deferred once a run has at least 64 channel-ciphertexts to spread over
+        // the SMs -- below that a run is a chain of under-filled launches and the longer CTAs of k_defB2 / k_defB5 cost more
+        // than the transforms saved (measured, B = 16: 0.41 / 0.52 / 0.73 ms deferred against 0.37 / 0.50 / 0.74 ms for
+        // 1 / 2 / 4 ciphertexts per run, 3.84 against 4.32 ms for 32)
         static const int env_defer = getenv("HEC_DEFER") ? atoi(getenv("HEC_DEFER")) : 1;
-        if (env_defer && B <= 256) {
+        if (env_defer && B <= 256 && (env_defer == 2 || (size_t)M * na >= 64)) {
             int ok = pack_monomials_check(c, pt_idx, B, na);
             if (ok < 0) return bail(ok, "checking the pack monomials");
             p->defer = ok == 1;
@@ -541,6 +553,38 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
                                                           nullptr, c->modQ(l), c->dmods);
                 c->launches++;
             }
+        if (p->defer && levels >= 1) {
+            // first pack level: both inputs of butterfly u are ct_in times a kernel plaintext, so their sum and difference
+            // (X^step folded in) are ct_in times ONE table each; built here in Montgomery form, kept as pairs
+            const int nbf = na / 2;
+            int step0 = B / 2, logStep0 = 0;
+            for (int i = step0; i > 1; i /= 2) logStep0++;
+            if (!pt_idx[logStep0]) return bail(HEC_E_INVAL, "pt_idx entry missing");
+            u64 *tmp = nullptr;
+            if (cudaMalloc(&p->ptk_first, (size_t)2 * nbf * HEC_N * sizeof(ulonglong2)) != cudaSuccess ||
+                cudaMalloc(&tmp, (size_t)3 * nbf * HEC_N * sizeof(u64)) != cudaSuccess)
+                return bail(HEC_E_NOMEM, "cudaMalloc");
+            const int m0 = c->modQ(0);
+            std::vector<EwJob> jm, js, ja;
+            for (int u = 0; u < nbf; u++) {
+                const u64 *pa = p->ptk_scaled + (size_t)u * 2 * HEC_N, *pb = p->ptk_scaled + (size_t)(u + nbf) * 2 * HEC_N;
+                u64 *t = tmp + (size_t)3 * u * HEC_N;
+                jm.push_back(ewjob(pb, pt_idx[logStep0]->buf, t, m0));
+                js.push_back(ewjob(pa, t, t + HEC_N, m0));
+                ja.push_back(ewjob(pa, t, t + 2 * HEC_N, m0));
+            }
+            if (launch_ew<EW_MULMONT>(c, jm) || launch_ew<EW_SUB>(c, js) || launch_ew<EW_ADD>(c, ja)) {
+                cudaFree(tmp);
+                return bail(HEC_E_CUDA, "first-level plaintext tables");
+            }
+            for (int u = 0; u < nbf; u++)
+                for (int t = 0; t < 2; t++) {
+                    k_plan_tables<<<64, 256, 0, c->stream>>>(tmp + (size_t)(3 * u + 1 + t) * HEC_N, p->ptk_first + ((size_t)t * nbf + u) * HEC_N,
+                                                              nullptr, m0, c->dmods);
+                    c->launches++;
+                }
+            cudaFreeAsync(tmp, c->stream);
+        }
         cudaFreeAsync(p->ptk_scaled, c->stream); // only the pairs are read from here on
         p->ptk_scaled = nullptr;
     }
@@ -655,13 +699,19 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
             b.step = (u32)step;
             b.pinv = pair(invmod(p0 % q0, q0), q0);
             b.bias = nullptr; // added by the last transform (k_defF2)
+            if (l == 0) {
+                b.ctin = p->d_ctin;
+                b.ptkz = p->ptk_first;
+                b.ptks = p->ptk_first + (size_t)(na / 2) * HEC_N;
+            }
         }
         p->pb.push_back(b);
     }
     p->launches_per_run = p->defer ? 4 + 5 * levels : (3 + 5 * levels) * (M / p->Mc) + ((levels == 0 && pt_bias) ? M : 0);
     if (cudaFuncSetAttribute(k_defB2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEC_DB2_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(k_defB4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEC_DB4_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(k_defB5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEC_B5_SMEM) != cudaSuccess)
+        cudaFuncSetAttribute(k_defB5<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEC_B5_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(k_defB5<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEC_B5_SMEM) != cudaSuccess)
         return bail(HEC_E_CUDA, "cudaFuncSetAttribute(k_defB2/B4/B5)");
     if (cudaFuncSetAttribute(k_convB3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEC_B3_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(k_convB5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEC_B5_SMEM) != cudaSuccess ||

@@ -698,6 +698,10 @@ struct ConvB {
     u32 ginv;        // galEl^-1 mod 2N
     u32 step;        // the level's monomial is X^step
     ulonglong2 pinv; // P^-1 mod q0 as a Shoup pair
+    // first pack level of a deferred plan: the U halves of its inputs are ct_in * (plaintext table) and are formed where
+    // they are used instead of being written by stage A and read back
+    const u64 *const *ctin;        // [M] -> [2 polys][2 limbs][N]
+    const ulonglong2 *ptkz, *ptks; // [n/2][N] pairs: ptk'[a] -+ X^step ptk'[b] per butterfly (ptk' = pl_ker * k0 / q1 on limb q0)
 };
 struct BJob {
     int c, u, m;
@@ -935,11 +939,39 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_defA2(ConvA P, const 
         out[G.gA(k)] = cred(shoup(r, P.q1inv, M0.q), M0.q);
     }
 }
-// dB1 = k_convB1 on the U halves (z = Ua1 - Ub1*mono, inverse stages t = 1..128)
+// dB1 = k_convB1 on the U halves (z = Ua1 - Ub1*mono, inverse stages t = 1..128); on the FIRST pack level Ua1 and Ub1 are
+// both ct_in.c1 times a kernel plaintext, so z = ct_in.c1 * (ptk'[a] - X^step ptk'[b]): one product with a table the plan
+// prepared per butterfly, no U halves to read (or to have been written), no z to store (k_defB5<true> does not need it)
+__global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_defB1f(ConvB P, const ModC *__restrict__ mods) {
+    __shared__ u64 sm[16 * HEC_ROW_PITCH];
+    const ModC M = mods[P.mq0];
+    RowGeom G(HEC_BTILE);
+    const int nb = P.n >> 1, m = HEC_BJOB / nb, u = HEC_BJOB % nb;
+    const u64 *ct1 = P.ctin[m] + (size_t)2 * HEC_N;            // limb q0 of c1
+    const ulonglong2 *tz = P.ptkz + (size_t)u * HEC_N;
+    u64 x[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        u32 i = G.gbase + 16 * k;
+        x[k] = shoup4(ct1[i], __ldg(tz + i), M.q); // < 4q
+    }
+    row_AtoB(x, sm, G);
+    row_inv8(x, sm, G, M);
+    row_storeA(x, P.w1 + (size_t)HEC_BJOB * HEC_N, G);
+}
 // dB2: finish InvNTT_q0, subtract the e half of tmp2.c1 (ea1 - X^step eb1): the digit d, canonical; forward stages
 //      m = 1..128 of d under p0 (-> w2) AND under q0 (-> w4): the value of tmp2.c1 is NTT_q0(d)
 #define HEC_DB2_SMEM (2 * HEC_TILE * sizeof(u64))
-__global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_defB2(ConvB P, const ModC *__restrict__ mods) {
+#ifndef HEC_DB2_MINB
+#define HEC_DB2_MINB HEC_MINB
+#endif
+#ifndef HEC_DB4_MINB
+#define HEC_DB4_MINB HEC_MINB
+#endif
+#ifndef HEC_DB5_MINB
+#define HEC_DB5_MINB HEC_B5_MINB
+#endif
+__global__ void __launch_bounds__(HEC_THREADS, HEC_DB2_MINB) k_defB2(ConvB P, const ModC *__restrict__ mods) {
     extern __shared__ __align__(128) u64 dsm[];
     u64 *sm = dsm, *stash = dsm + HEC_TILE;
     const ModC MQ = mods[P.mq0];
@@ -949,14 +981,21 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_defB2(ConvB P, const 
     const u64 *ea = P.ein + ((size_t)(m * P.n + u) * 2 + 1) * HEC_N;
     const u64 *eb = P.ein + ((size_t)(m * P.n + u + nb) * 2 + 1) * HEC_N;
     const u64 *in = P.w1 + (size_t)HEC_BJOB * HEC_N;
+    // the e operands FIRST, parked in the thread's own stash slots: their loads sit at the start of the CTA, where the
+    // other CTAs of the SM cover them, instead of behind the inverse transform (as in k_convA3 / k_convB5)
+    const u64 *__restrict__ ebs = eb - P.step; // only slot k = 0 can hold a coefficient n < step (row 0)
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const u32 n = G.gA(k);
+        stash[k * HEC_THREADS + threadIdx.x] = (MQ.q - ea[n]) + (k == 0 ? shifted_coeff(eb, n, P.step, MQ.q) : ebs[n]); // [0,2q]
+    }
     u64 x[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) x[k] = in[G.gB(k)];
     col_inv8_final(x, sm, G, MQ);
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        const u32 n = G.gA(k);
-        u64 d = x[k] + (MQ.q - ea[n]) + shifted_coeff(eb, n, P.step, MQ.q); // [0,3q]
+        u64 d = x[k] + stash[k * HEC_THREADS + threadIdx.x]; // [0,3q]
         d = cred(cred(d, MQ.q2), MQ.q);
         x[k] = d;
         stash[k * HEC_THREADS + threadIdx.x] = d; // own slots only
@@ -977,13 +1016,36 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_defB2(ConvB P, const 
     for (int k = 0; k < 16; k++) outq[G.gB(k)] = x[k];
 }
 // dB3 = k_convB3 (NTT_p0 of the digit, key products on the P limb, inverse stages t = 1..128 for both key polys)
-// dB4: finish InvNTTLazy_p0, exact basis extension P -> q0, divide by P: the e half of the key-switch output;
-//      add the e half of tmp2.c0 (c = 0), apply sigma_g on coefficients (row permutation with sign inside the column
-//      tile), add the e half of tmp1                                                grid.y = M*nb*2
+// dB4: finish InvNTTLazy_p0, exact basis extension P -> q0, divide by P: the e half of the key-switch output; apply
+//      sigma_g on coefficients (row permutation with sign inside the column tile); add the e halves of tmp1 and, for
+//      c = 0, of sigma(tmp2.c0)                                                     grid.y = M*nb*2
 #define HEC_DB4_SMEM (2 * HEC_TILE * sizeof(u64))
-__global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_defB4(ConvB P, const ModC *__restrict__ mods) {
+// everything of the result that does not pass through the key switch, for the thread's own 16 coefficients:
+//   (ea + X^step eb)[n]  +  (c = 0) sigma(ea - X^step eb)[n]     -- sigma read straight from global memory: it maps a row of
+// the column tile onto another row (same 16 columns), so the permuted loads are as coalesced as the straight ones
+template <bool C0>
+__device__ __forceinline__ void defb4_operands(u64 *S, const u64 *__restrict__ ea, const u64 *__restrict__ eb, const ConvB &P,
+                                               const ColGeom &G, u64 q) {
+    // only coefficients n < step wrap around (row 0 of the limb: slot k = 0 of the threads with pg = 0; step <= 128), and
+    // a permuted row index is never 0 unless the row itself is: everything else is a plain load at n - step
+    const u64 *__restrict__ ebs = eb - P.step;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const u32 n = G.gA(k);
+        u64 s = ea[n] + (k == 0 ? shifted_coeff(eb, n, P.step, q) : ebs[n]); // <= 2q
+        if (C0) {
+            const u32 src = (n * P.ginv) & (2u * HEC_N - 1u);
+            const u32 n2 = (src & (HEC_N - 1u));                              // same column, row (src >> 8) & 255
+            const u64 d2 = ea[n2] + (q - shifted_coeff(eb, n2, P.step, q));   // [0,2q]
+            s += (src & HEC_N) ? 2 * q - d2 : d2;                             // <= 4q
+        }
+        S[k * HEC_THREADS + threadIdx.x] = s;
+    }
+}
+__global__ void __launch_bounds__(HEC_THREADS, HEC_DB4_MINB) k_defB4(ConvB P, const ModC *__restrict__ mods) {
     extern __shared__ __align__(128) u64 dsm[];
-    u64 *sm = dsm, *T = dsm + HEC_TILE;
+    u64 *sm = dsm;              // exchange buffer of the transform, then the e half of the key-switch output (for sigma)
+    u64 *S = dsm + HEC_TILE;    // own slots: the operand sums, loaded before the transform
     const ModC MP = mods[P.mp0];
     const ModC MQ = mods[P.mq0];
     ColGeom G(HEC_BTILE);
@@ -991,38 +1053,36 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_defB4(ConvB P, const 
     const u64 *ea = P.ein + ((size_t)(m * P.n + u) * 2 + c) * HEC_N;
     const u64 *eb = P.ein + ((size_t)(m * P.n + u + nb) * 2 + c) * HEC_N;
     const u64 *in = P.w3 + (size_t)HEC_BJOB * HEC_N;
+    if (c == 0) defb4_operands<true>(S, ea, eb, P, G, MQ.q);
+    else defb4_operands<false>(S, ea, eb, P, G, MQ.q);
     u64 x[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) x[k] = in[G.gB(k)];
-    col_inv8_final(x, sm, G, MP);
+    col_inv8_final(x, sm, G, MP);                           // ends past its last barrier: sm is free again
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        const u32 n = G.gA(k);
+        // (y - v p0) / P mod q0 with P = p0: y / P - v -- the float overflow count v is 0 below P.vthr and 1 from there on,
+        // and the Shoup product takes any y < 2^64, so the extension needs no reduction of its own
         const u64 y = x[k];
-        const u64 ext = reduce_lazy(y, MQ.q, P.mu0) + (y >= P.vthr ? P.qpj1 : 0ull); // [0,3q0)
-        u64 t = shoup(ext, P.pinv, MQ.q);                                           // [0,2q)
-        const u64 a = ea[n], sh = shifted_coeff(eb, n, P.step, MQ.q);
-        if (c == 0) t += a + (MQ.q - sh);                                           // + e half of tmp2.c0, <= 4q
-        T[G.sA(k)] = t;
-        x[k] = a + sh;                                                              // e half of tmp1, <= 2q
+        sm[G.sA(k)] = shoup(y, P.pinv, MQ.q) + (y >= P.vthr ? MQ.q - 1 : 0ull);      // [0,3q)
     }
     __syncthreads();
     u64 *out = P.eout + (size_t)HEC_BJOB * HEC_N;
-    const u64 q4 = 2 * MQ.q2;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         const u32 n = G.gA(k);
         const u32 src = (n * P.ginv) & (2u * HEC_N - 1u);    // sigma(T)[n] = +-T[n g^-1 mod 2N]; same column for g = 1 mod 256
-        const u32 r = src >> 8;                              // row 0..511: past 255 the sign flips
-        const u64 t = T[(r & 255u) * 16 + G.cc];
-        out[n] = canon8(x[k] + ((r & 256u) ? q4 - t : t), MQ.q); // <= 6q
+        const u64 t = sm[((src >> 8) & 255u) * 16 + G.cc];
+        out[n] = canon8(S[k * HEC_THREADS + threadIdx.x] + ((src & HEC_N) ? 3 * MQ.q - t : t), MQ.q); // <= 7q
     }
 }
 // dB5: finish NTT_q0 of the digit = the value of tmp2.c1, ONCE for both key polys; for each: product with key[c]/P
 //      (Q limb), + the U half of tmp2.c0 (c = 0), sigma_g inside the 256-word block, + the U half of tmp1   grid.y = M*nb
-template <bool C0>
+template <bool C0, bool FIRST>
 __device__ __forceinline__ void defb5_pointwise(const u64 (&x)[16], u64 *sm, u64 *st, const ConvB &P, const BJob &J, const ModC &M,
-                                                const RowGeom &G, const u64 *__restrict__ zb, const ulonglong2 *__restrict__ kq) {
+                                                const RowGeom &G, const u64 *__restrict__ zb, const ulonglong2 *__restrict__ kq,
+                                                const u64 *__restrict__ ct, const ulonglong2 *__restrict__ tz,
+                                                const ulonglong2 *__restrict__ ts) {
     const u64 *__restrict__ a = C0 ? J.a : J.a + HEC_N;
     const u64 *__restrict__ b = J.b;
 #pragma unroll
@@ -1030,7 +1090,11 @@ __device__ __forceinline__ void defb5_pointwise(const u64 (&x)[16], u64 *sm, u64
         const u32 i = G.gbase + 16 * k, e = G.p + 16 * k;
         u64 d = shoup4(x[k], __ldg(kq + i), M.q);                               // U half of the key-switch output, < 4q
         u64 t1;
-        if (C0) {
+        if (FIRST) {
+            const u64 cv = ct[i];                                               // limb q0 of ct_in.c0 / .c1
+            if (C0) d += shoup(cv, __ldg(tz + i), M.q);                         // + U half of tmp2.c0, < 6q
+            t1 = shoup(cv, __ldg(ts + i), M.q);                                 // U half of tmp1, [0,2q)
+        } else if (C0) {
             const u64 a0 = a[i];
             const u64 m0 = shoup(b[i], __ldg(P.mono + i), M.q);                 // [0,2q)
             d += a0 + M.q2 - m0;                                                // + U half of tmp2.c0, < 7q
@@ -1042,7 +1106,8 @@ __device__ __forceinline__ void defb5_pointwise(const u64 (&x)[16], u64 *sm, u64
         st[G.sbase + e + (e >> 4)] = t1;
     }
 }
-__global__ void __launch_bounds__(HEC_THREADS, HEC_B5_MINB) k_defB5(ConvB P, const ModC *__restrict__ mods) {
+template <bool FIRST>
+__global__ void __launch_bounds__(HEC_THREADS, HEC_DB5_MINB) k_defB5(ConvB P, const ModC *__restrict__ mods) {
     extern __shared__ __align__(128) u64 dsm[];
     u64 *sm = dsm, *st = dsm + 16 * HEC_ROW_PITCH;
     const BJob J(HEC_BJOB, false, P);
@@ -1053,11 +1118,13 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_B5_MINB) k_defB5(ConvB P, con
     row_fwd8(x, sm, G, M);
     row_BtoA(x, sm, G);
     const u64 *zb = P.z + (size_t)HEC_BJOB * HEC_N;
+    const u64 *ct = FIRST ? P.ctin[J.m] : nullptr;
+    const ulonglong2 *tz = FIRST ? P.ptkz + (size_t)J.u * HEC_N : nullptr, *ts = FIRST ? P.ptks + (size_t)J.u * HEC_N : nullptr;
     const bool in_block = P.galEl > 512u;
 #pragma unroll 1
     for (int c = 0; c < 2; c++) {
-        if (c == 0) defb5_pointwise<true>(x, sm, st, P, J, M, G, zb, P.key);
-        else defb5_pointwise<false>(x, sm, st, P, J, M, G, zb, P.key + HEC_N);
+        if (c == 0) defb5_pointwise<true, FIRST>(x, sm, st, P, J, M, G, zb, P.key, ct, tz, ts);
+        else defb5_pointwise<false, FIRST>(x, sm, st, P, J, M, G, zb, P.key + HEC_N, FIRST ? ct + 2 * HEC_N : nullptr, tz, ts);
         if (in_block) __syncwarp(); else __syncthreads();
         u64 *out = P.xout + (size_t)(HEC_BJOB * 2 + c) * HEC_N;
 #pragma unroll

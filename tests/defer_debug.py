@@ -34,6 +34,8 @@ na = B // norm
 for lv, cts in enumerate(trace):
     n = na >> lv
     for half, nm in ((0, "U"), (1, "e")):
+        if lv == 0 and half == 0 and len(trace) > 1:
+            continue    # the U halves of stage A are not materialised when a pack level follows
         buf = np.empty((n, 2, N), dtype=np.uint64)
         rc = L.hec_plan_debug_level(plan.h, lv, half, buf.ctypes.data_as(C.c_void_p))
         assert rc == 0, rc

@@ -1017,7 +1017,7 @@ def test_conv_then_pack_plan_cache_and_object_lifetimes(orc, idx_np):
         assert c.plan_cache_size() == 1
         n0 = c.launch_count()
         check(c.conv_then_pack(G.cts[1], G.ker, 1, PR.SCALE, G.idx, G.bias), 1)   # same plan, other input
-        assert c.plan_cache_size() == 1 and c.launch_count() - n0 == 3 + 5 * 2    # no plaintext-rescale launch
+        assert c.plan_cache_size() == 1 and c.launch_count() - n0 == 3 + 5 * 2    # no plaintext-rescale launch (one ciphertext of 4 channels: the plan does not defer)
         r = c.conv_then_pack(G.cts[0], G.ker, 1, PR.SCALE, G.idx, None)            # other arguments: a second plan
         r.free()
         assert c.plan_cache_size() == 2
@@ -1117,6 +1117,67 @@ def test_conv_4096_slots_is_the_last_fused_packing(idx_np):
         with pytest.raises(hec.HecError) as e:
             c.conv_then_pack(ct, ker + [None] * B, norm, PR.SCALE, idx, bias, hec.CONV_FUSED)
         assert e.value.code == hec.HEC_E_UNSUPPORTED
+    finally:
+        c.close()
+
+
+def test_deferred_plan_needs_monomials_and_falls_back_without_them(orc, idx_np):
+    """A plan with enough work per run (batch * channels >= 64, B <= 256) defers the forward transforms (pairs (U, e),
+    DESIGN.md 4.5) after checking that the pl_idx plaintexts are the monomials X^step; with any other plaintext in their
+    place the products are real products and the plan keeps the transform-per-mod-down kernels; a small batch keeps them
+    too.  All must equal the oracle fed with the same plaintexts."""
+    c = hec.Context(PR.LOGN, Q2, P1)
+    try:
+        M = 8
+        w = common.workload({"B": 8, "seed": 4242}, n_ct=M)
+        G = common.GpuConv(c, w, idx_np, norm=1)
+        refs = [common.oracle_conv(orc, w, 1, PR.SCALE, idx_np, m=m) for m in range(M)]
+        plan = c.plan(G.ker, 1, PR.SCALE, PR.SCALE, G.idx, G.bias, M)
+        assert plan.deferred
+        outs = plan.run(G.cts)
+        for m in range(M):
+            g0, g1 = outs[m].download()
+            assert np.array_equal(g0, refs[m].c0) and np.array_equal(g1, refs[m].c1), m
+        plan.destroy()
+        small = c.plan(G.ker, 1, PR.SCALE, PR.SCALE, G.idx, G.bias, 2)
+        assert not small.deferred
+        outs = small.run(G.cts[:2])
+        for m in range(2):
+            g0, g1 = outs[m].download()
+            assert np.array_equal(g0, refs[m].c0) and np.array_equal(g1, refs[m].c1), m
+        small.destroy()
+        odd = idx_np.copy()
+        odd[1] = synth.uniform_mod(777, 1 << PR.LOGN, Q2[0])       # the level with step 2 multiplies by a random plaintext
+        idx2 = [c.upload_pt(odd[i:i + 1], 1.0) for i in range(PR.LOGN)]
+        plan = c.plan(G.ker, 1, PR.SCALE, PR.SCALE, idx2, G.bias, M)
+        assert not plan.deferred
+        outs = plan.run(G.cts)
+        for m in (0, M - 1):
+            ref = common.oracle_conv(orc, w, 1, PR.SCALE, odd, m=m)
+            g0, g1 = outs[m].download()
+            assert np.array_equal(g0, ref.c0) and np.array_equal(g1, ref.c1), m
+        plan.destroy()
+    finally:
+        c.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,norm,M,bias", [(16, 2, 8, True), (4, 4, 64, True), (16, 16, 64, False), (64, 1, 1, True), (32, 4, 8, False)])
+def test_deferred_plan_shapes(orc, idx_np, B, norm, M, bias):
+    """deferred plans over the shapes the tree can take: norm > 1 (fewer levels), a single active channel (no level: stage A
+    straight into the final transform, with and without bias), one ciphertext of many channels, no bias"""
+    c = hec.Context(PR.LOGN, Q2, P1)
+    try:
+        w = common.workload({"B": B, "seed": 5000 + B + norm}, n_ct=M)
+        G = common.GpuConv(c, w, idx_np, norm=norm)
+        plan = c.plan(G.ker, norm, PR.SCALE, PR.SCALE, G.idx, G.bias if bias else None, M)
+        assert plan.deferred
+        outs = plan.run(G.cts)
+        for m in sorted({0, M // 2, M - 1}):
+            ref = common.oracle_conv(orc, w, norm, PR.SCALE, idx_np, m=m, bias=bias, nthreads=os.cpu_count() or 1)
+            g0, g1 = outs[m].download()
+            assert np.array_equal(g0, ref.c0) and np.array_equal(g1, ref.c1), m
+        plan.destroy()
     finally:
         c.close()
 

@@ -338,8 +338,8 @@ static int plan_launch_chunk(hec_plan *p, const ConvA &A, const std::vector<Conv
             after();
             k_defB4<<<g2, HEC_THREADS, HEC_DB4_SMEM, s>>>(b, c->dmods);
             after();
-            if (first) k_defB5<true><<<g1, HEC_THREADS, HEC_B5_SMEM, s>>>(b, c->dmods);
-            else k_defB5<false><<<g1, HEC_THREADS, HEC_B5_SMEM, s>>>(b, c->dmods);
+            if (first) k_defB5<true><<<g1, HEC_THREADS, HEC_DB5_SMEM, s>>>(b, c->dmods);
+            else k_defB5<false><<<g1, HEC_THREADS, HEC_DB5_SMEM, s>>>(b, c->dmods);
             after();
             first = false;
         }
@@ -710,8 +710,8 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
     p->launches_per_run = p->defer ? 4 + 5 * levels : (3 + 5 * levels) * (M / p->Mc) + ((levels == 0 && pt_bias) ? M : 0);
     if (cudaFuncSetAttribute(k_defB2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEC_DB2_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(k_defB4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEC_DB4_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(k_defB5<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEC_B5_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(k_defB5<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEC_B5_SMEM) != cudaSuccess)
+        cudaFuncSetAttribute(k_defB5<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEC_DB5_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(k_defB5<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEC_DB5_SMEM) != cudaSuccess)
         return bail(HEC_E_CUDA, "cudaFuncSetAttribute(k_defB2/B4/B5)");
     if (cudaFuncSetAttribute(k_convB3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEC_B3_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(k_convB5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEC_B5_SMEM) != cudaSuccess ||

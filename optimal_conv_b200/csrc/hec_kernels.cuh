@@ -966,7 +966,7 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_defB1f(ConvB P, const
 #define HEC_DB2_MINB HEC_MINB
 #endif
 #ifndef HEC_DB4_MINB
-#define HEC_DB4_MINB HEC_MINB
+#define HEC_DB4_MINB 2 // measured: 1.389 -> 1.331 ms per 64 convolutions against 3 CTAs / 80 registers (k_defB2 and k_defB5 lose with the other setting)
 #endif
 #ifndef HEC_DB5_MINB
 #define HEC_DB5_MINB HEC_B5_MINB
@@ -1079,7 +1079,7 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_DB4_MINB) k_defB4(ConvB P, co
 // dB5: finish NTT_q0 of the digit = the value of tmp2.c1, ONCE for both key polys; for each: product with key[c]/P
 //      (Q limb), + the U half of tmp2.c0 (c = 0), sigma_g inside the 256-word block, + the U half of tmp1   grid.y = M*nb
 template <bool C0, bool FIRST>
-__device__ __forceinline__ void defb5_pointwise(const u64 (&x)[16], u64 *sm, u64 *st, const ConvB &P, const BJob &J, const ModC &M,
+__device__ __forceinline__ void defb5_pointwise(const u64 *xs, u64 *sm, u64 *st, const ConvB &P, const BJob &J, const ModC &M,
                                                 const RowGeom &G, const u64 *__restrict__ zb, const ulonglong2 *__restrict__ kq,
                                                 const u64 *__restrict__ ct, const ulonglong2 *__restrict__ tz,
                                                 const ulonglong2 *__restrict__ ts) {
@@ -1088,10 +1088,10 @@ __device__ __forceinline__ void defb5_pointwise(const u64 (&x)[16], u64 *sm, u64
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         const u32 i = G.gbase + 16 * k, e = G.p + 16 * k;
-        u64 d = shoup4(x[k], __ldg(kq + i), M.q);                               // U half of the key-switch output, < 4q
+        u64 d = shoup4(xs[k * HEC_THREADS + threadIdx.x], __ldg(kq + i), M.q);  // U half of the key-switch output, < 4q
         u64 t1;
         if (FIRST) {
-            const u64 cv = ct[i];                                               // limb q0 of ct_in.c0 / .c1
+            const u64 cv = __ldg(ct + i);                                       // limb q0 of ct_in.c0 / .c1
             if (C0) d += shoup(cv, __ldg(tz + i), M.q);                         // + U half of tmp2.c0, < 6q
             t1 = shoup(cv, __ldg(ts + i), M.q);                                 // U half of tmp1, [0,2q)
         } else if (C0) {
@@ -1106,25 +1106,33 @@ __device__ __forceinline__ void defb5_pointwise(const u64 (&x)[16], u64 *sm, u64
         st[G.sbase + e + (e >> 4)] = t1;
     }
 }
+// The transform's result is parked in shared memory (the thread's own 16 slots) rather than kept in 32 registers across
+// both polynomials: with it in registers the point-wise loops had no room to run their operand loads ahead (first
+// capture: every iteration waited for its own 128-bit load, 6.3 warps per issue on the long scoreboard, 43 % pipe use).
+#define HEC_DB5_SMEM ((2 * 16 * HEC_ROW_PITCH + HEC_TILE) * sizeof(u64))
 template <bool FIRST>
 __global__ void __launch_bounds__(HEC_THREADS, HEC_DB5_MINB) k_defB5(ConvB P, const ModC *__restrict__ mods) {
     extern __shared__ __align__(128) u64 dsm[];
-    u64 *sm = dsm, *st = dsm + 16 * HEC_ROW_PITCH;
+    u64 *sm = dsm, *st = dsm + 16 * HEC_ROW_PITCH, *xs = dsm + 2 * 16 * HEC_ROW_PITCH;
     const BJob J(HEC_BJOB, false, P);
     const ModC M = mods[P.mq0];
     RowGeom G(HEC_BTILE);
-    u64 x[16];
-    row_loadA(x, P.w4 + (size_t)HEC_BJOB * HEC_N, G);
-    row_fwd8(x, sm, G, M);
-    row_BtoA(x, sm, G);
+    {
+        u64 x[16];
+        row_loadA(x, P.w4 + (size_t)HEC_BJOB * HEC_N, G);
+        row_fwd8(x, sm, G, M);
+        row_BtoA(x, sm, G);
+#pragma unroll
+        for (int k = 0; k < 16; k++) xs[k * HEC_THREADS + threadIdx.x] = x[k];
+    }
     const u64 *zb = P.z + (size_t)HEC_BJOB * HEC_N;
     const u64 *ct = FIRST ? P.ctin[J.m] : nullptr;
     const ulonglong2 *tz = FIRST ? P.ptkz + (size_t)J.u * HEC_N : nullptr, *ts = FIRST ? P.ptks + (size_t)J.u * HEC_N : nullptr;
     const bool in_block = P.galEl > 512u;
 #pragma unroll 1
     for (int c = 0; c < 2; c++) {
-        if (c == 0) defb5_pointwise<true, FIRST>(x, sm, st, P, J, M, G, zb, P.key, ct, tz, ts);
-        else defb5_pointwise<false, FIRST>(x, sm, st, P, J, M, G, zb, P.key + HEC_N, FIRST ? ct + 2 * HEC_N : nullptr, tz, ts);
+        if (c == 0) defb5_pointwise<true, FIRST>(xs, sm, st, P, J, M, G, zb, P.key, ct, tz, ts);
+        else defb5_pointwise<false, FIRST>(xs, sm, st, P, J, M, G, zb, P.key + HEC_N, FIRST ? ct + 2 * HEC_N : nullptr, tz, ts);
         if (in_block) __syncwarp(); else __syncthreads();
         u64 *out = P.xout + (size_t)(HEC_BJOB * 2 + c) * HEC_N;
 #pragma unroll

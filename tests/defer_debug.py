@@ -3,6 +3,8 @@ import ctypes as C
 import os
 import sys
 
+os.environ.setdefault("HEC_DEFER", "2")   # deferred whatever the batch (a single ciphertext here)
+
 import numpy as np
 
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")

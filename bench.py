@@ -111,7 +111,7 @@ def kname(short, deferred):
     """kernel symbol of a plan launch (the first, largest, of a run): the deferred plan reuses k_convA1 / k_convB3 and
     has its own A2, B1 (first level), B2, B4, B5, F1, F2"""
     if deferred:
-        return {"A1": "k_convA1", "B1": "k_defB1f", "B3": "k_convB3", "B5": "k_defB5<(bool)1>"}.get(short, "k_def" + short)
+        return {"A1": "k_convA1", "B1": "k_defB1f", "B3": "k_convB3", "B5": "k_defB5<1>"}.get(short, "k_def" + short)
     return "k_conv" + short
 
 

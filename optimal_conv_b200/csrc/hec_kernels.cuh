@@ -1,10 +1,13 @@
 // hec_kernels.cuh -- all CUDA kernels of libhec (sm_100a).
 //
-// Two families:
+// Three families:
 //  (1) generic per-limb kernels (NTT passes, element-wise ops, basis extension) from which
 //      the op-level evaluator (any level / alpha / beta) is composed;
 //  (2) fused kernels for the reference's conv_then_pack path (conv.go:522-546, 266-300) at
-//      level 1 -> 0 with one special prime: 3 kernels for Stage A, 5 per pack-tree level.
+//      level 1 -> 0 with one special prime: 3 kernels for Stage A, 5 per pack-tree level;
+//  (3) the same path with the forward transforms deferred (k_def*): level-0 polynomials carried as
+//      pairs (U, e), value = U - NTT(e); 2 kernels for Stage A, 5 per level, 2 at the end.  The
+//      default for batched plans; shares k_convA1 / k_convB1 / k_convB3 with (2).
 // Reference routines each kernel covers are cited at the kernel.
 #pragma once
 #include <cooperative_groups.h>

@@ -188,16 +188,18 @@ int hec_launch_ntt(hec_ctx *c, std::vector<LimbJob> &jobs, bool inverse) {
         A[i] = j;
         B[i] = j;
         A[i].out = mid;              // first pass: in -> mid (prologue, if any)
-        A[i].flags = inverse ? 0 : (j.flags & HEC_LJ_PRO);
+        A[i].flags = inverse ? 0 : (j.flags & (HEC_LJ_PRO | HEC_LJ_PRO2));
         B[i].in = mid;               // second pass: mid -> out (epilogue, if any)
-        B[i].flags = inverse ? 0 : (j.flags & (HEC_LJ_EPI | HEC_LJ_ADD));
+        B[i].flags = inverse ? 0 : (j.flags & (HEC_LJ_EPI | HEC_LJ_ADD | HEC_LJ_ADDS));
         A[i].scatter_g = 0;
         if (inverse) B[i].scatter_g = 0;
     }
     // HEC_FWD16=1: the forward transform as one launch per limb list, a limb per 16-CTA cluster exchanging through
     // distributed shared memory (k_fwd16); 0: column pass + row pass through global memory
     static const int fwd16 = getenv("HEC_FWD16") ? atoi(getenv("HEC_FWD16")) : HEC_FWD16_DEFAULT;
-    if (!inverse && fwd16) {
+    bool ext_flags = false; // PRO2 / ADDS exist in the two-pass kernels only
+    for (const LimbJob &j : jobs) ext_flags = ext_flags || (j.flags & (HEC_LJ_PRO2 | HEC_LJ_ADDS));
+    if (!inverse && fwd16 && !ext_flags) {
         static int ready = 0; // 1: usable, -1: this device / driver refuses the cluster shape
         if (!ready) {
             bool ok = cudaFuncSetAttribute(k_fwd16, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
@@ -236,8 +238,13 @@ int hec_launch_ntt(hec_ctx *c, std::vector<LimbJob> &jobs, bool inverse) {
     for (size_t off = 0; off < n; off += 65535) { // grid.y limit
         dim3 grid(HEC_TILES_PER_LIMB, (unsigned)std::min<size_t>(65535, n - off));
         if (!inverse) {
-            launch_k(c, k_col_fwd, grid, dim3(HEC_THREADS), dA + off, c->dmods);
-            launch_k(c, k_row_fwd, grid, dim3(HEC_THREADS), dB + off, c->dmods);
+            if (ext_flags) {
+                launch_k(c, k_col_fwd<true>, grid, dim3(HEC_THREADS), dA + off, c->dmods);
+                launch_k(c, k_row_fwd<true>, grid, dim3(HEC_THREADS), dB + off, c->dmods);
+            } else {
+                launch_k(c, k_col_fwd<false>, grid, dim3(HEC_THREADS), dA + off, c->dmods);
+                launch_k(c, k_row_fwd<false>, grid, dim3(HEC_THREADS), dB + off, c->dmods);
+            }
         } else {
             launch_k(c, k_row_inv, grid, dim3(HEC_THREADS), dA + off, c->dmods);
             launch_k(c, k_col_inv, grid, dim3(HEC_THREADS), dB + off, c->dmods);
@@ -1175,6 +1182,110 @@ int hec_mul_relin_many(hec_ctx *c, const std::vector<const hec_ct *> &a, const s
     std::vector<const u64 *> o0(n), o1(n);
     for (size_t m = 0; m < n; m++) { o0[m] = out[m]->limb(0, 0); o1[m] = out[m]->limb(1, 0); }
     if ((rc = keyswitch_many(c, level, dc, keys, d0, d1, o0, o1, true))) return bail(rc);
+    return HEC_OK;
+}
+// Rescale(MulRelinNew(a, b), min_scale) for a batch, the first division fused into the relinearisation's mod-down.
+// Both end with a forward transform per limb: ModDownSplitNTTPQ with NTT(x_l), x_l the basis-extended P part, and
+// divRoundByLastModulusNTT with NTT(r_l), r_l the centred remainder of the dropped limb.  On the kept limbs
+//   ((accQ_l - NTT(x_l)) / P + d_l - NTT(r_l)) / q_T  =  (NTT(x_l + P r_l) - accQ_l) * (-(P q_T)^-1) + d_l / q_T
+// (d = the tensor product's c0 / c1, T the dropped limb): ONE transform of x_l + P r_l instead of two.  The dropped limb
+// itself is completed first (its mod-down as usual), transformed back and centred to give r.  Exact arithmetic modulo
+// every q_l, so the result is bit for bit that of the two operations in sequence (L:ckks/evaluator.go:1398-1444,
+// 1291-1325; L:ring/ring_scaling.go:442-513).  Further divisions, if the scale asks for them, run unfused.
+int hec_mul_relin_rescale_many(hec_ctx *c, const std::vector<const hec_ct *> &a, const std::vector<const hec_ct *> &b, double min_scale,
+                               std::vector<hec_ct *> &out) {
+    static const int fuse = getenv("HEC_RELIN_RESCALE") ? atoi(getenv("HEC_RELIN_RESCALE")) : 1;
+    size_t n = a.size();
+    int level = std::min(a[0]->level, b[0]->level), L = level + 1, rc;
+    const double s0 = a[0]->scale * b[0]->scale;
+    bool same = true;
+    for (size_t m = 0; m < n; m++) same = same && std::min(a[m]->level, b[m]->level) == level && a[m]->scale * b[m]->scale == s0;
+    if (!fuse || !same || level == 0 || !(s0 / (double)c->q(level) >= min_scale / 2)) {
+        if ((rc = hec_mul_relin_many(c, a, b, out))) return rc;
+        rc = hec_rescale_many(c, out, min_scale);
+        if (rc) { for (hec_ct *o : out) hec_ct_free(c, o); out.assign(n, nullptr); }
+        return rc;
+    }
+    auto it = c->keys.find(HEC_RLK_ID);
+    if (it == c->keys.end()) return c->fail(HEC_E_NOKEY, "relinearisation key missing");
+    out.assign(n, nullptr);
+    auto bail = [&](int e) { for (hec_ct *o : out) hec_ct_free(c, o); out.assign(n, nullptr); return e; };
+    for (size_t m = 0; m < n; m++)
+        if ((rc = hec_ct_alloc(c, level, s0, &out[m]))) return bail(rc);
+    const int nP = c->nP, T = level;
+    if ((rc = reserve(c, n * (decomp_limbs(c, level) + ks_limbs(c, level) + 3 * (size_t)L + 2 * (size_t)L + 4)))) return bail(rc);
+    std::vector<u64 *> c2(n), d0(n), d1(n);
+    std::vector<TensorJob> tj;
+    for (size_t m = 0; m < n; m++) {
+        c2[m] = c->scratch(L); d0[m] = c->scratch(L); d1[m] = c->scratch(L);
+        for (int i = 0; i < L; i++)
+            tj.push_back({a[m]->limb(0, i), a[m]->limb(1, i), b[m]->limb(0, i), b[m]->limb(1, i), out[m]->limb(0, i), out[m]->limb(1, i),
+                          c2[m] + (size_t)i * HEC_N, mform(c->hm[i].rmod, c->q(i)), i});
+    }
+    for (size_t off = 0; off < tj.size(); off += HEC_TNJOBS) {
+        int k = (int)std::min<size_t>(HEC_TNJOBS, tj.size() - off);
+        TensorJobs J;
+        for (int i = 0; i < k; i++) J.j[i] = tj[off + i];
+        launch_k(c, k_tensor, dim3(32, k), dim3(256), J, c->dmods);
+        c->launches += 1;
+    }
+    if ((rc = check_launch(c, "tensor"))) return bail(rc);
+    std::vector<const u64 *> src(c2.begin(), c2.end());
+    std::vector<Decomp> dc;
+    if ((rc = decompose_many(c, level, src, dc))) return bail(rc);
+    std::vector<const SwKey *> keys(n, &it->second);
+    // inner product with the key, left in Q||P: item 2m + p = polynomial p of ciphertext m
+    std::vector<u64 *> accQ, accP;
+    for (size_t m = 0; m < n; m++) {
+        u64 *ap = c->scratch(2 * (size_t)nP);
+        accQ.push_back(d0[m]); accP.push_back(ap);
+        accQ.push_back(d1[m]); accP.push_back(ap + (size_t)nP * HEC_N);
+    }
+    if ((rc = ks_mac_many(c, level, dc, keys, accQ, accP))) return bail(rc);
+    // mod-down, first half: InvNTT on P, exact basis extension P -> every Q limb (coefficient domain)
+    std::vector<LimbJob> nj;
+    for (size_t i = 0; i < 2 * n; i++)
+        for (int j = 0; j < nP; j++) nj.push_back({accP[i] + (size_t)j * HEC_N, accP[i] + (size_t)j * HEC_N, c->modP(j), 0});
+    if ((rc = hec_launch_ntt(c, nj, true))) return bail(rc);
+    u64 *x = c->scratch(2 * n * L), *vt = c->scratch(2 * n);
+    std::vector<ModupJob> mj;
+    for (size_t i = 0; i < 2 * n; i++)
+        for (int l = 0; l < L; l++) mj.push_back(modup_job(c, c->pq, accP[i], HEC_N, c->modQ(l), x + (i * L + l) * HEC_N));
+    if ((rc = launch_modup(c, mj))) return bail(rc);
+    // the limb that is dropped: complete its mod-down (+ the tensor product's c0 / c1), transform back, centre
+    nj.clear();
+    for (size_t i = 0; i < 2 * n; i++) {
+        u64 *xi = x + (i * L + T) * HEC_N;
+        nj.push_back({xi, vt + i * HEC_N, T, HEC_LJ_EPI | HEC_LJ_ADD, xi, accQ[i] + (size_t)T * HEC_N, c->negpinv[T], 0,
+                      out[i / 2]->limb((int)(i & 1), T), 0});
+    }
+    if ((rc = hec_launch_ntt(c, nj, false))) return bail(rc);
+    nj.clear();
+    const u64 qT = c->q(T), half = (qT - 1) >> 1;
+    std::vector<EwJob> ej;
+    for (size_t i = 0; i < 2 * n; i++) {
+        nj.push_back({vt + i * HEC_N, vt + i * HEC_N, T, 0});
+        ej.push_back(ewjob(vt + i * HEC_N, nullptr, vt + i * HEC_N, T, half));
+    }
+    if ((rc = hec_launch_ntt(c, nj, true))) return bail(rc);
+    if ((rc = launch_ew<EW_CENTER>(c, ej))) return bail(rc);
+    // the kept limbs: one transform of x_l + P r_l, both combines in its epilogue
+    nj.clear();
+    for (size_t i = 0; i < 2 * n; i++)
+        for (int l = 0; l < T; l++) {
+            const u64 ql = c->q(l);
+            u64 Pm = 1;
+            for (int j = 0; j < nP; j++) Pm = mulmod(Pm, c->q(c->modP(j)) % ql, ql);
+            const u64 pq_inv = invmod(mulmod(Pm, qT % ql, ql), ql);
+            u64 *xi = x + (i * L + l) * HEC_N;
+            u64 *dl = out[i / 2]->limb((int)(i & 1), l); // d_l in, the result out (each thread reads its element before it writes it)
+            LimbJob j = {xi, dl, l, HEC_LJ_PRO2 | HEC_LJ_EPI | HEC_LJ_ADDS, xi, accQ[i] + (size_t)l * HEC_N, mform(ql - pq_inv, ql),
+                         ql - half % ql, dl, 0, vt + i * HEC_N, mform(Pm, ql), mform(invmod(qT % ql, ql), ql)};
+            nj.push_back(j);
+        }
+    if ((rc = hec_launch_ntt(c, nj, false))) return bail(rc);
+    for (size_t m = 0; m < n; m++) { out[m]->level = level - 1; out[m]->scale = s0 / (double)qT; }
+    if ((rc = hec_rescale_many(c, out, min_scale))) return bail(rc);
     return HEC_OK;
 }
 extern "C" int hec_mul_relin_new(hec_ctx *c, const hec_ct *a, const hec_ct *b, hec_ct **out) {

@@ -23,10 +23,20 @@
 // mid: where the first pass leaves its result (null: out) -- needed when ep_b aliases out
 //   scatter_g != 0: the result is written through the automorphism, out[index_g^-1[i]] = x[i] with scatter_g = g^-1 mod 2N
 //                   (PermuteNTTWithIndexLvl as scattered stores of the last pass instead of a gather pass of its own)
-struct LimbJob { const u64 *in; u64 *out; int mod; int flags; u64 *mid; const u64 *ep_b; u64 ep_s0; u64 pro_s0; const u64 *ep_add; u32 scatter_g; };
+//   HEC_LJ_PRO2: x = in mod q + ((pro_b mod q) + pro_s0) * pro_s1 * R^-1 -- a second coefficient-domain operand, scaled
+//                (the rescale's centred remainder times P, folded into the mod-down's transform: hec_mul_relin_rescale_many)
+//   HEC_LJ_ADDS: like ADD with the addend scaled: x += ep_add * ep_s1 * R^-1
+struct LimbJob { const u64 *in; u64 *out; int mod; int flags; u64 *mid; const u64 *ep_b; u64 ep_s0; u64 pro_s0; const u64 *ep_add; u32 scatter_g;
+                 const u64 *pro_b; u64 pro_s1; u64 ep_s1; };
 #define HEC_LJ_PRO 1
 #define HEC_LJ_EPI 2
 #define HEC_LJ_ADD 4
+#define HEC_LJ_PRO2 8
+#define HEC_LJ_ADDS 16
+__device__ __forceinline__ u64 lj_pro2(const LimbJob &job, u32 n, const ModC &M) {
+    const u64 r = mred(addmod(canon(job.pro_b[n], M), job.pro_s0, M.q), job.pro_s1, M.q, M.qinv);
+    return addmod(canon(job.in[n], M), r, M.q);
+}
 // programmatic dependent launch: let the next kernel of the stream be scheduled while this grid drains, and do not touch
 // memory before the previous grid has completed (both are no-ops for a kernel launched without the attribute)
 #define HEC_PDL_SYNC() asm volatile("griddepcontrol.launch_dependents;\n\tgriddepcontrol.wait;" ::: "memory")
@@ -42,6 +52,8 @@ struct LimbJob { const u64 *in; u64 *out; int mod; int flags; u64 *mid; const u6
 // forward NTT = k_col_fwd then k_row_fwd;  inverse = k_row_inv then k_col_inv
 // (ring.NTT / ring.InvNTT, L:ring/ring_ntt.go:74-626).  grid = (16, njobs); the job table lives in device memory
 // (content-addressed, hec.cu stage_cached), so one launch takes every limb of a batched operation.
+// EXT: the job list uses HEC_LJ_PRO2 / HEC_LJ_ADDS (a separate instantiation: the common one stays as lean as it was)
+template <bool EXT>
 __global__ void __launch_bounds__(HEC_THREADS, HEC_GEN_MINB) k_col_fwd(const LimbJob *__restrict__ jobs, const ModC *__restrict__ mods) {
     HEC_PDL_TRIGGER();
     __shared__ u64 sm[HEC_TILE];
@@ -51,7 +63,10 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_GEN_MINB) k_col_fwd(const Lim
     ColGeom G(blockIdx.x);
     if (M.small) {
         u32 y[16];
-        if (job.flags & HEC_LJ_PRO) {
+        if (EXT && (job.flags & HEC_LJ_PRO2)) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) y[k] = (u32)lj_pro2(job, G.gA(k), M);
+        } else if (job.flags & HEC_LJ_PRO) {
 #pragma unroll
             for (int k = 0; k < 16; k++) y[k] = (u32)addmod(canon(job.in[G.gA(k)], M), job.pro_s0, M.q);
         } else {
@@ -64,16 +79,22 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_GEN_MINB) k_col_fwd(const Lim
         return;
     }
     u64 x[16];
+    if (EXT && (job.flags & HEC_LJ_PRO2)) {
 #pragma unroll
-    for (int k = 0; k < 16; k++) x[k] = job.in[G.gA(k)];
-    if (job.flags & HEC_LJ_PRO) {
+        for (int k = 0; k < 16; k++) x[k] = lj_pro2(job, G.gA(k), M);
+    } else {
 #pragma unroll
-        for (int k = 0; k < 16; k++) x[k] = addmod(canon(x[k], M), job.pro_s0, M.q);
+        for (int k = 0; k < 16; k++) x[k] = job.in[G.gA(k)];
+        if (job.flags & HEC_LJ_PRO) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) x[k] = addmod(canon(x[k], M), job.pro_s0, M.q);
+        }
     }
     col_fwd8(x, sm, G, M);
 #pragma unroll
     for (int k = 0; k < 16; k++) job.out[G.gB(k)] = x[k];
 }
+template <bool EXT>
 __global__ void __launch_bounds__(HEC_THREADS, HEC_GEN_MINB) k_row_fwd(const LimbJob *__restrict__ jobs, const ModC *__restrict__ mods) {
     HEC_PDL_TRIGGER();
     __shared__ u64 sm[16 * HEC_ROW_PITCH];
@@ -103,6 +124,9 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_GEN_MINB) k_row_fwd(const Lim
         if (job.flags & HEC_LJ_ADD) {
 #pragma unroll
             for (int k = 0; k < 16; k++) x[k] = addmod(x[k], job.ep_add[G.gbase + 16 * k], M.q);
+        } else if (EXT && (job.flags & HEC_LJ_ADDS)) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) x[k] = addmod(x[k], mred(job.ep_add[G.gbase + 16 * k], job.ep_s1, M.q, M.qinv), M.q);
         }
     }
     if (job.scatter_g) {
@@ -370,6 +394,25 @@ __global__ void __launch_bounds__(256) k_dot(const DotJob *__restrict__ jobs, co
         }
 #pragma unroll
         for (int k = 0; k < HEC_DOT_U; k++) job.out[i + k * S] = acc[k];
+    }
+}
+
+// out = cst + sum_t a_t * s_t * R^-1 with scalars s_t (Montgomery form): the whole linear combination of power-basis
+// ciphertexts that EvaluatePoly's leaf forms (evaluatePolyFromPowerBasis: AddConst + one MultByGaussianIntegerAndAdd per
+// coefficient) in ONE pass -- each term is read once and the sum written once, instead of a read-modify-write launch per
+// term.  table[a_off + t] holds the operand pointers, table[s_off + t] the scalars.
+struct LinJob { long long a_off, s_off; u64 *out; u64 cst; int mod; int T; };
+__global__ void __launch_bounds__(256) k_lincomb(const LinJob *__restrict__ jobs, const u64 *__restrict__ table, const ModC *__restrict__ mods) {
+    HEC_PDL_SYNC();
+    const LinJob J = jobs[blockIdx.y];
+    const u64 q = mods[J.mod].q, qinv = mods[J.mod].qinv;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < HEC_N; i += gridDim.x * blockDim.x) {
+        u64 acc = J.cst;
+        for (int t = 0; t < J.T; t++) {
+            const u64 *a = reinterpret_cast<const u64 *>(table[J.a_off + t]);
+            acc = addmod(acc, mred(a[i], table[J.s_off + t], q, qinv), q);
+        }
+        J.out[i] = acc;
     }
 }
 

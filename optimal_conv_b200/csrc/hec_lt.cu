@@ -385,6 +385,41 @@ static int btp_evaluate_cheby(hec_ctx *c, hec_ct **pct, const hec_btp_params *b)
     return rc;
 }
 
+// the same on both halves of a fully packed ciphertext at once (they share level and scale): every step is one launch
+// sequence for the two -- half the launches of the sine evaluation, and grids twice as full (a single ciphertext leaves
+// most of the 148 SMs idle in the small kernels)
+static int btp_evaluate_cheby_pair(hec_ctx *c, hec_ct **p0, hec_ct **p1, const hec_btp_params *b) {
+    std::vector<hec_ct *> cts = {*p0, *p1};
+    volatile double target = b->sinescale;
+    for (int i = 0; i < b->sin_rescal; i++) { volatile double prod = target * (double)b->sine_qi[i]; target = sqrt(prod); }
+    int rc = HEC_OK;
+    if (b->sin_type == 1 || b->sin_type == 2) {
+        volatile double den = b->sc_fac * (b->cheby_b - b->cheby_a);
+        rc = add_const_many(c, cts, -0.5 / den);
+    }
+    std::vector<hec_ct *> r;
+    if (!rc) rc = evaluate_poly_many(c, std::vector<const hec_ct *>(cts.begin(), cts.end()), b->cheby, b->n_cheby, target, b->sinescale, r, true);
+    if (rc) return rc;
+    hec_ct_free(c, cts[0]); hec_ct_free(c, cts[1]);
+    *p0 = r[0]; *p1 = r[1];
+    cts = r;
+    volatile double s = b->sqrt2pi;
+    for (int i = 0; i < b->sin_rescal && !rc; i++) {
+        s = s * s;
+        std::vector<hec_ct *> sq;
+        std::vector<const hec_ct *> cc(cts.begin(), cts.end());
+        rc = hec_mul_relin_many(c, cc, cc, sq);
+        if (rc) break;
+        hec_ct_free(c, cts[0]); hec_ct_free(c, cts[1]);
+        *p0 = sq[0]; *p1 = sq[1];
+        cts = sq;
+        rc = add_inplace_many(c, cts, std::vector<const hec_ct *>(cts.begin(), cts.end()));
+        if (!rc) rc = add_const_many(c, cts, -s);
+        if (!rc) rc = hec_rescale_many(c, cts, b->sinescale);
+    }
+    return rc;
+}
+
 // the common head of Bootstrapp (0x505d00) and BootstrappConv_CtoS (0x506800): to the bootstrapping scale at level 0,
 // modUp, ScaleUp, CoeffsToSlots, evaluateSine on both halves
 static int btp_until_sine(hec_ctx *c, const hec_ct *ct_in, const hec_btp_params *b, const hec_ptdiag *const *pdftinv, int nmat,
@@ -418,6 +453,17 @@ static int btp_until_sine(hec_ctx *c, const hec_ct *ct_in, const hec_btp_params 
     if (!rc) rc = hec_sub_sum(c, up, pdftinv[0]->log_slots);
     if (!rc) rc = hec_coeffs_to_slots(c, up, pdftinv, nmat, &r0, &r1);
     hec_ct **halves[2] = {&r0, &r1};
+    static const int pair = getenv("HEC_SINE_PAIR") ? atoi(getenv("HEC_SINE_PAIR")) : 1;
+    if (!rc && pair && r0 && r1 && r0->level == r1->level && r0->scale == r1->scale) { // evaluateSine on both halves at once
+        r0->scale = r0->scale * b->message_ratio;
+        r1->scale = r1->scale * b->message_ratio;
+        rc = btp_evaluate_cheby_pair(c, &r0, &r1, b);
+        for (int h = 0; h < 2 && !rc; h++) {
+            hec_ct *x = *halves[h];
+            volatile double d = b->postscale * b->message_ratio / b->params_scale;
+            x->scale = x->scale / d;
+        }
+    } else
     for (int h = 0; h < 2 && !rc; h++) {                       // evaluateSine (0x508380); ct1 is NULL under sparse packing
         hec_ct *x = *halves[h];
         if (!x) continue;
@@ -444,11 +490,12 @@ extern "C" int hec_bootstrap_ctos(hec_ctx *c, const hec_ct *ct_in, const hec_btp
     // (under sparse packing the reference binary dereferences its nil second half here, 0x506e8e, and dies; the one
     // ciphertext there is gets the same treatment as at full packing)
     hec_ct *halves[2] = {r0, r1};
-    for (int h = 0; h < 2 && !rc; h++) {
-        if (!halves[h]) continue;
-        rc = hec_mult_by_const(c, halves[h], k);
-        if (!rc) rc = hec_rescale(c, halves[h], b->params_scale);
-    }
+    for (int h = 0; h < 2 && !rc; h++)
+        if (halves[h]) rc = hec_mult_by_const(c, halves[h], k);
+    if (!rc && r0 && r1 && r0->level == r1->level && r0->scale == r1->scale) rc = hec_rescale_many(c, {r0, r1}, b->params_scale);
+    else
+        for (int h = 0; h < 2 && !rc; h++)
+            if (halves[h]) rc = hec_rescale(c, halves[h], b->params_scale);
     if (rc) { hec_ct_free(c, r0); hec_ct_free(c, r1); return rc; }
     *ct0 = r0; *ct1 = r1;
     if (constant) *constant = k;

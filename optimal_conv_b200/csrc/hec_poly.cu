@@ -174,14 +174,22 @@ struct PolyEval {
         for (hec_ct *p : o) v.push_back(hold(p));
         return v;
     }
+    // Rescale(MulRelinNew(a, b), eval_scale) with the first division fused into the relinearisation (hec.cu)
+    CtV mul_relin_rescale(const CtV &a, const CtV &b) {
+        std::vector<hec_ct *> o;
+        if ((rc = hec_mul_relin_rescale_many(c, craw(a), craw(b), eval_scale, o))) return CtV();
+        CtV v;
+        for (hec_ct *p : o) v.push_back(hold(p));
+        return v;
+    }
     // computePowerBasis: C[n] = Rescale(MulRelinNew(C[ceil(n/2)], C[n/2]))
     bool power(int n) {
         if (C.count(n)) return true;
         int a = (n + 1) / 2, b = n >> 1;
         if (!power(a) || !power(b)) return false;
         if (cheby && a != b && !power(a - b)) return false;
-        CtV r = mul_relin(C[a], C[b]);
-        if (r.empty() || (rc = hec_rescale_many(c, raw(r), eval_scale))) return false;
+        CtV r = mul_relin_rescale(C[a], C[b]);
+        if (r.empty()) return false;
         if (cheby) {
             if ((rc = add_inplace_many(c, raw(r), craw(r)))) return false;                       // 2 T_a T_b
             if (a == b) rc = add_const_many(c, raw(r), -1.0);                                    // - T_0
@@ -215,17 +223,58 @@ struct PolyEval {
         }
         int lvl = level(C[p.degree()]);
         double qi = (double)c->q(lvl);
-        CtV res = zero(n, lvl, ts * qi);
-        if (res.empty()) return res;
-        if (fabs(p.co[0]) > 1e-14 && (rc = add_const_many(c, raw(res), p.co[0]))) return CtV();
+        // res = p.co[0] + sum_key C[key] * k_key: NewCiphertext (zero) + AddConst + MultByGaussianIntegerAndAdd per term,
+        // formed in one pass (k_lincomb); every C[key] is at a level >= lvl, so each term covers all limbs of res
+        CtV res;
+        for (size_t m = 0; m < n; m++) {
+            hec_ct *o = nullptr;
+            if ((rc = hec_ct_alloc(c, lvl, ts * qi, &o))) return CtV();
+            res.push_back(hold(o));
+        }
+        std::vector<int> keys;
+        std::vector<int64_t> ks;
         for (int key = p.degree(); key > 0; key--)
             if (fabs(p.co[key]) > 1e-14) {
                 volatile double const_scale = ts * qi / scale(C[key]); // (ts * qi) / scale, as the Go expression associates
                 volatile double prod = p.co[key] * const_scale;
                 // Go's int64(float64) on amd64 is CVTTSD2SQ: out-of-range (and NaN) give the "integer indefinite" -2^63
                 int64_t k = (prod >= -9223372036854775808.0 && prod < 9223372036854775808.0) ? (int64_t)prod : INT64_MIN;
-                if ((rc = mult_int_add_many(c, craw(C[key]), k, raw(res)))) return CtV();
+                if (level(C[key]) < lvl) { rc = c->fail(HEC_E_LEVEL, "power basis below the leaf's level"); return CtV(); }
+                keys.push_back(key); ks.push_back(k);
             }
+        {
+            const size_t nt = keys.size();
+            std::vector<u64> table;          // per job: nt pointers, then nt scalars
+            std::vector<LinJob> jobs;
+            for (size_t m = 0; m < n; m++)
+                for (int pp = 0; pp < 2; pp++)
+                    for (int i = 0; i <= lvl; i++) {
+                        const u64 q = c->q(i);
+                        LinJob J;
+                        J.a_off = (long long)table.size(); J.s_off = J.a_off + (long long)nt;
+                        J.out = res[m]->limb(pp, i); J.mod = i; J.T = (int)nt;
+                        // AddConst touches c0 only: scaleUpExact(c, scale, q_i) in every slot
+                        J.cst = (pp == 0 && fabs(p.co[0]) > 1e-14) ? scale_up_exact(p.co[0], res[m]->scale, q) % q : 0;
+                        for (size_t t = 0; t < nt; t++) table.push_back((u64)(uintptr_t)C[keys[t]][m]->limb(pp, i));
+                        for (size_t t = 0; t < nt; t++) {
+                            const int64_t k = ks[t];
+                            const u64 r = k < 0 ? (q - ((u64)(-(k + 1)) + 1) % q) % q : (u64)k % q; // interfaceMod
+                            table.push_back(mform(r, q));
+                        }
+                        jobs.push_back(J);
+                    }
+            std::vector<char> h(table.size() * sizeof(u64) + jobs.size() * sizeof(LinJob));
+            memcpy(h.data(), table.data(), table.size() * sizeof(u64));
+            memcpy(h.data() + table.size() * sizeof(u64), jobs.data(), jobs.size() * sizeof(LinJob));
+            char *dbuf = nullptr;
+            if ((rc = stage_cached(c, h, &dbuf))) return CtV();
+            const LinJob *dj = reinterpret_cast<const LinJob *>(dbuf + table.size() * sizeof(u64));
+            unsigned gx = 32;
+            while (gx < 256 && gx * (unsigned)jobs.size() < 592) gx *= 2;
+            launch_k(c, k_lincomb, dim3(gx, (unsigned)jobs.size()), dim3(256), dj, reinterpret_cast<const u64 *>(dbuf), c->dmods);
+            c->launches += 1;
+            if ((rc = check_launch(c, "lincomb"))) return CtV();
+        }
         if ((rc = hec_rescale_many(c, raw(res), eval_scale))) return CtV();
         return res;
     }
@@ -254,6 +303,12 @@ struct PolyEval {
             while (level(res) != level(tmp) + 1)
                 for (auto &x : res)
                     if ((rc = hec_drop_level(c, x.get(), 1))) return CtV();
+        if (std::min(level(res), level(C[nxt])) > level(tmp)) { // the product's level: rescale first, then add
+            CtV prod = mul_relin_rescale(res, C[nxt]);
+            if (prod.empty()) return prod;
+            if ((rc = add_inplace_many(c, raw(prod), craw(tmp)))) return CtV();
+            return prod;
+        }
         CtV prod = mul_relin(res, C[nxt]);
         if (prod.empty()) return prod;
         if (level(prod) > level(tmp)) {

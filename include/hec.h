@@ -315,7 +315,8 @@ int hec_plan_kernel_names(const hec_plan *plan, char *buf, int cap);
 /* 1 if the plan carries its level-0 polynomials as pairs (U, e), value = U - NTT(e), and runs one forward transform per
  * output polynomial at the end instead of one per rescale / mod-down (same results bit for bit; chosen at creation when
  * max_ob <= 256, batch * max_ob / norm >= 64 and the pl_idx plaintexts are the monomials of conv.go:241-254; HEC_DEFER=0
- * in the environment turns it off, 2 forces it for small batches too) */
+ * in the environment turns it off, 2 forces it for small batches too; the single-ciphertext plans hec_conv_then_pack
+ * builds and caches never defer: they may run once, and a deferred plan costs more to set up than one run saves) */
 int hec_plan_is_deferred(const hec_plan *plan);
 void hec_plan_destroy(hec_plan *plan);
 /* hec_conv_then_pack (fused) keeps the plans it builds, keyed by its arguments' identities (plaintext and key

@@ -276,7 +276,7 @@ static EwJob ewjob(const u64 *a, const u64 *b, u64 *out, int mod, u64 s0 = 0, u3
 
 // device copy of a small host table, cached by content (hec_ctx::staged).  The tables hold buffer addresses, which
 // repeat as long as the caller repeats the operation on the same ciphertexts / scratch layout.
-#define HEC_STAGE_CAP ((size_t)1 << 30) // a network layer chain stages thousands of distinct tables; starting over costs a device sync
+#define HEC_STAGE_CAP ((size_t)1 << 30) // size of the ring of slabs (a network layer chain stages thousands of distinct tables per image)
 #define HEC_STAGE_SLAB ((size_t)16 << 20)
 static int stage_cached(hec_ctx *c, std::vector<char> &h, char **dev) {
     h.resize((h.size() + 7) & ~(size_t)7, 0);
@@ -288,34 +288,59 @@ static int stage_cached(hec_ctx *c, std::vector<char> &h, char **dev) {
         for (auto &e : it->second)
             if (e.host.size() == h.size() && memcmp(e.host.data(), h.data(), h.size()) == 0) { *dev = e.dev; return HEC_OK; }
     const size_t need = (h.size() + 255) & ~(size_t)255;
-    if (c->staged_bytes + need > HEC_STAGE_CAP) { // rare: start over (kernels in flight may still read the old tables)
-        HEC_CUDA(c, cudaStreamSynchronize(c->stream));
-        for (char *p : c->stage_slabs) cudaFree(p);
-        c->stage_slabs.clear();
-        c->stage_cur = nullptr;
-        c->staged.clear();
-        c->staged_bytes = 0;
-    }
     hec_ctx::StagedTab e;
-    if (need > HEC_STAGE_SLAB) { // an unusually large table gets a block of its own
+    const size_t ring = HEC_STAGE_CAP / HEC_STAGE_SLAB;
+    if (need > HEC_STAGE_SLAB) { // an unusually large table gets a block of its own (freed when the ring wraps)
         HEC_CUDA(c, cudaMalloc(&e.dev, need));
-        c->stage_slabs.push_back(e.dev);
+        c->stage_big.push_back(e.dev);
     } else {
         if (!c->stage_cur || c->stage_slab_top + need > HEC_STAGE_SLAB) {
-            char *slab = nullptr;
-            HEC_CUDA(c, cudaMalloc(&slab, HEC_STAGE_SLAB));
-            c->stage_slabs.push_back(slab);
-            c->stage_cur = slab;
+            if (c->stage_cur) {
+                HEC_CUDA(c, cudaEventRecord(c->stage_events[c->stage_idx], c->stream)); // every launch that reads this slab is in the stream by now
+                c->stage_idx = (c->stage_idx + 1) % ring;
+            }
+            if (c->stage_idx == c->stage_slabs.size()) { // the ring is still growing
+                char *slab = nullptr;
+                cudaEvent_t ev = nullptr;
+                HEC_CUDA(c, cudaMalloc(&slab, HEC_STAGE_SLAB));
+                HEC_CUDA(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                c->stage_slabs.push_back(slab);
+                c->stage_events.push_back(ev);
+                c->stage_keys.emplace_back();
+            } else {                                     // come round: retire what this slab held
+                HEC_CUDA(c, cudaEventSynchronize(c->stage_events[c->stage_idx]));
+                char *lo = c->stage_slabs[c->stage_idx], *hi = lo + HEC_STAGE_SLAB;
+                for (uint64_t key : c->stage_keys[c->stage_idx]) {
+                    auto f = c->staged.find(key);
+                    if (f == c->staged.end()) continue;
+                    auto &v = f->second;
+                    v.erase(std::remove_if(v.begin(), v.end(), [&](const hec_ctx::StagedTab &t) { return t.dev >= lo && t.dev < hi; }), v.end());
+                    if (v.empty()) c->staged.erase(f);
+                }
+                c->stage_keys[c->stage_idx].clear();
+                if (c->stage_idx == 0 && !c->stage_big.empty()) { // the oversized blocks go once per turn of the ring
+                    HEC_CUDA(c, cudaStreamSynchronize(c->stream));
+                    for (auto itb = c->staged.begin(); itb != c->staged.end();) {
+                        auto &v = itb->second;
+                        v.erase(std::remove_if(v.begin(), v.end(), [&](const hec_ctx::StagedTab &t) {
+                                    return std::find(c->stage_big.begin(), c->stage_big.end(), t.dev) != c->stage_big.end(); }), v.end());
+                        itb = v.empty() ? c->staged.erase(itb) : std::next(itb);
+                    }
+                    for (char *pb : c->stage_big) cudaFree(pb);
+                    c->stage_big.clear();
+                }
+            }
+            c->stage_cur = c->stage_slabs[c->stage_idx];
             c->stage_slab_top = 0;
         }
         e.dev = c->stage_cur + c->stage_slab_top;
         c->stage_slab_top += need;
+        c->stage_keys[c->stage_idx].push_back(k);
     }
     e.host = h;
     // pageable source: staged by the driver before the call returns
     HEC_CUDA(c, cudaMemcpyAsync(e.dev, e.host.data(), h.size(), cudaMemcpyHostToDevice, c->stream));
     *dev = e.dev;
-    c->staged_bytes += need;
     c->staged[k].push_back(std::move(e));
     return HEC_OK;
 }
@@ -483,6 +508,8 @@ extern "C" void hec_ctx_destroy(hec_ctx *c) {
     hec_plan_cache_clear(c);
     for (auto &kv : c->keys) { cudaFree(kv.second.buf); delete kv.second.kb; }
     for (char *p : c->stage_slabs) cudaFree(p);
+    for (char *p : c->stage_big) cudaFree(p);
+    for (cudaEvent_t ev : c->stage_events) cudaEventDestroy(ev);
     if (c->arena) cudaFree(c->arena);
     if (c->dtables) cudaFree(c->dtables);
     if (c->dmods) cudaFree(c->dmods);
@@ -1192,15 +1219,33 @@ int hec_mul_relin_many(hec_ctx *c, const std::vector<const hec_ct *> &a, const s
 // itself is completed first (its mod-down as usual), transformed back and centred to give r.  Exact arithmetic modulo
 // every q_l, so the result is bit for bit that of the two operations in sequence (L:ckks/evaluator.go:1398-1444,
 // 1291-1325; L:ring/ring_scaling.go:442-513).  Further divisions, if the scale asks for them, run unfused.
-int hec_mul_relin_rescale_many(hec_ctx *c, const std::vector<const hec_ct *> &a, const std::vector<const hec_ct *> &b, double min_scale,
-                               std::vector<hec_ct *> &out) {
+// addend (optional): Rescale(Add(MulRelinNew(a, b), addend)) -- the sum is formed on the tensor product's c0 / c1 before the
+// mod-down adds the key-switched part (exact, so the order is free).  The caller guarantees what hec_relin_rescale_fusable
+// checks: levels and scales uniform over the batch, addend at the product's level or above with a scale the Add would
+// not have to match by an integer factor.
+static bool hec_relin_rescale_fusable(hec_ctx *c, const std::vector<const hec_ct *> &a, const std::vector<const hec_ct *> &b, double min_scale,
+                                      const std::vector<const hec_ct *> *addend) {
     static const int fuse = getenv("HEC_RELIN_RESCALE") ? atoi(getenv("HEC_RELIN_RESCALE")) : 1;
+    const size_t n = a.size();
+    const int level = std::min(a[0]->level, b[0]->level);
+    double s0 = a[0]->scale * b[0]->scale;
+    bool same = fuse && level > 0;
+    for (size_t m = 0; m < n && same; m++) same = std::min(a[m]->level, b[m]->level) == level && a[m]->scale * b[m]->scale == s0;
+    if (same && addend) {
+        const double sb = (*addend)[0]->scale;
+        for (size_t m = 0; m < n && same; m++) same = (*addend)[m]->level >= level && (*addend)[m]->scale == sb;
+        if (same && ((s0 > sb && floor(s0 / sb) > 1) || (sb > s0 && floor(sb / s0) > 1))) same = false; // evaluateInPlace would rescale one side
+        s0 = std::max(s0, sb);
+    }
+    return same && s0 / (double)c->q(level) >= min_scale / 2;
+}
+int hec_mul_relin_rescale_many(hec_ctx *c, const std::vector<const hec_ct *> &a, const std::vector<const hec_ct *> &b, double min_scale,
+                               std::vector<hec_ct *> &out, const std::vector<const hec_ct *> *addend = nullptr) {
     size_t n = a.size();
     int level = std::min(a[0]->level, b[0]->level), L = level + 1, rc;
-    const double s0 = a[0]->scale * b[0]->scale;
-    bool same = true;
-    for (size_t m = 0; m < n; m++) same = same && std::min(a[m]->level, b[m]->level) == level && a[m]->scale * b[m]->scale == s0;
-    if (!fuse || !same || level == 0 || !(s0 / (double)c->q(level) >= min_scale / 2)) {
+    double s0 = a[0]->scale * b[0]->scale;
+    if (!hec_relin_rescale_fusable(c, a, b, min_scale, addend)) {
+        if (addend) return c->fail(HEC_E_INVAL, "fused MulRelin + Add + Rescale: operands do not qualify");
         if ((rc = hec_mul_relin_many(c, a, b, out))) return rc;
         rc = hec_rescale_many(c, out, min_scale);
         if (rc) { for (hec_ct *o : out) hec_ct_free(c, o); out.assign(n, nullptr); }
@@ -1230,6 +1275,14 @@ int hec_mul_relin_rescale_many(hec_ctx *c, const std::vector<const hec_ct *> &a,
         c->launches += 1;
     }
     if ((rc = check_launch(c, "tensor"))) return bail(rc);
+    if (addend) { // Add(prod, addend): on the tensor product's c0 / c1, before the key-switched part joins them
+        std::vector<EwJob> aj;
+        for (size_t m = 0; m < n; m++)
+            for (int p = 0; p < 2; p++)
+                for (int i = 0; i < L; i++) aj.push_back(ewjob(out[m]->limb(p, i), (*addend)[m]->limb(p, i), out[m]->limb(p, i), i));
+        if ((rc = launch_ew<EW_ADD>(c, aj))) return bail(rc);
+        s0 = std::max(s0, (*addend)[0]->scale);
+    }
     std::vector<const u64 *> src(c2.begin(), c2.end());
     std::vector<Decomp> dc;
     if ((rc = decompose_many(c, level, src, dc))) return bail(rc);

@@ -434,15 +434,15 @@ extern "C" void hec_plan_destroy(hec_plan *p) {
     if (p->ev_t1) cudaEventDestroy(p->ev_t1);
     if (p->s_in) cudaStreamDestroy(p->s_in);
     if (p->s_out) cudaStreamDestroy(p->s_out);
-    if (p->pool) cudaFree(p->pool);
-    if (p->ptk_scaled) cudaFree(p->ptk_scaled);
-    if (p->ptk_pairs) cudaFree(p->ptk_pairs);
-    if (p->ptk_first) cudaFree(p->ptk_first);
-    if (p->key_pairs) cudaFree(p->key_pairs);
-    if (p->mono_pairs) cudaFree(p->mono_pairs);
-    if (p->bias_plain) cudaFree(p->bias_plain);
-    if (p->d_ctin) cudaFree((void *)p->d_ctin);
-    if (p->d_ptk) cudaFree((void *)p->d_ptk);
+    if (p->pool) cudaFreeAsync(p->pool, p->c->stream);
+    if (p->ptk_scaled) cudaFreeAsync(p->ptk_scaled, p->c->stream);
+    if (p->ptk_pairs) cudaFreeAsync(p->ptk_pairs, p->c->stream);
+    if (p->ptk_first) cudaFreeAsync(p->ptk_first, p->c->stream);
+    if (p->key_pairs) cudaFreeAsync(p->key_pairs, p->c->stream);
+    if (p->mono_pairs) cudaFreeAsync(p->mono_pairs, p->c->stream);
+    if (p->bias_plain) cudaFreeAsync(p->bias_plain, p->c->stream);
+    if (p->d_ctin) cudaFreeAsync((void *)p->d_ctin, p->c->stream);
+    if (p->d_ptk) cudaFreeAsync((void *)p->d_ptk, p->c->stream);
     plan_unref_all(p);
     delete p;
 }
@@ -450,11 +450,16 @@ extern "C" void hec_plan_destroy(hec_plan *p) {
 // The deferred-transform plan turns the products with the pack monomials into index shifts of coefficients, so the
 // plaintexts the caller passes as pl_idx must BE the monomials X^step of gen_idxNlogs (conv.go:241-254): compare each
 // with the transform of the unit vector.  Returns 1 / 0, or a negative error code.
+// plan memory comes from the context's stream-ordered pool (freed blocks stay cached there): a caller that builds a plan
+// per convolution -- hec_conv_then_pack with fresh kernel plaintexts for every image -- would otherwise pay cudaMalloc /
+// cudaFree round trips of hundreds of megabytes to the driver per layer
+static cudaError_t plan_alloc(hec_ctx *c, void **p, size_t bytes) { return cudaMallocFromPoolAsync(p, bytes, c->pool, c->stream); }
+
 static int pack_monomials_check(hec_ctx *c, const hec_pt *const *pt_idx, int B, int na) {
     u64 *tmp = nullptr;
     int *flag = nullptr;
-    if (cudaMalloc(&tmp, 3 * HEC_N * sizeof(u64)) != cudaSuccess) return HEC_E_NOMEM;
-    if (cudaMalloc(&flag, sizeof(int)) != cudaSuccess) { cudaFree(tmp); return HEC_E_NOMEM; }
+    if (plan_alloc(c, (void **)&tmp, 3 * HEC_N * sizeof(u64)) != cudaSuccess) return HEC_E_NOMEM;
+    if (plan_alloc(c, (void **)&flag, sizeof(int)) != cudaSuccess) { cudaFreeAsync(tmp, c->stream); return HEC_E_NOMEM; }
     cudaMemsetAsync(flag, 0, sizeof(int), c->stream);
     static const u64 one = 1;
     int step = B / 2, logStep = 0, rc = HEC_OK;
@@ -473,14 +478,26 @@ static int pack_monomials_check(hec_ctx *c, const hec_pt *const *pt_idx, int B, 
     int h = 0;
     if (!rc && cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) rc = HEC_E_CUDA;
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) rc = HEC_E_CUDA;
-    cudaFree(tmp);
-    cudaFree(flag);
+    cudaFreeAsync(tmp, c->stream);
+    cudaFreeAsync(flag, c->stream);
     return rc ? rc : (h == 0 ? 1 : 0);
 }
 
+static int plan_create_impl(hec_ctx *c, const hec_pt *const *pt_ker, int max_ob, int norm, double in_scale,
+                            double out_scale, const hec_pt *const *pt_idx, const hec_pt *pt_bias, int batch,
+                            hec_plan **out, bool allow_defer);
 extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_ob, int norm, double in_scale,
                                double out_scale, const hec_pt *const *pt_idx, const hec_pt *pt_bias, int batch,
                                hec_plan **out) {
+    return plan_create_impl(c, pt_ker, max_ob, norm, in_scale, out_scale, pt_idx, pt_bias, batch, out, true);
+}
+// allow_defer = false: the plan hec_conv_then_pack builds for ONE ciphertext.  Its caller may come back with fresh
+// plaintext handles for every image (the network harness does: a new prep_Ker result per layer and image), so the plan
+// may run once -- and a deferred plan costs more to set up (monomial check with a synchronisation, per-butterfly tables)
+// than one run of it saves (0.2 ms at B = 256).
+static int plan_create_impl(hec_ctx *c, const hec_pt *const *pt_ker, int max_ob, int norm, double in_scale,
+                            double out_scale, const hec_pt *const *pt_idx, const hec_pt *pt_bias, int batch,
+                            hec_plan **out, bool allow_defer) {
     if (!c || !pt_ker || !pt_idx || !out || batch < 1 || max_ob < 1 || norm < 1) return c ? c->fail(HEC_E_INVAL, "plan args") : HEC_E_INVAL;
     cudaSetDevice(c->device);
     if ((max_ob & (max_ob - 1)) || (norm & (norm - 1)) || norm > max_ob || max_ob > 4096)
@@ -519,7 +536,7 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
         // than the transforms saved (measured, B = 16: 0.41 / 0.52 / 0.73 ms deferred against 0.37 / 0.50 / 0.74 ms for
         // 1 / 2 / 4 ciphertexts per run, 3.84 against 4.32 ms for 32)
         static const int env_defer = getenv("HEC_DEFER") ? atoi(getenv("HEC_DEFER")) : 1;
-        if (env_defer && B <= 256 && (env_defer == 2 || (size_t)M * na >= 64)) {
+        if (env_defer && B <= 256 && (env_defer == 2 || (allow_defer && (size_t)M * na >= 64))) {
             int ok = pack_monomials_check(c, pt_idx, B, na);
             if (ok < 0) return bail(ok, "checking the pack monomials");
             p->defer = ok == 1;
@@ -528,12 +545,12 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
     const int mq0_ = c->modQ(0);
     const u64 q1inv0 = invmod(c->q(c->modQ(1)) % c->q(mq0_), c->q(mq0_)); // q1^-1 mod q0
     // ---- device memory: pointer tables + one pool ----
-    if (cudaMalloc((void **)&p->d_ctin, M * sizeof(u64 *)) != cudaSuccess) return bail(HEC_E_NOMEM, "cudaMalloc");
-    if (cudaMalloc((void **)&p->d_ptk, B * sizeof(ulonglong2 *)) != cudaSuccess) return bail(HEC_E_NOMEM, "cudaMalloc");
+    if (plan_alloc(c, (void **)&p->d_ctin, M * sizeof(u64 *)) != cudaSuccess) return bail(HEC_E_NOMEM, "cudaMalloc");
+    if (plan_alloc(c, (void **)&p->d_ptk, B * sizeof(ulonglong2 *)) != cudaSuccess) return bail(HEC_E_NOMEM, "cudaMalloc");
     // plan-owned copies of the kernel plaintexts with the MultByConst constants folded in:
     // (ct*pt)*k == ct*(pt*k); one multiply per coefficient at plan creation instead of one per conv
-    if (cudaMalloc(&p->ptk_scaled, (size_t)na * 2 * HEC_N * sizeof(u64)) != cudaSuccess) return bail(HEC_E_NOMEM, "cudaMalloc");
-    if (cudaMalloc(&p->ptk_pairs, (size_t)na * 2 * HEC_N * sizeof(ulonglong2)) != cudaSuccess) return bail(HEC_E_NOMEM, "cudaMalloc");
+    if (plan_alloc(c, (void **)&p->ptk_scaled, (size_t)na * 2 * HEC_N * sizeof(u64)) != cudaSuccess) return bail(HEC_E_NOMEM, "cudaMalloc");
+    if (plan_alloc(c, (void **)&p->ptk_pairs, (size_t)na * 2 * HEC_N * sizeof(ulonglong2)) != cudaSuccess) return bail(HEC_E_NOMEM, "cudaMalloc");
     std::vector<const ulonglong2 *> hk(B, nullptr);
     {
         std::vector<EwJob> ej;
@@ -561,8 +578,8 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
             for (int i = step0; i > 1; i /= 2) logStep0++;
             if (!pt_idx[logStep0]) return bail(HEC_E_INVAL, "pt_idx entry missing");
             u64 *tmp = nullptr;
-            if (cudaMalloc(&p->ptk_first, (size_t)2 * nbf * HEC_N * sizeof(ulonglong2)) != cudaSuccess ||
-                cudaMalloc(&tmp, (size_t)3 * nbf * HEC_N * sizeof(u64)) != cudaSuccess)
+            if (plan_alloc(c, (void **)&p->ptk_first, (size_t)2 * nbf * HEC_N * sizeof(ulonglong2)) != cudaSuccess ||
+                plan_alloc(c, (void **)&tmp, (size_t)3 * nbf * HEC_N * sizeof(u64)) != cudaSuccess)
                 return bail(HEC_E_NOMEM, "cudaMalloc");
             const int m0 = c->modQ(0);
             std::vector<EwJob> jm, js, ja;
@@ -574,7 +591,7 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
                 ja.push_back(ewjob(pa, t, t + 2 * HEC_N, m0));
             }
             if (launch_ew<EW_MULMONT>(c, jm) || launch_ew<EW_SUB>(c, js) || launch_ew<EW_ADD>(c, ja)) {
-                cudaFree(tmp);
+                cudaFreeAsync(tmp, c->stream);
                 return bail(HEC_E_CUDA, "first-level plaintext tables");
             }
             for (int u = 0; u < nbf; u++)
@@ -588,7 +605,8 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
         cudaFreeAsync(p->ptk_scaled, c->stream); // only the pairs are read from here on
         p->ptk_scaled = nullptr;
     }
-    if (cudaMemcpy((void *)p->d_ptk, hk.data(), B * sizeof(ulonglong2 *), cudaMemcpyHostToDevice) != cudaSuccess) return bail(HEC_E_CUDA, "memcpy ptk");
+    // small pageable copy, staged by the driver before the call returns; on the context's stream like the allocation
+    if (cudaMemcpyAsync((void *)p->d_ptk, hk.data(), B * sizeof(ulonglong2 *), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return bail(HEC_E_CUDA, "memcpy ptk");
     // chunking (see hec_plan): HEC_PLAN_CHUNK ciphertexts per chunk (0 / not a divisor of M: the whole batch at once),
     // HEC_PLAN_CHAINS chunks in flight
     {
@@ -605,7 +623,7 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
                  + (size_t)p->nchains * per_chain
                  + 2 * jobsA                     // X_0 .. X_last (geometric, < 2x)
                  + (p->defer ? 2 * jobsA + 4 * (size_t)M : 0); // deferred: the e halves of every level, the last transform's scratch, the results
-    if (cudaMalloc(&p->pool, limbs * HEC_N * sizeof(u64)) != cudaSuccess) return bail(HEC_E_NOMEM, "cudaMalloc plan pool");
+    if (plan_alloc(c, (void **)&p->pool, limbs * HEC_N * sizeof(u64)) != cudaSuccess) return bail(HEC_E_NOMEM, "cudaMalloc plan pool");
     u64 *cur = p->pool;
     auto take = [&](size_t n) { u64 *r = cur; cur += n * HEC_N; return r; };
     p->stage_in = take(4 * (size_t)M);
@@ -642,11 +660,11 @@ extern "C" int hec_plan_create(hec_ctx *c, const hec_pt *const *pt_ker, int max_
     auto pair = [](u64 w, u64 q) { return make_ulonglong2(w, (u64)(((u128)w << 64) / q)); };
     A.resc0 = pair(q0 - invmod(q1 % q0, q0), q0);
     A.uout = X[0]; A.eout = XE[0]; A.q1inv = pair(q1inv0, q0);
-    if (levels > 0 && (cudaMalloc(&p->mono_pairs, (size_t)levels * HEC_N * sizeof(ulonglong2)) != cudaSuccess ||
-                       cudaMalloc(&p->key_pairs, (size_t)levels * 2 * HEC_N * sizeof(ulonglong2)) != cudaSuccess))
+    if (levels > 0 && (plan_alloc(c, (void **)&p->mono_pairs, (size_t)levels * HEC_N * sizeof(ulonglong2)) != cudaSuccess ||
+                       plan_alloc(c, (void **)&p->key_pairs, (size_t)levels * 2 * HEC_N * sizeof(ulonglong2)) != cudaSuccess))
         return bail(HEC_E_NOMEM, "cudaMalloc");
     if (pt_bias) {
-        if (cudaMalloc(&p->bias_plain, HEC_N * sizeof(u64)) != cudaSuccess) return bail(HEC_E_NOMEM, "cudaMalloc");
+        if (plan_alloc(c, (void **)&p->bias_plain, HEC_N * sizeof(u64)) != cudaSuccess) return bail(HEC_E_NOMEM, "cudaMalloc");
         k_plan_tables<<<64, 256, 0, c->stream>>>(pt_bias->buf, nullptr, p->bias_plain, mq0, c->dmods);
         c->launches++;
     }
@@ -981,7 +999,7 @@ static int plan_cached(hec_ctx *c, const hec_pt *const *pt_ker, int max_ob, int 
             }
     }
     hec_plan *p = nullptr;
-    int rc = hec_plan_create(c, pt_ker, max_ob, norm, in_scale, out_scale, pt_idx, pt_bias, 1, &p);
+    int rc = plan_create_impl(c, pt_ker, max_ob, norm, in_scale, out_scale, pt_idx, pt_bias, 1, &p, false);
     if (rc) return rc;
     p->cache_key = key;
     c->plan_cache.insert(c->plan_cache.begin(), p);

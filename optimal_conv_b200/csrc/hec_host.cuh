@@ -97,11 +97,18 @@ struct hec_ctx {
     size_t arena_limbs = 0, arena_top = 0;
     // small job / pointer tables of k_modup2 and k_dot, kept on the device and found again by content: the same
     // operation on the same buffers (a layer repeated per image, a benchmark loop) then launches without a copy
+    // The device memory is a ring of slabs: when the ring comes round to a slab, the tables it held are dropped from
+    // the cache (and the event recorded when the ring left it is waited for -- long past by then), so a long chain of
+    // operations on ever new addresses (a network, image after image) keeps the most recent tables and never stalls
+    // to start over.
     struct StagedTab { std::vector<char> host; char *dev = nullptr; };
     std::unordered_map<uint64_t, std::vector<StagedTab>> staged;
-    size_t staged_bytes = 0;
-    std::vector<char *> stage_slabs; // device memory the tables are carved from (bump allocation)
-    char *stage_cur = nullptr;       // slab being filled
+    std::vector<char *> stage_slabs;                 // ring of slabs the tables are carved from (bump allocation inside a slab)
+    std::vector<cudaEvent_t> stage_events;           // recorded on the stream when the ring leaves a slab
+    std::vector<std::vector<uint64_t>> stage_keys;   // hash keys of the tables living in each slab
+    std::vector<char *> stage_big;                   // tables larger than a slab: blocks of their own, freed when the ring wraps
+    size_t stage_idx = 0;                            // slab being filled
+    char *stage_cur = nullptr;
     size_t stage_slab_top = 0;
     uint64_t launches = 0;
     uint64_t next_serial = 1;

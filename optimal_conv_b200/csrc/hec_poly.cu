@@ -309,6 +309,16 @@ struct PolyEval {
             if ((rc = add_inplace_many(c, raw(prod), craw(tmp)))) return CtV();
             return prod;
         }
+        {   // the product's level <= tmp's: Add first, then Rescale -- fused with the relinearisation when the Add is a plain one
+            std::vector<const hec_ct *> ra = craw(res), rb = craw(C[nxt]), rt = craw(tmp);
+            if (hec_relin_rescale_fusable(c, ra, rb, eval_scale, &rt)) {
+                std::vector<hec_ct *> o;
+                if ((rc = hec_mul_relin_rescale_many(c, ra, rb, eval_scale, o, &rt))) return CtV();
+                CtV v;
+                for (hec_ct *p2 : o) v.push_back(hold(p2));
+                return v;
+            }
+        }
         CtV prod = mul_relin(res, C[nxt]);
         if (prod.empty()) return prod;
         if (level(prod) > level(tmp)) {

@@ -802,7 +802,13 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convB2(ConvB P, const
 // B3: finish NTT_p0 of the digit (once), then for both key polys: multiply by key[c] (P limb) and
 //     run inverse stages t = 1..128 under p0                               grid.y = M*nb
 #define HEC_B3_SMEM ((16 * HEC_ROW_PITCH + HEC_TILE) * sizeof(u64)) // dynamic: above the 48 KB static limit
-__global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convB3(ConvB P, const ModC *__restrict__ mods) {
+#ifndef HEC_B3_MINB
+#define HEC_B3_MINB 2 // measured: 1.268 -> 1.253 ms per 64 convolutions against 3 CTAs / 80 registers; unrolling the key-polynomial loop loses (spills at 80, no gain at 128)
+#endif
+#ifndef HEC_B3_UNROLL
+#define HEC_B3_UNROLL 1
+#endif
+__global__ void __launch_bounds__(HEC_THREADS, HEC_B3_MINB) k_convB3(ConvB P, const ModC *__restrict__ mods) {
     extern __shared__ __align__(128) u64 dsm[];
     u64 *sm = dsm;
     u64 *stash = dsm + 16 * HEC_ROW_PITCH; // NTT_p0(digit), kept for the second key poly
@@ -815,7 +821,8 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convB3(ConvB P, const
 #pragma unroll
         for (int k = 0; k < 16; k++) stash[k * HEC_THREADS + threadIdx.x] = x[k]; // own slots only
     }
-#pragma unroll 1
+    constexpr int kUnrollC = HEC_B3_UNROLL; // (a macro is not expanded inside the pragma)
+#pragma unroll kUnrollC
     for (int c = 0; c < 2; c++) {
         const ulonglong2 *kv = reinterpret_cast<const ulonglong2 *>(P.keyP + c * P.keyPstride + G.b * 256 + 16 * G.p);
         u64 y[16];

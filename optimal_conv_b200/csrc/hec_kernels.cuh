@@ -621,7 +621,10 @@ struct AJob {
     __device__ __forceinline__ AJob(int job, int na) { c = job & 1; a = (job >> 1) % na; m = (job >> 1) / na; }
 };
 // A1: limb q1:  ct*(pt*k1) -> inverse stages t = 1..128
-__global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convA1(ConvA P, const ModC *__restrict__ mods) {
+#ifndef HEC_A1_MINB
+#define HEC_A1_MINB HEC_MINB
+#endif
+__global__ void __launch_bounds__(HEC_THREADS, HEC_A1_MINB) k_convA1(ConvA P, const ModC *__restrict__ mods) {
     __shared__ u64 sm[16 * HEC_ROW_PITCH];
     const AJob J(HEC_BJOB, P.na);
     const ModC M = mods[P.mq1];
@@ -762,7 +765,10 @@ struct BJob {
     }
 };
 // B1: z = tmp2.c1 = a1 - b1*mono (also stored) ; inverse stages t = 1..128 under q0      grid.y = M*nb
-__global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_convB1(ConvB P, const ModC *__restrict__ mods) {
+#ifndef HEC_B1_MINB
+#define HEC_B1_MINB 2 // measured: B1 0.483 -> 0.440 ms per 64 convolutions (its loads are latency-bound: more of them in flight at 128 registers); A1 and k_defA2 lose with the same change
+#endif
+__global__ void __launch_bounds__(HEC_THREADS, HEC_B1_MINB) k_convB1(ConvB P, const ModC *__restrict__ mods) {
     __shared__ u64 sm[16 * HEC_ROW_PITCH];
     const BJob J(HEC_BJOB, false, P);
     const ModC M = mods[P.mq0];
@@ -973,7 +979,10 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_defA1(ConvA P, const 
     row_storeA(x, P.w1 + (size_t)HEC_BJOB * HEC_N, G);
 }
 // dA2: finish InvNTT_q1, centre, lift into q0, divide by q1: e (coefficient domain, natural order)
-__global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_defA2(ConvA P, const ModC *__restrict__ mods) {
+#ifndef HEC_DA2_MINB
+#define HEC_DA2_MINB HEC_MINB
+#endif
+__global__ void __launch_bounds__(HEC_THREADS, HEC_DA2_MINB) k_defA2(ConvA P, const ModC *__restrict__ mods) {
     __shared__ u64 sm[HEC_TILE];
     const ModC M1 = mods[P.mq1];
     const ModC M0 = mods[P.mq0];
@@ -995,7 +1004,7 @@ __global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_defA2(ConvA P, const 
 // dB1 = k_convB1 on the U halves (z = Ua1 - Ub1*mono, inverse stages t = 1..128); on the FIRST pack level Ua1 and Ub1 are
 // both ct_in.c1 times a kernel plaintext, so z = ct_in.c1 * (ptk'[a] - X^step ptk'[b]): one product with a table the plan
 // prepared per butterfly, no U halves to read (or to have been written), no z to store (k_defB5<true> does not need it)
-__global__ void __launch_bounds__(HEC_THREADS, HEC_MINB) k_defB1f(ConvB P, const ModC *__restrict__ mods) {
+__global__ void __launch_bounds__(HEC_THREADS, HEC_B1_MINB) k_defB1f(ConvB P, const ModC *__restrict__ mods) {
     __shared__ u64 sm[16 * HEC_ROW_PITCH];
     const ModC M = mods[P.mq0];
     RowGeom G(HEC_BTILE);

@@ -23,7 +23,7 @@
 // mid: where the first pass leaves its result (null: out) -- needed when ep_b aliases out
 //   scatter_g != 0: the result is written through the automorphism, out[index_g^-1[i]] = x[i] with scatter_g = g^-1 mod 2N
 //                   (PermuteNTTWithIndexLvl as scattered stores of the last pass instead of a gather pass of its own)
-//   HEC_LJ_PRO2: x = in mod q + ((pro_b mod q) + pro_s0) * pro_s1 * R^-1 -- a second coefficient-domain operand, scaled
+//   HEC_LJ_PRO2: x = in + ((pro_b mod q) + pro_s0) * pro_s1 * R^-1 (in canonical) -- a second coefficient-domain operand, scaled
 //                (the rescale's centred remainder times P, folded into the mod-down's transform: hec_mul_relin_rescale_many)
 //   HEC_LJ_ADDS: like ADD with the addend scaled: x += ep_add * ep_s1 * R^-1
 struct LimbJob { const u64 *in; u64 *out; int mod; int flags; u64 *mid; const u64 *ep_b; u64 ep_s0; u64 pro_s0; const u64 *ep_add; u32 scatter_g;
@@ -34,8 +34,9 @@ struct LimbJob { const u64 *in; u64 *out; int mod; int flags; u64 *mid; const u6
 #define HEC_LJ_PRO2 8
 #define HEC_LJ_ADDS 16
 __device__ __forceinline__ u64 lj_pro2(const LimbJob &job, u32 n, const ModC &M) {
+    // `in` is canonical already (the basis extension's output); pro_b is a residue of ANOTHER modulus
     const u64 r = mred(addmod(canon(job.pro_b[n], M), job.pro_s0, M.q), job.pro_s1, M.q, M.qinv);
-    return addmod(canon(job.in[n], M), r, M.q);
+    return addmod(job.in[n], r, M.q);
 }
 // programmatic dependent launch: let the next kernel of the stream be scheduled while this grid drains, and do not touch
 // memory before the previous grid has completed (both are no-ops for a kernel launched without the attribute)

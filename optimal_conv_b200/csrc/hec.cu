@@ -276,8 +276,6 @@ static EwJob ewjob(const u64 *a, const u64 *b, u64 *out, int mod, u64 s0 = 0, u3
 
 // device copy of a small host table, cached by content (hec_ctx::staged).  The tables hold buffer addresses, which
 // repeat as long as the caller repeats the operation on the same ciphertexts / scratch layout.
-#define HEC_STAGE_CAP ((size_t)1 << 30) // size of the ring of slabs (a network layer chain stages thousands of distinct tables per image)
-#define HEC_STAGE_SLAB ((size_t)16 << 20)
 static int stage_cached(hec_ctx *c, std::vector<char> &h, char **dev) {
     h.resize((h.size() + 7) & ~(size_t)7, 0);
     uint64_t k = 1469598103934665603ull;
@@ -289,12 +287,12 @@ static int stage_cached(hec_ctx *c, std::vector<char> &h, char **dev) {
             if (e.host.size() == h.size() && memcmp(e.host.data(), h.data(), h.size()) == 0) { *dev = e.dev; return HEC_OK; }
     const size_t need = (h.size() + 255) & ~(size_t)255;
     hec_ctx::StagedTab e;
-    const size_t ring = HEC_STAGE_CAP / HEC_STAGE_SLAB;
-    if (need > HEC_STAGE_SLAB) { // an unusually large table gets a block of its own (freed when the ring wraps)
+    const size_t ring = c->stage_ring, SLAB = c->stage_slab_bytes;
+    if (need > SLAB) { // an unusually large table gets a block of its own (freed when the ring wraps)
         HEC_CUDA(c, cudaMalloc(&e.dev, need));
         c->stage_big.push_back(e.dev);
     } else {
-        if (!c->stage_cur || c->stage_slab_top + need > HEC_STAGE_SLAB) {
+        if (!c->stage_cur || c->stage_slab_top + need > SLAB) {
             if (c->stage_cur) {
                 HEC_CUDA(c, cudaEventRecord(c->stage_events[c->stage_idx], c->stream)); // every launch that reads this slab is in the stream by now
                 c->stage_idx = (c->stage_idx + 1) % ring;
@@ -302,14 +300,14 @@ static int stage_cached(hec_ctx *c, std::vector<char> &h, char **dev) {
             if (c->stage_idx == c->stage_slabs.size()) { // the ring is still growing
                 char *slab = nullptr;
                 cudaEvent_t ev = nullptr;
-                HEC_CUDA(c, cudaMalloc(&slab, HEC_STAGE_SLAB));
+                HEC_CUDA(c, cudaMalloc(&slab, SLAB));
                 HEC_CUDA(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
                 c->stage_slabs.push_back(slab);
                 c->stage_events.push_back(ev);
                 c->stage_keys.emplace_back();
             } else {                                     // come round: retire what this slab held
                 HEC_CUDA(c, cudaEventSynchronize(c->stage_events[c->stage_idx]));
-                char *lo = c->stage_slabs[c->stage_idx], *hi = lo + HEC_STAGE_SLAB;
+                char *lo = c->stage_slabs[c->stage_idx], *hi = lo + SLAB;
                 for (uint64_t key : c->stage_keys[c->stage_idx]) {
                     auto f = c->staged.find(key);
                     if (f == c->staged.end()) continue;
@@ -431,6 +429,9 @@ extern "C" int hec_ctx_create(hec_ctx **out, int logN, const uint64_t *Q, int nQ
     }
     auto bail = [&](int code) { hec_ctx_destroy(c); return code; };
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(HEC_E_CUDA);
+    // test hooks: a tiny ring makes the job-table cache wrap (and overflow into blocks of their own) within a few operations
+    if (getenv("HEC_STAGE_SLAB_KB")) c->stage_slab_bytes = std::max<size_t>(4, (size_t)atol(getenv("HEC_STAGE_SLAB_KB"))) << 10;
+    if (getenv("HEC_STAGE_RING")) c->stage_ring = std::max<size_t>(2, (size_t)atol(getenv("HEC_STAGE_RING")));
     {   // a pool of the context's own for the stream-ordered allocations (ciphertexts, plaintexts): freed buffers stay
         // cached in it instead of going back to the driver, and nothing of that outlives the context or touches the
         // device's default pool, which the host process may share

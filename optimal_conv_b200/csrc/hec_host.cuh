@@ -108,6 +108,8 @@ struct hec_ctx {
     std::vector<std::vector<uint64_t>> stage_keys;   // hash keys of the tables living in each slab
     std::vector<char *> stage_big;                   // tables larger than a slab: blocks of their own, freed when the ring wraps
     size_t stage_idx = 0;                            // slab being filled
+    size_t stage_slab_bytes = (size_t)16 << 20;      // slab size and number of slabs in the ring: 1 GiB in all (a network
+    size_t stage_ring = 64;                          // layer chain stages thousands of distinct tables per image)
     char *stage_cur = nullptr;
     size_t stage_slab_top = 0;
     uint64_t launches = 0;

@@ -197,6 +197,37 @@ def test_keyswitch_and_rotations_alpha1(ctx, orc, level):
     assert e.value.code == hec.HEC_E_NOKEY
 
 
+def test_job_table_cache_wraps_without_changing_results(orc, monkeypatch):
+    """The generic kernels read their job tables from a content-addressed ring of slabs on the device.  With a ring of
+    three 8 KiB slabs every operation overflows it: tables larger than a slab take blocks of their own, the ring comes
+    round every few launches and retires what it held.  Rotations and a ct x ct product on ever new buffers must keep
+    giving the oracle's result."""
+    monkeypatch.setenv("HEC_STAGE_SLAB_KB", "8")
+    monkeypatch.setenv("HEC_STAGE_RING", "3")
+    c = hec.Context(PR.LOGN, Q2, P1)
+    monkeypatch.delenv("HEC_STAGE_SLAB_KB")
+    monkeypatch.delenv("HEC_STAGE_RING")
+    try:
+        w = common.workload(common.GOLDEN_CONFIGS[1])
+        g = (1 << 13) + 1
+        c.upload_swk(g, w["keys"][12], 1)
+        c0, c1 = w["ct"][0][0], w["ct"][0][1]
+        want = orc.rotate_gal(Ct(c0, c1, PR.SCALE), g, w["keys"][12])
+        held = []
+        for i in range(24):
+            A = c.upload_ct(c0, c1, PR.SCALE)           # a new buffer every time: its tables are new to the cache
+            out = c.CopyNew(A)
+            c.RotateGal(A, g, out)
+            g0, g1 = out.download()
+            assert np.array_equal(g0, want.c0) and np.array_equal(g1, want.c1), i
+            held.append(A if i % 3 else out)            # keep some buffers alive so that addresses do not simply recur
+            (out if i % 3 else A).free()
+        for h in held:
+            h.free()
+    finally:
+        c.close()
+
+
 def test_general_decomposition_alpha2_and_hoisted_rotations():
     """Baseline shape (main.go:416-430): level 1, two special primes -> one 2-limb digit through
     the float-assisted exact basis extension; RotateHoisted == per-rotation RotateNew."""
